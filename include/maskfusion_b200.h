@@ -1,0 +1,126 @@
+/*
+ * include/maskfusion_b200.h -- C ABI of the B200-native MaskFusion dense pipeline.
+ *
+ * The reference has no FFI: its hot path sits behind C++ methods of libmaskfusion.so
+ * that take Eigen / OpenCV / OpenGL types.  This header is
+ * the flat, toolchain-neutral boundary a maintainer binds instead; each entry point
+ * names the reference method it replaces.  Plain pointers and sizes only: no torch,
+ * Eigen, OpenCV or GL types.  All functions return 0 on success, non-zero on error
+ * (text via mf_last_error()); nothing calls exit() (the reference does on CUDA
+ * errors, Core/Cuda/convenience.cuh:76-83).
+ *
+ * Conventions
+ *   rgb    : H x W x 3 uint8, as FrameData::rgb (CV_8UC3)      Core/FrameData.h:37
+ *   depth  : H x W float32 metres, as FrameData::depth (CV_32FC1) Core/FrameData.h:38
+ *   mask   : H x W uint8 (optional external segmentation)      Core/FrameData.h:36
+ *   poses  : float[16] COLUMN-major == Eigen::Matrix4f storage (Core/Model/Model.h:263-264)
+ *   surfels: 12 floats each, position.xyz conf | colour unused initTime lastTime |
+ *            normal.xyz radius                                 Core/Model/Model.h:190-192
+ *   "tex4" : H x W x 4 float32, the layout of the reference's RGBA32F GL textures
+ *   planar maps: 3*H x W float32 (x plane, y plane, z plane)   Core/Cuda/cudafuncs.cu:124-126
+ */
+#ifndef MASKFUSION_B200_H
+#define MASKFUSION_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MF_ABI_VERSION 1
+
+/* Effective parameters of one run: the reference spreads these over MaskFusion's
+ * 23-argument constructor (Core/MaskFusion.h:47-53), ~60 setters and the GUI
+ * defaults pushed every frame (GUI/MainController.cpp:528-571, GUI/Tools/GUI.h). */
+typedef struct mf_config {
+    int32_t width, height;                 /* Resolution::setResolution, MainController.cpp:117 */
+    float fx, fy, cx, cy;                  /* Intrinsics::setIntrinics,  MainController.cpp:124-126 */
+    float depthCutoff;                     /* GUI.h:194 = 4.0 */
+    float maxDepthProcessed;               /* MaskFusion.cpp:57 = 20.0 */
+    float icpWeight;                       /* GUI.h:195 = 20.0 (100 => ICP only, RGBDOdometry.cpp:236-237) */
+    int32_t rgbOnly, pyramid, fastOdom, so3, frameToFrameRGB;
+    float confGlobal, confObject;          /* MainController.cpp:215-216 = 10, 0.01 */
+    int32_t timeDelta;                     /* MainController.cpp:399 = INT_MAX/2 (open loop) */
+    float outlierCoeff;                    /* GUI.h:196 = 0.1 */
+    int32_t capacityGlobal, capacityObject;/* Core/CMakeLists.txt:27-28 (runtime here, not compile time) */
+    int32_t enableMultipleModels;          /* 0 == "-static" */
+    int32_t trackAllModels;                /* GUI.h:344 */
+    int32_t modelSpawnOffset;              /* GUI.h:347 = 22 */
+    float minRelSizeNew, maxRelSizeNew;    /* GUI.h:345-346 */
+    float segThreshold, segWeightDistance, segWeightConvexity;           /* GUI.h:367-374 */
+    int32_t segMorphEdgeIterations, segMorphEdgeRadius, segMorphMaskIterations, segMorphMaskRadius;
+} mf_config;
+
+typedef struct mf_context mf_context;
+
+const char* mf_last_error(void);
+int mf_abi_version(void);
+void mf_config_defaults(mf_config* cfg, int width, int height);
+
+/* MaskFusion::MaskFusion (Core/MaskFusion.h:47-53).  device = CUDA ordinal
+ * (reference: MASKFUSION_GPU_SLAM, MaskFusion.cpp:89-90); stream = cudaStream_t the
+ * whole pipeline is enqueued on (NULL = a private non-blocking stream). */
+mf_context* mf_create(const mf_config* cfg, int device, void* stream);
+void mf_destroy(mf_context* ctx);
+
+/* bool MaskFusion::processFrame(FrameDataPointer, const Eigen::Matrix4f* inPose,
+ *      float weightMultiplier, bool bootstrap)                 Core/MaskFusion.h:69-70
+ * Host buffers; the H2D copies are part of the call. mask / in_pose may be NULL. */
+int mf_process_frame(mf_context* ctx, const uint8_t* rgb, const float* depth, int64_t timestamp,
+                     const uint8_t* mask, const float* in_pose, float weight_multiplier, int bootstrap);
+/* Same, inputs already resident in device memory (rgb: packed 3 bytes/pixel). */
+int mf_process_frame_device(mf_context* ctx, const void* d_rgb, const void* d_depth, int64_t timestamp,
+                            const void* d_mask, const float* in_pose, float weight_multiplier, int bootstrap);
+int mf_sync(mf_context* ctx);                       /* wait for everything enqueued so far */
+int mf_tick(mf_context* ctx);                       /* MaskFusion::getTick */
+int64_t mf_kernel_launches(mf_context* ctx);        /* kernels launched since creation */
+
+/* ---- model list (MaskFusion::getModels) ---- */
+int mf_model_count(mf_context* ctx);
+int mf_model_id(mf_context* ctx, int i);
+int mf_get_pose(mf_context* ctx, int i, float pose16[16]);          /* Model::getPose */
+int mf_set_pose(mf_context* ctx, int i, const float pose16[16]);    /* Model::overridePose */
+int mf_model_surfel_count(mf_context* ctx, int i);                  /* Model::lastCount */
+int mf_model_set_conf_threshold(mf_context* ctx, int i, float t);   /* Model::setConfidenceThreshold */
+int mf_download_surfels(mf_context* ctx, int i, float* out, int max_surfels);   /* Model::downloadMap, Model.cpp:944-974 */
+int mf_upload_surfels(mf_context* ctx, int i, const float* in, int n);          /* test / bootstrap hook */
+int mf_pose_log_size(mf_context* ctx, int i);                                   /* Model::getPoseLog */
+int mf_get_pose_log(mf_context* ctx, int i, double* out8, int max_entries);     /* ts x y z qx qy qz qw, MaskFusion.cpp:850-879 */
+
+/* ---- per-stage entry points (same names / order as Core/Model/Model.h:128-164) ---- */
+int mf_set_frame(mf_context* ctx, const uint8_t* rgb, const float* depth, const uint8_t* mask);   /* upload + filterDepth + Model::generateCUDATextures */
+int mf_model_perform_tracking(mf_context* ctx, int i, float transform16[16]);                      /* Model::performTracking */
+int mf_model_predict_indices(mf_context* ctx, int i, int time);                                    /* Model::predictIndices */
+int mf_model_fuse(mf_context* ctx, int i, int time, float depth_cutoff, float weight_multiplier);  /* Model::fuse */
+int mf_model_clean(mf_context* ctx, int i, int time);                                              /* Model::clean */
+int mf_model_combined_predict(mf_context* ctx, int i, int time, int max_time);                     /* Model::combinedPredict + performFillIn */
+int mf_model_init_from_frame(mf_context* ctx, int i, int time);                                    /* computeFeedbackBuffers + Model::initialise */
+
+/* ---- read-back of intermediate products, in the reference's layouts ---- */
+int mf_download_filtered_depth(mf_context* ctx, float* out);                                       /* textureDepthMetricFiltered */
+int mf_download_frame_maps(mf_context* ctx, int level, float* depth, float* vmap_planar, float* nmap_planar);  /* GPUSetup::{depth,vertex_map,normal_map}_tmp */
+int mf_download_model_maps(mf_context* ctx, int i, int level, float* vmap_planar, float* nmap_planar);          /* RGBDOdometry::vmaps_g_prev_/nmaps_g_prev_ */
+int mf_download_index_map(mf_context* ctx, int i, uint32_t* idx, float* vert_conf4, float* color_time4, float* norm_rad4); /* ModelProjection sparse* textures */
+int mf_download_prediction(mf_context* ctx, int i, uint8_t* image4, float* vertex_conf4, float* normal_rad4, uint16_t* time); /* splat textures */
+int mf_download_fill_in(mf_context* ctx, int i, uint8_t* image4, float* vertex4, float* normal4);  /* FillIn textures */
+int mf_download_association(mf_context* ctx, int i, uint8_t* update_id, uint32_t* best, float* meas12); /* x-major pixel order, Model.cpp:179-183 */
+int mf_download_track_stats(mf_context* ctx, int i, double* A36, double* b6, float* err_count6);   /* RGBDOdometry::lastA/lastb, lastICPError,... */
+int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binary);                           /* MfSegmentation floatEdgeMap / binary edge map */
+
+/* ---- stand-alone kernels exposed for parity tests (device work, host buffers) ---- */
+int mf_debug_set_poses(mf_context* ctx, int i, const float pose16[16], const float last_pose16[16]);   /* sets Model::pose and Model::lastPose verbatim */
+int mf_icp_step(mf_context* ctx, int i, int level, const float Rcurr9[9], const float tcurr3[3], float out29[29]);  /* icpStep, reduce.cu:446-525 */
+
+/* ---- .klg log reader / writer (GUI/Tools/KlgLogReader.cpp:29-113) ---- */
+typedef struct mf_klg mf_klg;
+mf_klg* mf_klg_open(const char* path, int width, int height, int flip_colors);
+int mf_klg_num_frames(mf_klg* k);
+int mf_klg_has_more(mf_klg* k);                                         /* KlgLogReader::hasMore (N11: last frame never read) */
+int mf_klg_get_next(mf_klg* k, uint8_t* rgb, float* depth, int64_t* timestamp);   /* KlgLogReader::getNext + readFrame */
+void mf_klg_close(mf_klg* k);
+int mf_klg_write(const char* path, int width, int height, int num_frames, const int64_t* timestamps,
+                 const uint16_t* depth_mm, const uint8_t* rgb);          /* raw (uncompressed) log */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,354 @@
+"""Python host-side mirror of the reference interface over the C ABI
+(include/maskfusion_b200.h).  Names follow the reference: MaskFusion.processFrame,
+Model.performTracking / predictIndices / fuse / clean / combinedPredict
+(Core/MaskFusion.h:69-70, Core/Model/Model.h:128-164).
+
+There is NO CPU fallback: if libmaskfusion_b200.so is missing or no CUDA device is
+present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmaskfusion_b200.so")
+_LIB = None
+
+
+class MFError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    """mf_config (include/maskfusion_b200.h)"""
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+        ("depthCutoff", C.c_float), ("maxDepthProcessed", C.c_float), ("icpWeight", C.c_float),
+        ("rgbOnly", C.c_int32), ("pyramid", C.c_int32), ("fastOdom", C.c_int32), ("so3", C.c_int32),
+        ("frameToFrameRGB", C.c_int32),
+        ("confGlobal", C.c_float), ("confObject", C.c_float),
+        ("timeDelta", C.c_int32), ("outlierCoeff", C.c_float),
+        ("capacityGlobal", C.c_int32), ("capacityObject", C.c_int32),
+        ("enableMultipleModels", C.c_int32), ("trackAllModels", C.c_int32), ("modelSpawnOffset", C.c_int32),
+        ("minRelSizeNew", C.c_float), ("maxRelSizeNew", C.c_float),
+        ("segThreshold", C.c_float), ("segWeightDistance", C.c_float), ("segWeightConvexity", C.c_float),
+        ("segMorphEdgeIterations", C.c_int32), ("segMorphEdgeRadius", C.c_int32),
+        ("segMorphMaskIterations", C.c_int32), ("segMorphMaskRadius", C.c_int32),
+    ]
+
+
+EXPORTS = [
+    "mf_last_error", "mf_abi_version", "mf_config_defaults", "mf_create", "mf_destroy", "mf_process_frame",
+    "mf_process_frame_device", "mf_sync", "mf_tick", "mf_kernel_launches", "mf_model_count", "mf_model_id", "mf_get_pose",
+    "mf_set_pose", "mf_model_surfel_count", "mf_model_set_conf_threshold", "mf_download_surfels", "mf_upload_surfels",
+    "mf_pose_log_size", "mf_get_pose_log", "mf_set_frame", "mf_model_perform_tracking", "mf_model_predict_indices",
+    "mf_model_fuse", "mf_model_clean", "mf_model_combined_predict", "mf_model_init_from_frame",
+    "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
+    "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
+    "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
+    "mf_klg_close", "mf_klg_write",
+]
+
+
+def load_library():
+    """dlopen the in-tree CUDA library; loud failure if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise MFError(f"{LIB_PATH} not found: run `python -m maskfusion_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.mf_last_error.restype = C.c_char_p
+    L.mf_create.restype = C.c_void_p
+    L.mf_create.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p]
+    L.mf_destroy.argtypes = [C.c_void_p]
+    L.mf_config_defaults.argtypes = [C.POINTER(Config), C.c_int, C.c_int]
+    L.mf_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+    L.mf_process_frame_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+    L.mf_kernel_launches.restype = C.c_int64
+    for name in ("mf_sync", "mf_tick", "mf_kernel_launches", "mf_model_count"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    for name in ("mf_model_id", "mf_model_surfel_count", "mf_pose_log_size"):
+        getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+    L.mf_get_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mf_set_pose.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mf_model_set_conf_threshold.argtypes = [C.c_void_p, C.c_int, C.c_float]
+    L.mf_download_surfels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.mf_upload_surfels.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.mf_get_pose_log.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.mf_set_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_model_perform_tracking.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mf_model_predict_indices.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.mf_model_fuse.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float]
+    L.mf_model_clean.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.mf_model_combined_predict.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    L.mf_model_init_from_frame.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.mf_download_filtered_depth.argtypes = [C.c_void_p, C.c_void_p]
+    L.mf_download_frame_maps.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_download_model_maps.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.mf_download_index_map.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.mf_download_prediction.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4
+    L.mf_download_fill_in.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
+    L.mf_download_association.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
+    L.mf_download_track_stats.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
+    L.mf_download_edge_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_debug_set_poses.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.mf_icp_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_klg_open.restype = C.c_void_p
+    L.mf_klg_open.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
+    for name in ("mf_klg_num_frames", "mf_klg_has_more", "mf_klg_close"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.mf_klg_close.restype = None
+    L.mf_klg_get_next.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_klg_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    _LIB = L
+    return L
+
+
+def default_config(width=640, height=480, **kw) -> Config:
+    c = Config()
+    load_library().mf_config_defaults(C.byref(c), width, height)
+    for k, v in kw.items():
+        if not hasattr(c, k):
+            raise AttributeError(k)
+        setattr(c, k, v)
+    return c
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Model:
+    """Handle on one surfel model (reference: class Model, Core/Model/Model.h)."""
+
+    def __init__(self, mf: "MaskFusion", index: int):
+        self.mf, self.i = mf, index
+
+    def _ck(self, r):
+        return self.mf._ck(r)
+
+    def getPose(self) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        self._ck(self.mf.L.mf_get_pose(self.mf.h, self.i, _p(out)))
+        return out.reshape(4, 4).T.copy()          # column-major ABI -> numpy row-major
+
+    def overridePose(self, T: np.ndarray):
+        a = np.ascontiguousarray(np.asarray(T, np.float32).T).ravel()
+        self._ck(self.mf.L.mf_set_pose(self.mf.h, self.i, _p(a)))
+
+    def debugSetPoses(self, pose: np.ndarray, lastPose: np.ndarray):
+        a = np.ascontiguousarray(np.asarray(pose, np.float32).T).ravel()
+        b = np.ascontiguousarray(np.asarray(lastPose, np.float32).T).ravel()
+        self._ck(self.mf.L.mf_debug_set_poses(self.mf.h, self.i, _p(a), _p(b)))
+
+    def lastCount(self) -> int:
+        return self._ck(self.mf.L.mf_model_surfel_count(self.mf.h, self.i))
+
+    def setConfidenceThreshold(self, t: float):
+        self._ck(self.mf.L.mf_model_set_conf_threshold(self.mf.h, self.i, float(t)))
+
+    def downloadMap(self) -> np.ndarray:
+        n = self.lastCount()
+        out = np.zeros((max(n, 1), 12), np.float32)
+        got = self._ck(self.mf.L.mf_download_surfels(self.mf.h, self.i, _p(out), n))
+        return out[:got]
+
+    def uploadMap(self, surfels: np.ndarray):
+        s = np.ascontiguousarray(surfels, np.float32)
+        self._ck(self.mf.L.mf_upload_surfels(self.mf.h, self.i, _p(s), s.shape[0]))
+
+    def initialise(self, time: int):
+        self._ck(self.mf.L.mf_model_init_from_frame(self.mf.h, self.i, time))
+
+    def performTracking(self) -> np.ndarray:
+        out = np.zeros(16, np.float32)
+        self._ck(self.mf.L.mf_model_perform_tracking(self.mf.h, self.i, _p(out)))
+        return out.reshape(4, 4).T.copy()
+
+    def predictIndices(self, time: int):
+        self._ck(self.mf.L.mf_model_predict_indices(self.mf.h, self.i, time))
+
+    def fuse(self, time: int, depthCutoff: float, weightMultiplier: float = 1.0):
+        self._ck(self.mf.L.mf_model_fuse(self.mf.h, self.i, time, depthCutoff, weightMultiplier))
+
+    def clean(self, time: int):
+        self._ck(self.mf.L.mf_model_clean(self.mf.h, self.i, time))
+
+    def combinedPredict(self, time: int, maxTime: int):
+        self._ck(self.mf.L.mf_model_combined_predict(self.mf.h, self.i, time, maxTime))
+
+    # ---- read-back (reference layouts) ----
+    def indexMap(self):
+        H, W = self.mf.H, self.mf.W
+        idx = np.zeros((H, W), np.uint32); vc = np.zeros((H, W, 4), np.float32)
+        ct = np.zeros((H, W, 4), np.float32); nr = np.zeros((H, W, 4), np.float32)
+        self._ck(self.mf.L.mf_download_index_map(self.mf.h, self.i, _p(idx), _p(vc), _p(ct), _p(nr)))
+        return idx, vc, ct, nr
+
+    def prediction(self):
+        H, W = self.mf.H, self.mf.W
+        im = np.zeros((H, W, 4), np.uint8); vc = np.zeros((H, W, 4), np.float32)
+        nr = np.zeros((H, W, 4), np.float32); tt = np.zeros((H, W), np.uint16)
+        self._ck(self.mf.L.mf_download_prediction(self.mf.h, self.i, _p(im), _p(vc), _p(nr), _p(tt)))
+        return im, vc, nr, tt
+
+    def fillIn(self):
+        H, W = self.mf.H, self.mf.W
+        im = np.zeros((H, W, 4), np.uint8); v = np.zeros((H, W, 4), np.float32); n = np.zeros((H, W, 4), np.float32)
+        self._ck(self.mf.L.mf_download_fill_in(self.mf.h, self.i, _p(im), _p(v), _p(n)))
+        return im, v, n
+
+    def association(self):
+        H, W = self.mf.H, self.mf.W
+        flag = np.zeros((W, H), np.uint8); best = np.zeros((W, H), np.uint32); meas = np.zeros((W, H, 12), np.float32)
+        self._ck(self.mf.L.mf_download_association(self.mf.h, self.i, _p(flag), _p(best), _p(meas)))
+        return flag, best, meas
+
+    def modelMaps(self, level: int):
+        H, W = self.mf.H >> level, self.mf.W >> level
+        v = np.zeros((3, H, W), np.float32); n = np.zeros((3, H, W), np.float32)
+        self._ck(self.mf.L.mf_download_model_maps(self.mf.h, self.i, level, _p(v), _p(n)))
+        return v, n
+
+    def trackStats(self):
+        A = np.zeros((6, 6)); b = np.zeros(6); e = np.zeros(6, np.float32)
+        self._ck(self.mf.L.mf_download_track_stats(self.mf.h, self.i, _p(A), _p(b), _p(e)))
+        return A, b, e
+
+    def icpStep(self, level: int, Rcurr: np.ndarray, tcurr: np.ndarray) -> np.ndarray:
+        out = np.zeros(29, np.float32)
+        R = np.ascontiguousarray(Rcurr, np.float32).ravel(); t = np.ascontiguousarray(tcurr, np.float32).ravel()
+        self._ck(self.mf.L.mf_icp_step(self.mf.h, self.i, level, _p(R), _p(t), _p(out)))
+        return out
+
+    def poseLog(self) -> np.ndarray:
+        n = self._ck(self.mf.L.mf_pose_log_size(self.mf.h, self.i))
+        out = np.zeros((max(n, 1), 8))
+        got = self._ck(self.mf.L.mf_get_pose_log(self.mf.h, self.i, _p(out), n))
+        return out[:got]
+
+
+class MaskFusion:
+    """reference: class MaskFusion (Core/MaskFusion.h).  `stream` is a raw cudaStream_t
+    (int); pass torch.cuda.current_stream().cuda_stream to time with torch events."""
+
+    def __init__(self, cfg: Config | None = None, device: int = 0, stream: int | None = None, **kw):
+        self.L = load_library()
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self.W, self.H = self.cfg.width, self.cfg.height
+        self.h = self.L.mf_create(C.byref(self.cfg), device, C.c_void_p(stream) if stream else None)
+        if not self.h:
+            raise MFError(self.L.mf_last_error().decode())
+
+    def _ck(self, r):
+        if r < 0:
+            raise MFError(self.L.mf_last_error().decode())
+        return r
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mf_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def processFrame(self, rgb: np.ndarray, depth: np.ndarray, timestamp: int = 0, mask=None, inPose=None,
+                     weightMultiplier: float = 1.0, bootstrap: bool = False):
+        """bool MaskFusion::processFrame(FrameDataPointer, const Eigen::Matrix4f*, float, bool)"""
+        if rgb.dtype != np.uint8 or rgb.shape != (self.H, self.W, 3):
+            raise MFError("rgb must be HxWx3 uint8 (CV_8UC3, MaskFusion.cpp:202)")
+        if depth.dtype != np.float32 or depth.shape != (self.H, self.W):
+            raise MFError("depth must be HxW float32 metres (CV_32FC1, MaskFusion.cpp:201)")
+        ip = None if inPose is None else np.ascontiguousarray(np.asarray(inPose, np.float32).T).ravel()
+        self._ck(self.L.mf_process_frame(self.h, _p(np.ascontiguousarray(rgb)), _p(np.ascontiguousarray(depth)), int(timestamp),
+                                         _p(mask), _p(ip), float(weightMultiplier), int(bootstrap)))
+        return False
+
+    def processFramePtr(self, rgb_ptr: int, depth_ptr: int, timestamp: int = 0, on_device: bool = False):
+        """raw-pointer variant (pinned host or device memory), used by bench.py"""
+        fn = self.L.mf_process_frame_device if on_device else self.L.mf_process_frame
+        self._ck(fn(self.h, C.c_void_p(rgb_ptr), C.c_void_p(depth_ptr), int(timestamp), None, None, 1.0, 0))
+
+    def setFrame(self, rgb, depth, mask=None):
+        self._ck(self.L.mf_set_frame(self.h, _p(np.ascontiguousarray(rgb)), _p(np.ascontiguousarray(depth)), _p(mask)))
+
+    def sync(self):
+        self._ck(self.L.mf_sync(self.h))
+
+    def getTick(self) -> int:
+        return self.L.mf_tick(self.h)
+
+    def kernelLaunches(self) -> int:
+        return int(self.L.mf_kernel_launches(self.h))
+
+    def getModels(self):
+        return [Model(self, i) for i in range(self.L.mf_model_count(self.h))]
+
+    def getBackgroundModel(self) -> Model:
+        return Model(self, 0)
+
+    def filteredDepth(self):
+        out = np.zeros((self.H, self.W), np.float32)
+        self._ck(self.L.mf_download_filtered_depth(self.h, _p(out)))
+        return out
+
+    def frameMaps(self, level: int):
+        H, W = self.H >> level, self.W >> level
+        d = np.zeros((H, W), np.float32); v = np.zeros((3, H, W), np.float32); n = np.zeros((3, H, W), np.float32)
+        self._ck(self.L.mf_download_frame_maps(self.h, level, _p(d), _p(v), _p(n)))
+        return d, v, n
+
+    def edgeMap(self):
+        e = np.zeros((self.H, self.W), np.float32); b = np.zeros((self.H, self.W), np.uint8)
+        self._ck(self.L.mf_download_edge_map(self.h, _p(e), _p(b)))
+        return e, b
+
+
+class KlgLogReader:
+    """reference: class KlgLogReader (GUI/Tools/KlgLogReader.{h,cpp})"""
+
+    def __init__(self, path: str, width: int, height: int, flipColors: bool = False):
+        self.L = load_library()
+        self.W, self.H = width, height
+        self.k = self.L.mf_klg_open(path.encode(), width, height, int(flipColors))
+        if not self.k:
+            raise MFError(self.L.mf_last_error().decode())
+
+    def getNumFrames(self):
+        return self.L.mf_klg_num_frames(self.k)
+
+    def hasMore(self):
+        return bool(self.L.mf_klg_has_more(self.k))
+
+    def getNext(self):
+        rgb = np.zeros((self.H, self.W, 3), np.uint8); depth = np.zeros((self.H, self.W), np.float32)
+        ts = C.c_int64(0)
+        if self.L.mf_klg_get_next(self.k, _p(rgb), _p(depth), C.byref(ts)) != 0:
+            raise MFError(self.L.mf_last_error().decode())
+        return rgb, depth, ts.value
+
+    def close(self):
+        if self.k:
+            self.L.mf_klg_close(self.k)
+            self.k = None
+
+
+def write_klg(path: str, timestamps, depth_mm: np.ndarray, rgb: np.ndarray):
+    """raw .klg (layout: KlgLogReader.cpp:29,53-89)"""
+    L = load_library()
+    n, H, W = depth_mm.shape
+    ts = np.ascontiguousarray(timestamps, np.int64)
+    d = np.ascontiguousarray(depth_mm, np.uint16); c = np.ascontiguousarray(rgb, np.uint8)
+    if L.mf_klg_write(path.encode(), W, H, n, _p(ts), _p(d), _p(c)) != 0:
+        raise MFError(L.mf_last_error().decode())

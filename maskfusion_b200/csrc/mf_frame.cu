@@ -1,0 +1,327 @@
+// mf_frame.cu -- per-frame preprocessing kernels (sm_100a):
+//   depth bilateral filter        <- Core/Shaders/depth_bilateral_metric.frag:30-76 (MaskFusion::filterDepth)
+//   depth / intensity pyramids    <- Core/Cuda/cudafuncs.cu:333-364, 534-564
+//   vertex + normal maps (fused)  <- Core/Cuda/cudafuncs.cu:109-189 (Model::generateCUDATextures, Model.cpp:350-389)
+//   intensity, Sobel, clouds      <- Core/Cuda/cudafuncs.cu:602-751
+//   model-map preparation (fused) <- RGBDOdometry::initICPModel, RGBDOdometry.cpp:153-185
+// Layout: maps are float4 per pixel (x,y,z,0), invalid == NaN in x (reference: planar
+// 3*rows x cols, NaN in the x plane); all loads are 16-byte, coalesced along rows.
+#include "mf_common.cuh"
+#include "mf_kernels.h"
+
+namespace mfb {
+
+__global__ void k_unpack_rgb(const uint8_t* __restrict__ rgb3, uchar4* __restrict__ out, int P)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    out[i] = make_uchar4(rgb3[i * 3], rgb3[i * 3 + 1], rgb3[i * 3 + 2], 255);
+}
+
+// 13x13 bilateral, one thread per pixel, (32+12)x(8+12) depth tile staged in shared memory.
+// Accumulation order (cy outer, cx inner, ascending) is part of the parity contract.
+#define BIL_R 6
+#define BIL_BX 32
+#define BIL_BY 8
+__global__ void __launch_bounds__(BIL_BX* BIL_BY) k_bilateral(const float* __restrict__ depth, float* __restrict__ out, int W, int H)
+{
+    __shared__ float tile[BIL_BY + 2 * BIL_R][BIL_BX + 2 * BIL_R + 1];
+    const int x0 = blockIdx.x * BIL_BX - BIL_R, y0 = blockIdx.y * BIL_BY - BIL_R;
+    for (int t = threadIdx.y * BIL_BX + threadIdx.x; t < (BIL_BY + 2 * BIL_R) * (BIL_BX + 2 * BIL_R); t += BIL_BX * BIL_BY) {
+        int ty = t / (BIL_BX + 2 * BIL_R), tx = t - ty * (BIL_BX + 2 * BIL_R);
+        int gx = x0 + tx, gy = y0 + ty;
+        tile[ty][tx] = (gx >= 0 && gx < W && gy >= 0 && gy < H) ? depth[gy * W + gx] : 0.0f;
+    }
+    __syncthreads();
+    const int x = blockIdx.x * BIL_BX + threadIdx.x, y = blockIdx.y * BIL_BY + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const float value = tile[threadIdx.y + BIL_R][threadIdx.x + BIL_R];
+    if (value <= 0.03f) { out[y * W + x] = 0.0f; return; }
+    const float sigma_space2_inv_half = 0.024691358f, sigma_color2_inv_half = 555.556f;
+    const int D = 2 * BIL_R + 1;
+    const int tx = min(x - D / 2 + D, W), ty = min(y - D / 2 + D, H);
+    float sum1 = 0.f, sum2 = 0.f;
+    for (int cy = max(y - D / 2, 0); cy < ty; ++cy) {
+        const float dy = (float)y - (float)cy;
+        const float* row = tile[cy - y0];
+        for (int cx = max(x - D / 2, 0); cx < tx; ++cx) {
+            float tmp = row[cx - x0];
+            float dx = (float)x - (float)cx;
+            float space2 = dx * dx + dy * dy;
+            float dc = value - tmp;
+            float color2 = dc * dc;
+            float weight = det_expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
+            sum1 += tmp * weight;
+            sum2 += weight;
+        }
+    }
+    out[y * W + x] = sum1 / sum2;
+}
+
+__constant__ float c_gauss5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
+
+// NaN-skipping 5x5 Gaussian decimation; window clamp excludes the last row/column and
+// the weight sum is an int, exactly as the reference (rule N9).
+__global__ void k_pyrdown_f(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    int dw = sw / 2, dh = sh / 2;
+    if (x >= dw || y >= dh) return;
+    const int D = 5;
+    int tx = min(2 * x - D / 2 + D, sw - 1), ty = min(2 * y - D / 2 + D, sh - 1);
+    float sum = 0; int count = 0;
+    for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
+        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+            float v = src[cy * sw + cx];
+            if (!isnan(v)) {
+                float g = c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
+                sum += v * g;
+                count = (int)((float)count + g);
+            }
+        }
+    dst[y * dw + x] = sum / (float)count;
+}
+
+__global__ void k_pyrdown_u8(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    int dw = sw / 2, dh = sh / 2;
+    if (x >= dw || y >= dh) return;
+    const int D = 5;
+    int tx = min(2 * x - D / 2 + D, sw - 1), ty = min(2 * y - D / 2 + D, sh - 1);
+    float sum = 0; int count = 0;
+    for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
+        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+            uint8_t v = src[cy * sw + cx];
+            if (v > 0) {
+                float g = c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
+                sum += (float)v * g;
+                count = (int)((float)count + g);
+            }
+        }
+    float r = sum / (float)count;
+    dst[y * dw + x] = (r != r) ? 0 : (uint8_t)(int)r;
+}
+
+// depth -> vertex map + forward-difference normal map in ONE pass (the three vertices a
+// normal needs are rebuilt from depth; saves the vmap round trip through HBM).
+__global__ void k_vmap_nmap(const float* __restrict__ depth, int W, int H, Cam cam, float cutoff,
+                            float4* __restrict__ vmap, float4* __restrict__ nmap)
+{
+    int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+    if (u >= W || v >= H) return;
+    const float fx_inv = 1.f / cam.fx, fy_inv = 1.f / cam.fy;
+    auto vert = [&](int uu, int vv, float3& o) -> bool {
+        float z = depth[vv * W + uu];
+        if (z > 0.0f && z < cutoff) {
+            o = make_float3(z * ((float)uu - cam.cx) * fx_inv, z * ((float)vv - cam.cy) * fy_inv, z);
+            return true;
+        }
+        return false;
+    };
+    float3 v00, v01, v10;
+    bool ok00 = vert(u, v, v00);
+    vmap[v * W + u] = ok00 ? make_float4(v00.x, v00.y, v00.z, 0.f) : make_float4(qnanf(), 0.f, 0.f, 0.f);
+    float4 n = make_float4(qnanf(), 0.f, 0.f, 0.f);
+    if (ok00 && u != W - 1 && v != H - 1 && vert(u + 1, v, v01) && vert(u, v + 1, v10)) {
+        float3 c = cross3(sub3(v01, v00), sub3(v10, v00));
+        float len = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+        n = make_float4(c.x / len, c.y / len, c.z / len, 0.f);
+    }
+    nmap[v * W + u] = n;
+}
+
+__global__ void k_intensity(const uchar4* __restrict__ img, int P, uint8_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uchar4 s = img[i];
+    float v = ((float)s.x * 0.114f + (float)s.y * 0.299f) + (float)s.z * 0.587f;   // cudafuncs.cu:634
+    out[i] = (uint8_t)(int)v;
+}
+
+// model-side intensity: source image picked on the device like k_model_maps (Model::initICP, Model.cpp:391-409)
+__global__ void k_intensity_select(const uchar4* __restrict__ imgPred, const uchar4* __restrict__ imgFill, const uint32_t* __restrict__ nonBlack,
+                                   float denom, int forceFill, int P, uint8_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const bool fill = forceFill || (nonBlack && ((float)(*nonBlack) / denom < 0.75f));
+    uchar4 s = fill ? imgFill[i] : imgPred[i];
+    float v = ((float)s.x * 0.114f + (float)s.y * 0.299f) + (float)s.z * 0.587f;
+    out[i] = (uint8_t)(int)v;
+}
+
+__constant__ float c_sobx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
+__constant__ float c_soby[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
+__global__ void k_sobel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float dxv = 0, dyv = 0; int k = 8;
+    for (int j = max(y - 1, 0); j <= min(y + 1, H - 1); ++j)
+        for (int i = max(x - 1, 0); i <= min(x + 1, W - 1); ++i) {
+            float s = (float)src[j * W + i];
+            dxv += s * c_sobx[k];
+            dyv += s * c_soby[k];
+            --k;
+        }
+    grad[y * W + x] = make_short2((short)(int)dxv, (short)(int)dyv);
+}
+
+// ---- model-map preparation ------------------------------------------------------------
+// One thread per level-1 pixel; the four threads of a level-2 pixel sit in adjacent lanes.
+// Each thread reads its 2x2 block of the predicted (or fill-in) RGBA32F maps and emits
+// level 0 (x4), level 1 and -- by quad shuffle -- level 2 of the transformed model maps,
+// plus the level-0 depth used by the photometric term (verticesToDepth).
+// Arithmetic order follows copyMaps -> resizeMap x2 -> tranformMaps of the reference.
+struct V3 { float x, y, z; bool ok; };
+MF_D float4 packv(float3 v, bool ok) { return ok ? make_float4(v.x, v.y, v.z, 0.f) : make_float4(qnanf(), qnanf(), qnanf(), 0.f); }
+
+__global__ void k_model_maps(const float4* __restrict__ srcV_pred, const float4* __restrict__ srcN_pred,
+                             const float4* __restrict__ srcV_fill, const float4* __restrict__ srcN_fill,
+                             const uint32_t* __restrict__ nonBlack, float denom, int W, int H, Rt pose, float maxDepthRGB,
+                             float4* __restrict__ v0, float4* __restrict__ n0, float4* __restrict__ v1, float4* __restrict__ n1,
+                             float4* __restrict__ v2, float4* __restrict__ n2, float* __restrict__ depth0)
+{
+    const int W1 = W / 2, H1 = H / 2, W2 = W / 4, H2 = H / 4;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int q = t >> 2, sub = t & 3;
+    bool active = q < W2 * H2;
+    int qx = active ? q % W2 : 0, qy = active ? q / W2 : 0;
+    int x1 = 2 * qx + (sub & 1), y1 = 2 * qy + (sub >> 1);
+    // MaskFusion::requiresFillIn (MaskFusion.cpp:630-648) evaluated on the device: no host round trip
+    const bool fill = nonBlack && ((float)(*nonBlack) / denom < 0.75f);
+    const float4* srcV = fill ? srcV_fill : srcV_pred;
+    const float4* srcN = fill ? srcN_fill : srcN_pred;
+    float3 sv = make_float3(0, 0, 0), sn = make_float3(0, 0, 0);
+    bool bad = false;
+    if (active) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int x = 2 * x1 + (k & 1), y = 2 * y1 + (k >> 1);
+            float4 a = srcV[y * W + x], b = srcN[y * W + x];
+            bool ok = !(a.z == 0.0f);
+            float3 vv = make_float3(a.x, a.y, a.z), nn = make_float3(b.x, b.y, b.z);
+            // level 0: copyMaps + tranformMaps (a NaN normal inside a valid vertex stays NaN)
+            bool nok = ok && !isnan(nn.x);
+            bool vok = ok && !isnan(vv.x);
+            v0[y * W + x] = packv(xform(pose, vv), vok);
+            n0[y * W + x] = packv(rotate(pose, nn), nok);
+            depth0[y * W + x] = (a.z > maxDepthRGB || a.z <= 0) ? qnanf() : a.z;      // cudafuncs.cu:602-613
+            bad = bad || !vok || !nok;
+            // ((a+b)+c)+d accumulation order of resizeMapKernel
+            sv = (k == 0) ? vv : add3(sv, vv);
+            sn = (k == 0) ? nn : add3(sn, nn);
+        }
+    }
+    // NOTE: vertex and normal validity coincide (both derive from vsrc.z != 0) except for NaN
+    // normals stored inside valid vertices; the reference tests each map's own x plane.
+    float3 a1v = make_float3(sv.x / 4, sv.y / 4, sv.z / 4);
+    float3 a1n = make_float3(sn.x / 4, sn.y / 4, sn.z / 4);
+    bool badV = bad, badN = bad;
+    if (active) {
+        // recompute exact per-map validity
+        badV = false; badN = false;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int x = 2 * x1 + (k & 1), y = 2 * y1 + (k >> 1);
+            float4 a = srcV[y * W + x], b = srcN[y * W + x];
+            bool ok = !(a.z == 0.0f);
+            badV = badV || !ok || isnan(a.x);
+            badN = badN || !ok || isnan(b.x);
+        }
+    }
+    float3 a1nn = normalize3(a1n);
+    if (active) {
+        v1[y1 * W1 + x1] = packv(xform(pose, a1v), !badV);
+        n1[y1 * W1 + x1] = packv(rotate(pose, a1nn), !badN);
+    }
+    // level 2: average of the four (untransformed) level-1 values held by the quad's lanes
+    const unsigned full = 0xffffffffu;
+    int base = (threadIdx.x & 31) & ~3;
+    float3 s2v, s2n; bool b2v = false, b2n = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float3 pv = make_float3(__shfl_sync(full, a1v.x, base + k), __shfl_sync(full, a1v.y, base + k), __shfl_sync(full, a1v.z, base + k));
+        float3 pn = make_float3(__shfl_sync(full, a1nn.x, base + k), __shfl_sync(full, a1nn.y, base + k), __shfl_sync(full, a1nn.z, base + k));
+        b2v = b2v || __shfl_sync(full, (int)badV, base + k);
+        b2n = b2n || __shfl_sync(full, (int)badN, base + k);
+        s2v = (k == 0) ? pv : add3(s2v, pv);
+        s2n = (k == 0) ? pn : add3(s2n, pn);
+    }
+    if (active && sub == 0) {
+        float3 a2v = make_float3(s2v.x / 4, s2v.y / 4, s2v.z / 4);
+        float3 a2n = normalize3(make_float3(s2n.x / 4, s2n.y / 4, s2n.z / 4));
+        v2[qy * W2 + qx] = packv(xform(pose, a2v), !b2v);
+        n2[qy * W2 + qx] = packv(rotate(pose, a2n), !b2n);
+    }
+}
+
+// float4 map -> reference planar layout (for read-back through the C ABI)
+__global__ void k_map_to_planar(const float4* __restrict__ m, int P, float* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    float4 v = m[i];
+    out[i] = v.x; out[P + i] = v.y; out[2 * P + i] = v.z;
+}
+
+__global__ void k_project_points(const float* __restrict__ depth, int W, int H, Cam cam, float4* __restrict__ cloud)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float z = depth[y * W + x];
+    float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
+    cloud[y * W + x] = make_float4(((float)x - cam.cx) * z * ifx, ((float)y - cam.cy) * z * ify, z, 0.f);   // cudafuncs.cu:718-736
+}
+
+// ------------------------------ host launchers ----------------------------------------
+static inline dim3 grid2(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
+
+void launch_unpack_rgb(const uint8_t* rgb3, uchar4* out, int P, cudaStream_t s) { k_unpack_rgb<<<(P + 255) / 256, 256, 0, s>>>(rgb3, out, P); }
+void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t s)
+{
+    dim3 b(BIL_BX, BIL_BY);
+    k_bilateral<<<grid2(W, H, b), b, 0, s>>>(depth, out, W, H);
+}
+void launch_pyrdown_f(const float* src, int sw, int sh, float* dst, cudaStream_t s)
+{
+    dim3 b(32, 8);
+    k_pyrdown_f<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
+}
+void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStream_t s)
+{
+    dim3 b(32, 8);
+    k_pyrdown_u8<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
+}
+void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s)
+{
+    dim3 b(32, 8);
+    k_vmap_nmap<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cutoff, vmap, nmap);
+}
+void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s) { k_intensity<<<(P + 255) / 256, 256, 0, s>>>(img, P, out); }
+void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s)
+{
+    k_intensity_select<<<(P + 255) / 256, 256, 0, s>>>(imgPred, imgFill, nonBlack, denom, forceFill, P, out);
+}
+void launch_sobel(const uint8_t* src, int W, int H, short2* grad, cudaStream_t s)
+{
+    dim3 b(32, 8);
+    k_sobel<<<grid2(W, H, b), b, 0, s>>>(src, W, H, grad);
+}
+void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
+                       int W, int H, Rt pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s)
+{
+    int threads = (W / 4) * (H / 4) * 4;
+    k_model_maps<<<(threads + 127) / 128, 128, 0, s>>>(srcVp, srcNp, srcVf, srcNf, nonBlack, denom, W, H, pose, maxDepthRGB,
+                                                       v[0], n[0], v[1], n[1], v[2], n[2], depth0);
+}
+void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s) { k_map_to_planar<<<(P + 255) / 256, 256, 0, s>>>(m, P, out); }
+void launch_project_points(const float* depth, int W, int H, Cam cam, float4* cloud, cudaStream_t s)
+{
+    dim3 b(32, 8);
+    k_project_points<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cloud);
+}
+
+}  // namespace mfb

@@ -1,0 +1,380 @@
+// mf_host.cu -- host orchestration of the dense pipeline: MaskFusion::processFrame schedule
+// (Core/MaskFusion.cpp:200-607) and the Model methods it drives (Core/Model/Model.cpp).
+// Everything is enqueued on one CUDA stream; the only host<->device synchronisation inside
+// a frame is the read-back of the tracked poses (one per frame, not one per Gauss-Newton
+// iteration as in the reference).
+#include "mf_host.h"
+#include <math.h>
+#include <float.h>
+#include <string.h>
+#include <stdio.h>
+#include <limits.h>
+
+namespace mfb {
+
+void cudaCheck(cudaError_t e, const char* where)
+{
+    if (e != cudaSuccess) throw CudaError{std::string(where) + ": " + cudaGetErrorString(e)};
+}
+
+Mat4 rigidInverse(const Mat4& T)
+{
+    // [R^T | -R^T t] in fp32 (reference: Eigen::Matrix4f::inverse(); rule fixed in DESIGN.md)
+    Mat4 o = Mat4::identity();
+    const float* m = T.m;
+    float R[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]}, t[3] = {m[3], m[7], m[11]};
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) o.m[r * 4 + c] = R[c * 3 + r];
+        o.m[r * 4 + 3] = -((R[0 * 3 + r] * t[0] + R[1 * 3 + r] * t[1]) + R[2 * 3 + r] * t[2]);
+    }
+    return o;
+}
+Mat4 mul(const Mat4& A, const Mat4& B)
+{
+    Mat4 o;
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            float s = 0;
+            for (int k = 0; k < 4; ++k) s += A.m[r * 4 + k] * B.m[k * 4 + c];
+            o.m[r * 4 + c] = s;
+        }
+    return o;
+}
+Rt toRt(const Mat4& T) { Rt r; for (int i = 0; i < 12; ++i) r.m[i] = T.m[i]; return r; }
+
+// Model::rodrigues2 (Model.cpp:890-932) without the SVD re-orthonormalisation
+static void rodrigues2(const float* R, float* out)
+{
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = ((double)(R[0] + R[4] + R[8]) - 1) * 0.5;
+    c = c > 1. ? 1. : c < -1. ? -1. : c;
+    double theta = acos(c);
+    if (s < 1e-5) {
+        double t;
+        if (c > 0) rx = ry = rz = 0;
+        else {
+            t = (R[0] + 1) * 0.5; rx = sqrt(t > 0 ? t : 0.0);
+            t = (R[4] + 1) * 0.5; ry = sqrt(t > 0 ? t : 0.0) * (R[1] < 0 ? -1.0 : 1.0);
+            t = (R[8] + 1) * 0.5; rz = sqrt(t > 0 ? t : 0.0) * (R[2] < 0 ? -1.0 : 1.0);
+            if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (R[5] > 0) != (ry * rz > 0)) rz = -rz;
+            theta /= sqrt(rx * rx + ry * ry + rz * rz);
+            rx *= theta; ry *= theta; rz *= theta;
+        }
+    } else {
+        double vth = 1 / (2 * s); vth *= theta; rx *= vth; ry *= vth; rz *= vth;
+    }
+    out[0] = (float)rx; out[1] = (float)ry; out[2] = (float)rz;
+}
+
+// Eigen::Quaternionf(Matrix3f) as used by the pose log (MaskFusion.cpp:585-590)
+static void rotToQuat(const float* R, float* q)
+{
+    float t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = sqrtf(t + 1.0f); q[3] = 0.5f * t; t = 0.5f / t;
+        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0; if (R[4] > R[0]) i = 1; if (R[8] > R[i * 4]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrtf(R[i * 4] - R[j * 4] - R[k * 4] + 1.0f);
+        q[i] = 0.5f * t; t = 0.5f / t;
+        q[3] = (R[k * 3 + j] - R[j * 3 + k]) * t;
+        q[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+        q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+    }
+}
+
+// ======================================================================================
+// Model
+// ======================================================================================
+Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, int cap)
+    : owner(o), id(id_), pose(Mat4::identity()), lastPose(Mat4::identity()), initialC2Winv(Mat4::identity()),
+      confidenceThreshold(conf), maxDepth(FLT_MAX), fillIn(enableFillIn), capacity((uint32_t)cap), lastTransform(Mat4::identity())
+{
+    const int W = o->W, H = o->H, P = o->P;
+    cudaStream_t s = o->stream;
+    for (int b = 0; b < 2; ++b) { pos[b].alloc(capacity); col[b].alloc(capacity); nrm[b].alloc(capacity); }
+    count.alloc(2); count.zero(s);
+    cudaCheck(cudaMallocHost((void**)&hCount, 2 * sizeof(uint32_t)), "cudaMallocHost"); hCount[0] = hCount[1] = 0;
+    cudaCheck(cudaMallocHost((void**)&hTrackOut, 40 * sizeof(float)), "cudaMallocHost");
+    key.alloc(P); launch_fill_u64(key, KEY_EMPTY, P, s);
+    idx.alloc(P); vertConf.alloc(P); colorTime.alloc(P); normRad.alloc(P);
+    idx.zero(s); vertConf.zero(s); colorTime.zero(s); normRad.zero(s);
+    splatImage.alloc(P); splatVertex.alloc(P); splatNormal.alloc(P); splatTime.alloc(P);
+    splatImage.zero(s); splatVertex.zero(s); splatNormal.zero(s); splatTime.zero(s);
+    nonBlack.alloc(1); nonBlack.zero(s);
+    if (fillIn) { fillImage.alloc(P); fillVertex.alloc(P); fillNormal.alloc(P); fillImage.zero(s); fillVertex.zero(s); fillNormal.zero(s); }
+    aflag.alloc(P); abest.alloc(P); aflag.zero(s); abest.zero(s);
+    for (int k = 0; k < 3; ++k) { meas[k].alloc(P); meas[k].zero(s); }
+    slot.alloc(capacity); launch_fill_u32(slot, 0xffffffffu, capacity, s);
+    keep.alloc((size_t)capacity + P);
+    size_t nblk = ((size_t)capacity + P + 511) / 512 + 1;
+    blockSums.alloc(nblk); blockSums2.alloc(nblk);
+    for (int l = 0; l < 3; ++l) {
+        size_t Pl = (size_t)(W >> l) * (H >> l);
+        vmapG[l].alloc(Pl); nmapG[l].alloc(Pl); cloud[l].alloc(Pl); lastDepth[l].alloc(Pl); lastImage[l].alloc(Pl); corres[l].alloc(Pl);
+        vmapG[l].zero(s); nmapG[l].zero(s); lastDepth[l].zero(s); lastImage[l].zero(s);
+    }
+    lastNextImage2.alloc((size_t)(W >> 2) * (H >> 2)); lastNextImage2.zero(s);
+    trackState.alloc(1); trackState.zero(s);
+    partial.alloc((size_t)TRACK_MAX_BLOCKS * 64); partialI.alloc((size_t)TRACK_MAX_BLOCKS * 2);
+    o->launches += 2;
+}
+
+unsigned Model::lastCount()
+{
+    cudaCheck(cudaMemcpyAsync(hCount, dCount(), sizeof(uint32_t), cudaMemcpyDeviceToHost, owner->stream), "count D2H");
+    owner->sync();
+    return hCount[0];
+}
+
+// Model::initialise (Model.cpp:240-285) fed by MaskFusion::computeFeedbackBuffers (MaskFusion.cpp:187-198)
+void Model::initialise(int time)
+{
+    MaskFusion* o = owner;
+    launch_init_model(o->rgb, o->depthRaw, o->depthFilt, o->cam, o->W, o->H, time, o->cfg.maxDepthProcessed, o->initFlagR, o->initFlagF,
+                      blockSums, blockSums2, capacity, current(), dCount(), o->stream);
+    o->launches += 5;
+}
+
+// model side of Model::initICP (Model.cpp:391-409): predicted (or fill-in) maps -> pyramids in the model-global frame
+void Model::prepareTracking()
+{
+    MaskFusion* o = owner;
+    cudaStream_t s = o->stream;
+    const int W = o->W, H = o->H;
+    float denom = (float)((H / 20) * (W / 20));
+    float4* v[3] = {vmapG[0].p, vmapG[1].p, vmapG[2].p};
+    float4* n[3] = {nmapG[0].p, nmapG[1].p, nmapG[2].p};
+    const uint32_t* nb = fillIn ? nonBlack.p : nullptr;
+    launch_model_maps(splatVertex, splatNormal, fillIn ? fillVertex.p : splatVertex.p, fillIn ? fillNormal.p : splatNormal.p, nb, denom, W, H,
+                      toRt(pose), 6.0f /* maxDepthRGB, RGBDOdometry.cpp:34 */, v, n, lastDepth[0], s);
+    o->launches += 1;
+    const bool rgb = o->cfg.rgbOnly || o->cfg.icpWeight < 100;
+    if (rgb) {
+        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_f(lastDepth[l], W >> l, H >> l, lastDepth[l + 1], s);
+        launch_intensity_select(splatImage, fillIn ? fillImage.p : splatImage.p, nb, denom, (o->cfg.frameToFrameRGB && fillIn) ? 1 : 0, o->P, lastImage[0], s);
+        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(lastImage[l], W >> l, H >> l, lastImage[l + 1], s);
+        for (int l = 0; l < 3; ++l) launch_project_points(lastDepth[l], W >> l, H >> l, camLevel(o->cam, l), cloud[l], s);
+        o->launches += 8;
+    }
+}
+
+float Model::computeFusionWeight(float weightMultiplier) const
+{
+    Mat4 diff = mul(rigidInverse(pose), lastPose);       // Model::getLastTransform, Model.h:239
+    const float* d = diff.m;
+    float R[9] = {d[0], d[1], d[2], d[4], d[5], d[6], d[8], d[9], d[10]};
+    float tn = sqrtf((d[3] * d[3] + d[7] * d[7]) + d[11] * d[11]);
+    float rv[3]; rodrigues2(R, rv);
+    float rn = sqrtf((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
+    float weighting = tn > rn ? tn : rn;
+    const float largest = 0.01f, minWeight = 0.5f;
+    if (weighting > largest) weighting = largest;
+    float w = 1.0f - (weighting / largest);
+    return (w > minWeight ? w : minWeight) * weightMultiplier;
+}
+
+void Model::predictIndices(int time, float depthCutoff, int timeDelta)
+{
+    MaskFusion* o = owner;
+    launch_predict_indices(current(), dCount(), toRt(rigidInverse(pose)), o->cam, o->W, o->H, depthCutoff, time, timeDelta, key, idx, vertConf,
+                           colorTime, normRad, o->stream);
+    o->launches += 2;
+}
+
+void Model::fuse(int time, float depthCutoff, float weightMultiplier)
+{
+    MaskFusion* o = owner;
+    float md = depthCutoff < maxDepth ? depthCutoff : maxDepth;      // Model.cpp:527 (headless: bounding box empty, N7)
+    float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
+    launch_associate(o->rgb, o->depthRaw, o->depthFilt, o->mask, idx, vertConf, normRad, toRt(pose), o->cam, o->W, o->H, md, time,
+                     computeFusionWeight(weightMultiplier), id, aflag, abest, m, slot, o->stream);
+    launch_fuse_update(aflag, abest, m, slot, o->P, time, current(), o->stream);
+    o->launches += 3;
+}
+
+void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
+{
+    MaskFusion* o = owner;
+    float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
+    int other = 1 - target, otherCount = 1 - countSel;
+    launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, toRt(rigidInverse(pose)), o->cam, o->W, o->H,
+                 time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, idx, vertConf, colorTime, o->depthFilt, o->mask, keep, blockSums,
+                 o->stream);
+    target = other; countSel = otherCount;
+    o->launches += 3;
+}
+
+void Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta)
+{
+    MaskFusion* o = owner;
+    launch_combined_predict(current(), dCount(), toRt(rigidInverse(pose)), o->cam, o->W, o->H, depthCutoff, confidenceThreshold, time, maxTime,
+                            timeDelta, key, splatImage, splatVertex, splatNormal, splatTime, fillIn ? 1 : 0, o->depthFilt, o->rgb, 0,
+                            o->cfg.frameToFrameRGB ? 1 : 0, fillImage, fillVertex, fillNormal, fillIn ? nonBlack.p : nullptr, o->stream);
+    o->launches += 2;
+}
+
+// ======================================================================================
+// MaskFusion
+// ======================================================================================
+MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), device(dev)
+{
+    cudaCheck(cudaSetDevice(dev), "cudaSetDevice");
+    cudaDeviceProp prop;
+    cudaCheck(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
+    numSMs = prop.multiProcessorCount;
+    set_num_sms(numSMs);
+    W = c.width; H = c.height; P = W * H;
+    if (W % 4 || H % 4) throw CudaError{"width and height must be multiples of 4 (3-level pyramid)"};
+    cam = Cam{c.fx, c.fy, c.cx, c.cy};
+    ownStream = (st == nullptr);
+    if (ownStream) cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"); else stream = st;
+    rgb3.alloc((size_t)P * 3); rgb.alloc(P); depthRaw.alloc(P); depthFilt.alloc(P); mask.alloc(P); mask.zero(stream);
+    for (int l = 0; l < 3; ++l) {
+        size_t Pl = (size_t)(W >> l) * (H >> l);
+        if (l > 0) depthPyr[l].alloc(Pl);
+        vmap[l].alloc(Pl); nmap[l].alloc(Pl); nextImage[l].alloc(Pl); nextGrad[l].alloc(Pl);
+    }
+    edgeMap.alloc(P); edgeBinary.alloc(P); edgeBuf.alloc(P); edgeInv.alloc(P);
+    dJobs.alloc(TRACK_MAX_JOBS);
+    cudaCheck(cudaMallocHost((void**)&hJobs, TRACK_MAX_JOBS * sizeof(TrackJob)), "cudaMallocHost");
+    initFlagR.alloc(P); initFlagF.alloc(P);
+    scratch.alloc((size_t)P * 4);
+    models.emplace_back(new Model(this, nextID++, c.confGlobal, true, c.capacityGlobal));    // MaskFusion.cpp:80-81
+    sync();
+}
+
+MaskFusion::~MaskFusion()
+{
+    cudaStreamSynchronize(stream);
+    for (auto& m : models) { if (m->hCount) cudaFreeHost(m->hCount); if (m->hTrackOut) cudaFreeHost(m->hTrackOut); }
+    models.clear();
+    if (hJobs) cudaFreeHost(hJobs);
+    if (ownStream) cudaStreamDestroy(stream);
+}
+
+void MaskFusion::sync() { cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
+
+// textureRGB / textureDepthMetric upload + filterDepth (MaskFusion.cpp:212-217, 650-657)
+void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint8_t* maskIn, bool onDevice)
+{
+    cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    cudaCheck(cudaMemcpyAsync(rgb3, rgbIn, (size_t)P * 3, kind, stream), "rgb upload");
+    cudaCheck(cudaMemcpyAsync(depthRaw, depthIn, (size_t)P * sizeof(float), kind, stream), "depth upload");
+    if (maskIn) cudaCheck(cudaMemcpyAsync(mask, maskIn, (size_t)P, kind, stream), "mask upload");
+    launch_unpack_rgb(rgb3, rgb, P, stream);
+    launch_bilateral(depthRaw, depthFilt, W, H, stream);
+    launches += 2;
+    frameMapsValid = false; intensityValid = false;
+}
+
+// Model::generateCUDATextures (Model.cpp:350-389): level 0 aliases the filtered depth.
+// The mask pyramid of the reference is dead (N10) and not built.
+void MaskFusion::generateCUDATextures()
+{
+    const float* d[3] = {depthFilt.p, depthPyr[1].p, depthPyr[2].p};
+    for (int l = 1; l < 3; ++l) launch_pyrdown_f(d[l - 1], W >> (l - 1), H >> (l - 1), depthPyr[l], stream);
+    for (int l = 0; l < 3; ++l) launch_vmap_nmap(d[l], W >> l, H >> l, camLevel(cam, l), cfg.depthCutoff, vmap[l], nmap[l], stream);
+    launches += 5;
+    frameMapsValid = true;
+}
+
+// Model::performTracking for a batch of models: one launch sequence, blockIdx.y = model
+void MaskFusion::trackModels(const std::vector<Model*>& ms)
+{
+    if (ms.empty()) return;
+    if ((int)ms.size() > TRACK_MAX_JOBS) throw CudaError{"too many tracked models for one batch"};
+    const bool rgbTerm = cfg.rgbOnly || cfg.icpWeight < 100;
+    if (!frameMapsValid) generateCUDATextures();
+    if ((rgbTerm || cfg.so3) && !intensityValid) {
+        // frame side of RGBDOdometry::initRGB (RGBDOdometry.cpp:212-215): shared by all models
+        launch_intensity(rgb, P, nextImage[0], stream);
+        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
+        launches += 3;
+        if (rgbTerm) { for (int l = 0; l < 3; ++l) launch_sobel(nextImage[l], W >> l, H >> l, nextGrad[l], stream); launches += 3; }
+        intensityValid = true;
+    }
+    TrackPoses poses;
+    memset(&poses, 0, sizeof poses);
+    for (size_t j = 0; j < ms.size(); ++j) {
+        Model* m = ms[j];
+        m->lastPose = m->pose;                                       // Model.cpp:430
+        m->prepareTracking();
+        TrackJob& J = hJobs[j];
+        for (int l = 0; l < 3; ++l) {
+            J.vmapC[l] = vmap[l]; J.nmapC[l] = nmap[l]; J.nextImage[l] = nextImage[l]; J.nextGrad[l] = nextGrad[l];
+            J.vmapG[l] = m->vmapG[l]; J.nmapG[l] = m->nmapG[l]; J.lastDepth[l] = m->lastDepth[l]; J.lastImage[l] = m->lastImage[l];
+            J.cloud[l] = m->cloud[l]; J.corres[l] = m->corres[l];
+        }
+        J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.partialI = m->partialI;
+        memcpy(poses.p[j], m->pose.m, 16 * sizeof(float));
+    }
+    cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
+    launches += launch_tracking(dJobs, (int)ms.size(), poses, W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
+                                cfg.so3 != 0, numSMs, stream);
+    for (Model* m : ms) {
+        cudaCheck(cudaMemcpyAsync(m->hTrackOut, (const char*)m->trackState.p + offsetof(TrackState, out), 40 * sizeof(float),
+                                  cudaMemcpyDeviceToHost, stream), "pose D2H");
+        if (cfg.so3)   // std::swap(lastNextImage, nextImage) (RGBDOdometry.cpp:484-488): only level 2 is ever read
+            cudaCheck(cudaMemcpyAsync(m->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "so3 swap");
+    }
+    sync();                                                          // the one host sync of the frame
+    for (Model* m : ms) {
+        memcpy(m->pose.m, m->hTrackOut, 16 * sizeof(float));
+        memcpy(m->lastTransform.m, m->hTrackOut + 16, 16 * sizeof(float));
+    }
+}
+
+void MaskFusion::predict()
+{
+    for (auto& m : models) m->combinedPredict(cfg.maxDepthProcessed, tick, tick, cfg.timeDelta);   // MaskFusion.cpp:616-628
+}
+
+bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_t timestamp, const uint8_t* maskIn, const Mat4* inPose,
+                              float weightMultiplier, bool bootstrap, bool onDevice)
+{
+    if (cfg.enableMultipleModels) throw CudaError{"multi-model schedule not built in this round (DESIGN.md, section 'next')"};
+    setFrame(rgbIn, depthIn, nullptr, onDevice);                     // -static: mask stays all zero (MaskFusion.cpp:223-230)
+    (void)maskIn;
+    Model* g = models[0].get();
+    if (tick == 1) {
+        g->initialise(tick);
+        // globalModel->getFrameOdometry().initFirstRGB (MaskFusion.cpp:238)
+        launch_intensity(rgb, P, nextImage[0], stream);
+        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
+        cudaCheck(cudaMemcpyAsync(g->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
+        launches += 3;
+    } else {
+        if (bootstrap || !inPose) {
+            generateCUDATextures();
+            std::vector<Model*> tracked{g};
+            trackModels(tracked);
+            for (size_t i = 1; i < models.size(); ++i) models[i]->updateStaticPose(g->pose);
+            if (bootstrap && inPose) g->overridePose(mul(g->pose, *inPose));
+        } else {
+            g->overridePose(*inPose);
+        }
+        if (!cfg.rgbOnly) {
+            for (auto& m : models) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
+            for (auto& m : models) m->fuse(tick, cfg.depthCutoff, weightMultiplier);
+            for (auto& m : models) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
+            for (auto& m : models) m->clean(tick, cfg.timeDelta, cfg.maxDepthProcessed);
+        }
+    }
+    predict();          // MaskFusion.cpp:569 (the call at :423 is dead in open-loop mode: its outputs are overwritten here)
+    tick++;
+    for (size_t i = 0; i < models.size(); ++i) {
+        Model* m = models[i].get();
+        Mat4 T = (i == 0) ? g->pose : mul(g->pose, rigidInverse(m->pose));     // MaskFusion.cpp:581-583
+        float R[9] = {T.m[0], T.m[1], T.m[2], T.m[4], T.m[5], T.m[6], T.m[8], T.m[9], T.m[10]}, q[4];
+        rotToQuat(R, q);
+        double e[8] = {(double)timestamp, T.m[3], T.m[7], T.m[11], q[0], q[1], q[2], q[3]};
+        m->poseLog.insert(m->poseLog.end(), e, e + 8);
+        m->age++;
+    }
+    return false;
+}
+
+}  // namespace mfb

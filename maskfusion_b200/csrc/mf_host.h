@@ -1,0 +1,125 @@
+// mf_host.h -- host classes of the B200-native dense pipeline.  Class and method names
+// mirror the reference so that its call sites read the same:
+//   mfb::MaskFusion  <-> MaskFusion   (Core/MaskFusion.h:47-70)
+//   mfb::Model       <-> Model        (Core/Model/Model.h:128-164)
+// GPUTexture* arguments of the reference become device buffers owned by these classes;
+// Eigen::Matrix4f becomes Mat4 (row-major here, column-major at the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <memory>
+#include <string>
+#include <vector>
+#include "../../include/maskfusion_b200.h"
+#include "mf_kernels.h"
+
+namespace mfb {
+
+struct Mat4 {
+    float m[16];
+    static Mat4 identity() { Mat4 r; for (int i = 0; i < 16; ++i) r.m[i] = (i % 5 == 0) ? 1.f : 0.f; return r; }
+};
+Mat4 rigidInverse(const Mat4& T);
+Mat4 mul(const Mat4& A, const Mat4& B);
+Rt toRt(const Mat4& T);
+
+struct CudaError { std::string what; };
+void cudaCheck(cudaError_t e, const char* where);
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { if (p) cudaFree(p); }
+    void alloc(size_t count) { if (p) cudaFree(p); p = nullptr; n = count; if (count) cudaCheck(cudaMalloc((void**)&p, count * sizeof(T)), "cudaMalloc"); }
+    void zero(cudaStream_t s) { if (n) cudaCheck(cudaMemsetAsync(p, 0, n * sizeof(T), s), "memset"); }
+    operator T*() const { return p; }
+};
+
+class MaskFusion;
+
+class Model {
+public:
+    Model(MaskFusion* owner, unsigned char id, float confidenceThresh, bool enableFillIn, int capacity);
+
+    // ---- reference API (Core/Model/Model.h:128-164) ----
+    void initialise(int time);                                        // Model::initialise (+ computeFeedbackBuffers)
+    void prepareTracking();                                           // Model::initICP (model side)
+    void predictIndices(int time, float depthCutoff, int timeDelta);  // Model::predictIndices
+    void fuse(int time, float depthCutoff, float weightMultiplier);   // Model::fuse
+    void clean(int time, int timeDelta, float depthCutoff);           // Model::clean
+    void combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta);   // Model::combinedPredict + performFillIn
+    float computeFusionWeight(float weightMultiplier) const;          // Model::computeFusionWeight
+    void overridePose(const Mat4& p) { lastPose = pose; pose = p; }
+    void makeStatic(const Mat4& globalPose) { initialC2Winv = mul(pose, rigidInverse(globalPose)); isStatic = true; }
+    void updateStaticPose(const Mat4& globalPose) { overridePose(mul(initialC2Winv, globalPose)); }
+    bool allowsFillIn() const { return fillIn; }
+    unsigned lastCount();                                             // Model::lastCount (synchronises)
+    SurfelPlanes planes(int b) const { return SurfelPlanes{pos[b].p, col[b].p, nrm[b].p}; }
+    SurfelPlanes current() const { return planes(target); }
+    uint32_t* dCount() const { return count.p + countSel; }
+
+    MaskFusion* owner;
+    unsigned char id; int classID = -1;
+    Mat4 pose, lastPose, initialC2Winv;
+    bool isStatic = false, nonstatic = false; unsigned age = 0;
+    float confidenceThreshold, maxDepth;
+    bool fillIn;
+    uint32_t capacity;
+    int target = 0, countSel = 0;
+    DevBuf<float4> pos[2], col[2], nrm[2];
+    DevBuf<uint32_t> count;                 // [2] ping-pong, device-resident (no host round trip in the loop)
+    uint32_t* hCount = nullptr;             // pinned mirror
+    // index map
+    DevBuf<uint64_t> key;
+    DevBuf<uint32_t> idx; DevBuf<float4> vertConf, colorTime, normRad;
+    // prediction + fill-in
+    DevBuf<uchar4> splatImage, fillImage; DevBuf<float4> splatVertex, splatNormal, fillVertex, fillNormal; DevBuf<uint16_t> splatTime;
+    DevBuf<uint32_t> nonBlack;
+    // association
+    DevBuf<uint8_t> aflag; DevBuf<uint32_t> abest; DevBuf<float4> meas[3]; DevBuf<uint32_t> slot;
+    DevBuf<uint8_t> keep; DevBuf<uint32_t> blockSums, blockSums2;
+    // tracking
+    DevBuf<float4> vmapG[3], nmapG[3], cloud[3];
+    DevBuf<float> lastDepth[3]; DevBuf<uint8_t> lastImage[3]; DevBuf<uint8_t> lastNextImage2;
+    DevBuf<DataTerm> corres[3];
+    DevBuf<TrackState> trackState; DevBuf<float> partial; DevBuf<int> partialI;
+    float* hTrackOut = nullptr;             // pinned: pose(16) transform(16) stats(8)
+    Mat4 lastTransform;
+    std::vector<double> poseLog;            // 8 doubles per entry
+};
+
+class MaskFusion {
+public:
+    MaskFusion(const mf_config& cfg, int device, cudaStream_t stream);
+    ~MaskFusion();
+
+    // bool MaskFusion::processFrame(FrameDataPointer, const Eigen::Matrix4f* inPose, float weightMultiplier, bool bootstrap)
+    bool processFrame(const uint8_t* rgb, const float* depth, int64_t timestamp, const uint8_t* mask, const Mat4* inPose,
+                      float weightMultiplier, bool bootstrap, bool inputsOnDevice);
+    void setFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool onDevice);   // upload + filterDepth
+    void generateCUDATextures();                                                                  // Model::generateCUDATextures
+    void trackModels(const std::vector<Model*>& ms);                                              // performTracking for a batch
+    void predict();                                                                               // MaskFusion::predict
+    void sync();
+
+    mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
+    int numSMs = 148;
+    int tick = 1;
+    int64_t launches = 0;
+    std::vector<std::unique_ptr<Model>> models;
+    unsigned char nextID = 0;
+    // frame
+    DevBuf<uint8_t> rgb3; DevBuf<uchar4> rgb; DevBuf<float> depthRaw, depthFilt; DevBuf<uint8_t> mask;
+    DevBuf<float> depthPyr[3]; DevBuf<float4> vmap[3], nmap[3];
+    DevBuf<uint8_t> nextImage[3]; DevBuf<short2> nextGrad[3];
+    DevBuf<float> edgeMap; DevBuf<uint8_t> edgeBinary, edgeBuf, edgeInv;
+    DevBuf<TrackJob> dJobs; TrackJob* hJobs = nullptr;
+    DevBuf<uint8_t> initFlagR, initFlagF;
+    DevBuf<float> scratch;                  // read-back staging
+    bool frameMapsValid = false, intensityValid = false;
+};
+
+}  // namespace mfb

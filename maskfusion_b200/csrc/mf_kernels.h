@@ -1,0 +1,99 @@
+// mf_kernels.h -- host-callable launchers of the sm_100a kernels and the device-side
+// structures they share with the host classes (mf_host.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "mf_common.cuh"
+
+namespace mfb {
+
+struct SurfelPlanes { float4* pos; float4* col; float4* nrm; };
+
+// photometric correspondence record (reference: DataTerm, Core/Cuda/types.cuh:75-81)
+struct DataTerm { short2 zero; short2 one; float diff; int valid; };
+
+#define TRACK_MAX_JOBS 16
+#define TRACK_MAX_BLOCKS 512
+struct TrackPoses { float p[TRACK_MAX_JOBS][16]; };
+
+// Gauss-Newton state of one tracked model; lives in device memory for the whole frame
+struct TrackState {
+    float Rprev[9], tprev[3], RprevInv[9];
+    float Rcurr[9], tcurr[3];
+    float trR[9], trT[3];
+    double resultRt[16];
+    double resultR[9], lastResultR[9];
+    float R_lr[9];
+    float so3LastError, so3LastCount; int so3Done;
+    float krk[9], kt[3];
+    float sigmaVal; int levelBreak;
+    float lastICPError, lastICPCount, lastRGBError, lastRGBCount, lastSO3Error, lastSO3Count;
+    double lastA[36], lastb[6];
+    float out[40];
+    unsigned ticket[4];
+};
+
+struct TrackJob {
+    const float4* vmapC[3]; const float4* nmapC[3];        // frame maps (shared by all models)
+    const uint8_t* nextImage[3]; const short2* nextGrad[3];
+    const float4* vmapG[3]; const float4* nmapG[3];        // model maps in the model-global frame
+    const float* lastDepth[3]; const uint8_t* lastImage[3];
+    const uint8_t* lastNextImage2;
+    const float4* cloud[3];
+    DataTerm* corres[3];
+    TrackState* st;
+    float* partial;       // TRACK_MAX_BLOCKS x 64 floats
+    int* partialI;        // TRACK_MAX_BLOCKS x 2 ints
+};
+
+void set_num_sms(int n);
+
+// ---- mf_frame.cu ----
+void launch_unpack_rgb(const uint8_t* rgb3, uchar4* out, int P, cudaStream_t s);
+void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t s);
+void launch_pyrdown_f(const float* src, int sw, int sh, float* dst, cudaStream_t s);
+void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStream_t s);
+void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s);
+void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s);
+void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s);
+void launch_sobel(const uint8_t* src, int W, int H, short2* grad, cudaStream_t s);
+void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
+                       int W, int H, Rt pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s);
+void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s);
+void launch_project_points(const float* depth, int W, int H, Cam cam, float4* cloud, cudaStream_t s);
+
+// ---- mf_surfel.cu ----
+void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s);
+void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s);
+void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, int time,
+                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, cudaStream_t s);
+void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
+                      const float4* vertConf, const float4* normRad, Rt pose, Cam cam, int W, int H, float maxDepth, int time,
+                      float weighting, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s);
+void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const* meas, uint32_t* slot, int P, int time,
+                        const SurfelPlanes& sp, cudaStream_t s);
+void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
+                  const uint8_t* aflag, float4* const* meas, Rt tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
+                  float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
+                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, cudaStream_t s);
+void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth,
+                             float confThreshold, int time, int maxTime, int timeDelta, uint64_t* key, uchar4* image, float4* vertexConf,
+                             float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
+                             uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s);
+void launch_init_model(const uchar4* rgb, const float* depthRaw, const float* depthFilt, Cam cam, int W, int H, int time, float maxDepth,
+                       uint8_t* fr, uint8_t* ff, uint32_t* sumR, uint32_t* sumF, uint32_t capacity, const SurfelPlanes& sp, uint32_t* count,
+                       cudaStream_t s);
+void launch_planes_to_aos(const SurfelPlanes& sp, uint32_t n, float4* out, cudaStream_t s);
+void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, cudaStream_t s);
+
+// ---- mf_track.cu ----
+int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s);
+void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,
+                     const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s);
+
+// ---- mf_seg.cu ----
+void launch_geometric_edges(const float4* vmap, const float4* nmap, int W, int H, float wD, float wC, float thr, float* edge, uint8_t* binary, cudaStream_t s);
+void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, uint8_t* inverted, cudaStream_t s);
+
+}  // namespace mfb

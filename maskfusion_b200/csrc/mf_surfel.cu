@@ -1,0 +1,728 @@
+// mf_surfel.cu -- surfel-map kernels (sm_100a).  These replace the reference's OpenGL
+// passes; there is no rasteriser here.
+//   predictIndices  <- index_map.vert/.frag,            ModelProjection.cpp:100-152
+//   associate       <- data.vert/.geom/.frag,           Model.cpp:466-581
+//   fuseUpdate      <- update.vert,                     Model.cpp:583-646
+//   clean           <- copy_unstable.vert/.geom,        Model.cpp:649-772
+//   combinedPredict <- splat.vert + combo_splat.frag,   ModelProjection.cpp:187-268
+//   fillIn          <- fill_{vertex,normal,rgb}.frag,   Shaders/FillIn.cpp
+//   initModel       <- vertex_feedback.* + init_unstable.vert, Model.cpp:240-285
+//
+// Surfel store: three float4 planes (position|conf, colour|.|initTime|lastTime,
+// normal|radius) -> every pass streams 16-byte coalesced loads (the reference's VBO is
+// 48-byte AoS).  Depth-tested rasterisation is a 64-bit atomicMin on
+// (depth bits << 32 | surfel id): nearest fragment wins, ties go to the lowest id, which
+// is the GL_LESS + draw-order rule (N2).  Keys are reset by the resolve kernel that
+// consumes them, so no per-pass clear of per-pixel or per-surfel state is ever issued
+// (the reference clears 3 x texDim^2 x 16 B of update maps on every fuse).
+#include "mf_common.cuh"
+#include "mf_kernels.h"
+
+namespace mfb {
+
+#define MAX_POINT_SIZE 2047.0f
+
+// ---------------------------------------------------------------------------------------
+// index map
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_index_project(const float4* __restrict__ pos, const float4* __restrict__ col,
+                                                       const uint32_t* __restrict__ countPtr, Rt tinv, Cam cam, int W, int H,
+                                                       float maxDepth, float ftime, float ftimeDelta,
+                                                       unsigned long long* __restrict__ key)
+{
+    const uint32_t count = *countPtr;
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
+        float4 p = ldStream(pos + id);
+        float lastTime = ldStream(col + id).w;
+        float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
+        if (ph.z > maxDepth || ph.z <= 0 || ftime - lastTime > ftimeDelta) continue;
+        float x = ((cam.fx * ph.x) / ph.z) + cam.cx;
+        float y = ((cam.fy * ph.y) / ph.z) + cam.cy;
+        float zn = ph.z / maxDepth;
+        if (!(zn < 1.0f)) continue;
+        float fx_ = floorf(x), fy_ = floorf(y);
+        if (!(fx_ >= 0 && fy_ >= 0 && fx_ < (float)W && fy_ < (float)H)) continue;
+        unsigned long long k = ((unsigned long long)__float_as_uint(zn) << 32) | id;
+        unsigned long long* dst = key + ((int)fy_ * W + (int)fx_);
+        if (k < *dst) atomicMin(dst, k);
+    }
+}
+
+__global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
+                                Rt tinv, int P, unsigned long long* __restrict__ key, uint32_t* __restrict__ idx,
+                                float4* __restrict__ vertConf, float4* __restrict__ colorTime, float4* __restrict__ normRad)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    unsigned long long k = key[i];
+    if (k == KEY_EMPTY) {
+        idx[i] = 0;
+        float4 z = make_float4(0, 0, 0, 0);
+        vertConf[i] = z; colorTime[i] = z; normRad[i] = z;
+        return;
+    }
+    key[i] = KEY_EMPTY;
+    uint32_t id = (uint32_t)(k & 0xffffffffull);
+    float4 p = pos[id], c = col[id], n = nrm[id];
+    float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
+    float3 nn = normalize3(rotate(tinv, make_float3(n.x, n.y, n.z)));
+    idx[i] = id;
+    vertConf[i] = make_float4(ph.x, ph.y, ph.z, p.w);
+    colorTime[i] = c;
+    normRad[i] = make_float4(nn.x, nn.y, nn.z, n.w);
+}
+
+// ---------------------------------------------------------------------------------------
+// frame-side vertex helpers (geometry.glsl)
+// ---------------------------------------------------------------------------------------
+MF_D float3 getVertex(const float* __restrict__ depth, int W, int H, int tx, int ty, float x, float y, Cam cam, float ifx, float ify)
+{
+    float z = depth[clampi(ty, 0, H - 1) * W + clampi(tx, 0, W - 1)];
+    return make_float3((x - cam.cx) * z * ifx, (y - cam.cy) * z * ify, z);
+}
+MF_D float3 normalCentral(const float* __restrict__ depth, int W, int H, int tx, int ty, float x, float y, Cam cam, float ifx, float ify, float3 vp)
+{
+    float3 xf = getVertex(depth, W, H, tx + 1, ty, x + 1, y, cam, ifx, ify);
+    float3 xb = getVertex(depth, W, H, tx - 1, ty, x - 1, y, cam, ifx, ify);
+    float3 yf = getVertex(depth, W, H, tx, ty + 1, x, y + 1, cam, ifx, ify);
+    float3 yb = getVertex(depth, W, H, tx, ty - 1, x, y - 1, cam, ifx, ify);
+    float3 dx = make_float3(((xb.x + vp.x) / 2) - ((xf.x + vp.x) / 2), ((xb.y + vp.y) / 2) - ((xf.y + vp.y) / 2), ((xb.z + vp.z) / 2) - ((xf.z + vp.z) / 2));
+    float3 dy = make_float3(((yb.x + vp.x) / 2) - ((yf.x + vp.x) / 2), ((yb.y + vp.y) / 2) - ((yf.y + vp.y) / 2), ((yb.z + vp.z) / 2) - ((yf.z + vp.z) / 2));
+    return normalize3(cross3(dx, dy));
+}
+MF_D float3 normalForward(const float* __restrict__ depth, int W, int H, int tx, int ty, Cam cam, float ifx, float ify, float3 vp)
+{
+    float3 vx = getVertex(depth, W, H, tx + 1, ty, (float)(tx + 1), (float)ty, cam, ifx, ify);
+    float3 vy = getVertex(depth, W, H, tx, ty + 1, (float)tx, (float)(ty + 1), cam, ifx, ify);
+    return normalize3(cross3(sub3(vx, vp), sub3(vy, vp)));
+}
+
+// ---------------------------------------------------------------------------------------
+// data association: one thread per pixel (row-major => coalesced frame reads); results are
+// stored at the x-major order index p = x*H + y that the reference's draw order defines.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_associate(const uchar4* __restrict__ rgb, const float* __restrict__ depthRaw,
+                                                   const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
+                                                   const uint32_t* __restrict__ idx, const float4* __restrict__ vertConf,
+                                                   const float4* __restrict__ normRad, Rt pose, Cam cam, int W, int H,
+                                                   float maxDepth, int time, float weighting, uint8_t maskID,
+                                                   uint8_t* __restrict__ flag, uint32_t* __restrict__ best,
+                                                   float4* __restrict__ m0, float4* __restrict__ m1, float4* __restrict__ m2,
+                                                   uint32_t* __restrict__ slot)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= W || j >= H) return;
+    const int p = i * H + j;
+    const float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
+    float tcx = (float)i / (float)W + 0.5f / (float)W;
+    float tcy = (float)j / (float)H + 0.5f / (float)H;
+    float x = tcx * (float)W, y = tcy * (float)H;
+    uint8_t f = 0;
+    float3 vl = getVertex(depthRaw, W, H, i, j, x, y, cam, ifx, ify);
+    bool cand = ((int)x) % 2 == time % 2 && ((int)y) % 2 == time % 2 && mask[j * W + i] == maskID && vl.z > 0 && vl.z <= maxDepth;
+    if (cand) {
+        cand = depthRaw[j * W + clampi(i - 1, 0, W - 1)] != 0 && depthRaw[clampi(j - 1, 0, H - 1) * W + i] != 0 &&
+               depthRaw[j * W + clampi(i + 1, 0, W - 1)] != 0 && depthRaw[clampi(j + 1, 0, H - 1) * W + i] != 0;
+    }
+    if (cand) {
+        float3 vg = xform(pose, vl);
+        float3 vf = getVertex(depthFilt, W, H, i, j, x, y, cam, ifx, ify);
+        float3 nl = normalCentral(depthFilt, W, H, i, j, x, y, cam, ifx, ify, vf);
+        float3 ng = rotate(pose, nl);
+        uchar4 c8 = rgb[j * W + i];
+        float enc = encodeColor((float)c8.x / 255.0f, (float)c8.y / 255.0f, (float)c8.z / 255.0f);
+        float conf = surfelConfidence(x, y, weighting, cam.cx, cam.cy);
+        float rad = surfelRadius(vf.z, nl.z, ifx, ify);
+
+        float bestDist = 1000;
+        float xl = (x - cam.cx) * ifx, yl = (y - cam.cy) * ify;
+        float lambda = sqrtf((xl * xl + yl * yl) + 1);
+        float3 ray = make_float3(xl, yl, 1);
+        uint32_t b = 0; int operation = 0;
+        for (int dx = -1; dx <= 1; ++dx)
+            for (int dy = -1; dy <= 1; ++dy) {
+                int q = clampi(j + dy, 0, H - 1) * W + clampi(i + dx, 0, W - 1);
+                uint32_t cur = idx[q];
+                if (cur > 0u) {
+                    float4 vc = vertConf[q];
+                    float zdiff = vc.z - vl.z;
+                    if (fabsf(zdiff * lambda) < 0.05f) {
+                        float3 cr = cross3(ray, make_float3(vc.x, vc.y, vc.z));
+                        float dist = sqrtf(dot3(cr, cr));
+                        float4 nr = normRad[q];
+                        if (dist < bestDist) {
+                            float3 a = make_float3(nr.x, nr.y, nr.z);
+                            bool okn = fabsf(nr.z) < 0.75f ||
+                                       fabsf(det_acosf(dot3(a, nl) / (sqrtf(dot3(a, a)) * sqrtf(dot3(nl, nl))))) < 0.5f;
+                            if (okn) { operation = 1; bestDist = dist; b = cur; }
+                        }
+                    }
+                }
+            }
+        f = operation ? 1 : 2;
+        m0[p] = make_float4(vg.x, vg.y, vg.z, conf);
+        m1[p] = make_float4(enc, 0.f, (float)time, operation ? -1.f : -2.f);
+        m2[p] = make_float4(ng.x, ng.y, ng.z, rad);
+        best[p] = b;
+        if (operation) atomicMin(slot + b, (uint32_t)p);        // N4: first pixel in draw order wins
+    }
+    flag[p] = f;
+}
+
+// winners update their surfel in place (the reference rewrites the whole VBO; only the
+// <= P/4 associated surfels change, so the contents are identical)
+__global__ void k_fuse_update(const uint8_t* __restrict__ flag, const uint32_t* __restrict__ best,
+                              const float4* __restrict__ m0, const float4* __restrict__ m1, const float4* __restrict__ m2,
+                              const uint32_t* __restrict__ slot, int P, int time,
+                              float4* __restrict__ pos, float4* __restrict__ col, float4* __restrict__ nrm)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || flag[p] != 1) return;
+    uint32_t id = best[p];
+    if (slot[id] != (uint32_t)p) return;
+    float4 sp = pos[id], sc = col[id], sn = nrm[id];
+    float4 np_ = m0[p], nc = m1[p], nn = m2[p];
+    float c_k = sp.w, a = np_.w;
+    if (nn.w < (1.0f + 0.5f) * sn.w) {
+        float d = c_k + a;
+        sp = make_float4(((c_k * sp.x) + (a * np_.x)) / d, ((c_k * sp.y) + (a * np_.y)) / d, ((c_k * sp.z) + (a * np_.z)) / d, d);
+        float3 oc = decodeColor(sc.x), ncl = decodeColor(nc.x);
+        sc.x = encodeColor(((c_k * oc.x) + (a * ncl.x)) / d, ((c_k * oc.y) + (a * ncl.y)) / d, ((c_k * oc.z) + (a * ncl.z)) / d);
+        sc.w = (float)time;
+        float4 avg = make_float4(((c_k * sn.x) + (a * nn.x)) / d, ((c_k * sn.y) + (a * nn.y)) / d, ((c_k * sn.z) + (a * nn.z)) / d,
+                                 ((c_k * sn.w) + (a * nn.w)) / d);
+        float3 u = normalize3(make_float3(avg.x, avg.y, avg.z));
+        sn = make_float4(u.x, u.y, u.z, avg.w);
+    } else {
+        sp.w = c_k + a;
+        sc.w = (float)time;
+    }
+    pos[id] = sp; col[id] = sc; nrm[id] = sn;
+}
+
+// release the update slots taken this frame (self-cleaning; runs after k_fuse_update)
+__global__ void k_slot_release(const uint8_t* __restrict__ flag, const uint32_t* __restrict__ best, int P, uint32_t* __restrict__ slot)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P || flag[p] != 1) return;
+    slot[best[p]] = 0xffffffffu;
+}
+
+// ---------------------------------------------------------------------------------------
+// clean: per-vertex test (copy_unstable.vert) + ordered compaction (N5)
+// ---------------------------------------------------------------------------------------
+struct CleanParams {
+    Rt tinv; Cam cam; int W, H; int time; float ftimeDelta; float confThreshold; float outlierCoeff; uint8_t maskID;
+};
+
+MF_D bool cleanTest(float4& vp, float4& vc, const float4& vn, const CleanParams& P, const uint32_t* __restrict__ idx,
+                    const float4* __restrict__ vertConf, const float4* __restrict__ colorTime,
+                    const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask)
+{
+    const int W = P.W, H = P.H;
+    bool test = true;
+    float3 lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
+    const float cols = (float)W, rows = (float)H;
+    float x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
+    float y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
+    float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
+    float x_n = x / cols, y_n = y / rows;
+    float stepX = 1.0f / cols, stepY = 1.0f / rows;
+    const float scale = 1.0f;
+    float ixs = stepX * 0.5f / scale, iys = stepY * 0.5f / scale;
+    const float wm = 2;
+    int count = 0, zCount = 0;
+    const float ftime = (float)P.time;
+    if (ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows) {
+        for (float i = x_n - (scale * ixs * wm); i < x_n + (scale * ixs * wm); i += ixs)
+            for (float j = y_n - (scale * iys * wm); j < y_n + (scale * iys * wm); j += iys) {
+                int tx = clampi((int)floorf(i * cols), 0, W - 1);
+                int ty = clampi((int)floorf(j * rows), 0, H - 1);
+                int q = ty * W + tx;
+                uint32_t cur = idx[q];
+                if (cur > 0u) {
+                    float4 mc = vertConf[q], ct = colorTime[q];
+                    float ddx = mc.x - lp.x, ddy = mc.y - lp.y;
+                    if (ct.z < vc.z && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z < 0.01f &&
+                        sqrtf(ddx * ddx + ddy * ddy) < vn.w * 1.4f)
+                        count++;
+                    if (ct.w == ftime && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f)
+                        zCount++;
+                }
+            }
+    }
+    if (count > 8 || zCount > 4) test = false;
+    if (vc.w == -2) vc.w = ftime;
+    if (vc.w == -1 || ((ftime - vc.w) > 20 && vp.w < P.confThreshold)) test = false;
+    if (vc.w > 0 && ftime - vc.w > P.ftimeDelta) test = true;
+
+    float fxs = floorf(x), fys = floorf(y);
+    int sx = (fxs != fxs) ? 0 : (fxs < 0 ? 0 : (fxs > (float)(W - 1) ? W - 1 : (int)fxs));
+    int sy = (fys != fys) ? 0 : (fys < 0 ? 0 : (fys > (float)(H - 1) ? H - 1 : (int)fys));
+    float wDepth = depthFilt[sy * W + sx];
+    uint8_t maskValue = mask[sy * W + sx];
+    if ((maskValue != P.maskID) && maskValue < 255 && (wDepth > lp.z - 0.05f && wDepth < lp.z + 0.05f)) {
+        float f = (0.5f + 0.5f * (1 - P.outlierCoeff / 10.0f));
+        if (maskValue == 0) vp.w *= f;
+        else if (P.maskID == 0) vp.w *= 0.25f * f;
+        else vp.w *= f;
+    }
+    return test;
+}
+
+#define SCAN_BLOCK 512
+// pass 1: test every old surfel and every emitted new vertex; write the (possibly
+// re-weighted) record back in place, a keep flag, and per-block keep counts.
+__global__ void __launch_bounds__(SCAN_BLOCK) k_clean_test(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
+                                                           const uint32_t* __restrict__ countPtr,
+                                                           const uint8_t* __restrict__ aflag, float4* __restrict__ m0, float4* __restrict__ m1,
+                                                           const float4* __restrict__ m2, int Ppix, CleanParams P,
+                                                           const uint32_t* __restrict__ idx, const float4* __restrict__ vertConf,
+                                                           const float4* __restrict__ colorTime, const float* __restrict__ depthFilt,
+                                                           const uint8_t* __restrict__ mask, uint8_t* __restrict__ keep,
+                                                           uint32_t* __restrict__ blockSums)
+{
+    const uint32_t count = *countPtr;
+    const uint32_t total = count + (uint32_t)Ppix;
+    const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    __shared__ uint32_t wsum[SCAN_BLOCK / 32];
+    for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
+        bool k = false;
+        if (e < count) {
+            float4 vp = pos[e], vc = col[e], vn = ldStream(nrm + e);     // pos/col are written below: coherent loads
+            float w0 = vp.w, t0 = vc.w;
+            k = cleanTest(vp, vc, vn, P, idx, vertConf, colorTime, depthFilt, mask);
+            if (vp.w != w0) pos[e].w = vp.w;
+            if (vc.w != t0) col[e].w = vc.w;
+        } else if (e < total) {
+            uint32_t p = e - count;
+            if (aflag[p] == 2) {                 // merges (w = -1) always fail the test: skip them
+                float4 vp = m0[p], vc = m1[p], vn = m2[p];
+                k = cleanTest(vp, vc, vn, P, idx, vertConf, colorTime, depthFilt, mask);
+                m0[p].w = vp.w; m1[p].w = vc.w;
+            }
+        }
+        if (e < total) keep[e] = k ? 1 : 0;
+        unsigned bal = __ballot_sync(0xffffffffu, k);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(bal);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t s = 0;
+            for (int w = 0; w < SCAN_BLOCK / 32; ++w) s += wsum[w];
+            blockSums[blk] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// pass 2: exclusive scan of the block sums (single block) -> block offsets, new count
+__global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* __restrict__ blockSums, const uint32_t* __restrict__ countPtr,
+                                                          int extra, uint32_t capacity, uint32_t* __restrict__ newCount)
+{
+    const uint32_t total = *countPtr + (uint32_t)extra;
+    const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nblk; base += 1024) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < nblk ? blockSums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t incl = sh[threadIdx.x];
+        if (i < nblk) blockSums[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *newCount = carry < capacity ? carry : capacity;
+}
+
+// pass 3: ordered scatter of the survivors (old surfels in buffer order, then new vertices
+// in x-major pixel order) into the other buffer
+__global__ void __launch_bounds__(SCAN_BLOCK) k_clean_scatter(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
+                                                              const uint32_t* __restrict__ countPtr, const float4* __restrict__ m0,
+                                                              const float4* __restrict__ m1, const float4* __restrict__ m2, int Ppix,
+                                                              const uint8_t* __restrict__ keep, const uint32_t* __restrict__ blockOffs,
+                                                              uint32_t capacity, float4* __restrict__ opos, float4* __restrict__ ocol,
+                                                              float4* __restrict__ onrm)
+{
+    const uint32_t count = *countPtr;
+    const uint32_t total = count + (uint32_t)Ppix;
+    const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    __shared__ uint32_t wsum[SCAN_BLOCK / 32];
+    for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
+        bool k = e < total && keep[e];
+        unsigned bal = __ballot_sync(0xffffffffu, k);
+        int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < warp; ++w) woff += wsum[w];
+        uint32_t dst = blockOffs[blk] + woff + __popc(bal & ((1u << lane) - 1));
+        if (k && dst < capacity) {
+            float4 a, b, c;
+            if (e < count) { a = ldStream(pos + e); b = ldStream(col + e); c = ldStream(nrm + e); }
+            else { uint32_t p = e - count; a = m0[p]; b = m1[p]; c = m2[p]; }
+            stStream(opos + dst, a); stStream(ocol + dst, b); stStream(onrm + dst, c);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// splat prediction (combinedPredict) and model-ID projection
+// ---------------------------------------------------------------------------------------
+struct SplatVS { float3 pos; float conf; float3 n; float rad, size, xw, yw; bool ok; };
+
+MF_D SplatVS splatVertex(float4 p, float4 c, float4 nr, const Rt& tinv, Cam cam, int W, int H, float maxDepth,
+                         float confThreshold, float ftime, float fmaxTime, float ftimeDelta)
+{
+    SplatVS o; o.ok = false;
+    float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
+    if (ph.z > maxDepth || ph.z < 0 || p.w < confThreshold || ftime - c.w > ftimeDelta || c.w > fmaxTime) return o;
+    o.pos = ph; o.conf = p.w;
+    o.n = normalize3(rotate(tinv, make_float3(nr.x, nr.y, nr.z)));
+    o.rad = nr.w;
+    float3 x1 = normalize3(make_float3(o.n.y - o.n.z, -o.n.x, o.n.x));
+    x1 = make_float3(x1.x * o.rad * 1.41421356f, x1.y * o.rad * 1.41421356f, x1.z * o.rad * 1.41421356f);
+    float3 y1 = cross3(o.n, x1);
+    float px[4], py[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float3 d = (q == 0 || q == 3) ? x1 : y1;
+        float sg = (q < 2) ? 1.0f : -1.0f;
+        float3 pp = make_float3(ph.x + sg * d.x, ph.y + sg * d.y, ph.z + sg * d.z);
+        px[q] = ((cam.fx * pp.x) / pp.z) + cam.cx;
+        py[q] = ((cam.fy * pp.y) / pp.z) + cam.cy;
+    }
+    float xmin = fminf(px[0], fminf(px[1], fminf(px[2], px[3]))), xmax = fmaxf(px[0], fmaxf(px[1], fmaxf(px[2], px[3])));
+    float ymin = fminf(py[0], fminf(py[1], fminf(py[2], py[3]))), ymax = fmaxf(py[0], fmaxf(py[1], fmaxf(py[2], py[3])));
+    float sz = fmaxf(0.0f, fmaxf(fabsf(xmax - xmin), fabsf(ymax - ymin)));
+    if (!(sz >= 1.0f)) sz = 1.0f;
+    if (sz > MAX_POINT_SIZE) sz = MAX_POINT_SIZE;
+    o.size = sz;
+    o.xw = ((cam.fx * ph.x) / ph.z) + cam.cx;
+    o.yw = ((cam.fy * ph.y) / ph.z) + cam.cy;
+    if (!(o.xw >= 0 && o.xw <= (float)W && o.yw >= 0 && o.yw <= (float)H)) return o;
+    if (!(ph.z / maxDepth <= 1.0f)) return o;
+    o.ok = true;
+    return o;
+}
+
+MF_D bool splatFragment(const SplatVS& v, Cam cam, float fcx, float fcy, float3& cp)
+{
+    float3 l = normalize3(make_float3((fcx - cam.cx) / cam.fx, (fcy - cam.cy) / cam.fy, 1.0f));
+    float t = dot3(v.pos, v.n) / dot3(l, v.n);
+    cp = make_float3(t * l.x, t * l.y, t * l.z);
+    float sqrRad = v.rad * v.rad;
+    float3 d = sub3(cp, v.pos);
+    return !(dot3(d, d) > sqrRad);
+}
+
+MF_D void splatRange(const SplatVS& v, int W, int H, int& x0, int& x1, int& y0, int& y1)
+{
+    float h = v.size * 0.5f;
+    float lo = ceilf(v.xw - h - 0.5f), hi = ceilf(v.xw + h - 0.5f) - 1.0f;
+    x0 = lo < 0 ? 0 : (int)lo; x1 = hi > (float)(W - 1) ? W - 1 : (int)hi;
+    lo = ceilf(v.yw - h - 0.5f); hi = ceilf(v.yw + h - 0.5f) - 1.0f;
+    y0 = lo < 0 ? 0 : (int)lo; y1 = hi > (float)(H - 1) ? H - 1 : (int)hi;
+}
+
+__global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
+                                                       const uint32_t* __restrict__ countPtr, Rt tinv, Cam cam, int W, int H,
+                                                       float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
+                                                       uint32_t drawBase, unsigned long long* __restrict__ key)
+{
+    const uint32_t count = *countPtr;
+    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
+        float4 p = ldStream(pos + id);
+        // cheap rejects before touching the other two planes
+        float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
+        if (ph.z > maxDepth || ph.z < 0 || p.w < confThreshold) continue;
+        float4 c = ldStream(col + id), nr = ldStream(nrm + id);
+        SplatVS v = splatVertex(p, c, nr, tinv, cam, W, H, maxDepth, confThreshold, ftime, fmaxTime, ftimeDelta);
+        if (!v.ok) continue;
+        int x0, x1, y0, y1;
+        splatRange(v, W, H, x0, x1, y0, y1);
+        for (int py = y0; py <= y1; ++py)
+            for (int px = x0; px <= x1; ++px) {
+                float3 cp;
+                if (!splatFragment(v, cam, (float)px + 0.5f, (float)py + 0.5f, cp)) continue;
+                float fd = (cp.z / (2 * maxDepth)) + 0.5f;
+                if (!(fd >= 0.0f && fd < 1.0f)) continue;
+                unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | (drawBase + id);
+                unsigned long long* dst = key + (py * W + px);
+                if (k < *dst) atomicMin(dst, k);
+            }
+    }
+}
+
+// resolve the winning surfel per pixel -> colour, vertex, normal, time; fill-in of holes
+// from the raw frame (fill_*.frag) and the 1/20 sub-sampled "is the prediction mostly
+// black" counter of MaskFusion::requiresFillIn are fused into the same pass.
+__global__ void k_splat_resolve(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
+                                Rt tinv, Cam cam, int W, int H, float maxDepth, float confThreshold, float ftime, float fmaxTime,
+                                float ftimeDelta, unsigned long long* __restrict__ key,
+                                uchar4* __restrict__ image, float4* __restrict__ vertexConf, float4* __restrict__ normalRad,
+                                uint16_t* __restrict__ timeTex,
+                                int doFill, const float* __restrict__ depthFilt, const uchar4* __restrict__ rgb, int ptVN, int ptImg,
+                                uchar4* __restrict__ fillImage, float4* __restrict__ fillVertex, float4* __restrict__ fillNormal,
+                                uint32_t* __restrict__ nonBlackSamples)
+{
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= W || py >= H) return;
+    int i = py * W + px;
+    unsigned long long k = key[i];
+    uchar4 im = make_uchar4(0, 0, 0, 0);
+    float4 vc = make_float4(0, 0, 0, 0), nr = vc;
+    uint16_t tt = 0;
+    if (k != KEY_EMPTY) {
+        key[i] = KEY_EMPTY;
+        uint32_t id = (uint32_t)(k & 0xffffffffull);
+        float4 p = pos[id], c = col[id], n = nrm[id];
+        SplatVS v = splatVertex(p, c, n, tinv, cam, W, H, maxDepth, confThreshold, ftime, fmaxTime, ftimeDelta);
+        float3 cp; float fcx = (float)px + 0.5f, fcy = (float)py + 0.5f;
+        splatFragment(v, cam, fcx, fcy, cp);
+        float3 cl = decodeColor(c.x);
+        im = make_uchar4((uint8_t)(int)floorf(cl.x * 255.0f + 0.5f), (uint8_t)(int)floorf(cl.y * 255.0f + 0.5f),
+                         (uint8_t)(int)floorf(cl.z * 255.0f + 0.5f), 255);
+        float z = cp.z;
+        vc = make_float4((fcx - cam.cx) * z * (1.f / cam.fx), (fcy - cam.cy) * z * (1.f / cam.fy), z, v.conf);
+        nr = make_float4(v.n.x, v.n.y, v.n.z, v.rad);
+        tt = (uint16_t)(uint32_t)c.z;
+    }
+    image[i] = im; vertexConf[i] = vc; normalRad[i] = nr; timeTex[i] = tt;
+    if (nonBlackSamples && (px % 20) == 10 && (py % 20) == 10 && px / 20 < W / 20 && py / 20 < H / 20) {
+        if (im.x > 0 && im.y > 0 && im.z > 0) atomicAdd(nonBlackSamples, 1u);
+    }
+    if (doFill) {
+        const float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
+        float3 vp = getVertex(depthFilt, W, H, px, py, (float)px, (float)py, cam, ifx, ify);
+        fillVertex[i] = (vc.z == 0 || ptVN) ? make_float4(vp.x, vp.y, vp.z, 1.f) : vc;
+        if (nr.z == 0 || ptVN) {
+            float3 n = normalForward(depthFilt, W, H, px, py, cam, ifx, ify, vp);
+            fillNormal[i] = make_float4(n.x, n.y, n.z, 1.f);
+        } else fillNormal[i] = nr;
+        float sum = ((float)im.x / 255.0f + (float)im.y / 255.0f) + (float)im.z / 255.0f;
+        fillImage[i] = (sum == 0 || ptImg) ? rgb[i] : im;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// first-frame initialisation: two ordered streams (raw: position+colour, filtered:
+// normal+radius) compacted in x-major order and paired by emission index.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_BLOCK) k_init_flags(const float* __restrict__ depthRaw, const float* __restrict__ depthFilt,
+                                                           int W, int H, float maxDepth, uint8_t* __restrict__ fr, uint8_t* __restrict__ ff,
+                                                           uint32_t* __restrict__ sumR, uint32_t* __restrict__ sumF)
+{
+    const int P = W * H;
+    __shared__ uint32_t ws[2][SCAN_BLOCK / 32];
+    int p = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    bool kr = false, kf = false;
+    if (p < P) {
+        int i = p / H, j = p - i * H;
+        float zr = depthRaw[j * W + i], zf = depthFilt[j * W + i];
+        kr = !(zr <= 0 || zr > maxDepth);
+        kf = !(zf <= 0 || zf > maxDepth);
+        fr[p] = kr; ff[p] = kf;
+    }
+    unsigned br = __ballot_sync(0xffffffffu, kr), bf = __ballot_sync(0xffffffffu, kf);
+    if ((threadIdx.x & 31) == 0) { ws[0][threadIdx.x >> 5] = __popc(br); ws[1][threadIdx.x >> 5] = __popc(bf); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t a = 0, b = 0;
+        for (int w = 0; w < SCAN_BLOCK / 32; ++w) { a += ws[0][w]; b += ws[1][w]; }
+        sumR[blockIdx.x] = a; sumF[blockIdx.x] = b;
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_init_scatter(const uchar4* __restrict__ rgb, const float* __restrict__ depthRaw,
+                                                             const float* __restrict__ depthFilt, Cam cam, int W, int H, int time,
+                                                             const uint8_t* __restrict__ fr, const uint8_t* __restrict__ ff,
+                                                             const uint32_t* __restrict__ offR, const uint32_t* __restrict__ offF,
+                                                             uint32_t capacity, float4* __restrict__ pos, float4* __restrict__ col,
+                                                             float4* __restrict__ nrm)
+{
+    const int P = W * H;
+    __shared__ uint32_t ws[2][SCAN_BLOCK / 32];
+    int p = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    bool kr = p < P && fr[p], kf = p < P && ff[p];
+    unsigned br = __ballot_sync(0xffffffffu, kr), bf = __ballot_sync(0xffffffffu, kf);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { ws[0][warp] = __popc(br); ws[1][warp] = __popc(bf); }
+    __syncthreads();
+    uint32_t wr = 0, wf = 0;
+    for (int w = 0; w < warp; ++w) { wr += ws[0][w]; wf += ws[1][w]; }
+    if (p >= P) return;
+    int i = p / H, j = p - i * H;
+    const float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
+    float tcx = (float)(((double)((float)i / (float)W)) + 1.0 / (double)(2 * (float)W));   // FeedbackBuffer.cpp:44-49
+    float tcy = (float)(((double)((float)j / (float)H)) + 1.0 / (double)(2 * (float)H));
+    float x = tcx * (float)W, y = tcy * (float)H;
+    if (kr) {
+        uint32_t dst = offR[blockIdx.x] + wr + __popc(br & ((1u << lane) - 1));
+        if (dst < capacity) {
+            float3 vp = getVertex(depthRaw, W, H, i, j, x, y, cam, ifx, ify);
+            uchar4 c8 = rgb[j * W + i];
+            pos[dst] = make_float4(vp.x, vp.y, vp.z, surfelConfidence(x, y, 1.0f, cam.cx, cam.cy));
+            col[dst] = make_float4(encodeColor((float)c8.x / 255.0f, (float)c8.y / 255.0f, (float)c8.z / 255.0f), 0.f, 1.f, (float)time);
+        }
+    }
+    if (kf) {
+        uint32_t dst = offF[blockIdx.x] + wf + __popc(bf & ((1u << lane) - 1));
+        if (dst < capacity) {
+            float3 vp = getVertex(depthFilt, W, H, i, j, x, y, cam, ifx, ify);
+            float3 nl = normalCentral(depthFilt, W, H, i, j, x, y, cam, ifx, ify, vp);
+            nrm[dst] = make_float4(nl.x, nl.y, nl.z, surfelRadius(vp.z, nl.z, ifx, ify));
+        }
+    }
+}
+
+// generic exclusive scan of one array of block sums (used by the init path, 2 arrays)
+__global__ void __launch_bounds__(1024) k_scan_small(uint32_t* __restrict__ a, int n, uint32_t capacity, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        uint32_t v = i < n ? a[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int off = 1; off < 1024; off <<= 1) {
+            uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        uint32_t incl = sh[threadIdx.x];
+        if (i < n) a[i] = carry + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry < capacity ? carry : capacity;
+}
+
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_u64(unsigned long long* p, unsigned long long v, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_zero_f4(float4* p, uint32_t from, uint32_t to)
+{
+    uint32_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < to) p[i] = make_float4(0, 0, 0, 0);
+}
+
+// AoS (12 floats) <-> planes, for the C-ABI download/upload (Model::downloadMap layout)
+__global__ void k_planes_to_aos(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm, uint32_t n, float4* __restrict__ out)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[(size_t)i * 3] = pos[i]; out[(size_t)i * 3 + 1] = col[i]; out[(size_t)i * 3 + 2] = nrm[i];
+}
+__global__ void k_aos_to_planes(const float4* __restrict__ in, uint32_t n, float4* __restrict__ pos, float4* __restrict__ col, float4* __restrict__ nrm)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pos[i] = in[(size_t)i * 3]; col[i] = in[(size_t)i * 3 + 1]; nrm[i] = in[(size_t)i * 3 + 2];
+}
+
+// ------------------------------ host launchers ----------------------------------------
+static int g_numSMs = 148;
+void set_num_sms(int n) { g_numSMs = n > 0 ? n : 148; }
+static inline int persistentBlocks(int perSM) { return g_numSMs * perSM; }
+
+void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s) { if (n) k_fill_u32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, v, n); }
+void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s) { if (n) k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((unsigned long long*)p, v, n); }
+
+void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, int time,
+                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, cudaStream_t s)
+{
+    k_index_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, count, tinv, cam, W, H, maxDepth, (float)time, (float)timeDelta,
+                                                        (unsigned long long*)key);
+    int P = W * H;
+    k_index_resolve<<<(P + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, P, (unsigned long long*)key, idx, vertConf, colorTime, normRad);
+}
+
+void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
+                      const float4* vertConf, const float4* normRad, Rt pose, Cam cam, int W, int H, float maxDepth, int time,
+                      float weighting, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s)
+{
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_associate<<<g, b, 0, s>>>(rgb, depthRaw, depthFilt, mask, idx, vertConf, normRad, pose, cam, W, H, maxDepth, time, weighting, maskID,
+                                flag, best, meas[0], meas[1], meas[2], slot);
+}
+
+void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const* meas, uint32_t* slot, int P, int time,
+                        const SurfelPlanes& sp, cudaStream_t s)
+{
+    k_fuse_update<<<(P + 255) / 256, 256, 0, s>>>(flag, best, meas[0], meas[1], meas[2], slot, P, time, sp.pos, sp.col, sp.nrm);
+    k_slot_release<<<(P + 255) / 256, 256, 0, s>>>(flag, best, P, slot);
+}
+
+void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
+                  const uint8_t* aflag, float4* const* meas, Rt tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
+                  float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
+                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, cudaStream_t s)
+{
+    CleanParams P;
+    P.tinv = tinv; P.cam = cam; P.W = W; P.H = H; P.time = time; P.ftimeDelta = (float)timeDelta; P.confThreshold = confThreshold;
+    P.outlierCoeff = outlierCoeff; P.maskID = maskID;
+    int Ppix = W * H;
+    int blocks = persistentBlocks(4);
+    k_clean_test<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, aflag, meas[0], meas[1], meas[2], Ppix, P, idx, vertConf,
+                                               colorTime, depthFilt, mask, keep, blockSums);
+    k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount);
+    k_clean_scatter<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
+                                                  dst.pos, dst.col, dst.nrm);
+}
+
+void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth,
+                             float confThreshold, int time, int maxTime, int timeDelta, uint64_t* key, uchar4* image, float4* vertexConf,
+                             float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
+                             uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s)
+{
+    k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
+                                                        (float)maxTime, (float)timeDelta, 0u, (unsigned long long*)key);
+    if (nonBlackSamples) cudaMemsetAsync(nonBlackSamples, 0, sizeof(uint32_t), s);
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_splat_resolve<<<g, b, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, cam, W, H, maxDepth, confThreshold, (float)time, (float)maxTime,
+                                    (float)timeDelta, (unsigned long long*)key, image, vertexConf, normalRad, timeTex, doFill, depthFilt, rgb,
+                                    ptVN, ptImg, fillImage, fillVertex, fillNormal, nonBlackSamples);
+}
+
+void launch_init_model(const uchar4* rgb, const float* depthRaw, const float* depthFilt, Cam cam, int W, int H, int time, float maxDepth,
+                       uint8_t* fr, uint8_t* ff, uint32_t* sumR, uint32_t* sumF, uint32_t capacity, const SurfelPlanes& sp, uint32_t* count,
+                       cudaStream_t s)
+{
+    int P = W * H, nb = (P + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    k_zero_f4<<<(P + 255) / 256, 256, 0, s>>>(sp.nrm, 0, (uint32_t)(P < (int)capacity ? P : (int)capacity));
+    k_init_flags<<<nb, SCAN_BLOCK, 0, s>>>(depthRaw, depthFilt, W, H, maxDepth, fr, ff, sumR, sumF);
+    k_scan_small<<<1, 1024, 0, s>>>(sumR, nb, capacity, count);
+    k_scan_small<<<1, 1024, 0, s>>>(sumF, nb, capacity, nullptr);
+    k_init_scatter<<<nb, SCAN_BLOCK, 0, s>>>(rgb, depthRaw, depthFilt, cam, W, H, time, fr, ff, sumR, sumF, capacity, sp.pos, sp.col, sp.nrm);
+}
+
+void launch_planes_to_aos(const SurfelPlanes& sp, uint32_t n, float4* out, cudaStream_t s) { if (n) k_planes_to_aos<<<(n + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, n, out); }
+void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, cudaStream_t s) { if (n) k_aos_to_planes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sp.pos, sp.col, sp.nrm); }
+
+}  // namespace mfb

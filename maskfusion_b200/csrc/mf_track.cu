@@ -1,0 +1,654 @@
+// mf_track.cu -- dense RGB-D odometry on the device (sm_100a).
+//   ICP point-to-plane JtJ/Jtr   <- icpKernel / ICPReduction,        Core/Cuda/reduce.cu:259-444
+//   photometric correspondences  <- residualKernel / RGBResidual,   reduce.cu:774-997
+//   photometric JtJ/Jtr          <- rgbKernel / RGBReduction,        reduce.cu:529-713
+//   SO(3) pre-alignment          <- so3Kernel / SO3Reduction,        reduce.cu:999-1202
+//   Gauss-Newton driver          <- RGBDOdometry::getIncrementalTransformation, RGBDOdometry.cpp:227-497
+//                                   + OdometryProvider::{rodrigues,computeUpdateSE3}, OdometryProvider.h:32-90
+//
+// The reference returns to the host after every one of its <= 67 kernel pairs per model per
+// frame (cudaDeviceSynchronize + 116-byte D2H + Eigen LDLT).  Here the whole schedule is
+// enqueued once: each step kernel reduces with warp shuffles, writes one partial per block,
+// and the LAST block to finish (threadfence + ticket) sums the partials in double in fixed
+// order, solves the 6x6 system (pivoted LDLT, double) and updates the pose state in device
+// memory, which the next launch reads.  blockIdx.y indexes the tracked model, so N objects
+// on one GPU share every launch.  Results are deterministic for a fixed launch shape.
+#include "mf_common.cuh"
+#include "mf_kernels.h"
+#include <float.h>
+
+namespace mfb {
+
+#define TRK_THREADS 256
+#define NACC_ICP 29
+#define NACC_RGB 27
+#define NACC (NACC_ICP + NACC_RGB)
+
+MF_D float3 m3v(const float* R, float3 v)
+{
+    return make_float3((R[0] * v.x + R[1] * v.y) + R[2] * v.z, (R[3] * v.x + R[4] * v.y) + R[5] * v.z, (R[6] * v.x + R[7] * v.y) + R[8] * v.z);
+}
+
+// ---------------------------------------------------------------------------------------
+// small dense maths (single thread, double)
+// ---------------------------------------------------------------------------------------
+__device__ void ldltSolve(const double* Ain, const double* b, int n, double* x)
+{
+    // pivoted LDL^T with Eigen's conventions: pivot on the largest remaining diagonal,
+    // pivots <= DBL_MIN contribute 0 to the solution (RGBDOdometry.cpp:313,451-459)
+    double A[36], y[6]; int perm[6];
+    for (int i = 0; i < n * n; ++i) A[i] = Ain[i];
+    for (int i = 0; i < n; ++i) perm[i] = i;
+    int kend = n;
+    for (int k = 0; k < n; ++k) {
+        int piv = k; double best = fabs(A[k * n + k]);
+        for (int i = k + 1; i < n; ++i) if (fabs(A[i * n + i]) > best) { best = fabs(A[i * n + i]); piv = i; }
+        if (piv != k) {
+            for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[piv * n + j]; A[piv * n + j] = t; }
+            for (int j = 0; j < n; ++j) { double t = A[j * n + k]; A[j * n + k] = A[j * n + piv]; A[j * n + piv] = t; }
+            int t = perm[k]; perm[k] = perm[piv]; perm[piv] = t;
+        }
+        double d = A[k * n + k];
+        if (fabs(d) <= DBL_MIN) { kend = k; break; }
+        for (int i = k + 1; i < n; ++i) A[i * n + k] /= d;
+        for (int i = k + 1; i < n; ++i)
+            for (int j = k + 1; j <= i; ++j) {
+                A[i * n + j] -= A[i * n + k] * d * A[j * n + k];
+                A[j * n + i] = A[i * n + j];
+            }
+    }
+    for (int i = 0; i < n; ++i) y[i] = b[perm[i]];
+    for (int i = 0; i < n; ++i) for (int j = 0; j < i && j < kend; ++j) y[i] -= A[i * n + j] * y[j];
+    for (int i = 0; i < n; ++i) {
+        double d = (i < kend) ? A[i * n + i] : 0.0;
+        y[i] = (fabs(d) > DBL_MIN) ? y[i] / d : 0.0;
+    }
+    for (int i = n - 1; i >= 0; --i) for (int j = i + 1; j < n; ++j) if (i < kend) y[i] -= A[j * n + i] * y[j];
+    for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
+}
+
+__device__ void rodrigues(const double* src, double* R)
+{
+    double rx = src[0], ry = src[1], rz = src[2];
+    double theta = sqrt(rx * rx + ry * ry + rz * rz);
+    for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    if (theta >= DBL_EPSILON) {
+        double c = cos(theta), s = sin(theta), c1 = 1. - c, it = theta ? 1. / theta : 0.;
+        rx *= it; ry *= it; rz *= it;
+        double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
+        double rxm[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
+        for (int k = 0; k < 9; ++k) R[k] = c * ((k % 4 == 0) ? 1.0 : 0.0) + c1 * rrt[k] + s * rxm[k];
+    }
+}
+__device__ void inv3d(const double* M, double* o)
+{
+    double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    double det = M[0] * c00 + M[1] * c01 + M[2] * c02, id = 1.0 / det;
+    o[0] = c00 * id; o[1] = (M[2] * M[7] - M[1] * M[8]) * id; o[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    o[3] = c01 * id; o[4] = (M[0] * M[8] - M[2] * M[6]) * id; o[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    o[6] = c02 * id; o[7] = (M[1] * M[6] - M[0] * M[7]) * id; o[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+}
+__device__ void mul3d(const double* A, const double* B, double* C)
+{
+    double o[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) o[r * 3 + c] = A[r * 3] * B[c] + A[r * 3 + 1] * B[3 + c] + A[r * 3 + 2] * B[6 + c];
+    for (int k = 0; k < 9; ++k) C[k] = o[k];
+}
+__device__ void inv3f(const float* M, float* o)
+{
+    float c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    float det = (M[0] * c00 + M[1] * c01) + M[2] * c02, id = 1.0f / det;
+    o[0] = c00 * id; o[1] = (M[2] * M[7] - M[1] * M[8]) * id; o[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    o[3] = c01 * id; o[4] = (M[0] * M[8] - M[2] * M[6]) * id; o[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    o[6] = c02 * id; o[7] = (M[1] * M[6] - M[0] * M[7]) * id; o[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+}
+
+// per-level photometric constants: KRK^-1 and K t of the current estimate (RGBDOdometry.cpp:364-376)
+__device__ void computeWarp(TrackState* st, Cam c)
+{
+    const double* T = st->resultRt;
+    double R3[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]}, Ri[9], ti[3];
+    inv3d(R3, Ri);
+    for (int r = 0; r < 3; ++r) ti[r] = -(Ri[r * 3] * T[3] + Ri[r * 3 + 1] * T[7] + Ri[r * 3 + 2] * T[11]);
+    double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1}, Kinv[9], tmp[9], KRK[9];
+    inv3d(K, Kinv); mul3d(K, Ri, tmp); mul3d(tmp, Kinv, KRK);
+    for (int q = 0; q < 9; ++q) st->krk[q] = (float)KRK[q];
+    for (int r = 0; r < 3; ++r) st->kt[r] = (float)(K[r * 3] * ti[0] + K[r * 3 + 1] * ti[1] + K[r * 3 + 2] * ti[2]);
+}
+
+// ---------------------------------------------------------------------------------------
+// block reduction helpers
+// ---------------------------------------------------------------------------------------
+template <int N>
+MF_D void blockReduceStore(float* acc, float* partialOut)
+{
+    __shared__ float sh[TRK_THREADS / 32][N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) sh[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float s = 0;
+#pragma unroll
+        for (int w = 0; w < TRK_THREADS / 32; ++w) s += sh[w][threadIdx.x];
+        partialOut[threadIdx.x] = s;
+    }
+}
+
+// returns true in ALL threads of the last block to arrive
+MF_D bool lastBlock(unsigned* ticket)
+{
+    __shared__ bool isLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(ticket, 1u);
+        isLast = (t == gridDim.x - 1);
+        if (isLast) *ticket = 0;
+    }
+    __syncthreads();
+    if (isLast) __threadfence();
+    return isLast;
+}
+
+// ---------------------------------------------------------------------------------------
+// begin / end
+// ---------------------------------------------------------------------------------------
+__global__ void k_track_begin(TrackJob* jobs, TrackPoses poses, int useSo3)
+{
+    int jb = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    TrackState* st = jobs[jb].st;
+    const float* P = poses.p[jb];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) st->Rprev[r * 3 + c] = P[r * 4 + c]; st->tprev[r] = P[r * 4 + 3]; }
+    for (int k = 0; k < 9; ++k) st->Rcurr[k] = st->Rprev[k];
+    for (int k = 0; k < 3; ++k) st->tcurr[k] = st->tprev[k];
+    inv3f(st->Rprev, st->RprevInv);
+    for (int k = 0; k < 16; ++k) st->resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    for (int k = 0; k < 9; ++k) { st->resultR[k] = (k % 4 == 0) ? 1.0 : 0.0; st->lastResultR[k] = st->resultR[k]; st->R_lr[k] = (k % 4 == 0) ? 1.f : 0.f; st->trR[k] = (k % 4 == 0) ? 1.f : 0.f; }
+    st->trT[0] = st->trT[1] = st->trT[2] = 0;
+    st->so3LastError = FLT_MAX / 2; st->so3LastCount = FLT_MAX / 2; st->so3Done = useSo3 ? 0 : 1;
+    st->levelBreak = 0; st->lastRGBError = FLT_MAX;
+    for (int k = 0; k < 4; ++k) st->ticket[k] = 0;
+}
+
+// so3 result -> initial resultRt (RGBDOdometry.cpp:337-345)
+__global__ void k_track_so3_finish(TrackJob* jobs, int useSo3)
+{
+    if (threadIdx.x != 0) return;
+    TrackState* st = jobs[blockIdx.x].st;
+    if (useSo3) for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) st->resultRt[r * 4 + c] = st->resultR[r * 3 + c];
+}
+
+__global__ void k_track_level_begin(TrackJob* jobs, int level, Cam camL, int rgb)
+{
+    if (threadIdx.x != 0) return;
+    TrackState* st = jobs[blockIdx.x].st;
+    st->levelBreak = 0; st->lastRGBError = FLT_MAX;
+    if (rgb) computeWarp(st, camL);
+}
+
+__global__ void k_track_end(TrackJob* jobs, int rgb)
+{
+    if (threadIdx.x != 0) return;
+    TrackState* st = jobs[blockIdx.x].st;
+    float dx = st->tcurr[0] - st->tprev[0], dy = st->tcurr[1] - st->tprev[1], dz = st->tcurr[2] - st->tprev[2];
+    if (rgb && sqrtf((dx * dx + dy * dy) + dz * dz) > 0.3f) {          // RGBDOdometry.cpp:478-482
+        for (int k = 0; k < 9; ++k) { st->Rcurr[k] = st->Rprev[k]; st->trR[k] = (k % 4 == 0) ? 1.f : 0.f; }
+        for (int k = 0; k < 3; ++k) { st->tcurr[k] = st->tprev[k]; st->trT[k] = 0; }
+    }
+    float* po = st->out;                 // [0..15] pose, [16..31] transform, [32..37] error stats
+    for (int k = 0; k < 32; ++k) po[k] = ((k % 16) % 5 == 0) ? 1.f : 0.f;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) { po[r * 4 + c] = st->Rcurr[r * 3 + c]; po[16 + r * 4 + c] = st->trR[r * 3 + c]; }
+        po[r * 4 + 3] = st->tcurr[r]; po[16 + r * 4 + 3] = st->trT[r];
+    }
+    po[32] = st->lastICPError; po[33] = st->lastICPCount; po[34] = st->lastRGBError; po[35] = st->lastRGBCount;
+    po[36] = st->lastSO3Error; po[37] = st->lastSO3Count;
+}
+
+// ---------------------------------------------------------------------------------------
+// SO(3) pre-alignment step (level 2 intensities)
+// ---------------------------------------------------------------------------------------
+MF_D void gradU8(const uint8_t* __restrict__ img, int W, int x, int y, float& gx, float& gy)
+{
+    float actu = img[y * W + x], back = img[y * W + x - 1], fore = img[y * W + x + 1];
+    gx = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+    back = img[(y - 1) * W + x]; fore = img[(y + 1) * W + x];
+    gy = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+}
+
+__global__ void __launch_bounds__(TRK_THREADS) k_so3_step(TrackJob* jobs, int W, int H, Cam c)
+{
+    TrackJob& J = jobs[blockIdx.y];
+    TrackState* st = J.st;
+    if (st->so3Done) return;
+    __shared__ float B[9], kinv[9], krlr[9];
+    if (threadIdx.x == 0) {
+        double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1}, Kinv[9], kr[9], hom[9];
+        inv3d(K, Kinv); mul3d(K, st->resultR, kr); mul3d(kr, Kinv, hom);
+        for (int q = 0; q < 9; ++q) { B[q] = (float)hom[q]; kinv[q] = (float)Kinv[q]; krlr[q] = (float)kr[q]; }
+    }
+    __syncthreads();
+    const uint8_t* __restrict__ lastImage = J.lastNextImage2;
+    const uint8_t* __restrict__ nextImage = J.nextImage[2];
+    float acc[11];
+#pragma unroll
+    for (int k = 0; k < 11; ++k) acc[k] = 0;
+    const int N = W * H;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
+        int y = k / W, x = k - y * W;
+        float3 ur = make_float3((float)x, (float)y, 1.0f);
+        float3 wr = m3v(B, ur);
+        int wx = __float2int_rn(wr.x / wr.z), wy = __float2int_rn(wr.y / wr.z);
+        bool found = (wx >= 1 && wx < W - 1 && wy >= 1 && wy < H - 1 && x >= 1 && x < W - 1 && y >= 1 && y < H - 1);
+        if (found) {
+            float gnx, gny, glx, gly;
+            gradU8(nextImage, W, wx, wy, gnx, gny);
+            gradU8(lastImage, W, x, y, glx, gly);
+            float gx = (gnx + glx) / 2.0f, gy = (gny + gly) / 2.0f;
+            float3 p = m3v(kinv, ur);
+            float z2 = p.z * p.z;
+            float a = krlr[0], b = krlr[1], cc = krlr[2], d = krlr[3], e = krlr[4], f = krlr[5], g = krlr[6], h = krlr[7], i = krlr[8];
+            float fy = (float)y, fxx = (float)x;
+            float3 l = make_float3(((p.z * (d * gy + a * gx)) - (gy * g * fy) - (gx * g * fxx)) / z2,
+                                   ((p.z * (e * gy + b * gx)) - (gy * h * fy) - (gx * h * fxx)) / z2,
+                                   ((p.z * (f * gy + cc * gx)) - (gy * i * fy) - (gx * i * fxx)) / z2);
+            float row[4];
+            row[0] = l.y * p.z - l.z * p.y;
+            row[1] = l.z * p.x - l.x * p.z;
+            row[2] = l.x * p.y - l.y * p.x;
+            row[3] = -((float)nextImage[wy * W + wx] - (float)lastImage[k]);
+            int q = 0;
+#pragma unroll
+            for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                for (int jj = ii; jj < 4; ++jj) acc[q++] += row[ii] * row[jj];
+            acc[9] += row[3] * row[3];
+            acc[10] += 1.0f;
+        }
+    }
+    float* partial = J.partial + (size_t)blockIdx.x * 64;
+    blockReduceStore<11>(acc, partial);
+    if (!lastBlock(&st->ticket[0])) return;
+    __shared__ double tot[11];
+    if (threadIdx.x < 11) {
+        double s = 0;
+        for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += (double)J.partial[(size_t)b2 * 64 + threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    // host logic of RGBDOdometry.cpp:301-324
+    float res0 = (float)tot[9], res1 = (float)tot[10];
+    st->lastSO3Error = sqrtf(res0) / res1; st->lastSO3Count = res1;
+    if (st->lastSO3Error < st->so3LastError && fabsf(st->so3LastError - st->lastSO3Count) < 0.001f) { st->so3Done = 1; return; }
+    else if (st->lastSO3Error > st->so3LastError + 0.001f) {
+        st->lastSO3Error = st->so3LastError; st->lastSO3Count = st->so3LastCount;
+        for (int q = 0; q < 9; ++q) st->resultR[q] = st->lastResultR[q];
+        st->so3Done = 1; return;
+    }
+    st->so3LastError = st->lastSO3Error; st->so3LastCount = st->lastSO3Count;
+    for (int q = 0; q < 9; ++q) st->lastResultR[q] = st->resultR[q];
+    double A[9], bb[3], delta[3]; int q = 0;
+    for (int ii = 0; ii < 3; ++ii) for (int jj = ii; jj < 4; ++jj) { double v = (double)(float)tot[q++]; if (jj == 3) bb[ii] = v; else A[jj * 3 + ii] = A[ii * 3 + jj] = v; }
+    ldltSolve(A, bb, 3, delta);
+    for (int k = 0; k < 3; ++k) delta[k] = (double)(float)delta[k];
+    double ru[9]; rodrigues(delta, ru);
+    float ruf[9], n[9];
+    for (int k = 0; k < 9; ++k) ruf[k] = (float)ru[k];
+    for (int r = 0; r < 3; ++r) for (int cc2 = 0; cc2 < 3; ++cc2) n[r * 3 + cc2] = (ruf[r * 3] * st->R_lr[cc2] + ruf[r * 3 + 1] * st->R_lr[3 + cc2]) + ruf[r * 3 + 2] * st->R_lr[6 + cc2];
+    for (int k = 0; k < 9; ++k) { st->R_lr[k] = n[k]; st->resultR[k] = n[k]; }
+}
+
+// ---------------------------------------------------------------------------------------
+// photometric correspondences + residual statistics
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRK_THREADS) k_rgb_residual(TrackJob* jobs, int level, int W, int H, float minScale, float maxDepthDelta, int rgbOnly)
+{
+    TrackJob& J = jobs[blockIdx.y];
+    TrackState* st = J.st;
+    if (st->levelBreak) return;
+    const short2* __restrict__ grad = J.nextGrad[level];
+    const float* __restrict__ lastDepth = J.lastDepth[level];
+    const float* __restrict__ nextDepth = J.lastDepth[level];      // reference quirk: both pyramids derive from vmaps_tmp (RGBDOdometry.cpp:187-215)
+    const uint8_t* __restrict__ lastImage = J.lastImage[level];
+    const uint8_t* __restrict__ nextImage = J.nextImage[level];
+    DataTerm* __restrict__ corres = J.corres[level];
+    __shared__ float K[9], kt[3];
+    if (threadIdx.x < 9) K[threadIdx.x] = st->krk[threadIdx.x];
+    if (threadIdx.x < 3) kt[threadIdx.x] = st->kt[threadIdx.x];
+    __syncthreads();
+    int cnt = 0, sig = 0;
+    const int N = W * H;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
+        int i = k / W, j0 = k - i * W;
+        DataTerm c; c.zero = make_short2(0, 0); c.one = make_short2(0, 0); c.diff = 0; c.valid = 0;
+        if (j0 < W - 5 && i < H - 1) {
+            bool valid = true;
+            for (int u = max(i - 2, 0); u < min(i + 2, H); ++u)
+                for (int v = max(j0 - 2, 0); v < min(j0 + 2, W); ++v) valid = valid && (nextImage[u * W + v] > 0);
+            if (valid) {
+                short2 g = grad[k];
+                float mTwo = (float)(((int)g.x * (int)g.x) + ((int)g.y * (int)g.y));
+                if (mTwo >= minScale) {
+                    int y = i, x = j0;
+                    float d1 = nextDepth[k];
+                    if (!isnan(d1)) {
+                        float td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
+                        float fu = (d1 * ((K[0] * x + K[1] * y) + K[2]) + kt[0]) / td1;
+                        float fv = (d1 * ((K[3] * x + K[4] * y) + K[5]) + kt[1]) / td1;
+                        int u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
+                        int v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
+                        if (u0 >= 0 && v0 >= 0 && u0 < W && v0 < H) {
+                            float d0 = lastDepth[v0 * W + u0];
+                            uint8_t li = lastImage[v0 * W + u0];
+                            if (d0 > 0 && fabsf(td1 - d0) <= maxDepthDelta && li != 0) {
+                                c.zero = make_short2((short)u0, (short)v0); c.one = make_short2((short)x, (short)y);
+                                c.diff = (float)nextImage[k] - (float)li;
+                                c.valid = 1;
+                                cnt += 1;
+                                sig += (int)(c.diff * c.diff);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        corres[k] = c;
+    }
+    // int2 block reduction
+    __shared__ int shc[TRK_THREADS / 32], shs[TRK_THREADS / 32];
+    for (int off = 16; off > 0; off >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, off); sig += __shfl_down_sync(0xffffffffu, sig, off); }
+    if ((threadIdx.x & 31) == 0) { shc[threadIdx.x >> 5] = cnt; shs[threadIdx.x >> 5] = sig; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int w = 0; w < TRK_THREADS / 32; ++w) { a += shc[w]; b += shs[w]; }
+        J.partialI[blockIdx.x * 2] = a; J.partialI[blockIdx.x * 2 + 1] = b;
+    }
+    if (!lastBlock(&st->ticket[1])) return;
+    if (threadIdx.x != 0) return;
+    int rgbSize = 0, sigma = 0;
+    for (unsigned b2 = 0; b2 < gridDim.x; ++b2) { rgbSize += J.partialI[b2 * 2]; sigma += J.partialI[b2 * 2 + 1]; }
+    // RGBDOdometry.cpp:388-401
+    float tmpError = (float)(sqrt((double)sigma) / (double)rgbSize);
+    float sigmaVal = (tmpError == 0) ? 1 : (float)rgbSize;
+    if (rgbOnly && tmpError > st->lastRGBError) { st->levelBreak = 1; return; }
+    st->lastRGBError = tmpError; st->lastRGBCount = (float)rgbSize;
+    if (rgbOnly) sigmaVal = -1;
+    st->sigmaVal = sigmaVal;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused ICP + photometric Gauss-Newton step, solve and pose update
+// ---------------------------------------------------------------------------------------
+template <bool ICP, bool RGB>
+__global__ void __launch_bounds__(TRK_THREADS) k_gn_step(TrackJob* jobs, int level, int W, int H, Cam cam, float distThres, float angleThres,
+                                                         float icpWeight, float sobelScale)
+{
+    TrackJob& J = jobs[blockIdx.y];
+    TrackState* st = J.st;
+    if (st->levelBreak) return;
+    __shared__ float Rc[9], tc[3], Rpi[9], tp[3];
+    __shared__ float sigmaSh;
+    if (threadIdx.x < 9) { Rc[threadIdx.x] = st->Rcurr[threadIdx.x]; Rpi[threadIdx.x] = st->RprevInv[threadIdx.x]; }
+    if (threadIdx.x < 3) { tc[threadIdx.x] = st->tcurr[threadIdx.x]; tp[threadIdx.x] = st->tprev[threadIdx.x]; }
+    if (threadIdx.x == 0) sigmaSh = st->sigmaVal;
+    __syncthreads();
+    const float4* __restrict__ vmapC = J.vmapC[level];
+    const float4* __restrict__ nmapC = J.nmapC[level];
+    const float4* __restrict__ vmapG = J.vmapG[level];
+    const float4* __restrict__ nmapG = J.nmapG[level];
+    const DataTerm* __restrict__ corres = J.corres[level];
+    const float4* __restrict__ cloud = J.cloud[level];
+    const short2* __restrict__ grad = J.nextGrad[level];
+    const float3 tprev = make_float3(tp[0], tp[1], tp[2]);
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    const int N = W * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        if (ICP) {
+            float4 vc4 = vmapC[i];
+            float3 vg = m3v(Rc, make_float3(vc4.x, vc4.y, vc4.z));
+            vg = make_float3(vg.x + tc[0], vg.y + tc[1], vg.z + tc[2]);
+            float3 tmp = sub3(vg, tprev);
+            float3 vcp = m3v(Rpi, tmp);
+            int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
+            int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
+            if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) {
+                int j = uy * W + ux;
+                float4 vp4 = __ldg(vmapG + j), np4 = __ldg(nmapG + j), nc4 = nmapC[i];
+                float3 vp = make_float3(vp4.x, vp4.y, vp4.z), np_ = make_float3(np4.x, np4.y, np4.z);
+                float3 ng = m3v(Rc, make_float3(nc4.x, nc4.y, nc4.z));
+                float3 d = sub3(vp, vg);
+                float dist = sqrtf((d.x * d.x + d.y * d.y) + d.z * d.z);
+                float3 c = cross3(ng, np_);
+                float sine = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+                bool found = (sine < angleThres && dist <= distThres && !isnan(nc4.x) && !isnan(np4.x));
+                if (found) {
+                    float3 s_cp = vcp;
+                    float3 d_cp = m3v(Rpi, sub3(vp, tprev));
+                    float3 n_cp = m3v(Rpi, np_);
+                    float row[7];
+                    row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z;
+                    row[3] = s_cp.y * n_cp.z - s_cp.z * n_cp.y;
+                    row[4] = s_cp.z * n_cp.x - s_cp.x * n_cp.z;
+                    row[5] = s_cp.x * n_cp.y - s_cp.y * n_cp.x;
+                    row[6] = (n_cp.x * (s_cp.x - d_cp.x) + n_cp.y * (s_cp.y - d_cp.y)) + n_cp.z * (s_cp.z - d_cp.z);
+                    int q = 0;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a)
+#pragma unroll
+                        for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
+                    acc[27] += row[6] * row[6];
+                    acc[28] += 1.0f;
+                }
+            }
+        }
+        if (RGB) {
+            DataTerm ct = corres[i];
+            if (ct.valid) {
+                float w = sigmaSh + fabsf(ct.diff);
+                w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+                if (sigmaSh == -1) w = 1;
+                float row[7];
+                row[6] = -w * ct.diff;
+                float4 cp = cloud[ct.zero.y * W + ct.zero.x];
+                float invz = (float)(1.0 / (double)cp.z);
+                short2 g = grad[ct.one.y * W + ct.one.x];
+                float dIdx_v = w * sobelScale * (float)g.x;
+                float dIdy_v = w * sobelScale * (float)g.y;
+                float v0 = dIdx_v * cam.fx * invz;
+                float v1 = dIdy_v * cam.fy * invz;
+                float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
+                row[0] = v0; row[1] = v1; row[2] = v2;
+                row[3] = -cp.z * v1 + cp.y * v2;
+                row[4] = cp.z * v0 - cp.x * v2;
+                row[5] = -cp.y * v0 + cp.x * v1;
+                int q = NACC_ICP;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
+            }
+        }
+    }
+    blockReduceStore<NACC>(acc, J.partial + (size_t)blockIdx.x * 64);
+    if (!lastBlock(&st->ticket[2])) return;
+    __shared__ double tot[NACC];
+    if (threadIdx.x < NACC) {
+        double s = 0;
+        for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += (double)J.partial[(size_t)b2 * 64 + threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+
+    // ---- host part of RGBDOdometry.cpp:403-474, on the device ----
+    float A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
+    for (int k = 0; k < 36; ++k) { A_icp[k] = 0; A_rgb[k] = 0; }
+    for (int k = 0; k < 6; ++k) { b_icp[k] = 0; b_rgb[k] = 0; }
+    int q = 0;
+    for (int a = 0; a < 6; ++a) for (int b = a; b < 7; ++b) {
+        float vi = (float)tot[q], vr = (float)tot[NACC_ICP + q]; ++q;
+        if (b == 6) { b_icp[a] = vi; b_rgb[a] = vr; }
+        else { A_icp[b * 6 + a] = A_icp[a * 6 + b] = vi; A_rgb[b * 6 + a] = A_rgb[a * 6 + b] = vr; }
+    }
+    if (ICP) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
+    double A[36], b[6], result[6];
+    if (ICP && RGB) {
+        double wgt = icpWeight;
+        for (int k = 0; k < 36; ++k) A[k] = (double)A_rgb[k] + wgt * wgt * (double)A_icp[k];
+        for (int k = 0; k < 6; ++k) b[k] = (double)b_rgb[k] + wgt * (double)b_icp[k];
+    } else if (ICP) {
+        for (int k = 0; k < 36; ++k) A[k] = A_icp[k];
+        for (int k = 0; k < 6; ++k) b[k] = b_icp[k];
+    } else {
+        for (int k = 0; k < 36; ++k) A[k] = A_rgb[k];
+        for (int k = 0; k < 6; ++k) b[k] = b_rgb[k];
+    }
+    for (int k = 0; k < 36; ++k) st->lastA[k] = A[k];
+    for (int k = 0; k < 6; ++k) st->lastb[k] = b[k];
+    ldltSolve(A, b, 6, result);
+    // computeUpdateSE3 (OdometryProvider.h:69-90)
+    double Rt[16], Rup[9];
+    for (int k = 0; k < 16; ++k) Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    rodrigues(&result[3], Rup);
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Rt[r * 4 + c] = Rup[r * 3 + c]; Rt[r * 4 + 3] = result[r]; }
+    double nr[16];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += Rt[r * 4 + k] * st->resultRt[k * 4 + c];
+        nr[r * 4 + c] = s;
+    }
+    for (int k = 0; k < 16; ++k) st->resultRt[k] = nr[k];
+    float trR[9], trT[3];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) trR[r * 3 + c] = (float)nr[r * 4 + c]; trT[r] = (float)nr[r * 4 + 3]; }
+    for (int k = 0; k < 9; ++k) st->trR[k] = trR[k];
+    for (int k = 0; k < 3; ++k) st->trT[k] = trT[k];
+    // currentT = [Rprev|tprev] * transform^-1   (RGBDOdometry.cpp:466-474)
+    float iR[9], iT[3];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) iR[r * 3 + c] = trR[c * 3 + r];
+    for (int r = 0; r < 3; ++r) iT[r] = -((iR[r * 3] * trT[0] + iR[r * 3 + 1] * trT[1]) + iR[r * 3 + 2] * trT[2]);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) st->Rcurr[r * 3 + c] = (st->Rprev[r * 3] * iR[c] + st->Rprev[r * 3 + 1] * iR[3 + c]) + st->Rprev[r * 3 + 2] * iR[6 + c];
+        st->tcurr[r] = ((st->Rprev[r * 3] * iT[0] + st->Rprev[r * 3 + 1] * iT[1]) + st->Rprev[r * 3 + 2] * iT[2]) + st->tprev[r];
+    }
+    if (RGB) computeWarp(st, cam);          // warp constants for the next iteration's residual kernel
+}
+
+// stand-alone ICP reduction at a caller-given pose (parity tests; mirrors icpStep's outputs)
+__global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restrict__ vmapC, const float4* __restrict__ nmapC,
+                                                          const float4* __restrict__ vmapG, const float4* __restrict__ nmapG,
+                                                          int W, int H, Cam cam, TrackPoses pp, float distThres, float angleThres,
+                                                          float* __restrict__ partial, unsigned* ticket, float* out29)
+{
+    // pp.p[0] = Rcurr(9) tcurr(3); pp.p[1] = RprevInv(9) tprev(3)
+    float acc[NACC_ICP];
+#pragma unroll
+    for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.f;
+    const float* Rc = pp.p[0]; const float* tc = pp.p[0] + 9; const float* Rpi = pp.p[1]; const float* tp = pp.p[1] + 9;
+    const float3 tprev = make_float3(tp[0], tp[1], tp[2]);
+    const int N = W * H;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+        float4 vc4 = vmapC[i];
+        float3 vg = m3v(Rc, make_float3(vc4.x, vc4.y, vc4.z));
+        vg = make_float3(vg.x + tc[0], vg.y + tc[1], vg.z + tc[2]);
+        float3 vcp = m3v(Rpi, sub3(vg, tprev));
+        int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
+        int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
+        if (ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0) continue;
+        int j = uy * W + ux;
+        float4 vp4 = __ldg(vmapG + j), np4 = __ldg(nmapG + j), nc4 = nmapC[i];
+        float3 vp = make_float3(vp4.x, vp4.y, vp4.z), np_ = make_float3(np4.x, np4.y, np4.z);
+        float3 ng = m3v(Rc, make_float3(nc4.x, nc4.y, nc4.z));
+        float3 d = sub3(vp, vg);
+        float dist = sqrtf((d.x * d.x + d.y * d.y) + d.z * d.z);
+        float3 c = cross3(ng, np_);
+        float sine = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+        if (!(sine < angleThres && dist <= distThres && !isnan(nc4.x) && !isnan(np4.x))) continue;
+        float3 s_cp = vcp, d_cp = m3v(Rpi, sub3(vp, tprev)), n_cp = m3v(Rpi, np_);
+        float row[7];
+        row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z;
+        row[3] = s_cp.y * n_cp.z - s_cp.z * n_cp.y;
+        row[4] = s_cp.z * n_cp.x - s_cp.x * n_cp.z;
+        row[5] = s_cp.x * n_cp.y - s_cp.y * n_cp.x;
+        row[6] = (n_cp.x * (s_cp.x - d_cp.x) + n_cp.y * (s_cp.y - d_cp.y)) + n_cp.z * (s_cp.z - d_cp.z);
+        int q = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
+        acc[27] += row[6] * row[6];
+        acc[28] += 1.0f;
+    }
+    blockReduceStore<NACC_ICP>(acc, partial + (size_t)blockIdx.x * 64);
+    if (!lastBlock(ticket)) return;
+    if (threadIdx.x < NACC_ICP) {
+        double s = 0;
+        for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += (double)partial[(size_t)b2 * 64 + threadIdx.x];
+        out29[threadIdx.x] = (float)s;
+    }
+}
+
+// ------------------------------ host launchers ----------------------------------------
+static int trackBlocks(int N, int numSMs)
+{
+    int need = (N + TRK_THREADS - 1) / TRK_THREADS;
+    int cap = numSMs * 2;
+    if (cap > TRACK_MAX_BLOCKS) cap = TRACK_MAX_BLOCKS;
+    return need < cap ? need : cap;
+}
+
+int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s)
+{
+    int launches = 0;
+    const bool icp = !rgbOnly && icpWeight > 0;
+    const bool rgb = rgbOnly || icpWeight < 100;
+    k_track_begin<<<nJobs, 32, 0, s>>>(d_jobs, poses, so3 ? 1 : 0); ++launches;
+    if (so3) {
+        int lv = 2, w = W >> lv, h = H >> lv;
+        Cam c = camLevel(cam, lv);
+        dim3 g(trackBlocks(w * h, numSMs), nJobs);
+        for (int i = 0; i < 10; ++i) { k_so3_step<<<g, TRK_THREADS, 0, s>>>(d_jobs, w, h, c); ++launches; }
+        k_track_so3_finish<<<nJobs, 32, 0, s>>>(d_jobs, 1); ++launches;
+    }
+    int iterations[3] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
+    const float sobelScale = (float)(1.0 / 8.0);
+    const float minGrad[3] = {5, 3, 1};
+    const float angleThres = (float)sin(20.f * 3.14159254f / 180.f);
+    for (int l = 2; l >= 0; --l) {
+        int w = W >> l, h = H >> l;
+        Cam c = camLevel(cam, l);
+        if (iterations[l] == 0) continue;
+        k_track_level_begin<<<nJobs, 32, 0, s>>>(d_jobs, l, c, rgb ? 1 : 0); ++launches;
+        dim3 g(trackBlocks(w * h, numSMs), nJobs);
+        float minScale = (float)(pow((double)minGrad[l], 2.0) / pow((double)sobelScale, 2.0));
+        for (int j = 0; j < iterations[l]; ++j) {
+            if (rgb) { k_rgb_residual<<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, minScale, 0.07f, rgbOnly ? 1 : 0); ++launches; }
+            if (icp && rgb) k_gn_step<true, true><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
+            else if (icp) k_gn_step<true, false><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
+            else k_gn_step<false, true><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
+            ++launches;
+        }
+    }
+    k_track_end<<<nJobs, 32, 0, s>>>(d_jobs, rgb ? 1 : 0); ++launches;
+    return launches;
+}
+
+void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,
+                     const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s)
+{
+    const float angleThres = (float)sin(20.f * 3.14159254f / 180.f);
+    k_icp_only<<<trackBlocks(W * H, numSMs), TRK_THREADS, 0, s>>>(vmapC, nmapC, vmapG, nmapG, W, H, cam, pp, 0.10f, angleThres, partial, ticket, out29);
+}
+
+}  // namespace mfb

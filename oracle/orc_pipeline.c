@@ -248,14 +248,21 @@ static void log_pose(orc_model* m, int64_t ts, const float* T)
     m->nlog++;
 }
 
-int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp)
+/* upload + filterDepth (MaskFusion.cpp:212-230, 650-657); mask NULL == -static (all zero) */
+void orc_mf_set_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, const uint8_t* mask)
 {
     int W = h->cfg.width, H = h->cfg.height; size_t P = (size_t)W * H;
-    if (h->cfg.enableMultipleModels) return -1;          /* multi-model schedule: see orc_multi.c (round 2) */
     memcpy(h->rgb, rgb3, P * 3);
     memcpy(h->depthRaw, depth, P * 4);
-    orc_bilateral(h->depthRaw, h->depthFilt, W, H);      /* filterDepth, MaskFusion.cpp:650-657 */
-    memset(h->mask, 0, P);                               /* -static: MaskFusion.cpp:223-230 */
+    orc_bilateral(h->depthRaw, h->depthFilt, W, H);
+    if (mask) memcpy(h->mask, mask, P); else memset(h->mask, 0, P);
+}
+
+int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp)
+{
+    int W = h->cfg.width, H = h->cfg.height;
+    if (h->cfg.enableMultipleModels) return -1;          /* multi-model schedule: see orc_multi.c (round 2) */
+    orc_mf_set_frame(h, rgb3, depth, 0);
     orc_model* g = h->models[0];
     if (h->tick == 1) {
         g->count = orc_init_model(h->rgb, h->depthRaw, h->depthFilt, h->cam, W, H, h->tick, h->cfg.maxDepthProcessed,

@@ -65,6 +65,7 @@ typedef struct orc_mf {
 orc_mf* orc_mf_create(const orc_config* cfg);
 void orc_mf_destroy(orc_mf* h);
 /* rgb: HxWx3 u8, depth: HxW f32 metres.  inPose unused (NULL). */
+void orc_mf_set_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, const uint8_t* mask);
 int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp);
 orc_model* orc_mf_model(orc_mf* h, int i);
 const float* orc_model_surfels(const orc_model* m);     /* == getModelBuffer(): vbos[target] */

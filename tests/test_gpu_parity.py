@@ -1,0 +1,256 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded synthetic inputs.  Integer / index / per-element fp32 outputs must be BIT-EXACT;
+Gauss-Newton reductions (summation order differs) are checked to the tolerances written
+next to each assertion.  Run on the B200 box: pytest -m gpu."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as ol
+from tests.stagewise import OracleStages, mismatch, planar_valid_equal
+
+pytestmark = pytest.mark.gpu
+
+W, H = 640, 480
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+class Report:
+    def __init__(self, name):
+        self.name, self.fail, self.log = name, [], []
+
+    def check(self, what, ok, detail=""):
+        self.log.append(f"{'ok  ' if ok else 'FAIL'} {what} {detail}")
+        if not ok:
+            self.fail.append(f"{what} {detail}")
+
+    def exact(self, what, a, b):
+        n, _ = mismatch(a, b)
+        self.check(what, n == 0, f"mismatches={n}/{np.asarray(a).size}")
+
+    def planar(self, what, a, b):
+        ok, n = planar_valid_equal(a, b)
+        self.check(what, ok, f"mismatches={n}")
+
+    def finish(self):
+        os.makedirs(OUT, exist_ok=True)
+        with open(os.path.join(OUT, f"parity_{self.name}.log"), "w") as f:
+            f.write("\n".join(self.log) + "\n")
+        assert not self.fail, f"{len(self.fail)} parity failures (first 12): " + " | ".join(self.fail[:12])
+
+
+def make_pair(**kw):
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene
+    cap = kw.pop("capacityGlobal", 1200000)
+    ocfg = ol.default_config(W, H, capacityGlobal=cap, **kw)
+    ccfg = mfb.default_config(W, H, capacityGlobal=cap, **kw)
+    return SynthScene(W, H, n_objects=0, seed=0), OracleStages(ocfg), mfb.MaskFusion(ccfg)
+
+
+def run_stagewise(name, nframes, **kw):
+    sc, orc, mf = make_pair(**kw)
+    rep = Report(name)
+    gm = mf.getBackgroundModel()
+    tick = 1
+    pose_err = []
+    for t in range(nframes):
+        rgb, depth, *_ = sc.render(t)
+        orc.set_frame(rgb, depth)
+        orc.tick = tick
+        fa = orc.frame_arrays()
+        if t == 0:
+            mf.setFrame(rgb, depth)
+            rep.exact(f"[{t}] bilateral", mf.filteredDepth(), fa["depthFilt"])
+            orc.init_first(); gm.initialise(tick)
+            # initFirstRGB on the CUDA side happens inside processFrame; stage-wise we replicate via a hidden track-less path:
+            so, sm = orc.p.surfels(0), gm.downloadMap()
+            rep.check(f"[{t}] init count", so.shape[0] == sm.shape[0], f"{so.shape[0]} vs {sm.shape[0]}")
+            if so.shape == sm.shape:
+                rep.exact(f"[{t}] init surfels", sm, so)
+        else:
+            mf.setFrame(rgb, depth)
+            rep.exact(f"[{t}] bilateral", mf.filteredDepth(), fa["depthFilt"])
+            orc.generate_maps()
+            for l in range(3):
+                d, v, n = mf.frameMaps(l)
+                if l > 0:
+                    rep.exact(f"[{t}] depth pyr L{l}", d, fa[f"depth{l}"])
+                rep.planar(f"[{t}] vmap L{l}", v, fa[f"vmap{l}"])
+                rep.planar(f"[{t}] nmap L{l}", n, fa[f"nmap{l}"])
+            orc.track()
+            gm.performTracking()
+            od = orc.odom(0)
+            for l in range(3):
+                v, n = gm.modelMaps(l)
+                rep.planar(f"[{t}] model vmap L{l}", v, ol.arr(od.vmap_g[l], (3, H >> l, W >> l), np.float32))
+                rep.planar(f"[{t}] model nmap L{l}", n, ol.arr(od.nmap_g[l], (3, H >> l, W >> l), np.float32))
+            Po, Pc = orc.pose(0), gm.getPose()
+            dt = float(np.linalg.norm(Po[:3, 3] - Pc[:3, 3])); dR = float(np.abs(Po[:3, :3] - Pc[:3, :3]).max())
+            pose_err.append(dt)
+            # tolerance: fp32 reduction order; 2e-5 m / 2e-5 is > 100x the observed difference, << the 1 mm ATE gate
+            rep.check(f"[{t}] tracked pose", dt < 2e-5 and dR < 2e-5, f"dt={dt:.3e} dR={dR:.3e}")
+            A, b, e = gm.trackStats()
+            Ao = np.array(od.lastA).reshape(6, 6); bo = np.array(od.lastb)
+            relA = float(np.abs(A - Ao).max() / (np.abs(Ao).max() + 1e-30)); relb = float(np.abs(b - bo).max() / (np.abs(bo).max() + 1e-30))
+            rep.check(f"[{t}] last JtJ/Jtr", relA < 1e-3 and relb < 5e-2, f"relA={relA:.2e} relb={relb:.2e}")
+            gm.debugSetPoses(Po, orc.last_pose(0))          # teacher forcing
+            orc.predict_indices(); gm.predictIndices(tick)
+            idx, vc, ct, nr = gm.indexMap()
+            rep.exact(f"[{t}] index map ids", idx, orc.p.tex(0, "idx"))
+            rep.exact(f"[{t}] index vertConf", vc, orc.p.tex(0, "vertConf"))
+            rep.exact(f"[{t}] index colorTime", ct, orc.p.tex(0, "colorTime"))
+            rep.exact(f"[{t}] index normRad", nr, orc.p.tex(0, "normRad"))
+            orc.fuse(); gm.fuse(tick, mf.cfg.depthCutoff, 1.0)
+            flag, best, meas = gm.association()
+            fo, bo_, mo = orc.p.tex(0, "updateId"), orc.p.tex(0, "best"), orc.p.tex(0, "meas")
+            rep.exact(f"[{t}] assoc flags", flag, fo)
+            sel = fo > 0
+            rep.exact(f"[{t}] assoc best", best[fo == 1], bo_[fo == 1])
+            rep.exact(f"[{t}] assoc meas", meas[sel], mo[sel])
+            so, sm = orc.p.surfels(0), gm.downloadMap()
+            rep.check(f"[{t}] fused count", so.shape == sm.shape, f"{so.shape} vs {sm.shape}")
+            if so.shape == sm.shape:
+                rep.exact(f"[{t}] fused surfels", sm, so)
+            orc.predict_indices(); gm.predictIndices(tick)
+            rep.exact(f"[{t}] index map ids (2)", gm.indexMap()[0], orc.p.tex(0, "idx"))
+            orc.clean(); gm.clean(tick)
+            so, sm = orc.p.surfels(0), gm.downloadMap()
+            rep.check(f"[{t}] clean count", so.shape[0] == sm.shape[0], f"{so.shape[0]} vs {sm.shape[0]}")
+            if so.shape == sm.shape:
+                rep.exact(f"[{t}] clean surfels (ordered)", sm, so)
+        orc.predict(); gm.combinedPredict(tick, tick)
+        im, vc, nr, tt = gm.prediction()
+        rep.exact(f"[{t}] splat image", im, orc.p.tex(0, "splatImage"))
+        rep.exact(f"[{t}] splat vertex", vc, orc.p.tex(0, "splatVertex"))
+        rep.exact(f"[{t}] splat normal", nr, orc.p.tex(0, "splatNormal"))
+        rep.exact(f"[{t}] splat time", tt, orc.p.tex(0, "splatTime"))
+        fim, fv, fn = gm.fillIn()
+        rep.exact(f"[{t}] fill image", fim, orc.p.tex(0, "fillImage"))
+        rep.exact(f"[{t}] fill vertex", fv, orc.p.tex(0, "fillVertex"))
+        rep.exact(f"[{t}] fill normal", fn, orc.p.tex(0, "fillNormal"))
+        if t == 0:
+            # CUDA-side initFirstRGB equivalent for the stage-wise driver: run a real processFrame on a twin? Not needed:
+            # so3 is exercised by the free-running sequence test; stage-wise runs use so3 only after frame 0 via processFrame state.
+            pass
+        tick += 1
+    rep.log.append("pose errors vs oracle (m): " + json.dumps(pose_err))
+    mf.close()
+    rep.finish()
+
+
+def test_stagewise_icp_only():
+    """-static, ICP-only tracking (icpWeight=100 => rgb=false, RGBDOdometry.cpp:236-237), no SO3"""
+    run_stagewise("stagewise_icp", 6, icpWeight=100.0, so3=0)
+
+
+def test_stagewise_rgbd():
+    """-static, GUI-default ICP+RGB weighting (icpWeight=20), no SO3 (needs initFirstRGB state: see sequence test)"""
+    run_stagewise("stagewise_rgbd", 4, icpWeight=20.0, so3=0)
+
+
+def _run_sequences(n, **kw):
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene
+    sc = SynthScene(W, H, n_objects=0, seed=1)
+    cap = 1500000
+    orc = ol.OraclePipeline(ol.default_config(W, H, capacityGlobal=cap, **kw))
+    mf = mfb.MaskFusion(mfb.default_config(W, H, capacityGlobal=cap, **kw))
+    agree = []
+    for t in range(n):
+        rgb, depth, *_ = sc.render(t)
+        orc.process_frame(rgb, depth, t * 33333)
+        mf.processFrame(rgb, depth, t * 33333)
+    mf.sync()
+    lo = np.array([orc.model(0).log[i] for i in range(orc.model(0).nlog * 8)]).reshape(-1, 8)
+    lc = mf.getBackgroundModel().poseLog()
+    counts = (orc.count(0), mf.getBackgroundModel().lastCount())
+    # index-map agreement on the final state (free-running, no teacher forcing)
+    mf.getBackgroundModel().predictIndices(mf.getTick())
+    idx_c = mf.getBackgroundModel().indexMap()[0]
+    mf.close()
+    return lo, lc, counts, idx_c, orc
+
+
+def test_sequence_ate_icp():
+    """free-running 16-frame replay, ICP only: per-frame translation within 1 mm ATE-RMSE of the oracle"""
+    lo, lc, counts, idx_c, orc = _run_sequences(16, icpWeight=100.0, so3=0)
+    assert lo.shape == lc.shape
+    assert np.array_equal(lo[:, 0], lc[:, 0])
+    ate = float(np.sqrt(np.mean(np.sum((lo[:, 1:4] - lc[:, 1:4]) ** 2, axis=1))))
+    assert ate < 1e-3, f"ATE-RMSE {ate*1e3:.4f} mm"
+    assert abs(counts[0] - counts[1]) <= max(50, counts[0] // 2000), counts
+
+
+def test_sequence_ate_rgbd_so3():
+    """free-running 12-frame replay with the GUI defaults (ICP+RGB, SO3 pre-alignment)"""
+    lo, lc, counts, idx_c, orc = _run_sequences(12)
+    ate = float(np.sqrt(np.mean(np.sum((lo[:, 1:4] - lc[:, 1:4]) ** 2, axis=1))))
+    assert ate < 1e-3, f"ATE-RMSE {ate*1e3:.4f} mm"
+
+
+def test_icp_step_matches_oracle():
+    """icpStep (reduce.cu:446-525) at a fixed pose: 29 sums within 1e-4 relative of the double-precision oracle"""
+    import ctypes as C
+    sc, orc, mf = make_pair(icpWeight=100.0, so3=0)
+    gm = mf.getBackgroundModel()
+    for t in range(2):
+        rgb, depth, *_ = sc.render(t)
+        orc.p.process_frame(rgb, depth, t)
+        mf.processFrame(rgb, depth, t)
+    rgb, depth, *_ = sc.render(2)
+    orc.set_frame(rgb, depth); orc.generate_maps(); orc.track()
+    mf.setFrame(rgb, depth); gm.performTracking()
+    od = orc.odom(0)
+    L = orc.L
+    R = np.eye(3, dtype=np.float32); tv = np.zeros(3, np.float32)
+    P = orc.last_pose(0)
+    for l in range(3):
+        w, h = W >> l, H >> l
+        fa = orc.frame_arrays()
+        Rpi = np.linalg.inv(P[:3, :3].astype(np.float64)).astype(np.float32)
+        Rc = P[:3, :3].copy(); tc = P[:3, 3].copy()
+        out = np.zeros(29)
+        cam = ol.cam(528.0 / (1 << l), 528.0 / (1 << l), 320.0 / (1 << l), 240.0 / (1 << l))
+        L.orc_icp_step(ol.ptr(np.ascontiguousarray(Rc)), ol.ptr(np.ascontiguousarray(tc)), ol.ptr(fa[f"vmap{l}"]), ol.ptr(fa[f"nmap{l}"]),
+                       ol.ptr(np.ascontiguousarray(Rpi)), ol.ptr(np.ascontiguousarray(P[:3, 3].copy())), cam,
+                       od.vmap_g[l], od.nmap_g[l], C.c_float(0.1), C.c_float(np.float32(np.sin(20.0 * 3.14159254 / 180.0))), w, h, ol.ptr(out))
+        gm.debugSetPoses(P, P)
+        got = gm.icpStep(l, Rc, tc).astype(np.float64)
+        assert got[28] == out[28], (l, got[28], out[28])            # inlier count is an integer: exact
+        scale = np.abs(out[:27]).max()
+        assert np.abs(got[:28] - out[:28]).max() <= 1e-4 * max(scale, 1.0), (l, np.abs(got - out).max(), scale)
+    mf.close()
+
+
+def test_edge_map_matches_oracle():
+    """geometric edge-ness + threshold + invert (segmentation.cu:122-177,257-269) bit-exact"""
+    import ctypes as C
+    sc, orc, mf = make_pair(icpWeight=100.0, so3=0)
+    rgb, depth, *_ = sc.render(3)
+    orc.set_frame(rgb, depth); orc.generate_maps()
+    mf.setFrame(rgb, depth)
+    e, b = mf.edgeMap()
+    fa = orc.frame_arrays()
+    eo = np.zeros((H, W), np.float32); bo = np.zeros((H, W), np.uint8); inv = np.zeros((H, W), np.uint8)
+    orc.L.orc_geometric_edges(ol.ptr(fa["vmap0"]), ol.ptr(fa["nmap0"]), W, H, C.c_float(150.0), C.c_float(2.8), ol.ptr(eo))
+    orc.L.orc_threshold(ol.ptr(eo), W * H, C.c_float(0.3), ol.ptr(bo))
+    orc.L.orc_invert(ol.ptr(bo), W * H, ol.ptr(inv))
+    assert mismatch(e, eo)[0] == 0
+    assert np.array_equal(b, inv)
+    mf.close()
+
+
+def test_process_frame_error_behaviour():
+    """argument checks mirror the asserts of MaskFusion::processFrame (MaskFusion.cpp:201-203)"""
+    import maskfusion_b200 as mfb
+    mf = mfb.MaskFusion(mfb.default_config(W, H, capacityGlobal=400000))
+    with pytest.raises(mfb.MFError):
+        mf.processFrame(np.zeros((H, W, 3), np.uint8), np.zeros((H, W), np.float64))
+    with pytest.raises(mfb.MFError):
+        mf.processFrame(np.zeros((H, W, 3), np.uint8), np.zeros((H, W), np.float32), timestamp=-1)
+    mf.close()
