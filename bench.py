@@ -1,0 +1,294 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of MaskFusion::processFrame on a synthetic 640x480 .klg replay.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A step is one processFrame call (one pass of the per-frame dense hot path) on one frame of
+a seeded synthetic replay.  Workload = BASELINE.json configs[1]: "-static" single-model
+path, 640x480, the background store pre-populated to ~4.7M surfels (capacity 2176^2, the
+reference's rounding of 5M, Model.cpp:101-106).
+  value : frames/s with every frame already resident in HBM when the timed region starts
+  e2e   : frames/s through the reference-facing C-ABI call mf_process_frame with pinned HOST
+          buffers (H2D copies of rgb+depth and the D2H pose read-back inside the timed region)
+  roofline     : dominant kernel (largest share of device time, measured live with CUDA events
+                 on the launching stream) as algorithmic GB/s against MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (oracle/, a restatement of the reference; the reference's own
+                 GL/CUDA program cannot run here) on a bounded sample of the same workload
+Multi-GPU (N>1, torchrun): the -static path has a single model and does not shard
+("replicas only"): every rank replays its own copy; value = total frames/s.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 640, 480
+CAPACITY = 2176 * 2176            # 64*floor(sqrt(5e6)/64) squared, Model.cpp:101-106
+PREPOP = 4_300_000                # dense room surfels uploaded after frame 0 (+ ~0.3M from the frame itself)
+METRIC = "frames/sec on 640x480 .klg replay"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def make_replay(n_frames, seed):
+    """synthetic replay written to a raw .klg and read back through KlgLogReader (the loader is outside the timed region)"""
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene
+    sc = SynthScene(W, H, n_objects=0, seed=seed)
+    d16 = np.zeros((n_frames + 1, H, W), np.uint16); rgb = np.zeros((n_frames + 1, H, W, 3), np.uint8)
+    for t in range(n_frames):
+        r, _, _, _, d = sc.render(t)
+        rgb[t], d16[t] = r, d
+    path = f"/tmp/mfb200_bench_{os.getpid()}.klg"
+    mfb.write_klg(path, np.arange(n_frames + 1, dtype=np.int64) * 33333, d16, rgb)     # +1: hasMore() never yields the last frame (N11)
+    rd = mfb.KlgLogReader(path, W, H)
+    frames = []
+    while rd.hasMore():
+        frames.append(rd.getNext())
+    rd.close()
+    os.remove(path)
+    return sc, frames
+
+
+def prepopulate(mf, sc):
+    """fill the background store to ~4.7M surfels: dense synthetic room cloud in the model frame (= camera-0 frame)"""
+    from maskfusion_b200.synth import dense_room_surfels
+    gm = mf.getBackgroundModel()
+    cur = gm.downloadMap()
+    room = dense_room_surfels(sc, PREPOP, time=1, conf=20.0)
+    Tinv = np.linalg.inv(sc.camera_pose(0))
+    room[:, 0:3] = (room[:, 0:3].astype(np.float64) @ Tinv[:3, :3].T + Tinv[:3, 3]).astype(np.float32)
+    room[:, 8:11] = (room[:, 8:11].astype(np.float64) @ Tinv[:3, :3].T).astype(np.float32)
+    allv = np.concatenate([cur, room], 0)
+    gm.uploadMap(allv)
+    return allv.shape[0]
+
+
+# algorithmic bytes of one launch, S = live surfels, P = pixels (DESIGN.md "kernels and rooflines")
+def algorithmic_bytes(name, S, P):
+    table = {
+        "k_index_project": 32 * S,                   # position + colour/time planes (normal plane never read)
+        "k_index_resolve": 8 * P + 52 * P,
+        "k_clean_test": 48 * S + 1 * (S + P),
+        "k_clean_scatter": 48 * S + 48 * S + 1 * (S + P),
+        "k_splat_project": 16 * S,                   # position plane for every surfel; +32 B only for in-frustum stable ones
+        "k_splat_resolve": 8 * P + 38 * P + 36 * P,
+        "k_associate": 13 * P + 93 * P,
+        "k_bilateral": 8 * P,
+        "k_gn_step_L0": 48 * P, "k_gn_step_L1": 48 * P // 4, "k_gn_step_L2": 48 * P // 16,
+        "k_rgb_residual": 30 * P,
+    }
+    return table.get(name)
+
+
+def run_ours(args, rank, world):
+    import torch
+    import maskfusion_b200 as mfb
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, Wm = args.steps, args.warmup
+    n_need = 1 + 2 * (Wm + K) + 2
+    sc, frames = make_replay(n_need, seed=rank)
+    stream = torch.cuda.current_stream()
+    cfg = mfb.default_config(W, H, capacityGlobal=CAPACITY)        # GUI defaults: ICP+RGB (w=20), SO3, -static
+    mf = mfb.MaskFusion(cfg, device=local, stream=stream.cuda_stream)
+    rgb0, d0, ts0 = frames[0]
+    mf.processFrame(rgb0, d0, ts0)
+    S0 = prepopulate(mf, sc)
+
+    # pinned host staging (e2e) and device-resident copies (value)
+    host_rgb = [torch.from_numpy(f[0]).pin_memory() for f in frames]
+    host_d = [torch.from_numpy(f[1]).pin_memory() for f in frames]
+    dev_rgb = [t.cuda() for t in host_rgb]
+    dev_d = [t.cuda() for t in host_d]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(first, on_device):
+        for i in range(Wm):
+            j = first + i
+            mf.processFramePtr((dev_rgb if on_device else host_rgb)[j].data_ptr(), (dev_d if on_device else host_d)[j].data_ptr(), frames[j][2], on_device)
+        mf.sync()
+        barrier()
+        l0 = mf.kernelLaunches()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K):
+            j = first + Wm + i
+            mf.processFramePtr((dev_rgb if on_device else host_rgb)[j].data_ptr(), (dev_d if on_device else host_d)[j].data_ptr(), frames[j][2], on_device)
+            if not on_device:
+                mf.getBackgroundModel().getPose()              # the step's result, read on the host every frame
+        e1.record(stream)
+        mf.sync()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        return ms, mf.kernelLaunches() - l0
+
+    sampler = ClockSampler(local); sampler.start()
+    mf.setProfiling(True)
+    ms_dev, launches = timed(1, True)
+    stages = mf.stageTimes()
+    mf.setProfiling(False)
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(1 + Wm + K, False)
+    S_live = mf.getBackgroundModel().lastCount()
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    fps = world * K / (ms_dev / 1e3)
+    fps_e2e = world * K / (ms_e2e / 1e3)
+    P = W * H
+    # dominant kernel by total device time inside the timed region
+    kern = {k: v for k, v in stages.items() if k.startswith("k_")}
+    total_ms = sum(v[1] for v in stages.values())
+    dom = max(kern, key=lambda k: kern[k][1])
+    peak, peak_src = load_peaks()
+    ab = algorithmic_bytes(dom, S_live, P)
+    avg_ms = kern[dom][1] / kern[dom][0]
+    achieved = (ab / 1e9) / (avg_ms / 1e3) if ab else None
+    shares = {k: round(v[1] / total_ms, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][1])[:12]}
+    out = {
+        "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: -static single model, 640x480 synthetic .klg replay, ICP+RGB+SO3 tracking + surfel fuse, 1 B200",
+                   "surfels_live": int(S_live), "surfel_capacity": CAPACITY, "tracking": "GUI defaults icpWeight=20 so3=1 pyramid=1",
+                   "l2": "surfel store 2x227 MB + per-frame maps exceed the 126 MB L2 between steps (no explicit flush)",
+                   "parallelism": "replicas only" if world > 1 else "single"},
+        "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": P * 3 + P * 4, "d2h_bytes_per_step": 160 + 64},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": None,
+                     "avg_launch_ms": round(avg_ms, 5), "algorithmic_bytes_per_launch": ab, "time_shares": shares},
+    }
+    if rank == 0 and world == 1:
+        out["cpu_baseline"] = cpu_baseline(sample_frames=4)
+    if rank == 0:
+        print(json.dumps(out))
+    mf.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def cpu_baseline(sample_frames):
+    """CPU oracle on a bounded sample of the same workload (same surfel count, same defaults)"""
+    from tests import oracle_lib as ol
+    from maskfusion_b200.synth import dense_room_surfels, SynthScene
+    import ctypes as C
+    sc = SynthScene(W, H, n_objects=0, seed=0)
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    p = ol.OraclePipeline(ol.default_config(W, H, capacityGlobal=CAPACITY))
+    rgb, depth, *_ = sc.render(0)
+    p.process_frame(rgb, depth, 0)
+    m = p.L.orc_mf_model(p.h, 0)
+    cur = p.surfels(0).copy()
+    room = dense_room_surfels(sc, PREPOP, time=1, conf=20.0)
+    Tinv = np.linalg.inv(sc.camera_pose(0))
+    room[:, 0:3] = (room[:, 0:3].astype(np.float64) @ Tinv[:3, :3].T + Tinv[:3, 3]).astype(np.float32)
+    room[:, 8:11] = (room[:, 8:11].astype(np.float64) @ Tinv[:3, :3].T).astype(np.float32)
+    allv = np.ascontiguousarray(np.concatenate([cur, room], 0))
+    C.memmove(m.contents.surf[m.contents.target], allv.ctypes.data, allv.nbytes)
+    m.contents.count = allv.shape[0]
+    fr = [sc.render(t)[:2] for t in range(1, 1 + sample_frames)]
+    t0 = time.time()
+    for i, (r, d) in enumerate(fr):
+        p.process_frame(r, d, (i + 1) * 33333)
+    dt = time.time() - t0
+    return {"value": round(sample_frames / dt, 4), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": f"{sample_frames} frames of the same replay, {allv.shape[0]} surfels; OpenMP only in the bilateral and association passes, surfel passes scalar"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU restatement (oracle port) on the host cores; rank 0 only"""
+    if rank != 0:
+        return
+    K = max(1, min(args.steps, 6))
+    cb = cpu_baseline(sample_frames=K)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": 0,
+           "ms_per_step": round(1e3 / cb["value"], 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic",
+           "config": {"workload": "configs[1]: -static single model, 640x480 synthetic replay, same surfel count and defaults as the CUDA arm",
+                      "note": "the reference's own CUDA+OpenGL program cannot run in this environment (no OpenGL/Pangolin/Eigen/OpenCV); this arm is the CPU oracle port"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

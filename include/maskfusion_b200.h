@@ -107,6 +107,9 @@ int mf_download_track_stats(mf_context* ctx, int i, double* A36, double* b6, flo
 int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binary);                           /* MfSegmentation floatEdgeMap / binary edge map */
 
 /* ---- stand-alone kernels exposed for parity tests (device work, host buffers) ---- */
+/* in-stream CUDA-event stage timer (replaces the reference's TICK/TOCK Stopwatch, Core/Utils/Stopwatch.h:46-54) */
+int mf_set_profiling(mf_context* ctx, int on);
+int mf_get_stage_times(mf_context* ctx, char* buf, int bufsize);   /* lines: "name count total_ms" */
 int mf_debug_set_poses(mf_context* ctx, int i, const float pose16[16], const float last_pose16[16]);   /* sets Model::pose and Model::lastPose verbatim */
 int mf_icp_step(mf_context* ctx, int i, int level, const float Rcurr9[9], const float tcurr3[3], float out29[29]);  /* icpStep, reduce.cu:446-525 */
 

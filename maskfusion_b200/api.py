@@ -48,7 +48,7 @@ EXPORTS = [
     "mf_model_fuse", "mf_model_clean", "mf_model_combined_predict", "mf_model_init_from_frame",
     "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
-    "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
+    "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write",
 ]
 
@@ -95,6 +95,8 @@ def load_library():
     L.mf_download_association.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_track_stats.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_edge_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_set_profiling.argtypes = [C.c_void_p, C.c_int]
+    L.mf_get_stage_times.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.mf_debug_set_poses.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.mf_icp_step.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mf_klg_open.restype = C.c_void_p
@@ -285,6 +287,19 @@ class MaskFusion:
 
     def sync(self):
         self._ck(self.L.mf_sync(self.h))
+
+    def setProfiling(self, on: bool):
+        self._ck(self.L.mf_set_profiling(self.h, int(on)))
+
+    def stageTimes(self) -> dict:
+        """{kernel name: (launch count, total device ms)} measured with CUDA events on the pipeline's stream"""
+        buf = C.create_string_buffer(1 << 16)
+        self._ck(self.L.mf_get_stage_times(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            n, c, ms = line.split()
+            out[n] = (int(c), float(ms))
+        return out
 
     def getTick(self) -> int:
         return self.L.mf_tick(self.h)

@@ -290,6 +290,27 @@ extern "C" int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binar
     MF_CATCH(-1)
 }
 
+extern "C" int mf_set_profiling(mf_context* ctx, int on)
+{
+    MF_TRY MF_NEED(ctx)
+    ctx->mf->sync();
+    ctx->mf->prof.on = on != 0; ctx->mf->prof.used = 0;
+    if (on) ctx->mf->prof.acc.clear();
+    return 0;
+    MF_CATCH(-1)
+}
+extern "C" int mf_get_stage_times(mf_context* ctx, char* buf, int bufsize)
+{
+    MF_TRY MF_NEED(ctx)
+    ctx->mf->sync();
+    std::string out;
+    char line[256];
+    for (auto& kv : ctx->mf->prof.acc) { snprintf(line, sizeof line, "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second); out += line; }
+    if ((int)out.size() + 1 > bufsize) { g_err = "buffer too small"; return -6; }
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return (int)out.size();
+    MF_CATCH(-1)
+}
 extern "C" int mf_debug_set_poses(mf_context* ctx, int i, const float* pose16, const float* last16)
 {
     MF_NEED(ctx) MF_MODEL(ctx, i)

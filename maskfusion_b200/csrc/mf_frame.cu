@@ -283,45 +283,45 @@ void launch_unpack_rgb(const uint8_t* rgb3, uchar4* out, int P, cudaStream_t s) 
 void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t s)
 {
     dim3 b(BIL_BX, BIL_BY);
-    k_bilateral<<<grid2(W, H, b), b, 0, s>>>(depth, out, W, H);
+    prof_mark(s, "k_bilateral"); k_bilateral<<<grid2(W, H, b), b, 0, s>>>(depth, out, W, H);
 }
 void launch_pyrdown_f(const float* src, int sw, int sh, float* dst, cudaStream_t s)
 {
     dim3 b(32, 8);
-    k_pyrdown_f<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
+    prof_mark(s, "k_pyrdown_f"); k_pyrdown_f<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
 }
 void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStream_t s)
 {
     dim3 b(32, 8);
-    k_pyrdown_u8<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
+    prof_mark(s, "k_pyrdown_u8"); k_pyrdown_u8<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
 }
 void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s)
 {
     dim3 b(32, 8);
-    k_vmap_nmap<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cutoff, vmap, nmap);
+    prof_mark(s, "k_vmap_nmap"); k_vmap_nmap<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cutoff, vmap, nmap);
 }
 void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s) { k_intensity<<<(P + 255) / 256, 256, 0, s>>>(img, P, out); }
 void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s)
 {
-    k_intensity_select<<<(P + 255) / 256, 256, 0, s>>>(imgPred, imgFill, nonBlack, denom, forceFill, P, out);
+    prof_mark(s, "k_intensity_select"); k_intensity_select<<<(P + 255) / 256, 256, 0, s>>>(imgPred, imgFill, nonBlack, denom, forceFill, P, out);
 }
 void launch_sobel(const uint8_t* src, int W, int H, short2* grad, cudaStream_t s)
 {
     dim3 b(32, 8);
-    k_sobel<<<grid2(W, H, b), b, 0, s>>>(src, W, H, grad);
+    prof_mark(s, "k_sobel"); k_sobel<<<grid2(W, H, b), b, 0, s>>>(src, W, H, grad);
 }
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
                        int W, int H, Rt pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s)
 {
     int threads = (W / 4) * (H / 4) * 4;
-    k_model_maps<<<(threads + 127) / 128, 128, 0, s>>>(srcVp, srcNp, srcVf, srcNf, nonBlack, denom, W, H, pose, maxDepthRGB,
+    prof_mark(s, "k_model_maps"); k_model_maps<<<(threads + 127) / 128, 128, 0, s>>>(srcVp, srcNp, srcVf, srcNf, nonBlack, denom, W, H, pose, maxDepthRGB,
                                                        v[0], n[0], v[1], n[1], v[2], n[2], depth0);
 }
 void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s) { k_map_to_planar<<<(P + 255) / 256, 256, 0, s>>>(m, P, out); }
 void launch_project_points(const float* depth, int W, int H, Cam cam, float4* cloud, cudaStream_t s)
 {
     dim3 b(32, 8);
-    k_project_points<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cloud);
+    prof_mark(s, "k_project_points"); k_project_points<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cloud);
 }
 
 }  // namespace mfb

@@ -17,6 +17,33 @@ void cudaCheck(cudaError_t e, const char* where)
     if (e != cudaSuccess) throw CudaError{std::string(where) + ": " + cudaGetErrorString(e)};
 }
 
+// --------------------------------------------------------------------------------------
+// in-stream stage timer: one CUDA event per mark on the launching stream; the interval up
+// to the next mark is attributed to the mark's name.  Off by default (zero overhead).
+// --------------------------------------------------------------------------------------
+Profiler* g_prof = nullptr;
+void prof_mark(cudaStream_t s, const char* name)
+{
+    Profiler* p = g_prof;
+    if (!p || !p->on) return;
+    if (p->used == (int)p->events.size()) {
+        cudaEvent_t e; cudaEventCreate(&e); p->events.push_back(e); p->names.push_back(nullptr);
+    }
+    p->names[p->used] = name;
+    cudaEventRecord(p->events[p->used], s);
+    p->used++;
+}
+void Profiler::resolve()
+{
+    // caller has synchronised the stream
+    for (int i = 0; i + 1 < used; ++i) {
+        if (!names[i]) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, events[i], events[i + 1]) == cudaSuccess) { auto& a = acc[names[i]]; a.first += 1; a.second += ms; }
+    }
+    used = 0;
+}
+
 Mat4 rigidInverse(const Mat4& T)
 {
     // [R^T | -R^T t] in fp32 (reference: Eigen::Matrix4f::inverse(); rule fixed in DESIGN.md)
@@ -231,6 +258,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     cam = Cam{c.fx, c.fy, c.cx, c.cy};
     ownStream = (st == nullptr);
     if (ownStream) cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"); else stream = st;
+    g_prof = &prof;
     rgb3.alloc((size_t)P * 3); rgb.alloc(P); depthRaw.alloc(P); depthFilt.alloc(P); mask.alloc(P); mask.zero(stream);
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
@@ -249,18 +277,27 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
 MaskFusion::~MaskFusion()
 {
     cudaStreamSynchronize(stream);
+    if (g_prof == &prof) g_prof = nullptr;
+    for (cudaEvent_t e : prof.events) cudaEventDestroy(e);
     for (auto& m : models) { if (m->hCount) cudaFreeHost(m->hCount); if (m->hTrackOut) cudaFreeHost(m->hTrackOut); }
     models.clear();
     if (hJobs) cudaFreeHost(hJobs);
     if (ownStream) cudaStreamDestroy(stream);
 }
 
-void MaskFusion::sync() { cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize"); }
+void MaskFusion::sync()
+{
+    if (prof.on) prof_mark(stream, nullptr);            // closes the last open interval
+    cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+    if (prof.on) prof.resolve();
+}
 
 // textureRGB / textureDepthMetric upload + filterDepth (MaskFusion.cpp:212-217, 650-657)
 void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint8_t* maskIn, bool onDevice)
 {
     cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    g_prof = &prof;
+    prof_mark(stream, onDevice ? "copy_d2d_frame" : "copy_h2d_frame");
     cudaCheck(cudaMemcpyAsync(rgb3, rgbIn, (size_t)P * 3, kind, stream), "rgb upload");
     cudaCheck(cudaMemcpyAsync(depthRaw, depthIn, (size_t)P * sizeof(float), kind, stream), "depth upload");
     if (maskIn) cudaCheck(cudaMemcpyAsync(mask, maskIn, (size_t)P, kind, stream), "mask upload");
@@ -311,9 +348,11 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
         J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.partialI = m->partialI;
         memcpy(poses.p[j], m->pose.m, 16 * sizeof(float));
     }
+    prof_mark(stream, "copy_jobs");
     cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
     launches += launch_tracking(dJobs, (int)ms.size(), poses, W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
                                 cfg.so3 != 0, numSMs, stream);
+    prof_mark(stream, "copy_pose_d2h");
     for (Model* m : ms) {
         cudaCheck(cudaMemcpyAsync(m->hTrackOut, (const char*)m->trackState.p + offsetof(TrackState, out), 40 * sizeof(float),
                                   cudaMemcpyDeviceToHost, stream), "pose D2H");

@@ -10,6 +10,7 @@
 #include <memory>
 #include <string>
 #include <vector>
+#include <map>
 #include "../../include/maskfusion_b200.h"
 #include "mf_kernels.h"
 
@@ -37,6 +38,14 @@ struct DevBuf {
     void zero(cudaStream_t s) { if (n) cudaCheck(cudaMemsetAsync(p, 0, n * sizeof(T), s), "memset"); }
     operator T*() const { return p; }
 };
+
+struct Profiler {
+    bool on = false; int used = 0;
+    std::vector<cudaEvent_t> events; std::vector<const char*> names;
+    std::map<std::string, std::pair<long, double>> acc;      // name -> (count, total ms)
+    void resolve();
+};
+extern Profiler* g_prof;
 
 class MaskFusion;
 
@@ -120,6 +129,7 @@ public:
     DevBuf<uint8_t> initFlagR, initFlagF;
     DevBuf<float> scratch;                  // read-back staging
     bool frameMapsValid = false, intensityValid = false;
+    Profiler prof;
 };
 
 }  // namespace mfb

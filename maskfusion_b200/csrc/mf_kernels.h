@@ -47,6 +47,8 @@ struct TrackJob {
 };
 
 void set_num_sms(int n);
+// in-stream stage timer hook (mf_host.cu): records a CUDA event on `s`; the time until the next mark is attributed to `name`
+void prof_mark(cudaStream_t s, const char* name);
 
 // ---- mf_frame.cu ----
 void launch_unpack_rgb(const uint8_t* rgb3, uchar4* out, int P, cudaStream_t s);

@@ -63,16 +63,16 @@ __global__ void k_invert(const uint8_t* __restrict__ in, int n, uint8_t* __restr
 void launch_geometric_edges(const float4* vmap, const float4* nmap, int W, int H, float wD, float wC, float thr, float* edge, uint8_t* binary, cudaStream_t s)
 {
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    k_geometric_edges<<<g, b, 0, s>>>(vmap, nmap, W, H, wD, wC, thr, edge, binary);
+    prof_mark(s, "k_geometric_edges"); k_geometric_edges<<<g, b, 0, s>>>(vmap, nmap, W, H, wD, wC, thr, edge, binary);
 }
 void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, uint8_t* inverted, cudaStream_t s)
 {
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
     for (int i = 0; i < iterations; ++i) {
-        k_morph<<<g, b, 0, s>>>(data, buf, W, H, radius, 1);
-        k_morph<<<g, b, 0, s>>>(buf, data, W, H, radius, 0);
+        prof_mark(s, "k_morph"); k_morph<<<g, b, 0, s>>>(data, buf, W, H, radius, 1);
+        prof_mark(s, "k_morph"); k_morph<<<g, b, 0, s>>>(buf, data, W, H, radius, 0);
     }
-    k_invert<<<(W * H + 255) / 256, 256, 0, s>>>(data, W * H, inverted);
+    prof_mark(s, "k_invert"); k_invert<<<(W * H + 255) / 256, 256, 0, s>>>(data, W * H, inverted);
 }
 
 }  // namespace mfb

@@ -657,10 +657,10 @@ void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s) { if (n)
 void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, int time,
                             int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, cudaStream_t s)
 {
-    k_index_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, count, tinv, cam, W, H, maxDepth, (float)time, (float)timeDelta,
+    prof_mark(s, "k_index_project"); k_index_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, count, tinv, cam, W, H, maxDepth, (float)time, (float)timeDelta,
                                                         (unsigned long long*)key);
     int P = W * H;
-    k_index_resolve<<<(P + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, P, (unsigned long long*)key, idx, vertConf, colorTime, normRad);
+    prof_mark(s, "k_index_resolve"); k_index_resolve<<<(P + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, P, (unsigned long long*)key, idx, vertConf, colorTime, normRad);
 }
 
 void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
@@ -668,15 +668,15 @@ void launch_associate(const uchar4* rgb, const float* depthRaw, const float* dep
                       float weighting, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s)
 {
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    k_associate<<<g, b, 0, s>>>(rgb, depthRaw, depthFilt, mask, idx, vertConf, normRad, pose, cam, W, H, maxDepth, time, weighting, maskID,
+    prof_mark(s, "k_associate"); k_associate<<<g, b, 0, s>>>(rgb, depthRaw, depthFilt, mask, idx, vertConf, normRad, pose, cam, W, H, maxDepth, time, weighting, maskID,
                                 flag, best, meas[0], meas[1], meas[2], slot);
 }
 
 void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const* meas, uint32_t* slot, int P, int time,
                         const SurfelPlanes& sp, cudaStream_t s)
 {
-    k_fuse_update<<<(P + 255) / 256, 256, 0, s>>>(flag, best, meas[0], meas[1], meas[2], slot, P, time, sp.pos, sp.col, sp.nrm);
-    k_slot_release<<<(P + 255) / 256, 256, 0, s>>>(flag, best, P, slot);
+    prof_mark(s, "k_fuse_update"); k_fuse_update<<<(P + 255) / 256, 256, 0, s>>>(flag, best, meas[0], meas[1], meas[2], slot, P, time, sp.pos, sp.col, sp.nrm);
+    prof_mark(s, "k_slot_release"); k_slot_release<<<(P + 255) / 256, 256, 0, s>>>(flag, best, P, slot);
 }
 
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
@@ -689,10 +689,10 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
     P.outlierCoeff = outlierCoeff; P.maskID = maskID;
     int Ppix = W * H;
     int blocks = persistentBlocks(4);
-    k_clean_test<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, aflag, meas[0], meas[1], meas[2], Ppix, P, idx, vertConf,
+    prof_mark(s, "k_clean_test"); k_clean_test<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, aflag, meas[0], meas[1], meas[2], Ppix, P, idx, vertConf,
                                                colorTime, depthFilt, mask, keep, blockSums);
-    k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount);
-    k_clean_scatter<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
+    prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount);
+    prof_mark(s, "k_clean_scatter"); k_clean_scatter<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
                                                   dst.pos, dst.col, dst.nrm);
 }
 
@@ -701,11 +701,11 @@ void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, Rt t
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
                              uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s)
 {
-    k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
+    prof_mark(s, "k_splat_project"); k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
                                                         (float)maxTime, (float)timeDelta, 0u, (unsigned long long*)key);
     if (nonBlackSamples) cudaMemsetAsync(nonBlackSamples, 0, sizeof(uint32_t), s);
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    k_splat_resolve<<<g, b, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, cam, W, H, maxDepth, confThreshold, (float)time, (float)maxTime,
+    prof_mark(s, "k_splat_resolve"); k_splat_resolve<<<g, b, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, cam, W, H, maxDepth, confThreshold, (float)time, (float)maxTime,
                                     (float)timeDelta, (unsigned long long*)key, image, vertexConf, normalRad, timeTex, doFill, depthFilt, rgb,
                                     ptVN, ptImg, fillImage, fillVertex, fillNormal, nonBlackSamples);
 }
@@ -715,11 +715,11 @@ void launch_init_model(const uchar4* rgb, const float* depthRaw, const float* de
                        cudaStream_t s)
 {
     int P = W * H, nb = (P + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    k_zero_f4<<<(P + 255) / 256, 256, 0, s>>>(sp.nrm, 0, (uint32_t)(P < (int)capacity ? P : (int)capacity));
-    k_init_flags<<<nb, SCAN_BLOCK, 0, s>>>(depthRaw, depthFilt, W, H, maxDepth, fr, ff, sumR, sumF);
-    k_scan_small<<<1, 1024, 0, s>>>(sumR, nb, capacity, count);
-    k_scan_small<<<1, 1024, 0, s>>>(sumF, nb, capacity, nullptr);
-    k_init_scatter<<<nb, SCAN_BLOCK, 0, s>>>(rgb, depthRaw, depthFilt, cam, W, H, time, fr, ff, sumR, sumF, capacity, sp.pos, sp.col, sp.nrm);
+    prof_mark(s, "k_zero_f4"); k_zero_f4<<<(P + 255) / 256, 256, 0, s>>>(sp.nrm, 0, (uint32_t)(P < (int)capacity ? P : (int)capacity));
+    prof_mark(s, "k_init_flags"); k_init_flags<<<nb, SCAN_BLOCK, 0, s>>>(depthRaw, depthFilt, W, H, maxDepth, fr, ff, sumR, sumF);
+    prof_mark(s, "k_scan_small"); k_scan_small<<<1, 1024, 0, s>>>(sumR, nb, capacity, count);
+    prof_mark(s, "k_scan_small"); k_scan_small<<<1, 1024, 0, s>>>(sumF, nb, capacity, nullptr);
+    prof_mark(s, "k_init_scatter"); k_init_scatter<<<nb, SCAN_BLOCK, 0, s>>>(rgb, depthRaw, depthFilt, cam, W, H, time, fr, ff, sumR, sumF, capacity, sp.pos, sp.col, sp.nrm);
 }
 
 void launch_planes_to_aos(const SurfelPlanes& sp, uint32_t n, float4* out, cudaStream_t s) { if (n) k_planes_to_aos<<<(n + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, n, out); }

@@ -613,13 +613,13 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W,
     int launches = 0;
     const bool icp = !rgbOnly && icpWeight > 0;
     const bool rgb = rgbOnly || icpWeight < 100;
-    k_track_begin<<<nJobs, 32, 0, s>>>(d_jobs, poses, so3 ? 1 : 0); ++launches;
+    prof_mark(s, "k_track_begin"); k_track_begin<<<nJobs, 32, 0, s>>>(d_jobs, poses, so3 ? 1 : 0); ++launches;
     if (so3) {
         int lv = 2, w = W >> lv, h = H >> lv;
         Cam c = camLevel(cam, lv);
         dim3 g(trackBlocks(w * h, numSMs), nJobs);
-        for (int i = 0; i < 10; ++i) { k_so3_step<<<g, TRK_THREADS, 0, s>>>(d_jobs, w, h, c); ++launches; }
-        k_track_so3_finish<<<nJobs, 32, 0, s>>>(d_jobs, 1); ++launches;
+        for (int i = 0; i < 10; ++i) { prof_mark(s, "k_so3_step"); k_so3_step<<<g, TRK_THREADS, 0, s>>>(d_jobs, w, h, c); ++launches; }
+        prof_mark(s, "k_track_so3_finish"); k_track_so3_finish<<<nJobs, 32, 0, s>>>(d_jobs, 1); ++launches;
     }
     int iterations[3] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
     const float sobelScale = (float)(1.0 / 8.0);
@@ -629,18 +629,19 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W,
         int w = W >> l, h = H >> l;
         Cam c = camLevel(cam, l);
         if (iterations[l] == 0) continue;
-        k_track_level_begin<<<nJobs, 32, 0, s>>>(d_jobs, l, c, rgb ? 1 : 0); ++launches;
+        prof_mark(s, "k_track_level_begin"); k_track_level_begin<<<nJobs, 32, 0, s>>>(d_jobs, l, c, rgb ? 1 : 0); ++launches;
         dim3 g(trackBlocks(w * h, numSMs), nJobs);
         float minScale = (float)(pow((double)minGrad[l], 2.0) / pow((double)sobelScale, 2.0));
         for (int j = 0; j < iterations[l]; ++j) {
-            if (rgb) { k_rgb_residual<<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, minScale, 0.07f, rgbOnly ? 1 : 0); ++launches; }
+            if (rgb) { prof_mark(s, "k_rgb_residual"); k_rgb_residual<<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, minScale, 0.07f, rgbOnly ? 1 : 0); ++launches; }
+            prof_mark(s, l == 0 ? "k_gn_step_L0" : (l == 1 ? "k_gn_step_L1" : "k_gn_step_L2"));
             if (icp && rgb) k_gn_step<true, true><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
             else if (icp) k_gn_step<true, false><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
             else k_gn_step<false, true><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
             ++launches;
         }
     }
-    k_track_end<<<nJobs, 32, 0, s>>>(d_jobs, rgb ? 1 : 0); ++launches;
+    prof_mark(s, "k_track_end"); k_track_end<<<nJobs, 32, 0, s>>>(d_jobs, rgb ? 1 : 0); ++launches;
     return launches;
 }
 
@@ -648,7 +649,7 @@ void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vma
                      const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s)
 {
     const float angleThres = (float)sin(20.f * 3.14159254f / 180.f);
-    k_icp_only<<<trackBlocks(W * H, numSMs), TRK_THREADS, 0, s>>>(vmapC, nmapC, vmapG, nmapG, W, H, cam, pp, 0.10f, angleThres, partial, ticket, out29);
+    prof_mark(s, "k_icp_only"); k_icp_only<<<trackBlocks(W * H, numSMs), TRK_THREADS, 0, s>>>(vmapC, nmapC, vmapG, nmapG, W, H, cam, pp, 0.10f, angleThres, partial, ticket, out29);
 }
 
 }  // namespace mfb

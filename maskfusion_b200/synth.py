@@ -208,6 +208,6 @@ def dense_room_surfels(scene: SynthScene, n_target: int, time: int = 1, conf: fl
         out[k:k + n, 6] = time
         out[k:k + n, 7] = time
         out[k:k + n, 8:11] = nrm
-        out[k:k + n, 11] = spacing * 0.8
+        out[k:k + n, 11] = spacing * 1.5
         k += n
     return out

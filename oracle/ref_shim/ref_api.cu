@@ -1,0 +1,137 @@
+// oracle/ref_shim/ref_api.cu -- TEST INFRASTRUCTURE (GPU-side oracle): a flat C wrapper
+// around the reference's OWN CUDA entry points (Core/Cuda/cudafuncs.cuh:64-193,
+// segmentation.cuh:28-52), compiled from the sources where they lie under /root/reference
+// by oracle/Makefile.ref into oracle/_ref/libmf_ref.so.  Host arrays in, host arrays out
+// (planar 3*rows x cols maps, exactly the reference's DeviceArray2D contents).  Used by
+// tests/test_gpu_ref.py to pin the CPU oracle against the reference's kernels on the B200.
+#include "cudafuncs.cuh"
+#include "segmentation.cuh"
+#include <cstring>
+#include <vector>
+
+static mat33 toMat(const float* R) { mat33 m; for (int r = 0; r < 3; ++r) m.data[r] = make_float3(R[r * 3], R[r * 3 + 1], R[r * 3 + 2]); return m; }
+
+extern "C" {
+
+int ref_vmap_nmap(const float* depth, int W, int H, float fx, float fy, float cx, float cy, float cutoff, float* vmap, float* nmap)
+{
+    DeviceArray2D<float> d, v, n;
+    d.upload(depth, W * sizeof(float), H, W);
+    v.create(H * 3, W); n.create(H * 3, W);
+    cudaMemset2D(v.ptr(), v.step(), 0, W * sizeof(float), H * 3);      // the kernels leave stale planes untouched
+    cudaMemset2D(n.ptr(), n.step(), 0, W * sizeof(float), H * 3);
+    createVMap(CameraModel(fx, fy, cx, cy), d, v, cutoff);
+    createNMap(v, n);
+    cudaDeviceSynchronize();
+    v.download(vmap, W * sizeof(float)); n.download(nmap, W * sizeof(float));
+    return (int)cudaGetLastError();
+}
+
+int ref_pyrdown_f(const float* src, int sw, int sh, float* dst)
+{
+    DeviceArray2D<float> s, d;
+    s.upload(src, sw * sizeof(float), sh, sw);
+    pyrDownGaussF(s, d);
+    cudaDeviceSynchronize();
+    d.download(dst, (sw / 2) * sizeof(float));
+    return (int)cudaGetLastError();
+}
+int ref_pyrdown_u8(const unsigned char* src, int sw, int sh, unsigned char* dst)
+{
+    DeviceArray2D<unsigned char> s, d;
+    s.upload(src, sw, sh, sw);
+    pyrDownUcharGauss(s, d);
+    cudaDeviceSynchronize();
+    d.download(dst, sw / 2);
+    return (int)cudaGetLastError();
+}
+
+// copyMaps + resize x2 + tranformMaps, i.e. RGBDOdometry::initICPModel (RGBDOdometry.cpp:153-185)
+int ref_model_maps(const float* vtex4, const float* ntex4, int W, int H, const float* R9, const float* t3, float** vout, float** nout)
+{
+    DeviceArray<float> vt, nt;
+    vt.upload(vtex4, (size_t)W * H * 4); nt.upload(ntex4, (size_t)W * H * 4);
+    DeviceArray2D<float> v[3], n[3];
+    for (int l = 0; l < 3; ++l) { v[l].create((H >> l) * 3, W >> l); n[l].create((H >> l) * 3, W >> l); }
+    copyMaps(vt, nt, v[0], n[0]);
+    for (int l = 1; l < 3; ++l) {
+        cudaMemset2D(v[l].ptr(), v[l].step(), 0, (W >> l) * sizeof(float), (H >> l) * 3);
+        cudaMemset2D(n[l].ptr(), n[l].step(), 0, (W >> l) * sizeof(float), (H >> l) * 3);
+        resizeVMap(v[l - 1], v[l]); resizeNMap(n[l - 1], n[l]);
+    }
+    mat33 R = toMat(R9); float3 t = make_float3(t3[0], t3[1], t3[2]);
+    for (int l = 0; l < 3; ++l) tranformMaps(v[l], n[l], R, t, v[l], n[l]);
+    cudaDeviceSynchronize();
+    for (int l = 0; l < 3; ++l) { v[l].download(vout[l], (W >> l) * sizeof(float)); n[l].download(nout[l], (W >> l) * sizeof(float)); }
+    return (int)cudaGetLastError();
+}
+
+int ref_icp_step(const float* Rcurr9, const float* tcurr3, const float* vmap_curr, const float* nmap_curr, const float* Rprev_inv9,
+                 const float* tprev3, float fx, float fy, float cx, float cy, const float* vmap_g, const float* nmap_g, float distThres,
+                 float angleThres, int W, int H, int threads, int blocks, float* A36, float* b6, float* res2)
+{
+    DeviceArray2D<float> vc, nc, vg, ng;
+    vc.upload(vmap_curr, W * sizeof(float), H * 3, W); nc.upload(nmap_curr, W * sizeof(float), H * 3, W);
+    vg.upload(vmap_g, W * sizeof(float), H * 3, W); ng.upload(nmap_g, W * sizeof(float), H * 3, W);
+    DeviceArray<JtJJtrSE3> sum, out; sum.create(MAX_THREADS); out.create(1);
+    DeviceArray2D<unsigned char> mask; mask.create(H, W);
+    icpStep(toMat(Rcurr9), make_float3(tcurr3[0], tcurr3[1], tcurr3[2]), vc, nc, toMat(Rprev_inv9), make_float3(tprev3[0], tprev3[1], tprev3[2]),
+            CameraModel(fx, fy, cx, cy), vg, ng, distThres, angleThres, sum, out, A36, b6, res2, threads, blocks, 0, mask, 0);
+    return (int)cudaGetLastError();
+}
+
+int ref_sobel(const unsigned char* img, int W, int H, short* dx, short* dy)
+{
+    DeviceArray2D<unsigned char> s; DeviceArray2D<short> gx, gy;
+    s.upload(img, W, H, W); gx.create(H, W); gy.create(H, W);
+    computeDerivativeImages(s, gx, gy);
+    gx.download(dx, W * sizeof(short)); gy.download(dy, W * sizeof(short));
+    return (int)cudaGetLastError();
+}
+
+int ref_so3_step(const unsigned char* lastImage, const unsigned char* nextImage, const float* basis9, const float* kinv9, const float* krlr9,
+                 int W, int H, int threads, int blocks, float* A9, float* b3, float* res2)
+{
+    DeviceArray2D<unsigned char> a, b;
+    a.upload(lastImage, W, H, W); b.upload(nextImage, W, H, W);
+    DeviceArray<JtJJtrSO3> sum, out; sum.create(MAX_THREADS); out.create(1);
+    so3Step(a, b, toMat(basis9), toMat(kinv9), toMat(krlr9), sum, out, A9, b3, res2, threads, blocks);
+    return (int)cudaGetLastError();
+}
+
+// computeRgbResidual + rgbStep for one iteration (RGBDOdometry.cpp:381-437)
+int ref_rgb_iteration(float minScale, const short* dIdx, const short* dIdy, const float* lastDepth, const float* nextDepth,
+                      const unsigned char* lastImage, const unsigned char* nextImage, float maxDepthDelta, const float* kt3, const float* krk9,
+                      float sigmaOverride, float fx, float fy, float cx, float cy, int level, float sobelScale, int W, int H,
+                      int* count, int* sigmaSum, float* A36, float* b6)
+{
+    DeviceArray2D<short> gx, gy; gx.upload(dIdx, W * sizeof(short), H, W); gy.upload(dIdy, W * sizeof(short), H, W);
+    DeviceArray2D<float> ld, nd; ld.upload(lastDepth, W * sizeof(float), H, W); nd.upload(nextDepth, W * sizeof(float), H, W);
+    DeviceArray2D<unsigned char> li, ni, m; li.upload(lastImage, W, H, W); ni.upload(nextImage, W, H, W); m.create(H, W);
+    DeviceArray2D<DataTerm> corres; corres.create(H, W);
+    DeviceArray<int2> sumRes; sumRes.create(MAX_THREADS);
+    computeRgbResidual(minScale, gx, gy, ld, nd, li, ni, m, m, corres, sumRes, maxDepthDelta, make_float3(kt3[0], kt3[1], kt3[2]), toMat(krk9),
+                       *sigmaSum, *count, 256, 336, 0, 0);
+    DeviceArray2D<float3> cloud; cloud.create(H, W);
+    CameraModel intr(fx * (1 << level), fy * (1 << level), cx * (1 << level), cy * (1 << level));
+    projectToPointCloud(ld, cloud, intr, level);
+    DeviceArray<JtJJtrSE3> sum, out; sum.create(MAX_THREADS); out.create(1);
+    float sigma = sigmaOverride != 0 ? sigmaOverride : (float)*count;
+    rgbStep(corres, sigma, cloud, fx, fy, gx, gy, sobelScale, sum, out, A36, b6, 128, 112);
+    return (int)cudaGetLastError();
+}
+
+int ref_geometric_edges(const float* vmap, const float* nmap, int W, int H, float wD, float wC, float thr, float* edge, unsigned char* inverted)
+{
+    DeviceArray2D<float> v, n, e; DeviceArray2D<unsigned char> bin, inv;
+    v.upload(vmap, W * sizeof(float), H * 3, W); n.upload(nmap, W * sizeof(float), H * 3, W);
+    e.create(H, W); bin.create(H, W); inv.create(H, W);
+    computeGeometricSegmentationMap(v, n, e, wD, wC);
+    thresholdMap(e, bin, thr);
+    invertMap(bin, inv);
+    cudaDeviceSynchronize();
+    e.download(edge, W * sizeof(float)); inv.download(inverted, W);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+"""Pins the CPU oracle against the REFERENCE'S OWN CUDA kernels (Core/Cuda/{reduce,cudafuncs,
+segmentation}.cu compiled unmodified for sm_100 into oracle/_ref/libmf_ref.so by
+oracle/Makefile.ref).  The reference builds with --ftz --prec-div=false --prec-sqrt=false
+and FMA contraction, and accumulates its reductions in fp32 in launch-shape order, so the
+comparison is tolerance based (N8); validity (NaN) patterns and integer outputs are exact.
+GPU only: the reference kernels need a device."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib as ol
+from tests.stagewise import OracleStages
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libmf_ref.so")
+W, H = 640, 480
+f32p = C.POINTER(C.c_float)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/libmf_ref.so not built (needs /root/reference at build time)")
+    return C.CDLL(REF)
+
+
+@pytest.fixture(scope="module")
+def state():
+    """oracle state after 3 frames + frame 4 prepared for tracking"""
+    from maskfusion_b200.synth import SynthScene
+    sc = SynthScene(W, H, n_objects=0, seed=0)
+    orc = OracleStages(ol.default_config(W, H, capacityGlobal=600000))
+    for t in range(3):
+        rgb, depth, *_ = sc.render(t)
+        orc.p.process_frame(rgb, depth, t)
+    rgb, depth, *_ = sc.render(3)
+    orc.set_frame(rgb, depth); orc.generate_maps()
+    pose_before = orc.pose(0).copy()
+    orc.track()
+    return sc, orc, pose_before
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def planar_close(a, b, tol):
+    na, nb = np.isnan(a[0]), np.isnan(b[0])
+    assert np.array_equal(na, nb), f"validity differs at {(na != nb).sum()} pixels"
+    ok = ~na
+    for p in range(3):
+        d = np.abs(a[p][ok] - b[p][ok])
+        assert d.max() <= tol, (p, d.max())
+
+
+def test_vmap_nmap(ref, state):
+    sc, orc, _ = state
+    fa = orc.frame_arrays()
+    for l in range(3):
+        w, h = W >> l, H >> l
+        v = np.zeros((3, h, w), np.float32); n = np.zeros((3, h, w), np.float32)
+        d = np.ascontiguousarray(fa[f"depth{l}"])
+        assert ref.ref_vmap_nmap(ol.ptr(d), w, h, C.c_float(528 / (1 << l)), C.c_float(528 / (1 << l)), C.c_float(320 / (1 << l)),
+                                 C.c_float(240 / (1 << l)), C.c_float(4.0), ol.ptr(v), ol.ptr(n)) == 0
+        planar_close(v, fa[f"vmap{l}"], 2e-6)            # fast reciprocal (prec-div=false) + FMA
+        planar_close(n, fa[f"nmap{l}"], 2e-5)            # rsqrtf normalisation
+
+
+def test_pyramids(ref, state):
+    sc, orc, _ = state
+    fa = orc.frame_arrays()
+    for l in range(2):
+        w, h = W >> l, H >> l
+        out = np.zeros((h // 2, w // 2), np.float32)
+        assert ref.ref_pyrdown_f(ol.ptr(np.ascontiguousarray(fa[f"depth{l}"])), w, h, ol.ptr(out)) == 0
+        assert np.abs(out - fa[f"depth{l+1}"]).max() < 2e-6
+    od = orc.odom(0)
+    img0 = ol.arr(od.nextImage[0], (H, W), np.uint8) if False else None
+    rng = np.random.default_rng(0)
+    src = rng.integers(0, 255, (H, W)).astype(np.uint8); src[rng.random((H, W)) < 0.1] = 0
+    o1 = np.zeros((H // 2, W // 2), np.uint8); o2 = np.zeros((H // 2, W // 2), np.uint8)
+    assert ref.ref_pyrdown_u8(ol.ptr(src), W, H, ol.ptr(o1)) == 0
+    orc.L.orc_pyrdown_gauss_u8(ol.ptr(src), W, H, ol.ptr(o2))
+    assert np.abs(o1.astype(int) - o2.astype(int)).max() <= 1 and (o1 != o2).mean() < 1e-3
+
+
+def test_model_maps(ref, state):
+    sc, orc, pose_before = state
+    m = orc.p.model(0)
+    fill = bool(orc.L.orc_requires_fill_in(m.splatImage, W, H, C.c_float(0.75)))
+    vt = np.ascontiguousarray(orc.p.tex(0, "fillVertex" if fill else "splatVertex"))
+    nt = np.ascontiguousarray(orc.p.tex(0, "fillNormal" if fill else "splatNormal"))
+    vs = [np.zeros((3, H >> l, W >> l), np.float32) for l in range(3)]
+    ns = [np.zeros((3, H >> l, W >> l), np.float32) for l in range(3)]
+    vp = (f32p * 3)(*[a.ctypes.data_as(f32p) for a in vs]); npp = (f32p * 3)(*[a.ctypes.data_as(f32p) for a in ns])
+    R = np.ascontiguousarray(pose_before[:3, :3]); t = np.ascontiguousarray(pose_before[:3, 3])
+    assert ref.ref_model_maps(ol.ptr(vt), ol.ptr(nt), W, H, ol.ptr(R), ol.ptr(t), vp, npp) == 0
+    od = orc.odom(0)
+    for l in range(3):
+        planar_close(vs[l], ol.arr(od.vmap_g[l], (3, H >> l, W >> l), np.float32), 5e-6)
+        planar_close(ns[l], ol.arr(od.nmap_g[l], (3, H >> l, W >> l), np.float32), 5e-5)
+
+
+def test_icp_step(ref, state):
+    """icpStep (reduce.cu:446-525) with the reference's fallback launch config 128x112 (GPUConfig.h:51-58)"""
+    sc, orc, pose_before = state
+    fa = orc.frame_arrays(); od = orc.odom(0)
+    P = pose_before
+    Rpi = np.ascontiguousarray(np.linalg.inv(P[:3, :3].astype(np.float64)).astype(np.float32))
+    Rc = np.ascontiguousarray(P[:3, :3]); tc = np.ascontiguousarray(P[:3, 3])
+    for l in range(3):
+        w, h = W >> l, H >> l
+        A = np.zeros(36, np.float32); b = np.zeros(6, np.float32); res = np.zeros(2, np.float32)
+        vg = ol.arr(od.vmap_g[l], (3, h, w), np.float32); ng = ol.arr(od.nmap_g[l], (3, h, w), np.float32)
+        assert ref.ref_icp_step(ol.ptr(Rc), ol.ptr(tc), ol.ptr(fa[f"vmap{l}"]), ol.ptr(fa[f"nmap{l}"]), ol.ptr(Rpi), ol.ptr(tc),
+                                C.c_float(528 / (1 << l)), C.c_float(528 / (1 << l)), C.c_float(320 / (1 << l)), C.c_float(240 / (1 << l)),
+                                ol.ptr(np.ascontiguousarray(vg)), ol.ptr(np.ascontiguousarray(ng)), C.c_float(0.1),
+                                C.c_float(np.float32(np.sin(20.0 * 3.14159254 / 180.0))), w, h, 128, 112, ol.ptr(A), ol.ptr(b), ol.ptr(res)) == 0
+        out = np.zeros(29)
+        orc.L.orc_icp_step(ol.ptr(Rc), ol.ptr(tc), ol.ptr(fa[f"vmap{l}"]), ol.ptr(fa[f"nmap{l}"]), ol.ptr(Rpi), ol.ptr(tc),
+                           ol.cam(528 / (1 << l), 528 / (1 << l), 320 / (1 << l), 240 / (1 << l)), od.vmap_g[l], od.nmap_g[l], C.c_float(0.1),
+                           C.c_float(np.float32(np.sin(20.0 * 3.14159254 / 180.0))), w, h, ol.ptr(out))
+        Ao = np.zeros((6, 6)); bo = np.zeros(6); k = 0
+        for i in range(6):
+            for j in range(i, 7):
+                if j == 6: bo[i] = out[k]
+                else: Ao[i, j] = Ao[j, i] = out[k]
+                k += 1
+        assert abs(res[1] - out[28]) <= max(3, 1e-4 * out[28]), (l, res[1], out[28])       # inliers: gate thresholds see ulp-level differences
+        assert rel(A.reshape(6, 6), Ao) < 2e-3, (l, rel(A.reshape(6, 6), Ao))               # fp32 accumulation of ~3e5 terms
+        assert np.abs(b - bo).max() < 2e-3 * np.abs(Ao).max() ** 0.5 + 5e-2, (l, b, bo)
+
+
+def test_sobel_and_so3(ref, state):
+    sc, orc, _ = state
+    od = orc.odom(0)
+    img = np.ascontiguousarray(ol.arr(od.nextImage[0], (H, W), np.uint8)) if od.nextImage[0] else None
+    rgb, *_ = sc.render(3)
+    inten = np.zeros((H, W), np.uint8)
+    orc.L.orc_rgb_to_intensity(ol.ptr(np.ascontiguousarray(rgb)), W, H, ol.ptr(inten))
+    dx = np.zeros((H, W), np.int16); dy = np.zeros((H, W), np.int16); dxo = np.zeros((H, W), np.int16); dyo = np.zeros((H, W), np.int16)
+    assert ref.ref_sobel(ol.ptr(inten), W, H, ol.ptr(dx), ol.ptr(dy)) == 0
+    orc.L.orc_sobel(ol.ptr(inten), W, H, ol.ptr(dxo), ol.ptr(dyo))
+    assert np.abs(dx.astype(int) - dxo).max() <= 1 and np.abs(dy.astype(int) - dyo).max() <= 1     # FMA vs separate rounding at truncation edges
+    assert (dx != dxo).mean() < 1e-3
+    # SO3 step on level-2 intensities of two consecutive frames
+    a = inten[::4, ::4].copy(); rgb2, *_ = sc.render(4); i2 = np.zeros((H, W), np.uint8)
+    orc.L.orc_rgb_to_intensity(ol.ptr(np.ascontiguousarray(rgb2)), W, H, ol.ptr(i2)); b2 = i2[::4, ::4].copy()
+    w, h = W // 4, H // 4
+    K = np.array([[132.0, 0, 80], [0, 132.0, 60], [0, 0, 1]]); Kinv = np.linalg.inv(K)
+    basis = np.ascontiguousarray((K @ np.eye(3) @ Kinv).astype(np.float32)); kinv = np.ascontiguousarray(Kinv.astype(np.float32)); krlr = np.ascontiguousarray(K.astype(np.float32))
+    A = np.zeros(9, np.float32); bb = np.zeros(3, np.float32); res = np.zeros(2, np.float32)
+    assert ref.ref_so3_step(ol.ptr(a), ol.ptr(b2), ol.ptr(basis), ol.ptr(kinv), ol.ptr(krlr), w, h, 160, 64, ol.ptr(A), ol.ptr(bb), ol.ptr(res)) == 0
+    out = np.zeros(11)
+    orc.L.orc_so3_step(ol.ptr(a), ol.ptr(b2), ol.ptr(basis), ol.ptr(kinv), ol.ptr(krlr), w, h, ol.ptr(out))
+    assert res[1] == out[10]
+    assert abs(res[0] - out[9]) < 1e-3 * out[9]
+    Ao = np.array([[out[0], out[1], out[2]], [out[1], out[4], out[5]], [out[2], out[5], out[7]]])
+    assert rel(A.reshape(3, 3), Ao) < 2e-3
+
+
+def test_geometric_edges(ref, state):
+    sc, orc, _ = state
+    fa = orc.frame_arrays()
+    e = np.zeros((H, W), np.float32); inv = np.zeros((H, W), np.uint8)
+    assert ref.ref_geometric_edges(ol.ptr(fa["vmap0"]), ol.ptr(fa["nmap0"]), W, H, C.c_float(150.0), C.c_float(2.8), C.c_float(0.3), ol.ptr(e), ol.ptr(inv)) == 0
+    eo = np.zeros((H, W), np.float32); bo = np.zeros((H, W), np.uint8); io = np.zeros((H, W), np.uint8)
+    orc.L.orc_geometric_edges(ol.ptr(fa["vmap0"]), ol.ptr(fa["nmap0"]), W, H, C.c_float(150.0), C.c_float(2.8), ol.ptr(eo))
+    orc.L.orc_threshold(ol.ptr(eo), W * H, C.c_float(0.3), ol.ptr(bo)); orc.L.orc_invert(ol.ptr(bo), W * H, ol.ptr(io))
+    assert np.abs(e - eo).max() < 1e-3
+    assert (inv != io).mean() < 1e-4
