@@ -47,43 +47,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
+    """SM clock / throttle reasons sampled through NVML (the same counters nvidia-smi prints) every ~2 ms
+    during the timed regions; the timed region of this workload is too short for `nvidia-smi -lms`."""
 
     def __init__(self, gpu):
-        self.gpu, self.rows, self.proc = gpu, [], None
+        self.gpu, self.sm, self.reasons, self.stop_flag, self.ok = gpu, [], 0, False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            idx = gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                idx = int(vis.split(",")[gpu])
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:          # noqa: BLE001
+            self.err = str(e)
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
-        except Exception:
-            self.proc = None
+        if not self.ok:
+            return
+        self.stop_flag = False
+        self.t = threading.Thread(target=self._loop, daemon=True); self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                self.reasons |= nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:           # noqa: BLE001
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.stop_flag = True
+        self.t.join(timeout=1)
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        reasons = [k for k, bit in names.items() if self.reasons & bit]
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": float(self.max), "reasons": reasons, "samples": len(self.sm)}
 
 
 def make_replay(n_frames, seed):
     """synthetic replay written to a raw .klg and read back through KlgLogReader (the loader is outside the timed region)"""
     import maskfusion_b200 as mfb
     from maskfusion_b200.synth import SynthScene
+    n_frames = min(n_frames, 96)           # unique frames; longer runs replay them forwards/backwards (camera reverses)
     sc = SynthScene(W, H, n_objects=0, seed=seed)
     d16 = np.zeros((n_frames + 1, H, W), np.uint16); rgb = np.zeros((n_frames + 1, H, W, 3), np.uint8)
     for t in range(n_frames):
@@ -140,8 +154,14 @@ def run_ours(args, rank, world):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     K, Wm = args.steps, args.warmup
-    n_need = 1 + 2 * (Wm + K) + 2
+    n_need = 1 + 3 * (Wm + K) + 2
     sc, frames = make_replay(n_need, seed=rank)
+    nu = len(frames)
+
+    def fidx(j):                        # ping-pong over the unique frames: 0..nu-1, nu-2..1, 0..
+        period = 2 * (nu - 1)
+        r = j % period
+        return r if r < nu else period - r
     stream = torch.cuda.current_stream()
     cfg = mfb.default_config(W, H, capacityGlobal=CAPACITY)        # GUI defaults: ICP+RGB (w=20), SO3, -static
     mf = mfb.MaskFusion(cfg, device=local, stream=stream.cuda_stream)
@@ -163,16 +183,16 @@ def run_ours(args, rank, world):
 
     def timed(first, on_device):
         for i in range(Wm):
-            j = first + i
-            mf.processFramePtr((dev_rgb if on_device else host_rgb)[j].data_ptr(), (dev_d if on_device else host_d)[j].data_ptr(), frames[j][2], on_device)
+            j = fidx(first + i)
+            mf.processFramePtr((dev_rgb if on_device else host_rgb)[j].data_ptr(), (dev_d if on_device else host_d)[j].data_ptr(), (first + i) * 33333, on_device)
         mf.sync()
         barrier()
         l0 = mf.kernelLaunches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(K):
-            j = first + Wm + i
-            mf.processFramePtr((dev_rgb if on_device else host_rgb)[j].data_ptr(), (dev_d if on_device else host_d)[j].data_ptr(), frames[j][2], on_device)
+            j = fidx(first + Wm + i)
+            mf.processFramePtr((dev_rgb if on_device else host_rgb)[j].data_ptr(), (dev_d if on_device else host_d)[j].data_ptr(), (first + Wm + i) * 33333, on_device)
             if not on_device:
                 mf.getBackgroundModel().getPose()              # the step's result, read on the host every frame
         e1.record(stream)
@@ -182,12 +202,13 @@ def run_ours(args, rank, world):
         return ms, mf.kernelLaunches() - l0
 
     sampler = ClockSampler(local); sampler.start()
-    mf.setProfiling(True)
-    ms_dev, launches = timed(1, True)
+    ms_dev, launches = timed(1, True)                      # value: inputs resident in HBM
+    ms_e2e, _ = timed(1 + Wm + K, False)                   # e2e: pinned host buffers through the C ABI
+    clocks = sampler.stop()
+    mf.setProfiling(True)                                  # same region again with the in-stream CUDA-event stage timer
+    ms_prof, _ = timed(1 + 2 * (Wm + K), True)
     stages = mf.stageTimes()
     mf.setProfiling(False)
-    clocks = sampler.stop()
-    ms_e2e, _ = timed(1 + Wm + K, False)
     S_live = mf.getBackgroundModel().lastCount()
 
     if world > 1:
@@ -220,7 +241,8 @@ def run_ours(args, rank, world):
         "clocks": clocks,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": peak_src,
                      "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": None,
-                     "avg_launch_ms": round(avg_ms, 5), "algorithmic_bytes_per_launch": ab, "time_shares": shares},
+                     "avg_launch_ms": round(avg_ms, 5), "algorithmic_bytes_per_launch": ab, "time_shares": shares,
+                     "profiled_ms_per_step": round(ms_prof / K, 4)},
     }
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline(sample_frames=4)
@@ -237,8 +259,7 @@ def cpu_baseline(sample_frames):
     from maskfusion_b200.synth import dense_room_surfels, SynthScene
     import ctypes as C
     sc = SynthScene(W, H, n_objects=0, seed=0)
-    threads = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     p = ol.OraclePipeline(ol.default_config(W, H, capacityGlobal=CAPACITY))
     rgb, depth, *_ = sc.render(0)
     p.process_frame(rgb, depth, 0)
@@ -279,11 +300,12 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 32)))      # oracle's OpenMP sections (cpu_baseline)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

@@ -234,21 +234,38 @@ MF_D bool cleanTest(float4& vp, float4& vc, const float4& vn, const CleanParams&
     int count = 0, zCount = 0;
     const float ftime = (float)P.time;
     if (ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows) {
-        for (float i = x_n - (scale * ixs * wm); i < x_n + (scale * ixs * wm); i += ixs)
-            for (float j = y_n - (scale * iys * wm); j < y_n + (scale * iys * wm); j += iys) {
-                int tx = clampi((int)floorf(i * cols), 0, W - 1);
-                int ty = clampi((int)floorf(j * rows), 0, H - 1);
-                int q = ty * W + tx;
-                uint32_t cur = idx[q];
-                if (cur > 0u) {
-                    float4 mc = vertConf[q], ct = colorTime[q];
-                    float ddx = mc.x - lp.x, ddy = mc.y - lp.y;
-                    if (ct.z < vc.z && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z < 0.01f &&
-                        sqrtf(ddx * ddx + ddy * ddy) < vn.w * 1.4f)
-                        count++;
-                    if (ct.w == ftime && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f)
-                        zCount++;
-                }
+        // The shader walks a 4x4 (occasionally 5 on rounding) grid of half-texel steps; the taps land on
+        // only 2-3 distinct texels per axis and the per-tap tests depend on the texel alone.  So: run the
+        // literal float loops to get the texel columns/rows, then visit each DISTINCT texel once and weight
+        // its result by its multiplicity.  Same counts as the tap loop, ~4x fewer (and independent) loads.
+        int txs[5], tys[5]; int nx = 0, ny = 0;
+        for (float i = x_n - (scale * ixs * wm); i < x_n + (scale * ixs * wm); i += ixs) { if (nx < 5) txs[nx] = clampi((int)floorf(i * cols), 0, W - 1); ++nx; }
+        for (float j = y_n - (scale * iys * wm); j < y_n + (scale * iys * wm); j += iys) { if (ny < 5) tys[ny] = clampi((int)floorf(j * rows), 0, H - 1); ++ny; }
+        nx = nx > 5 ? 5 : nx; ny = ny > 5 ? 5 : ny;
+        uint32_t cur[5][5];
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                bool first = a < nx && b < ny && (a == 0 || txs[a] != txs[a - 1]) && (b == 0 || tys[b] != tys[b - 1]);
+                cur[a][b] = first ? idx[tys[b] * W + txs[a]] : 0u;
+            }
+#pragma unroll
+        for (int a = 0; a < 5; ++a)
+#pragma unroll
+            for (int b = 0; b < 5; ++b) {
+                if (cur[a][b] == 0u) continue;
+                int mx = 0, my = 0;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) { mx += (c < nx && txs[c] == txs[a]) ? 1 : 0; my += (c < ny && tys[c] == tys[b]) ? 1 : 0; }
+                int q = tys[b] * W + txs[a];
+                float4 mc = vertConf[q], ct = colorTime[q];
+                float ddx = mc.x - lp.x, ddy = mc.y - lp.y;
+                if (ct.z < vc.z && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z < 0.01f &&
+                    sqrtf(ddx * ddx + ddy * ddy) < vn.w * 1.4f)
+                    count += mx * my;
+                if (ct.w == ftime && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f)
+                    zCount += mx * my;
             }
     }
     if (count > 8 || zCount > 4) test = false;
