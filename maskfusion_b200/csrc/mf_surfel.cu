@@ -287,6 +287,98 @@ MF_D bool cleanTest(float4& vp, float4& vc, const float4& vn, const CleanParams&
     return test;
 }
 
+// Warp-cooperative form of cleanTest (same results).  Only surfels that project into the image
+// need the index-map window, and they are scattered through the store: evaluated per thread the
+// window code ran with ~9 of 32 lanes active (ncu, profiles/r01).  Here every lane does the cheap
+// projection for its own surfel, then the warp walks the lanes that need a window and spends its
+// 32 lanes on that surfel's <= 5x5 tap grid (one distinct texel per lane, weighted by multiplicity).
+// Must be called by all 32 lanes of a warp.
+MF_D bool cleanTestWarp(bool valid, float4& vp, float4& vc, const float4& vn, const CleanParams& P, const uint32_t* __restrict__ idx,
+                        const float4* __restrict__ vertConf, const float4* __restrict__ colorTime,
+                        const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int W = P.W, H = P.H;
+    const float cols = (float)W, rows = (float)H;
+    const float ftime = (float)P.time;
+    float3 lp = make_float3(0, 0, 0); float x = 0, y = 0, x_n = 0, y_n = 0, lnz = 0;
+    bool need = false;
+    if (valid) {
+        lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
+        x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
+        y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
+        x_n = x / cols; y_n = y / rows;
+        need = ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows;
+        if (need) { float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z))); lnz = fabsf(ln.z); }
+    }
+    const float stepX = 1.0f / cols, stepY = 1.0f / rows;
+    const float scale = 1.0f, wm = 2;
+    const float ixs = stepX * 0.5f / scale, iys = stepY * 0.5f / scale;
+    int count = 0, zCount = 0;
+    unsigned m = __ballot_sync(full, need);
+    while (m) {
+        const int src = __ffs(m) - 1; m &= m - 1;
+        const float sxn = __shfl_sync(full, x_n, src), syn = __shfl_sync(full, y_n, src);
+        const float slx = __shfl_sync(full, lp.x, src), sly = __shfl_sync(full, lp.y, src), slz = __shfl_sync(full, lp.z, src);
+        const float sInit = __shfl_sync(full, vc.z, src), sRad = __shfl_sync(full, vn.w, src), sLnz = __shfl_sync(full, lnz, src);
+        // literal shader loops (copy_unstable.vert:86-87): texel columns / rows of the tap grid
+        int txs[5], tys[5]; int nx = 0, ny = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { txs[k] = 0; tys[k] = 0; }
+        for (float i = sxn - (scale * ixs * wm); i < sxn + (scale * ixs * wm); i += ixs) {
+            int t = clampi((int)floorf(i * cols), 0, W - 1);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) if (k == nx) txs[k] = t;
+            ++nx;
+        }
+        for (float j = syn - (scale * iys * wm); j < syn + (scale * iys * wm); j += iys) {
+            int t = clampi((int)floorf(j * rows), 0, H - 1);
+#pragma unroll
+            for (int k = 0; k < 5; ++k) if (k == ny) tys[k] = t;
+            ++ny;
+        }
+        nx = nx > 5 ? 5 : nx; ny = ny > 5 ? 5 : ny;
+        const int a = lane / 5, b = lane - a * 5;
+        int myx = 0, myy = 0, prevx = -1, prevy = -1, mx = 0, my = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { if (k == a) myx = txs[k]; if (k == b) myy = tys[k]; if (k + 1 == a) prevx = txs[k]; if (k + 1 == b) prevy = tys[k]; }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { mx += (k < nx && txs[k] == myx) ? 1 : 0; my += (k < ny && tys[k] == myy) ? 1 : 0; }
+        const bool mine = lane < 25 && a < nx && b < ny && (a == 0 || myx != prevx) && (b == 0 || myy != prevy);
+        int c1 = 0, c2 = 0;
+        if (mine) {
+            const int q = myy * W + myx;
+            if (idx[q] > 0u) {
+                float4 mc = vertConf[q], ct = colorTime[q];
+                float ddx = mc.x - slx, ddy = mc.y - sly;
+                if (ct.z < sInit && mc.w > P.confThreshold && mc.z > slz && mc.z - slz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < sRad * 1.4f) c1 = mx * my;
+                if (ct.w == ftime && mc.w > P.confThreshold && mc.z > slz && mc.z - slz > 0.01f && sLnz > 0.85f) c2 = mx * my;
+            }
+        }
+        c1 = __reduce_add_sync(full, c1); c2 = __reduce_add_sync(full, c2);
+        if (lane == src) { count = c1; zCount = c2; }
+    }
+    bool test = true;
+    if (!valid) return false;
+    if (count > 8 || zCount > 4) test = false;
+    if (vc.w == -2) vc.w = ftime;
+    if (vc.w == -1 || ((ftime - vc.w) > 20 && vp.w < P.confThreshold)) test = false;
+    if (vc.w > 0 && ftime - vc.w > P.ftimeDelta) test = true;
+    float fxs = floorf(x), fys = floorf(y);
+    int sx = (fxs != fxs) ? 0 : (fxs < 0 ? 0 : (fxs > (float)(W - 1) ? W - 1 : (int)fxs));
+    int sy = (fys != fys) ? 0 : (fys < 0 ? 0 : (fys > (float)(H - 1) ? H - 1 : (int)fys));
+    float wDepth = depthFilt[sy * W + sx];
+    uint8_t maskValue = mask[sy * W + sx];
+    if ((maskValue != P.maskID) && maskValue < 255 && (wDepth > lp.z - 0.05f && wDepth < lp.z + 0.05f)) {
+        float f = (0.5f + 0.5f * (1 - P.outlierCoeff / 10.0f));
+        if (maskValue == 0) vp.w *= f;
+        else if (P.maskID == 0) vp.w *= 0.25f * f;
+        else vp.w *= f;
+    }
+    return test;
+}
+
 #define SCAN_BLOCK 512
 // pass 1: test every old surfel and every emitted new vertex; write the (possibly
 // re-weighted) record back in place, a keep flag, and per-block keep counts.
@@ -305,20 +397,21 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_clean_test(float4* __restrict__ 
     __shared__ uint32_t wsum[SCAN_BLOCK / 32];
     for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
-        bool k = false;
-        if (e < count) {
-            float4 vp = pos[e], vc = col[e], vn = ldStream(nrm + e);     // pos/col are written below: coherent loads
-            float w0 = vp.w, t0 = vc.w;
-            k = cleanTest(vp, vc, vn, P, idx, vertConf, colorTime, depthFilt, mask);
-            if (vp.w != w0) pos[e].w = vp.w;
-            if (vc.w != t0) col[e].w = vc.w;
+        bool valid = false;
+        const bool isOld = e < count;
+        float4 vp = make_float4(0, 0, 0, 0), vc = vp, vn = vp;
+        if (isOld) {
+            vp = pos[e]; vc = col[e]; vn = ldStream(nrm + e);            // pos/col are written below: coherent loads
+            valid = true;
         } else if (e < total) {
             uint32_t p = e - count;
-            if (aflag[p] == 2) {                 // merges (w = -1) always fail the test: skip them
-                float4 vp = m0[p], vc = m1[p], vn = m2[p];
-                k = cleanTest(vp, vc, vn, P, idx, vertConf, colorTime, depthFilt, mask);
-                m0[p].w = vp.w; m1[p].w = vc.w;
-            }
+            if (aflag[p] == 2) { vp = m0[p]; vc = m1[p]; vn = m2[p]; valid = true; }   // merges (w = -1) always fail the test: skip them
+        }
+        const float w0 = vp.w, t0 = vc.w;
+        bool k = cleanTestWarp(valid, vp, vc, vn, P, idx, vertConf, colorTime, depthFilt, mask);
+        if (valid) {
+            if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
+            else { uint32_t p = e - count; m0[p].w = vp.w; m1[p].w = vc.w; }
         }
         if (e < total) keep[e] = k ? 1 : 0;
         unsigned bal = __ballot_sync(0xffffffffu, k);
@@ -460,27 +553,49 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
                                                        float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
                                                        uint32_t drawBase, unsigned long long* __restrict__ key)
 {
+    // Warp-cooperative rasterisation: every lane projects its own surfel (streaming loads), then the
+    // warp walks the lanes whose surfel is drawable and spreads that surfel's point-sprite square over
+    // its 32 lanes (one fragment test + 64-bit atomicMin per lane).  The per-thread pixel loop it
+    // replaces ran with ~5 of 32 lanes active (ncu, profiles/r01).
+    const unsigned full = 0xffffffffu;
     const uint32_t count = *countPtr;
-    for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
-        float4 p = ldStream(pos + id);
-        // cheap rejects before touching the other two planes
-        float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
-        if (ph.z > maxDepth || ph.z < 0 || p.w < confThreshold) continue;
-        float4 c = ldStream(col + id), nr = ldStream(nrm + id);
-        SplatVS v = splatVertex(p, c, nr, tinv, cam, W, H, maxDepth, confThreshold, ftime, fmaxTime, ftimeDelta);
-        if (!v.ok) continue;
-        int x0, x1, y0, y1;
-        splatRange(v, W, H, x0, x1, y0, y1);
-        for (int py = y0; py <= y1; ++py)
-            for (int px = x0; px <= x1; ++px) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
+        const uint32_t id = base + lane;
+        SplatVS v; v.ok = false;
+        int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+        if (id < count) {
+            float4 p = ldStream(pos + id);
+            // cheap rejects before touching the other two planes
+            float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
+            if (!(ph.z > maxDepth || ph.z < 0 || p.w < confThreshold)) {
+                float4 c = ldStream(col + id), nr = ldStream(nrm + id);
+                v = splatVertex(p, c, nr, tinv, cam, W, H, maxDepth, confThreshold, ftime, fmaxTime, ftimeDelta);
+                if (v.ok) splatRange(v, W, H, x0, x1, y0, y1);
+            }
+        }
+        unsigned m = __ballot_sync(full, v.ok && x1 >= x0 && y1 >= y0);
+        while (m) {
+            const int src = __ffs(m) - 1; m &= m - 1;
+            SplatVS s;
+            s.pos = make_float3(__shfl_sync(full, v.pos.x, src), __shfl_sync(full, v.pos.y, src), __shfl_sync(full, v.pos.z, src));
+            s.n = make_float3(__shfl_sync(full, v.n.x, src), __shfl_sync(full, v.n.y, src), __shfl_sync(full, v.n.z, src));
+            s.rad = __shfl_sync(full, v.rad, src);
+            const int sx0 = __shfl_sync(full, x0, src), sx1 = __shfl_sync(full, x1, src), sy0 = __shfl_sync(full, y0, src), sy1 = __shfl_sync(full, y1, src);
+            const int w = sx1 - sx0 + 1, n = w * (sy1 - sy0 + 1);
+            const uint32_t sid = drawBase + base + (uint32_t)src;
+            for (int t = lane; t < n; t += 32) {
+                const int py = sy0 + t / w, px = sx0 + t - (t / w) * w;
                 float3 cp;
-                if (!splatFragment(v, cam, (float)px + 0.5f, (float)py + 0.5f, cp)) continue;
+                if (!splatFragment(s, cam, (float)px + 0.5f, (float)py + 0.5f, cp)) continue;
                 float fd = (cp.z / (2 * maxDepth)) + 0.5f;
                 if (!(fd >= 0.0f && fd < 1.0f)) continue;
-                unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | (drawBase + id);
+                unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | sid;
                 unsigned long long* dst = key + (py * W + px);
                 if (k < *dst) atomicMin(dst, k);
             }
+        }
     }
 }
 
