@@ -215,152 +215,75 @@ struct CleanParams {
     Rt tinv; Cam cam; int W, H; int time; float ftimeDelta; float confThreshold; float outlierCoeff; uint8_t maskID;
 };
 
-MF_D bool cleanTest(float4& vp, float4& vc, const float4& vn, const CleanParams& P, const uint32_t* __restrict__ idx,
-                    const float4* __restrict__ vertConf, const float4* __restrict__ colorTime,
-                    const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask)
+// ---- clean, restructured for dense execution -------------------------------------------------
+// Only surfels that project into the image need the index-map window and they are scattered through
+// the store: evaluated inline per thread the window code ran with ~9 of 32 lanes active, and a
+// warp-cooperative variant was instruction bound (ncu, profiles/).  So each block (1) projects its
+// 512 surfels, (2) compacts the ones that need a window into shared memory, (3) runs the window code
+// densely, one compacted entry per thread, (4) hands the counts back to the owning threads.
+struct CleanEntry { float xn, yn, lx, ly, lz, init, rad, lnz; };
+
+// window of copy_unstable.vert:86-113 for one surfel.  The shader walks a 4x4 (5 on rounding) grid of
+// half-texel steps; the taps land on 2-3 distinct texels per axis and the per-tap tests depend on the texel
+// alone: run the literal float loops for the texel columns/rows, visit each DISTINCT texel once, weight by
+// its multiplicity (same counts as the tap loop, ~4x fewer loads).
+MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const uint32_t* __restrict__ idx, const float4* __restrict__ vertConf,
+                      const float4* __restrict__ colorTime, int& count, int& zCount)
 {
     const int W = P.W, H = P.H;
-    bool test = true;
-    float3 lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
-    const float cols = (float)W, rows = (float)H;
-    float x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
-    float y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
-    float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
-    float x_n = x / cols, y_n = y / rows;
-    float stepX = 1.0f / cols, stepY = 1.0f / rows;
-    const float scale = 1.0f;
-    float ixs = stepX * 0.5f / scale, iys = stepY * 0.5f / scale;
-    const float wm = 2;
-    int count = 0, zCount = 0;
-    const float ftime = (float)P.time;
-    if (ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows) {
-        // The shader walks a 4x4 (occasionally 5 on rounding) grid of half-texel steps; the taps land on
-        // only 2-3 distinct texels per axis and the per-tap tests depend on the texel alone.  So: run the
-        // literal float loops to get the texel columns/rows, then visit each DISTINCT texel once and weight
-        // its result by its multiplicity.  Same counts as the tap loop, ~4x fewer (and independent) loads.
-        int txs[5], tys[5]; int nx = 0, ny = 0;
-        for (float i = x_n - (scale * ixs * wm); i < x_n + (scale * ixs * wm); i += ixs) { if (nx < 5) txs[nx] = clampi((int)floorf(i * cols), 0, W - 1); ++nx; }
-        for (float j = y_n - (scale * iys * wm); j < y_n + (scale * iys * wm); j += iys) { if (ny < 5) tys[ny] = clampi((int)floorf(j * rows), 0, H - 1); ++ny; }
-        nx = nx > 5 ? 5 : nx; ny = ny > 5 ? 5 : ny;
-        uint32_t cur[5][5];
-#pragma unroll
-        for (int a = 0; a < 5; ++a)
-#pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                bool first = a < nx && b < ny && (a == 0 || txs[a] != txs[a - 1]) && (b == 0 || tys[b] != tys[b - 1]);
-                cur[a][b] = first ? idx[tys[b] * W + txs[a]] : 0u;
-            }
-#pragma unroll
-        for (int a = 0; a < 5; ++a)
-#pragma unroll
-            for (int b = 0; b < 5; ++b) {
-                if (cur[a][b] == 0u) continue;
-                int mx = 0, my = 0;
-#pragma unroll
-                for (int c = 0; c < 5; ++c) { mx += (c < nx && txs[c] == txs[a]) ? 1 : 0; my += (c < ny && tys[c] == tys[b]) ? 1 : 0; }
-                int q = tys[b] * W + txs[a];
-                float4 mc = vertConf[q], ct = colorTime[q];
-                float ddx = mc.x - lp.x, ddy = mc.y - lp.y;
-                if (ct.z < vc.z && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z < 0.01f &&
-                    sqrtf(ddx * ddx + ddy * ddy) < vn.w * 1.4f)
-                    count += mx * my;
-                if (ct.w == ftime && mc.w > P.confThreshold && mc.z > lp.z && mc.z - lp.z > 0.01f && fabsf(ln.z) > 0.85f)
-                    zCount += mx * my;
-            }
-    }
-    if (count > 8 || zCount > 4) test = false;
-    if (vc.w == -2) vc.w = ftime;
-    if (vc.w == -1 || ((ftime - vc.w) > 20 && vp.w < P.confThreshold)) test = false;
-    if (vc.w > 0 && ftime - vc.w > P.ftimeDelta) test = true;
-
-    float fxs = floorf(x), fys = floorf(y);
-    int sx = (fxs != fxs) ? 0 : (fxs < 0 ? 0 : (fxs > (float)(W - 1) ? W - 1 : (int)fxs));
-    int sy = (fys != fys) ? 0 : (fys < 0 ? 0 : (fys > (float)(H - 1) ? H - 1 : (int)fys));
-    float wDepth = depthFilt[sy * W + sx];
-    uint8_t maskValue = mask[sy * W + sx];
-    if ((maskValue != P.maskID) && maskValue < 255 && (wDepth > lp.z - 0.05f && wDepth < lp.z + 0.05f)) {
-        float f = (0.5f + 0.5f * (1 - P.outlierCoeff / 10.0f));
-        if (maskValue == 0) vp.w *= f;
-        else if (P.maskID == 0) vp.w *= 0.25f * f;
-        else vp.w *= f;
-    }
-    return test;
-}
-
-// Warp-cooperative form of cleanTest (same results).  Only surfels that project into the image
-// need the index-map window, and they are scattered through the store: evaluated per thread the
-// window code ran with ~9 of 32 lanes active (ncu, profiles/r01).  Here every lane does the cheap
-// projection for its own surfel, then the warp walks the lanes that need a window and spends its
-// 32 lanes on that surfel's <= 5x5 tap grid (one distinct texel per lane, weighted by multiplicity).
-// Must be called by all 32 lanes of a warp.
-MF_D bool cleanTestWarp(bool valid, float4& vp, float4& vc, const float4& vn, const CleanParams& P, const uint32_t* __restrict__ idx,
-                        const float4* __restrict__ vertConf, const float4* __restrict__ colorTime,
-                        const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask)
-{
-    const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int W = P.W, H = P.H;
-    const float cols = (float)W, rows = (float)H;
-    const float ftime = (float)P.time;
-    float3 lp = make_float3(0, 0, 0); float x = 0, y = 0, x_n = 0, y_n = 0, lnz = 0;
-    bool need = false;
-    if (valid) {
-        lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
-        x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
-        y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
-        x_n = x / cols; y_n = y / rows;
-        need = ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows;
-        if (need) { float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z))); lnz = fabsf(ln.z); }
-    }
+    const float cols = (float)W, rows = (float)H, ftime = (float)P.time;
     const float stepX = 1.0f / cols, stepY = 1.0f / rows;
     const float scale = 1.0f, wm = 2;
     const float ixs = stepX * 0.5f / scale, iys = stepY * 0.5f / scale;
-    int count = 0, zCount = 0;
-    unsigned m = __ballot_sync(full, need);
-    while (m) {
-        const int src = __ffs(m) - 1; m &= m - 1;
-        const float sxn = __shfl_sync(full, x_n, src), syn = __shfl_sync(full, y_n, src);
-        const float slx = __shfl_sync(full, lp.x, src), sly = __shfl_sync(full, lp.y, src), slz = __shfl_sync(full, lp.z, src);
-        const float sInit = __shfl_sync(full, vc.z, src), sRad = __shfl_sync(full, vn.w, src), sLnz = __shfl_sync(full, lnz, src);
-        // literal shader loops (copy_unstable.vert:86-87): texel columns / rows of the tap grid
-        int txs[5], tys[5]; int nx = 0, ny = 0;
+    int txs[5], tys[5]; int nx = 0, ny = 0;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { txs[k] = 0; tys[k] = 0; }
-        for (float i = sxn - (scale * ixs * wm); i < sxn + (scale * ixs * wm); i += ixs) {
-            int t = clampi((int)floorf(i * cols), 0, W - 1);
+    for (int k = 0; k < 5; ++k) { txs[k] = -1; tys[k] = -1; }
+    for (float i = e.xn - (scale * ixs * wm); i < e.xn + (scale * ixs * wm); i += ixs) {
+        int t = clampi((int)floorf(i * cols), 0, W - 1);
 #pragma unroll
-            for (int k = 0; k < 5; ++k) if (k == nx) txs[k] = t;
-            ++nx;
-        }
-        for (float j = syn - (scale * iys * wm); j < syn + (scale * iys * wm); j += iys) {
-            int t = clampi((int)floorf(j * rows), 0, H - 1);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) if (k == ny) tys[k] = t;
-            ++ny;
-        }
-        nx = nx > 5 ? 5 : nx; ny = ny > 5 ? 5 : ny;
-        const int a = lane / 5, b = lane - a * 5;
-        int myx = 0, myy = 0, prevx = -1, prevy = -1, mx = 0, my = 0;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { if (k == a) myx = txs[k]; if (k == b) myy = tys[k]; if (k + 1 == a) prevx = txs[k]; if (k + 1 == b) prevy = tys[k]; }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) { mx += (k < nx && txs[k] == myx) ? 1 : 0; my += (k < ny && tys[k] == myy) ? 1 : 0; }
-        const bool mine = lane < 25 && a < nx && b < ny && (a == 0 || myx != prevx) && (b == 0 || myy != prevy);
-        int c1 = 0, c2 = 0;
-        if (mine) {
-            const int q = myy * W + myx;
-            if (idx[q] > 0u) {
-                float4 mc = vertConf[q], ct = colorTime[q];
-                float ddx = mc.x - slx, ddy = mc.y - sly;
-                if (ct.z < sInit && mc.w > P.confThreshold && mc.z > slz && mc.z - slz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < sRad * 1.4f) c1 = mx * my;
-                if (ct.w == ftime && mc.w > P.confThreshold && mc.z > slz && mc.z - slz > 0.01f && sLnz > 0.85f) c2 = mx * my;
-            }
-        }
-        c1 = __reduce_add_sync(full, c1); c2 = __reduce_add_sync(full, c2);
-        if (lane == src) { count = c1; zCount = c2; }
+        for (int k = 0; k < 5; ++k) if (k == nx) txs[k] = t;
+        ++nx;
     }
+    for (float j = e.yn - (scale * iys * wm); j < e.yn + (scale * iys * wm); j += iys) {
+        int t = clampi((int)floorf(j * rows), 0, H - 1);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) if (k == ny) tys[k] = t;
+        ++ny;
+    }
+    // unused slots hold -1 and never match a texel
+    int mxs[5], mys[5];
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        mxs[a] = 0; mys[a] = 0;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) { mxs[a] += (txs[c] == txs[a]) ? 1 : 0; mys[a] += (tys[c] == tys[a]) ? 1 : 0; }
+    }
+    count = 0; zCount = 0;
+#pragma unroll
+    for (int a = 0; a < 5; ++a) {
+        if (txs[a] < 0 || (a > 0 && txs[a] == txs[a - 1])) continue;
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            if (tys[b] < 0 || (b > 0 && tys[b] == tys[b - 1])) continue;
+            const int q = tys[b] * W + txs[a];
+            if (idx[q] == 0u) continue;
+            float4 mc = vertConf[q], ct = colorTime[q];
+            float ddx = mc.x - e.lx, ddy = mc.y - e.ly;
+            if (ct.z < e.init && mc.w > P.confThreshold && mc.z > e.lz && mc.z - e.lz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < e.rad * 1.4f)
+                count += mxs[a] * mys[b];
+            if (ct.w == ftime && mc.w > P.confThreshold && mc.z > e.lz && mc.z - e.lz > 0.01f && e.lnz > 0.85f)
+                zCount += mxs[a] * mys[b];
+        }
+    }
+}
+
+// everything of copy_unstable.vert after the window (:128-157)
+MF_D bool cleanFinish(float4& vp, float4& vc, float x, float y, float lpz, int count, int zCount, const CleanParams& P,
+                      const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask)
+{
+    const int W = P.W, H = P.H;
+    const float ftime = (float)P.time;
     bool test = true;
-    if (!valid) return false;
     if (count > 8 || zCount > 4) test = false;
     if (vc.w == -2) vc.w = ftime;
     if (vc.w == -1 || ((ftime - vc.w) > 20 && vp.w < P.confThreshold)) test = false;
@@ -370,7 +293,7 @@ MF_D bool cleanTestWarp(bool valid, float4& vp, float4& vc, const float4& vn, co
     int sy = (fys != fys) ? 0 : (fys < 0 ? 0 : (fys > (float)(H - 1) ? H - 1 : (int)fys));
     float wDepth = depthFilt[sy * W + sx];
     uint8_t maskValue = mask[sy * W + sx];
-    if ((maskValue != P.maskID) && maskValue < 255 && (wDepth > lp.z - 0.05f && wDepth < lp.z + 0.05f)) {
+    if ((maskValue != P.maskID) && maskValue < 255 && (wDepth > lpz - 0.05f && wDepth < lpz + 0.05f)) {
         float f = (0.5f + 0.5f * (1 - P.outlierCoeff / 10.0f));
         if (maskValue == 0) vp.w *= f;
         else if (P.maskID == 0) vp.w *= 0.25f * f;
@@ -395,6 +318,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_clean_test(float4* __restrict__ 
     const uint32_t total = count + (uint32_t)Ppix;
     const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
     __shared__ uint32_t wsum[SCAN_BLOCK / 32];
+    __shared__ int wneed[SCAN_BLOCK / 32];
+    __shared__ CleanEntry entries[SCAN_BLOCK];
+    __shared__ int2 results[SCAN_BLOCK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float cols = (float)P.W, rows = (float)P.H, ftime = (float)P.time;
     for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
         bool valid = false;
@@ -408,19 +336,52 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_clean_test(float4* __restrict__ 
             if (aflag[p] == 2) { vp = m0[p]; vc = m1[p]; vn = m2[p]; valid = true; }   // merges (w = -1) always fail the test: skip them
         }
         const float w0 = vp.w, t0 = vc.w;
-        bool k = cleanTestWarp(valid, vp, vc, vn, P, idx, vertConf, colorTime, depthFilt, mask);
+        // (1) projection
+        float3 lp = make_float3(0, 0, 0); float x = 0, y = 0;
+        bool need = false;
         if (valid) {
+            lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
+            x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
+            y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
+            need = ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows;
+        }
+        // (2) compact the window candidates of this block into shared memory
+        unsigned nb = __ballot_sync(0xffffffffu, need);
+        if (lane == 0) wneed[warp] = __popc(nb);
+        __syncthreads();
+        int off = 0, nNeed = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_BLOCK / 32; ++w) { int c = wneed[w]; if (w < warp) off += c; nNeed += c; }
+        const int slot = off + __popc(nb & ((1u << lane) - 1));
+        if (need) {
+            float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
+            CleanEntry ce; ce.xn = x / cols; ce.yn = y / rows; ce.lx = lp.x; ce.ly = lp.y; ce.lz = lp.z; ce.init = vc.z; ce.rad = vn.w; ce.lnz = fabsf(ln.z);
+            entries[slot] = ce;
+        }
+        __syncthreads();
+        // (3) dense window evaluation: one compacted entry per thread
+        if ((int)threadIdx.x < nNeed) {
+            int c1, c2;
+            cleanWindow(entries[threadIdx.x], P, idx, vertConf, colorTime, c1, c2);
+            results[threadIdx.x] = make_int2(c1, c2);
+        }
+        __syncthreads();
+        // (4) back to the owners
+        bool k = false;
+        if (valid) {
+            int2 r = need ? results[slot] : make_int2(0, 0);
+            k = cleanFinish(vp, vc, x, y, lp.z, r.x, r.y, P, depthFilt, mask);
             if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
             else { uint32_t p = e - count; m0[p].w = vp.w; m1[p].w = vc.w; }
         }
         if (e < total) keep[e] = k ? 1 : 0;
         unsigned bal = __ballot_sync(0xffffffffu, k);
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(bal);
+        if (lane == 0) wsum[warp] = __popc(bal);
         __syncthreads();
         if (threadIdx.x == 0) {
-            uint32_t s = 0;
-            for (int w = 0; w < SCAN_BLOCK / 32; ++w) s += wsum[w];
-            blockSums[blk] = s;
+            uint32_t sum = 0;
+            for (int w = 0; w < SCAN_BLOCK / 32; ++w) sum += wsum[w];
+            blockSums[blk] = sum;
         }
         __syncthreads();
     }
@@ -553,16 +514,20 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
                                                        float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
                                                        uint32_t drawBase, unsigned long long* __restrict__ key)
 {
-    // Warp-cooperative rasterisation: every lane projects its own surfel (streaming loads), then the
-    // warp walks the lanes whose surfel is drawable and spreads that surfel's point-sprite square over
-    // its 32 lanes (one fragment test + 64-bit atomicMin per lane).  The per-thread pixel loop it
-    // replaces ran with ~5 of 32 lanes active (ncu, profiles/r01).
-    const unsigned full = 0xffffffffu;
+    // Flattened rasterisation.  A block projects 256 surfels, compacts the drawable ones with the exclusive
+    // prefix sum of their fragment counts (point-sprite squares, 1 .. 2047^2 pixels) into shared memory, and
+    // then walks the FLATTENED fragment list with all threads: fragment f belongs to the entry found by binary
+    // search in the prefix array.  Perfectly balanced whatever the mix of far (1 px) and near (large) surfels;
+    // the per-thread pixel loop it replaces ran with ~5 of 32 lanes active (ncu, profiles/).
+    struct Entry { float px, py, pz, nx, ny, nz, rad; int x0, y0, w; uint32_t id; };
+    __shared__ Entry ent[256];
+    __shared__ int offs[257];
+    __shared__ int wtot[8], wcnt[8];
     const uint32_t count = *countPtr;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < count; base += stride) {
-        const uint32_t id = base + lane;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
+        const uint32_t id = base + threadIdx.x;
         SplatVS v; v.ok = false;
         int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
         if (id < count) {
@@ -575,27 +540,44 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
                 if (v.ok) splatRange(v, W, H, x0, x1, y0, y1);
             }
         }
-        unsigned m = __ballot_sync(full, v.ok && x1 >= x0 && y1 >= y0);
-        while (m) {
-            const int src = __ffs(m) - 1; m &= m - 1;
-            SplatVS s;
-            s.pos = make_float3(__shfl_sync(full, v.pos.x, src), __shfl_sync(full, v.pos.y, src), __shfl_sync(full, v.pos.z, src));
-            s.n = make_float3(__shfl_sync(full, v.n.x, src), __shfl_sync(full, v.n.y, src), __shfl_sync(full, v.n.z, src));
-            s.rad = __shfl_sync(full, v.rad, src);
-            const int sx0 = __shfl_sync(full, x0, src), sx1 = __shfl_sync(full, x1, src), sy0 = __shfl_sync(full, y0, src), sy1 = __shfl_sync(full, y1, src);
-            const int w = sx1 - sx0 + 1, n = w * (sy1 - sy0 + 1);
-            const uint32_t sid = drawBase + base + (uint32_t)src;
-            for (int t = lane; t < n; t += 32) {
-                const int py = sy0 + t / w, px = sx0 + t - (t / w) * w;
-                float3 cp;
-                if (!splatFragment(s, cam, (float)px + 0.5f, (float)py + 0.5f, cp)) continue;
-                float fd = (cp.z / (2 * maxDepth)) + 0.5f;
-                if (!(fd >= 0.0f && fd < 1.0f)) continue;
-                unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | sid;
-                unsigned long long* dst = key + (py * W + px);
-                if (k < *dst) atomicMin(dst, k);
-            }
+        const bool draw = v.ok && x1 >= x0 && y1 >= y0;
+        const int nfrag = draw ? (x1 - x0 + 1) * (y1 - y0 + 1) : 0;
+        // block exclusive scans: fragment offsets and compact slots
+        int incl = nfrag;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        unsigned db = __ballot_sync(0xffffffffu, draw);
+        if (lane == 31) wtot[warp] = incl;
+        if (lane == 0) wcnt[warp] = __popc(db);
+        __syncthreads();
+        int fbase = 0, sbase = 0, total = 0, nent = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { if (w < warp) { fbase += wtot[w]; sbase += wcnt[w]; } total += wtot[w]; nent += wcnt[w]; }
+        if (draw) {
+            const int slot = sbase + __popc(db & ((1u << lane) - 1));
+            Entry e; e.px = v.pos.x; e.py = v.pos.y; e.pz = v.pos.z; e.nx = v.n.x; e.ny = v.n.y; e.nz = v.n.z; e.rad = v.rad;
+            e.x0 = x0; e.y0 = y0; e.w = x1 - x0 + 1; e.id = drawBase + id;
+            ent[slot] = e;
+            offs[slot] = fbase + incl - nfrag;
         }
+        if (threadIdx.x == 0) offs[nent] = total;
+        __syncthreads();
+        for (int f = threadIdx.x; f < total; f += blockDim.x) {
+            int lo = 0, hi = nent - 1;                       // last entry with offs[e] <= f
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (offs[mid] <= f) lo = mid; else hi = mid - 1; }
+            const Entry& e = ent[lo];
+            const int t = f - offs[lo];
+            const int py = e.y0 + t / e.w, px = e.x0 + t - (t / e.w) * e.w;
+            SplatVS sv; sv.pos = make_float3(e.px, e.py, e.pz); sv.n = make_float3(e.nx, e.ny, e.nz); sv.rad = e.rad;
+            float3 cp;
+            if (!splatFragment(sv, cam, (float)px + 0.5f, (float)py + 0.5f, cp)) continue;
+            float fd = (cp.z / (2 * maxDepth)) + 0.5f;
+            if (!(fd >= 0.0f && fd < 1.0f)) continue;
+            unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | e.id;
+            unsigned long long* dst = key + (py * W + px);
+            if (k < *dst) atomicMin(dst, k);
+        }
+        __syncthreads();
     }
 }
 

@@ -74,6 +74,9 @@ orc_mf* orc_mf_create(const orc_config* cfg)
         h->depthPyr[l] = (float*)calloc(Pl, 4); h->maskPyr[l] = (uint8_t*)calloc(Pl, 1);
         h->vmap[l] = (float*)calloc(Pl * 3, 4); h->nmap[l] = (float*)calloc(Pl * 3, 4);
     }
+    h->projKeys = (uint64_t*)calloc(P, 8); h->projectedIDs = (uint8_t*)calloc(P, 1); h->fullSeg = (uint8_t*)calloc(P, 1);
+    h->edgeMap = (float*)calloc(P, 4); h->edgeBin = (uint8_t*)calloc(P, 1); h->edgeBuf = (uint8_t*)calloc(P, 1);
+    orc_mfseg_state_init(&h->seg, cfg->width, cfg->height);
     h->nextID = 0;
     h->models[0] = model_create(h, h->nextID++, cfg->confGlobal, 1, cfg->capacityGlobal);   /* MaskFusion.cpp:80-81 */
     h->nmodels = 1;
@@ -85,6 +88,8 @@ void orc_mf_destroy(orc_mf* h)
     if (!h) return;
     for (int i = 0; i < h->nmodels; ++i) model_destroy(h->models[i]);
     free(h->rgb); free(h->depthRaw); free(h->depthFilt); free(h->mask);
+    free(h->projKeys); free(h->projectedIDs); free(h->fullSeg); free(h->edgeMap); free(h->edgeBin); free(h->edgeBuf);
+    orc_mfseg_state_free(&h->seg);
     for (int l = 0; l < 3; ++l) { free(h->depthPyr[l]); free(h->maskPyr[l]); free(h->vmap[l]); free(h->nmap[l]); }
     free(h);
 }
@@ -258,11 +263,69 @@ void orc_mf_set_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, const 
     if (mask) memcpy(h->mask, mask, P); else memset(h->mask, 0, P);
 }
 
-int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp)
+/* GlobalProjection::project + downloadDirect (GlobalProjection.cpp:43-111): every model splatted with the fixed
+ * confidence threshold 12 (:61) into one depth-tested image; draw order = list order, then surfel id. */
+void orc_mf_global_projection(orc_mf* h)
 {
-    int W = h->cfg.width, H = h->cfg.height;
-    if (h->cfg.enableMultipleModels) return -1;          /* multi-model schedule: see orc_multi.c (round 2) */
-    orc_mf_set_frame(h, rgb3, depth, 0);
+    int W = h->cfg.width, H = h->cfg.height; size_t P = (size_t)W * H;
+    uint32_t base[257]; base[0] = 0;
+    orc_global_projection_begin(W, H, h->projKeys);
+    for (int i = 0; i < h->nmodels; ++i) {
+        orc_model* m = h->models[i];
+        orc_global_projection_add(m->surf[m->target], m->count, m->pose, h->cam, W, H, h->cfg.depthCutoff, 12.0f, h->tick, h->tick,
+                                  h->cfg.timeDelta, base[i], h->projKeys);
+        base[i + 1] = base[i] + (uint32_t)m->count;
+    }
+    for (size_t p = 0; p < P; ++p) {
+        uint8_t id = 0;
+        if (h->projKeys[p] != ~0ull) {
+            uint32_t d = (uint32_t)(h->projKeys[p] & 0xffffffffu);
+            for (int i = 0; i < h->nmodels; ++i) if (d >= base[i] && d < base[i + 1]) { id = (uint8_t)h->models[i]->id; break; }
+        }
+        h->projectedIDs[p] = id;
+    }
+}
+
+/* MfSegmentation::performSegmentation (MfSegmentation.cpp:83-538): GPU-kernel part restated by orc_geometric_edges /
+ * orc_threshold / orc_morph_close / orc_invert (uses the level-0 TRACKING maps, :149-151), CPU part by orc_mfseg_cpu. */
+void orc_mf_segmentation(orc_mf* h, const uint8_t* mask, const int32_t* classIDs, int nMasks, int allowNew, orc_mfseg_out* out)
+{
+    int W = h->cfg.width, H = h->cfg.height; size_t P = (size_t)W * H;
+    orc_geometric_edges(h->vmap[0], h->nmap[0], W, H, h->cfg.segWeightDistance, h->cfg.segWeightConvexity, h->edgeMap);
+    orc_threshold(h->edgeMap, (int)P, h->cfg.segThreshold, h->edgeBin);
+    orc_morph_close(h->edgeBin, h->edgeBuf, W, H, h->cfg.segMorphEdgeRadius, h->cfg.segMorphEdgeIterations);
+    orc_invert(h->edgeBin, (int)P, h->edgeBuf);
+    uint8_t ids[256]; int32_t cls[256];
+    for (int i = 0; i < h->nmodels; ++i) { ids[i] = (uint8_t)h->models[i]->id; cls[i] = h->models[i]->classID; }
+    orc_mfseg_in in;
+    memset(&in, 0, sizeof in);
+    in.W = W; in.H = H; in.edgesInv = h->edgeBuf; in.depth = h->depthRaw; in.mask = mask; in.nMasks = nMasks; in.classIDs = classIDs;
+    in.projectedIDs = h->projectedIDs; in.nModels = h->nmodels; in.modelIDs = ids; in.modelClassIDs = cls;
+    in.nextModelID = h->nextID; in.allowNew = allowNew; in.minRelSizeNew = h->cfg.minRelSizeNew; in.maxRelSizeNew = h->cfg.maxRelSizeNew;
+    in.morphMaskRadius = h->cfg.segMorphMaskRadius; in.morphMaskIterations = h->cfg.segMorphMaskIterations;
+    out->fullSegmentation = h->fullSeg; out->labels = 0;
+    orc_mfseg_cpu(&h->seg, &in, out);
+}
+
+/* MaskFusion::getNextModelID(assign=true), MaskFusion.cpp:712-730 */
+static uint8_t next_model_id_assign(orc_mf* h)
+{
+    uint8_t next = h->nextID;
+    for (;;) {
+        h->nextID++;
+        int occupied = 0;
+        for (int i = 0; i < h->nmodels; ++i) if (h->nextID == h->models[i]->id) occupied = 1;
+        if (!occupied) break;
+    }
+    return next;
+}
+
+int orc_mf_process_frame_ex(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp, const uint8_t* maskIn,
+                            const int32_t* classIDs, int nMasks)
+{
+    int W = h->cfg.width, H = h->cfg.height; size_t P = (size_t)W * H;
+    const int multi = h->cfg.enableMultipleModels;
+    orc_mf_set_frame(h, rgb3, depth, multi ? h->mask : 0);          /* multi: textureMask keeps the last segmentation until :297 */
     orc_model* g = h->models[0];
     if (h->tick == 1) {
         g->count = orc_init_model(h->rgb, h->depthRaw, h->depthFilt, h->cam, W, H, h->tick, h->cfg.maxDepthProcessed,
@@ -271,11 +334,53 @@ int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int
     } else {
         orc_generate_frame_maps(h);
         orc_model_track(h, g, 0);
-        for (int i = 1; i < h->nmodels; ++i) {
+        for (int i = 1; i < h->nmodels; ++i) {                       /* MaskFusion.cpp:258-276 */
             orc_model* m = h->models[i];
-            float nw[16];
-            orc_pose_mul(m->initialC2Winv, g->pose, nw);                 /* updateStaticPose, Model.h:263 */
-            memcpy(m->lastPose, m->pose, sizeof m->pose); memcpy(m->pose, nw, sizeof nw);
+            if (m->nonstatic || h->cfg.trackAllModels) {
+                float T[16];
+                orc_model_track(h, m, T);
+                float d = sqrtf((T[3] * T[3] + T[7] * T[7]) + T[11] * T[11]);
+                if (d > 0.2f) {                                      /* inactivateModel (:268-272) */
+                    model_destroy(m);
+                    for (int k = i; k + 1 < h->nmodels; ++k) h->models[k] = h->models[k + 1];
+                    h->nmodels--; --i;
+                }
+            } else {
+                float nw[16];
+                orc_pose_mul(m->initialC2Winv, g->pose, nw);          /* updateStaticPose, Model.h:263 */
+                memcpy(m->lastPose, m->pose, sizeof m->pose); memcpy(m->pose, nw, sizeof nw);
+            }
+        }
+        if (multi) {
+            orc_mf_global_projection(h);                             /* :289-290 */
+            if (h->spawnOffset < h->cfg.modelSpawnOffset) h->spawnOffset++;
+            orc_mfseg_out so;
+            orc_mf_segmentation(h, maskIn, classIDs, nMasks, h->spawnOffset >= h->cfg.modelSpawnOffset, &so);
+            memcpy(h->mask, h->fullSeg, P);                          /* textureMask upload, :297 */
+            h->lastHasNewLabel = so.hasNewLabel;
+            orc_model* nm = 0;
+            if (so.hasNewLabel) {                                    /* spawnObjectModel + moveNewModelToList, :313-334, :671-684 */
+                uint8_t id = next_model_id_assign(h);
+                nm = model_create(h, id, h->cfg.confObject, 0, h->cfg.capacityObject);
+                orc_odom_init_first_rgb(nm->odom, h->rgb);
+                float ginv[16]; orc_pose_inverse(g->pose, ginv);
+                orc_pose_mul(nm->pose, ginv, nm->initialC2Winv);     /* makeStatic, Model.h:264 */
+                nm->isStatic = 1;
+                h->spawnOffset = 0;
+                nm->maxDepth = 30.0f + 30.0f * 1.2f;                 /* getMaxDepth(depthMean=30, depthStd=30), :292,328 */
+                nm->classID = so.newClassID;
+                h->models[h->nmodels++] = nm;
+            }
+            for (int i = 1; i < h->nmodels; ++i) h->models[i]->maxDepth = 30.0f + 30.0f * 1.2f;     /* :337-341 */
+            if (nm) {                                                /* :344-353 */
+                orc_model_predict_indices(h, nm, h->tick);
+                orc_model_fuse(h, nm, h->tick, h->cfg.maxDepthProcessed, 100.0f);
+                orc_model_clean(h, nm, h->tick);
+            }
+            for (int i = 1; i < h->nmodels; ++i) {                   /* :369-374 */
+                float f = (float)h->models[i]->age / 25.0f;
+                h->models[i]->confThreshold = f < 4.5f ? f : 4.5f;
+            }
         }
         if (!h->cfg.rgbOnly) {
             for (int i = 0; i < h->nmodels; ++i) orc_model_predict_indices(h, h->models[i], h->tick);
@@ -286,6 +391,7 @@ int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int
     }
     predict(h);
     h->tick++;
+    g = h->models[0];
     for (int i = 0; i < h->nmodels; ++i) {
         orc_model* m = h->models[i];
         float T[16];
@@ -295,4 +401,9 @@ int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int
         m->age++;
     }
     return 0;
+}
+
+int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp)
+{
+    return orc_mf_process_frame_ex(h, rgb3, depth, timestamp, 0, 0, 0);
 }

@@ -5,6 +5,7 @@
 #define ORC_PIPELINE_H
 #include "orc.h"
 #include "orc_odom.h"
+#include "orc_mfseg.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -35,6 +36,7 @@ typedef struct orc_model {
     int id; int classID;
     float pose[16], lastPose[16], initialC2Winv[16];
     int isStatic, age;
+    int nonstatic;
     float confThreshold, maxDepth;
     int capacity, count;
     float* surf[2]; int target;           /* ping-pong VBOs (Model.h:285) */
@@ -60,12 +62,21 @@ typedef struct orc_mf {
     int nmodels; orc_model* models[256];
     uint8_t nextID;
     int spawnOffset;
+    /* multi-model state */
+    uint64_t* projKeys; uint8_t* projectedIDs; uint8_t* fullSeg;
+    float* edgeMap; uint8_t* edgeBin; uint8_t* edgeBuf;
+    orc_mfseg_state seg;
+    int lastHasNewLabel;
 } orc_mf;
 
 orc_mf* orc_mf_create(const orc_config* cfg);
 void orc_mf_destroy(orc_mf* h);
 /* rgb: HxWx3 u8, depth: HxW f32 metres.  inPose unused (NULL). */
 void orc_mf_set_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, const uint8_t* mask);
+int orc_mf_process_frame_ex(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp, const uint8_t* mask,
+                            const int32_t* classIDs, int nMasks);
+void orc_mf_global_projection(orc_mf* h);
+void orc_mf_segmentation(orc_mf* h, const uint8_t* mask, const int32_t* classIDs, int nMasks, int allowNew, orc_mfseg_out* out);
 int orc_mf_process_frame(orc_mf* h, const uint8_t* rgb3, const float* depth, int64_t timestamp);
 orc_model* orc_mf_model(orc_mf* h, int i);
 const float* orc_model_surfels(const orc_model* m);     /* == getModelBuffer(): vbos[target] */

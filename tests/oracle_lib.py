@@ -45,7 +45,7 @@ class Model(C.Structure):
     _fields_ = [
         ("id", C.c_int), ("classID", C.c_int),
         ("pose", C.c_float * 16), ("lastPose", C.c_float * 16), ("initialC2Winv", C.c_float * 16),
-        ("isStatic", C.c_int), ("age", C.c_int),
+        ("isStatic", C.c_int), ("age", C.c_int), ("nonstatic", C.c_int),
         ("confThreshold", C.c_float), ("maxDepth", C.c_float),
         ("capacity", C.c_int), ("count", C.c_int),
         ("surf", f32p * 2), ("target", C.c_int), ("allowFillIn", C.c_int),
