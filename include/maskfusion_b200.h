@@ -107,6 +107,10 @@ int mf_download_track_stats(mf_context* ctx, int i, double* A36, double* b6, flo
 int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binary);                           /* MfSegmentation floatEdgeMap / binary edge map */
 
 /* ---- stand-alone kernels exposed for parity tests (device work, host buffers) ---- */
+/* ---- multi-model inputs / outputs ---- */
+int mf_set_frame_classes(mf_context* ctx, const int32_t* class_ids, int n);   /* FrameData::classIDs of the NEXT processFrame call (classIDs[mask value]; entry 0 = background), Core/FrameData.h:40 */
+int mf_download_segmentation(mf_context* ctx, uint8_t* mask, uint8_t* projected_ids);   /* SegmentationResult::fullSegmentation (textureMask) and GlobalProjection::getProjectedModelIDs */
+int mf_model_class_id(mf_context* ctx, int i);                                /* Model::getClassID */
 /* in-stream CUDA-event stage timer (replaces the reference's TICK/TOCK Stopwatch, Core/Utils/Stopwatch.h:46-54) */
 int mf_set_profiling(mf_context* ctx, int on);
 int mf_get_stage_times(mf_context* ctx, char* buf, int bufsize);   /* lines: "name count total_ms" */

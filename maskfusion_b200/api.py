@@ -48,7 +48,7 @@ EXPORTS = [
     "mf_model_fuse", "mf_model_clean", "mf_model_combined_predict", "mf_model_init_from_frame",
     "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
-    "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
+    "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write",
 ]
 
@@ -95,6 +95,9 @@ def load_library():
     L.mf_download_association.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_track_stats.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_edge_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_set_frame_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.mf_download_segmentation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_model_class_id.argtypes = [C.c_void_p, C.c_int]
     L.mf_set_profiling.argtypes = [C.c_void_p, C.c_int]
     L.mf_get_stage_times.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
     L.mf_debug_set_poses.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
@@ -149,6 +152,12 @@ class Model:
         a = np.ascontiguousarray(np.asarray(pose, np.float32).T).ravel()
         b = np.ascontiguousarray(np.asarray(lastPose, np.float32).T).ravel()
         self._ck(self.mf.L.mf_debug_set_poses(self.mf.h, self.i, _p(a), _p(b)))
+
+    def getClassID(self) -> int:
+        return self.mf.L.mf_model_class_id(self.mf.h, self.i)
+
+    def getID(self) -> int:
+        return self.mf.L.mf_model_id(self.mf.h, self.i)
 
     def lastCount(self) -> int:
         return self._ck(self.mf.L.mf_model_surfel_count(self.mf.h, self.i))
@@ -266,8 +275,16 @@ class MaskFusion:
             pass
 
     def processFrame(self, rgb: np.ndarray, depth: np.ndarray, timestamp: int = 0, mask=None, inPose=None,
-                     weightMultiplier: float = 1.0, bootstrap: bool = False):
-        """bool MaskFusion::processFrame(FrameDataPointer, const Eigen::Matrix4f*, float, bool)"""
+                     weightMultiplier: float = 1.0, bootstrap: bool = False, classIDs=None):
+        """bool MaskFusion::processFrame(FrameDataPointer, const Eigen::Matrix4f*, float, bool); mask/classIDs are
+        FrameData::mask / FrameData::classIDs (external instance masks, Core/FrameData.h:36-40)"""
+        if classIDs is not None:
+            c = np.ascontiguousarray(classIDs, np.int32)
+            self._ck(self.L.mf_set_frame_classes(self.h, _p(c), int(c.shape[0])))
+        if mask is not None:
+            if mask.dtype != np.uint8 or mask.shape != (self.H, self.W):
+                raise MFError("mask must be HxW uint8 (CV_8UC1)")
+            mask = np.ascontiguousarray(mask)
         if rgb.dtype != np.uint8 or rgb.shape != (self.H, self.W, 3):
             raise MFError("rgb must be HxWx3 uint8 (CV_8UC3, MaskFusion.cpp:202)")
         if depth.dtype != np.float32 or depth.shape != (self.H, self.W):
@@ -284,6 +301,12 @@ class MaskFusion:
 
     def setFrame(self, rgb, depth, mask=None):
         self._ck(self.L.mf_set_frame(self.h, _p(np.ascontiguousarray(rgb)), _p(np.ascontiguousarray(depth)), _p(mask)))
+
+    def segmentation(self):
+        m = np.zeros((self.H, self.W), np.uint8); p = np.zeros((self.H, self.W), np.uint8)
+        multi = bool(self.cfg.enableMultipleModels)
+        self._ck(self.L.mf_download_segmentation(self.h, _p(m), _p(p) if multi else None))
+        return m, p
 
     def sync(self):
         self._ck(self.L.mf_sync(self.h))

@@ -290,6 +290,24 @@ extern "C" int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binar
     MF_CATCH(-1)
 }
 
+extern "C" int mf_set_frame_classes(mf_context* ctx, const int32_t* class_ids, int n)
+{
+    MF_TRY MF_NEED(ctx)
+    if (n < 0 || n > 256) { g_err = "class id list must have 0..256 entries"; return -3; }
+    ctx->mf->setFrameClasses(class_ids, n);
+    return 0;
+    MF_CATCH(-1)
+}
+extern "C" int mf_download_segmentation(mf_context* ctx, uint8_t* mask, uint8_t* projected_ids)
+{
+    MF_TRY MF_NEED(ctx)
+    MaskFusion* o = ctx->mf;
+    d2h(o, mask, o->mask.p, o->P);
+    if (projected_ids) { if (!o->projectedIDs.p) { g_err = "not a multi-model context"; return -5; } d2h(o, projected_ids, o->projectedIDs.p, o->P); }
+    o->sync(); return 0;
+    MF_CATCH(-1)
+}
+extern "C" int mf_model_class_id(mf_context* ctx, int i) { MF_NEED(ctx) MF_MODEL(ctx, i) return m->classID; }
 extern "C" int mf_set_profiling(mf_context* ctx, int on)
 {
     MF_TRY MF_NEED(ctx)

@@ -149,6 +149,12 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     o->launches += 2;
 }
 
+Model::~Model()
+{
+    if (hCount) cudaFreeHost(hCount);
+    if (hTrackOut) cudaFreeHost(hTrackOut);
+}
+
 unsigned Model::lastCount()
 {
     cudaCheck(cudaMemcpyAsync(hCount, dCount(), sizeof(uint32_t), cudaMemcpyDeviceToHost, owner->stream), "count D2H");
@@ -270,6 +276,16 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     cudaCheck(cudaMallocHost((void**)&hJobs, TRACK_MAX_JOBS * sizeof(TrackJob)), "cudaMallocHost");
     initFlagR.alloc(P); initFlagF.alloc(P);
     scratch.alloc((size_t)P * 4);
+    if (c.enableMultipleModels) {
+        frameMask.alloc(P); frameMask.zero(stream);
+        projKeys.alloc(P); launch_fill_u64(projKeys, KEY_EMPTY, P, stream); projectedIDs.alloc(P); projectedIDs.zero(stream);
+        ccL.alloc(P); ccDense.alloc(P); ccLabA.alloc(P); ccLabB.alloc(P); ccArea.alloc((size_t)P + 1); mapToMask.alloc((size_t)P / 2 + 2); absorbId.alloc((size_t)P / 2 + 2);
+        maskPixels.alloc(256); ccCounter.alloc(1); maskOverlap.alloc(64 * 256);
+        segTmp.alloc(P); ignoreMap.alloc(P); ignoreMap.zero(stream);
+        tblIdToIndex.alloc(256); tblIndexToId.alloc(256); tblIsModel.alloc(256); tblMaskToID.alloc(256); tblIsPerson.alloc(256);
+        cudaCheck(cudaMallocHost((void**)&hSmall, (64 * 256 + 1024) * sizeof(uint32_t)), "cudaMallocHost");
+        memset(maskToID, 0, sizeof maskToID); maskToID[255] = 255;                             // MfSegmentation.cpp:70-71
+    }
     models.emplace_back(new Model(this, nextID++, c.confGlobal, true, c.capacityGlobal));    // MaskFusion.cpp:80-81
     sync();
 }
@@ -279,9 +295,9 @@ MaskFusion::~MaskFusion()
     cudaStreamSynchronize(stream);
     if (g_prof == &prof) g_prof = nullptr;
     for (cudaEvent_t e : prof.events) cudaEventDestroy(e);
-    for (auto& m : models) { if (m->hCount) cudaFreeHost(m->hCount); if (m->hTrackOut) cudaFreeHost(m->hTrackOut); }
     models.clear();
     if (hJobs) cudaFreeHost(hJobs);
+    if (hSmall) cudaFreeHost(hSmall);
     if (ownStream) cudaStreamDestroy(stream);
 }
 
@@ -371,12 +387,150 @@ void MaskFusion::predict()
     for (auto& m : models) m->combinedPredict(cfg.maxDepthProcessed, tick, tick, cfg.timeDelta);   // MaskFusion.cpp:616-628
 }
 
+// GlobalProjection::project (GlobalProjection.cpp:43-107): all models into one depth-tested key image; the key's low word
+// is (model list index << 26 | surfel id), i.e. the reference's draw order.  The ID image stays on the device.
+void MaskFusion::globalProjection()
+{
+    uint8_t idx2id[256]; memset(idx2id, 0, sizeof idx2id);
+    if (models.size() > 63) throw CudaError{"global projection supports up to 63 models"};
+    for (size_t i = 0; i < models.size(); ++i) {
+        Model* m = models[i].get();
+        idx2id[i] = m->id;
+        launch_splat_project_only(m->current(), m->dCount(), toRt(rigidInverse(m->pose)), cam, W, H, cfg.depthCutoff, 12.0f /* :61 */, tick, tick,
+                                  cfg.timeDelta, (uint32_t)i << 26, projKeys, stream);
+        launches += 1;
+    }
+    memcpy(hSmall, idx2id, 256);
+    cudaCheck(cudaMemcpyAsync(tblIndexToId, hSmall, 256, cudaMemcpyHostToDevice, stream), "tbl upload");
+    sync();      // hSmall is reused below
+    launch_proj_resolve(projKeys, P, tblIndexToId, projectedIDs, stream);
+    launches += 1;
+}
+
+// MfSegmentation::performSegmentation (MfSegmentation.cpp:83-538) with the CPU tail on the GPU (mf_seg.cu).
+MaskFusion::SegmentationResult MaskFusion::performSegmentation(bool allowNew)
+{
+    SegmentationResult res;
+    const int nMasks = frameHasMask ? (int)classIDs.size() : 0;
+    const int nModels = (int)models.size();
+    if (nMasks > 256) throw CudaError{"more than 256 mask labels"};
+    if (!frameMapsValid) generateCUDATextures();
+    // edge-ness -> threshold -> close -> invert (MfSegmentation.cpp:149-208)
+    launch_geometric_edges(vmap[0], nmap[0], W, H, cfg.segWeightDistance, cfg.segWeightConvexity, cfg.segThreshold, edgeMap, edgeBinary, stream);
+    launch_morph_close_invert(edgeBinary, edgeBuf, W, H, cfg.segMorphEdgeRadius, cfg.segMorphEdgeIterations, edgeInv, stream);
+    launches += 2 + 2 * cfg.segMorphEdgeIterations;
+    // small tables
+    uint8_t* t = (uint8_t*)hSmall;
+    uint8_t* id2idx = t, *idx2id = t + 256, *isModel = t + 512, *isPerson = t + 768;
+    memset(t, 0, 1024);
+    for (int i = 0; i < nModels; ++i) { id2idx[models[i]->id] = (uint8_t)i; idx2id[i] = models[i]->id; isModel[models[i]->id] = 1; }
+    bool anyPerson = false;
+    for (int m = 0; m < nMasks; ++m) if (classIDs[m] == personClassID) { isPerson[m] = 1; anyPerson = true; }
+    cudaCheck(cudaMemcpyAsync(tblIdToIndex, id2idx, 256, cudaMemcpyHostToDevice, stream), "tbl");
+    cudaCheck(cudaMemcpyAsync(tblIndexToId, idx2id, 256, cudaMemcpyHostToDevice, stream), "tbl");
+    cudaCheck(cudaMemcpyAsync(tblIsModel, isModel, 256, cudaMemcpyHostToDevice, stream), "tbl");
+    cudaCheck(cudaMemcpyAsync(tblIsPerson, isPerson, 256, cudaMemcpyHostToDevice, stream), "tbl");
+    // ignore map (:221-235)
+    launch_apply_ignore(frameMask, tblIsPerson, nMasks, P, ignoreMap, edgeInv, stream);
+    (void)anyPerson;
+    // connected components + 5 edge-removal sweeps (:238-291)
+    launch_cc(edgeInv, W, H, ccL, ccDense, ccLabA, ccArea, ccCounter, stream);
+    launch_remove_edges(ccLabA, ccLabB, depthRaw, ccArea, W, H, 5, stream);
+    int* lab = ccLabB;                                     // odd number of sweeps ends in B
+    launches += 10;
+    cudaCheck(cudaMemcpyAsync(hSmall + 512, ccCounter, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "ncomp D2H");
+    sync();
+    const int nComponents = (int)hSmall[512] + 1;
+    // overlap histograms (:303-346)
+    if (compModel.n < (size_t)nComponents * nModels) compModel.alloc((size_t)nComponents * nModels * 2);
+    if (nMasks && compMask.n < (size_t)nComponents * nMasks) compMask.alloc((size_t)nComponents * nMasks * 2);
+    cudaCheck(cudaMemsetAsync(compModel, 0, (size_t)nComponents * nModels * sizeof(int), stream), "memset");
+    if (nMasks) cudaCheck(cudaMemsetAsync(compMask, 0, (size_t)nComponents * nMasks * sizeof(int), stream), "memset");
+    maskPixels.zero(stream);
+    launch_seg_hist(lab, projectedIDs, frameMask, P, tblIdToIndex, nModels, nMasks, compModel, compMask, stream);
+    launch_component_map(nComponents, ccArea, compModel, compMask, nModels, nMasks, tblIndexToId, minMappedComponentSize, mapToMask, absorbId, maskPixels, stream);
+    launch_seg_assign(lab, mapToMask, ignoreMap, P, segTmp, stream);
+    launches += 3;
+    if (nMasks) {
+        if (cfg.segMorphMaskIterations > 0) throw CudaError{"morphological closing of the mask image (morphMaskIterations > 0) is not built yet (GUI default 0)"};
+        // mask -> model vote (:433-492): two small tables to the host
+        if ((size_t)nModels * 256 > maskOverlap.n) maskOverlap.alloc((size_t)nModels * 256);
+        maskOverlap.zero(stream);
+        launch_mask_overlap(segTmp, projectedIDs, tblIdToIndex, tblIsModel, P, maskOverlap, stream);
+        launches += 1;
+        cudaCheck(cudaMemcpyAsync(hSmall, maskPixels, 256 * sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H");
+        cudaCheck(cudaMemcpyAsync(hSmall + 256, maskOverlap, (size_t)nModels * 256 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H");
+        sync();
+        const int* maskComponentPixels = (const int*)hSmall;
+        const unsigned* ov = (const unsigned*)(hSmall + 256);
+        const size_t total = (size_t)P;
+        const size_t minNew = (size_t)(cfg.minRelSizeNew * total), maxNew = (size_t)(cfg.maxRelSizeNew * total);
+        const unsigned char nextModelID = getNextModelID(false);
+        for (int midx = 1; midx < nMasks; ++midx) { maskToID[midx] = 0; if (classIDs[midx] == personClassID) maskToID[midx] = 255; }
+        for (int midx = 1; midx < nMasks; ++midx) {
+            if (maskToID[midx] == 255) continue;
+            int bestModelIndex = 0; unsigned bestOverlap = 0;
+            const int maskClassID = classIDs[midx];
+            for (int j = 1; j < nModels; ++j) { unsigned o = ov[(size_t)j * 256 + midx]; if (o > bestOverlap) { bestOverlap = o; bestModelIndex = j; } }
+            const bool matches = models[bestModelIndex]->classID == maskClassID;
+            if (bestOverlap < minMaskModelOverlap * maskComponentPixels[midx]) bestModelIndex = 0;
+            if (bestModelIndex != 0 && matches) maskToID[midx] = models[bestModelIndex]->id;
+            else if (!res.hasNewLabel && allowNew && (size_t)maskComponentPixels[midx] > minNew && (size_t)maskComponentPixels[midx] < maxNew && bestModelIndex == 0) {
+                maskToID[midx] = nextModelID; res.hasNewLabel = true; res.newClassID = maskClassID;
+            } else maskToID[midx] = 255;
+        }
+    }
+    memcpy(hSmall, maskToID, 256);
+    cudaCheck(cudaMemcpyAsync(tblMaskToID, hSmall, 256, cudaMemcpyHostToDevice, stream), "tbl");
+    launch_seg_final(segTmp, lab, mapToMask, absorbId, tblMaskToID, P, mask, stream);      // writes textureMask directly (:297)
+    launches += 1;
+    sync();                                                                                  // hSmall reused by the next stage
+    return res;
+}
+
+// MaskFusion::getNextModelID (MaskFusion.cpp:712-730)
+unsigned char MaskFusion::getNextModelID(bool assign)
+{
+    unsigned char next = nextID;
+    if (assign) {
+        if (models.size() == 256) throw CudaError{"getNextModelID(): maximum amount of models is already in use (256)"};
+        while (true) {
+            nextID++;
+            bool occupied = false;
+            for (auto& m : models) if (nextID == m->id) occupied = true;
+            if (!occupied) break;
+        }
+    }
+    return next;
+}
+
+// MaskFusion::spawnObjectModel + moveNewModelToList (MaskFusion.cpp:671-690)
+Model* MaskFusion::spawnObjectModel()
+{
+    Model* g = models[0].get();
+    models.emplace_back(new Model(this, getNextModelID(true), cfg.confObject, false, cfg.capacityObject));
+    Model* nm = models.back().get();
+    // newModel->getFrameOdometry().initFirstRGB(textureRGB)
+    if (!intensityValid) {
+        launch_intensity(rgb, P, nextImage[0], stream);
+        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
+        launches += 3; intensityValid = true;
+    }
+    cudaCheck(cudaMemcpyAsync(nm->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
+    nm->makeStatic(g->pose);
+    return nm;
+}
+
 bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_t timestamp, const uint8_t* maskIn, const Mat4* inPose,
                               float weightMultiplier, bool bootstrap, bool onDevice)
 {
-    if (cfg.enableMultipleModels) throw CudaError{"multi-model schedule not built in this round (DESIGN.md, section 'next')"};
-    setFrame(rgbIn, depthIn, nullptr, onDevice);                     // -static: mask stays all zero (MaskFusion.cpp:223-230)
-    (void)maskIn;
+    const bool multi = cfg.enableMultipleModels != 0;
+    setFrame(rgbIn, depthIn, nullptr, onDevice);        // -static: textureMask stays all zero (MaskFusion.cpp:223-230); multi: keeps the last segmentation
+    frameHasMask = false;
+    if (multi && maskIn) {
+        cudaCheck(cudaMemcpyAsync(frameMask, maskIn, (size_t)P, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream), "mask upload");
+        frameHasMask = !classIDs.empty();
+    }
     Model* g = models[0].get();
     if (tick == 1) {
         g->initialise(tick);
@@ -388,10 +542,41 @@ bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_
     } else {
         if (bootstrap || !inPose) {
             generateCUDATextures();
+            // MaskFusion.cpp:247-276: the global model and every tracked object share one batched launch sequence
             std::vector<Model*> tracked{g};
+            for (size_t i = 1; i < models.size(); ++i)
+                if (models[i]->nonstatic || cfg.trackAllModels) tracked.push_back(models[i].get());
             trackModels(tracked);
-            for (size_t i = 1; i < models.size(); ++i) models[i]->updateStaticPose(g->pose);
+            for (size_t i = 1; i < models.size(); ++i) {
+                Model* m = models[i].get();
+                if (m->nonstatic || cfg.trackAllModels) {
+                    const float* T = m->lastTransform.m;
+                    float d = sqrtf((T[3] * T[3] + T[7] * T[7]) + T[11] * T[11]);
+                    if (d > 0.2f) { models.erase(models.begin() + i); --i; }          // inactivateModel (:268-272)
+                } else m->updateStaticPose(g->pose);
+            }
             if (bootstrap && inPose) g->overridePose(mul(g->pose, *inPose));
+            if (multi) {
+                globalProjection();                                                    // :289-290
+                if (spawnOffset < cfg.modelSpawnOffset) spawnOffset++;
+                SegmentationResult seg = performSegmentation(spawnOffset >= cfg.modelSpawnOffset);
+                Model* nm = nullptr;
+                if (seg.hasNewLabel) {                                                 // :313-334
+                    nm = spawnObjectModel();
+                    spawnOffset = 0;
+                    nm->classID = seg.newClassID;
+                }
+                for (size_t i = 1; i < models.size(); ++i) models[i]->maxDepth = 30.0f + 30.0f * 1.2f;   // getMaxDepth(30, 30), :292,337-341
+                if (nm) {                                                              // :344-353
+                    nm->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
+                    nm->fuse(tick, cfg.maxDepthProcessed, 100.0f);
+                    nm->clean(tick, cfg.timeDelta, cfg.maxDepthProcessed);
+                }
+                for (size_t i = 1; i < models.size(); ++i) {                           // :369-374
+                    float f = (float)models[i]->age / 25.0f;
+                    models[i]->confidenceThreshold = f < 4.5f ? f : 4.5f;
+                }
+            }
         } else {
             g->overridePose(*inPose);
         }
@@ -404,6 +589,7 @@ bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_
     }
     predict();          // MaskFusion.cpp:569 (the call at :423 is dead in open-loop mode: its outputs are overwritten here)
     tick++;
+    g = models[0].get();
     for (size_t i = 0; i < models.size(); ++i) {
         Model* m = models[i].get();
         Mat4 T = (i == 0) ? g->pose : mul(g->pose, rigidInverse(m->pose));     // MaskFusion.cpp:581-583

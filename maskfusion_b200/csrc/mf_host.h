@@ -52,6 +52,8 @@ class MaskFusion;
 class Model {
 public:
     Model(MaskFusion* owner, unsigned char id, float confidenceThresh, bool enableFillIn, int capacity);
+    ~Model();
+    Model(const Model&) = delete;
 
     // ---- reference API (Core/Model/Model.h:128-164) ----
     void initialise(int time);                                        // Model::initialise (+ computeFeedbackBuffers)
@@ -113,6 +115,13 @@ public:
     void trackModels(const std::vector<Model*>& ms);                                              // performTracking for a batch
     void predict();                                                                               // MaskFusion::predict
     void sync();
+    // ---- multi-model path (MaskFusion.cpp:287-375) ----
+    struct SegmentationResult { bool hasNewLabel = false; int newClassID = -1; };                 // SegmentationResult.h:32-73 (fields the schedule reads)
+    void globalProjection();                                                                      // GlobalProjection::project + downloadDirect (stays on the device)
+    SegmentationResult performSegmentation(bool allowNew);                                        // MfSegmentation::performSegmentation
+    unsigned char getNextModelID(bool assign);                                                    // MaskFusion::getNextModelID
+    Model* spawnObjectModel();                                                                    // MaskFusion::spawnObjectModel + moveNewModelToList
+    void setFrameClasses(const int32_t* ids, int n) { classIDs.assign(ids, ids + n); }            // FrameData::classIDs
 
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;
@@ -130,6 +139,18 @@ public:
     DevBuf<float> scratch;                  // read-back staging
     bool frameMapsValid = false, intensityValid = false;
     Profiler prof;
+    // multi-model state
+    std::vector<int32_t> classIDs;          // of the frame being processed
+    bool frameHasMask = false;
+    int spawnOffset = 0;
+    DevBuf<uint8_t> frameMask;              // FrameData::mask (external instance masks)
+    DevBuf<uint64_t> projKeys; DevBuf<uint8_t> projectedIDs;
+    DevBuf<int> ccL, ccDense, ccLabA, ccLabB, ccArea, mapToMask, absorbId, maskPixels, compModel, compMask;
+    DevBuf<uint32_t> ccCounter; DevBuf<unsigned> maskOverlap;
+    DevBuf<uint8_t> segTmp, ignoreMap, tblIdToIndex, tblIndexToId, tblIsModel, tblMaskToID, tblIsPerson;
+    uint8_t maskToID[256];
+    uint32_t* hSmall = nullptr;             // pinned scratch for the small tables
+    float minMaskModelOverlap = 0.05f; int minMappedComponentSize = 160; int personClassID = 255;   // MfSegmentation.cpp:43, MfSegmentation.h:58
 };
 
 }  // namespace mfb

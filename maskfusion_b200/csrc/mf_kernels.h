@@ -99,3 +99,20 @@ void launch_geometric_edges(const float4* vmap, const float4* nmap, int W, int H
 void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, uint8_t* inverted, cudaStream_t s);
 
 }  // namespace mfb
+
+namespace mfb {
+// ---- mf_seg.cu: GPU segmentation tail + global projection resolve ----
+void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, uint32_t* counter, cudaStream_t s);
+void launch_remove_edges(int* labA, int* labB, const float* depth, const int* area, int W, int H, int iterations, cudaStream_t s);
+void launch_seg_hist(const int* lab, const uint8_t* projID, const uint8_t* mask, int P, const uint8_t* idToIndex, int nModels, int nMasks,
+                     int* compModel, int* compMask, cudaStream_t s);
+void launch_component_map(int nComponents, const int* area, const int* compModel, const int* compMask, int nModels, int nMasks,
+                          const uint8_t* indexToId, int minMapped, int* mapToMask, int* absorb, int* maskPixels, cudaStream_t s);
+void launch_seg_assign(const int* lab, const int* mapToMask, const uint8_t* ignore, int P, uint8_t* seg, cudaStream_t s);
+void launch_mask_overlap(const uint8_t* seg, const uint8_t* projID, const uint8_t* idToIndex, const uint8_t* isModelId, int P, unsigned* maskOverlap, cudaStream_t s);
+void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, int P, uint8_t* out, cudaStream_t s);
+void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, int nMasks, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s);
+void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s);
+void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, float confThreshold,
+                               int time, int maxTime, int timeDelta, uint32_t drawBase, uint64_t* key, cudaStream_t s);
+}  // namespace mfb

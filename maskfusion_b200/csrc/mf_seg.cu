@@ -76,3 +76,205 @@ void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int ra
 }
 
 }  // namespace mfb
+
+// =======================================================================================
+// GPU replacement of the CPU tail of MfSegmentation::performSegmentation
+// (Core/Segmentation/MfSegmentation.cpp:208-538).  The reference downloads the
+// edge mask and runs ~15 single-threaded full-image sweeps + OpenCV connected components; here
+// the sweeps are kernels and only two tiny tables (per-mask pixel counts, mask x model overlaps)
+// visit the host for the mask->model vote.
+// Component numbering is arbitrary (atomic counter): the reference's results do not depend on it.
+// =======================================================================================
+namespace mfb {
+
+// ---- 4-connected components: union-find with atomicMin (root = smallest pixel index) ----
+MF_D int ccFind(const int* __restrict__ L, int x)
+{
+    int p = L[x];
+    while (p != x) { x = p; p = L[x]; }
+    return x;
+}
+MF_D void ccUnion(int* L, int a, int b)
+{
+    while (true) {
+        a = ccFind(L, a); b = ccFind(L, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }        // a > b: hook the larger root under the smaller
+        int old = atomicMin(&L[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+__global__ void k_cc_init(const uint8_t* __restrict__ img, int P, int* __restrict__ L, int* __restrict__ area, uint32_t* counter)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *counter = 0;
+    if (i >= P) return;
+    L[i] = img[i] ? i : -1;
+    area[i] = 0;
+}
+__global__ void k_cc_merge(const uint8_t* __restrict__ img, int W, int H, int* L)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    int i = y * W + x;
+    if (!img[i]) return;
+    if (x > 0 && img[i - 1]) ccUnion(L, i, i - 1);
+    if (y > 0 && img[i - W]) ccUnion(L, i, i - W);
+}
+// roots get a dense id 1..n-1 (0 = background/edge); area is accumulated per dense id
+__global__ void k_cc_number(int* __restrict__ L, int P, int* __restrict__ dense, uint32_t* counter)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (L[i] == i) dense[i] = (int)atomicAdd(counter, 1u) + 1;
+}
+__global__ void k_cc_relabel(const int* __restrict__ L, const int* __restrict__ dense, int P, int* __restrict__ lab, int* __restrict__ area)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int l = 0;
+    if (L[i] >= 0) { l = dense[ccFind(L, i)]; atomicAdd(&area[l], 1); }
+    lab[i] = l;
+}
+// one Jacobi sweep of the edge-removal loop (MfSegmentation.cpp:243-291): reads the previous labels only
+__global__ void k_remove_edges(const int* __restrict__ labIn, int* __restrict__ labOut, const float* __restrict__ depth,
+                               const int* __restrict__ area, int W, int H)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    int i = y * W + x;
+    int c = labIn[i];
+    if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1 && (c == 0 || area[c] < 50)) {
+        float d = depth[i];
+        const int oy[8] = {-1, -1, -1, 0, 0, 1, 1, 1}, ox[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int j = (y + oy[k]) * W + x + ox[k];
+            int n = labIn[j];
+            if (n != 0 && fabsf(depth[j] - d) < 0.008 && area[n] > 50) { c = n; break; }
+        }
+    }
+    labOut[i] = c;
+}
+__global__ void k_seg_hist(const int* __restrict__ lab, const uint8_t* __restrict__ projID, const uint8_t* __restrict__ mask, int P,
+                           const uint8_t* __restrict__ idToIndex, int nModels, int nMasks, int* __restrict__ compModel, int* __restrict__ compMask)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    int c = lab[i];
+    atomicAdd(&compModel[(size_t)c * nModels + idToIndex[projID[i]]], 1);
+    if (nMasks) atomicAdd(&compMask[(size_t)c * nMasks + mask[i]], 1);
+}
+__global__ void k_component_map(int nComponents, const int* __restrict__ area, const int* __restrict__ compModel, const int* __restrict__ compMask,
+                                int nModels, int nMasks, const uint8_t* __restrict__ indexToId, int minMappedComponentSize,
+                                int* __restrict__ mapToMask, int* __restrict__ absorb, int* __restrict__ maskPixels)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nComponents) return;
+    int m2m = 0, ab = 0;
+    if (c >= 1) {
+        int csize = area[c];
+        if (nMasks && csize > minMappedComponentSize) {
+            int t = (int)(0.65f * csize);
+            for (int m = 1; m < nMasks; ++m)
+                if (compMask[(size_t)c * nMasks + m] > t) { m2m = m; atomicAdd(&maskPixels[m], csize); }
+        }
+        int best = compModel[(size_t)c * nModels], bi = 0;
+        for (int m = 1; m < nModels; ++m) { int v = compModel[(size_t)c * nModels + m]; if (v > best) { best = v; bi = m; } }
+        int id = indexToId[bi];
+        if (id > 0 && best > 0.6f * csize) ab = id;
+    }
+    mapToMask[c] = m2m; absorb[c] = ab;
+}
+__global__ void k_seg_assign(const int* __restrict__ lab, const int* __restrict__ mapToMask, const uint8_t* __restrict__ ignore, int P,
+                             uint8_t* __restrict__ seg)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    seg[i] = ignore[i] ? 255 : (uint8_t)mapToMask[lab[i]];
+}
+__global__ void k_mask_overlap(const uint8_t* __restrict__ seg, const uint8_t* __restrict__ projID, const uint8_t* __restrict__ idToIndex,
+                               const uint8_t* __restrict__ isModelId, int P, unsigned* __restrict__ maskOverlap)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint8_t id = projID[i];
+    if (isModelId[id]) atomicAdd(&maskOverlap[(int)idToIndex[id] * 256 + seg[i]], 1u);
+}
+__global__ void k_seg_final(const uint8_t* __restrict__ seg, const int* __restrict__ lab, const int* __restrict__ mapToMask,
+                            const int* __restrict__ absorb, const uint8_t* __restrict__ maskToID, int P, uint8_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint8_t s = maskToID[seg[i]];
+    int c = lab[i];
+    if (c > 0 && mapToMask[c] == 0 && absorb[c] > 0) s = (uint8_t)absorb[c];
+    out[i] = s;
+}
+__global__ void k_apply_ignore(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ isPerson, int nMasks, int P,
+                               uint8_t* __restrict__ ignore, uint8_t* __restrict__ edges)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    if (nMasks) ignore[i] = isPerson[mask[i]] ? 255 : 0;
+    if (ignore[i]) edges[i] = 0;
+}
+// model-ID image from the global-projection keys (GlobalProjection.cpp:43-111): low word = modelIndex << 26 | surfel id
+__global__ void k_proj_resolve(unsigned long long* __restrict__ key, int P, const uint8_t* __restrict__ indexToId, uint8_t* __restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    unsigned long long k = key[i];
+    uint8_t id = 0;
+    if (k != KEY_EMPTY) { key[i] = KEY_EMPTY; id = indexToId[(uint32_t)(k & 0xffffffffull) >> 26]; }
+    out[i] = id;
+}
+
+void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, uint32_t* counter, cudaStream_t s)
+{
+    int P = W * H; dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    prof_mark(s, "k_cc_init"); k_cc_init<<<(P + 255) / 256, 256, 0, s>>>(img, P, L, area, counter);
+    prof_mark(s, "k_cc_merge"); k_cc_merge<<<g, b, 0, s>>>(img, W, H, L);
+    prof_mark(s, "k_cc_number"); k_cc_number<<<(P + 255) / 256, 256, 0, s>>>(L, P, dense, counter);
+    prof_mark(s, "k_cc_relabel"); k_cc_relabel<<<(P + 255) / 256, 256, 0, s>>>(L, dense, P, lab, area);
+}
+void launch_remove_edges(int* labA, int* labB, const float* depth, const int* area, int W, int H, int iterations, cudaStream_t s)
+{
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    for (int i = 0; i < iterations; ++i) {          // caller guarantees an even ping-pong ends in labA when iterations is odd -> see host
+        prof_mark(s, "k_remove_edges"); k_remove_edges<<<g, b, 0, s>>>(i % 2 == 0 ? labA : labB, i % 2 == 0 ? labB : labA, depth, area, W, H);
+    }
+}
+void launch_seg_hist(const int* lab, const uint8_t* projID, const uint8_t* mask, int P, const uint8_t* idToIndex, int nModels, int nMasks,
+                     int* compModel, int* compMask, cudaStream_t s)
+{
+    prof_mark(s, "k_seg_hist"); k_seg_hist<<<(P + 255) / 256, 256, 0, s>>>(lab, projID, mask, P, idToIndex, nModels, nMasks, compModel, compMask);
+}
+void launch_component_map(int nComponents, const int* area, const int* compModel, const int* compMask, int nModels, int nMasks,
+                          const uint8_t* indexToId, int minMapped, int* mapToMask, int* absorb, int* maskPixels, cudaStream_t s)
+{
+    prof_mark(s, "k_component_map"); k_component_map<<<(nComponents + 127) / 128, 128, 0, s>>>(nComponents, area, compModel, compMask, nModels, nMasks, indexToId, minMapped, mapToMask, absorb, maskPixels);
+}
+void launch_seg_assign(const int* lab, const int* mapToMask, const uint8_t* ignore, int P, uint8_t* seg, cudaStream_t s)
+{
+    prof_mark(s, "k_seg_assign"); k_seg_assign<<<(P + 255) / 256, 256, 0, s>>>(lab, mapToMask, ignore, P, seg);
+}
+void launch_mask_overlap(const uint8_t* seg, const uint8_t* projID, const uint8_t* idToIndex, const uint8_t* isModelId, int P, unsigned* maskOverlap, cudaStream_t s)
+{
+    prof_mark(s, "k_mask_overlap"); k_mask_overlap<<<(P + 255) / 256, 256, 0, s>>>(seg, projID, idToIndex, isModelId, P, maskOverlap);
+}
+void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, int P, uint8_t* out, cudaStream_t s)
+{
+    prof_mark(s, "k_seg_final"); k_seg_final<<<(P + 255) / 256, 256, 0, s>>>(seg, lab, mapToMask, absorb, maskToID, P, out);
+}
+void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, int nMasks, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s)
+{
+    prof_mark(s, "k_apply_ignore"); k_apply_ignore<<<(P + 255) / 256, 256, 0, s>>>(mask, isPerson, nMasks, P, ignore, edges);
+}
+void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s)
+{
+    prof_mark(s, "k_proj_resolve"); k_proj_resolve<<<(P + 255) / 256, 256, 0, s>>>((unsigned long long*)key, P, indexToId, out);
+}
+
+}  // namespace mfb

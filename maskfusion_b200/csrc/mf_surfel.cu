@@ -840,3 +840,14 @@ void launch_planes_to_aos(const SurfelPlanes& sp, uint32_t n, float4* out, cudaS
 void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, cudaStream_t s) { if (n) k_aos_to_planes<<<(n + 255) / 256, 256, 0, s>>>(in, n, sp.pos, sp.col, sp.nrm); }
 
 }  // namespace mfb
+
+namespace mfb {
+// splat projection into a caller-owned key image (GlobalProjection: all models share one key image)
+void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, float confThreshold,
+                               int time, int maxTime, int timeDelta, uint32_t drawBase, uint64_t* key, cudaStream_t s)
+{
+    prof_mark(s, "k_splat_project_ids");
+    k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
+                                                        (float)maxTime, (float)timeDelta, drawBase, (unsigned long long*)key);
+}
+}  // namespace mfb

@@ -189,6 +189,33 @@ MF_D void blockReduceStore(float* acc, float* partialOut)
     }
 }
 
+// Sum the per-block partials (rows of 64 floats, N used) with the WHOLE last block: warp w takes blocks
+// w, w+8, ...; lanes take columns lane and lane+32 (coalesced 128-byte rows, independent loads), doubles
+// throughout; the 8 warp sums are combined in fixed order.  Deterministic for a fixed launch shape.
+// (A single thread per column walking all partials serially cost ~10 us of exposed L2 latency per step.)
+template <int N>
+MF_D void sumPartials(const float* __restrict__ partial, unsigned nblocks, double* tot /* shared, >= N */)
+{
+    __shared__ double ws[TRK_THREADS / 32][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double a0 = 0, a1 = 0;
+#pragma unroll 4
+    for (unsigned b = warp; b < nblocks; b += TRK_THREADS / 32) {
+        const float* row = partial + (size_t)b * 64;
+        a0 += (double)row[lane];
+        if (N > 32) a1 += (double)row[32 + lane];
+    }
+    ws[warp][lane] = a0; ws[warp][32 + lane] = a1;
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < TRK_THREADS / 32; ++w) s += ws[w][threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
 // returns true in ALL threads of the last block to arrive
 MF_D bool lastBlock(unsigned* ticket)
 {
@@ -326,12 +353,7 @@ __global__ void __launch_bounds__(TRK_THREADS) k_so3_step(TrackJob* jobs, int W,
     blockReduceStore<11>(acc, partial);
     if (!lastBlock(&st->ticket[0])) return;
     __shared__ double tot[11];
-    if (threadIdx.x < 11) {
-        double s = 0;
-        for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += (double)J.partial[(size_t)b2 * 64 + threadIdx.x];
-        tot[threadIdx.x] = s;
-    }
-    __syncthreads();
+    sumPartials<11>(J.partial, gridDim.x, tot);
     if (threadIdx.x != 0) return;
     // host logic of RGBDOdometry.cpp:301-324
     float res0 = (float)tot[9], res1 = (float)tot[10];
@@ -422,9 +444,16 @@ __global__ void __launch_bounds__(TRK_THREADS) k_rgb_residual(TrackJob* jobs, in
         J.partialI[blockIdx.x * 2] = a; J.partialI[blockIdx.x * 2 + 1] = b;
     }
     if (!lastBlock(&st->ticket[1])) return;
+    // integer partials: exact, summed by the whole block
+    int ps = 0, pc = 0;
+    for (unsigned b2 = threadIdx.x; b2 < gridDim.x; b2 += TRK_THREADS) { pc += J.partialI[b2 * 2]; ps += J.partialI[b2 * 2 + 1]; }
+    for (int off = 16; off > 0; off >>= 1) { pc += __shfl_down_sync(0xffffffffu, pc, off); ps += __shfl_down_sync(0xffffffffu, ps, off); }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { shc[threadIdx.x >> 5] = pc; shs[threadIdx.x >> 5] = ps; }
+    __syncthreads();
     if (threadIdx.x != 0) return;
     int rgbSize = 0, sigma = 0;
-    for (unsigned b2 = 0; b2 < gridDim.x; ++b2) { rgbSize += J.partialI[b2 * 2]; sigma += J.partialI[b2 * 2 + 1]; }
+    for (int w = 0; w < TRK_THREADS / 32; ++w) { rgbSize += shc[w]; sigma += shs[w]; }
     // RGBDOdometry.cpp:388-401
     float tmpError = (float)(sqrt((double)sigma) / (double)rgbSize);
     float sigmaVal = (tmpError == 0) ? 1 : (float)rgbSize;
@@ -532,12 +561,7 @@ __global__ void __launch_bounds__(TRK_THREADS) k_gn_step(TrackJob* jobs, int lev
     blockReduceStore<NACC>(acc, J.partial + (size_t)blockIdx.x * 64);
     if (!lastBlock(&st->ticket[2])) return;
     __shared__ double tot[NACC];
-    if (threadIdx.x < NACC) {
-        double s = 0;
-        for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += (double)J.partial[(size_t)b2 * 64 + threadIdx.x];
-        tot[threadIdx.x] = s;
-    }
-    __syncthreads();
+    sumPartials<NACC>(J.partial, gridDim.x, tot);
     if (threadIdx.x != 0) return;
 
     // ---- host part of RGBDOdometry.cpp:403-474, on the device ----
@@ -640,11 +664,9 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restri
     }
     blockReduceStore<NACC_ICP>(acc, partial + (size_t)blockIdx.x * 64);
     if (!lastBlock(ticket)) return;
-    if (threadIdx.x < NACC_ICP) {
-        double s = 0;
-        for (unsigned b2 = 0; b2 < gridDim.x; ++b2) s += (double)partial[(size_t)b2 * 64 + threadIdx.x];
-        out29[threadIdx.x] = (float)s;
-    }
+    __shared__ double tot[NACC_ICP];
+    sumPartials<NACC_ICP>(partial, gridDim.x, tot);
+    if (threadIdx.x < NACC_ICP) out29[threadIdx.x] = (float)tot[threadIdx.x];
 }
 
 // ------------------------------ host launchers ----------------------------------------
