@@ -117,6 +117,25 @@ int mf_get_stage_times(mf_context* ctx, char* buf, int bufsize);   /* lines: "na
 int mf_debug_set_poses(mf_context* ctx, int i, const float pose16[16], const float last_pose16[16]);   /* sets Model::pose and Model::lastPose verbatim */
 int mf_icp_step(mf_context* ctx, int i, int level, const float Rcurr9[9], const float tcurr3[3], float out29[29]);  /* icpStep, reduce.cu:446-525 */
 
+/* ---- Mask R-CNN backbone: ResNet-101 + FPN as tcgen05/TMEM GEMMs (replaces the dense part of the Keras/TF sidecar,
+ *      Core/Segmentation/MaskRCNN/MaskRCNN.py.in:55-58,101-111; weights are synthetic/seeded: no COCO weights offline) ---- */
+typedef struct mf_backbone mf_backbone;
+const char* mf_cnn_last_error(void);
+/* out[MxN] = relu?(A[MxK] * B[NxK]^T + bias[N] + residual[MxN]); bf16 device pointers, K % 64 == 0, N % 64 == 0 */
+int mf_gemm_bf16(const void* dA, const void* dB, const float* dBias, const void* dResidual, void* dOut, int M, int N, int K, int relu, void* stream);
+mf_backbone* mf_backbone_create(int input_size, unsigned seed, void* stream);
+void mf_backbone_destroy(mf_backbone* h);
+int mf_backbone_num_layers(mf_backbone* h);
+int mf_backbone_layer(mf_backbone* h, int i, int* cin_cout_k_stride_pad_kpad);
+int mf_backbone_get_weights(mf_backbone* h, int i, float* w_cout_kpad, float* bias);
+int mf_backbone_mold(mf_backbone* h, const void* d_rgba, int W, int H);            /* letter-box + mean subtraction -> network input */
+void* mf_backbone_input_buffer(mf_backbone* h);
+int mf_backbone_forward(mf_backbone* h, const void* d_input_nhwc_bf16);
+void* mf_backbone_output(mf_backbone* h, int level, int* dims_hwc);               /* 0..3 = C2..C5, 4..8 = P2..P6 (device, NHWC bf16) */
+int mf_backbone_download(mf_backbone* h, int level, void* host_bf16);
+double mf_backbone_flops(mf_backbone* h);
+int mf_backbone_num_gemms(mf_backbone* h);
+
 /* ---- .klg log reader / writer (GUI/Tools/KlgLogReader.cpp:29-113) ---- */
 typedef struct mf_klg mf_klg;
 mf_klg* mf_klg_open(const char* path, int width, int height, int flip_colors);

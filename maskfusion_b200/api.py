@@ -49,7 +49,9 @@ EXPORTS = [
     "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
     "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
-    "mf_klg_close", "mf_klg_write",
+    "mf_klg_close", "mf_klg_write", "mf_cnn_last_error", "mf_gemm_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
+    "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
+    "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
 ]
 
 
@@ -109,6 +111,21 @@ def load_library():
     L.mf_klg_close.restype = None
     L.mf_klg_get_next.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mf_klg_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_cnn_last_error.restype = C.c_char_p
+    L.mf_gemm_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]
+    L.mf_backbone_create.restype = C.c_void_p
+    L.mf_backbone_create.argtypes = [C.c_int, C.c_uint, C.c_void_p]
+    L.mf_backbone_destroy.argtypes = [C.c_void_p]; L.mf_backbone_destroy.restype = None
+    L.mf_backbone_num_layers.argtypes = [C.c_void_p]
+    L.mf_backbone_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mf_backbone_get_weights.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.mf_backbone_mold.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.mf_backbone_input_buffer.restype = C.c_void_p; L.mf_backbone_input_buffer.argtypes = [C.c_void_p]
+    L.mf_backbone_forward.argtypes = [C.c_void_p, C.c_void_p]
+    L.mf_backbone_output.restype = C.c_void_p; L.mf_backbone_output.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mf_backbone_flops.restype = C.c_double; L.mf_backbone_flops.argtypes = [C.c_void_p]
+    L.mf_backbone_num_gemms.argtypes = [C.c_void_p]
+    L.mf_backbone_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     _LIB = L
     return L
 
@@ -390,3 +407,55 @@ def write_klg(path: str, timestamps, depth_mm: np.ndarray, rgb: np.ndarray):
     d = np.ascontiguousarray(depth_mm, np.uint16); c = np.ascontiguousarray(rgb, np.uint8)
     if L.mf_klg_write(path.encode(), W, H, n, _p(ts), _p(d), _p(c)) != 0:
         raise MFError(L.mf_last_error().decode())
+
+
+class Backbone:
+    """Mask R-CNN ResNet-101-FPN backbone on tcgen05 GEMMs (csrc/mf_cnn.cu).  Weights are synthetic (seeded)."""
+
+    def __init__(self, input_size=1024, seed=1, stream: int | None = None):
+        self.L = load_library()
+        self.S = input_size
+        self.h = self.L.mf_backbone_create(input_size, seed, C.c_void_p(stream) if stream else None)
+        if not self.h:
+            raise MFError(self.L.mf_cnn_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mf_backbone_destroy(self.h); self.h = None
+
+    def layers(self):
+        out = []
+        for i in range(self.L.mf_backbone_num_layers(self.h)):
+            d = np.zeros(6, np.int32)
+            self.L.mf_backbone_layer(self.h, i, _p(d))
+            out.append(tuple(int(v) for v in d))
+        return out
+
+    def weights(self, i):
+        cin, cout, k, stride, pad, kpad = self.layers()[i]
+        w = np.zeros((cout, kpad), np.float32); b = np.zeros(cout, np.float32)
+        self.L.mf_backbone_get_weights(self.h, i, _p(w), _p(b))
+        return w[:, :k * k * cin].reshape(cout, k, k, cin), b
+
+    def forward(self, input_ptr: int):
+        if self.L.mf_backbone_forward(self.h, C.c_void_p(input_ptr)) != 0:
+            raise MFError(self.L.mf_cnn_last_error().decode())
+
+    def output(self, level):
+        d = np.zeros(3, np.int32)
+        ptr = self.L.mf_backbone_output(self.h, level, _p(d))
+        return ptr, tuple(int(v) for v in d)
+
+    def download(self, level) -> np.ndarray:
+        """bf16 output as float32 numpy (H, W, C)"""
+        _, (h, w, c) = self.output(level)
+        raw = np.zeros((h, w, c), np.uint16)
+        if self.L.mf_backbone_download(self.h, level, _p(raw)) != 0:
+            raise MFError("backbone download failed")
+        return (raw.astype(np.uint32) << 16).view(np.float32)
+
+    def flops(self):
+        return float(self.L.mf_backbone_flops(self.h))
+
+    def numGemms(self):
+        return int(self.L.mf_backbone_num_gemms(self.h))

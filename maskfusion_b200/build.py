@@ -32,6 +32,7 @@ SOURCES = {
     "mf_track.cu": ["-fmad=false"],
     "mf_host.cu": ["-fmad=false"],
     "mf_capi.cu": ["-fmad=false"],
+    "mf_cnn.cu": [],                      # tensor-core GEMMs: no bit-exactness contract, FMA contraction on
 }
 
 

@@ -6,7 +6,11 @@ mkdir -p gpurun_out
 MODE=${1:-full}; shift || true
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1 ; echo "smoke rc=$?" ; tail -2 gpurun_out/smoke.log
-echo "== pytest gpu" ; timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 600 > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -12 gpurun_out/pytest_gpu.log | cut -c1-400
+if [ "${CNN_FIRST:-0}" = "1" ]; then
+  echo "== pytest cnn (isolated, short timeout: a hung tcgen05 pipeline must not take the box down)"
+  timeout 240 python -m pytest tests/test_gpu_cnn.py -q -m gpu -p no:cacheprovider --timeout 120 > gpurun_out/pytest_cnn.log 2>&1 ; echo "pytest cnn rc=$?" ; tail -30 gpurun_out/pytest_cnn.log | cut -c1-600
+fi
+echo "== pytest gpu" ; timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider --timeout 600 ${PYTEST_EXTRA:-} > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -12 gpurun_out/pytest_gpu.log | cut -c1-400
 echo "== bench" ; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?" ; tail -c 3500 gpurun_out/bench.json ; tail -5 gpurun_out/bench.err
 if [ "$MODE" = "full" ]; then
   echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ; tail -c 1200 gpurun_out/bench_ref.json
