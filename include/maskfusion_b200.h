@@ -123,6 +123,8 @@ typedef struct mf_backbone mf_backbone;
 const char* mf_cnn_last_error(void);
 /* out[MxN] = relu?(A[MxK] * B[NxK]^T + bias[N] + residual[MxN]); bf16 device pointers, K % 64 == 0, N % 64 == 0 */
 int mf_gemm_bf16(const void* dA, const void* dB, const float* dBias, const void* dResidual, void* dOut, int M, int N, int K, int relu, void* stream);
+/* implicit-GEMM 3x3/s1/p1 convolution, NHWC bf16, weights [Cout][3][3][Cin]; the activation is read through a 3-D TMA map (no im2col) */
+int mf_conv3x3_bf16(const void* dIn, const void* dW, const float* dBias, const void* dResidual, void* dOut, int H, int W, int Cin, int Cout, int relu, void* stream);
 mf_backbone* mf_backbone_create(int input_size, unsigned seed, void* stream);
 void mf_backbone_destroy(mf_backbone* h);
 int mf_backbone_num_layers(mf_backbone* h);

@@ -49,7 +49,7 @@ EXPORTS = [
     "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
     "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
-    "mf_klg_close", "mf_klg_write", "mf_cnn_last_error", "mf_gemm_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
+    "mf_klg_close", "mf_klg_write", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
 ]
@@ -113,6 +113,7 @@ def load_library():
     L.mf_klg_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mf_cnn_last_error.restype = C.c_char_p
     L.mf_gemm_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]
+    L.mf_conv3x3_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p]
     L.mf_backbone_create.restype = C.c_void_p
     L.mf_backbone_create.argtypes = [C.c_int, C.c_uint, C.c_void_p]
     L.mf_backbone_destroy.argtypes = [C.c_void_p]; L.mf_backbone_destroy.restype = None

@@ -50,6 +50,11 @@ MF_D void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, 
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+MF_D void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 MF_D void tcgen05_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 MF_D void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 MF_D void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -87,12 +92,17 @@ MF_D void tmem_ld32(uint32_t taddr, uint32_t* r)
 // ------------------------------------------------------------------------------------------
 // GEMM: out[M x N] (bf16) = relu?( A[M x K] * B[N x K]^T + bias[N] + residual[M x N] )
 // ------------------------------------------------------------------------------------------
-constexpr int GEMM_BM = 128, GEMM_BK = 64, GEMM_STAGES = 4, GEMM_THREADS = 192;
+constexpr int GEMM_BM = 128, GEMM_BK = 64, GEMM_STAGES = 3, GEMM_THREADS = 192;   // 3 stages (<= 99 KB): two CTAs per SM, one's epilogue overlaps the other's main loop
+
+// implicit-GEMM geometry of a 3x3 / stride 1 / pad 1 convolution: the A operand is the NHWC activation itself, seen through a 3-D
+// tensor map (C, W, H); an M tile is a Wbox x Hbox pixel block (Wbox*Hbox = 128) and each of the 9 taps is the same block shifted
+// by (kx-1, ky-1) -- TMA zero-fills the out-of-image part, which IS the padding.  No im2col buffer.
+struct ConvGeom { int mode; int Wimg, Himg, Wbox, Hbox, cblocks; };
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                                         const float* __restrict__ bias, const __nv_bfloat16* __restrict__ residual,
-                                                                        __nv_bfloat16* __restrict__ out, int M, int N, int K, int relu)
+                                                                        __nv_bfloat16* __restrict__ out, int M, int N, int K, int relu, ConvGeom geo)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages x A tile 16 KB][stages x B tile BN*128 B][barriers][tmem ptr]
@@ -108,6 +118,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_bf16_tcgen05(const __g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile_m = blockIdx.x, tile_n = blockIdx.y;
     const int num_k = K / GEMM_BK;
+    int px0 = 0, py0 = 0;
+    if (geo.mode) { const int tilesX = geo.Wimg / geo.Wbox; py0 = (tile_m / tilesX) * geo.Hbox; px0 = (tile_m % tilesX) * geo.Wbox; }
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -131,7 +143,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_bf16_tcgen05(const __g
                 const uint32_t ph = (kb / GEMM_STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
-                tma_load_2d(&mapA, &full[s], sA + s * A_BYTES, kb * GEMM_BK, tile_m * GEMM_BM);
+                if (geo.mode) {
+                    const int tap = kb / geo.cblocks, cb = kb - tap * geo.cblocks;
+                    tma_load_3d(&mapA, &full[s], sA + s * A_BYTES, cb * GEMM_BK, px0 + tap % 3 - 1, py0 + tap / 3 - 1);
+                } else
+                    tma_load_2d(&mapA, &full[s], sA + s * A_BYTES, kb * GEMM_BK, tile_m * GEMM_BM);
                 tma_load_2d(&mapB, &full[s], sB + s * B_BYTES, kb * GEMM_BK, tile_n * BN);
             }
         }
@@ -159,7 +175,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_bf16_tcgen05(const __g
         const int q = warp & 3;
         mbar_wait(tmem_full, 0);
         tcgen05_fence_after();
-        const int row = tile_m * GEMM_BM + q * 32 + lane;
+        const int rt = q * 32 + lane;
+        const int row = geo.mode ? (py0 + rt / geo.Wbox) * geo.Wimg + px0 + rt % geo.Wbox : tile_m * GEMM_BM + rt;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -176,8 +193,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) k_gemm_bf16_tcgen05(const __g
                     uint4 o4;
                     __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(&o4);
 #pragma unroll
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col + v * 8)), b1 = __ldg(reinterpret_cast<const float4*>(bias + col + v * 8 + 4));
+                    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
                     for (int e = 0; e < 8; ++e) {
-                        float x = __uint_as_float(r[v * 8 + e]) + bias[col + v * 8 + e];
+                        float x = __uint_as_float(r[v * 8 + e]) + bb[e];
                         if (rptr) x += __bfloat162float(rb[e]);
                         if (relu) x = fmaxf(x, 0.f);
                         ob[e] = __float2bfloat16(x);
@@ -323,29 +343,53 @@ static bool make_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t K,
     return true;
 }
 
+// 3-D map over an NHWC activation (C, W, H), box = {64, Wbox, Hbox}, SWIZZLE_128B
+static bool make_map_nhwc(CUtensorMap* m, const void* ptr, int C, int W, int H, int Wbox, int Hbox)
+{
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)Wbox, (cuuint32_t)Hbox};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { g_cnn_err = "cuTensorMapEncodeTiled (3-D) failed: " + std::to_string((int)r); return false; }
+    return true;
+}
+
 template <int BN>
 static size_t gemm_smem_bytes() { return (size_t)GEMM_STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 256 + 1024; }
 
 const char* cnn_last_error() { return g_cnn_err.c_str(); }
 
 // D = relu?(A * B^T + bias + residual); all device pointers; K % 64 == 0, N % 64 == 0
-int launch_gemm_bf16(const void* A, const void* B, const float* bias, const void* residual, void* out, int M, int N, int K, int relu, cudaStream_t s)
+// conv3x3 != nullptr: A is an NHWC activation [Himg x Wimg x Cin] and the GEMM is the implicit 3x3/s1/p1 convolution (K = 9*Cin)
+int launch_gemm_bf16(const void* A, const void* B, const float* bias, const void* residual, void* out, int M, int N, int K, int relu, cudaStream_t s,
+                     const int* conv3x3 /* Wimg, Himg, Cin */ = nullptr)
 {
     if (!ensure_encode()) return -1;
     if (K % 64 || N % 64 || M <= 0) { g_cnn_err = "gemm: need K % 64 == 0 and N % 64 == 0"; return -2; }
-    const int BN = (N % 128 == 0) ? 128 : 64;
+    const int mtiles = (M + GEMM_BM - 1) / GEMM_BM;
+    // fill the machine: with few M tiles prefer the narrow N tile (twice the CTAs)
+    const int BN = (N % 128 == 0 && mtiles * (N / 128) >= 148) ? 128 : 64;
     CUtensorMap mA, mB;
-    if (!make_map(&mA, A, (uint64_t)M, (uint64_t)K, GEMM_BM) || !make_map(&mB, B, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return -3;
-    dim3 grid((M + GEMM_BM - 1) / GEMM_BM, N / BN);
+    ConvGeom geo; memset(&geo, 0, sizeof geo);
+    if (conv3x3) {
+        const int Wimg = conv3x3[0], Himg = conv3x3[1], Cin = conv3x3[2];
+        geo.mode = 1; geo.Wimg = Wimg; geo.Himg = Himg; geo.Wbox = Wimg >= 128 ? 128 : Wimg; geo.Hbox = 128 / geo.Wbox; geo.cblocks = Cin / 64;
+        if (Wimg % geo.Wbox || Himg % geo.Hbox || Cin % 64 || K != 9 * Cin) { g_cnn_err = "conv3x3: unsupported geometry"; return -2; }
+        if (!make_map_nhwc(&mA, A, Cin, Wimg, Himg, geo.Wbox, geo.Hbox)) return -3;
+    } else if (!make_map(&mA, A, (uint64_t)M, (uint64_t)K, GEMM_BM)) return -3;
+    if (!make_map(&mB, B, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return -3;
+    dim3 grid(mtiles, N / BN);
     prof_mark(s, BN == 128 ? "k_gemm_bf16_tcgen05_n128" : "k_gemm_bf16_tcgen05_n64");
     if (BN == 128) {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_gemm_bf16_tcgen05<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<128>()); attr = true; }
-        k_gemm_bf16_tcgen05<128><<<grid, GEMM_THREADS, gemm_smem_bytes<128>(), s>>>(mA, mB, bias, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, M, N, K, relu);
+        k_gemm_bf16_tcgen05<128><<<grid, GEMM_THREADS, gemm_smem_bytes<128>(), s>>>(mA, mB, bias, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, M, N, K, relu, geo);
     } else {
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(k_gemm_bf16_tcgen05<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<64>()); attr = true; }
-        k_gemm_bf16_tcgen05<64><<<grid, GEMM_THREADS, gemm_smem_bytes<64>(), s>>>(mA, mB, bias, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, M, N, K, relu);
+        k_gemm_bf16_tcgen05<64><<<grid, GEMM_THREADS, gemm_smem_bytes<64>(), s>>>(mA, mB, bias, (const __nv_bfloat16*)residual, (__nv_bfloat16*)out, M, N, K, relu, geo);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { g_cnn_err = std::string("gemm launch: ") + cudaGetErrorString(e); return -4; }
@@ -396,6 +440,18 @@ static int run_conv(Backbone* b, int li, const __nv_bfloat16* in, int Hin, int W
     const int Hout = (Hin + 2 * L.pad - L.k) / L.stride + 1, Wout = (Win + 2 * L.pad - L.k) / L.stride + 1;
     const int M = Hout * Wout;
     const __nv_bfloat16* A = in;
+    const int wbox = Win >= 128 ? 128 : Win;
+    const bool implicit3 = L.k == 3 && L.stride == 1 && L.pad == 1 && (L.Cin % 64) == 0 && Win <= 128 * 1024 && (128 % wbox) == 0 && (Win % wbox) == 0 &&
+                           (Hin % (128 / wbox)) == 0 && wbox >= 8;
+    if (implicit3) {
+        int g3[3] = {Win, Hin, L.Cin};
+        int rc = launch_gemm_bf16(in, b->dW + L.wOff, b->dB + L.bOff, residual, out, M, L.Cout, L.Kpad, relu, s, g3);
+        b->flops += 2.0 * M * (double)L.Cout * (double)(9 * L.Cin);
+        b->gemms++;
+        if (HoutP) *HoutP = Hout;
+        if (WoutP) *WoutP = Wout;
+        return rc;
+    }
     if (!(L.k == 1 && L.stride == 1)) {
         if (L.k == 1 && L.stride == 2 && (L.Cin % 8) == 0) {
             prof_mark(s, "k_subsample2"); k_subsample2<<<592, 256, 0, s>>>(in, Hin, Win, L.Cin, b->col);
@@ -427,6 +483,14 @@ extern "C" int mf_gemm_bf16(const void* dA, const void* dB, const float* dBias, 
 {
     int rc = launch_gemm_bf16(dA, dB, dBias, dResidual, dOut, M, N, K, relu, (cudaStream_t)stream);
     return rc;
+}
+
+// implicit-GEMM 3x3 / stride 1 / pad 1 convolution on an NHWC bf16 activation (weights [Cout][3][3][Cin] bf16)
+extern "C" int mf_conv3x3_bf16(const void* dIn, const void* dW, const float* dBias, const void* dResidual, void* dOut, int H, int W, int Cin, int Cout,
+                               int relu, void* stream)
+{
+    int g3[3] = {W, H, Cin};
+    return launch_gemm_bf16(dIn, dW, dBias, dResidual, dOut, H * W, Cout, 9 * Cin, relu, (cudaStream_t)stream, g3);
 }
 
 // ResNet-101 (stages 3,4,23,3; stride in the first 1x1 of each stage as in Keras/matterport) + FPN(256)

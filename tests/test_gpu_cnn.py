@@ -47,6 +47,29 @@ def test_gemm_matches_torch(M, N, K, relu, res):
     assert err <= 2.0 ** -7 * max(scale, 1.0), (err, scale)       # one bf16 rounding of the output (fp32 accumulate on both sides)
 
 
+@pytest.mark.parametrize("H,W,Cin,Cout", [(256, 256, 64, 64), (128, 128, 128, 128), (64, 64, 256, 256), (32, 32, 512, 512), (16, 16, 256, 256)])
+def test_implicit_conv3x3_matches_torch(H, W, Cin, Cout):
+    """3x3/s1/p1 convolution through the 3-D TMA map (zero fill == padding), tiles of 128 / (64x2) / (32x4) / (16x8) pixels"""
+    import torch
+    import torch.nn.functional as F
+    import maskfusion_b200 as mfb
+    g = torch.Generator(device="cuda").manual_seed(H + Cin)
+    x = torch.randn(H, W, Cin, device="cuda", generator=g).to(torch.bfloat16).contiguous()
+    w = (torch.randn(Cout, 3, 3, Cin, device="cuda", generator=g) * (2.0 / (9 * Cin)) ** 0.5).to(torch.bfloat16).contiguous()
+    bias = torch.randn(Cout, device="cuda", generator=g)
+    res = torch.randn(H, W, Cout, device="cuda", generator=g).to(torch.bfloat16).contiguous()
+    out = torch.full((H, W, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    L = mfb.load_library()
+    rc = L.mf_conv3x3_bf16(C.c_void_p(x.data_ptr()), C.c_void_p(w.data_ptr()), C.c_void_p(bias.data_ptr()), C.c_void_p(res.data_ptr()),
+                           C.c_void_p(out.data_ptr()), H, W, Cin, Cout, 1, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, L.mf_cnn_last_error().decode()
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(2, 0, 1)[None], w.float().permute(0, 3, 1, 2), bias, padding=1)[0].permute(1, 2, 0) + res.float()
+    ref = torch.relu(ref)
+    assert not torch.isnan(out.float()).any()
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * max(ref.abs().max().item(), 1.0)
+
+
 def _torch_backbone(torch, bb, x_nhwc_bf16):
     """PyTorch restatement of resnet_graph(resnet101, stage5) + FPN (matterport mrcnn/model.py) with bf16 storage between layers"""
     import torch.nn.functional as F
