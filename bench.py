@@ -133,7 +133,8 @@ def algorithmic_bytes(name, S, P):
     table = {
         "k_index_project": 32 * S,                   # position + colour/time planes (normal plane never read)
         "k_index_resolve": 8 * P + 52 * P,
-        "k_clean_test": 48 * S + 1 * (S + P),
+        "k_clean_p1": 32 * S + 1 * (S + P),       # position + colour/time planes, keep flag
+        "k_clean_p2": 48 * P + 4 * P,              # ~one candidate per pixel neighbourhood; window reads hit L2
         "k_clean_scatter": 48 * S + 48 * S + 1 * (S + P),
         "k_splat_project": 16 * S,                   # position plane for every surfel; +32 B only for in-frustum stable ones
         "k_splat_resolve": 8 * P + 38 * P + 36 * P,

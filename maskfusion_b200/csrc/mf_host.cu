@@ -138,6 +138,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     keep.alloc((size_t)capacity + P);
     size_t nblk = ((size_t)capacity + P + 511) / 512 + 1;
     blockSums.alloc(nblk); blockSums2.alloc(nblk);
+    cand.alloc((size_t)capacity + P); candCount.alloc(1); candCount.zero(s);
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
         vmapG[l].alloc(Pl); nmapG[l].alloc(Pl); cloud[l].alloc(Pl); lastDepth[l].alloc(Pl); lastImage[l].alloc(Pl); corres[l].alloc(Pl);
@@ -235,9 +236,9 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
     int other = 1 - target, otherCount = 1 - countSel;
     launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, toRt(rigidInverse(pose)), o->cam, o->W, o->H,
                  time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, idx, vertConf, colorTime, o->depthFilt, o->mask, keep, blockSums,
-                 o->stream);
+                 cand, candCount, o->stream);
     target = other; countSel = otherCount;
-    o->launches += 3;
+    o->launches += 5;
 }
 
 void Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta)
@@ -269,7 +270,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
         if (l > 0) depthPyr[l].alloc(Pl);
-        vmap[l].alloc(Pl); nmap[l].alloc(Pl); nextImage[l].alloc(Pl); nextGrad[l].alloc(Pl);
+        vmap[l].alloc(Pl); nmap[l].alloc(Pl); nextImage[l].alloc(Pl); nextGrad[l].alloc(Pl); rgbValid[l].alloc(Pl);
     }
     edgeMap.alloc(P); edgeBinary.alloc(P); edgeBuf.alloc(P); edgeInv.alloc(P);
     dJobs.alloc(TRACK_MAX_JOBS);
@@ -357,7 +358,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
         m->prepareTracking();
         TrackJob& J = hJobs[j];
         for (int l = 0; l < 3; ++l) {
-            J.vmapC[l] = vmap[l]; J.nmapC[l] = nmap[l]; J.nextImage[l] = nextImage[l]; J.nextGrad[l] = nextGrad[l];
+            J.vmapC[l] = vmap[l]; J.nmapC[l] = nmap[l]; J.nextImage[l] = nextImage[l]; J.nextGrad[l] = nextGrad[l]; J.rgbValid[l] = rgbValid[l];
             J.vmapG[l] = m->vmapG[l]; J.nmapG[l] = m->nmapG[l]; J.lastDepth[l] = m->lastDepth[l]; J.lastImage[l] = m->lastImage[l];
             J.cloud[l] = m->cloud[l]; J.corres[l] = m->corres[l];
         }
@@ -366,8 +367,11 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
     }
     prof_mark(stream, "copy_jobs");
     cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
+    const uint8_t* fi[3] = {nextImage[0].p, nextImage[1].p, nextImage[2].p};
+    const short2* fg[3] = {nextGrad[0].p, nextGrad[1].p, nextGrad[2].p};
+    uint8_t* rv[3] = {rgbValid[0].p, rgbValid[1].p, rgbValid[2].p};
     launches += launch_tracking(dJobs, (int)ms.size(), poses, W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
-                                cfg.so3 != 0, numSMs, stream);
+                                cfg.so3 != 0, numSMs, stream, fi, fg, rv);
     prof_mark(stream, "copy_pose_d2h");
     for (Model* m : ms) {
         cudaCheck(cudaMemcpyAsync(m->hTrackOut, (const char*)m->trackState.p + offsetof(TrackState, out), 40 * sizeof(float),

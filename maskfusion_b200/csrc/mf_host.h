@@ -91,7 +91,7 @@ public:
     DevBuf<uint32_t> nonBlack;
     // association
     DevBuf<uint8_t> aflag; DevBuf<uint32_t> abest; DevBuf<float4> meas[3]; DevBuf<uint32_t> slot;
-    DevBuf<uint8_t> keep; DevBuf<uint32_t> blockSums, blockSums2;
+    DevBuf<uint8_t> keep; DevBuf<uint32_t> blockSums, blockSums2, cand, candCount;
     // tracking
     DevBuf<float4> vmapG[3], nmapG[3], cloud[3];
     DevBuf<float> lastDepth[3]; DevBuf<uint8_t> lastImage[3]; DevBuf<uint8_t> lastNextImage2;
@@ -132,7 +132,7 @@ public:
     // frame
     DevBuf<uint8_t> rgb3; DevBuf<uchar4> rgb; DevBuf<float> depthRaw, depthFilt; DevBuf<uint8_t> mask;
     DevBuf<float> depthPyr[3]; DevBuf<float4> vmap[3], nmap[3];
-    DevBuf<uint8_t> nextImage[3]; DevBuf<short2> nextGrad[3];
+    DevBuf<uint8_t> nextImage[3]; DevBuf<short2> nextGrad[3]; DevBuf<uint8_t> rgbValid[3];
     DevBuf<float> edgeMap; DevBuf<uint8_t> edgeBinary, edgeBuf, edgeInv;
     DevBuf<TrackJob> dJobs; TrackJob* hJobs = nullptr;
     DevBuf<uint8_t> initFlagR, initFlagF;

@@ -13,7 +13,7 @@ struct SurfelPlanes { float4* pos; float4* col; float4* nrm; };
 struct DataTerm { short2 zero; short2 one; float diff; int valid; };
 
 #define TRACK_MAX_JOBS 16
-#define TRACK_MAX_BLOCKS 512
+#define TRACK_MAX_BLOCKS 1024
 struct TrackPoses { float p[TRACK_MAX_JOBS][16]; };
 
 // Gauss-Newton state of one tracked model; lives in device memory for the whole frame
@@ -35,7 +35,7 @@ struct TrackState {
 
 struct TrackJob {
     const float4* vmapC[3]; const float4* nmapC[3];        // frame maps (shared by all models)
-    const uint8_t* nextImage[3]; const short2* nextGrad[3];
+    const uint8_t* nextImage[3]; const short2* nextGrad[3]; const uint8_t* rgbValid[3];
     const float4* vmapG[3]; const float4* nmapG[3];        // model maps in the model-global frame
     const float* lastDepth[3]; const uint8_t* lastImage[3];
     const uint8_t* lastNextImage2;
@@ -77,7 +77,7 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, Rt tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
-                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, cudaStream_t s);
+                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s);
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth,
                              float confThreshold, int time, int maxTime, int timeDelta, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
@@ -90,7 +90,8 @@ void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, 
 
 // ---- mf_track.cu ----
 int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
-                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s);
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s, const uint8_t* const* frameImage,
+                    const short2* const* frameGrad, uint8_t* const* rgbValid);
 void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,
                      const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s);
 

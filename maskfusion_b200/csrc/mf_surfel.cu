@@ -303,80 +303,94 @@ MF_D bool cleanFinish(float4& vp, float4& vc, float x, float y, float lpz, int c
 }
 
 #define SCAN_BLOCK 512
-// pass 1: test every old surfel and every emitted new vertex; write the (possibly
-// re-weighted) record back in place, a keep flag, and per-block keep counts.
-__global__ void __launch_bounds__(SCAN_BLOCK) k_clean_test(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
-                                                           const uint32_t* __restrict__ countPtr,
-                                                           const uint8_t* __restrict__ aflag, float4* __restrict__ m0, float4* __restrict__ m1,
-                                                           const float4* __restrict__ m2, int Ppix, CleanParams P,
-                                                           const uint32_t* __restrict__ idx, const float4* __restrict__ vertConf,
-                                                           const float4* __restrict__ colorTime, const float* __restrict__ depthFilt,
-                                                           const uint8_t* __restrict__ mask, uint8_t* __restrict__ keep,
-                                                           uint32_t* __restrict__ blockSums)
+// clean, pass 1a: stream the whole store once (old surfels, then the new vertices emitted by the association pass).
+// A vertex that does not project into the image needs no index-map window: it is finished here.  The others are
+// only REGISTERED in a device-wide candidate list (warp-aggregated atomic append); pass 1b works that list densely.
+// (An in-kernel window ran with 9/32 lanes active; a block-compacted variant was still latency bound at 2 blocks/SM.)
+__global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, float4* __restrict__ col, const uint32_t* __restrict__ countPtr,
+                                                  const uint8_t* __restrict__ aflag, float4* __restrict__ m0, float4* __restrict__ m1, int Ppix,
+                                                  CleanParams P, const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
+                                                  uint8_t* __restrict__ keep, uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount)
 {
     const uint32_t count = *countPtr;
     const uint32_t total = count + (uint32_t)Ppix;
+    const float cols = (float)P.W, rows = (float)P.H, ftime = (float)P.time;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
+        const uint32_t e = base + lane;
+        bool valid = false, need = false;
+        const bool isOld = e < count;
+        float4 vp = make_float4(0, 0, 0, 0), vc = vp;
+        if (isOld) { vp = pos[e]; vc = col[e]; valid = true; }
+        else if (e < total) { uint32_t p = e - count; if (aflag[p] == 2) { vp = m0[p]; vc = m1[p]; valid = true; } }
+        if (valid) {
+            float3 lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
+            float x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
+            float y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
+            need = ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows;
+            if (!need) {
+                const float w0 = vp.w, t0 = vc.w;
+                bool k = cleanFinish(vp, vc, x, y, lp.z, 0, 0, P, depthFilt, mask);
+                if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
+                else { uint32_t p = e - count; m0[p].w = vp.w; m1[p].w = vc.w; }
+                keep[e] = k ? 1 : 0;
+            }
+        } else if (e < total) keep[e] = 0;
+        unsigned nb = __ballot_sync(0xffffffffu, need);
+        if (nb) {
+            uint32_t wbase = 0;
+            if (lane == 0) wbase = atomicAdd(candCount, (uint32_t)__popc(nb));
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (need) cand[wbase + __popc(nb & ((1u << lane) - 1))] = e;
+        }
+    }
+}
+
+// clean, pass 1b: one thread per candidate: index-map window (copy_unstable.vert:86-113) + the rest of the shader
+__global__ void __launch_bounds__(256) k_clean_p2(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
+                                                  const uint32_t* __restrict__ countPtr, float4* __restrict__ m0, float4* __restrict__ m1,
+                                                  const float4* __restrict__ m2, CleanParams P, const uint32_t* __restrict__ idx,
+                                                  const float4* __restrict__ vertConf, const float4* __restrict__ colorTime,
+                                                  const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask, uint8_t* __restrict__ keep,
+                                                  const uint32_t* __restrict__ cand, const uint32_t* __restrict__ candCount)
+{
+    const uint32_t count = *countPtr, n = *candCount;
+    const float cols = (float)P.W, rows = (float)P.H;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t e = cand[j];
+        const bool isOld = e < count;
+        const uint32_t p = e - count;
+        float4 vp, vc, vn;
+        if (isOld) { vp = pos[e]; vc = col[e]; vn = nrm[e]; } else { vp = m0[p]; vc = m1[p]; vn = m2[p]; }
+        const float w0 = vp.w, t0 = vc.w;
+        float3 lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
+        float x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
+        float y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
+        float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
+        CleanEntry ce; ce.xn = x / cols; ce.yn = y / rows; ce.lx = lp.x; ce.ly = lp.y; ce.lz = lp.z; ce.init = vc.z; ce.rad = vn.w; ce.lnz = fabsf(ln.z);
+        int c1, c2;
+        cleanWindow(ce, P, idx, vertConf, colorTime, c1, c2);
+        bool k = cleanFinish(vp, vc, x, y, lp.z, c1, c2, P, depthFilt, mask);
+        if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
+        else { m0[p].w = vp.w; m1[p].w = vc.w; }
+        keep[e] = k ? 1 : 0;
+    }
+}
+
+// per-512-element keep counts for the ordered compaction
+__global__ void __launch_bounds__(SCAN_BLOCK) k_keep_block_sums(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ countPtr, int Ppix,
+                                                                uint32_t* __restrict__ blockSums, uint32_t* __restrict__ candCount)
+{
+    const uint32_t total = *countPtr + (uint32_t)Ppix;
     const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
     __shared__ uint32_t wsum[SCAN_BLOCK / 32];
-    __shared__ int wneed[SCAN_BLOCK / 32];
-    __shared__ CleanEntry entries[SCAN_BLOCK];
-    __shared__ int2 results[SCAN_BLOCK];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const float cols = (float)P.W, rows = (float)P.H, ftime = (float)P.time;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *candCount = 0;          // self-cleaning: ready for the next clean
     for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
         uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
-        bool valid = false;
-        const bool isOld = e < count;
-        float4 vp = make_float4(0, 0, 0, 0), vc = vp, vn = vp;
-        if (isOld) {
-            vp = pos[e]; vc = col[e]; vn = ldStream(nrm + e);            // pos/col are written below: coherent loads
-            valid = true;
-        } else if (e < total) {
-            uint32_t p = e - count;
-            if (aflag[p] == 2) { vp = m0[p]; vc = m1[p]; vn = m2[p]; valid = true; }   // merges (w = -1) always fail the test: skip them
-        }
-        const float w0 = vp.w, t0 = vc.w;
-        // (1) projection
-        float3 lp = make_float3(0, 0, 0); float x = 0, y = 0;
-        bool need = false;
-        if (valid) {
-            lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
-            x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
-            y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
-            need = ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows;
-        }
-        // (2) compact the window candidates of this block into shared memory
-        unsigned nb = __ballot_sync(0xffffffffu, need);
-        if (lane == 0) wneed[warp] = __popc(nb);
-        __syncthreads();
-        int off = 0, nNeed = 0;
-#pragma unroll
-        for (int w = 0; w < SCAN_BLOCK / 32; ++w) { int c = wneed[w]; if (w < warp) off += c; nNeed += c; }
-        const int slot = off + __popc(nb & ((1u << lane) - 1));
-        if (need) {
-            float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
-            CleanEntry ce; ce.xn = x / cols; ce.yn = y / rows; ce.lx = lp.x; ce.ly = lp.y; ce.lz = lp.z; ce.init = vc.z; ce.rad = vn.w; ce.lnz = fabsf(ln.z);
-            entries[slot] = ce;
-        }
-        __syncthreads();
-        // (3) dense window evaluation: one compacted entry per thread
-        if ((int)threadIdx.x < nNeed) {
-            int c1, c2;
-            cleanWindow(entries[threadIdx.x], P, idx, vertConf, colorTime, c1, c2);
-            results[threadIdx.x] = make_int2(c1, c2);
-        }
-        __syncthreads();
-        // (4) back to the owners
-        bool k = false;
-        if (valid) {
-            int2 r = need ? results[slot] : make_int2(0, 0);
-            k = cleanFinish(vp, vc, x, y, lp.z, r.x, r.y, P, depthFilt, mask);
-            if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
-            else { uint32_t p = e - count; m0[p].w = vp.w; m1[p].w = vc.w; }
-        }
-        if (e < total) keep[e] = k ? 1 : 0;
+        bool k = e < total && keep[e];
         unsigned bal = __ballot_sync(0xffffffffu, k);
-        if (lane == 0) wsum[warp] = __popc(bal);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(bal);
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t sum = 0;
@@ -534,7 +548,10 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
             float4 p = ldStream(pos + id);
             // cheap rejects before touching the other two planes
             float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
-            if (!(ph.z > maxDepth || ph.z < 0 || p.w < confThreshold)) {
+            // ... including the point-clipping test on the projected centre (same arithmetic as splatVertex), which most
+            // surfels of a large map fail: the basis / extent maths below then only runs for surfels inside the view
+            const float cxw = ((cam.fx * ph.x) / ph.z) + cam.cx, cyw = ((cam.fy * ph.y) / ph.z) + cam.cy;
+            if (!(ph.z > maxDepth || ph.z < 0 || p.w < confThreshold) && cxw >= 0 && cxw <= (float)W && cyw >= 0 && cyw <= (float)H) {
                 float4 c = ldStream(col + id), nr = ldStream(nrm + id);
                 v = splatVertex(p, c, nr, tinv, cam, W, H, maxDepth, confThreshold, ftime, fmaxTime, ftimeDelta);
                 if (v.ok) splatRange(v, W, H, x0, x1, y0, y1);
@@ -796,15 +813,17 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, Rt tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
-                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, cudaStream_t s)
+                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s)
 {
     CleanParams P;
     P.tinv = tinv; P.cam = cam; P.W = W; P.H = H; P.time = time; P.ftimeDelta = (float)timeDelta; P.confThreshold = confThreshold;
     P.outlierCoeff = outlierCoeff; P.maskID = maskID;
     int Ppix = W * H;
     int blocks = persistentBlocks(4);
-    prof_mark(s, "k_clean_test"); k_clean_test<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, aflag, meas[0], meas[1], meas[2], Ppix, P, idx, vertConf,
-                                               colorTime, depthFilt, mask, keep, blockSums);
+    prof_mark(s, "k_clean_p1"); k_clean_p1<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, count, aflag, meas[0], meas[1], Ppix, P, depthFilt, mask, keep, cand, candCount);
+    prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, idx, vertConf, colorTime, depthFilt,
+                                                                               mask, keep, cand, candCount);
+    prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<blocks, SCAN_BLOCK, 0, s>>>(keep, count, Ppix, blockSums, candCount);
     prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount);
     prof_mark(s, "k_clean_scatter"); k_clean_scatter<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
                                                   dst.pos, dst.col, dst.nrm);

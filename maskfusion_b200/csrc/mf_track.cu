@@ -380,12 +380,33 @@ __global__ void __launch_bounds__(TRK_THREADS) k_so3_step(TrackJob* jobs, int W,
 // ---------------------------------------------------------------------------------------
 // photometric correspondences + residual statistics
 // ---------------------------------------------------------------------------------------
+// pose-independent part of residualKernel (reduce.cu:821-845): 4x4 window of non-zero intensities + gradient-magnitude gate.
+// Evaluated once per level per frame instead of once per Gauss-Newton iteration (16 byte loads per pixel per iteration saved).
+__global__ void k_rgb_valid(const uint8_t* __restrict__ nextImage, const short2* __restrict__ grad, int W, int H, float minScale, uint8_t* __restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= W * H) return;
+    int i = k / W, j0 = k - i * W;
+    bool valid = false;
+    if (j0 < W - 5 && i < H - 1) {
+        valid = true;
+        for (int u = max(i - 2, 0); u < min(i + 2, H); ++u)
+            for (int v = max(j0 - 2, 0); v < min(j0 + 2, W); ++v) valid = valid && (nextImage[u * W + v] > 0);
+        if (valid) {
+            short2 g = grad[k];
+            float mTwo = (float)(((int)g.x * (int)g.x) + ((int)g.y * (int)g.y));
+            valid = mTwo >= minScale;
+        }
+    }
+    out[k] = valid ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(TRK_THREADS) k_rgb_residual(TrackJob* jobs, int level, int W, int H, float minScale, float maxDepthDelta, int rgbOnly)
 {
     TrackJob& J = jobs[blockIdx.y];
     TrackState* st = J.st;
     if (st->levelBreak) return;
-    const short2* __restrict__ grad = J.nextGrad[level];
+    const uint8_t* __restrict__ rgbValid = J.rgbValid[level];
     const float* __restrict__ lastDepth = J.lastDepth[level];
     const float* __restrict__ nextDepth = J.lastDepth[level];      // reference quirk: both pyramids derive from vmaps_tmp (RGBDOdometry.cpp:187-215)
     const uint8_t* __restrict__ lastImage = J.lastImage[level];
@@ -400,14 +421,9 @@ __global__ void __launch_bounds__(TRK_THREADS) k_rgb_residual(TrackJob* jobs, in
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
         int i = k / W, j0 = k - i * W;
         DataTerm c; c.zero = make_short2(0, 0); c.one = make_short2(0, 0); c.diff = 0; c.valid = 0;
-        if (j0 < W - 5 && i < H - 1) {
-            bool valid = true;
-            for (int u = max(i - 2, 0); u < min(i + 2, H); ++u)
-                for (int v = max(j0 - 2, 0); v < min(j0 + 2, W); ++v) valid = valid && (nextImage[u * W + v] > 0);
-            if (valid) {
-                short2 g = grad[k];
-                float mTwo = (float)(((int)g.x * (int)g.x) + ((int)g.y * (int)g.y));
-                if (mTwo >= minScale) {
+        {
+            {
+                if (rgbValid[k]) {
                     int y = i, x = j0;
                     float d1 = nextDepth[k];
                     if (!isnan(d1)) {
@@ -673,13 +689,14 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restri
 static int trackBlocks(int N, int numSMs)
 {
     int need = (N + TRK_THREADS - 1) / TRK_THREADS;
-    int cap = numSMs * 2;
+    int cap = numSMs * 4;
     if (cap > TRACK_MAX_BLOCKS) cap = TRACK_MAX_BLOCKS;
     return need < cap ? need : cap;
 }
 
 int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
-                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s)
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s, const uint8_t* const* frameImage,
+                    const short2* const* frameGrad, uint8_t* const* rgbValid)
 {
     int launches = 0;
     const bool icp = !rgbOnly && icpWeight > 0;
