@@ -111,6 +111,27 @@ int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binary);        
 int mf_set_frame_classes(mf_context* ctx, const int32_t* class_ids, int n);   /* FrameData::classIDs of the NEXT processFrame call (classIDs[mask value]; entry 0 = background), Core/FrameData.h:40 */
 int mf_download_segmentation(mf_context* ctx, uint8_t* mask, uint8_t* projected_ids);   /* SegmentationResult::fullSegmentation (textureMask) and GlobalProjection::getProjectedModelIDs */
 int mf_model_class_id(mf_context* ctx, int i);                                /* Model::getClassID */
+
+/* ---- object-sharded mode: one context per GPU/rank, object Models (and their surfel stores) partitioned over the ranks
+ *      (BASELINE.json north_star "Object Models ... shard one-per-GPU"; couplings per frame are exactly those of
+ *      MaskFusion.cpp:274 (global pose -> static objects), GlobalProjection.cpp:66-95 (one depth-tested ID image) and
+ *      MaskFusion.cpp:296-297 (one segmentation).  One frame on every rank =
+ *          [broadcast rgb/depth/mask/classIDs]  mf_set_frame_classes; mf_shard_frame_begin;
+ *          mf_shard_get_poses -> [all-gather] -> mf_shard_set_poses;
+ *          mf_shard_project -> [all-reduce MIN over the uint64 keys at mf_shard_projection_keys] ;
+ *          mf_shard_frame_end
+ *      The collectives themselves run above this ABI (NCCL through torch.distributed, maskfusion_b200/sharding.py) on the
+ *      context's stream.  With world == 1 the three calls are exactly mf_process_frame. ---- */
+int mf_shard_configure(mf_context* ctx, int rank, int world);                 /* before the first frame; rank 0 owns the background model */
+int mf_shard_frame_begin(mf_context* ctx, const void* rgb, const void* depth, int64_t timestamp, const void* mask, int on_device);
+int mf_shard_get_poses(mf_context* ctx, float* out_nmodels_x32, int capacity_models);   /* returns nModels; row = pose(16) lastTransform(16), row-major; ghost rows = 0 */
+int mf_shard_set_poses(mf_context* ctx, const float* gathered_world_x_nmodels_x32);
+int mf_shard_project(mf_context* ctx);                                        /* lifecycle after tracking + local models into the key image */
+void* mf_shard_projection_keys(mf_context* ctx);                              /* device pointer, width*height uint64 (depth bits << 32 | model index << 26 | surfel) */
+int mf_shard_frame_end(mf_context* ctx, float weight_multiplier);
+int mf_model_owner(mf_context* ctx, int i);                                   /* rank holding model i's surfels */
+int mf_shard_pick_owner(const int64_t* loads, int world);                     /* placement rule for a new model: least owned capacity, ties -> highest rank (host only) */
+
 /* in-stream CUDA-event stage timer (replaces the reference's TICK/TOCK Stopwatch, Core/Utils/Stopwatch.h:46-54) */
 int mf_set_profiling(mf_context* ctx, int on);
 int mf_get_stage_times(mf_context* ctx, char* buf, int bufsize);   /* lines: "name count total_ms" */

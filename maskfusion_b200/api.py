@@ -52,6 +52,8 @@ EXPORTS = [
     "mf_klg_close", "mf_klg_write", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
+    "mf_shard_configure", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
+    "mf_shard_projection_keys", "mf_shard_frame_end", "mf_model_owner", "mf_shard_pick_owner",
 ]
 
 
@@ -127,6 +129,15 @@ def load_library():
     L.mf_backbone_flops.restype = C.c_double; L.mf_backbone_flops.argtypes = [C.c_void_p]
     L.mf_backbone_num_gemms.argtypes = [C.c_void_p]
     L.mf_backbone_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mf_shard_configure.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.mf_shard_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    L.mf_shard_get_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.mf_shard_set_poses.argtypes = [C.c_void_p, C.c_void_p]
+    L.mf_shard_project.argtypes = [C.c_void_p]
+    L.mf_shard_projection_keys.restype = C.c_void_p; L.mf_shard_projection_keys.argtypes = [C.c_void_p]
+    L.mf_shard_frame_end.argtypes = [C.c_void_p, C.c_float]
+    L.mf_model_owner.argtypes = [C.c_void_p, C.c_int]
+    L.mf_shard_pick_owner.argtypes = [C.c_void_p, C.c_int]
     _LIB = L
     return L
 

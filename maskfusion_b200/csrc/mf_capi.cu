@@ -25,6 +25,8 @@ extern "C" int mf_abi_version(void) { return MF_ABI_VERSION; }
 #define MF_NEED(ctx) if (!(ctx) || !(ctx)->mf) { g_err = "null context"; return -1; }
 #define MF_MODEL(ctx, i) if ((i) < 0 || (i) >= (int)(ctx)->mf->models.size()) { g_err = "model index out of range"; return -2; } Model* m = (ctx)->mf->models[i].get();
 
+#define MF_OWNED(m) if (!(m)->owned) { g_err = "model is owned by another rank (sharded mode): no device buffers here"; return -4; }
+
 static Mat4 fromColMajor(const float* p) { Mat4 r; for (int rr = 0; rr < 4; ++rr) for (int c = 0; c < 4; ++c) r.m[rr * 4 + c] = p[c * 4 + rr]; return r; }
 static void toColMajor(const Mat4& T, float* p) { for (int rr = 0; rr < 4; ++rr) for (int c = 0; c < 4; ++c) p[c * 4 + rr] = T.m[rr * 4 + c]; }
 
@@ -94,7 +96,7 @@ extern "C" int mf_model_surfel_count(mf_context* ctx, int i) { MF_TRY MF_NEED(ct
 
 extern "C" int mf_download_surfels(mf_context* ctx, int i, float* out, int max_surfels)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     uint32_t n = m->lastCount();
     if ((int)n > max_surfels) n = (uint32_t)max_surfels;
@@ -108,7 +110,7 @@ extern "C" int mf_download_surfels(mf_context* ctx, int i, float* out, int max_s
 }
 extern "C" int mf_upload_surfels(mf_context* ctx, int i, const float* in, int n)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     if (n < 0 || (uint32_t)n > m->capacity) { g_err = "upload exceeds model capacity"; return -4; }
     if (n) {
@@ -145,7 +147,7 @@ extern "C" int mf_set_frame(mf_context* ctx, const uint8_t* rgb, const float* de
 }
 extern "C" int mf_model_perform_tracking(mf_context* ctx, int i, float* transform16)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     std::vector<Model*> ms{m};
     ctx->mf->trackModels(ms);
     if (transform16) toColMajor(m->lastTransform, transform16);
@@ -154,31 +156,31 @@ extern "C" int mf_model_perform_tracking(mf_context* ctx, int i, float* transfor
 }
 extern "C" int mf_model_predict_indices(mf_context* ctx, int i, int time)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     m->predictIndices(time, ctx->mf->cfg.maxDepthProcessed, ctx->mf->cfg.timeDelta); return 0;
     MF_CATCH(-1)
 }
 extern "C" int mf_model_fuse(mf_context* ctx, int i, int time, float depth_cutoff, float weight_multiplier)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     m->fuse(time, depth_cutoff, weight_multiplier); return 0;
     MF_CATCH(-1)
 }
 extern "C" int mf_model_clean(mf_context* ctx, int i, int time)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     m->clean(time, ctx->mf->cfg.timeDelta, ctx->mf->cfg.maxDepthProcessed); return 0;
     MF_CATCH(-1)
 }
 extern "C" int mf_model_combined_predict(mf_context* ctx, int i, int time, int max_time)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     m->combinedPredict(ctx->mf->cfg.maxDepthProcessed, time, max_time, ctx->mf->cfg.timeDelta); return 0;
     MF_CATCH(-1)
 }
 extern "C" int mf_model_init_from_frame(mf_context* ctx, int i, int time)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     m->initialise(time); return 0;
     MF_CATCH(-1)
 }
@@ -215,7 +217,7 @@ extern "C" int mf_download_frame_maps(mf_context* ctx, int level, float* depth, 
 }
 extern "C" int mf_download_model_maps(mf_context* ctx, int i, int level, float* vmap, float* nmap)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     if (level < 0 || level > 2) { g_err = "level out of range"; return -2; }
     int Pl = (o->W >> level) * (o->H >> level);
@@ -226,7 +228,7 @@ extern "C" int mf_download_model_maps(mf_context* ctx, int i, int level, float* 
 }
 extern "C" int mf_download_index_map(mf_context* ctx, int i, uint32_t* idx, float* vc, float* ct, float* nr)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     d2h(o, idx, m->idx.p, o->P); d2h(o, vc, m->vertConf.p, o->P); d2h(o, ct, m->colorTime.p, o->P); d2h(o, nr, m->normRad.p, o->P);
     o->sync(); return 0;
@@ -234,7 +236,7 @@ extern "C" int mf_download_index_map(mf_context* ctx, int i, uint32_t* idx, floa
 }
 extern "C" int mf_download_prediction(mf_context* ctx, int i, uint8_t* image4, float* vc, float* nr, uint16_t* time)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     d2h(o, image4, m->splatImage.p, o->P); d2h(o, vc, m->splatVertex.p, o->P); d2h(o, nr, m->splatNormal.p, o->P); d2h(o, time, m->splatTime.p, o->P);
     o->sync(); return 0;
@@ -242,7 +244,7 @@ extern "C" int mf_download_prediction(mf_context* ctx, int i, uint8_t* image4, f
 }
 extern "C" int mf_download_fill_in(mf_context* ctx, int i, uint8_t* image4, float* v4, float* n4)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     if (!m->fillIn) { g_err = "model has no fill-in textures"; return -5; }
     d2h(o, image4, m->fillImage.p, o->P); d2h(o, v4, m->fillVertex.p, o->P); d2h(o, n4, m->fillNormal.p, o->P);
@@ -251,7 +253,7 @@ extern "C" int mf_download_fill_in(mf_context* ctx, int i, uint8_t* image4, floa
 }
 extern "C" int mf_download_association(mf_context* ctx, int i, uint8_t* flag, uint32_t* best, float* meas12)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     d2h(o, flag, m->aflag.p, o->P); d2h(o, best, m->abest.p, o->P);
     if (meas12) {
@@ -265,7 +267,7 @@ extern "C" int mf_download_association(mf_context* ctx, int i, uint8_t* flag, ui
 }
 extern "C" int mf_download_track_stats(mf_context* ctx, int i, double* A36, double* b6, float* err6)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     TrackState st;
     cudaCheck(cudaMemcpyAsync(&st, m->trackState.p, sizeof st, cudaMemcpyDeviceToHost, o->stream), "D2H");
@@ -307,6 +309,31 @@ extern "C" int mf_download_segmentation(mf_context* ctx, uint8_t* mask, uint8_t*
     o->sync(); return 0;
     MF_CATCH(-1)
 }
+// ---- object-sharded mode ----
+extern "C" int mf_shard_configure(mf_context* ctx, int rank, int world) { MF_TRY MF_NEED(ctx) ctx->mf->configureShard(rank, world); return 0; MF_CATCH(-1) }
+extern "C" int mf_shard_frame_begin(mf_context* ctx, const void* rgb, const void* depth, int64_t ts, const void* mask, int on_device)
+{
+    MF_TRY MF_NEED(ctx)
+    if (!rgb || !depth || ts < 0) { g_err = "frame_begin: rgb/depth must be non-null and timestamp >= 0"; return -3; }
+    ctx->mf->frameBegin((const uint8_t*)rgb, (const float*)depth, ts, (const uint8_t*)mask, nullptr, false, on_device != 0);
+    return 0;
+    MF_CATCH(-1)
+}
+extern "C" int mf_shard_get_poses(mf_context* ctx, float* out, int capacity_models)
+{
+    MF_TRY MF_NEED(ctx)
+    if ((int)ctx->mf->models.size() > capacity_models) { g_err = "get_poses: buffer too small"; return -2; }
+    ctx->mf->getShardPoses(out);
+    return (int)ctx->mf->models.size();
+    MF_CATCH(-1)
+}
+extern "C" int mf_shard_set_poses(mf_context* ctx, const float* gathered) { MF_TRY MF_NEED(ctx) ctx->mf->setShardPoses(gathered); return 0; MF_CATCH(-1) }
+extern "C" int mf_shard_project(mf_context* ctx) { MF_TRY MF_NEED(ctx) ctx->mf->frameProject(); return 0; MF_CATCH(-1) }
+extern "C" void* mf_shard_projection_keys(mf_context* ctx) { if (!ctx || !ctx->mf) return nullptr; return ctx->mf->projKeys.p; }
+extern "C" int mf_shard_frame_end(mf_context* ctx, float weight_multiplier) { MF_TRY MF_NEED(ctx) ctx->mf->frameEnd(weight_multiplier); return 0; MF_CATCH(-1) }
+extern "C" int mf_model_owner(mf_context* ctx, int i) { MF_NEED(ctx) MF_MODEL(ctx, i) return m->ownerRank; }
+extern "C" int mf_shard_pick_owner(const int64_t* loads, int world) { if (!loads || world < 1 || world > 64) return -1; return MaskFusion::pickOwner(loads, world); }
+
 extern "C" int mf_model_class_id(mf_context* ctx, int i) { MF_NEED(ctx) MF_MODEL(ctx, i) return m->classID; }
 extern "C" int mf_set_profiling(mf_context* ctx, int on)
 {
@@ -337,7 +364,7 @@ extern "C" int mf_debug_set_poses(mf_context* ctx, int i, const float* pose16, c
 }
 extern "C" int mf_icp_step(mf_context* ctx, int i, int level, const float* Rcurr9, const float* tcurr3, float* out29)
 {
-    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i)
+    MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
     if (level < 0 || level > 2) { g_err = "level out of range"; return -2; }
     TrackPoses pp; memset(&pp, 0, sizeof pp);

@@ -115,12 +115,13 @@ static void rotToQuat(const float* R, float* q)
 // ======================================================================================
 // Model
 // ======================================================================================
-Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, int cap)
-    : owner(o), id(id_), pose(Mat4::identity()), lastPose(Mat4::identity()), initialC2Winv(Mat4::identity()),
+Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, int cap, int ownerRank_, bool ghost)
+    : owner(o), ownerRank(ownerRank_), owned(!ghost), id(id_), pose(Mat4::identity()), lastPose(Mat4::identity()), initialC2Winv(Mat4::identity()),
       confidenceThreshold(conf), maxDepth(FLT_MAX), fillIn(enableFillIn), capacity((uint32_t)cap), lastTransform(Mat4::identity())
 {
     const int W = o->W, H = o->H, P = o->P;
     cudaStream_t s = o->stream;
+    if (ghost) return;
     for (int b = 0; b < 2; ++b) { pos[b].alloc(capacity); col[b].alloc(capacity); nrm[b].alloc(capacity); }
     count.alloc(2); count.zero(s);
     cudaCheck(cudaMallocHost((void**)&hCount, 2 * sizeof(uint32_t)), "cudaMallocHost"); hCount[0] = hCount[1] = 0;
@@ -158,6 +159,7 @@ Model::~Model()
 
 unsigned Model::lastCount()
 {
+    if (!owned) throw CudaError{"model is owned by another rank (sharded mode): no surfel store here"};
     cudaCheck(cudaMemcpyAsync(hCount, dCount(), sizeof(uint32_t), cudaMemcpyDeviceToHost, owner->stream), "count D2H");
     owner->sync();
     return hCount[0];
@@ -388,22 +390,30 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
 
 void MaskFusion::predict()
 {
-    for (auto& m : models) m->combinedPredict(cfg.maxDepthProcessed, tick, tick, cfg.timeDelta);   // MaskFusion.cpp:616-628
+    for (auto& m : models) if (m->owned) m->combinedPredict(cfg.maxDepthProcessed, tick, tick, cfg.timeDelta);   // MaskFusion.cpp:616-628
 }
 
 // GlobalProjection::project (GlobalProjection.cpp:43-107): all models into one depth-tested key image; the key's low word
 // is (model list index << 26 | surfel id), i.e. the reference's draw order.  The ID image stays on the device.
-void MaskFusion::globalProjection()
+void MaskFusion::globalProjection() { projectLocal(); projectResolve(); }
+
+// local half: every model whose surfels live here goes into the key image (ghost models arrive through the min all-reduce)
+void MaskFusion::projectLocal()
 {
-    uint8_t idx2id[256]; memset(idx2id, 0, sizeof idx2id);
     if (models.size() > 63) throw CudaError{"global projection supports up to 63 models"};
     for (size_t i = 0; i < models.size(); ++i) {
         Model* m = models[i].get();
-        idx2id[i] = m->id;
+        if (!m->owned) continue;
         launch_splat_project_only(m->current(), m->dCount(), toRt(rigidInverse(m->pose)), cam, W, H, cfg.depthCutoff, 12.0f /* :61 */, tick, tick,
                                   cfg.timeDelta, (uint32_t)i << 26, projKeys, stream);
         launches += 1;
     }
+}
+
+void MaskFusion::projectResolve()
+{
+    uint8_t idx2id[256]; memset(idx2id, 0, sizeof idx2id);
+    for (size_t i = 0; i < models.size(); ++i) idx2id[i] = models[i]->id;
     memcpy(hSmall, idx2id, 256);
     cudaCheck(cudaMemcpyAsync(tblIndexToId, hSmall, 256, cudaMemcpyHostToDevice, stream), "tbl upload");
     sync();      // hSmall is reused below
@@ -512,23 +522,86 @@ unsigned char MaskFusion::getNextModelID(bool assign)
 Model* MaskFusion::spawnObjectModel()
 {
     Model* g = models[0].get();
-    models.emplace_back(new Model(this, getNextModelID(true), cfg.confObject, false, cfg.capacityObject));
+    // sharded mode: the new store goes to the least-loaded rank; every rank evaluates the same rule on the same replicated list
+    int64_t loads[64] = {0};
+    for (auto& m : models) loads[m->ownerRank] += m->capacity;
+    const int ownerRank = world > 1 ? pickOwner(loads, world) : 0;
+    models.emplace_back(new Model(this, getNextModelID(true), cfg.confObject, false, cfg.capacityObject, ownerRank, ownerRank != rank));
     Model* nm = models.back().get();
-    // newModel->getFrameOdometry().initFirstRGB(textureRGB)
-    if (!intensityValid) {
-        launch_intensity(rgb, P, nextImage[0], stream);
-        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
-        launches += 3; intensityValid = true;
+    if (nm->owned) {
+        // newModel->getFrameOdometry().initFirstRGB(textureRGB)
+        if (!intensityValid) {
+            launch_intensity(rgb, P, nextImage[0], stream);
+            for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
+            launches += 3; intensityValid = true;
+        }
+        cudaCheck(cudaMemcpyAsync(nm->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
     }
-    cudaCheck(cudaMemcpyAsync(nm->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
     nm->makeStatic(g->pose);
     return nm;
+}
+
+int MaskFusion::pickOwner(const int64_t* loads, int world)
+{
+    int best = 0;
+    for (int r = 1; r < world; ++r) if (loads[r] <= loads[best]) best = r;
+    return best;
+}
+
+void MaskFusion::configureShard(int rank_, int world_)
+{
+    if (world_ < 1 || world_ > 64 || rank_ < 0 || rank_ >= world_) throw CudaError{"configureShard: need 0 <= rank < world <= 64"};
+    if (tick != 1) throw CudaError{"configureShard: must be called before the first frame"};
+    if (world_ > 1 && !cfg.enableMultipleModels) throw CudaError{"configureShard: a -static run has one model and does not shard (run replicas instead)"};
+    rank = rank_; world = world_;
+    if (rank != 0) {          // the background model lives on rank 0
+        Model* g = models[0].get();
+        models[0].reset(new Model(this, g->id, cfg.confGlobal, true, cfg.capacityGlobal, 0, true));
+        sync();
+    }
+}
+
+// [nModels][32] row-major pose + lastTransform of the models tracked here
+void MaskFusion::getShardPoses(float* out) const
+{
+    for (size_t i = 0; i < models.size(); ++i) {
+        const Model* m = models[i].get();
+        if (m->owned) { memcpy(out + i * 32, m->pose.m, 64); memcpy(out + i * 32 + 16, m->lastTransform.m, 64); }
+        else memset(out + i * 32, 0, 128);
+    }
+}
+
+void MaskFusion::setShardPoses(const float* all)
+{
+    const size_t n = models.size();
+    for (size_t i = 0; i < n; ++i) {
+        Model* m = models[i].get();
+        if (m->owned) continue;
+        const bool tracked = i == 0 || m->nonstatic || cfg.trackAllModels;
+        if (!tracked) continue;                                        // static objects are re-posed from the background pose below
+        const float* row = all + ((size_t)m->ownerRank * n + i) * 32;
+        m->lastPose = m->pose;
+        memcpy(m->pose.m, row, 64); memcpy(m->lastTransform.m, row + 16, 64);
+    }
 }
 
 bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_t timestamp, const uint8_t* maskIn, const Mat4* inPose,
                               float weightMultiplier, bool bootstrap, bool onDevice)
 {
+    if (world > 1) throw CudaError{"processFrame: this context is one shard of several; drive it through the frame_begin/project/end phases"};
+    frameBegin(rgbIn, depthIn, timestamp, maskIn, inPose, bootstrap, onDevice);
+    frameProject();
+    frameEnd(weightMultiplier);
+    return false;
+}
+
+// MaskFusion.cpp:200-276: upload, filter, first-frame initialisation or tracking of every model whose store lives here
+void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t timestamp, const uint8_t* maskIn, const Mat4* inPose, bool bootstrap,
+                            bool onDevice)
+{
     const bool multi = cfg.enableMultipleModels != 0;
+    if (world > 1 && inPose) throw CudaError{"sharded mode tracks every frame (no external poses)"};
+    fTimestamp = timestamp; fHasPose = inPose != nullptr; if (inPose) fInPose = *inPose; fBootstrap = bootstrap;
     setFrame(rgbIn, depthIn, nullptr, onDevice);        // -static: textureMask stays all zero (MaskFusion.cpp:223-230); multi: keeps the last segmentation
     frameHasMask = false;
     if (multi && maskIn) {
@@ -537,31 +610,50 @@ bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_
     }
     Model* g = models[0].get();
     if (tick == 1) {
-        g->initialise(tick);
-        // globalModel->getFrameOdometry().initFirstRGB (MaskFusion.cpp:238)
-        launch_intensity(rgb, P, nextImage[0], stream);
-        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
-        cudaCheck(cudaMemcpyAsync(g->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
-        launches += 3;
-    } else {
-        if (bootstrap || !inPose) {
-            generateCUDATextures();
-            // MaskFusion.cpp:247-276: the global model and every tracked object share one batched launch sequence
-            std::vector<Model*> tracked{g};
-            for (size_t i = 1; i < models.size(); ++i)
-                if (models[i]->nonstatic || cfg.trackAllModels) tracked.push_back(models[i].get());
-            trackModels(tracked);
-            for (size_t i = 1; i < models.size(); ++i) {
-                Model* m = models[i].get();
-                if (m->nonstatic || cfg.trackAllModels) {
-                    const float* T = m->lastTransform.m;
-                    float d = sqrtf((T[3] * T[3] + T[7] * T[7]) + T[11] * T[11]);
-                    if (d > 0.2f) { models.erase(models.begin() + i); --i; }          // inactivateModel (:268-272)
-                } else m->updateStaticPose(g->pose);
-            }
-            if (bootstrap && inPose) g->overridePose(mul(g->pose, *inPose));
+        if (g->owned) {
+            g->initialise(tick);
+            // globalModel->getFrameOdometry().initFirstRGB (MaskFusion.cpp:238)
+            launch_intensity(rgb, P, nextImage[0], stream);
+            for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
+            cudaCheck(cudaMemcpyAsync(g->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
+            launches += 3;
+        }
+    } else if (bootstrap || !inPose) {
+        generateCUDATextures();
+        // MaskFusion.cpp:247-276: the global model and every tracked object share one batched launch sequence
+        std::vector<Model*> tracked;
+        for (size_t i = 0; i < models.size(); ++i)
+            if (models[i]->owned && (i == 0 || models[i]->nonstatic || cfg.trackAllModels)) tracked.push_back(models[i].get());
+        trackModels(tracked);
+    }
+}
+
+// MaskFusion.cpp:257-290 after the poses are known everywhere: inactivation, static poses, local part of the ID projection
+void MaskFusion::frameProject()
+{
+    if (tick == 1 || !(fBootstrap || !fHasPose)) return;
+    Model* g = models[0].get();
+    for (size_t i = 1; i < models.size(); ++i) {
+        Model* m = models[i].get();
+        if (m->nonstatic || cfg.trackAllModels) {
+            const float* T = m->lastTransform.m;
+            float d = sqrtf((T[3] * T[3] + T[7] * T[7]) + T[11] * T[11]);
+            if (d > 0.2f) { models.erase(models.begin() + i); --i; }          // inactivateModel (:268-272)
+        } else m->updateStaticPose(g->pose);
+    }
+    if (fBootstrap && fHasPose) g->overridePose(mul(g->pose, fInPose));
+    if (cfg.enableMultipleModels) projectLocal();                              // :289-290
+}
+
+// MaskFusion.cpp:290-607: segmentation (replicated: every rank holds the same merged key image), spawn, fusion of the local stores
+void MaskFusion::frameEnd(float weightMultiplier)
+{
+    const bool multi = cfg.enableMultipleModels != 0;
+    Model* g = models[0].get();
+    if (tick > 1) {
+        if (fBootstrap || !fHasPose) {
             if (multi) {
-                globalProjection();                                                    // :289-290
+                projectResolve();
                 if (spawnOffset < cfg.modelSpawnOffset) spawnOffset++;
                 SegmentationResult seg = performSegmentation(spawnOffset >= cfg.modelSpawnOffset);
                 Model* nm = nullptr;
@@ -571,7 +663,7 @@ bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_
                     nm->classID = seg.newClassID;
                 }
                 for (size_t i = 1; i < models.size(); ++i) models[i]->maxDepth = 30.0f + 30.0f * 1.2f;   // getMaxDepth(30, 30), :292,337-341
-                if (nm) {                                                              // :344-353
+                if (nm && nm->owned) {                                                 // :344-353
                     nm->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
                     nm->fuse(tick, cfg.maxDepthProcessed, 100.0f);
                     nm->clean(tick, cfg.timeDelta, cfg.maxDepthProcessed);
@@ -582,13 +674,13 @@ bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_
                 }
             }
         } else {
-            g->overridePose(*inPose);
+            g->overridePose(fInPose);
         }
         if (!cfg.rgbOnly) {
-            for (auto& m : models) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
-            for (auto& m : models) m->fuse(tick, cfg.depthCutoff, weightMultiplier);
-            for (auto& m : models) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
-            for (auto& m : models) m->clean(tick, cfg.timeDelta, cfg.maxDepthProcessed);
+            for (auto& m : models) if (m->owned) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
+            for (auto& m : models) if (m->owned) m->fuse(tick, cfg.depthCutoff, weightMultiplier);
+            for (auto& m : models) if (m->owned) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
+            for (auto& m : models) if (m->owned) m->clean(tick, cfg.timeDelta, cfg.maxDepthProcessed);
         }
     }
     predict();          // MaskFusion.cpp:569 (the call at :423 is dead in open-loop mode: its outputs are overwritten here)
@@ -599,11 +691,10 @@ bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_
         Mat4 T = (i == 0) ? g->pose : mul(g->pose, rigidInverse(m->pose));     // MaskFusion.cpp:581-583
         float R[9] = {T.m[0], T.m[1], T.m[2], T.m[4], T.m[5], T.m[6], T.m[8], T.m[9], T.m[10]}, q[4];
         rotToQuat(R, q);
-        double e[8] = {(double)timestamp, T.m[3], T.m[7], T.m[11], q[0], q[1], q[2], q[3]};
+        double e[8] = {(double)fTimestamp, T.m[3], T.m[7], T.m[11], q[0], q[1], q[2], q[3]};
         m->poseLog.insert(m->poseLog.end(), e, e + 8);
         m->age++;
     }
-    return false;
 }
 
 }  // namespace mfb

@@ -51,7 +51,8 @@ class MaskFusion;
 
 class Model {
 public:
-    Model(MaskFusion* owner, unsigned char id, float confidenceThresh, bool enableFillIn, int capacity);
+    // ghost = replica of a model whose surfel store lives on another rank: pose, ids and age only, no device buffers
+    Model(MaskFusion* owner, unsigned char id, float confidenceThresh, bool enableFillIn, int capacity, int ownerRank = 0, bool ghost = false);
     ~Model();
     Model(const Model&) = delete;
 
@@ -73,6 +74,7 @@ public:
     uint32_t* dCount() const { return count.p + countSel; }
 
     MaskFusion* owner;
+    int ownerRank = 0; bool owned = true;                             // sharded mode: which rank holds the surfels
     unsigned char id; int classID = -1;
     Mat4 pose, lastPose, initialC2Winv;
     bool isStatic = false, nonstatic = false; unsigned age = 0;
@@ -122,6 +124,19 @@ public:
     unsigned char getNextModelID(bool assign);                                                    // MaskFusion::getNextModelID
     Model* spawnObjectModel();                                                                    // MaskFusion::spawnObjectModel + moveNewModelToList
     void setFrameClasses(const int32_t* ids, int n) { classIDs.assign(ids, ids + n); }            // FrameData::classIDs
+
+    // ---- object-sharded mode: processFrame == frameBegin; [pose all-gather]; frameProject; [u64 min all-reduce of the
+    // projection keys]; frameEnd.  The collectives run in the host layer above the C ABI (torch.distributed), on this stream.
+    void configureShard(int rank, int world);
+    void frameBegin(const uint8_t* rgb, const float* depth, int64_t timestamp, const uint8_t* mask, const Mat4* inPose, bool bootstrap, bool onDevice);
+    void getShardPoses(float* out) const;                       // [nModels][32]: pose, lastTransform (row-major); rows of ghosts are zero
+    void setShardPoses(const float* gathered);                  // [world][nModels][32]: every model takes its owner's row
+    void frameProject();                                        // lifecycle after tracking + local part of the global ID projection
+    void frameEnd(float weightMultiplier);
+    void projectLocal(); void projectResolve();                 // the two halves of globalProjection()
+    static int pickOwner(const int64_t* loads, int world);      // least-loaded rank (by owned surfel capacity), ties -> highest rank
+    int rank = 0, world = 1;
+    int64_t fTimestamp = 0; Mat4 fInPose; bool fHasPose = false, fBootstrap = false;
 
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;

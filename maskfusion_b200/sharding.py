@@ -1,0 +1,195 @@
+"""Object-sharded MaskFusion: one process per GPU, object Models partitioned over the ranks.
+
+Per frame the ranks exchange exactly what couples the models in the reference:
+
+  frame in          rgb + depth + instance mask + class ids, broadcast from the loader rank     (MaskFusion.cpp:212-217)
+  poses             every tracked model's pose / last transform, all-gather                      (MaskFusion.cpp:257-276)
+  ID projection     64-bit (depth bits << 32 | model index << 26 | surfel) keys, all-reduce MIN  (GlobalProjection.cpp:66-95)
+
+Everything after the merged key image (segmentation, mask<->model voting, spawn decision, inactivation) is a
+deterministic function of replicated inputs and is evaluated on every rank; the surfel passes (index map,
+association, fusion, clean, splat) run only on the rank that holds the model's store.  The compute lives behind
+the C ABI (mf_shard_*); this file is the torch.distributed plumbing (NCCL over NVLink on the GPU box; the same
+code path runs over gloo with host staging, which is how it is tested on one GPU or none).
+
+The helpers at module level are device-agnostic and are what tests/test_cpu_sharding.py exercises over gloo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import api
+
+_SIGN = -(2 ** 63)
+MAX_MODELS = 64
+MAX_CLASSES = 256
+
+
+# ------------------------------------------------------------------------------------------------------------
+# device-agnostic plumbing (torch tensors, any backend)
+# ------------------------------------------------------------------------------------------------------------
+def frame_packet_bytes(W: int, H: int) -> int:
+    """rgb (3P) | depth f32 (4P) | mask u8 (P) | header int64[2] = (timestamp, nClasses) | classIDs int32[256]"""
+    P = W * H
+    return 8 * P + 16 + 4 * MAX_CLASSES
+
+
+def pack_frame(buf, W, H, rgb, depth, mask, timestamp, classIDs):
+    """loader rank: fill the broadcast packet (a uint8 torch tensor of frame_packet_bytes) from numpy inputs"""
+    import torch
+    P = W * H
+    n = 0 if classIDs is None else len(classIDs)
+    if n > MAX_CLASSES:
+        raise api.MFError("more than 256 mask labels")
+    host = np.zeros(frame_packet_bytes(W, H), np.uint8)
+    host[0:3 * P] = np.ascontiguousarray(rgb, np.uint8).reshape(-1)
+    host[3 * P:7 * P] = np.ascontiguousarray(depth, np.float32).reshape(-1).view(np.uint8)
+    if mask is not None:
+        host[7 * P:8 * P] = np.ascontiguousarray(mask, np.uint8).reshape(-1)
+    host[8 * P:8 * P + 16] = np.array([int(timestamp), n if mask is not None else -1], np.int64).view(np.uint8)
+    if n:
+        host[8 * P + 16:8 * P + 16 + 4 * n] = np.ascontiguousarray(classIDs, np.int32).view(np.uint8)
+    buf.copy_(torch.from_numpy(host), non_blocking=False)
+
+
+def unpack_header(buf, W, H):
+    """-> (timestamp, classIDs or None); one small device->host read"""
+    P = W * H
+    tail = buf[8 * P:].cpu().numpy()
+    ts, n = (int(v) for v in tail[:16].view(np.int64))
+    if n < 0:
+        return ts, None
+    return ts, tail[16:16 + 4 * n].view(np.int32).copy()
+
+
+def allreduce_min_u64(keys_i64, group=None):
+    """unsigned 64-bit MIN all-reduce of a tensor that holds uint64 bit patterns in int64 storage.
+    Flipping the top bit maps unsigned order onto signed order (the empty key 0xFFFF.. must stay the maximum)."""
+    import torch
+    import torch.distributed as dist
+    sign = torch.tensor(_SIGN, dtype=torch.int64, device=keys_i64.device)
+    keys_i64.bitwise_xor_(sign)
+    dist.all_reduce(keys_i64, op=dist.ReduceOp.MIN, group=group)
+    keys_i64.bitwise_xor_(sign)
+    return keys_i64
+
+
+def gather_rows(local_rows, group=None):
+    """all-gather of a [nModels, 32] float32 table -> [world, nModels, 32] (bit-exact: no arithmetic on the payload)"""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    flat = local_rows.contiguous().view(-1)
+    out = torch.empty(world * flat.numel(), dtype=flat.dtype, device=flat.device)
+    dist.all_gather_into_tensor(out, flat, group=group)
+    return out.view((world,) + tuple(local_rows.shape))
+
+
+def pick_owner(loads) -> int:
+    """placement of a new model (host rule shared with the library: mf_shard_pick_owner)"""
+    a = np.ascontiguousarray(loads, np.int64)
+    r = api.load_library().mf_shard_pick_owner(a.ctypes.data_as(C.c_void_p), int(a.shape[0]))
+    if r < 0:
+        raise api.MFError("pick_owner: bad arguments")
+    return r
+
+
+class _DevPtr:
+    """expose a raw device pointer to torch through __cuda_array_interface__"""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ShardedMaskFusion:
+    """MaskFusion with the object Models sharded over the ranks of a torch.distributed group.
+
+    Every rank constructs it with the same config and calls processFrame every frame; only `src` needs real
+    inputs.  Poses, ids, classes and pose logs of ALL models are available on every rank; surfel read-backs only
+    on the owner (`owner(i)`)."""
+
+    def __init__(self, cfg: api.Config, device: int = 0, group=None, src: int = 0):
+        import torch
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise api.MFError("ShardedMaskFusion needs an initialised torch.distributed process group")
+        self.torch, self.dist, self.group, self.src = torch, dist, group, src
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.on_nccl = dist.get_backend(group) == "nccl"
+        self.dev = torch.device("cuda", device)
+        torch.cuda.set_device(self.dev)
+        self.stream = torch.cuda.current_stream(self.dev)
+        self.mf = api.MaskFusion(cfg, device=device, stream=self.stream.cuda_stream)
+        self.L, self.h = self.mf.L, self.mf.h
+        self.W, self.H = cfg.width, cfg.height
+        self.P = self.W * self.H
+        self.mf._ck(self.L.mf_shard_configure(self.h, self.rank, self.world))
+        self.packet = torch.zeros(frame_packet_bytes(self.W, self.H), dtype=torch.uint8, device=self.dev)
+        self.packet_host = None if self.on_nccl else torch.zeros(frame_packet_bytes(self.W, self.H), dtype=torch.uint8).pin_memory()
+        self.keys = None
+        self.rows = np.zeros((MAX_MODELS, 32), np.float32)
+        self.bytes_collective = 0
+
+    # -- collectives: on the device over NCCL, staged through the host for any other backend --
+    def _broadcast_packet(self):
+        if self.on_nccl:
+            self.dist.broadcast(self.packet, src=self.src, group=self.group)
+        else:
+            self.packet_host.copy_(self.packet)
+            self.dist.broadcast(self.packet_host, src=self.src, group=self.group)
+            self.packet.copy_(self.packet_host)
+        self.bytes_collective += self.packet.numel()
+
+    def _exchange_poses(self, n):
+        t = self.torch.from_numpy(self.rows[:n])
+        if self.on_nccl:
+            g = gather_rows(t.to(self.dev), self.group).cpu()
+        else:
+            g = gather_rows(t, self.group)
+        self.bytes_collective += g.numel() * 4
+        return np.ascontiguousarray(g.numpy())
+
+    def _merge_keys(self):
+        if self.keys is None:
+            ptr = self.L.mf_shard_projection_keys(self.h)
+            self.keys = self.torch.as_tensor(_DevPtr(ptr, self.P, "<i8"), device=self.dev)
+        if self.on_nccl:
+            allreduce_min_u64(self.keys, self.group)
+        else:
+            k = self.keys.cpu()
+            allreduce_min_u64(k, self.group)
+            self.keys.copy_(k)
+        self.bytes_collective += self.P * 8
+
+    # -- one frame --
+    def processFrame(self, rgb=None, depth=None, timestamp: int = 0, mask=None, classIDs=None, weightMultiplier: float = 1.0):
+        ck, L, h, P = self.mf._ck, self.L, self.h, self.P
+        if self.rank == self.src:
+            pack_frame(self.packet, self.W, self.H, rgb, depth, mask, timestamp, classIDs)
+        self._broadcast_packet()
+        ts, classes = unpack_header(self.packet, self.W, self.H)
+        base = self.packet.data_ptr()
+        if classes is not None:
+            ck(L.mf_set_frame_classes(h, classes.ctypes.data_as(C.c_void_p), int(classes.shape[0])))
+        ck(L.mf_shard_frame_begin(h, C.c_void_p(base), C.c_void_p(base + 3 * P), ts, C.c_void_p(base + 7 * P) if classes is not None else None, 1))
+        n = ck(L.mf_shard_get_poses(h, self.rows.ctypes.data_as(C.c_void_p), MAX_MODELS))
+        gathered = self._exchange_poses(n)
+        ck(L.mf_shard_set_poses(h, gathered.ctypes.data_as(C.c_void_p)))
+        ck(L.mf_shard_project(h))
+        if self.mf.cfg.enableMultipleModels and self.mf.getTick() > 1:
+            self._merge_keys()
+        ck(L.mf_shard_frame_end(h, float(weightMultiplier)))
+        return False
+
+    # -- replicated queries --
+    def owner(self, i: int) -> int:
+        return self.mf._ck(self.L.mf_model_owner(self.h, i))
+
+    def models(self):
+        return self.mf.getModels()
+
+    def close(self):
+        self.mf.close()

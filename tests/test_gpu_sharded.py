@@ -1,0 +1,57 @@
+"""Object-sharded pipeline against the single-process pipeline on the same replay: the shards must
+reproduce it BIT FOR BIT (same kernels on the same inputs; the only cross-rank arithmetic is an integer MIN).
+Two ranks: NCCL with one GPU each when the box has two GPUs, else gloo with both ranks on cuda:0 (host-staged
+collectives, same C-ABI phases) -- so the round-end single-GPU run covers the sharded code path as well."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from tests.test_cpu_sharding import launch
+
+pytestmark = pytest.mark.gpu
+W, H = 640, 480
+
+
+def single(nframes, track_all):
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene
+    kw = dict(capacityGlobal=1000000, capacityObject=200000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all))
+    sc = SynthScene(W, H, n_objects=3, seed=0)
+    mf = mfb.MaskFusion(mfb.default_config(W, H, **kw))
+    cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
+    out = {}
+    for t in range(nframes):
+        rgb, depth, mask, *_ = sc.render(t)
+        mf.processFrame(rgb, depth, t * 33333, mask=np.ascontiguousarray(mask), classIDs=cls)
+        models = mf.getModels()
+        seg, proj = mf.segmentation()
+        out[f"ids{t}"] = np.array([m.getID() for m in models]); out[f"cls{t}"] = np.array([m.getClassID() for m in models])
+        out[f"pose{t}"] = np.stack([m.getPose() for m in models]); out[f"cnt{t}"] = np.array([m.lastCount() for m in models])
+        out[f"seg{t}"] = np.packbits(seg == 0); out[f"segsum{t}"] = np.array([int(seg.astype(np.int64).sum()), int(proj.astype(np.int64).sum())])
+    for i, m in enumerate(mf.getModels()):
+        out[f"map{i}"] = m.downloadMap()
+    mf.close()
+    return out
+
+
+@pytest.mark.parametrize("track_all", [0, 1])
+def test_two_shards_equal_one_process(tmp_path, track_all):
+    nframes = 30
+    ref = single(nframes, track_all)
+    launch(2, ["gpu", tmp_path, nframes, track_all], timeout=900)
+    ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(2)]
+    nmodels_final = len(ref[f"ids{nframes - 1}"])
+    assert nmodels_final >= 3, "no object model was spawned: the test would not exercise sharding"
+    owners = ranks[0][f"own{nframes - 1}"]
+    assert owners[0] == 0 and set(owners.tolist()) == {0, 1}, owners              # both ranks hold stores
+    for t in range(nframes):
+        for z in ranks:                                                           # replicated state is identical on every rank and equal to the single run
+            for k in ("ids", "cls", "pose", "seg", "segsum"):
+                assert np.array_equal(z[f"{k}{t}"], ref[f"{k}{t}"]), (t, k)
+        assert np.array_equal(ranks[0][f"own{t}"], ranks[1][f"own{t}"])
+        cnt = np.where(ranks[0][f"cnt{t}"] >= 0, ranks[0][f"cnt{t}"], ranks[1][f"cnt{t}"])
+        assert np.array_equal(cnt, ref[f"cnt{t}"]), (t, cnt, ref[f"cnt{t}"])
+    for i in range(nmodels_final):                                                # the surfel stores themselves
+        m = ranks[int(owners[i])][f"map{i}"]
+        assert m.shape == ref[f"map{i}"].shape and np.array_equal(m.view(np.uint32), ref[f"map{i}"].view(np.uint32)), i
