@@ -140,8 +140,7 @@ def algorithmic_bytes(name, S, P):
         "k_splat_resolve": 8 * P + 38 * P + 36 * P,
         "k_associate": 13 * P + 93 * P,
         "k_bilateral": 8 * P,
-        "k_gn_step_L0": 48 * P, "k_gn_step_L1": 48 * P // 4, "k_gn_step_L2": 48 * P // 16,
-        "k_rgb_residual": 30 * P,
+        "k_track_persistent": (552 + 713) * P,       # ICP 48 B x P_l and photometric 62 B x P_l per iteration over the 10/5/4 schedule
     }
     return table.get(name)
 

@@ -147,7 +147,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     }
     lastNextImage2.alloc((size_t)(W >> 2) * (H >> 2)); lastNextImage2.zero(s);
     trackState.alloc(1); trackState.zero(s);
-    partial.alloc((size_t)TRACK_MAX_BLOCKS * 64); partialI.alloc((size_t)TRACK_MAX_BLOCKS * 2);
+    partial.alloc((size_t)TRACK_MAX_BLOCKS * 64);
     o->launches += 2;
 }
 
@@ -275,7 +275,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
         vmap[l].alloc(Pl); nmap[l].alloc(Pl); nextImage[l].alloc(Pl); nextGrad[l].alloc(Pl); rgbValid[l].alloc(Pl);
     }
     edgeMap.alloc(P); edgeBinary.alloc(P); edgeBuf.alloc(P); edgeInv.alloc(P);
-    dJobs.alloc(TRACK_MAX_JOBS);
+    dJobs.alloc(TRACK_MAX_JOBS); trackBars.alloc(TRACK_MAX_JOBS * 32);
     cudaCheck(cudaMallocHost((void**)&hJobs, TRACK_MAX_JOBS * sizeof(TrackJob)), "cudaMallocHost");
     initFlagR.alloc(P); initFlagF.alloc(P);
     scratch.alloc((size_t)P * 4);
@@ -364,16 +364,13 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
             J.vmapG[l] = m->vmapG[l]; J.nmapG[l] = m->nmapG[l]; J.lastDepth[l] = m->lastDepth[l]; J.lastImage[l] = m->lastImage[l];
             J.cloud[l] = m->cloud[l]; J.corres[l] = m->corres[l];
         }
-        J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.partialI = m->partialI;
+        J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.bar = trackBars.p + j * 32;
         memcpy(poses.p[j], m->pose.m, 16 * sizeof(float));
     }
     prof_mark(stream, "copy_jobs");
     cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
-    const uint8_t* fi[3] = {nextImage[0].p, nextImage[1].p, nextImage[2].p};
-    const short2* fg[3] = {nextGrad[0].p, nextGrad[1].p, nextGrad[2].p};
-    uint8_t* rv[3] = {rgbValid[0].p, rgbValid[1].p, rgbValid[2].p};
     launches += launch_tracking(dJobs, (int)ms.size(), poses, W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
-                                cfg.so3 != 0, numSMs, stream, fi, fg, rv);
+                                cfg.so3 != 0, numSMs, trackBars, stream);
     prof_mark(stream, "copy_pose_d2h");
     for (Model* m : ms) {
         cudaCheck(cudaMemcpyAsync(m->hTrackOut, (const char*)m->trackState.p + offsetof(TrackState, out), 40 * sizeof(float),

@@ -98,7 +98,7 @@ public:
     DevBuf<float4> vmapG[3], nmapG[3], cloud[3];
     DevBuf<float> lastDepth[3]; DevBuf<uint8_t> lastImage[3]; DevBuf<uint8_t> lastNextImage2;
     DevBuf<DataTerm> corres[3];
-    DevBuf<TrackState> trackState; DevBuf<float> partial; DevBuf<int> partialI;
+    DevBuf<TrackState> trackState; DevBuf<float> partial;
     float* hTrackOut = nullptr;             // pinned: pose(16) transform(16) stats(8)
     Mat4 lastTransform;
     std::vector<double> poseLog;            // 8 doubles per entry
@@ -149,7 +149,7 @@ public:
     DevBuf<float> depthPyr[3]; DevBuf<float4> vmap[3], nmap[3];
     DevBuf<uint8_t> nextImage[3]; DevBuf<short2> nextGrad[3]; DevBuf<uint8_t> rgbValid[3];
     DevBuf<float> edgeMap; DevBuf<uint8_t> edgeBinary, edgeBuf, edgeInv;
-    DevBuf<TrackJob> dJobs; TrackJob* hJobs = nullptr;
+    DevBuf<TrackJob> dJobs; TrackJob* hJobs = nullptr; DevBuf<unsigned> trackBars;
     DevBuf<uint8_t> initFlagR, initFlagF;
     DevBuf<float> scratch;                  // read-back staging
     bool frameMapsValid = false, intensityValid = false;

@@ -35,15 +35,15 @@ struct TrackState {
 
 struct TrackJob {
     const float4* vmapC[3]; const float4* nmapC[3];        // frame maps (shared by all models)
-    const uint8_t* nextImage[3]; const short2* nextGrad[3]; const uint8_t* rgbValid[3];
+    const uint8_t* nextImage[3]; const short2* nextGrad[3]; uint8_t* rgbValid[3];
     const float4* vmapG[3]; const float4* nmapG[3];        // model maps in the model-global frame
     const float* lastDepth[3]; const uint8_t* lastImage[3];
     const uint8_t* lastNextImage2;
     const float4* cloud[3];
     DataTerm* corres[3];
     TrackState* st;
-    float* partial;       // TRACK_MAX_BLOCKS x 64 floats
-    int* partialI;        // TRACK_MAX_BLOCKS x 2 ints
+    float* partial;       // 2 x (TRACK_MAX_BLOCKS / 2) rows of 64 floats: per-CTA partial sums, ping-pong between reductions
+    unsigned* bar;        // grid barrier counter of this job (own 128-byte line)
 };
 
 void set_num_sms(int n);
@@ -90,8 +90,7 @@ void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, 
 
 // ---- mf_track.cu ----
 int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
-                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s, const uint8_t* const* frameImage,
-                    const short2* const* frameGrad, uint8_t* const* rgbValid);
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s);
 void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,
                      const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s);
 

@@ -305,20 +305,27 @@ MF_D bool cleanFinish(float4& vp, float4& vc, float x, float y, float lpz, int c
 #define SCAN_BLOCK 512
 // clean, pass 1a: stream the whole store once (old surfels, then the new vertices emitted by the association pass).
 // A vertex that does not project into the image needs no index-map window: it is finished here.  The others are
-// only REGISTERED in a device-wide candidate list (warp-aggregated atomic append); pass 1b works that list densely.
+// only REGISTERED in a device-wide candidate list; pass 1b works that list densely.
 // (An in-kernel window ran with 9/32 lanes active; a block-compacted variant was still latency bound at 2 blocks/SM.)
+#define CAND_BUF 2048
 __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, float4* __restrict__ col, const uint32_t* __restrict__ countPtr,
                                                   const uint8_t* __restrict__ aflag, float4* __restrict__ m0, float4* __restrict__ m1, int Ppix,
                                                   CleanParams P, const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
                                                   uint8_t* __restrict__ keep, uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount)
 {
+    // candidates are staged per block in shared memory and flushed in chunks: one device-wide atomic per ~2k candidates
+    // (a warp-aggregated global append put ~130k returning atomics on ONE L2 address: 62 % busy slice, ncu r01b)
+    __shared__ uint32_t sBuf[CAND_BUF];
+    __shared__ uint32_t sCount, sBase;
     const uint32_t count = *countPtr;
     const uint32_t total = count + (uint32_t)Ppix;
     const float cols = (float)P.W, rows = (float)P.H, ftime = (float)P.time;
     const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < total; base += stride) {
-        const uint32_t e = base + lane;
+    if (threadIdx.x == 0) sCount = 0;
+    __syncthreads();
+    uint32_t staged = 0;                                                 // block-uniform copy of sCount
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const uint32_t e = base + threadIdx.x;
         bool valid = false, need = false;
         const bool isOld = e < count;
         float4 vp = make_float4(0, 0, 0, 0), vc = vp;
@@ -340,10 +347,23 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
         unsigned nb = __ballot_sync(0xffffffffu, need);
         if (nb) {
             uint32_t wbase = 0;
-            if (lane == 0) wbase = atomicAdd(candCount, (uint32_t)__popc(nb));
+            if (lane == 0) wbase = atomicAdd(&sCount, (uint32_t)__popc(nb));
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (need) cand[wbase + __popc(nb & ((1u << lane) - 1))] = e;
+            if (need) sBuf[wbase + __popc(nb & ((1u << lane) - 1))] = e;
         }
+        staged += (uint32_t)__syncthreads_count(need);
+        if (staged > CAND_BUF - 256) {                                   // uniform: the next iteration might not fit
+            if (threadIdx.x == 0) { sBase = atomicAdd(candCount, staged); sCount = 0; }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < staged; i += blockDim.x) cand[sBase + i] = sBuf[i];
+            staged = 0;
+            __syncthreads();
+        }
+    }
+    if (staged) {
+        if (threadIdx.x == 0) sBase = atomicAdd(candCount, staged);
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < staged; i += blockDim.x) cand[sBase + i] = sBuf[i];
     }
 }
 

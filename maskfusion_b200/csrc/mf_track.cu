@@ -15,7 +15,9 @@
 // on one GPU share every launch.  Results are deterministic for a fixed launch shape.
 #include "mf_common.cuh"
 #include "mf_kernels.h"
+#include "mf_host.h"
 #include <float.h>
+#include <string>
 
 namespace mfb {
 
@@ -232,407 +234,6 @@ MF_D bool lastBlock(unsigned* ticket)
     return isLast;
 }
 
-// ---------------------------------------------------------------------------------------
-// begin / end
-// ---------------------------------------------------------------------------------------
-__global__ void k_track_begin(TrackJob* jobs, TrackPoses poses, int useSo3)
-{
-    int jb = blockIdx.x;
-    if (threadIdx.x != 0) return;
-    TrackState* st = jobs[jb].st;
-    const float* P = poses.p[jb];
-    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) st->Rprev[r * 3 + c] = P[r * 4 + c]; st->tprev[r] = P[r * 4 + 3]; }
-    for (int k = 0; k < 9; ++k) st->Rcurr[k] = st->Rprev[k];
-    for (int k = 0; k < 3; ++k) st->tcurr[k] = st->tprev[k];
-    inv3f(st->Rprev, st->RprevInv);
-    for (int k = 0; k < 16; ++k) st->resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
-    for (int k = 0; k < 9; ++k) { st->resultR[k] = (k % 4 == 0) ? 1.0 : 0.0; st->lastResultR[k] = st->resultR[k]; st->R_lr[k] = (k % 4 == 0) ? 1.f : 0.f; st->trR[k] = (k % 4 == 0) ? 1.f : 0.f; }
-    st->trT[0] = st->trT[1] = st->trT[2] = 0;
-    st->so3LastError = FLT_MAX / 2; st->so3LastCount = FLT_MAX / 2; st->so3Done = useSo3 ? 0 : 1;
-    st->levelBreak = 0; st->lastRGBError = FLT_MAX;
-    for (int k = 0; k < 4; ++k) st->ticket[k] = 0;
-}
-
-// so3 result -> initial resultRt (RGBDOdometry.cpp:337-345)
-__global__ void k_track_so3_finish(TrackJob* jobs, int useSo3)
-{
-    if (threadIdx.x != 0) return;
-    TrackState* st = jobs[blockIdx.x].st;
-    if (useSo3) for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) st->resultRt[r * 4 + c] = st->resultR[r * 3 + c];
-}
-
-__global__ void k_track_level_begin(TrackJob* jobs, int level, Cam camL, int rgb)
-{
-    if (threadIdx.x != 0) return;
-    TrackState* st = jobs[blockIdx.x].st;
-    st->levelBreak = 0; st->lastRGBError = FLT_MAX;
-    if (rgb) computeWarp(st, camL);
-}
-
-__global__ void k_track_end(TrackJob* jobs, int rgb)
-{
-    if (threadIdx.x != 0) return;
-    TrackState* st = jobs[blockIdx.x].st;
-    float dx = st->tcurr[0] - st->tprev[0], dy = st->tcurr[1] - st->tprev[1], dz = st->tcurr[2] - st->tprev[2];
-    if (rgb && sqrtf((dx * dx + dy * dy) + dz * dz) > 0.3f) {          // RGBDOdometry.cpp:478-482
-        for (int k = 0; k < 9; ++k) { st->Rcurr[k] = st->Rprev[k]; st->trR[k] = (k % 4 == 0) ? 1.f : 0.f; }
-        for (int k = 0; k < 3; ++k) { st->tcurr[k] = st->tprev[k]; st->trT[k] = 0; }
-    }
-    float* po = st->out;                 // [0..15] pose, [16..31] transform, [32..37] error stats
-    for (int k = 0; k < 32; ++k) po[k] = ((k % 16) % 5 == 0) ? 1.f : 0.f;
-    for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) { po[r * 4 + c] = st->Rcurr[r * 3 + c]; po[16 + r * 4 + c] = st->trR[r * 3 + c]; }
-        po[r * 4 + 3] = st->tcurr[r]; po[16 + r * 4 + 3] = st->trT[r];
-    }
-    po[32] = st->lastICPError; po[33] = st->lastICPCount; po[34] = st->lastRGBError; po[35] = st->lastRGBCount;
-    po[36] = st->lastSO3Error; po[37] = st->lastSO3Count;
-}
-
-// ---------------------------------------------------------------------------------------
-// SO(3) pre-alignment step (level 2 intensities)
-// ---------------------------------------------------------------------------------------
-MF_D void gradU8(const uint8_t* __restrict__ img, int W, int x, int y, float& gx, float& gy)
-{
-    float actu = img[y * W + x], back = img[y * W + x - 1], fore = img[y * W + x + 1];
-    gx = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
-    back = img[(y - 1) * W + x]; fore = img[(y + 1) * W + x];
-    gy = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
-}
-
-__global__ void __launch_bounds__(TRK_THREADS) k_so3_step(TrackJob* jobs, int W, int H, Cam c)
-{
-    TrackJob& J = jobs[blockIdx.y];
-    TrackState* st = J.st;
-    if (st->so3Done) return;
-    __shared__ float B[9], kinv[9], krlr[9];
-    if (threadIdx.x == 0) {
-        double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1}, Kinv[9], kr[9], hom[9];
-        inv3d(K, Kinv); mul3d(K, st->resultR, kr); mul3d(kr, Kinv, hom);
-        for (int q = 0; q < 9; ++q) { B[q] = (float)hom[q]; kinv[q] = (float)Kinv[q]; krlr[q] = (float)kr[q]; }
-    }
-    __syncthreads();
-    const uint8_t* __restrict__ lastImage = J.lastNextImage2;
-    const uint8_t* __restrict__ nextImage = J.nextImage[2];
-    float acc[11];
-#pragma unroll
-    for (int k = 0; k < 11; ++k) acc[k] = 0;
-    const int N = W * H;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
-        int y = k / W, x = k - y * W;
-        float3 ur = make_float3((float)x, (float)y, 1.0f);
-        float3 wr = m3v(B, ur);
-        int wx = __float2int_rn(wr.x / wr.z), wy = __float2int_rn(wr.y / wr.z);
-        bool found = (wx >= 1 && wx < W - 1 && wy >= 1 && wy < H - 1 && x >= 1 && x < W - 1 && y >= 1 && y < H - 1);
-        if (found) {
-            float gnx, gny, glx, gly;
-            gradU8(nextImage, W, wx, wy, gnx, gny);
-            gradU8(lastImage, W, x, y, glx, gly);
-            float gx = (gnx + glx) / 2.0f, gy = (gny + gly) / 2.0f;
-            float3 p = m3v(kinv, ur);
-            float z2 = p.z * p.z;
-            float a = krlr[0], b = krlr[1], cc = krlr[2], d = krlr[3], e = krlr[4], f = krlr[5], g = krlr[6], h = krlr[7], i = krlr[8];
-            float fy = (float)y, fxx = (float)x;
-            float3 l = make_float3(((p.z * (d * gy + a * gx)) - (gy * g * fy) - (gx * g * fxx)) / z2,
-                                   ((p.z * (e * gy + b * gx)) - (gy * h * fy) - (gx * h * fxx)) / z2,
-                                   ((p.z * (f * gy + cc * gx)) - (gy * i * fy) - (gx * i * fxx)) / z2);
-            float row[4];
-            row[0] = l.y * p.z - l.z * p.y;
-            row[1] = l.z * p.x - l.x * p.z;
-            row[2] = l.x * p.y - l.y * p.x;
-            row[3] = -((float)nextImage[wy * W + wx] - (float)lastImage[k]);
-            int q = 0;
-#pragma unroll
-            for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-                for (int jj = ii; jj < 4; ++jj) acc[q++] += row[ii] * row[jj];
-            acc[9] += row[3] * row[3];
-            acc[10] += 1.0f;
-        }
-    }
-    float* partial = J.partial + (size_t)blockIdx.x * 64;
-    blockReduceStore<11>(acc, partial);
-    if (!lastBlock(&st->ticket[0])) return;
-    __shared__ double tot[11];
-    sumPartials<11>(J.partial, gridDim.x, tot);
-    if (threadIdx.x != 0) return;
-    // host logic of RGBDOdometry.cpp:301-324
-    float res0 = (float)tot[9], res1 = (float)tot[10];
-    st->lastSO3Error = sqrtf(res0) / res1; st->lastSO3Count = res1;
-    if (st->lastSO3Error < st->so3LastError && fabsf(st->so3LastError - st->lastSO3Count) < 0.001f) { st->so3Done = 1; return; }
-    else if (st->lastSO3Error > st->so3LastError + 0.001f) {
-        st->lastSO3Error = st->so3LastError; st->lastSO3Count = st->so3LastCount;
-        for (int q = 0; q < 9; ++q) st->resultR[q] = st->lastResultR[q];
-        st->so3Done = 1; return;
-    }
-    st->so3LastError = st->lastSO3Error; st->so3LastCount = st->lastSO3Count;
-    for (int q = 0; q < 9; ++q) st->lastResultR[q] = st->resultR[q];
-    double A[9], bb[3], delta[3]; int q = 0;
-    for (int ii = 0; ii < 3; ++ii) for (int jj = ii; jj < 4; ++jj) { double v = (double)(float)tot[q++]; if (jj == 3) bb[ii] = v; else A[jj * 3 + ii] = A[ii * 3 + jj] = v; }
-    ldltSolve(A, bb, 3, delta);
-    for (int k = 0; k < 3; ++k) delta[k] = (double)(float)delta[k];
-    double ru[9]; rodrigues(delta, ru);
-    float ruf[9], n[9];
-    for (int k = 0; k < 9; ++k) ruf[k] = (float)ru[k];
-    for (int r = 0; r < 3; ++r) for (int cc2 = 0; cc2 < 3; ++cc2) n[r * 3 + cc2] = (ruf[r * 3] * st->R_lr[cc2] + ruf[r * 3 + 1] * st->R_lr[3 + cc2]) + ruf[r * 3 + 2] * st->R_lr[6 + cc2];
-    for (int k = 0; k < 9; ++k) { st->R_lr[k] = n[k]; st->resultR[k] = n[k]; }
-}
-
-// ---------------------------------------------------------------------------------------
-// photometric correspondences + residual statistics
-// ---------------------------------------------------------------------------------------
-// pose-independent part of residualKernel (reduce.cu:821-845): 4x4 window of non-zero intensities + gradient-magnitude gate.
-// Evaluated once per level per frame instead of once per Gauss-Newton iteration (16 byte loads per pixel per iteration saved).
-__global__ void k_rgb_valid(const uint8_t* __restrict__ nextImage, const short2* __restrict__ grad, int W, int H, float minScale, uint8_t* __restrict__ out)
-{
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= W * H) return;
-    int i = k / W, j0 = k - i * W;
-    bool valid = false;
-    if (j0 < W - 5 && i < H - 1) {
-        valid = true;
-        for (int u = max(i - 2, 0); u < min(i + 2, H); ++u)
-            for (int v = max(j0 - 2, 0); v < min(j0 + 2, W); ++v) valid = valid && (nextImage[u * W + v] > 0);
-        if (valid) {
-            short2 g = grad[k];
-            float mTwo = (float)(((int)g.x * (int)g.x) + ((int)g.y * (int)g.y));
-            valid = mTwo >= minScale;
-        }
-    }
-    out[k] = valid ? 1 : 0;
-}
-
-__global__ void __launch_bounds__(TRK_THREADS) k_rgb_residual(TrackJob* jobs, int level, int W, int H, float minScale, float maxDepthDelta, int rgbOnly)
-{
-    TrackJob& J = jobs[blockIdx.y];
-    TrackState* st = J.st;
-    if (st->levelBreak) return;
-    const uint8_t* __restrict__ rgbValid = J.rgbValid[level];
-    const float* __restrict__ lastDepth = J.lastDepth[level];
-    const float* __restrict__ nextDepth = J.lastDepth[level];      // reference quirk: both pyramids derive from vmaps_tmp (RGBDOdometry.cpp:187-215)
-    const uint8_t* __restrict__ lastImage = J.lastImage[level];
-    const uint8_t* __restrict__ nextImage = J.nextImage[level];
-    DataTerm* __restrict__ corres = J.corres[level];
-    __shared__ float K[9], kt[3];
-    if (threadIdx.x < 9) K[threadIdx.x] = st->krk[threadIdx.x];
-    if (threadIdx.x < 3) kt[threadIdx.x] = st->kt[threadIdx.x];
-    __syncthreads();
-    int cnt = 0, sig = 0;
-    const int N = W * H;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) {
-        int i = k / W, j0 = k - i * W;
-        DataTerm c; c.zero = make_short2(0, 0); c.one = make_short2(0, 0); c.diff = 0; c.valid = 0;
-        {
-            {
-                if (rgbValid[k]) {
-                    int y = i, x = j0;
-                    float d1 = nextDepth[k];
-                    if (!isnan(d1)) {
-                        float td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
-                        float fu = (d1 * ((K[0] * x + K[1] * y) + K[2]) + kt[0]) / td1;
-                        float fv = (d1 * ((K[3] * x + K[4] * y) + K[5]) + kt[1]) / td1;
-                        int u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
-                        int v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
-                        if (u0 >= 0 && v0 >= 0 && u0 < W && v0 < H) {
-                            float d0 = lastDepth[v0 * W + u0];
-                            uint8_t li = lastImage[v0 * W + u0];
-                            if (d0 > 0 && fabsf(td1 - d0) <= maxDepthDelta && li != 0) {
-                                c.zero = make_short2((short)u0, (short)v0); c.one = make_short2((short)x, (short)y);
-                                c.diff = (float)nextImage[k] - (float)li;
-                                c.valid = 1;
-                                cnt += 1;
-                                sig += (int)(c.diff * c.diff);
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        corres[k] = c;
-    }
-    // int2 block reduction
-    __shared__ int shc[TRK_THREADS / 32], shs[TRK_THREADS / 32];
-    for (int off = 16; off > 0; off >>= 1) { cnt += __shfl_down_sync(0xffffffffu, cnt, off); sig += __shfl_down_sync(0xffffffffu, sig, off); }
-    if ((threadIdx.x & 31) == 0) { shc[threadIdx.x >> 5] = cnt; shs[threadIdx.x >> 5] = sig; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int a = 0, b = 0;
-        for (int w = 0; w < TRK_THREADS / 32; ++w) { a += shc[w]; b += shs[w]; }
-        J.partialI[blockIdx.x * 2] = a; J.partialI[blockIdx.x * 2 + 1] = b;
-    }
-    if (!lastBlock(&st->ticket[1])) return;
-    // integer partials: exact, summed by the whole block
-    int ps = 0, pc = 0;
-    for (unsigned b2 = threadIdx.x; b2 < gridDim.x; b2 += TRK_THREADS) { pc += J.partialI[b2 * 2]; ps += J.partialI[b2 * 2 + 1]; }
-    for (int off = 16; off > 0; off >>= 1) { pc += __shfl_down_sync(0xffffffffu, pc, off); ps += __shfl_down_sync(0xffffffffu, ps, off); }
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { shc[threadIdx.x >> 5] = pc; shs[threadIdx.x >> 5] = ps; }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    int rgbSize = 0, sigma = 0;
-    for (int w = 0; w < TRK_THREADS / 32; ++w) { rgbSize += shc[w]; sigma += shs[w]; }
-    // RGBDOdometry.cpp:388-401
-    float tmpError = (float)(sqrt((double)sigma) / (double)rgbSize);
-    float sigmaVal = (tmpError == 0) ? 1 : (float)rgbSize;
-    if (rgbOnly && tmpError > st->lastRGBError) { st->levelBreak = 1; return; }
-    st->lastRGBError = tmpError; st->lastRGBCount = (float)rgbSize;
-    if (rgbOnly) sigmaVal = -1;
-    st->sigmaVal = sigmaVal;
-}
-
-// ---------------------------------------------------------------------------------------
-// fused ICP + photometric Gauss-Newton step, solve and pose update
-// ---------------------------------------------------------------------------------------
-template <bool ICP, bool RGB>
-__global__ void __launch_bounds__(TRK_THREADS) k_gn_step(TrackJob* jobs, int level, int W, int H, Cam cam, float distThres, float angleThres,
-                                                         float icpWeight, float sobelScale)
-{
-    TrackJob& J = jobs[blockIdx.y];
-    TrackState* st = J.st;
-    if (st->levelBreak) return;
-    __shared__ float Rc[9], tc[3], Rpi[9], tp[3];
-    __shared__ float sigmaSh;
-    if (threadIdx.x < 9) { Rc[threadIdx.x] = st->Rcurr[threadIdx.x]; Rpi[threadIdx.x] = st->RprevInv[threadIdx.x]; }
-    if (threadIdx.x < 3) { tc[threadIdx.x] = st->tcurr[threadIdx.x]; tp[threadIdx.x] = st->tprev[threadIdx.x]; }
-    if (threadIdx.x == 0) sigmaSh = st->sigmaVal;
-    __syncthreads();
-    const float4* __restrict__ vmapC = J.vmapC[level];
-    const float4* __restrict__ nmapC = J.nmapC[level];
-    const float4* __restrict__ vmapG = J.vmapG[level];
-    const float4* __restrict__ nmapG = J.nmapG[level];
-    const DataTerm* __restrict__ corres = J.corres[level];
-    const float4* __restrict__ cloud = J.cloud[level];
-    const short2* __restrict__ grad = J.nextGrad[level];
-    const float3 tprev = make_float3(tp[0], tp[1], tp[2]);
-    float acc[NACC];
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
-    const int N = W * H;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
-        if (ICP) {
-            float4 vc4 = vmapC[i];
-            float3 vg = m3v(Rc, make_float3(vc4.x, vc4.y, vc4.z));
-            vg = make_float3(vg.x + tc[0], vg.y + tc[1], vg.z + tc[2]);
-            float3 tmp = sub3(vg, tprev);
-            float3 vcp = m3v(Rpi, tmp);
-            int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
-            int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
-            if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) {
-                int j = uy * W + ux;
-                float4 vp4 = __ldg(vmapG + j), np4 = __ldg(nmapG + j), nc4 = nmapC[i];
-                float3 vp = make_float3(vp4.x, vp4.y, vp4.z), np_ = make_float3(np4.x, np4.y, np4.z);
-                float3 ng = m3v(Rc, make_float3(nc4.x, nc4.y, nc4.z));
-                float3 d = sub3(vp, vg);
-                float dist = sqrtf((d.x * d.x + d.y * d.y) + d.z * d.z);
-                float3 c = cross3(ng, np_);
-                float sine = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
-                bool found = (sine < angleThres && dist <= distThres && !isnan(nc4.x) && !isnan(np4.x));
-                if (found) {
-                    float3 s_cp = vcp;
-                    float3 d_cp = m3v(Rpi, sub3(vp, tprev));
-                    float3 n_cp = m3v(Rpi, np_);
-                    float row[7];
-                    row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z;
-                    row[3] = s_cp.y * n_cp.z - s_cp.z * n_cp.y;
-                    row[4] = s_cp.z * n_cp.x - s_cp.x * n_cp.z;
-                    row[5] = s_cp.x * n_cp.y - s_cp.y * n_cp.x;
-                    row[6] = (n_cp.x * (s_cp.x - d_cp.x) + n_cp.y * (s_cp.y - d_cp.y)) + n_cp.z * (s_cp.z - d_cp.z);
-                    int q = 0;
-#pragma unroll
-                    for (int a = 0; a < 6; ++a)
-#pragma unroll
-                        for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
-                    acc[27] += row[6] * row[6];
-                    acc[28] += 1.0f;
-                }
-            }
-        }
-        if (RGB) {
-            DataTerm ct = corres[i];
-            if (ct.valid) {
-                float w = sigmaSh + fabsf(ct.diff);
-                w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
-                if (sigmaSh == -1) w = 1;
-                float row[7];
-                row[6] = -w * ct.diff;
-                float4 cp = cloud[ct.zero.y * W + ct.zero.x];
-                float invz = (float)(1.0 / (double)cp.z);
-                short2 g = grad[ct.one.y * W + ct.one.x];
-                float dIdx_v = w * sobelScale * (float)g.x;
-                float dIdy_v = w * sobelScale * (float)g.y;
-                float v0 = dIdx_v * cam.fx * invz;
-                float v1 = dIdy_v * cam.fy * invz;
-                float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
-                row[0] = v0; row[1] = v1; row[2] = v2;
-                row[3] = -cp.z * v1 + cp.y * v2;
-                row[4] = cp.z * v0 - cp.x * v2;
-                row[5] = -cp.y * v0 + cp.x * v1;
-                int q = NACC_ICP;
-#pragma unroll
-                for (int a = 0; a < 6; ++a)
-#pragma unroll
-                    for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
-            }
-        }
-    }
-    blockReduceStore<NACC>(acc, J.partial + (size_t)blockIdx.x * 64);
-    if (!lastBlock(&st->ticket[2])) return;
-    __shared__ double tot[NACC];
-    sumPartials<NACC>(J.partial, gridDim.x, tot);
-    if (threadIdx.x != 0) return;
-
-    // ---- host part of RGBDOdometry.cpp:403-474, on the device ----
-    float A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
-    for (int k = 0; k < 36; ++k) { A_icp[k] = 0; A_rgb[k] = 0; }
-    for (int k = 0; k < 6; ++k) { b_icp[k] = 0; b_rgb[k] = 0; }
-    int q = 0;
-    for (int a = 0; a < 6; ++a) for (int b = a; b < 7; ++b) {
-        float vi = (float)tot[q], vr = (float)tot[NACC_ICP + q]; ++q;
-        if (b == 6) { b_icp[a] = vi; b_rgb[a] = vr; }
-        else { A_icp[b * 6 + a] = A_icp[a * 6 + b] = vi; A_rgb[b * 6 + a] = A_rgb[a * 6 + b] = vr; }
-    }
-    if (ICP) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
-    double A[36], b[6], result[6];
-    if (ICP && RGB) {
-        double wgt = icpWeight;
-        for (int k = 0; k < 36; ++k) A[k] = (double)A_rgb[k] + wgt * wgt * (double)A_icp[k];
-        for (int k = 0; k < 6; ++k) b[k] = (double)b_rgb[k] + wgt * (double)b_icp[k];
-    } else if (ICP) {
-        for (int k = 0; k < 36; ++k) A[k] = A_icp[k];
-        for (int k = 0; k < 6; ++k) b[k] = b_icp[k];
-    } else {
-        for (int k = 0; k < 36; ++k) A[k] = A_rgb[k];
-        for (int k = 0; k < 6; ++k) b[k] = b_rgb[k];
-    }
-    for (int k = 0; k < 36; ++k) st->lastA[k] = A[k];
-    for (int k = 0; k < 6; ++k) st->lastb[k] = b[k];
-    if (!ldltSolve6Fast(A, b, result)) ldltSolve(A, b, 6, result);
-    // computeUpdateSE3 (OdometryProvider.h:69-90)
-    double Rt[16], Rup[9];
-    for (int k = 0; k < 16; ++k) Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
-    rodrigues(&result[3], Rup);
-    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Rt[r * 4 + c] = Rup[r * 3 + c]; Rt[r * 4 + 3] = result[r]; }
-    double nr[16];
-    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
-        double s = 0;
-        for (int k = 0; k < 4; ++k) s += Rt[r * 4 + k] * st->resultRt[k * 4 + c];
-        nr[r * 4 + c] = s;
-    }
-    for (int k = 0; k < 16; ++k) st->resultRt[k] = nr[k];
-    float trR[9], trT[3];
-    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) trR[r * 3 + c] = (float)nr[r * 4 + c]; trT[r] = (float)nr[r * 4 + 3]; }
-    for (int k = 0; k < 9; ++k) st->trR[k] = trR[k];
-    for (int k = 0; k < 3; ++k) st->trT[k] = trT[k];
-    // currentT = [Rprev|tprev] * transform^-1   (RGBDOdometry.cpp:466-474)
-    float iR[9], iT[3];
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) iR[r * 3 + c] = trR[c * 3 + r];
-    for (int r = 0; r < 3; ++r) iT[r] = -((iR[r * 3] * trT[0] + iR[r * 3 + 1] * trT[1]) + iR[r * 3 + 2] * trT[2]);
-    for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) st->Rcurr[r * 3 + c] = (st->Rprev[r * 3] * iR[c] + st->Rprev[r * 3 + 1] * iR[3 + c]) + st->Rprev[r * 3 + 2] * iR[6 + c];
-        st->tcurr[r] = ((st->Rprev[r * 3] * iT[0] + st->Rprev[r * 3 + 1] * iT[1]) + st->Rprev[r * 3 + 2] * iT[2]) + st->tprev[r];
-    }
-    if (RGB) computeWarp(st, cam);          // warp constants for the next iteration's residual kernel
-}
-
 // stand-alone ICP reduction at a caller-given pose (parity tests; mirrors icpStep's outputs)
 __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restrict__ vmapC, const float4* __restrict__ nmapC,
                                                           const float4* __restrict__ vmapG, const float4* __restrict__ nmapG,
@@ -685,52 +286,551 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restri
     if (threadIdx.x < NACC_ICP) out29[threadIdx.x] = (float)tot[threadIdx.x];
 }
 
+// =======================================================================================
+// The whole Gauss-Newton schedule of a frame as ONE cooperative kernel.
+//
+// The reference returns to the host after each of its <= 67 reductions per model per frame; a launch-per-iteration
+// device port (round 1, first version) still paid ~10-45 us of launch + tail latency 38 times per frame, 40 % of the
+// frame.  Here a persistent grid (1 CTA per SM, split between the tracked models along blockIdx.y) walks the schedule
+//     SO(3) pre-alignment (<= 10 its) -> level 2 (4) -> level 1 (5) -> level 0 (10)
+// with one software grid barrier per reduction.  The solver state is REPLICATED: after a barrier every CTA sums the
+// same per-CTA partial rows in the same order and runs the same 6x6 solve, so all CTAs hold bit-identical poses and
+// take identical break decisions without a second barrier or a broadcast.  Per-pixel data that a later phase needs
+// (photometric correspondences, validity) is written and re-read by the same thread.
+// =======================================================================================
+#define PT_THREADS 512
+#define PT_WARPS (PT_THREADS / 32)
+
+struct TrackParams {
+    int W, H; Cam cam;
+    int icp, rgb, rgbOnly, so3;
+    int iterations[3];
+    float icpWeight, angleThres, distThres, sobelScale, maxDepthDelta;
+    float minScale[3];
+};
+
+// sum of NP (= 32 or 64, zero padded) per-lane values over the warp with NP-ish shuffles instead of 5*NP:
+// each step exchanges HALF of the remaining values with the xor partner.  Lane l ends with values l (NP=32) or 2l, 2l+1 (NP=64).
+template <int NP>
+MF_D void warpReduceHalving(float* v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int off = 16 >> s, h = (NP / 2) >> s;
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int k = 0; k < h; ++k) {
+            float keep = up ? v[k + h] : v[k];
+            float send = up ? v[k] : v[k + h];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// CTA-wide sum of N accumulators -> one row of 64 floats in global memory (row = this CTA's partial)
+template <int N>
+MF_D void ctaReduceStore(const float* acc, float (*red)[64], float* __restrict__ rowOut, int extra0 = 0, int extra1 = 0, bool hasExtra = false)
+{
+    constexpr int NP = N <= 32 ? 32 : 64;
+    float v[NP];
+#pragma unroll
+    for (int k = 0; k < NP; ++k) v[k] = k < N ? acc[k] : 0.f;
+    warpReduceHalving<NP>(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (NP == 32) red[warp][lane] = v[0];
+    else { red[warp][2 * lane] = v[0]; red[warp][2 * lane + 1] = v[1]; }
+    int e0 = extra0, e1 = extra1;
+    if (hasExtra) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { e0 += __shfl_down_sync(0xffffffffu, e0, off); e1 += __shfl_down_sync(0xffffffffu, e1, off); }
+        if (lane == 0) { red[warp][62] = __int_as_float(e0); red[warp][63] = __int_as_float(e1); }
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        float s = 0;
+#pragma unroll
+        for (int w = 0; w < PT_WARPS; ++w) s += red[w][threadIdx.x];
+        rowOut[threadIdx.x] = s;
+    } else if (hasExtra && (threadIdx.x == 62 || threadIdx.x == 63)) {
+        int s = 0;
+#pragma unroll
+        for (int w = 0; w < PT_WARPS; ++w) s += __float_as_int(red[w][threadIdx.x]);
+        rowOut[threadIdx.x] = __int_as_float(s);
+    }
+}
+
+// all CTAs of one model: arrive, wait until `target` arrivals have been counted since the launch (monotonic counter)
+MF_D void gridBarrier(unsigned* bar, unsigned target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // our partial row is visible before the arrival
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// every CTA: sum the G partial rows (fixed order, double) -> tot[0..N); columns 62/63 carry exact integers
+template <int N, bool EXTRA>
+MF_D void sumRows(const float* __restrict__ rows, unsigned G, double (*ws)[64], double* tot)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double a0 = 0, a1 = 0;
+#pragma unroll 4
+    for (unsigned b = warp; b < G; b += PT_WARPS) {
+        const float* row = rows + (size_t)b * 64;
+        if (lane < N) a0 += (double)__ldcg(row + lane);
+        if (N > 32 || EXTRA) {
+            float x = __ldcg(row + 32 + lane);
+            if (EXTRA && lane >= 30) a1 += (double)__float_as_int(x);
+            else if (32 + lane < N) a1 += (double)x;
+        }
+    }
+    ws[warp][lane] = a0; ws[warp][32 + lane] = a1;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < PT_WARPS; ++w) s += ws[w][threadIdx.x];
+        tot[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+MF_D void gradU8(const uint8_t* __restrict__ img, int W, int x, int y, float& gx, float& gy)
+{
+    float actu = img[y * W + x], back = img[y * W + x - 1], fore = img[y * W + x + 1];
+    gx = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+    back = img[(y - 1) * W + x]; fore = img[(y + 1) * W + x];
+    gy = ((back + actu) / 2.0f) - ((fore + actu) / 2.0f);
+}
+
+
+// pose-independent part of residualKernel (reduce.cu:821-845): 4x4 window of non-zero intensities + gradient-magnitude gate
+MF_D bool rgbValidPixel(const uint8_t* __restrict__ nextImage, const short2* __restrict__ grad, int W, int H, int k, float minScale)
+{
+    int i = k / W, j0 = k - i * W;
+    bool valid = false;
+    if (j0 < W - 5 && i < H - 1) {
+        valid = true;
+        for (int u = max(i - 2, 0); u < min(i + 2, H); ++u)
+            for (int v = max(j0 - 2, 0); v < min(j0 + 2, W); ++v) valid = valid && (nextImage[u * W + v] > 0);
+        if (valid) {
+            short2 g = grad[k];
+            float mTwo = (float)(((int)g.x * (int)g.x) + ((int)g.y * (int)g.y));
+            valid = mTwo >= minScale;
+        }
+    }
+    return valid;
+}
+
+// host part of one Gauss-Newton iteration (RGBDOdometry.cpp:403-474) on the replicated state
+MF_D void solveAndUpdate(TrackState* st, const double* tot, bool ICP, bool RGB, float icpWeight, Cam cam)
+{
+    float A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
+    for (int k = 0; k < 36; ++k) { A_icp[k] = 0; A_rgb[k] = 0; }
+    for (int k = 0; k < 6; ++k) { b_icp[k] = 0; b_rgb[k] = 0; }
+    int q = 0;
+    for (int a = 0; a < 6; ++a) for (int b = a; b < 7; ++b) {
+        float vi = (float)tot[q], vr = (float)tot[NACC_ICP + q]; ++q;
+        if (b == 6) { b_icp[a] = vi; b_rgb[a] = vr; }
+        else { A_icp[b * 6 + a] = A_icp[a * 6 + b] = vi; A_rgb[b * 6 + a] = A_rgb[a * 6 + b] = vr; }
+    }
+    if (ICP) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
+    double A[36], b[6], result[6];
+    if (ICP && RGB) {
+        double wgt = icpWeight;
+        for (int k = 0; k < 36; ++k) A[k] = (double)A_rgb[k] + wgt * wgt * (double)A_icp[k];
+        for (int k = 0; k < 6; ++k) b[k] = (double)b_rgb[k] + wgt * (double)b_icp[k];
+    } else if (ICP) {
+        for (int k = 0; k < 36; ++k) A[k] = A_icp[k];
+        for (int k = 0; k < 6; ++k) b[k] = b_icp[k];
+    } else {
+        for (int k = 0; k < 36; ++k) A[k] = A_rgb[k];
+        for (int k = 0; k < 6; ++k) b[k] = b_rgb[k];
+    }
+    for (int k = 0; k < 36; ++k) st->lastA[k] = A[k];
+    for (int k = 0; k < 6; ++k) st->lastb[k] = b[k];
+    if (!ldltSolve6Fast(A, b, result)) ldltSolve(A, b, 6, result);
+    // computeUpdateSE3 (OdometryProvider.h:69-90)
+    double Rt[16], Rup[9];
+    for (int k = 0; k < 16; ++k) Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    rodrigues(&result[3], Rup);
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Rt[r * 4 + c] = Rup[r * 3 + c]; Rt[r * 4 + 3] = result[r]; }
+    double nr[16];
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
+        double s = 0;
+        for (int k = 0; k < 4; ++k) s += Rt[r * 4 + k] * st->resultRt[k * 4 + c];
+        nr[r * 4 + c] = s;
+    }
+    for (int k = 0; k < 16; ++k) st->resultRt[k] = nr[k];
+    float trR[9], trT[3];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) trR[r * 3 + c] = (float)nr[r * 4 + c]; trT[r] = (float)nr[r * 4 + 3]; }
+    for (int k = 0; k < 9; ++k) st->trR[k] = trR[k];
+    for (int k = 0; k < 3; ++k) st->trT[k] = trT[k];
+    // currentT = [Rprev|tprev] * transform^-1   (RGBDOdometry.cpp:466-474)
+    float iR[9], iT[3];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) iR[r * 3 + c] = trR[c * 3 + r];
+    for (int r = 0; r < 3; ++r) iT[r] = -((iR[r * 3] * trT[0] + iR[r * 3 + 1] * trT[1]) + iR[r * 3 + 2] * trT[2]);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) st->Rcurr[r * 3 + c] = (st->Rprev[r * 3] * iR[c] + st->Rprev[r * 3 + 1] * iR[3 + c]) + st->Rprev[r * 3 + 2] * iR[6 + c];
+        st->tcurr[r] = ((st->Rprev[r * 3] * iT[0] + st->Rprev[r * 3 + 1] * iT[1]) + st->Rprev[r * 3 + 2] * iT[2]) + st->tprev[r];
+    }
+    if (RGB) computeWarp(st, cam);          // warp constants for the next iteration's residuals
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackPoses poses, TrackParams tp)
+{
+    __shared__ TrackJob J;
+    __shared__ TrackState S;
+    __shared__ float red[PT_WARPS][64];
+    __shared__ double ws[PT_WARPS][64];
+    __shared__ double tot[64];
+    __shared__ float so3B[9], so3Kinv[9], so3Krlr[9];
+    __shared__ double totR[64];
+    __shared__ int flag;
+    {   // job record -> shared memory (one coalesced read instead of dependent pointer chases in every phase)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + blockIdx.y);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&J);
+        for (int k = threadIdx.x; k < (int)(sizeof(TrackJob) / 4); k += PT_THREADS) dst[k] = src[k];
+    }
+    TrackState* st = &S;
+    const unsigned G = gridDim.x;
+    const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)G * PT_THREADS;
+    unsigned gen = 0;                                                  // barriers passed (uniform)
+    if (threadIdx.x == 0) {
+        // RGBDOdometry.cpp:331-345 initial state
+        const float* P = poses.p[blockIdx.y];
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) st->Rprev[r * 3 + c] = P[r * 4 + c]; st->tprev[r] = P[r * 4 + 3]; }
+        for (int k = 0; k < 9; ++k) st->Rcurr[k] = st->Rprev[k];
+        for (int k = 0; k < 3; ++k) st->tcurr[k] = st->tprev[k];
+        inv3f(st->Rprev, st->RprevInv);
+        for (int k = 0; k < 16; ++k) st->resultRt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+        for (int k = 0; k < 9; ++k) { st->resultR[k] = (k % 4 == 0) ? 1.0 : 0.0; st->lastResultR[k] = st->resultR[k]; st->R_lr[k] = (k % 4 == 0) ? 1.f : 0.f; st->trR[k] = (k % 4 == 0) ? 1.f : 0.f; }
+        st->trT[0] = st->trT[1] = st->trT[2] = 0;
+        st->so3LastError = FLT_MAX / 2; st->so3LastCount = FLT_MAX / 2; st->so3Done = 0;
+        st->levelBreak = 0; st->lastRGBError = FLT_MAX; st->lastRGBCount = 0; st->lastICPError = 0; st->lastICPCount = 0;
+        st->lastSO3Error = 0; st->lastSO3Count = 0; st->sigmaVal = 0;
+        for (int k = 0; k < 36; ++k) st->lastA[k] = 0;
+        for (int k = 0; k < 6; ++k) st->lastb[k] = 0;
+    }
+    __syncthreads();
+    float* const rowsBuf[2] = {J.partial, J.partial + (size_t)G * 64};
+    unsigned* const bar = J.bar;
+
+    // ---------------- SO(3) pre-alignment on level-2 intensities (RGBDOdometry.cpp:272-345) ----------------
+    if (tp.so3) {
+        const int W = tp.W >> 2, H = tp.H >> 2, N = W * H;
+        const Cam c = camLevel(tp.cam, 2);
+        const uint8_t* __restrict__ lastImage = J.lastNextImage2;
+        const uint8_t* __restrict__ nextImage = J.nextImage[2];
+        for (int it = 0; it < 10; ++it) {
+            if (threadIdx.x == 0) {
+                double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1}, Kinv[9], kr[9], hom[9];
+                inv3d(K, Kinv); mul3d(K, st->resultR, kr); mul3d(kr, Kinv, hom);
+                for (int q = 0; q < 9; ++q) { so3B[q] = (float)hom[q]; so3Kinv[q] = (float)Kinv[q]; so3Krlr[q] = (float)kr[q]; }
+            }
+            __syncthreads();
+            float acc[11];
+#pragma unroll
+            for (int k = 0; k < 11; ++k) acc[k] = 0;
+            for (int k = tid; k < N; k += nthr) {
+                int y = k / W, x = k - y * W;
+                float3 ur = make_float3((float)x, (float)y, 1.0f);
+                float3 wr = m3v(so3B, ur);
+                int wx = __float2int_rn(wr.x / wr.z), wy = __float2int_rn(wr.y / wr.z);
+                bool found = (wx >= 1 && wx < W - 1 && wy >= 1 && wy < H - 1 && x >= 1 && x < W - 1 && y >= 1 && y < H - 1);
+                if (found) {
+                    float gnx, gny, glx, gly;
+                    gradU8(nextImage, W, wx, wy, gnx, gny);
+                    gradU8(lastImage, W, x, y, glx, gly);
+                    float gx = (gnx + glx) / 2.0f, gy = (gny + gly) / 2.0f;
+                    float3 p = m3v(so3Kinv, ur);
+                    float z2 = p.z * p.z;
+                    float a = so3Krlr[0], b = so3Krlr[1], cc = so3Krlr[2], d = so3Krlr[3], e = so3Krlr[4], f = so3Krlr[5], g = so3Krlr[6], h = so3Krlr[7], i = so3Krlr[8];
+                    float fy = (float)y, fxx = (float)x;
+                    float3 l = make_float3(((p.z * (d * gy + a * gx)) - (gy * g * fy) - (gx * g * fxx)) / z2,
+                                           ((p.z * (e * gy + b * gx)) - (gy * h * fy) - (gx * h * fxx)) / z2,
+                                           ((p.z * (f * gy + cc * gx)) - (gy * i * fy) - (gx * i * fxx)) / z2);
+                    float row[4];
+                    row[0] = l.y * p.z - l.z * p.y;
+                    row[1] = l.z * p.x - l.x * p.z;
+                    row[2] = l.x * p.y - l.y * p.x;
+                    row[3] = -((float)nextImage[wy * W + wx] - (float)lastImage[k]);
+                    int q = 0;
+#pragma unroll
+                    for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                        for (int jj = ii; jj < 4; ++jj) acc[q++] += row[ii] * row[jj];
+                    acc[9] += row[3] * row[3];
+                    acc[10] += 1.0f;
+                }
+            }
+            float* rows = rowsBuf[gen & 1];
+            ctaReduceStore<11>(acc, red, rows + (size_t)blockIdx.x * 64);
+            ++gen; gridBarrier(bar, gen * G);
+            sumRows<11, false>(rows, G, ws, tot);
+            if (threadIdx.x == 0) {
+                // host logic of RGBDOdometry.cpp:301-324
+                int done = 0;
+                float res0 = (float)tot[9], res1 = (float)tot[10];
+                st->lastSO3Error = sqrtf(res0) / res1; st->lastSO3Count = res1;
+                if (st->lastSO3Error < st->so3LastError && fabsf(st->so3LastError - st->lastSO3Count) < 0.001f) done = 1;
+                else if (st->lastSO3Error > st->so3LastError + 0.001f) {
+                    st->lastSO3Error = st->so3LastError; st->lastSO3Count = st->so3LastCount;
+                    for (int q = 0; q < 9; ++q) st->resultR[q] = st->lastResultR[q];
+                    done = 1;
+                } else {
+                    st->so3LastError = st->lastSO3Error; st->so3LastCount = st->lastSO3Count;
+                    for (int q = 0; q < 9; ++q) st->lastResultR[q] = st->resultR[q];
+                    double A[9], bb[3], delta[3]; int q = 0;
+                    for (int ii = 0; ii < 3; ++ii) for (int jj = ii; jj < 4; ++jj) { double v = (double)(float)tot[q++]; if (jj == 3) bb[ii] = v; else A[jj * 3 + ii] = A[ii * 3 + jj] = v; }
+                    ldltSolve(A, bb, 3, delta);
+                    for (int k = 0; k < 3; ++k) delta[k] = (double)(float)delta[k];
+                    double ru[9]; rodrigues(delta, ru);
+                    float ruf[9], n[9];
+                    for (int k = 0; k < 9; ++k) ruf[k] = (float)ru[k];
+                    for (int r = 0; r < 3; ++r) for (int cc2 = 0; cc2 < 3; ++cc2) n[r * 3 + cc2] = (ruf[r * 3] * st->R_lr[cc2] + ruf[r * 3 + 1] * st->R_lr[3 + cc2]) + ruf[r * 3 + 2] * st->R_lr[6 + cc2];
+                    for (int k = 0; k < 9; ++k) { st->R_lr[k] = n[k]; st->resultR[k] = n[k]; }
+                }
+                flag = done;
+            }
+            __syncthreads();
+            if (flag) break;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)          // so3 result -> initial resultRt (RGBDOdometry.cpp:337-345)
+            for (int r = 0; r < 3; ++r) for (int cc = 0; cc < 3; ++cc) st->resultRt[r * 4 + cc] = st->resultR[r * 3 + cc];
+        __syncthreads();
+    }
+
+    // ---------------- pyramid levels, coarse to fine (RGBDOdometry.cpp:347-476) ----------------
+    for (int level = 2; level >= 0; --level) {
+        if (tp.iterations[level] == 0) continue;
+        const int W = tp.W >> level, H = tp.H >> level, N = W * H;
+        const Cam cam = camLevel(tp.cam, level);
+        const float4* __restrict__ vmapC = J.vmapC[level];
+        const float4* __restrict__ nmapC = J.nmapC[level];
+        const float4* __restrict__ vmapG = J.vmapG[level];
+        const float4* __restrict__ nmapG = J.nmapG[level];
+        DataTerm* __restrict__ corres = J.corres[level];
+        const float4* __restrict__ cloud = J.cloud[level];
+        const short2* __restrict__ grad = J.nextGrad[level];
+        const float* __restrict__ lastDepth = J.lastDepth[level];
+        const float* __restrict__ nextDepth = J.lastDepth[level];      // reference quirk: both pyramids derive from vmaps_tmp (RGBDOdometry.cpp:187-215)
+        const uint8_t* __restrict__ lastImage = J.lastImage[level];
+        const uint8_t* __restrict__ nextImage = J.nextImage[level];
+        uint8_t* __restrict__ rgbValid = J.rgbValid[level];
+        if (threadIdx.x == 0) { st->levelBreak = 0; st->lastRGBError = FLT_MAX; if (tp.rgb) computeWarp(st, cam); }
+        if (tp.rgb)                                                     // validity is pose independent: once per level, same thread reads it back
+            for (int k = tid; k < N; k += nthr) rgbValid[k] = rgbValidPixel(nextImage, grad, W, H, k, tp.minScale[level]) ? 1 : 0;
+        __syncthreads();
+        for (int it = 0; it < tp.iterations[level]; ++it) {
+            // ---- phase A: photometric correspondences + statistics, ICP normal equations ----
+            float acc[NACC_ICP];
+#pragma unroll
+            for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.f;
+            int cnt = 0, sig = 0;
+            const float3 tprev = make_float3(st->tprev[0], st->tprev[1], st->tprev[2]);
+            for (int k = tid; k < N; k += nthr) {
+                if (tp.rgb) {
+                    int i = k / W, j0 = k - i * W;
+                    DataTerm c; c.zero = make_short2(0, 0); c.one = make_short2(0, 0); c.diff = 0; c.valid = 0;
+                    if (rgbValid[k]) {
+                        int y = i, x = j0;
+                        float d1 = nextDepth[k];
+                        if (!isnan(d1)) {
+                            const float* K = st->krk; const float* kt = st->kt;
+                            float td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
+                            float fu = (d1 * ((K[0] * x + K[1] * y) + K[2]) + kt[0]) / td1;
+                            float fv = (d1 * ((K[3] * x + K[4] * y) + K[5]) + kt[1]) / td1;
+                            int u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
+                            int v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
+                            if (u0 >= 0 && v0 >= 0 && u0 < W && v0 < H) {
+                                float d0 = lastDepth[v0 * W + u0];
+                                uint8_t li = lastImage[v0 * W + u0];
+                                if (d0 > 0 && fabsf(td1 - d0) <= tp.maxDepthDelta && li != 0) {
+                                    c.zero = make_short2((short)u0, (short)v0); c.one = make_short2((short)x, (short)y);
+                                    c.diff = (float)nextImage[k] - (float)li;
+                                    c.valid = 1;
+                                    cnt += 1;
+                                    sig += (int)(c.diff * c.diff);
+                                }
+                            }
+                        }
+                    }
+                    corres[k] = c;
+                }
+                if (tp.icp) {
+                    float4 vc4 = vmapC[k];
+                    float3 vg = m3v(st->Rcurr, make_float3(vc4.x, vc4.y, vc4.z));
+                    vg = make_float3(vg.x + st->tcurr[0], vg.y + st->tcurr[1], vg.z + st->tcurr[2]);
+                    float3 tmp = sub3(vg, tprev);
+                    float3 vcp = m3v(st->RprevInv, tmp);
+                    int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
+                    int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
+                    if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) {
+                        int j = uy * W + ux;
+                        float4 vp4 = __ldg(vmapG + j), np4 = __ldg(nmapG + j), nc4 = nmapC[k];
+                        float3 vp = make_float3(vp4.x, vp4.y, vp4.z), np_ = make_float3(np4.x, np4.y, np4.z);
+                        float3 ng = m3v(st->Rcurr, make_float3(nc4.x, nc4.y, nc4.z));
+                        float3 d = sub3(vp, vg);
+                        float dist = sqrtf((d.x * d.x + d.y * d.y) + d.z * d.z);
+                        float3 c = cross3(ng, np_);
+                        float sine = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
+                        bool found = (sine < tp.angleThres && dist <= tp.distThres && !isnan(nc4.x) && !isnan(np4.x));
+                        if (found) {
+                            float3 s_cp = vcp;
+                            float3 d_cp = m3v(st->RprevInv, sub3(vp, tprev));
+                            float3 n_cp = m3v(st->RprevInv, np_);
+                            float row[7];
+                            row[0] = n_cp.x; row[1] = n_cp.y; row[2] = n_cp.z;
+                            row[3] = s_cp.y * n_cp.z - s_cp.z * n_cp.y;
+                            row[4] = s_cp.z * n_cp.x - s_cp.x * n_cp.z;
+                            row[5] = s_cp.x * n_cp.y - s_cp.y * n_cp.x;
+                            row[6] = (n_cp.x * (s_cp.x - d_cp.x) + n_cp.y * (s_cp.y - d_cp.y)) + n_cp.z * (s_cp.z - d_cp.z);
+                            int q = 0;
+#pragma unroll
+                            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                                for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
+                            acc[27] += row[6] * row[6];
+                            acc[28] += 1.0f;
+                        }
+                    }
+                }
+            }
+            __syncthreads();                                            // everyone has read the state before thread 0 rewrites it below
+            float* rowsA = rowsBuf[gen & 1];
+            ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * 64, cnt, sig, true);
+            ++gen; gridBarrier(bar, gen * G);
+            sumRows<NACC_ICP, true>(rowsA, G, ws, tot);
+            if (tp.rgb) {
+                if (threadIdx.x == 0) {
+                    // RGBDOdometry.cpp:388-401
+                    int rgbSize = (int)(long long)tot[62], sigma = (int)(long long)tot[63];
+                    float tmpError = (float)(sqrt((double)sigma) / (double)rgbSize);
+                    float sigmaVal = (tmpError == 0) ? 1 : (float)rgbSize;
+                    int brk = 0;
+                    if (tp.rgbOnly && tmpError > st->lastRGBError) brk = 1;
+                    else {
+                        st->lastRGBError = tmpError; st->lastRGBCount = (float)rgbSize;
+                        if (tp.rgbOnly) sigmaVal = -1;
+                        st->sigmaVal = sigmaVal;
+                    }
+                    flag = brk;
+                }
+                __syncthreads();
+                if (flag) break;                                        // uniform over the whole grid: every CTA holds the same state
+                // ---- phase B: photometric normal equations with the weights of this iteration ----
+                float accR[NACC_RGB];
+#pragma unroll
+                for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.f;
+                const float sigmaSh = st->sigmaVal;
+                for (int k = tid; k < N; k += nthr) {
+                    DataTerm ct = corres[k];
+                    if (ct.valid) {
+                        float w = sigmaSh + fabsf(ct.diff);
+                        w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+                        if (sigmaSh == -1) w = 1;
+                        float row[7];
+                        row[6] = -w * ct.diff;
+                        float4 cp = cloud[ct.zero.y * W + ct.zero.x];
+                        float invz = (float)(1.0 / (double)cp.z);
+                        short2 g = grad[ct.one.y * W + ct.one.x];
+                        float dIdx_v = w * tp.sobelScale * (float)g.x;
+                        float dIdy_v = w * tp.sobelScale * (float)g.y;
+                        float v0 = dIdx_v * cam.fx * invz;
+                        float v1 = dIdy_v * cam.fy * invz;
+                        float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
+                        row[0] = v0; row[1] = v1; row[2] = v2;
+                        row[3] = -cp.z * v1 + cp.y * v2;
+                        row[4] = cp.z * v0 - cp.x * v2;
+                        row[5] = -cp.y * v0 + cp.x * v1;
+                        int q = 0;
+#pragma unroll
+                        for (int a = 0; a < 6; ++a)
+#pragma unroll
+                            for (int b = a; b < 7; ++b) accR[q++] += row[a] * row[b];
+                    }
+                }
+                float* rowsB = rowsBuf[gen & 1];
+                ctaReduceStore<NACC_RGB>(accR, red, rowsB + (size_t)blockIdx.x * 64);
+                ++gen; gridBarrier(bar, gen * G);
+                // ICP totals stay in tot[0..28]; the photometric ones go behind them
+                sumRows<NACC_RGB, false>(rowsB, G, ws, totR);
+                if (threadIdx.x < NACC_RGB) tot[NACC_ICP + threadIdx.x] = totR[threadIdx.x];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) solveAndUpdate(st, tot, tp.icp != 0, tp.rgb != 0, tp.icpWeight, cam);
+            __syncthreads();
+        }
+        __syncthreads();
+    }
+
+    // ---------------- result (RGBDOdometry.cpp:478-497) ----------------
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float dx = st->tcurr[0] - st->tprev[0], dy = st->tcurr[1] - st->tprev[1], dz = st->tcurr[2] - st->tprev[2];
+        if (tp.rgb && sqrtf((dx * dx + dy * dy) + dz * dz) > 0.3f) {          // :478-482
+            for (int k = 0; k < 9; ++k) { st->Rcurr[k] = st->Rprev[k]; st->trR[k] = (k % 4 == 0) ? 1.f : 0.f; }
+            for (int k = 0; k < 3; ++k) { st->tcurr[k] = st->tprev[k]; st->trT[k] = 0; }
+        }
+        float* po = st->out;                 // [0..15] pose, [16..31] transform, [32..37] error stats
+        for (int k = 0; k < 32; ++k) po[k] = ((k % 16) % 5 == 0) ? 1.f : 0.f;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) { po[r * 4 + c] = st->Rcurr[r * 3 + c]; po[16 + r * 4 + c] = st->trR[r * 3 + c]; }
+            po[r * 4 + 3] = st->tcurr[r]; po[16 + r * 4 + 3] = st->trT[r];
+        }
+        po[32] = st->lastICPError; po[33] = st->lastICPCount; po[34] = st->lastRGBError; po[35] = st->lastRGBCount;
+        po[36] = st->lastSO3Error; po[37] = st->lastSO3Count;
+        *J.st = *st;
+    }
+}
+
 // ------------------------------ host launchers ----------------------------------------
 static int trackBlocks(int N, int numSMs)
 {
     int need = (N + TRK_THREADS - 1) / TRK_THREADS;
-    int cap = numSMs * 4;
+    int cap = numSMs * 2;
     if (cap > TRACK_MAX_BLOCKS) cap = TRACK_MAX_BLOCKS;
     return need < cap ? need : cap;
 }
 
 int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
-                    bool pyramid, bool fastOdom, bool so3, int numSMs, cudaStream_t s, const uint8_t* const* frameImage,
-                    const short2* const* frameGrad, uint8_t* const* rgbValid)
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s)
 {
-    int launches = 0;
-    const bool icp = !rgbOnly && icpWeight > 0;
-    const bool rgb = rgbOnly || icpWeight < 100;
-    prof_mark(s, "k_track_begin"); k_track_begin<<<nJobs, 32, 0, s>>>(d_jobs, poses, so3 ? 1 : 0); ++launches;
-    if (so3) {
-        int lv = 2, w = W >> lv, h = H >> lv;
-        Cam c = camLevel(cam, lv);
-        dim3 g(trackBlocks(w * h, numSMs), nJobs);
-        for (int i = 0; i < 10; ++i) { prof_mark(s, "k_so3_step"); k_so3_step<<<g, TRK_THREADS, 0, s>>>(d_jobs, w, h, c); ++launches; }
-        prof_mark(s, "k_track_so3_finish"); k_track_so3_finish<<<nJobs, 32, 0, s>>>(d_jobs, 1); ++launches;
+    static int coResident = -1;                 // CTAs of k_track_persistent the device can hold at once
+    if (coResident < 0) {
+        int perSM = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_track_persistent, PT_THREADS, 0);
+        if (e != cudaSuccess || perSM < 1) throw CudaError{std::string("k_track_persistent does not fit on an SM: ") + cudaGetErrorString(e)};
+        coResident = perSM * numSMs;
     }
-    int iterations[3] = {fastOdom ? 3 : 10, pyramid ? 5 : 0, pyramid ? 4 : 0};
-    const float sobelScale = (float)(1.0 / 8.0);
+    TrackParams tp;
+    tp.W = W; tp.H = H; tp.cam = cam;
+    tp.icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
+    tp.rgb = (rgbOnly || icpWeight < 100) ? 1 : 0;
+    tp.rgbOnly = rgbOnly ? 1 : 0; tp.so3 = so3 ? 1 : 0;
+    tp.iterations[0] = fastOdom ? 3 : 10; tp.iterations[1] = pyramid ? 5 : 0; tp.iterations[2] = pyramid ? 4 : 0;
+    tp.icpWeight = icpWeight;
+    tp.angleThres = (float)sin(20.f * 3.14159254f / 180.f);
+    tp.distThres = 0.10f; tp.sobelScale = (float)(1.0 / 8.0); tp.maxDepthDelta = 0.07f;
     const float minGrad[3] = {5, 3, 1};
-    const float angleThres = (float)sin(20.f * 3.14159254f / 180.f);
-    for (int l = 2; l >= 0; --l) {
-        int w = W >> l, h = H >> l;
-        Cam c = camLevel(cam, l);
-        if (iterations[l] == 0) continue;
-        prof_mark(s, "k_track_level_begin"); k_track_level_begin<<<nJobs, 32, 0, s>>>(d_jobs, l, c, rgb ? 1 : 0); ++launches;
-        dim3 g(trackBlocks(w * h, numSMs), nJobs);
-        float minScale = (float)(pow((double)minGrad[l], 2.0) / pow((double)sobelScale, 2.0));
-        for (int j = 0; j < iterations[l]; ++j) {
-            if (rgb) { prof_mark(s, "k_rgb_residual"); k_rgb_residual<<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, minScale, 0.07f, rgbOnly ? 1 : 0); ++launches; }
-            prof_mark(s, l == 0 ? "k_gn_step_L0" : (l == 1 ? "k_gn_step_L1" : "k_gn_step_L2"));
-            if (icp && rgb) k_gn_step<true, true><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
-            else if (icp) k_gn_step<true, false><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
-            else k_gn_step<false, true><<<g, TRK_THREADS, 0, s>>>(d_jobs, l, w, h, c, 0.10f, angleThres, icpWeight, sobelScale);
-            ++launches;
-        }
-    }
-    prof_mark(s, "k_track_end"); k_track_end<<<nJobs, 32, 0, s>>>(d_jobs, rgb ? 1 : 0); ++launches;
-    return launches;
+    for (int l = 0; l < 3; ++l) tp.minScale[l] = (float)(pow((double)minGrad[l], 2.0) / pow((double)tp.sobelScale, 2.0));
+    int G = numSMs / nJobs;                      // one CTA per SM, the SMs split between the tracked models
+    if (G * nJobs > coResident) G = coResident / nJobs;
+    if (G > TRACK_MAX_BLOCKS / 2) G = TRACK_MAX_BLOCKS / 2;
+    if (G < 1) throw CudaError{"too many tracked models for one cooperative launch"};
+    cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
+    prof_mark(s, "k_track_persistent");
+    const TrackJob* jp = d_jobs;
+    void* args[] = {(void*)&jp, (void*)&poses, (void*)&tp};
+    cudaCheck(cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(G, nJobs), dim3(PT_THREADS), args, 0, s), "cooperative launch (tracking)");
+    return 1;
 }
 
 void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,

@@ -99,6 +99,13 @@ def run_stagewise(name, nframes, **kw):
             # last-iteration system: A to 1e-5 relative; b (which is ~0 at convergence) relative to |A|, not to itself
             relA = float(np.abs(A - Ao).max() / (np.abs(Ao).max() + 1e-30)); relb = float(np.abs(b - bo).max() / (np.abs(Ao).max() + 1e-30))
             rep.check(f"[{t}] last JtJ/Jtr", relA < 1e-5 and relb < 1e-5, f"relA={relA:.2e} relb={relb:.2e}")
+            # residual statistics of the last iteration: the counts are integers decided per pixel (a pixel may flip at a ~1e-9 pose difference)
+            eo = np.array([od.lastICPError, od.lastICPCount, od.lastRGBError, od.lastRGBCount], np.float64)
+            rep.check(f"[{t}] ICP count", abs(e[1] - eo[1]) <= max(3, 1e-4 * eo[1]) and eo[1] > 1000, f"{e[1]} vs {eo[1]}")
+            rep.check(f"[{t}] ICP error", abs(e[0] - eo[0]) <= 1e-4 * abs(eo[0]) + 1e-12, f"{e[0]} vs {eo[0]}")
+            if mf.cfg.icpWeight < 100:
+                rep.check(f"[{t}] RGB correspondences", abs(e[3] - eo[3]) <= max(3, 1e-4 * eo[3]) and eo[3] > 1000, f"{e[3]} vs {eo[3]}")
+                rep.check(f"[{t}] RGB error", abs(e[2] - eo[2]) <= 1e-4 * abs(eo[2]) + 1e-12, f"{e[2]} vs {eo[2]}")
             gm.debugSetPoses(Po, orc.last_pose(0))          # teacher forcing
             orc.predict_indices(); gm.predictIndices(tick)
             idx, vc, ct, nr = gm.indexMap()
