@@ -374,29 +374,42 @@ MF_D void gridBarrier(unsigned* bar, unsigned target)
     __syncthreads();
 }
 
-// every CTA: sum the G partial rows (fixed order, double) -> tot[0..N); columns 62/63 carry exact integers
+// every CTA: sum the R partial rows (fixed order, double) -> tot[0..N); columns 62/63 carry exact integers.
+// Each warp owns rows warp, warp+16, ...: at most SUM_MAX_ROWS of them, all loaded before the first add (one L2 round trip;
+// a rolled loop paid one per 4 rows, ncu r01c: 29 % of the kernel).
+#define SUM_MAX_ROWS ((TRACK_MAX_BLOCKS / 2 + PT_WARPS - 1) / PT_WARPS)
 template <int N, bool EXTRA>
-MF_D void sumRows(const float* __restrict__ rows, unsigned G, double (*ws)[64], double* tot)
+MF_D void sumRows(const float* __restrict__ rows, unsigned R, double (*ws)[64], double* tot)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double a0 = 0, a1 = 0;
-#pragma unroll 4
-    for (unsigned b = warp; b < G; b += PT_WARPS) {
-        const float* row = rows + (size_t)b * 64;
-        if (lane < N) a0 += (double)__ldcg(row + lane);
-        if (N > 32 || EXTRA) {
-            float x = __ldcg(row + 32 + lane);
-            if (EXTRA && lane >= 30) a1 += (double)__float_as_int(x);
-            else if (32 + lane < N) a1 += (double)x;
+    constexpr bool HI = (N > 32) || EXTRA;
+    for (unsigned base = warp; base < R; base += PT_WARPS * 8) {
+        float x0[8], x1[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const unsigned b = base + (unsigned)i * PT_WARPS;
+            const bool ok = b < R;
+            const float* row = rows + (size_t)(ok ? b : base) * 64;
+            x0[i] = (ok && lane < N) ? __ldcg(row + lane) : 0.f;
+            if (HI) x1[i] = ok ? __ldcg(row + 32 + lane) : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a0 += (double)x0[i];
+            if (HI) {
+                if (EXTRA && lane >= 30) a1 += (double)__float_as_int(x1[i]);
+                else if (32 + lane < N) a1 += (double)x1[i];
+            }
         }
     }
     ws[warp][lane] = a0; ws[warp][32 + lane] = a1;
     __syncthreads();
     if (threadIdx.x < 64) {
-        double s = 0;
+        double s2 = 0;
 #pragma unroll
-        for (int w = 0; w < PT_WARPS; ++w) s += ws[w][threadIdx.x];
-        tot[threadIdx.x] = s;
+        for (int w = 0; w < PT_WARPS; ++w) s2 += ws[w][threadIdx.x];
+        tot[threadIdx.x] = s2;
     }
     __syncthreads();
 }
@@ -428,70 +441,143 @@ MF_D bool rgbValidPixel(const uint8_t* __restrict__ nextImage, const short2* __r
     return valid;
 }
 
-// host part of one Gauss-Newton iteration (RGBDOdometry.cpp:403-474) on the replicated state
-MF_D void solveAndUpdate(TrackState* st, const double* tot, bool ICP, bool RGB, float icpWeight, Cam cam)
+// unpivoted, unrolled 3x3 LDL^T for the SO(3) step (same contract as ldltSolve6Fast)
+__device__ __forceinline__ bool ldltSolve3Fast(const double* A, const double* b, double* x)
 {
-    float A_icp[36], b_icp[6], A_rgb[36], b_rgb[6];
-    for (int k = 0; k < 36; ++k) { A_icp[k] = 0; A_rgb[k] = 0; }
-    for (int k = 0; k < 6; ++k) { b_icp[k] = 0; b_rgb[k] = 0; }
-    int q = 0;
-    for (int a = 0; a < 6; ++a) for (int b = a; b < 7; ++b) {
-        float vi = (float)tot[q], vr = (float)tot[NACC_ICP + q]; ++q;
-        if (b == 6) { b_icp[a] = vi; b_rgb[a] = vr; }
-        else { A_icp[b * 6 + a] = A_icp[a * 6 + b] = vi; A_rgb[b * 6 + a] = A_rgb[a * 6 + b] = vr; }
-    }
-    if (ICP) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
-    double A[36], b[6], result[6];
-    if (ICP && RGB) {
-        double wgt = icpWeight;
-        for (int k = 0; k < 36; ++k) A[k] = (double)A_rgb[k] + wgt * wgt * (double)A_icp[k];
-        for (int k = 0; k < 6; ++k) b[k] = (double)b_rgb[k] + wgt * (double)b_icp[k];
-    } else if (ICP) {
-        for (int k = 0; k < 36; ++k) A[k] = A_icp[k];
-        for (int k = 0; k < 6; ++k) b[k] = b_icp[k];
-    } else {
-        for (int k = 0; k < 36; ++k) A[k] = A_rgb[k];
-        for (int k = 0; k < 6; ++k) b[k] = b_rgb[k];
-    }
-    for (int k = 0; k < 36; ++k) st->lastA[k] = A[k];
-    for (int k = 0; k < 6; ++k) st->lastb[k] = b[k];
-    if (!ldltSolve6Fast(A, b, result)) ldltSolve(A, b, 6, result);
-    // computeUpdateSE3 (OdometryProvider.h:69-90)
-    double Rt[16], Rup[9];
-    for (int k = 0; k < 16; ++k) Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
-    rodrigues(&result[3], Rup);
-    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) Rt[r * 4 + c] = Rup[r * 3 + c]; Rt[r * 4 + 3] = result[r]; }
-    double nr[16];
-    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) {
-        double s = 0;
-        for (int k = 0; k < 4; ++k) s += Rt[r * 4 + k] * st->resultRt[k * 4 + c];
-        nr[r * 4 + c] = s;
-    }
-    for (int k = 0; k < 16; ++k) st->resultRt[k] = nr[k];
-    float trR[9], trT[3];
-    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) trR[r * 3 + c] = (float)nr[r * 4 + c]; trT[r] = (float)nr[r * 4 + 3]; }
-    for (int k = 0; k < 9; ++k) st->trR[k] = trR[k];
-    for (int k = 0; k < 3; ++k) st->trT[k] = trT[k];
-    // currentT = [Rprev|tprev] * transform^-1   (RGBDOdometry.cpp:466-474)
-    float iR[9], iT[3];
-    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) iR[r * 3 + c] = trR[c * 3 + r];
-    for (int r = 0; r < 3; ++r) iT[r] = -((iR[r * 3] * trT[0] + iR[r * 3 + 1] * trT[1]) + iR[r * 3 + 2] * trT[2]);
-    for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) st->Rcurr[r * 3 + c] = (st->Rprev[r * 3] * iR[c] + st->Rprev[r * 3 + 1] * iR[3 + c]) + st->Rprev[r * 3 + 2] * iR[6 + c];
-        st->tcurr[r] = ((st->Rprev[r * 3] * iT[0] + st->Rprev[r * 3 + 1] * iT[1]) + st->Rprev[r * 3 + 2] * iT[2]) + st->tprev[r];
-    }
-    if (RGB) computeWarp(st, cam);          // warp constants for the next iteration's residuals
+    double maxDiag = fmax(fabs(A[0]), fmax(fabs(A[4]), fabs(A[8])));
+    const double tiny = maxDiag * 1e-12;
+    double d0 = A[0];
+    if (!(maxDiag > 0) || !(d0 > tiny)) return false;
+    double l10 = A[3] / d0, l20 = A[6] / d0;
+    double d1 = A[4] - l10 * l10 * d0;
+    if (!(d1 > tiny)) return false;
+    double l21 = (A[7] - l20 * l10 * d0) / d1;
+    double d2 = A[8] - l20 * l20 * d0 - l21 * l21 * d1;
+    if (!(d2 > tiny)) return false;
+    double y0 = b[0], y1 = b[1] - l10 * y0, y2 = b[2] - l20 * y0 - l21 * y1;
+    y0 /= d0; y1 /= d1; y2 /= d2;
+    x[2] = y2; x[1] = y1 - l21 * x[2]; x[0] = y0 - l10 * x[1] - l20 * x[2];
+    return true;
 }
+
+// entry e of the inverse of a 3x3 (cofactor form of inv3d: every lane evaluates the same determinant)
+MF_D double inv3dEntry(const double* M, int e)
+{
+    double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    double det = M[0] * c00 + M[1] * c01 + M[2] * c02, id = 1.0 / det;
+    double v;
+    switch (e) {
+        case 0: v = c00; break;
+        case 1: v = M[2] * M[7] - M[1] * M[8]; break;
+        case 2: v = M[1] * M[5] - M[2] * M[4]; break;
+        case 3: v = c01; break;
+        case 4: v = M[0] * M[8] - M[2] * M[6]; break;
+        case 5: v = M[2] * M[3] - M[0] * M[5]; break;
+        case 6: v = c02; break;
+        case 7: v = M[1] * M[6] - M[0] * M[7]; break;
+        default: v = M[0] * M[4] - M[1] * M[3]; break;
+    }
+    return v * id;
+}
+
+struct SolveScratch { double A[36], b[6], x[6], Rt[16], nr[16], Ri[9], Kinv[9], tmp[9], ti[3]; float trR[9], trT[3], iR[9], iT[3]; int fast; };
+
+// computeWarp (RGBDOdometry.cpp:364-376) by one warp: every matrix entry keeps the scalar routine's formula, lanes take entries
+MF_D void computeWarpCoop(TrackState* st, Cam c, SolveScratch* sc, int lane)
+{
+    const double* T = st->resultRt;
+    const double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1};
+    if (lane < 9) {
+        double R3[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+        sc->Ri[lane] = inv3dEntry(R3, lane);
+        sc->Kinv[lane] = inv3dEntry(K, lane);
+    }
+    __syncwarp();
+    if (lane < 3) sc->ti[lane] = -(sc->Ri[lane * 3] * T[3] + sc->Ri[lane * 3 + 1] * T[7] + sc->Ri[lane * 3 + 2] * T[11]);
+    if (lane < 9) { int r = lane / 3, cc = lane % 3; sc->tmp[lane] = K[r * 3] * sc->Ri[cc] + K[r * 3 + 1] * sc->Ri[3 + cc] + K[r * 3 + 2] * sc->Ri[6 + cc]; }
+    __syncwarp();
+    if (lane < 9) { int r = lane / 3, cc = lane % 3; st->krk[lane] = (float)(sc->tmp[r * 3] * sc->Kinv[cc] + sc->tmp[r * 3 + 1] * sc->Kinv[3 + cc] + sc->tmp[r * 3 + 2] * sc->Kinv[6 + cc]); }
+    if (lane < 3) st->kt[lane] = (float)(K[lane * 3] * sc->ti[0] + K[lane * 3 + 1] * sc->ti[1] + K[lane * 3 + 2] * sc->ti[2]);
+    __syncwarp();
+}
+
+// host part of one Gauss-Newton iteration (RGBDOdometry.cpp:403-474) on the replicated state, executed by warp 0:
+// the serial LDL^T stays on lane 0, everything around it (normal equations, SE(3) update, warp constants) is spread over lanes.
+// (One thread doing all of it cost ~5 us per iteration with its matrices in local memory, ncu r01c.)
+__device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, bool ICP, bool RGB, float icpWeight, Cam cam, SolveScratch* sc)
+{
+    const int lane = threadIdx.x & 31;
+    const double wgt = icpWeight;
+    for (int e = lane; e < 42; e += 32) {
+        const bool isA = e < 36;
+        int r = isA ? e / 6 : e - 36, c2 = isA ? e % 6 : 6;
+        int a = r < c2 ? r : c2, b = r < c2 ? c2 : r;
+        int q = 7 * a - (a * (a - 1)) / 2 + (b - a);
+        float vi = (float)tot[q], vr = (float)tot[NACC_ICP + q];
+        double v;
+        if (ICP && RGB) v = isA ? (double)vr + wgt * wgt * (double)vi : (double)vr + wgt * (double)vi;
+        else if (ICP) v = (double)vi;
+        else v = (double)vr;
+        if (isA) { sc->A[e] = v; st->lastA[e] = v; } else { sc->b[r] = v; st->lastb[r] = v; }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (ICP) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
+        double result[6];
+        if (!ldltSolve6Fast(sc->A, sc->b, result)) ldltSolve(sc->A, sc->b, 6, result);
+        // computeUpdateSE3 (OdometryProvider.h:69-90)
+        double Rup[9];
+        rodrigues(&result[3], Rup);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) sc->Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sc->Rt[r * 4 + c] = Rup[r * 3 + c];
+            sc->Rt[r * 4 + 3] = result[r];
+        }
+    }
+    __syncwarp();
+    double nrv = 0;
+    if (lane < 16) {
+        int r = lane >> 2, c = lane & 3;
+        double s2 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s2 += sc->Rt[r * 4 + k] * st->resultRt[k * 4 + c];
+        nrv = s2;
+    }
+    __syncwarp();
+    if (lane < 16) { st->resultRt[lane] = nrv; sc->nr[lane] = nrv; }
+    __syncwarp();
+    if (lane < 9) { float v = (float)sc->nr[(lane / 3) * 4 + lane % 3]; sc->trR[lane] = v; st->trR[lane] = v; }
+    else if (lane < 12) { float v = (float)sc->nr[(lane - 9) * 4 + 3]; sc->trT[lane - 9] = v; st->trT[lane - 9] = v; }
+    __syncwarp();
+    // currentT = [Rprev|tprev] * transform^-1   (RGBDOdometry.cpp:466-474)
+    if (lane < 9) sc->iR[lane] = sc->trR[(lane % 3) * 3 + lane / 3];
+    __syncwarp();
+    if (lane < 3) sc->iT[lane] = -((sc->iR[lane * 3] * sc->trT[0] + sc->iR[lane * 3 + 1] * sc->trT[1]) + sc->iR[lane * 3 + 2] * sc->trT[2]);
+    __syncwarp();
+    if (lane < 9) { int r = lane / 3, c = lane % 3; st->Rcurr[lane] = (st->Rprev[r * 3] * sc->iR[c] + st->Rprev[r * 3 + 1] * sc->iR[3 + c]) + st->Rprev[r * 3 + 2] * sc->iR[6 + c]; }
+    else if (lane < 12) { int r = lane - 9; st->tcurr[r] = ((st->Rprev[r * 3] * sc->iT[0] + st->Rprev[r * 3 + 1] * sc->iT[1]) + st->Rprev[r * 3 + 2] * sc->iT[2]) + st->tprev[r]; }
+    __syncwarp();
+    if (RGB) computeWarpCoop(st, cam, sc, lane);          // warp constants for the next iteration's residuals
+}
+
+// pose-independent inputs of one pixel in phase A (prefetched one round ahead: the pose-dependent gathers of the current
+// pixel and the streaming loads of the next one are in flight together)
+struct PixA { float4 vc, nc; float d1; int valid, ni; };
+struct PixB { DataTerm ct; short2 g; };
 
 __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackPoses poses, TrackParams tp)
 {
     __shared__ TrackJob J;
     __shared__ TrackState S;
+    __shared__ SolveScratch sc;
     __shared__ float red[PT_WARPS][64];
     __shared__ double ws[PT_WARPS][64];
     __shared__ double tot[64];
-    __shared__ float so3B[9], so3Kinv[9], so3Krlr[9];
     __shared__ double totR[64];
+    __shared__ float so3B[9], so3Kinv[9], so3Krlr[9];
     __shared__ int flag;
     {   // job record -> shared memory (one coalesced read instead of dependent pointer chases in every phase)
         const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + blockIdx.y);
@@ -500,7 +586,6 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     }
     TrackState* st = &S;
     const unsigned G = gridDim.x;
-    const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)G * PT_THREADS;
     unsigned gen = 0;                                                  // barriers passed (uniform)
     if (threadIdx.x == 0) {
         // RGBDOdometry.cpp:331-345 initial state
@@ -525,6 +610,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     // ---------------- SO(3) pre-alignment on level-2 intensities (RGBDOdometry.cpp:272-345) ----------------
     if (tp.so3) {
         const int W = tp.W >> 2, H = tp.H >> 2, N = W * H;
+        // CTAs beyond the pixel count only wait at the barriers: fewer partial rows to sum
+        const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
+        const bool active = blockIdx.x < Gact;
+        const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
         const Cam c = camLevel(tp.cam, 2);
         const uint8_t* __restrict__ lastImage = J.lastNextImage2;
         const uint8_t* __restrict__ nextImage = J.nextImage[2];
@@ -535,45 +624,47 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 for (int q = 0; q < 9; ++q) { so3B[q] = (float)hom[q]; so3Kinv[q] = (float)Kinv[q]; so3Krlr[q] = (float)kr[q]; }
             }
             __syncthreads();
-            float acc[11];
-#pragma unroll
-            for (int k = 0; k < 11; ++k) acc[k] = 0;
-            for (int k = tid; k < N; k += nthr) {
-                int y = k / W, x = k - y * W;
-                float3 ur = make_float3((float)x, (float)y, 1.0f);
-                float3 wr = m3v(so3B, ur);
-                int wx = __float2int_rn(wr.x / wr.z), wy = __float2int_rn(wr.y / wr.z);
-                bool found = (wx >= 1 && wx < W - 1 && wy >= 1 && wy < H - 1 && x >= 1 && x < W - 1 && y >= 1 && y < H - 1);
-                if (found) {
-                    float gnx, gny, glx, gly;
-                    gradU8(nextImage, W, wx, wy, gnx, gny);
-                    gradU8(lastImage, W, x, y, glx, gly);
-                    float gx = (gnx + glx) / 2.0f, gy = (gny + gly) / 2.0f;
-                    float3 p = m3v(so3Kinv, ur);
-                    float z2 = p.z * p.z;
-                    float a = so3Krlr[0], b = so3Krlr[1], cc = so3Krlr[2], d = so3Krlr[3], e = so3Krlr[4], f = so3Krlr[5], g = so3Krlr[6], h = so3Krlr[7], i = so3Krlr[8];
-                    float fy = (float)y, fxx = (float)x;
-                    float3 l = make_float3(((p.z * (d * gy + a * gx)) - (gy * g * fy) - (gx * g * fxx)) / z2,
-                                           ((p.z * (e * gy + b * gx)) - (gy * h * fy) - (gx * h * fxx)) / z2,
-                                           ((p.z * (f * gy + cc * gx)) - (gy * i * fy) - (gx * i * fxx)) / z2);
-                    float row[4];
-                    row[0] = l.y * p.z - l.z * p.y;
-                    row[1] = l.z * p.x - l.x * p.z;
-                    row[2] = l.x * p.y - l.y * p.x;
-                    row[3] = -((float)nextImage[wy * W + wx] - (float)lastImage[k]);
-                    int q = 0;
-#pragma unroll
-                    for (int ii = 0; ii < 3; ++ii)
-#pragma unroll
-                        for (int jj = ii; jj < 4; ++jj) acc[q++] += row[ii] * row[jj];
-                    acc[9] += row[3] * row[3];
-                    acc[10] += 1.0f;
-                }
-            }
             float* rows = rowsBuf[gen & 1];
-            ctaReduceStore<11>(acc, red, rows + (size_t)blockIdx.x * 64);
+            if (active) {
+                float acc[11];
+#pragma unroll
+                for (int k = 0; k < 11; ++k) acc[k] = 0;
+                for (int k = tid; k < N; k += nthr) {
+                    int y = k / W, x = k - y * W;
+                    float3 ur = make_float3((float)x, (float)y, 1.0f);
+                    float3 wr = m3v(so3B, ur);
+                    int wx = __float2int_rn(wr.x / wr.z), wy = __float2int_rn(wr.y / wr.z);
+                    bool found = (wx >= 1 && wx < W - 1 && wy >= 1 && wy < H - 1 && x >= 1 && x < W - 1 && y >= 1 && y < H - 1);
+                    if (found) {
+                        float gnx, gny, glx, gly;
+                        gradU8(nextImage, W, wx, wy, gnx, gny);
+                        gradU8(lastImage, W, x, y, glx, gly);
+                        float gx = (gnx + glx) / 2.0f, gy = (gny + gly) / 2.0f;
+                        float3 p = m3v(so3Kinv, ur);
+                        float z2 = p.z * p.z;
+                        float a = so3Krlr[0], b = so3Krlr[1], cc = so3Krlr[2], d = so3Krlr[3], e = so3Krlr[4], f = so3Krlr[5], g = so3Krlr[6], h = so3Krlr[7], i = so3Krlr[8];
+                        float fy = (float)y, fxx = (float)x;
+                        float3 l = make_float3(((p.z * (d * gy + a * gx)) - (gy * g * fy) - (gx * g * fxx)) / z2,
+                                               ((p.z * (e * gy + b * gx)) - (gy * h * fy) - (gx * h * fxx)) / z2,
+                                               ((p.z * (f * gy + cc * gx)) - (gy * i * fy) - (gx * i * fxx)) / z2);
+                        float row[4];
+                        row[0] = l.y * p.z - l.z * p.y;
+                        row[1] = l.z * p.x - l.x * p.z;
+                        row[2] = l.x * p.y - l.y * p.x;
+                        row[3] = -((float)nextImage[wy * W + wx] - (float)lastImage[k]);
+                        int q = 0;
+#pragma unroll
+                        for (int ii = 0; ii < 3; ++ii)
+#pragma unroll
+                            for (int jj = ii; jj < 4; ++jj) acc[q++] += row[ii] * row[jj];
+                        acc[9] += row[3] * row[3];
+                        acc[10] += 1.0f;
+                    }
+                }
+                ctaReduceStore<11>(acc, red, rows + (size_t)blockIdx.x * 64);
+            }
             ++gen; gridBarrier(bar, gen * G);
-            sumRows<11, false>(rows, G, ws, tot);
+            sumRows<11, false>(rows, Gact, ws, tot);
             if (threadIdx.x == 0) {
                 // host logic of RGBDOdometry.cpp:301-324
                 int done = 0;
@@ -587,9 +678,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 } else {
                     st->so3LastError = st->lastSO3Error; st->so3LastCount = st->lastSO3Count;
                     for (int q = 0; q < 9; ++q) st->lastResultR[q] = st->resultR[q];
-                    double A[9], bb[3], delta[3]; int q = 0;
-                    for (int ii = 0; ii < 3; ++ii) for (int jj = ii; jj < 4; ++jj) { double v = (double)(float)tot[q++]; if (jj == 3) bb[ii] = v; else A[jj * 3 + ii] = A[ii * 3 + jj] = v; }
-                    ldltSolve(A, bb, 3, delta);
+                    double A[9], bb[3], delta[3];
+                    A[0] = (double)(float)tot[0]; A[1] = A[3] = (double)(float)tot[1]; A[2] = A[6] = (double)(float)tot[2]; bb[0] = (double)(float)tot[3];
+                    A[4] = (double)(float)tot[4]; A[5] = A[7] = (double)(float)tot[5]; bb[1] = (double)(float)tot[6];
+                    A[8] = (double)(float)tot[7]; bb[2] = (double)(float)tot[8];
+                    if (!ldltSolve3Fast(A, bb, delta)) ldltSolve(A, bb, 3, delta);
                     for (int k = 0; k < 3; ++k) delta[k] = (double)(float)delta[k];
                     double ru[9]; rodrigues(delta, ru);
                     float ruf[9], n[9];
@@ -612,6 +705,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     for (int level = 2; level >= 0; --level) {
         if (tp.iterations[level] == 0) continue;
         const int W = tp.W >> level, H = tp.H >> level, N = W * H;
+        const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
+        const bool active = blockIdx.x < Gact;
+        const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
         const Cam cam = camLevel(tp.cam, level);
         const float4* __restrict__ vmapC = J.vmapC[level];
         const float4* __restrict__ nmapC = J.nmapC[level];
@@ -625,57 +721,76 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         const uint8_t* __restrict__ lastImage = J.lastImage[level];
         const uint8_t* __restrict__ nextImage = J.nextImage[level];
         uint8_t* __restrict__ rgbValid = J.rgbValid[level];
-        if (threadIdx.x == 0) { st->levelBreak = 0; st->lastRGBError = FLT_MAX; if (tp.rgb) computeWarp(st, cam); }
-        if (tp.rgb)                                                     // validity is pose independent: once per level, same thread reads it back
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) { st->levelBreak = 0; st->lastRGBError = FLT_MAX; }
+            if (tp.rgb) computeWarpCoop(st, cam, &sc, threadIdx.x);
+        }
+        if (tp.rgb && active)                                           // validity is pose independent: once per level, same thread reads it back
             for (int k = tid; k < N; k += nthr) rgbValid[k] = rgbValidPixel(nextImage, grad, W, H, k, tp.minScale[level]) ? 1 : 0;
         __syncthreads();
         for (int it = 0; it < tp.iterations[level]; ++it) {
             // ---- phase A: photometric correspondences + statistics, ICP normal equations ----
-            float acc[NACC_ICP];
+            float* rowsA = rowsBuf[gen & 1];
+            if (active) {
+                float acc[NACC_ICP];
 #pragma unroll
-            for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.f;
-            int cnt = 0, sig = 0;
-            const float3 tprev = make_float3(st->tprev[0], st->tprev[1], st->tprev[2]);
-            for (int k = tid; k < N; k += nthr) {
-                if (tp.rgb) {
-                    int i = k / W, j0 = k - i * W;
-                    DataTerm c; c.zero = make_short2(0, 0); c.one = make_short2(0, 0); c.diff = 0; c.valid = 0;
-                    if (rgbValid[k]) {
-                        int y = i, x = j0;
-                        float d1 = nextDepth[k];
-                        if (!isnan(d1)) {
-                            const float* K = st->krk; const float* kt = st->kt;
-                            float td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
-                            float fu = (d1 * ((K[0] * x + K[1] * y) + K[2]) + kt[0]) / td1;
-                            float fv = (d1 * ((K[3] * x + K[4] * y) + K[5]) + kt[1]) / td1;
-                            int u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
-                            int v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
-                            if (u0 >= 0 && v0 >= 0 && u0 < W && v0 < H) {
-                                float d0 = lastDepth[v0 * W + u0];
-                                uint8_t li = lastImage[v0 * W + u0];
-                                if (d0 > 0 && fabsf(td1 - d0) <= tp.maxDepthDelta && li != 0) {
-                                    c.zero = make_short2((short)u0, (short)v0); c.one = make_short2((short)x, (short)y);
-                                    c.diff = (float)nextImage[k] - (float)li;
-                                    c.valid = 1;
-                                    cnt += 1;
-                                    sig += (int)(c.diff * c.diff);
-                                }
-                            }
-                        }
-                    }
-                    corres[k] = c;
+                for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.f;
+                int cnt = 0, sig = 0;
+                const float3 tprev = make_float3(st->tprev[0], st->tprev[1], st->tprev[2]);
+                PixA cur, nxt;
+                cur.valid = 0; cur.ni = 0; cur.d1 = 0; cur.vc = make_float4(0, 0, 0, 0); cur.nc = cur.vc; nxt = cur;
+                int k = tid;
+                if (k < N) {
+                    if (tp.rgb) { cur.valid = rgbValid[k]; cur.d1 = nextDepth[k]; cur.ni = nextImage[k]; }
+                    if (tp.icp) { cur.vc = vmapC[k]; cur.nc = nmapC[k]; }
                 }
-                if (tp.icp) {
-                    float4 vc4 = vmapC[k];
-                    float3 vg = m3v(st->Rcurr, make_float3(vc4.x, vc4.y, vc4.z));
-                    vg = make_float3(vg.x + st->tcurr[0], vg.y + st->tcurr[1], vg.z + st->tcurr[2]);
-                    float3 tmp = sub3(vg, tprev);
-                    float3 vcp = m3v(st->RprevInv, tmp);
-                    int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
-                    int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
-                    if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) {
-                        int j = uy * W + ux;
-                        float4 vp4 = __ldg(vmapG + j), np4 = __ldg(nmapG + j), nc4 = nmapC[k];
+                while (k < N) {
+                    const int kn = k + nthr;
+                    if (kn < N) {
+                        if (tp.rgb) { nxt.valid = rgbValid[kn]; nxt.d1 = nextDepth[kn]; nxt.ni = nextImage[kn]; }
+                        if (tp.icp) { nxt.vc = vmapC[kn]; nxt.nc = nmapC[kn]; }
+                    }
+                    // pose-dependent addresses of both gathers first, then the gathers, then the arithmetic
+                    bool rOK = false, iOK = false; int jr = 0, ji = 0, u0 = 0, v0 = 0;
+                    const int y = k / W, x = k - y * W;
+                    float td1 = 0;
+                    if (tp.rgb && cur.valid && !isnan(cur.d1)) {
+                        const float* K = st->krk; const float* kt = st->kt;
+                        const float d1 = cur.d1;
+                        td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
+                        float fu = (d1 * ((K[0] * x + K[1] * y) + K[2]) + kt[0]) / td1;
+                        float fv = (d1 * ((K[3] * x + K[4] * y) + K[5]) + kt[1]) / td1;
+                        u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
+                        v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
+                        if (u0 >= 0 && v0 >= 0 && u0 < W && v0 < H) { rOK = true; jr = v0 * W + u0; }
+                    }
+                    float3 vg = make_float3(0, 0, 0), vcp = vg;
+                    if (tp.icp) {
+                        vg = m3v(st->Rcurr, make_float3(cur.vc.x, cur.vc.y, cur.vc.z));
+                        vg = make_float3(vg.x + st->tcurr[0], vg.y + st->tcurr[1], vg.z + st->tcurr[2]);
+                        float3 tmp = sub3(vg, tprev);
+                        vcp = m3v(st->RprevInv, tmp);
+                        int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
+                        int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
+                        if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) { iOK = true; ji = uy * W + ux; }
+                    }
+                    float d0 = 0; int li = 0;
+                    float4 vp4 = make_float4(0, 0, 0, 0), np4 = vp4;
+                    if (rOK) { d0 = lastDepth[jr]; li = lastImage[jr]; }
+                    if (iOK) { vp4 = __ldg(vmapG + ji); np4 = __ldg(nmapG + ji); }
+                    if (tp.rgb) {
+                        DataTerm c; c.zero = make_short2(0, 0); c.one = make_short2(0, 0); c.diff = 0; c.valid = 0;
+                        if (rOK && d0 > 0 && fabsf(td1 - d0) <= tp.maxDepthDelta && li != 0) {
+                            c.zero = make_short2((short)u0, (short)v0); c.one = make_short2((short)x, (short)y);
+                            c.diff = (float)cur.ni - (float)li;
+                            c.valid = 1;
+                            cnt += 1;
+                            sig += (int)(c.diff * c.diff);
+                        }
+                        corres[k] = c;
+                    }
+                    if (iOK) {
+                        const float4 nc4 = cur.nc;
                         float3 vp = make_float3(vp4.x, vp4.y, vp4.z), np_ = make_float3(np4.x, np4.y, np4.z);
                         float3 ng = m3v(st->Rcurr, make_float3(nc4.x, nc4.y, nc4.z));
                         float3 d = sub3(vp, vg);
@@ -702,13 +817,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                             acc[28] += 1.0f;
                         }
                     }
+                    cur = nxt; k = kn;
                 }
+                ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * 64, cnt, sig, true);
             }
-            __syncthreads();                                            // everyone has read the state before thread 0 rewrites it below
-            float* rowsA = rowsBuf[gen & 1];
-            ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * 64, cnt, sig, true);
             ++gen; gridBarrier(bar, gen * G);
-            sumRows<NACC_ICP, true>(rowsA, G, ws, tot);
+            sumRows<NACC_ICP, true>(rowsA, Gact, ws, tot);
             if (tp.rgb) {
                 if (threadIdx.x == 0) {
                     // RGBDOdometry.cpp:388-401
@@ -727,46 +841,55 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 __syncthreads();
                 if (flag) break;                                        // uniform over the whole grid: every CTA holds the same state
                 // ---- phase B: photometric normal equations with the weights of this iteration ----
-                float accR[NACC_RGB];
-#pragma unroll
-                for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.f;
-                const float sigmaSh = st->sigmaVal;
-                for (int k = tid; k < N; k += nthr) {
-                    DataTerm ct = corres[k];
-                    if (ct.valid) {
-                        float w = sigmaSh + fabsf(ct.diff);
-                        w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
-                        if (sigmaSh == -1) w = 1;
-                        float row[7];
-                        row[6] = -w * ct.diff;
-                        float4 cp = cloud[ct.zero.y * W + ct.zero.x];
-                        float invz = (float)(1.0 / (double)cp.z);
-                        short2 g = grad[ct.one.y * W + ct.one.x];
-                        float dIdx_v = w * tp.sobelScale * (float)g.x;
-                        float dIdy_v = w * tp.sobelScale * (float)g.y;
-                        float v0 = dIdx_v * cam.fx * invz;
-                        float v1 = dIdy_v * cam.fy * invz;
-                        float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
-                        row[0] = v0; row[1] = v1; row[2] = v2;
-                        row[3] = -cp.z * v1 + cp.y * v2;
-                        row[4] = cp.z * v0 - cp.x * v2;
-                        row[5] = -cp.y * v0 + cp.x * v1;
-                        int q = 0;
-#pragma unroll
-                        for (int a = 0; a < 6; ++a)
-#pragma unroll
-                            for (int b = a; b < 7; ++b) accR[q++] += row[a] * row[b];
-                    }
-                }
                 float* rowsB = rowsBuf[gen & 1];
-                ctaReduceStore<NACC_RGB>(accR, red, rowsB + (size_t)blockIdx.x * 64);
+                if (active) {
+                    float accR[NACC_RGB];
+#pragma unroll
+                    for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.f;
+                    const float sigmaSh = st->sigmaVal;
+                    PixB cur, nxt;
+                    cur.ct.valid = 0; cur.ct.diff = 0; cur.ct.zero = make_short2(0, 0); cur.ct.one = cur.ct.zero; cur.g = make_short2(0, 0); nxt = cur;
+                    int k = tid;
+                    if (k < N) { cur.ct = corres[k]; cur.g = grad[k]; }
+                    while (k < N) {
+                        const int kn = k + nthr;
+                        if (kn < N) { nxt.ct = corres[kn]; nxt.g = grad[kn]; }
+                        const DataTerm ct = cur.ct;
+                        if (ct.valid) {
+                            float4 cp = cloud[ct.zero.y * W + ct.zero.x];
+                            float w = sigmaSh + fabsf(ct.diff);
+                            w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+                            if (sigmaSh == -1) w = 1;
+                            float row[7];
+                            row[6] = -w * ct.diff;
+                            float invz = (float)(1.0 / (double)cp.z);
+                            short2 g = cur.g;                            // == grad[one]: `one` is this pixel (reduce.cu:934)
+                            float dIdx_v = w * tp.sobelScale * (float)g.x;
+                            float dIdy_v = w * tp.sobelScale * (float)g.y;
+                            float v0 = dIdx_v * cam.fx * invz;
+                            float v1 = dIdy_v * cam.fy * invz;
+                            float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
+                            row[0] = v0; row[1] = v1; row[2] = v2;
+                            row[3] = -cp.z * v1 + cp.y * v2;
+                            row[4] = cp.z * v0 - cp.x * v2;
+                            row[5] = -cp.y * v0 + cp.x * v1;
+                            int q = 0;
+#pragma unroll
+                            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                                for (int b = a; b < 7; ++b) accR[q++] += row[a] * row[b];
+                        }
+                        cur = nxt; k = kn;
+                    }
+                    ctaReduceStore<NACC_RGB>(accR, red, rowsB + (size_t)blockIdx.x * 64);
+                }
                 ++gen; gridBarrier(bar, gen * G);
                 // ICP totals stay in tot[0..28]; the photometric ones go behind them
-                sumRows<NACC_RGB, false>(rowsB, G, ws, totR);
+                sumRows<NACC_RGB, false>(rowsB, Gact, ws, totR);
                 if (threadIdx.x < NACC_RGB) tot[NACC_ICP + threadIdx.x] = totR[threadIdx.x];
                 __syncthreads();
             }
-            if (threadIdx.x == 0) solveAndUpdate(st, tot, tp.icp != 0, tp.rgb != 0, tp.icpWeight, cam);
+            if (threadIdx.x < 32) solveAndUpdate(st, tot, tp.icp != 0, tp.rgb != 0, tp.icpWeight, cam, &sc);
             __syncthreads();
         }
         __syncthreads();

@@ -16,6 +16,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+# replay used by the GPU sharding test: objects spawn every 6 frames so that three of them exist after 20 frames; capacities chosen so
+# that the placement rule puts stores on both ranks
+def shard_kw(track_all):
+    return dict(capacityGlobal=1000000, capacityObject=600000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all),
+                modelSpawnOffset=6)
+
+
 def cpu_mode(out_dir):
     import torch
     import torch.distributed as dist
@@ -105,8 +112,7 @@ def gpu_mode(out_dir, nframes, track_all):
     else:
         dist.init_process_group("gloo")
     W, H = 640, 480
-    kw = dict(capacityGlobal=1000000, capacityObject=200000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all))
-    smf = ShardedMaskFusion(mfb.default_config(W, H, **kw), device=dev)
+    smf = ShardedMaskFusion(mfb.default_config(W, H, **shard_kw(track_all)), device=dev)
     sc = SynthScene(W, H, n_objects=3, seed=0)
     cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
     out = {"backend": np.array(dist.get_backend())}
@@ -127,6 +133,7 @@ def gpu_mode(out_dir, nframes, track_all):
     for i, m in enumerate(models):
         if smf.owner(i) == rank:
             out[f"map{i}"] = m.downloadMap()
+    out["bytes_collective"] = np.array(smf.bytes_collective)
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
     smf.close()
     dist.destroy_process_group()
