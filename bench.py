@@ -162,7 +162,8 @@ def run_ours(args, rank, world):
         period = 2 * (nu - 1)
         r = j % period
         return r if r < nu else period - r
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # explicit: the default stream's NULL handle would make mf_create open a private stream the events cannot see
+    torch.cuda.set_stream(stream)
     cfg = mfb.default_config(W, H, capacityGlobal=CAPACITY)        # GUI defaults: ICP+RGB (w=20), SO3, -static
     mf = mfb.MaskFusion(cfg, device=local, stream=stream.cuda_stream)
     rgb0, d0, ts0 = frames[0]

@@ -22,7 +22,14 @@ extern "C" int mf_abi_version(void) { return MF_ABI_VERSION; }
     } catch (const CudaError& e) { g_err = e.what; return ret; }                   \
     catch (const std::exception& e) { g_err = e.what(); return ret; }              \
     catch (...) { g_err = "unknown error"; return ret; }
-#define MF_NEED(ctx) if (!(ctx) || !(ctx)->mf) { g_err = "null context"; return -1; }
+// every entry point first picks up a tracked pose that is still in flight (-static frames return before it has arrived)
+static int mf_finalise(mf_context* ctx)
+{
+    try { ctx->mf->finalisePending(); return 0; }
+    catch (const CudaError& e) { g_err = e.what; return -1; }
+    catch (...) { g_err = "unknown error"; return -1; }
+}
+#define MF_NEED(ctx) if (!(ctx) || !(ctx)->mf) { g_err = "null context"; return -1; } if (mf_finalise(ctx) != 0) return -1;
 #define MF_MODEL(ctx, i) if ((i) < 0 || (i) >= (int)(ctx)->mf->models.size()) { g_err = "model index out of range"; return -2; } Model* m = (ctx)->mf->models[i].get();
 
 #define MF_OWNED(m) if (!(m)->owned) { g_err = "model is owned by another rank (sharded mode): no device buffers here"; return -4; }
@@ -150,6 +157,7 @@ extern "C" int mf_model_perform_tracking(mf_context* ctx, int i, float* transfor
     MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     std::vector<Model*> ms{m};
     ctx->mf->trackModels(ms);
+    ctx->mf->finalisePending();
     if (transform16) toColMajor(m->lastTransform, transform16);
     return 0;
     MF_CATCH(-1)
@@ -360,6 +368,7 @@ extern "C" int mf_debug_set_poses(mf_context* ctx, int i, const float* pose16, c
 {
     MF_NEED(ctx) MF_MODEL(ctx, i)
     m->pose = fromColMajor(pose16); m->lastPose = fromColMajor(last16);
+    m->pushPose();
     return 0;
 }
 extern "C" int mf_icp_step(mf_context* ctx, int i, int level, const float* Rcurr9, const float* tcurr3, float* out29)

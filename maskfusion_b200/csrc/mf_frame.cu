@@ -180,10 +180,11 @@ MF_D float4 packv(float3 v, bool ok) { return ok ? make_float4(v.x, v.y, v.z, 0.
 
 __global__ void k_model_maps(const float4* __restrict__ srcV_pred, const float4* __restrict__ srcN_pred,
                              const float4* __restrict__ srcV_fill, const float4* __restrict__ srcN_fill,
-                             const uint32_t* __restrict__ nonBlack, float denom, int W, int H, Rt pose, float maxDepthRGB,
+                             const uint32_t* __restrict__ nonBlack, float denom, int W, int H, const DevPose* __restrict__ dpose, float maxDepthRGB,
                              float4* __restrict__ v0, float4* __restrict__ n0, float4* __restrict__ v1, float4* __restrict__ n1,
                              float4* __restrict__ v2, float4* __restrict__ n2, float* __restrict__ depth0)
 {
+    const Rt pose = dpose->pose;
     const int W1 = W / 2, H1 = H / 2, W2 = W / 4, H2 = H / 4;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int q = t >> 2, sub = t & 3;
@@ -311,7 +312,7 @@ void launch_sobel(const uint8_t* src, int W, int H, short2* grad, cudaStream_t s
     prof_mark(s, "k_sobel"); k_sobel<<<grid2(W, H, b), b, 0, s>>>(src, W, H, grad);
 }
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
-                       int W, int H, Rt pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s)
+                       int W, int H, const DevPose* pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s)
 {
     int threads = (W / 4) * (H / 4) * 4;
     prof_mark(s, "k_model_maps"); k_model_maps<<<(threads + 127) / 128, 128, 0, s>>>(srcVp, srcNp, srcVf, srcNf, nonBlack, denom, W, H, pose, maxDepthRGB,

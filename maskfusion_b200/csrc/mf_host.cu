@@ -142,13 +142,21 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     cand.alloc((size_t)capacity + P); candCount.alloc(1); candCount.zero(s);
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
-        vmapG[l].alloc(Pl); nmapG[l].alloc(Pl); cloud[l].alloc(Pl); lastDepth[l].alloc(Pl); lastImage[l].alloc(Pl); corres[l].alloc(Pl);
+        vmapG[l].alloc(Pl); nmapG[l].alloc(Pl); cloud[l].alloc(Pl); lastDepth[l].alloc(Pl); lastImage[l].alloc(Pl); corres[l].alloc(l == 0 ? Pl + (size_t)o->numSMs * 512 : 1);   // level 0 only: scratch when the correspondences do not fit in shared memory
         vmapG[l].zero(s); nmapG[l].zero(s); lastDepth[l].zero(s); lastImage[l].zero(s);
     }
     lastNextImage2.alloc((size_t)(W >> 2) * (H >> 2)); lastNextImage2.zero(s);
     trackState.alloc(1); trackState.zero(s);
     partial.alloc((size_t)TRACK_MAX_BLOCKS * 64);
-    o->launches += 2;
+    dpose.alloc(1); pushPose();
+    o->launches += 3;
+}
+
+void Model::pushPose()
+{
+    if (!owned || !dpose.p) return;          // ghosts hold no device state; during construction the buffer appears last
+    launch_set_pose(dpose, pose.m, lastPose.m, owner->stream);
+    owner->launches += 1;
 }
 
 Model::~Model()
@@ -185,7 +193,7 @@ void Model::prepareTracking()
     float4* n[3] = {nmapG[0].p, nmapG[1].p, nmapG[2].p};
     const uint32_t* nb = fillIn ? nonBlack.p : nullptr;
     launch_model_maps(splatVertex, splatNormal, fillIn ? fillVertex.p : splatVertex.p, fillIn ? fillNormal.p : splatNormal.p, nb, denom, W, H,
-                      toRt(pose), 6.0f /* maxDepthRGB, RGBDOdometry.cpp:34 */, v, n, lastDepth[0], s);
+                      dpose, 6.0f /* maxDepthRGB, RGBDOdometry.cpp:34 */, v, n, lastDepth[0], s);
     o->launches += 1;
     const bool rgb = o->cfg.rgbOnly || o->cfg.icpWeight < 100;
     if (rgb) {
@@ -215,7 +223,7 @@ float Model::computeFusionWeight(float weightMultiplier) const
 void Model::predictIndices(int time, float depthCutoff, int timeDelta)
 {
     MaskFusion* o = owner;
-    launch_predict_indices(current(), dCount(), toRt(rigidInverse(pose)), o->cam, o->W, o->H, depthCutoff, time, timeDelta, key, idx, vertConf,
+    launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, time, timeDelta, key, idx, vertConf,
                            colorTime, normRad, o->stream);
     o->launches += 2;
 }
@@ -225,8 +233,8 @@ void Model::fuse(int time, float depthCutoff, float weightMultiplier)
     MaskFusion* o = owner;
     float md = depthCutoff < maxDepth ? depthCutoff : maxDepth;      // Model.cpp:527 (headless: bounding box empty, N7)
     float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
-    launch_associate(o->rgb, o->depthRaw, o->depthFilt, o->mask, idx, vertConf, normRad, toRt(pose), o->cam, o->W, o->H, md, time,
-                     computeFusionWeight(weightMultiplier), id, aflag, abest, m, slot, o->stream);
+    launch_associate(o->rgb, o->depthRaw, o->depthFilt, o->mask, idx, vertConf, normRad, dpose, o->cam, o->W, o->H, md, time,
+                     weightMultiplier, id, aflag, abest, m, slot, o->stream);
     launch_fuse_update(aflag, abest, m, slot, o->P, time, current(), o->stream);
     o->launches += 3;
 }
@@ -236,7 +244,7 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
     MaskFusion* o = owner;
     float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
     int other = 1 - target, otherCount = 1 - countSel;
-    launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, toRt(rigidInverse(pose)), o->cam, o->W, o->H,
+    launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, dpose, o->cam, o->W, o->H,
                  time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, idx, vertConf, colorTime, o->depthFilt, o->mask, keep, blockSums,
                  cand, candCount, o->stream);
     target = other; countSel = otherCount;
@@ -246,7 +254,7 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
 void Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta)
 {
     MaskFusion* o = owner;
-    launch_combined_predict(current(), dCount(), toRt(rigidInverse(pose)), o->cam, o->W, o->H, depthCutoff, confidenceThreshold, time, maxTime,
+    launch_combined_predict(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, confidenceThreshold, time, maxTime,
                             timeDelta, key, splatImage, splatVertex, splatNormal, splatTime, fillIn ? 1 : 0, o->depthFilt, o->rgb, 0,
                             o->cfg.frameToFrameRGB ? 1 : 0, fillImage, fillVertex, fillNormal, fillIn ? nonBlack.p : nullptr, o->stream);
     o->launches += 2;
@@ -298,6 +306,7 @@ MaskFusion::~MaskFusion()
     cudaStreamSynchronize(stream);
     if (g_prof == &prof) g_prof = nullptr;
     for (cudaEvent_t e : prof.events) cudaEventDestroy(e);
+    if (trackDone) cudaEventDestroy(trackDone);
     models.clear();
     if (hJobs) cudaFreeHost(hJobs);
     if (hSmall) cudaFreeHost(hSmall);
@@ -309,6 +318,7 @@ void MaskFusion::sync()
     if (prof.on) prof_mark(stream, nullptr);            // closes the last open interval
     cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
     if (prof.on) prof.resolve();
+    finalisePending();
 }
 
 // textureRGB / textureDepthMetric upload + filterDepth (MaskFusion.cpp:212-217, 650-657)
@@ -352,8 +362,6 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
         if (rgbTerm) { for (int l = 0; l < 3; ++l) launch_sobel(nextImage[l], W >> l, H >> l, nextGrad[l], stream); launches += 3; }
         intensityValid = true;
     }
-    TrackPoses poses;
-    memset(&poses, 0, sizeof poses);
     for (size_t j = 0; j < ms.size(); ++j) {
         Model* m = ms[j];
         m->lastPose = m->pose;                                       // Model.cpp:430
@@ -365,11 +373,11 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
             J.cloud[l] = m->cloud[l]; J.corres[l] = m->corres[l];
         }
         J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.bar = trackBars.p + j * 32;
-        memcpy(poses.p[j], m->pose.m, 16 * sizeof(float));
+        J.dpose = m->dpose;
     }
     prof_mark(stream, "copy_jobs");
     cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
-    launches += launch_tracking(dJobs, (int)ms.size(), poses, W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
+    launches += launch_tracking(dJobs, (int)ms.size(), W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
                                 cfg.so3 != 0, numSMs, trackBars, stream);
     prof_mark(stream, "copy_pose_d2h");
     for (Model* m : ms) {
@@ -378,10 +386,36 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
         if (cfg.so3)   // std::swap(lastNextImage, nextImage) (RGBDOdometry.cpp:484-488): only level 2 is ever read
             cudaCheck(cudaMemcpyAsync(m->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "so3 swap");
     }
-    sync();                                                          // the one host sync of the frame
-    for (Model* m : ms) {
-        memcpy(m->pose.m, m->hTrackOut, 16 * sizeof(float));
-        memcpy(m->lastTransform.m, m->hTrackOut + 16, 16 * sizeof(float));
+    if (!trackDone) cudaCheck(cudaEventCreateWithFlags(&trackDone, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventRecord(trackDone, stream), "cudaEventRecord");
+    pendingModels = ms; pendingTrack = true;
+}
+
+// host copies of the tracked poses: waits for the event behind the tracking kernel only, not for the rest of the frame
+void MaskFusion::finalisePending()
+{
+    if (pendingTrack) {
+        cudaCheck(cudaEventSynchronize(trackDone), "cudaEventSynchronize");
+        for (Model* m : pendingModels) {
+            memcpy(m->pose.m, m->hTrackOut, 16 * sizeof(float));
+            memcpy(m->lastTransform.m, m->hTrackOut + 16, 16 * sizeof(float));
+        }
+        pendingTrack = false; pendingModels.clear();
+    }
+    if (pendingLog) { pendingLog = false; logPoses(pendingTimestamp); }
+}
+
+// MaskFusion.cpp:577-592: one pose-log entry per model per frame
+void MaskFusion::logPoses(int64_t timestamp)
+{
+    Model* g = models[0].get();
+    for (size_t i = 0; i < models.size(); ++i) {
+        Model* m = models[i].get();
+        Mat4 T = (i == 0) ? g->pose : mul(g->pose, rigidInverse(m->pose));     // MaskFusion.cpp:581-583
+        float R[9] = {T.m[0], T.m[1], T.m[2], T.m[4], T.m[5], T.m[6], T.m[8], T.m[9], T.m[10]}, q[4];
+        rotToQuat(R, q);
+        double e[8] = {(double)timestamp, T.m[3], T.m[7], T.m[11], q[0], q[1], q[2], q[3]};
+        m->poseLog.insert(m->poseLog.end(), e, e + 8);
     }
 }
 
@@ -401,7 +435,7 @@ void MaskFusion::projectLocal()
     for (size_t i = 0; i < models.size(); ++i) {
         Model* m = models[i].get();
         if (!m->owned) continue;
-        launch_splat_project_only(m->current(), m->dCount(), toRt(rigidInverse(m->pose)), cam, W, H, cfg.depthCutoff, 12.0f /* :61 */, tick, tick,
+        launch_splat_project_only(m->current(), m->dCount(), m->dpose, cam, W, H, cfg.depthCutoff, 12.0f /* :61 */, tick, tick,
                                   cfg.timeDelta, (uint32_t)i << 26, projKeys, stream);
         launches += 1;
     }
@@ -598,6 +632,7 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
 {
     const bool multi = cfg.enableMultipleModels != 0;
     if (world > 1 && inPose) throw CudaError{"sharded mode tracks every frame (no external poses)"};
+    finalisePending();                                  // previous frame's tracked pose + pose-log entry (its event lies mid-frame: the GPU still has work queued)
     fTimestamp = timestamp; fHasPose = inPose != nullptr; if (inPose) fInPose = *inPose; fBootstrap = bootstrap;
     setFrame(rgbIn, depthIn, nullptr, onDevice);        // -static: textureMask stays all zero (MaskFusion.cpp:223-230); multi: keeps the last segmentation
     frameHasMask = false;
@@ -622,6 +657,8 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
         for (size_t i = 0; i < models.size(); ++i)
             if (models[i]->owned && (i == 0 || models[i]->nonstatic || cfg.trackAllModels)) tracked.push_back(models[i].get());
         trackModels(tracked);
+        // the multi-model schedule takes host decisions on the tracked poses (inactivation, static poses, spawn); so does bootstrap mode
+        if (multi || world > 1 || (bootstrap && inPose)) finalisePending();
     }
 }
 
@@ -682,16 +719,9 @@ void MaskFusion::frameEnd(float weightMultiplier)
     }
     predict();          // MaskFusion.cpp:569 (the call at :423 is dead in open-loop mode: its outputs are overwritten here)
     tick++;
-    g = models[0].get();
-    for (size_t i = 0; i < models.size(); ++i) {
-        Model* m = models[i].get();
-        Mat4 T = (i == 0) ? g->pose : mul(g->pose, rigidInverse(m->pose));     // MaskFusion.cpp:581-583
-        float R[9] = {T.m[0], T.m[1], T.m[2], T.m[4], T.m[5], T.m[6], T.m[8], T.m[9], T.m[10]}, q[4];
-        rotToQuat(R, q);
-        double e[8] = {(double)fTimestamp, T.m[3], T.m[7], T.m[11], q[0], q[1], q[2], q[3]};
-        m->poseLog.insert(m->poseLog.end(), e, e + 8);
-        m->age++;
-    }
+    if (pendingTrack) { pendingLog = true; pendingTimestamp = fTimestamp; }    // -static: the entry is written when the pose arrives
+    else logPoses(fTimestamp);
+    for (auto& m : models) m->age++;
 }
 
 }  // namespace mfb

@@ -64,9 +64,10 @@ public:
     void clean(int time, int timeDelta, float depthCutoff);           // Model::clean
     void combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta);   // Model::combinedPredict + performFillIn
     float computeFusionWeight(float weightMultiplier) const;          // Model::computeFusionWeight
-    void overridePose(const Mat4& p) { lastPose = pose; pose = p; }
+    void overridePose(const Mat4& p) { lastPose = pose; pose = p; pushPose(); }
     void makeStatic(const Mat4& globalPose) { initialC2Winv = mul(pose, rigidInverse(globalPose)); isStatic = true; }
     void updateStaticPose(const Mat4& globalPose) { overridePose(mul(initialC2Winv, globalPose)); }
+    void pushPose();                                                  // host pose/lastPose -> device-resident DevPose (k_set_pose)
     bool allowsFillIn() const { return fillIn; }
     unsigned lastCount();                                             // Model::lastCount (synchronises)
     SurfelPlanes planes(int b) const { return SurfelPlanes{pos[b].p, col[b].p, nrm[b].p}; }
@@ -99,6 +100,7 @@ public:
     DevBuf<float> lastDepth[3]; DevBuf<uint8_t> lastImage[3]; DevBuf<uint8_t> lastNextImage2;
     DevBuf<DataTerm> corres[3];
     DevBuf<TrackState> trackState; DevBuf<float> partial;
+    DevBuf<DevPose> dpose;                  // what every kernel reads: pose, inverse, fusion weight (device resident)
     float* hTrackOut = nullptr;             // pinned: pose(16) transform(16) stats(8)
     Mat4 lastTransform;
     std::vector<double> poseLog;            // 8 doubles per entry
@@ -117,6 +119,12 @@ public:
     void trackModels(const std::vector<Model*>& ms);                                              // performTracking for a batch
     void predict();                                                                               // MaskFusion::predict
     void sync();
+    // The tracked pose reaches the host through an asynchronous copy + event recorded right after the tracking kernel.  The -static
+    // schedule has no host decision that depends on it, so processFrame returns with the rest of the frame enqueued and the pose is
+    // picked up (finalisePending) by the next processFrame / getPose / sync; the multi-model schedule finalises inside the frame.
+    void finalisePending();
+    void logPoses(int64_t timestamp);
+    bool pendingTrack = false, pendingLog = false; int64_t pendingTimestamp = 0; std::vector<Model*> pendingModels; cudaEvent_t trackDone = nullptr;
     // ---- multi-model path (MaskFusion.cpp:287-375) ----
     struct SegmentationResult { bool hasNewLabel = false; int newClassID = -1; };                 // SegmentationResult.h:32-73 (fields the schedule reads)
     void globalProjection();                                                                      // GlobalProjection::project + downloadDirect (stays on the device)

@@ -16,6 +16,75 @@ struct DataTerm { short2 zero; short2 one; float diff; int valid; };
 #define TRACK_MAX_BLOCKS 1024
 struct TrackPoses { float p[TRACK_MAX_JOBS][16]; };
 
+// Pose of one model as the kernels see it: DEVICE resident, so that the passes after tracking (index map, association,
+// fusion, clean, splat) are enqueued without waiting for the tracked pose on the host.  Written by the tracking kernel's
+// epilogue or by k_set_pose (host-driven poses); both run the same derivePose().
+//   pose  : Model::pose, camera -> model frame, row-major [R|t]
+//   tinv  : pose.inverse() as [R^T | -R^T t] (rule R-INV)
+//   fusionW : Model::computeFusionWeight(1.0), Model.cpp:449-464 (the caller's weightMultiplier is applied by the kernel)
+struct DevPose { Rt pose; Rt tinv; float fusionW; float pad[7]; };
+
+#ifdef __CUDACC__
+// Model::rodrigues2 (Model.cpp:890-932) without the SVD re-orthonormalisation (rule R-SVD); R row-major 3x3
+__device__ inline void rodrigues2Dev(const float* R, float* out)
+{
+    double rx = R[7] - R[5], ry = R[2] - R[6], rz = R[3] - R[1];
+    double s = sqrt((rx * rx + ry * ry + rz * rz) * 0.25);
+    double c = ((double)(R[0] + R[4] + R[8]) - 1) * 0.5;
+    c = c > 1. ? 1. : c < -1. ? -1. : c;
+    double theta = acos(c);
+    if (s < 1e-5) {
+        double t;
+        if (c > 0) rx = ry = rz = 0;
+        else {
+            t = (R[0] + 1) * 0.5; rx = sqrt(t > 0 ? t : 0.0);
+            t = (R[4] + 1) * 0.5; ry = sqrt(t > 0 ? t : 0.0) * (R[1] < 0 ? -1.0 : 1.0);
+            t = (R[8] + 1) * 0.5; rz = sqrt(t > 0 ? t : 0.0) * (R[2] < 0 ? -1.0 : 1.0);
+            if (fabs(rx) < fabs(ry) && fabs(rx) < fabs(rz) && (R[5] > 0) != (ry * rz > 0)) rz = -rz;
+            theta /= sqrt(rx * rx + ry * ry + rz * rz);
+            rx *= theta; ry *= theta; rz *= theta;
+        }
+    } else {
+        double vth = 1 / (2 * s); vth *= theta; rx *= vth; ry *= vth; rz *= vth;
+    }
+    out[0] = (float)rx; out[1] = (float)ry; out[2] = (float)rz;
+}
+
+// pose (row-major 4x4, rigid) + the pose before this frame's update -> everything the surfel passes read.
+// One thread.  tinv: [R^T | -R^T t] in fp32 with the operation order of the host rule (R-INV);
+// fusionW: max(1 - max(|t|, |rotation vector|) of (pose^-1 * lastPose) / 0.01, 0.5)  (Model.cpp:449-464)
+__device__ inline void derivePose(DevPose* d, const float* m, const float* last)
+{
+    float inv[16];
+    {
+        const float R[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]}, t[3] = {m[3], m[7], m[11]};
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) inv[r * 4 + c] = R[c * 3 + r];
+            inv[r * 4 + 3] = -((R[0 * 3 + r] * t[0] + R[1 * 3 + r] * t[1]) + R[2 * 3 + r] * t[2]);
+        }
+        inv[12] = 0.f; inv[13] = 0.f; inv[14] = 0.f; inv[15] = 1.f;
+    }
+    for (int k = 0; k < 12; ++k) { d->pose.m[k] = m[k]; d->tinv.m[k] = inv[k]; }
+    // diff = pose^-1 * lastPose, full 4x4 product in the order of the host routine (s += A[r][k] * B[k][c], k = 0..3)
+    float diff[16];
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) {
+            float s = 0;
+            for (int k = 0; k < 4; ++k) s += inv[r * 4 + k] * last[k * 4 + c];
+            diff[r * 4 + c] = s;
+        }
+    const float R[9] = {diff[0], diff[1], diff[2], diff[4], diff[5], diff[6], diff[8], diff[9], diff[10]};
+    float tn = sqrtf((diff[3] * diff[3] + diff[7] * diff[7]) + diff[11] * diff[11]);
+    float rv[3]; rodrigues2Dev(R, rv);
+    float rn = sqrtf((rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]);
+    float weighting = tn > rn ? tn : rn;
+    const float largest = 0.01f, minWeight = 0.5f;
+    if (weighting > largest) weighting = largest;
+    float w = 1.0f - (weighting / largest);
+    d->fusionW = w > minWeight ? w : minWeight;
+}
+#endif
+
 // Gauss-Newton state of one tracked model; lives in device memory for the whole frame
 struct TrackState {
     float Rprev[9], tprev[3], RprevInv[9];
@@ -41,6 +110,7 @@ struct TrackJob {
     const uint8_t* lastNextImage2;
     const float4* cloud[3];
     DataTerm* corres[3];
+    DevPose* dpose;       // initial pose in, tracked pose + derived quantities out
     TrackState* st;
     float* partial;       // 2 x (TRACK_MAX_BLOCKS / 2) rows of 64 floats: per-CTA partial sums, ping-pong between reductions
     unsigned* bar;        // grid barrier counter of this job (own 128-byte line)
@@ -60,25 +130,26 @@ void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s);
 void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s);
 void launch_sobel(const uint8_t* src, int W, int H, short2* grad, cudaStream_t s);
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
-                       int W, int H, Rt pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s);
+                       int W, int H, const DevPose* dpose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s);
 void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s);
 void launch_project_points(const float* depth, int W, int H, Cam cam, float4* cloud, cudaStream_t s);
 
 // ---- mf_surfel.cu ----
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s);
 void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s);
-void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, int time,
+void launch_set_pose(DevPose* d, const float* pose16, const float* lastPose16, cudaStream_t s);      // host-driven pose -> DevPose
+void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, int time,
                             int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, cudaStream_t s);
 void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
-                      const float4* vertConf, const float4* normRad, Rt pose, Cam cam, int W, int H, float maxDepth, int time,
-                      float weighting, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s);
+                      const float4* vertConf, const float4* normRad, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, int time,
+                      float weightMultiplier, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s);
 void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const* meas, uint32_t* slot, int P, int time,
                         const SurfelPlanes& sp, cudaStream_t s);
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
-                  const uint8_t* aflag, float4* const* meas, Rt tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
+                  const uint8_t* aflag, float4* const* meas, const DevPose* dpose, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s);
-void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth,
+void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth,
                              float confThreshold, int time, int maxTime, int timeDelta, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
                              uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s);
@@ -89,7 +160,7 @@ void launch_planes_to_aos(const SurfelPlanes& sp, uint32_t n, float4* out, cudaS
 void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, cudaStream_t s);
 
 // ---- mf_track.cu ----
-int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
+int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
                     bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s);
 void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,
                      const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s);
@@ -113,6 +184,6 @@ void launch_mask_overlap(const uint8_t* seg, const uint8_t* projID, const uint8_
 void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, int P, uint8_t* out, cudaStream_t s);
 void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, int nMasks, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s);
 void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s);
-void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, float confThreshold,
+void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, float confThreshold,
                                int time, int maxTime, int timeDelta, uint32_t drawBase, uint64_t* key, cudaStream_t s);
 }  // namespace mfb

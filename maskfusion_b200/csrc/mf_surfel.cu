@@ -26,10 +26,11 @@ namespace mfb {
 // index map
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_index_project(const float4* __restrict__ pos, const float4* __restrict__ col,
-                                                       const uint32_t* __restrict__ countPtr, Rt tinv, Cam cam, int W, int H,
+                                                       const uint32_t* __restrict__ countPtr, const DevPose* __restrict__ dpose, Cam cam, int W, int H,
                                                        float maxDepth, float ftime, float ftimeDelta,
                                                        unsigned long long* __restrict__ key)
 {
+    const Rt tinv = dpose->tinv;
     const uint32_t count = *countPtr;
     for (uint32_t id = blockIdx.x * blockDim.x + threadIdx.x; id < count; id += gridDim.x * blockDim.x) {
         float4 p = ldStream(pos + id);
@@ -49,9 +50,10 @@ __global__ void __launch_bounds__(256) k_index_project(const float4* __restrict_
 }
 
 __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
-                                Rt tinv, int P, unsigned long long* __restrict__ key, uint32_t* __restrict__ idx,
+                                const DevPose* __restrict__ dpose, int P, unsigned long long* __restrict__ key, uint32_t* __restrict__ idx,
                                 float4* __restrict__ vertConf, float4* __restrict__ colorTime, float4* __restrict__ normRad)
 {
+    const Rt tinv = dpose->tinv;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     unsigned long long k = key[i];
@@ -104,8 +106,8 @@ MF_D float3 normalForward(const float* __restrict__ depth, int W, int H, int tx,
 __global__ void __launch_bounds__(256) k_associate(const uchar4* __restrict__ rgb, const float* __restrict__ depthRaw,
                                                    const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
                                                    const uint32_t* __restrict__ idx, const float4* __restrict__ vertConf,
-                                                   const float4* __restrict__ normRad, Rt pose, Cam cam, int W, int H,
-                                                   float maxDepth, int time, float weighting, uint8_t maskID,
+                                                   const float4* __restrict__ normRad, const DevPose* __restrict__ dpose, Cam cam, int W, int H,
+                                                   float maxDepth, int time, float weightMultiplier, uint8_t maskID,
                                                    uint8_t* __restrict__ flag, uint32_t* __restrict__ best,
                                                    float4* __restrict__ m0, float4* __restrict__ m1, float4* __restrict__ m2,
                                                    uint32_t* __restrict__ slot)
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(256) k_associate(const uchar4* __restrict__ rg
                depthRaw[j * W + clampi(i + 1, 0, W - 1)] != 0 && depthRaw[clampi(j + 1, 0, H - 1) * W + i] != 0;
     }
     if (cand) {
+        const Rt pose = dpose->pose;
+        const float weighting = dpose->fusionW * weightMultiplier;          // Model::computeFusionWeight (Model.cpp:449-464)
         float3 vg = xform(pose, vl);
         float3 vf = getVertex(depthFilt, W, H, i, j, x, y, cam, ifx, ify);
         float3 nl = normalCentral(depthFilt, W, H, i, j, x, y, cam, ifx, ify, vf);
@@ -310,13 +314,14 @@ MF_D bool cleanFinish(float4& vp, float4& vc, float x, float y, float lpz, int c
 #define CAND_BUF 2048
 __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, float4* __restrict__ col, const uint32_t* __restrict__ countPtr,
                                                   const uint8_t* __restrict__ aflag, float4* __restrict__ m0, float4* __restrict__ m1, int Ppix,
-                                                  CleanParams P, const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
+                                                  CleanParams P, const DevPose* __restrict__ dpose, const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
                                                   uint8_t* __restrict__ keep, uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount)
 {
     // candidates are staged per block in shared memory and flushed in chunks: one device-wide atomic per ~2k candidates
     // (a warp-aggregated global append put ~130k returning atomics on ONE L2 address: 62 % busy slice, ncu r01b)
     __shared__ uint32_t sBuf[CAND_BUF];
     __shared__ uint32_t sCount, sBase;
+    P.tinv = dpose->tinv;
     const uint32_t count = *countPtr;
     const uint32_t total = count + (uint32_t)Ppix;
     const float cols = (float)P.W, rows = (float)P.H, ftime = (float)P.time;
@@ -370,11 +375,12 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
 // clean, pass 1b: one thread per candidate: index-map window (copy_unstable.vert:86-113) + the rest of the shader
 __global__ void __launch_bounds__(256) k_clean_p2(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
                                                   const uint32_t* __restrict__ countPtr, float4* __restrict__ m0, float4* __restrict__ m1,
-                                                  const float4* __restrict__ m2, CleanParams P, const uint32_t* __restrict__ idx,
+                                                  const float4* __restrict__ m2, CleanParams P, const DevPose* __restrict__ dpose, const uint32_t* __restrict__ idx,
                                                   const float4* __restrict__ vertConf, const float4* __restrict__ colorTime,
                                                   const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask, uint8_t* __restrict__ keep,
                                                   const uint32_t* __restrict__ cand, const uint32_t* __restrict__ candCount)
 {
+    P.tinv = dpose->tinv;
     const uint32_t count = *countPtr, n = *candCount;
     const float cols = (float)P.W, rows = (float)P.H;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
@@ -544,10 +550,11 @@ MF_D void splatRange(const SplatVS& v, int W, int H, int& x0, int& x1, int& y0, 
 }
 
 __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
-                                                       const uint32_t* __restrict__ countPtr, Rt tinv, Cam cam, int W, int H,
+                                                       const uint32_t* __restrict__ countPtr, const DevPose* __restrict__ dpose, Cam cam, int W, int H,
                                                        float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
                                                        uint32_t drawBase, unsigned long long* __restrict__ key)
 {
+    const Rt tinv = dpose->tinv;
     // Flattened rasterisation.  A block projects 256 surfels, compacts the drawable ones with the exclusive
     // prefix sum of their fragment counts (point-sprite squares, 1 .. 2047^2 pixels) into shared memory, and
     // then walks the FLATTENED fragment list with all threads: fragment f belongs to the entry found by binary
@@ -622,7 +629,7 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
 // from the raw frame (fill_*.frag) and the 1/20 sub-sampled "is the prediction mostly
 // black" counter of MaskFusion::requiresFillIn are fused into the same pass.
 __global__ void k_splat_resolve(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
-                                Rt tinv, Cam cam, int W, int H, float maxDepth, float confThreshold, float ftime, float fmaxTime,
+                                const DevPose* __restrict__ dpose, Cam cam, int W, int H, float maxDepth, float confThreshold, float ftime, float fmaxTime,
                                 float ftimeDelta, unsigned long long* __restrict__ key,
                                 uchar4* __restrict__ image, float4* __restrict__ vertexConf, float4* __restrict__ normalRad,
                                 uint16_t* __restrict__ timeTex,
@@ -630,6 +637,7 @@ __global__ void k_splat_resolve(const float4* __restrict__ pos, const float4* __
                                 uchar4* __restrict__ fillImage, float4* __restrict__ fillVertex, float4* __restrict__ fillNormal,
                                 uint32_t* __restrict__ nonBlackSamples)
 {
+    const Rt tinv = dpose->tinv;
     int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
     if (px >= W || py >= H) return;
     int i = py * W + px;
@@ -802,10 +810,23 @@ static int g_numSMs = 148;
 void set_num_sms(int n) { g_numSMs = n > 0 ? n : 148; }
 static inline int persistentBlocks(int perSM) { return g_numSMs * perSM; }
 
+// host-driven pose (constructor, overridePose, updateStaticPose, C-ABI set_pose) -> device-resident DevPose; matrices by value
+struct Pose2 { float p[16], l[16]; };
+__global__ void k_set_pose(DevPose* d, Pose2 in)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) derivePose(d, in.p, in.l);
+}
+void launch_set_pose(DevPose* d, const float* pose16, const float* lastPose16, cudaStream_t s)
+{
+    Pose2 in;
+    for (int k = 0; k < 16; ++k) { in.p[k] = pose16[k]; in.l[k] = lastPose16[k]; }
+    k_set_pose<<<1, 32, 0, s>>>(d, in);
+}
+
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s) { if (n) k_fill_u32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, v, n); }
 void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s) { if (n) k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((unsigned long long*)p, v, n); }
 
-void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, int time,
+void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth, int time,
                             int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, cudaStream_t s)
 {
     prof_mark(s, "k_index_project"); k_index_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, count, tinv, cam, W, H, maxDepth, (float)time, (float)timeDelta,
@@ -815,7 +836,7 @@ void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, Rt ti
 }
 
 void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
-                      const float4* vertConf, const float4* normRad, Rt pose, Cam cam, int W, int H, float maxDepth, int time,
+                      const float4* vertConf, const float4* normRad, const DevPose* pose, Cam cam, int W, int H, float maxDepth, int time,
                       float weighting, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s)
 {
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
@@ -831,17 +852,18 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
 }
 
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
-                  const uint8_t* aflag, float4* const* meas, Rt tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
+                  const uint8_t* aflag, float4* const* meas, const DevPose* tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s)
 {
     CleanParams P;
-    P.tinv = tinv; P.cam = cam; P.W = W; P.H = H; P.time = time; P.ftimeDelta = (float)timeDelta; P.confThreshold = confThreshold;
+    P.tinv = Rt{};                          // filled from the device-resident pose inside the kernels
+    P.cam = cam; P.W = W; P.H = H; P.time = time; P.ftimeDelta = (float)timeDelta; P.confThreshold = confThreshold;
     P.outlierCoeff = outlierCoeff; P.maskID = maskID;
     int Ppix = W * H;
     int blocks = persistentBlocks(4);
-    prof_mark(s, "k_clean_p1"); k_clean_p1<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, count, aflag, meas[0], meas[1], Ppix, P, depthFilt, mask, keep, cand, candCount);
-    prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, idx, vertConf, colorTime, depthFilt,
+    prof_mark(s, "k_clean_p1"); k_clean_p1<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, count, aflag, meas[0], meas[1], Ppix, P, tinv, depthFilt, mask, keep, cand, candCount);
+    prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, idx, vertConf, colorTime, depthFilt,
                                                                                mask, keep, cand, candCount);
     prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<blocks, SCAN_BLOCK, 0, s>>>(keep, count, Ppix, blockSums, candCount);
     prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount);
@@ -849,7 +871,7 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
                                                   dst.pos, dst.col, dst.nrm);
 }
 
-void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth,
+void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth,
                              float confThreshold, int time, int maxTime, int timeDelta, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
                              uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s)
@@ -882,7 +904,7 @@ void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, 
 
 namespace mfb {
 // splat projection into a caller-owned key image (GlobalProjection: all models share one key image)
-void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, Rt tinv, Cam cam, int W, int H, float maxDepth, float confThreshold,
+void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth, float confThreshold,
                                int time, int maxTime, int timeDelta, uint32_t drawBase, uint64_t* key, cudaStream_t s)
 {
     prof_mark(s, "k_splat_project_ids");

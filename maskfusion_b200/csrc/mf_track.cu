@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restri
 // =======================================================================================
 #define PT_THREADS 512
 #define PT_WARPS (PT_THREADS / 32)
+#define ROWF 32                        // floats per partial row: one 128-byte line per CTA per reduction
 
 struct TrackParams {
     int W, H; Cam cam;
@@ -307,17 +308,17 @@ struct TrackParams {
     int iterations[3];
     float icpWeight, angleThres, distThres, sobelScale, maxDepthDelta;
     float minScale[3];
+    int corrSlots;                     // photometric correspondences kept per CTA in shared memory (0: global scratch instead)
 };
 
-// sum of NP (= 32 or 64, zero padded) per-lane values over the warp with NP-ish shuffles instead of 5*NP:
-// each step exchanges HALF of the remaining values with the xor partner.  Lane l ends with values l (NP=32) or 2l, 2l+1 (NP=64).
-template <int NP>
-MF_D void warpReduceHalving(float* v)
+// sum of 32 per-lane values over the warp with 31 shuffles instead of 5*32: each step exchanges HALF of the remaining
+// values with the xor partner.  Lane l ends with the total of value l.
+MF_D void warpReduceHalving32(float* v)
 {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int s = 0; s < 5; ++s) {
-        const int off = 16 >> s, h = (NP / 2) >> s;
+        const int off = 16 >> s, h = 16 >> s;
         const bool up = (lane & off) != 0;
 #pragma unroll
         for (int k = 0; k < h; ++k) {
@@ -328,23 +329,23 @@ MF_D void warpReduceHalving(float* v)
     }
 }
 
-// CTA-wide sum of N accumulators -> one row of 64 floats in global memory (row = this CTA's partial)
+// CTA-wide sum of N (<= 29) accumulators -> one row of 32 floats in global memory (row = this CTA's partial);
+// two exact integer counters ride in columns 29 and 30
 template <int N>
-MF_D void ctaReduceStore(const float* acc, float (*red)[64], float* __restrict__ rowOut, int extra0 = 0, int extra1 = 0, bool hasExtra = false)
+MF_D void ctaReduceStore(const float* acc, float (*red)[ROWF], float* __restrict__ rowOut, int extra0 = 0, int extra1 = 0, bool hasExtra = false)
 {
-    constexpr int NP = N <= 32 ? 32 : 64;
-    float v[NP];
+    float v[32];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) v[k] = k < N ? acc[k] : 0.f;
-    warpReduceHalving<NP>(v);
+    for (int k = 0; k < 32; ++k) v[k] = k < N ? acc[k] : 0.f;
+    warpReduceHalving32(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (NP == 32) red[warp][lane] = v[0];
-    else { red[warp][2 * lane] = v[0]; red[warp][2 * lane + 1] = v[1]; }
-    int e0 = extra0, e1 = extra1;
+    red[warp][lane] = v[0];
+    __syncwarp();
     if (hasExtra) {
+        int e0 = extra0, e1 = extra1;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) { e0 += __shfl_down_sync(0xffffffffu, e0, off); e1 += __shfl_down_sync(0xffffffffu, e1, off); }
-        if (lane == 0) { red[warp][62] = __int_as_float(e0); red[warp][63] = __int_as_float(e1); }
+        if (lane == 0) { red[warp][29] = __int_as_float(e0); red[warp][30] = __int_as_float(e1); }
     }
     __syncthreads();
     if (threadIdx.x < N) {
@@ -352,7 +353,7 @@ MF_D void ctaReduceStore(const float* acc, float (*red)[64], float* __restrict__
 #pragma unroll
         for (int w = 0; w < PT_WARPS; ++w) s += red[w][threadIdx.x];
         rowOut[threadIdx.x] = s;
-    } else if (hasExtra && (threadIdx.x == 62 || threadIdx.x == 63)) {
+    } else if (hasExtra && (threadIdx.x == 29 || threadIdx.x == 30)) {
         int s = 0;
 #pragma unroll
         for (int w = 0; w < PT_WARPS; ++w) s += __float_as_int(red[w][threadIdx.x]);
@@ -360,52 +361,42 @@ MF_D void ctaReduceStore(const float* acc, float (*red)[64], float* __restrict__
     }
 }
 
-// all CTAs of one model: arrive, wait until `target` arrivals have been counted since the launch (monotonic counter)
+// all CTAs of one model: arrive (release: this CTA's partial row is visible first), then wait until `target` arrivals have been
+// counted since the launch (monotonic counter, acquire)
 MF_D void gridBarrier(unsigned* bar, unsigned target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();                                   // our partial row is visible before the arrival
-        atomicAdd(bar, 1u);
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
         unsigned v;
-        do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
-        __threadfence();
+        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
     }
     __syncthreads();
 }
 
-// every CTA: sum the R partial rows (fixed order, double) -> tot[0..N); columns 62/63 carry exact integers.
-// Each warp owns rows warp, warp+16, ...: at most SUM_MAX_ROWS of them, all loaded before the first add (one L2 round trip;
-// a rolled loop paid one per 4 rows, ncu r01c: 29 % of the kernel).
-#define SUM_MAX_ROWS ((TRACK_MAX_BLOCKS / 2 + PT_WARPS - 1) / PT_WARPS)
+// every CTA: sum the R partial rows (fixed order, double) -> tot[0..32); columns 29/30 carry exact integers when EXTRA.
+// Warp w owns rows w, w+16, ...; the rows of a batch are all loaded before the first add (one L2 round trip for R <= 160).
+#define SUM_BATCH 10
 template <int N, bool EXTRA>
-MF_D void sumRows(const float* __restrict__ rows, unsigned R, double (*ws)[64], double* tot)
+MF_D void sumRows(const float* __restrict__ rows, unsigned R, double (*ws)[ROWF], double* tot)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double a0 = 0, a1 = 0;
-    constexpr bool HI = (N > 32) || EXTRA;
-    for (unsigned base = warp; base < R; base += PT_WARPS * 8) {
-        float x0[8], x1[8];
+    const bool isInt = EXTRA && (lane == 29 || lane == 30);
+    const bool used = lane < N || isInt;
+    double a0 = 0;
+    for (unsigned base = warp; base < R; base += PT_WARPS * SUM_BATCH) {
+        float x[SUM_BATCH];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < SUM_BATCH; ++i) {
             const unsigned b = base + (unsigned)i * PT_WARPS;
-            const bool ok = b < R;
-            const float* row = rows + (size_t)(ok ? b : base) * 64;
-            x0[i] = (ok && lane < N) ? __ldcg(row + lane) : 0.f;
-            if (HI) x1[i] = ok ? __ldcg(row + 32 + lane) : 0.f;
+            x[i] = (b < R && used) ? __ldcg(rows + (size_t)b * ROWF + lane) : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            a0 += (double)x0[i];
-            if (HI) {
-                if (EXTRA && lane >= 30) a1 += (double)__float_as_int(x1[i]);
-                else if (32 + lane < N) a1 += (double)x1[i];
-            }
-        }
+        for (int i = 0; i < SUM_BATCH; ++i) a0 += isInt ? (double)__float_as_int(x[i]) : (double)x[i];
     }
-    ws[warp][lane] = a0; ws[warp][32 + lane] = a1;
+    ws[warp][lane] = a0;
     __syncthreads();
-    if (threadIdx.x < 64) {
+    if (threadIdx.x < ROWF) {
         double s2 = 0;
 #pragma unroll
         for (int w = 0; w < PT_WARPS; ++w) s2 += ws[w][threadIdx.x];
@@ -460,29 +451,84 @@ __device__ __forceinline__ bool ldltSolve3Fast(const double* A, const double* b,
     return true;
 }
 
-// entry e of the inverse of a 3x3 (cofactor form of inv3d: every lane evaluates the same determinant)
+// entry e = (r, c) of the inverse of a 3x3: cofactor(c, r) / det with cyclic indices (no sign bookkeeping, no divergent
+// switch: a 9-way switch serialised the nine lanes, ncu r01d).  Products and differences are the ones inv3d forms.
 MF_D double inv3dEntry(const double* M, int e)
 {
-    double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
-    double det = M[0] * c00 + M[1] * c01 + M[2] * c02, id = 1.0 / det;
-    double v;
-    switch (e) {
-        case 0: v = c00; break;
-        case 1: v = M[2] * M[7] - M[1] * M[8]; break;
-        case 2: v = M[1] * M[5] - M[2] * M[4]; break;
-        case 3: v = c01; break;
-        case 4: v = M[0] * M[8] - M[2] * M[6]; break;
-        case 5: v = M[2] * M[3] - M[0] * M[5]; break;
-        case 6: v = c02; break;
-        case 7: v = M[1] * M[6] - M[0] * M[7]; break;
-        default: v = M[0] * M[4] - M[1] * M[3]; break;
-    }
-    return v * id;
+    const int r = e / 3, c = e - 3 * r;
+    const int c1 = c == 2 ? 0 : c + 1, c2 = c1 == 2 ? 0 : c1 + 1, r1 = r == 2 ? 0 : r + 1, r2 = r1 == 2 ? 0 : r1 + 1;
+    const double cof = M[c1 * 3 + r1] * M[c2 * 3 + r2] - M[c1 * 3 + r2] * M[c2 * 3 + r1];
+    const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
+    return cof * (1.0 / det);
 }
 
 struct SolveScratch { double A[36], b[6], x[6], Rt[16], nr[16], Ri[9], Kinv[9], tmp[9], ti[3]; float trR[9], trT[3], iR[9], iT[3]; int fast; };
 
-// computeWarp (RGBDOdometry.cpp:364-376) by one warp: every matrix entry keeps the scalar routine's formula, lanes take entries
+MF_D double shflD(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+// 6x6 normal equations by one warp: lane r < 6 keeps row r of A and b_r in registers; right-looking unpivoted LDL^T with the
+// forward substitution folded into the elimination and the pivots broadcast by shuffle.  The dependent chain per column is
+// one reciprocal and two multiply-adds (a single thread walking the whole factorisation took ~2.4 us per Gauss-Newton
+// iteration, ncu r01d).  Returns false (warp uniform) when a pivot is not safely positive: the caller then runs the pivoted solve.
+// Differences to a sequential LDL^T are at the 1e-16 level (fused multiply-adds, reciprocal instead of division); parity of the
+// solver is a tolerance contract (DESIGN.md R-LDLT).
+MF_D bool ldltSolve6Warp(const double* __restrict__ A, const double* __restrict__ b, double* x /* shared, 6 */)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = lane < 6 ? lane : 5;
+    double a[6], y = b[r];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = A[r * 6 + k];
+    double maxDiag = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) maxDiag = fmax(maxDiag, fabs(A[k * 6 + k]));
+    const double tiny = maxDiag * 1e-12;
+    bool ok = maxDiag > 0;
+    double myInv = 0;                                      // reciprocal of this lane's own pivot
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        // row j is final: broadcast its pivot, its tail and its right-hand side
+        const double dj = shflD(a[j], j);
+        ok = ok && (dj > tiny);
+        const double inv = 1.0 / dj;
+        if (lane == j) myInv = inv;
+        const double yj = shflD(y, j);
+        double rowj[6];
+#pragma unroll
+        for (int k = j + 1; k < 6; ++k) rowj[k] = shflD(a[k], j);
+        const double l = a[j] * inv;                       // L[r][j] for rows below the pivot
+        if (lane > j) {
+#pragma unroll
+            for (int k = j + 1; k < 6; ++k) a[k] = fma(-l, rowj[k], a[k]);
+            y = fma(-l, yj, y);
+            a[j] = l;                                      // keep the factor in place
+        }
+    }
+    if (!ok) return false;
+    // lane r now holds y_r (of L y = b), the pivots' reciprocals and row r of L; z = D^-1 y, then L^T x = z from the last row up
+    double z = y * myInv;
+#pragma unroll
+    for (int i = 5; i >= 1; --i) {
+        const double xi = shflD(z, i);
+#pragma unroll
+        for (int k = 0; k < i; ++k) {
+            const double lik = shflD(a[k], i);             // L[i][k] lives in lane i
+            if (lane == k) z = fma(-lik, xi, z);
+        }
+    }
+    if (lane < 6) x[lane] = z;
+    __syncwarp();
+    return true;
+}
+
+// computeWarp (RGBDOdometry.cpp:364-376) by one warp: every matrix entry keeps the scalar routine's formula, lanes take entries.
+// sc->Kinv holds the inverse intrinsics of the level (set once per level).
 MF_D void computeWarpCoop(TrackState* st, Cam c, SolveScratch* sc, int lane)
 {
     const double* T = st->resultRt;
@@ -490,7 +536,6 @@ MF_D void computeWarpCoop(TrackState* st, Cam c, SolveScratch* sc, int lane)
     if (lane < 9) {
         double R3[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
         sc->Ri[lane] = inv3dEntry(R3, lane);
-        sc->Kinv[lane] = inv3dEntry(K, lane);
     }
     __syncwarp();
     if (lane < 3) sc->ti[lane] = -(sc->Ri[lane * 3] * T[3] + sc->Ri[lane * 3 + 1] * T[7] + sc->Ri[lane * 3 + 2] * T[11]);
@@ -501,9 +546,7 @@ MF_D void computeWarpCoop(TrackState* st, Cam c, SolveScratch* sc, int lane)
     __syncwarp();
 }
 
-// host part of one Gauss-Newton iteration (RGBDOdometry.cpp:403-474) on the replicated state, executed by warp 0:
-// the serial LDL^T stays on lane 0, everything around it (normal equations, SE(3) update, warp constants) is spread over lanes.
-// (One thread doing all of it cost ~5 us per iteration with its matrices in local memory, ncu r01c.)
+// host part of one Gauss-Newton iteration (RGBDOdometry.cpp:403-474) on the replicated state, executed by warp 0
 __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, bool ICP, bool RGB, float icpWeight, Cam cam, SolveScratch* sc)
 {
     const int lane = threadIdx.x & 31;
@@ -520,21 +563,36 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
         else v = (double)vr;
         if (isA) { sc->A[e] = v; st->lastA[e] = v; } else { sc->b[r] = v; st->lastb[r] = v; }
     }
+    if (ICP && lane == 31) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
     __syncwarp();
-    if (lane == 0) {
-        if (ICP) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
-        double result[6];
-        if (!ldltSolve6Fast(sc->A, sc->b, result)) ldltSolve(sc->A, sc->b, 6, result);
-        // computeUpdateSE3 (OdometryProvider.h:69-90)
-        double Rup[9];
-        rodrigues(&result[3], Rup);
-#pragma unroll
-        for (int k = 0; k < 16; ++k) sc->Rt[k] = (k % 5 == 0) ? 1.0 : 0.0;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sc->Rt[r * 4 + c] = Rup[r * 3 + c];
-            sc->Rt[r * 4 + 3] = result[r];
+    if (!ldltSolve6Warp(sc->A, sc->b, sc->x)) {
+        if (lane == 0) ldltSolve(sc->A, sc->b, 6, sc->x);
+        __syncwarp();
+    }
+    // computeUpdateSE3 (OdometryProvider.h:69-90): Rt = [rodrigues(x[3..5]) | x[0..2]]; every lane evaluates the (cheap, identical)
+    // scalar part, lanes < 16 assemble one entry each
+    {
+        double rx = sc->x[3], ry = sc->x[4], rz = sc->x[5];
+        const double theta = sqrt(rx * rx + ry * ry + rz * rz);
+        double c = 1.0, s = 0.0, c1 = 0.0;
+        const bool rot = theta >= DBL_EPSILON;
+        if (rot) { sincos(theta, &s, &c); c1 = 1. - c; const double it = 1. / theta; rx *= it; ry *= it; rz *= it; }
+        if (lane < 16) {
+            const int r = lane >> 2, cc = lane & 3;
+            double v;
+            if (r == 3) v = cc == 3 ? 1.0 : 0.0;
+            else if (cc == 3) v = sc->x[r];
+            else if (!rot) v = r == cc ? 1.0 : 0.0;
+            else {
+                const double u[3] = {rx, ry, rz};
+                const double rrt = u[r] * u[cc];
+                // [r]_x entries: (0,1) -rz (0,2) ry (1,0) rz (1,2) -rx (2,0) -ry (2,1) rx
+                const int d = cc - r;                                  // +-1, +-2
+                const int o = 3 - r - cc;                              // the third index
+                const double rxm = (r == cc) ? 0.0 : ((d == 1 || d == -2) ? -u[o] : u[o]);
+                v = c * (r == cc ? 1.0 : 0.0) + c1 * rrt + s * rxm;
+            }
+            sc->Rt[lane] = v;
         }
     }
     __syncwarp();
@@ -563,21 +621,28 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
     if (RGB) computeWarpCoop(st, cam, sc, lane);          // warp constants for the next iteration's residuals
 }
 
-// pose-independent inputs of one pixel in phase A (prefetched one round ahead: the pose-dependent gathers of the current
-// pixel and the streaming loads of the next one are in flight together)
-struct PixA { float4 vc, nc; float d1; int valid, ni; };
-struct PixB { DataTerm ct; short2 g; };
+MF_D void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackPoses poses, TrackParams tp)
+// one pixel of phase A through its four stages; two of these are in flight per thread (their gathers overlap)
+struct PixA {
+    float4 vc, nc; float d1; int valid, ni;                       // pose-independent inputs
+    bool rOK, iOK; int jr, ji, u0, v0; float td1; float3 vg, vcp;  // projections under the current estimate
+    float d0; int li; float4 vp4, np4;                             // gathered model data
+};
+
+extern __shared__ int2 corrShared[];
+
+__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackParams tp)
 {
     __shared__ TrackJob J;
     __shared__ TrackState S;
     __shared__ SolveScratch sc;
-    __shared__ float red[PT_WARPS][64];
-    __shared__ double ws[PT_WARPS][64];
+    __shared__ float red[PT_WARPS][ROWF];
+    __shared__ double ws[PT_WARPS][ROWF];
     __shared__ double tot[64];
-    __shared__ double totR[64];
+    __shared__ double totR[ROWF];
     __shared__ float so3B[9], so3Kinv[9], so3Krlr[9];
+    __shared__ double so3K[9], so3KinvD[9];
     __shared__ int flag;
     {   // job record -> shared memory (one coalesced read instead of dependent pointer chases in every phase)
         const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + blockIdx.y);
@@ -587,9 +652,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     TrackState* st = &S;
     const unsigned G = gridDim.x;
     unsigned gen = 0;                                                  // barriers passed (uniform)
+    __syncthreads();
     if (threadIdx.x == 0) {
-        // RGBDOdometry.cpp:331-345 initial state
-        const float* P = poses.p[blockIdx.y];
+        // RGBDOdometry.cpp:331-345 initial state; the model's pose is device resident (written by the previous frame's epilogue or k_set_pose)
+        const float* P = J.dpose->pose.m;
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) st->Rprev[r * 3 + c] = P[r * 4 + c]; st->tprev[r] = P[r * 4 + 3]; }
         for (int k = 0; k < 9; ++k) st->Rcurr[k] = st->Rprev[k];
         for (int k = 0; k < 3; ++k) st->tcurr[k] = st->tprev[k];
@@ -604,8 +670,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         for (int k = 0; k < 6; ++k) st->lastb[k] = 0;
     }
     __syncthreads();
-    float* const rowsBuf[2] = {J.partial, J.partial + (size_t)G * 64};
+    float* const rowsBuf[2] = {J.partial, J.partial + (size_t)G * ROWF};
     unsigned* const bar = J.bar;
+    // photometric correspondences of this thread's pixels, slot = round * PT_THREADS + thread: written in phase A, read in phase B
+    // by the same thread.  Shared memory when the launch reserved enough, else a private stripe of the model's scratch buffer.
+    int2* const corr = tp.corrSlots ? corrShared : reinterpret_cast<int2*>(J.corres[0]) + (size_t)blockIdx.x * ((size_t)((tp.W * tp.H + G * PT_THREADS - 1) / (G * PT_THREADS)) * PT_THREADS);
 
     // ---------------- SO(3) pre-alignment on level-2 intensities (RGBDOdometry.cpp:272-345) ----------------
     if (tp.so3) {
@@ -617,11 +686,21 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         const Cam c = camLevel(tp.cam, 2);
         const uint8_t* __restrict__ lastImage = J.lastNextImage2;
         const uint8_t* __restrict__ nextImage = J.nextImage[2];
+        if (threadIdx.x == 0) {
+            double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1}, Kinv[9];
+            inv3d(K, Kinv);
+            for (int q = 0; q < 9; ++q) { so3K[q] = K[q]; so3KinvD[q] = Kinv[q]; so3Kinv[q] = (float)Kinv[q]; }
+        }
+        __syncthreads();
         for (int it = 0; it < 10; ++it) {
-            if (threadIdx.x == 0) {
-                double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1}, Kinv[9], kr[9], hom[9];
-                inv3d(K, Kinv); mul3d(K, st->resultR, kr); mul3d(kr, Kinv, hom);
-                for (int q = 0; q < 9; ++q) { so3B[q] = (float)hom[q]; so3Kinv[q] = (float)Kinv[q]; so3Krlr[q] = (float)kr[q]; }
+            if (threadIdx.x < 9) {
+                // homography K R K^-1 of the current estimate, one entry per lane (same sums as mul3d)
+                const int r = threadIdx.x / 3, cc = threadIdx.x % 3;
+                double kr[3];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) kr[q] = so3K[r * 3] * st->resultR[q] + so3K[r * 3 + 1] * st->resultR[3 + q] + so3K[r * 3 + 2] * st->resultR[6 + q];
+                so3Krlr[threadIdx.x] = (float)kr[cc];
+                so3B[threadIdx.x] = (float)(kr[0] * so3KinvD[cc] + kr[1] * so3KinvD[3 + cc] + kr[2] * so3KinvD[6 + cc]);
             }
             __syncthreads();
             float* rows = rowsBuf[gen & 1];
@@ -661,7 +740,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                         acc[10] += 1.0f;
                     }
                 }
-                ctaReduceStore<11>(acc, red, rows + (size_t)blockIdx.x * 64);
+                ctaReduceStore<11>(acc, red, rows + (size_t)blockIdx.x * ROWF);
             }
             ++gen; gridBarrier(bar, gen * G);
             sumRows<11, false>(rows, Gact, ws, tot);
@@ -708,12 +787,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
         const bool active = blockIdx.x < Gact;
         const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
+        const int rounds = (active && tid < N) ? (N - tid + nthr - 1) / nthr : 0;      // pixels of this thread: tid + r * nthr
         const Cam cam = camLevel(tp.cam, level);
         const float4* __restrict__ vmapC = J.vmapC[level];
         const float4* __restrict__ nmapC = J.nmapC[level];
         const float4* __restrict__ vmapG = J.vmapG[level];
         const float4* __restrict__ nmapG = J.nmapG[level];
-        DataTerm* __restrict__ corres = J.corres[level];
         const float4* __restrict__ cloud = J.cloud[level];
         const short2* __restrict__ grad = J.nextGrad[level];
         const float* __restrict__ lastDepth = J.lastDepth[level];
@@ -723,11 +802,51 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         uint8_t* __restrict__ rgbValid = J.rgbValid[level];
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) { st->levelBreak = 0; st->lastRGBError = FLT_MAX; }
+            if (threadIdx.x < 9) { const double K[9] = {cam.fx, 0, cam.cx, 0, cam.fy, cam.cy, 0, 0, 1}; sc.Kinv[threadIdx.x] = inv3dEntry(K, threadIdx.x); }
+            __syncwarp();
             if (tp.rgb) computeWarpCoop(st, cam, &sc, threadIdx.x);
         }
-        if (tp.rgb && active)                                           // validity is pose independent: once per level, same thread reads it back
-            for (int k = tid; k < N; k += nthr) rgbValid[k] = rgbValidPixel(nextImage, grad, W, H, k, tp.minScale[level]) ? 1 : 0;
+        if (tp.rgb)                                                     // validity is pose independent: once per level, same thread reads it back
+            for (int r = 0; r < rounds; ++r) { const int k = tid + r * nthr; rgbValid[k] = rgbValidPixel(nextImage, grad, W, H, k, tp.minScale[level]) ? 1 : 0; }
         __syncthreads();
+
+        // pose-independent inputs of pixel k
+        auto stage0 = [&](PixA& p, int k) {
+            p.valid = 0; p.d1 = 0.f; p.ni = 0; p.vc = make_float4(0, 0, 0, 0); p.nc = p.vc;
+            if (tp.rgb) { p.valid = rgbValid[k]; p.d1 = nextDepth[k]; p.ni = nextImage[k]; }
+            if (tp.icp) { p.vc = vmapC[k]; p.nc = nmapC[k]; }
+        };
+        // addresses of both gathers under the current estimate
+        auto stage1 = [&](PixA& p, int k, const float3 tprev) {
+            p.rOK = false; p.iOK = false; p.jr = 0; p.ji = 0; p.u0 = 0; p.v0 = 0; p.td1 = 0.f;
+            p.vg = make_float3(0, 0, 0); p.vcp = p.vg;
+            const int y = k / W, x = k - y * W;
+            if (tp.rgb && p.valid && !isnan(p.d1)) {
+                const float* K = st->krk; const float* kt = st->kt;
+                const float d1 = p.d1;
+                p.td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
+                float fu = (d1 * ((K[0] * x + K[1] * y) + K[2]) + kt[0]) / p.td1;
+                float fv = (d1 * ((K[3] * x + K[4] * y) + K[5]) + kt[1]) / p.td1;
+                p.u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
+                p.v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
+                if (p.u0 >= 0 && p.v0 >= 0 && p.u0 < W && p.v0 < H) { p.rOK = true; p.jr = p.v0 * W + p.u0; }
+            }
+            if (tp.icp) {
+                float3 vg = m3v(st->Rcurr, make_float3(p.vc.x, p.vc.y, p.vc.z));
+                vg = make_float3(vg.x + st->tcurr[0], vg.y + st->tcurr[1], vg.z + st->tcurr[2]);
+                float3 vcp = m3v(st->RprevInv, sub3(vg, tprev));
+                int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
+                int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
+                if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) { p.iOK = true; p.ji = uy * W + ux; }
+                p.vg = vg; p.vcp = vcp;
+            }
+        };
+        auto stage2 = [&](PixA& p) {
+            p.d0 = 0.f; p.li = 0; p.vp4 = make_float4(0, 0, 0, 0); p.np4 = p.vp4;
+            if (p.rOK) { p.d0 = lastDepth[p.jr]; p.li = lastImage[p.jr]; }
+            if (p.iOK) { p.vp4 = __ldg(vmapG + p.ji); p.np4 = __ldg(nmapG + p.ji); }
+        };
+
         for (int it = 0; it < tp.iterations[level]; ++it) {
             // ---- phase A: photometric correspondences + statistics, ICP normal equations ----
             float* rowsA = rowsBuf[gen & 1];
@@ -737,69 +856,29 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.f;
                 int cnt = 0, sig = 0;
                 const float3 tprev = make_float3(st->tprev[0], st->tprev[1], st->tprev[2]);
-                PixA cur, nxt;
-                cur.valid = 0; cur.ni = 0; cur.d1 = 0; cur.vc = make_float4(0, 0, 0, 0); cur.nc = cur.vc; nxt = cur;
-                int k = tid;
-                if (k < N) {
-                    if (tp.rgb) { cur.valid = rgbValid[k]; cur.d1 = nextDepth[k]; cur.ni = nextImage[k]; }
-                    if (tp.icp) { cur.vc = vmapC[k]; cur.nc = nmapC[k]; }
-                }
-                while (k < N) {
-                    const int kn = k + nthr;
-                    if (kn < N) {
-                        if (tp.rgb) { nxt.valid = rgbValid[kn]; nxt.d1 = nextDepth[kn]; nxt.ni = nextImage[kn]; }
-                        if (tp.icp) { nxt.vc = vmapC[kn]; nxt.nc = nmapC[kn]; }
-                    }
-                    // pose-dependent addresses of both gathers first, then the gathers, then the arithmetic
-                    bool rOK = false, iOK = false; int jr = 0, ji = 0, u0 = 0, v0 = 0;
-                    const int y = k / W, x = k - y * W;
-                    float td1 = 0;
-                    if (tp.rgb && cur.valid && !isnan(cur.d1)) {
-                        const float* K = st->krk; const float* kt = st->kt;
-                        const float d1 = cur.d1;
-                        td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
-                        float fu = (d1 * ((K[0] * x + K[1] * y) + K[2]) + kt[0]) / td1;
-                        float fv = (d1 * ((K[3] * x + K[4] * y) + K[5]) + kt[1]) / td1;
-                        u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
-                        v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
-                        if (u0 >= 0 && v0 >= 0 && u0 < W && v0 < H) { rOK = true; jr = v0 * W + u0; }
-                    }
-                    float3 vg = make_float3(0, 0, 0), vcp = vg;
-                    if (tp.icp) {
-                        vg = m3v(st->Rcurr, make_float3(cur.vc.x, cur.vc.y, cur.vc.z));
-                        vg = make_float3(vg.x + st->tcurr[0], vg.y + st->tcurr[1], vg.z + st->tcurr[2]);
-                        float3 tmp = sub3(vg, tprev);
-                        vcp = m3v(st->RprevInv, tmp);
-                        int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
-                        int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
-                        if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) { iOK = true; ji = uy * W + ux; }
-                    }
-                    float d0 = 0; int li = 0;
-                    float4 vp4 = make_float4(0, 0, 0, 0), np4 = vp4;
-                    if (rOK) { d0 = lastDepth[jr]; li = lastImage[jr]; }
-                    if (iOK) { vp4 = __ldg(vmapG + ji); np4 = __ldg(nmapG + ji); }
+                // arithmetic of one pixel (same order of accumulation as a one-pixel-at-a-time loop: a before b, rounds ascending)
+                auto stage3 = [&](const PixA& p, int k, int slot) {
                     if (tp.rgb) {
-                        DataTerm c; c.zero = make_short2(0, 0); c.one = make_short2(0, 0); c.diff = 0; c.valid = 0;
-                        if (rOK && d0 > 0 && fabsf(td1 - d0) <= tp.maxDepthDelta && li != 0) {
-                            c.zero = make_short2((short)u0, (short)v0); c.one = make_short2((short)x, (short)y);
-                            c.diff = (float)cur.ni - (float)li;
-                            c.valid = 1;
+                        int2 c = make_int2(-1, 0);                     // .x = u0 | v0 << 16 (or -1: no correspondence), .y = bits of diff
+                        if (p.rOK && p.d0 > 0 && fabsf(p.td1 - p.d0) <= tp.maxDepthDelta && p.li != 0) {
+                            const float diff = (float)p.ni - (float)p.li;
+                            c.x = (p.u0 & 0xffff) | (p.v0 << 16); c.y = __float_as_int(diff);
                             cnt += 1;
-                            sig += (int)(c.diff * c.diff);
+                            sig += (int)(diff * diff);
                         }
-                        corres[k] = c;
+                        corr[slot] = c;
                     }
-                    if (iOK) {
-                        const float4 nc4 = cur.nc;
+                    if (p.iOK) {
+                        const float4 nc4 = p.nc, vp4 = p.vp4, np4 = p.np4;
                         float3 vp = make_float3(vp4.x, vp4.y, vp4.z), np_ = make_float3(np4.x, np4.y, np4.z);
                         float3 ng = m3v(st->Rcurr, make_float3(nc4.x, nc4.y, nc4.z));
-                        float3 d = sub3(vp, vg);
+                        float3 d = sub3(vp, p.vg);
                         float dist = sqrtf((d.x * d.x + d.y * d.y) + d.z * d.z);
                         float3 c = cross3(ng, np_);
                         float sine = sqrtf((c.x * c.x + c.y * c.y) + c.z * c.z);
                         bool found = (sine < tp.angleThres && dist <= tp.distThres && !isnan(nc4.x) && !isnan(np4.x));
                         if (found) {
-                            float3 s_cp = vcp;
+                            float3 s_cp = p.vcp;
                             float3 d_cp = m3v(st->RprevInv, sub3(vp, tprev));
                             float3 n_cp = m3v(st->RprevInv, np_);
                             float row[7];
@@ -817,16 +896,34 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                             acc[28] += 1.0f;
                         }
                     }
-                    cur = nxt; k = kn;
+                };
+                for (int r = 0; r < rounds; r += 2) {
+                    const int k0 = tid + r * nthr, k1 = k0 + nthr;
+                    const bool two = r + 1 < rounds;
+                    // next pair's streaming inputs -> L1 while this pair's dependent gathers are in flight
+                    for (int q = 2; q < 4; ++q)
+                        if (r + q < rounds) {
+                            const int kn = k0 + q * nthr;
+                            if (tp.icp) { prefetchL1(vmapC + kn); prefetchL1(nmapC + kn); }
+                            if (tp.rgb) { prefetchL1(nextDepth + kn); }
+                        }
+                    PixA a, b;
+                    stage0(a, k0);
+                    if (two) stage0(b, k1); else { b.valid = 0; b.d1 = 0.f; b.ni = 0; b.vc = make_float4(0, 0, 0, 0); b.nc = b.vc; }
+                    stage1(a, k0, tprev);
+                    if (two) stage1(b, k1, tprev); else { b.rOK = false; b.iOK = false; b.jr = 0; b.ji = 0; b.u0 = 0; b.v0 = 0; b.td1 = 0.f; b.vg = make_float3(0, 0, 0); b.vcp = b.vg; }
+                    stage2(a); stage2(b);
+                    stage3(a, k0, r * PT_THREADS + threadIdx.x);
+                    if (two) stage3(b, k1, (r + 1) * PT_THREADS + threadIdx.x);
                 }
-                ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * 64, cnt, sig, true);
+                ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * ROWF, cnt, sig, true);
             }
             ++gen; gridBarrier(bar, gen * G);
             sumRows<NACC_ICP, true>(rowsA, Gact, ws, tot);
             if (tp.rgb) {
                 if (threadIdx.x == 0) {
                     // RGBDOdometry.cpp:388-401
-                    int rgbSize = (int)(long long)tot[62], sigma = (int)(long long)tot[63];
+                    int rgbSize = (int)(long long)tot[29], sigma = (int)(long long)tot[30];
                     float tmpError = (float)(sqrt((double)sigma) / (double)rgbSize);
                     float sigmaVal = (tmpError == 0) ? 1 : (float)rgbSize;
                     int brk = 0;
@@ -847,41 +944,42 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
 #pragma unroll
                     for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.f;
                     const float sigmaSh = st->sigmaVal;
-                    PixB cur, nxt;
-                    cur.ct.valid = 0; cur.ct.diff = 0; cur.ct.zero = make_short2(0, 0); cur.ct.one = cur.ct.zero; cur.g = make_short2(0, 0); nxt = cur;
-                    int k = tid;
-                    if (k < N) { cur.ct = corres[k]; cur.g = grad[k]; }
-                    while (k < N) {
-                        const int kn = k + nthr;
-                        if (kn < N) { nxt.ct = corres[kn]; nxt.g = grad[kn]; }
-                        const DataTerm ct = cur.ct;
-                        if (ct.valid) {
-                            float4 cp = cloud[ct.zero.y * W + ct.zero.x];
-                            float w = sigmaSh + fabsf(ct.diff);
-                            w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
-                            if (sigmaSh == -1) w = 1;
-                            float row[7];
-                            row[6] = -w * ct.diff;
-                            float invz = (float)(1.0 / (double)cp.z);
-                            short2 g = cur.g;                            // == grad[one]: `one` is this pixel (reduce.cu:934)
-                            float dIdx_v = w * tp.sobelScale * (float)g.x;
-                            float dIdy_v = w * tp.sobelScale * (float)g.y;
-                            float v0 = dIdx_v * cam.fx * invz;
-                            float v1 = dIdy_v * cam.fy * invz;
-                            float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
-                            row[0] = v0; row[1] = v1; row[2] = v2;
-                            row[3] = -cp.z * v1 + cp.y * v2;
-                            row[4] = cp.z * v0 - cp.x * v2;
-                            row[5] = -cp.y * v0 + cp.x * v1;
-                            int q = 0;
+                    auto rgbRow = [&](int2 c, short2 g, float4 cp) {
+                        const float diff = __int_as_float(c.y);
+                        float w = sigmaSh + fabsf(diff);
+                        w = w > 1.19209290E-07F ? 1.0f / w : 1.0f;
+                        if (sigmaSh == -1) w = 1;
+                        float row[7];
+                        row[6] = -w * diff;
+                        float invz = (float)(1.0 / (double)cp.z);
+                        float dIdx_v = w * tp.sobelScale * (float)g.x;      // grad[one]: `one` is this pixel (reduce.cu:934)
+                        float dIdy_v = w * tp.sobelScale * (float)g.y;
+                        float v0 = dIdx_v * cam.fx * invz;
+                        float v1 = dIdy_v * cam.fy * invz;
+                        float v2 = -(v0 * cp.x + v1 * cp.y) * invz;
+                        row[0] = v0; row[1] = v1; row[2] = v2;
+                        row[3] = -cp.z * v1 + cp.y * v2;
+                        row[4] = cp.z * v0 - cp.x * v2;
+                        row[5] = -cp.y * v0 + cp.x * v1;
+                        int q = 0;
 #pragma unroll
-                            for (int a = 0; a < 6; ++a)
+                        for (int a = 0; a < 6; ++a)
 #pragma unroll
-                                for (int b = a; b < 7; ++b) accR[q++] += row[a] * row[b];
-                        }
-                        cur = nxt; k = kn;
+                            for (int b = a; b < 7; ++b) accR[q++] += row[a] * row[b];
+                    };
+                    for (int r = 0; r < rounds; r += 2) {
+                        const int k0 = tid + r * nthr, k1 = k0 + nthr;
+                        const bool two = r + 1 < rounds;
+                        const int2 c0 = corr[r * PT_THREADS + threadIdx.x];
+                        const int2 c1 = two ? corr[(r + 1) * PT_THREADS + threadIdx.x] : make_int2(-1, 0);
+                        short2 g0 = make_short2(0, 0), g1 = g0;
+                        float4 p0 = make_float4(0, 0, 1, 0), p1 = p0;
+                        if (c0.x != -1) { g0 = grad[k0]; p0 = cloud[(c0.x >> 16) * W + (c0.x & 0xffff)]; }
+                        if (c1.x != -1) { g1 = grad[k1]; p1 = cloud[(c1.x >> 16) * W + (c1.x & 0xffff)]; }
+                        if (c0.x != -1) rgbRow(c0, g0, p0);
+                        if (c1.x != -1) rgbRow(c1, g1, p1);
                     }
-                    ctaReduceStore<NACC_RGB>(accR, red, rowsB + (size_t)blockIdx.x * 64);
+                    ctaReduceStore<NACC_RGB>(accR, red, rowsB + (size_t)blockIdx.x * ROWF);
                 }
                 ++gen; gridBarrier(bar, gen * G);
                 // ICP totals stay in tot[0..28]; the photometric ones go behind them
@@ -911,6 +1009,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         po[32] = st->lastICPError; po[33] = st->lastICPCount; po[34] = st->lastRGBError; po[35] = st->lastRGBCount;
         po[36] = st->lastSO3Error; po[37] = st->lastSO3Count;
         *J.st = *st;
+        // device-resident pose for the passes that follow (index map, association, clean, splat): no host round trip
+        float last[16];
+        for (int k = 0; k < 16; ++k) last[k] = (k % 5 == 0) ? 1.f : 0.f;
+        for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) last[r * 4 + c] = st->Rprev[r * 3 + c]; last[r * 4 + 3] = st->tprev[r]; }
+        derivePose(J.dpose, po, last);
     }
 }
 
@@ -923,7 +1026,7 @@ static int trackBlocks(int N, int numSMs)
     return need < cap ? need : cap;
 }
 
-int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
+int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
                     bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s)
 {
     static int coResident = -1;                 // CTAs of k_track_persistent the device can hold at once
@@ -948,11 +1051,22 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, const TrackPoses& poses, int W,
     if (G * nJobs > coResident) G = coResident / nJobs;
     if (G > TRACK_MAX_BLOCKS / 2) G = TRACK_MAX_BLOCKS / 2;
     if (G < 1) throw CudaError{"too many tracked models for one cooperative launch"};
+    // photometric correspondences stay in shared memory when the per-CTA pixel share fits (8 B per pixel slot)
+    const int rounds0 = (W * H + G * PT_THREADS - 1) / (G * PT_THREADS);
+    size_t dyn = (size_t)rounds0 * PT_THREADS * sizeof(int2);
+    static size_t dynMax = 0;
+    if (dynMax == 0) {
+        cudaFuncAttributes fa; cudaCheck(cudaFuncGetAttributes(&fa, k_track_persistent), "cudaFuncGetAttributes");
+        int optin = 0, dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        dynMax = (size_t)optin > fa.sharedSizeBytes + 2048 ? (size_t)optin - fa.sharedSizeBytes - 2048 : 0;
+        cudaCheck(cudaFuncSetAttribute(k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMax), "cudaFuncSetAttribute");
+    }
+    if (tp.rgb && dyn <= dynMax) tp.corrSlots = rounds0 * PT_THREADS; else { tp.corrSlots = 0; dyn = 0; }
     cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
     prof_mark(s, "k_track_persistent");
     const TrackJob* jp = d_jobs;
-    void* args[] = {(void*)&jp, (void*)&poses, (void*)&tp};
-    cudaCheck(cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(G, nJobs), dim3(PT_THREADS), args, 0, s), "cooperative launch (tracking)");
+    void* args[] = {(void*)&jp, (void*)&tp};
+    cudaCheck(cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(G, nJobs), dim3(PT_THREADS), args, dyn, s), "cooperative launch (tracking)");
     return 1;
 }
 

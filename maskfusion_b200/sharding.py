@@ -121,13 +121,16 @@ class ShardedMaskFusion:
         self.on_nccl = dist.get_backend(group) == "nccl"
         self.dev = torch.device("cuda", device)
         torch.cuda.set_device(self.dev)
-        self.stream = torch.cuda.current_stream(self.dev)
+        # one explicit stream for the kernels AND the collectives' staging ops: torch's default stream has the NULL handle, which
+        # mf_create reads as "make a private non-blocking stream" -- torch ops on the default stream would then race with the kernels
+        self.stream = torch.cuda.Stream(self.dev)
         self.mf = api.MaskFusion(cfg, device=device, stream=self.stream.cuda_stream)
         self.L, self.h = self.mf.L, self.mf.h
         self.W, self.H = cfg.width, cfg.height
         self.P = self.W * self.H
         self.mf._ck(self.L.mf_shard_configure(self.h, self.rank, self.world))
-        self.packet = torch.zeros(frame_packet_bytes(self.W, self.H), dtype=torch.uint8, device=self.dev)
+        with torch.cuda.stream(self.stream):
+            self.packet = torch.zeros(frame_packet_bytes(self.W, self.H), dtype=torch.uint8, device=self.dev)
         self.packet_host = None if self.on_nccl else torch.zeros(frame_packet_bytes(self.W, self.H), dtype=torch.uint8).pin_memory()
         self.keys = None
         self.rows = np.zeros((MAX_MODELS, 32), np.float32)
@@ -166,6 +169,10 @@ class ShardedMaskFusion:
 
     # -- one frame --
     def processFrame(self, rgb=None, depth=None, timestamp: int = 0, mask=None, classIDs=None, weightMultiplier: float = 1.0):
+        with self.torch.cuda.stream(self.stream):            # every torch op below is ordered with the kernels on self.stream
+            return self._process_frame(rgb, depth, timestamp, mask, classIDs, weightMultiplier)
+
+    def _process_frame(self, rgb, depth, timestamp, mask, classIDs, weightMultiplier):
         ck, L, h, P = self.mf._ck, self.L, self.h, self.P
         if self.rank == self.src:
             pack_frame(self.packet, self.W, self.H, rgb, depth, mask, timestamp, classIDs)

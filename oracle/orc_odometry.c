@@ -363,12 +363,25 @@ static void populate(orc_odom* o, const uint8_t* img, int stride, float** depths
 void orc_odom_init_rgb_model(orc_odom* o, const uint8_t* image4) { populate(o, image4, 4, o->lastDepth, o->lastImage); }
 void orc_odom_init_rgb(orc_odom* o, const uint8_t* rgb3) { populate(o, rgb3, 3, o->nextDepth, o->nextImage); }
 
+/* Sensitivity probe (tests only, off by default): scale every reduced sum by (1 + eps * u), u in [-1, 1] from a counter hash.
+ * eps = 1e-7 is the size of an fp32 tree-reduction's rounding, i.e. what separates two correct implementations of the same
+ * sums; tests/test_cpu.py uses it to document how far such noise moves a tracked pose (object models: near-singular systems). */
+static double g_sum_perturb = 0.0;
+static unsigned g_sum_counter = 0;
+void orc_debug_set_sum_perturb(double eps) { g_sum_perturb = eps; g_sum_counter = 0; }
+static double perturbed(double v)
+{
+    if (g_sum_perturb == 0.0) return v;
+    unsigned h = ++g_sum_counter * 2654435761u; h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    return v * (1.0 + g_sum_perturb * ((double)(h & 0xffffff) / 8388607.5 - 1.0));
+}
+
 static void unpack29(const double* s, float* A, float* b)
 {
     int k = 0;
     for (int i = 0; i < 6; ++i)
         for (int j = i; j < 7; ++j) {
-            float v = (float)s[k++];
+            float v = (float)perturbed(s[k++]);
             if (j == 6) b[i] = v; else A[j * 6 + i] = A[i * 6 + j] = v;
         }
 }

@@ -14,7 +14,7 @@ echo "== pytest gpu" ; timeout 1500 python -m pytest tests -q -m gpu -p no:cache
 echo "== bench" ; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err ; echo "bench rc=$?" ; tail -c 3500 gpurun_out/bench.json ; tail -5 gpurun_out/bench.err
 if [ "$MODE" = "full" ]; then
   echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ; tail -c 1200 gpurun_out/bench_ref.json
-  echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 300 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 2 > gpurun_out/ncu_bench.log 2>&1 ; echo "ncu rc=$?"
+  echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 330 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 2 > gpurun_out/ncu_bench.log 2>&1 ; echo "ncu rc=$?"
   for K in "$@"; do
     echo "== ncu full $K" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o gpurun_out/prof_$K python bench.py --steps 3 --warmup 2 > gpurun_out/ncu_$K.log 2>&1 ; echo "rc=$?"
   done

@@ -17,10 +17,12 @@ sys.path.insert(0, ROOT)
 
 
 # replay used by the GPU sharding test: objects spawn every 6 frames so that three of them exist after 20 frames; capacities chosen so
-# that the placement rule puts stores on both ranks
+# that the placement rule puts stores on both ranks.  Tracked objects need the photometric term (GUI default icpWeight=20): with ICP
+# alone the normal equations of a 3k-surfel sphere/capsule are near singular, the first step jumps > 0.2 m and the reference rule
+# (MaskFusion.cpp:268-272) removes the model one frame after its spawn -- in the oracle and in the CUDA path alike.
 def shard_kw(track_all):
-    return dict(capacityGlobal=1000000, capacityObject=600000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all),
-                modelSpawnOffset=6)
+    return dict(capacityGlobal=1000000, capacityObject=600000, enableMultipleModels=1, icpWeight=20.0 if track_all else 100.0, so3=0,
+                trackAllModels=int(track_all), modelSpawnOffset=6)
 
 
 def cpu_mode(out_dir):

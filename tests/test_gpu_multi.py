@@ -25,10 +25,11 @@ class MFS(C.Structure):
                 ("projKeys", C.c_void_p), ("projectedIDs", ol.u8p), ("fullSeg", ol.u8p)]
 
 
-def run(nframes, track_all):
+def run(nframes, track_all, **over):
     import maskfusion_b200 as mfb
     from maskfusion_b200.synth import SynthScene
     kw = dict(capacityGlobal=1000000, capacityObject=200000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all))
+    kw.update(over)
     sc = SynthScene(W, H, n_objects=3, seed=0)
     orc = ol.OraclePipeline(ol.default_config(W, H, **kw))
     L = orc.L
@@ -52,25 +53,69 @@ def run(nframes, track_all):
                "cnt_o": [int(orc.count(i)) for i in range(s.nmodels)], "cnt_c": [m.lastCount() for m in models_c]}
         if rec["n_o"] == rec["n_c"]:
             rec["dpose"] = [float(np.abs(orc.pose(i) - models_c[i].getPose()).max()) for i in range(rec["n_o"])]
+        rec["pose_o"] = [orc.pose(i).tolist() for i in range(s.nmodels)]
         log.append(rec)
     mf.close()
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, f"multi_trackall{int(track_all)}.json"), "w") as f:
+    with open(os.path.join(OUT, f"multi_trackall{int(track_all)}_w{int(kw['icpWeight'])}.json"), "w") as f:
         json.dump(log, f)
     return log
 
 
-def check(log, min_models):
+def oracle_poses(nframes, eps, **over):
+    """free-running oracle alone, every reduced sum of the tracker scaled by (1 + eps*u), |u| <= 1 (orc_debug_set_sum_perturb):
+    how far rounding-size noise in the normal equations moves each model's pose"""
+    from maskfusion_b200.synth import SynthScene
+    kw = dict(capacityGlobal=1000000, capacityObject=200000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=1)
+    kw.update(over)
+    sc = SynthScene(W, H, n_objects=3, seed=0)
+    orc = ol.OraclePipeline(ol.default_config(W, H, **kw))
+    L = orc.L
+    L.orc_debug_set_sum_perturb.argtypes = [C.c_double]
+    L.orc_mf_process_frame_ex.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
+    out = []
+    L.orc_debug_set_sum_perturb(eps)
+    try:
+        for t in range(nframes):
+            rgb, depth, mask, *_ = sc.render(t)
+            mask = np.ascontiguousarray(mask)
+            L.orc_mf_process_frame_ex(orc.h, ol.ptr(np.ascontiguousarray(rgb)), ol.ptr(np.ascontiguousarray(depth)), t * 33333, ol.ptr(mask), ol.ptr(cls), len(cls))
+            n = C.cast(orc.h, C.POINTER(MFS)).contents.nmodels
+            out.append([orc.pose(i).copy() for i in range(n)])
+    finally:
+        L.orc_debug_set_sum_perturb(0.0)
+    return out
+
+
+def check(log, min_models, envelope=None):
+    """envelope[t][i]: pose distance the oracle itself moves under fp32-rounding-size noise (tracked object models only)"""
     assert max(r["n_o"] for r in log) >= min_models, "oracle never spawned an object model"
+    worst = {}
     for r in log:
-        assert r["n_o"] == r["n_c"], r
-        assert r["ids_o"] == r["ids_c"] and r["cls_o"] == r["cls_c"], r
-        # bit-exact kernels + poses that agree to ~1e-8: the images agree except (rarely) at a pixel whose depth test flips
-        assert r["proj_diff"] <= 20, r
-        assert r["seg_diff"] <= 200, r
-        for a, b in zip(r["cnt_o"], r["cnt_c"]):
-            assert abs(a - b) <= max(30, a // 500), r
-        assert max(r["dpose"]) < 2e-5, r
+        assert r["n_o"] == r["n_c"], r["t"]
+        assert r["ids_o"] == r["ids_c"] and r["cls_o"] == r["cls_c"], r["t"]
+        rec = {k: v for k, v in r.items() if k != "pose_o"}
+        if envelope is None:
+            # bit-exact kernels + poses that agree to ~1e-8: the images agree except (rarely) at a pixel whose depth test flips
+            assert r["proj_diff"] <= 20, rec
+            assert r["seg_diff"] <= 200, rec
+            for a, b in zip(r["cnt_o"], r["cnt_c"]):
+                assert abs(a - b) <= max(30, a // 500), rec
+            assert max(r["dpose"]) < 2e-5, rec
+            continue
+        # tracked objects: a freshly spawned object model (3-5k surfels) gives near-singular normal equations; noise of the size of
+        # one fp32 rounding in the reduced sums moves the ORACLE's own object poses by 1e-4 .. 1e-2 (envelope), the background by < 1e-7.
+        # The CUDA path must stay inside that envelope (x10, running maximum) and bit-for-bit comparable where the problem is well posed.
+        assert r["dpose"][0] < 2e-5, rec                                     # background: well conditioned
+        assert abs(r["cnt_o"][0] - r["cnt_c"][0]) <= max(30, r["cnt_o"][0] // 500), rec
+        for i in range(1, r["n_o"]):
+            e = envelope[r["t"]][i] if i < len(envelope[r["t"]]) else 0.0
+            worst[i] = max(worst.get(i, 0.0), e)
+            assert r["dpose"][i] <= max(2e-5, 10.0 * worst[i]), (rec, worst)
+            assert r["dpose"][i] < 5e-2, rec                                  # and never a gross failure
+            assert abs(r["cnt_o"][i] - r["cnt_c"][i]) <= max(60, r["cnt_o"][i] // 20), rec
+        assert r["seg_diff"] <= 3000 and r["proj_diff"] <= 3000, rec          # object silhouettes move by a pixel at most
 
 
 def test_multi_model_static_objects():
@@ -80,6 +125,23 @@ def test_multi_model_static_objects():
 
 
 def test_multi_model_tracked_objects():
-    """trackAllModels=true: every object model runs its own ICP, batched with the background in one launch sequence"""
+    """trackAllModels=true, ICP only: every object model runs its own ICP, batched with the background in one launch sequence.
+    The near-singular ICP system of a freshly spawned 3k-surfel object makes its first step jump > 0.2 m, so the reference rule
+    (MaskFusion.cpp:268-272) removes it on the next frame -- the lifecycle (spawn, inactivate) must match the oracle exactly."""
     log = run(27, track_all=True)
     check(log, 2)
+    assert log[-1]["n_c"] == 1
+
+
+def test_multi_model_three_tracked_objects():
+    """BASELINE configs[2] shape: three objects, each tracked with ICP + photometric term (GUI default icpWeight=20) in the
+    batched persistent tracking kernel; a spawn every 6 frames so that all three exist after 18 frames and are tracked for 6 more"""
+    over = dict(icpWeight=20.0, modelSpawnOffset=6)
+    log = run(24, track_all=True, **over)
+    ref = [[np.array(p, np.float32) for p in r["pose_o"]] for r in log]
+    per = oracle_poses(24, 1e-7, **over)
+    envelope = [[float(np.abs(a - b).max()) for a, b in zip(pa, pb)] for pa, pb in zip(ref, per)]
+    with open(os.path.join(OUT, "multi_envelope_w20.json"), "w") as f:
+        json.dump({"envelope": envelope, "cuda_vs_oracle": [r.get("dpose") for r in log]}, f)
+    check(log, 4, envelope)
+    assert log[-1]["n_c"] == 4
