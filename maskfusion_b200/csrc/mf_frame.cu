@@ -154,7 +154,10 @@ __global__ void k_intensity_select(const uchar4* __restrict__ imgPred, const uch
 
 __constant__ float c_sobx[9] = {0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f};
 __constant__ float c_soby[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f};
-__global__ void k_sobel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad)
+// + the pose-independent half of residualKernel (reduce.cu:821-845): a pixel can enter the photometric term only if its 4x4
+// neighbourhood of intensities is non-zero and its own gradient magnitude passes the level's gate.  Frame-side, shared by all
+// models and all Gauss-Newton iterations (the tracker used to re-derive it per model per level).
+__global__ void k_sobel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad, float minScale, uint8_t* __restrict__ rgbValid)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -166,7 +169,19 @@ __global__ void k_sobel(const uint8_t* __restrict__ src, int W, int H, short2* _
             dyv += s * c_soby[k];
             --k;
         }
-    grad[y * W + x] = make_short2((short)(int)dxv, (short)(int)dyv);
+    const short2 g = make_short2((short)(int)dxv, (short)(int)dyv);
+    grad[y * W + x] = g;
+    bool valid = false;
+    if (x < W - 5 && y < H - 1) {
+        valid = true;
+        for (int u = max(y - 2, 0); u < min(y + 2, H); ++u)
+            for (int v = max(x - 2, 0); v < min(x + 2, W); ++v) valid = valid && (src[u * W + v] > 0);
+        if (valid) {
+            float mTwo = (float)(((int)g.x * (int)g.x) + ((int)g.y * (int)g.y));
+            valid = mTwo >= minScale;
+        }
+    }
+    rgbValid[y * W + x] = valid ? 1 : 0;
 }
 
 // ---- model-map preparation ------------------------------------------------------------
@@ -306,10 +321,10 @@ void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const
 {
     prof_mark(s, "k_intensity_select"); k_intensity_select<<<(P + 255) / 256, 256, 0, s>>>(imgPred, imgFill, nonBlack, denom, forceFill, P, out);
 }
-void launch_sobel(const uint8_t* src, int W, int H, short2* grad, cudaStream_t s)
+void launch_sobel(const uint8_t* src, int W, int H, short2* grad, float minScale, uint8_t* rgbValid, cudaStream_t s)
 {
     dim3 b(32, 8);
-    prof_mark(s, "k_sobel"); k_sobel<<<grid2(W, H, b), b, 0, s>>>(src, W, H, grad);
+    prof_mark(s, "k_sobel"); k_sobel<<<grid2(W, H, b), b, 0, s>>>(src, W, H, grad, minScale, rgbValid);
 }
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
                        int W, int H, const DevPose* pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s)

@@ -127,7 +127,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     cudaCheck(cudaMallocHost((void**)&hCount, 2 * sizeof(uint32_t)), "cudaMallocHost"); hCount[0] = hCount[1] = 0;
     cudaCheck(cudaMallocHost((void**)&hTrackOut, 40 * sizeof(float)), "cudaMallocHost");
     key.alloc(P); launch_fill_u64(key, KEY_EMPTY, P, s);
-    idx.alloc(P); vertConf.alloc(P); colorTime.alloc(P); normRad.alloc(P);
+    idx.alloc(P); vertConf.alloc(P); colorTime.alloc(P); normRad.alloc(P); cleanTex.alloc((size_t)P * 2); cleanTex.zero(s);
     idx.zero(s); vertConf.zero(s); colorTime.zero(s); normRad.zero(s);
     splatImage.alloc(P); splatVertex.alloc(P); splatNormal.alloc(P); splatTime.alloc(P);
     splatImage.zero(s); splatVertex.zero(s); splatNormal.zero(s); splatTime.zero(s);
@@ -224,7 +224,7 @@ void Model::predictIndices(int time, float depthCutoff, int timeDelta)
 {
     MaskFusion* o = owner;
     launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, time, timeDelta, key, idx, vertConf,
-                           colorTime, normRad, o->stream);
+                           colorTime, normRad, cleanTex, o->stream);
     o->launches += 2;
 }
 
@@ -245,7 +245,7 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
     float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
     int other = 1 - target, otherCount = 1 - countSel;
     launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, dpose, o->cam, o->W, o->H,
-                 time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, idx, vertConf, colorTime, o->depthFilt, o->mask, keep, blockSums,
+                 time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, cleanTex, o->depthFilt, o->mask, keep, blockSums,
                  cand, candCount, o->stream);
     target = other; countSel = otherCount;
     o->launches += 5;
@@ -255,7 +255,7 @@ void Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDe
 {
     MaskFusion* o = owner;
     launch_combined_predict(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, confidenceThreshold, time, maxTime,
-                            timeDelta, key, splatImage, splatVertex, splatNormal, splatTime, fillIn ? 1 : 0, o->depthFilt, o->rgb, 0,
+                            timeDelta, o->rayTab, key, splatImage, splatVertex, splatNormal, splatTime, fillIn ? 1 : 0, o->depthFilt, o->rgb, 0,
                             o->cfg.frameToFrameRGB ? 1 : 0, fillImage, fillVertex, fillNormal, fillIn ? nonBlack.p : nullptr, o->stream);
     o->launches += 2;
 }
@@ -287,6 +287,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     cudaCheck(cudaMallocHost((void**)&hJobs, TRACK_MAX_JOBS * sizeof(TrackJob)), "cudaMallocHost");
     initFlagR.alloc(P); initFlagF.alloc(P);
     scratch.alloc((size_t)P * 4);
+    rayTab.alloc(P); launch_ray_table(cam, W, H, rayTab, stream);
     if (c.enableMultipleModels) {
         frameMask.alloc(P); frameMask.zero(stream);
         projKeys.alloc(P); launch_fill_u64(projKeys, KEY_EMPTY, P, stream); projectedIDs.alloc(P); projectedIDs.zero(stream);
@@ -359,7 +360,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
         launch_intensity(rgb, P, nextImage[0], stream);
         for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
         launches += 3;
-        if (rgbTerm) { for (int l = 0; l < 3; ++l) launch_sobel(nextImage[l], W >> l, H >> l, nextGrad[l], stream); launches += 3; }
+        if (rgbTerm) { for (int l = 0; l < 3; ++l) launch_sobel(nextImage[l], W >> l, H >> l, nextGrad[l], track_min_scale(l), rgbValid[l], stream); launches += 3; }
         intensityValid = true;
     }
     for (size_t j = 0; j < ms.size(); ++j) {
@@ -436,7 +437,7 @@ void MaskFusion::projectLocal()
         Model* m = models[i].get();
         if (!m->owned) continue;
         launch_splat_project_only(m->current(), m->dCount(), m->dpose, cam, W, H, cfg.depthCutoff, 12.0f /* :61 */, tick, tick,
-                                  cfg.timeDelta, (uint32_t)i << 26, projKeys, stream);
+                                  cfg.timeDelta, (uint32_t)i << 26, rayTab, projKeys, stream);
         launches += 1;
     }
 }

@@ -88,7 +88,7 @@ public:
     uint32_t* hCount = nullptr;             // pinned mirror
     // index map
     DevBuf<uint64_t> key;
-    DevBuf<uint32_t> idx; DevBuf<float4> vertConf, colorTime, normRad;
+    DevBuf<uint32_t> idx; DevBuf<float4> vertConf, colorTime, normRad, cleanTex;
     // prediction + fill-in
     DevBuf<uchar4> splatImage, fillImage; DevBuf<float4> splatVertex, splatNormal, fillVertex, fillNormal; DevBuf<uint16_t> splatTime;
     DevBuf<uint32_t> nonBlack;
@@ -160,6 +160,7 @@ public:
     DevBuf<TrackJob> dJobs; TrackJob* hJobs = nullptr; DevBuf<unsigned> trackBars;
     DevBuf<uint8_t> initFlagR, initFlagF;
     DevBuf<float> scratch;                  // read-back staging
+    DevBuf<float4> rayTab;                  // viewing ray of every pixel centre (camera constant): read by the splat rasteriser
     bool frameMapsValid = false, intensityValid = false;
     Profiler prof;
     // multi-model state

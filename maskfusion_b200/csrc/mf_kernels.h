@@ -104,7 +104,7 @@ struct TrackState {
 
 struct TrackJob {
     const float4* vmapC[3]; const float4* nmapC[3];        // frame maps (shared by all models)
-    const uint8_t* nextImage[3]; const short2* nextGrad[3]; uint8_t* rgbValid[3];
+    const uint8_t* nextImage[3]; const short2* nextGrad[3]; const uint8_t* rgbValid[3];
     const float4* vmapG[3]; const float4* nmapG[3];        // model maps in the model-global frame
     const float* lastDepth[3]; const uint8_t* lastImage[3];
     const uint8_t* lastNextImage2;
@@ -128,7 +128,8 @@ void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStr
 void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s);
 void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s);
 void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s);
-void launch_sobel(const uint8_t* src, int W, int H, short2* grad, cudaStream_t s);
+void launch_sobel(const uint8_t* src, int W, int H, short2* grad, float minScale, uint8_t* rgbValid, cudaStream_t s);
+float track_min_scale(int level);          // gradient-magnitude gate of the photometric term at a pyramid level (RGBDOdometry.cpp:44-49)
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
                        int W, int H, const DevPose* dpose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s);
 void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s);
@@ -139,7 +140,8 @@ void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s);
 void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s);
 void launch_set_pose(DevPose* d, const float* pose16, const float* lastPose16, cudaStream_t s);      // host-driven pose -> DevPose
 void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, int time,
-                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, cudaStream_t s);
+                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, float4* cleanTex,
+                            cudaStream_t s);
 void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
                       const float4* vertConf, const float4* normRad, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, int time,
                       float weightMultiplier, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s);
@@ -147,12 +149,13 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
                         const SurfelPlanes& sp, cudaStream_t s);
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* dpose, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
-                  float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
+                  float outlierCoeff, uint8_t maskID, const float4* cleanTex,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s);
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth,
-                             float confThreshold, int time, int maxTime, int timeDelta, uint64_t* key, uchar4* image, float4* vertexConf,
+                             float confThreshold, int time, int maxTime, int timeDelta, const float4* rayTab, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
                              uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s);
+void launch_ray_table(Cam cam, int W, int H, float4* tab, cudaStream_t s);      // pixel-centre viewing rays (combo_splat.frag:39-45), once per context
 void launch_init_model(const uchar4* rgb, const float* depthRaw, const float* depthFilt, Cam cam, int W, int H, int time, float maxDepth,
                        uint8_t* fr, uint8_t* ff, uint32_t* sumR, uint32_t* sumF, uint32_t capacity, const SurfelPlanes& sp, uint32_t* count,
                        cudaStream_t s);
@@ -185,5 +188,5 @@ void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, 
 void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, int nMasks, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s);
 void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s);
 void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, float confThreshold,
-                               int time, int maxTime, int timeDelta, uint32_t drawBase, uint64_t* key, cudaStream_t s);
+                               int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s);
 }  // namespace mfb

@@ -51,8 +51,11 @@ __global__ void __launch_bounds__(256) k_index_project(const float4* __restrict_
 
 __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
                                 const DevPose* __restrict__ dpose, int P, unsigned long long* __restrict__ key, uint32_t* __restrict__ idx,
-                                float4* __restrict__ vertConf, float4* __restrict__ colorTime, float4* __restrict__ normRad)
+                                float4* __restrict__ vertConf, float4* __restrict__ colorTime, float4* __restrict__ normRad,
+                                float4* __restrict__ cleanTex)
 {
+    // cleanTex: what the clean pass reads per window texel, packed into ONE 32-byte sector
+    //   [2i] = vertConf, [2i+1] = (initTime, lastTime, idx != 0, -)   (three separate images cost three sectors per tap)
     const Rt tinv = dpose->tinv;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -61,6 +64,7 @@ __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __
         idx[i] = 0;
         float4 z = make_float4(0, 0, 0, 0);
         vertConf[i] = z; colorTime[i] = z; normRad[i] = z;
+        cleanTex[2 * i] = z; cleanTex[2 * i + 1] = z;
         return;
     }
     key[i] = KEY_EMPTY;
@@ -72,6 +76,8 @@ __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __
     vertConf[i] = make_float4(ph.x, ph.y, ph.z, p.w);
     colorTime[i] = c;
     normRad[i] = make_float4(nn.x, nn.y, nn.z, n.w);
+    cleanTex[2 * i] = make_float4(ph.x, ph.y, ph.z, p.w);
+    cleanTex[2 * i + 1] = make_float4(c.z, c.w, id != 0u ? 1.f : 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -231,8 +237,7 @@ struct CleanEntry { float xn, yn, lx, ly, lz, init, rad, lnz; };
 // half-texel steps; the taps land on 2-3 distinct texels per axis and the per-tap tests depend on the texel
 // alone: run the literal float loops for the texel columns/rows, visit each DISTINCT texel once, weight by
 // its multiplicity (same counts as the tap loop, ~4x fewer loads).
-MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const uint32_t* __restrict__ idx, const float4* __restrict__ vertConf,
-                      const float4* __restrict__ colorTime, int& count, int& zCount)
+MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const float4* __restrict__ cleanTex, int& count, int& zCount)
 {
     const int W = P.W, H = P.H;
     const float cols = (float)W, rows = (float)H, ftime = (float)P.time;
@@ -270,8 +275,9 @@ MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const uint32_t*
         for (int b = 0; b < 5; ++b) {
             if (tys[b] < 0 || (b > 0 && tys[b] == tys[b - 1])) continue;
             const int q = tys[b] * W + txs[a];
-            if (idx[q] == 0u) continue;
-            float4 mc = vertConf[q], ct = colorTime[q];
+            const float4 mc = __ldg(cleanTex + 2 * q), tt = __ldg(cleanTex + 2 * q + 1);
+            if (tt.z == 0.f) continue;                                   // idx == 0: empty texel (or surfel 0, N2)
+            float4 ct; ct.z = tt.x; ct.w = tt.y;
             float ddx = mc.x - e.lx, ddy = mc.y - e.ly;
             if (ct.z < e.init && mc.w > P.confThreshold && mc.z > e.lz && mc.z - e.lz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < e.rad * 1.4f)
                 count += mxs[a] * mys[b];
@@ -375,8 +381,7 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
 // clean, pass 1b: one thread per candidate: index-map window (copy_unstable.vert:86-113) + the rest of the shader
 __global__ void __launch_bounds__(256) k_clean_p2(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
                                                   const uint32_t* __restrict__ countPtr, float4* __restrict__ m0, float4* __restrict__ m1,
-                                                  const float4* __restrict__ m2, CleanParams P, const DevPose* __restrict__ dpose, const uint32_t* __restrict__ idx,
-                                                  const float4* __restrict__ vertConf, const float4* __restrict__ colorTime,
+                                                  const float4* __restrict__ m2, CleanParams P, const DevPose* __restrict__ dpose, const float4* __restrict__ cleanTex,
                                                   const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask, uint8_t* __restrict__ keep,
                                                   const uint32_t* __restrict__ cand, const uint32_t* __restrict__ candCount)
 {
@@ -396,7 +401,7 @@ __global__ void __launch_bounds__(256) k_clean_p2(float4* __restrict__ pos, floa
         float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
         CleanEntry ce; ce.xn = x / cols; ce.yn = y / rows; ce.lx = lp.x; ce.ly = lp.y; ce.lz = lp.z; ce.init = vc.z; ce.rad = vn.w; ce.lnz = fabsf(ln.z);
         int c1, c2;
-        cleanWindow(ce, P, idx, vertConf, colorTime, c1, c2);
+        cleanWindow(ce, P, cleanTex, c1, c2);
         bool k = cleanFinish(vp, vc, x, y, lp.z, c1, c2, P, depthFilt, mask);
         if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
         else { m0[p].w = vp.w; m1[p].w = vc.w; }
@@ -530,15 +535,29 @@ MF_D SplatVS splatVertex(float4 p, float4 c, float4 nr, const Rt& tinv, Cam cam,
     return o;
 }
 
-MF_D bool splatFragment(const SplatVS& v, Cam cam, float fcx, float fcy, float3& cp)
+// viewing ray of the pixel centre (combo_splat.frag:39-45).  It depends on the camera alone: k_ray_table evaluates it once
+// per context, the rasteriser reads it back (two IEEE divisions, a square root and three more divisions per FRAGMENT otherwise).
+MF_D float3 pixelRay(Cam cam, float fcx, float fcy)
 {
-    float3 l = normalize3(make_float3((fcx - cam.cx) / cam.fx, (fcy - cam.cy) / cam.fy, 1.0f));
+    return normalize3(make_float3((fcx - cam.cx) / cam.fx, (fcy - cam.cy) / cam.fy, 1.0f));
+}
+__global__ void k_ray_table(Cam cam, int W, int H, float4* __restrict__ tab)
+{
+    int px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y * blockDim.y + threadIdx.y;
+    if (px >= W || py >= H) return;
+    float3 l = pixelRay(cam, (float)px + 0.5f, (float)py + 0.5f);
+    tab[py * W + px] = make_float4(l.x, l.y, l.z, 0.f);
+}
+
+MF_D bool splatFragmentRay(const SplatVS& v, float3 l, float3& cp)
+{
     float t = dot3(v.pos, v.n) / dot3(l, v.n);
     cp = make_float3(t * l.x, t * l.y, t * l.z);
     float sqrRad = v.rad * v.rad;
     float3 d = sub3(cp, v.pos);
     return !(dot3(d, d) > sqrRad);
 }
+MF_D bool splatFragment(const SplatVS& v, Cam cam, float fcx, float fcy, float3& cp) { return splatFragmentRay(v, pixelRay(cam, fcx, fcy), cp); }
 
 MF_D void splatRange(const SplatVS& v, int W, int H, int& x0, int& x1, int& y0, int& y1)
 {
@@ -549,17 +568,20 @@ MF_D void splatRange(const SplatVS& v, int W, int H, int& x0, int& x1, int& y0, 
     y0 = lo < 0 ? 0 : (int)lo; y1 = hi > (float)(H - 1) ? H - 1 : (int)hi;
 }
 
+#define SPLAT_SEG 8
 __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
                                                        const uint32_t* __restrict__ countPtr, const DevPose* __restrict__ dpose, Cam cam, int W, int H,
                                                        float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
-                                                       uint32_t drawBase, unsigned long long* __restrict__ key)
+                                                       uint32_t drawBase, const float4* __restrict__ rayTab, unsigned long long* __restrict__ key)
 {
     const Rt tinv = dpose->tinv;
-    // Flattened rasterisation.  A block projects 256 surfels, compacts the drawable ones with the exclusive
-    // prefix sum of their fragment counts (point-sprite squares, 1 .. 2047^2 pixels) into shared memory, and
-    // then walks the FLATTENED fragment list with all threads: fragment f belongs to the entry found by binary
-    // search in the prefix array.  Perfectly balanced whatever the mix of far (1 px) and near (large) surfels;
-    // the per-thread pixel loop it replaces ran with ~5 of 32 lanes active (ncu, profiles/).
+    // Row-segment rasterisation.  A block projects 256 surfels and compacts the drawable ones into shared memory.  Their point
+    // sprites (1 .. 2047^2 pixels) are cut into UNITS of up to SPLAT_SEG consecutive pixels of one sprite row; the units are
+    // numbered by an exclusive prefix sum and walked by all threads, unit u belonging to the entry found by binary search.
+    // Balanced whatever the mix of far (1 px) and near (large) surfels, and the per-fragment work is the ray/disc test alone:
+    // the search and the unit -> (row, x range) arithmetic are paid once per SPLAT_SEG fragments, the pixel ray comes from the
+    // table.  (One search + one integer division + one ray normalisation per FRAGMENT made this kernel instruction bound:
+    // 139 M warp instructions, ncu r01e; a per-thread pixel loop before that ran with ~5 of 32 lanes active.)
     struct Entry { float px, py, pz, nx, ny, nz, rad; int x0, y0, w; uint32_t id; };
     __shared__ Entry ent[256];
     __shared__ int offs[257];
@@ -585,9 +607,9 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
             }
         }
         const bool draw = v.ok && x1 >= x0 && y1 >= y0;
-        const int nfrag = draw ? (x1 - x0 + 1) * (y1 - y0 + 1) : 0;
-        // block exclusive scans: fragment offsets and compact slots
-        int incl = nfrag;
+        const int nunit = draw ? (y1 - y0 + 1) * ((x1 - x0 + SPLAT_SEG) / SPLAT_SEG) : 0;
+        // block exclusive scans: unit offsets and compact slots
+        int incl = nunit;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
         unsigned db = __ballot_sync(0xffffffffu, draw);
@@ -602,24 +624,31 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
             Entry e; e.px = v.pos.x; e.py = v.pos.y; e.pz = v.pos.z; e.nx = v.n.x; e.ny = v.n.y; e.nz = v.n.z; e.rad = v.rad;
             e.x0 = x0; e.y0 = y0; e.w = x1 - x0 + 1; e.id = drawBase + id;
             ent[slot] = e;
-            offs[slot] = fbase + incl - nfrag;
+            offs[slot] = fbase + incl - nunit;
         }
         if (threadIdx.x == 0) offs[nent] = total;
         __syncthreads();
-        for (int f = threadIdx.x; f < total; f += blockDim.x) {
-            int lo = 0, hi = nent - 1;                       // last entry with offs[e] <= f
-            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (offs[mid] <= f) lo = mid; else hi = mid - 1; }
-            const Entry& e = ent[lo];
-            const int t = f - offs[lo];
-            const int py = e.y0 + t / e.w, px = e.x0 + t - (t / e.w) * e.w;
+        for (int u = threadIdx.x; u < total; u += blockDim.x) {
+            int lo = 0, hi = nent - 1;                       // last entry with offs[e] <= u
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (offs[mid] <= u) lo = mid; else hi = mid - 1; }
+            const Entry e = ent[lo];
+            const int t = u - offs[lo];
+            const int nseg = (e.w + SPLAT_SEG - 1) / SPLAT_SEG;
+            const int row = t / nseg, seg = t - row * nseg;
+            const int py = e.y0 + row, xs = e.x0 + seg * SPLAT_SEG;
+            const int xe = min(xs + SPLAT_SEG, e.x0 + e.w);
             SplatVS sv; sv.pos = make_float3(e.px, e.py, e.pz); sv.n = make_float3(e.nx, e.ny, e.nz); sv.rad = e.rad;
-            float3 cp;
-            if (!splatFragment(sv, cam, (float)px + 0.5f, (float)py + 0.5f, cp)) continue;
-            float fd = (cp.z / (2 * maxDepth)) + 0.5f;
-            if (!(fd >= 0.0f && fd < 1.0f)) continue;
-            unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | e.id;
-            unsigned long long* dst = key + (py * W + px);
-            if (k < *dst) atomicMin(dst, k);
+            const float4* __restrict__ ray = rayTab + py * W;
+            unsigned long long* __restrict__ krow = key + py * W;
+            for (int px = xs; px < xe; ++px) {
+                const float4 l4 = __ldg(ray + px);
+                float3 cp;
+                if (!splatFragmentRay(sv, make_float3(l4.x, l4.y, l4.z), cp)) continue;
+                float fd = (cp.z / (2 * maxDepth)) + 0.5f;
+                if (!(fd >= 0.0f && fd < 1.0f)) continue;
+                unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | e.id;
+                if (k < krow[px]) atomicMin(krow + px, k);
+            }
         }
         __syncthreads();
     }
@@ -630,7 +659,7 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
 // black" counter of MaskFusion::requiresFillIn are fused into the same pass.
 __global__ void k_splat_resolve(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
                                 const DevPose* __restrict__ dpose, Cam cam, int W, int H, float maxDepth, float confThreshold, float ftime, float fmaxTime,
-                                float ftimeDelta, unsigned long long* __restrict__ key,
+                                float ftimeDelta, const float4* __restrict__ rayTab, unsigned long long* __restrict__ key,
                                 uchar4* __restrict__ image, float4* __restrict__ vertexConf, float4* __restrict__ normalRad,
                                 uint16_t* __restrict__ timeTex,
                                 int doFill, const float* __restrict__ depthFilt, const uchar4* __restrict__ rgb, int ptVN, int ptImg,
@@ -651,7 +680,8 @@ __global__ void k_splat_resolve(const float4* __restrict__ pos, const float4* __
         float4 p = pos[id], c = col[id], n = nrm[id];
         SplatVS v = splatVertex(p, c, n, tinv, cam, W, H, maxDepth, confThreshold, ftime, fmaxTime, ftimeDelta);
         float3 cp; float fcx = (float)px + 0.5f, fcy = (float)py + 0.5f;
-        splatFragment(v, cam, fcx, fcy, cp);
+        const float4 l4 = __ldg(rayTab + i);
+        splatFragmentRay(v, make_float3(l4.x, l4.y, l4.z), cp);
         float3 cl = decodeColor(c.x);
         im = make_uchar4((uint8_t)(int)floorf(cl.x * 255.0f + 0.5f), (uint8_t)(int)floorf(cl.y * 255.0f + 0.5f),
                          (uint8_t)(int)floorf(cl.z * 255.0f + 0.5f), 255);
@@ -827,12 +857,12 @@ void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s) { if (n)
 void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s) { if (n) k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((unsigned long long*)p, v, n); }
 
 void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth, int time,
-                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, cudaStream_t s)
+                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, float4* cleanTex, cudaStream_t s)
 {
     prof_mark(s, "k_index_project"); k_index_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, count, tinv, cam, W, H, maxDepth, (float)time, (float)timeDelta,
                                                         (unsigned long long*)key);
     int P = W * H;
-    prof_mark(s, "k_index_resolve"); k_index_resolve<<<(P + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, P, (unsigned long long*)key, idx, vertConf, colorTime, normRad);
+    prof_mark(s, "k_index_resolve"); k_index_resolve<<<(P + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, P, (unsigned long long*)key, idx, vertConf, colorTime, normRad, cleanTex);
 }
 
 void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
@@ -853,7 +883,7 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
 
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
-                  float outlierCoeff, uint8_t maskID, const uint32_t* idx, const float4* vertConf, const float4* colorTime,
+                  float outlierCoeff, uint8_t maskID, const float4* cleanTex,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s)
 {
     CleanParams P;
@@ -863,7 +893,7 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
     int Ppix = W * H;
     int blocks = persistentBlocks(4);
     prof_mark(s, "k_clean_p1"); k_clean_p1<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, count, aflag, meas[0], meas[1], Ppix, P, tinv, depthFilt, mask, keep, cand, candCount);
-    prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, idx, vertConf, colorTime, depthFilt,
+    prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, cleanTex, depthFilt,
                                                                                mask, keep, cand, candCount);
     prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<blocks, SCAN_BLOCK, 0, s>>>(keep, count, Ppix, blockSums, candCount);
     prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount);
@@ -871,17 +901,23 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
                                                   dst.pos, dst.col, dst.nrm);
 }
 
+void launch_ray_table(Cam cam, int W, int H, float4* tab, cudaStream_t s)
+{
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    k_ray_table<<<g, b, 0, s>>>(cam, W, H, tab);
+}
+
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth,
-                             float confThreshold, int time, int maxTime, int timeDelta, uint64_t* key, uchar4* image, float4* vertexConf,
+                             float confThreshold, int time, int maxTime, int timeDelta, const float4* rayTab, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
                              uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s)
 {
     prof_mark(s, "k_splat_project"); k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
-                                                        (float)maxTime, (float)timeDelta, 0u, (unsigned long long*)key);
+                                                        (float)maxTime, (float)timeDelta, 0u, rayTab, (unsigned long long*)key);
     if (nonBlackSamples) cudaMemsetAsync(nonBlackSamples, 0, sizeof(uint32_t), s);
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
     prof_mark(s, "k_splat_resolve"); k_splat_resolve<<<g, b, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, cam, W, H, maxDepth, confThreshold, (float)time, (float)maxTime,
-                                    (float)timeDelta, (unsigned long long*)key, image, vertexConf, normalRad, timeTex, doFill, depthFilt, rgb,
+                                    (float)timeDelta, rayTab, (unsigned long long*)key, image, vertexConf, normalRad, timeTex, doFill, depthFilt, rgb,
                                     ptVN, ptImg, fillImage, fillVertex, fillNormal, nonBlackSamples);
 }
 
@@ -905,10 +941,10 @@ void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, 
 namespace mfb {
 // splat projection into a caller-owned key image (GlobalProjection: all models share one key image)
 void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth, float confThreshold,
-                               int time, int maxTime, int timeDelta, uint32_t drawBase, uint64_t* key, cudaStream_t s)
+                               int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s)
 {
     prof_mark(s, "k_splat_project_ids");
     k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
-                                                        (float)maxTime, (float)timeDelta, drawBase, (unsigned long long*)key);
+                                                        (float)maxTime, (float)timeDelta, drawBase, rayTab, (unsigned long long*)key);
 }
 }  // namespace mfb

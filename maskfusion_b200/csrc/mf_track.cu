@@ -453,17 +453,20 @@ __device__ __forceinline__ bool ldltSolve3Fast(const double* A, const double* b,
 
 // entry e = (r, c) of the inverse of a 3x3: cofactor(c, r) / det with cyclic indices (no sign bookkeeping, no divergent
 // switch: a 9-way switch serialised the nine lanes, ncu r01d).  Products and differences are the ones inv3d forms.
+// M is read in place with row stride LD (3 for a 3x3, 4 for the rotation block of a 4x4): no local copies.
+template <int LD>
 MF_D double inv3dEntry(const double* M, int e)
 {
     const int r = e / 3, c = e - 3 * r;
     const int c1 = c == 2 ? 0 : c + 1, c2 = c1 == 2 ? 0 : c1 + 1, r1 = r == 2 ? 0 : r + 1, r2 = r1 == 2 ? 0 : r1 + 1;
-    const double cof = M[c1 * 3 + r1] * M[c2 * 3 + r2] - M[c1 * 3 + r2] * M[c2 * 3 + r1];
-    const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    const double cof = M[c1 * LD + r1] * M[c2 * LD + r2] - M[c1 * LD + r2] * M[c2 * LD + r1];
+    const double c00 = M[LD + 1] * M[2 * LD + 2] - M[LD + 2] * M[2 * LD + 1], c01 = M[LD + 2] * M[2 * LD] - M[LD] * M[2 * LD + 2],
+                 c02 = M[LD] * M[2 * LD + 1] - M[LD + 1] * M[2 * LD];
     const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
     return cof * (1.0 / det);
 }
 
-struct SolveScratch { double A[36], b[6], x[6], Rt[16], nr[16], Ri[9], Kinv[9], tmp[9], ti[3]; float trR[9], trT[3], iR[9], iT[3]; int fast; };
+struct SolveScratch { double A[36], b[6], x[6], Rt[16], nr[16], Ri[9], K[9], Kinv[9], tmp[9], ti[3]; float trR[9], trT[3], iR[9], iT[3]; int fast; };
 
 MF_D double shflD(double v, int src)
 {
@@ -532,11 +535,8 @@ MF_D bool ldltSolve6Warp(const double* __restrict__ A, const double* __restrict_
 MF_D void computeWarpCoop(TrackState* st, Cam c, SolveScratch* sc, int lane)
 {
     const double* T = st->resultRt;
-    const double K[9] = {c.fx, 0, c.cx, 0, c.fy, c.cy, 0, 0, 1};
-    if (lane < 9) {
-        double R3[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
-        sc->Ri[lane] = inv3dEntry(R3, lane);
-    }
+    const double* K = sc->K;
+    if (lane < 9) sc->Ri[lane] = inv3dEntry<4>(T, lane);
     __syncwarp();
     if (lane < 3) sc->ti[lane] = -(sc->Ri[lane * 3] * T[3] + sc->Ri[lane * 3 + 1] * T[7] + sc->Ri[lane * 3 + 2] * T[11]);
     if (lane < 9) { int r = lane / 3, cc = lane % 3; sc->tmp[lane] = K[r * 3] * sc->Ri[cc] + K[r * 3 + 1] * sc->Ri[3 + cc] + K[r * 3 + 2] * sc->Ri[6 + cc]; }
@@ -584,12 +584,13 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
             else if (cc == 3) v = sc->x[r];
             else if (!rot) v = r == cc ? 1.0 : 0.0;
             else {
-                const double u[3] = {rx, ry, rz};
-                const double rrt = u[r] * u[cc];
+                const double ur = r == 0 ? rx : r == 1 ? ry : rz, uc = cc == 0 ? rx : cc == 1 ? ry : rz;
+                const double rrt = ur * uc;
                 // [r]_x entries: (0,1) -rz (0,2) ry (1,0) rz (1,2) -rx (2,0) -ry (2,1) rx
                 const int d = cc - r;                                  // +-1, +-2
                 const int o = 3 - r - cc;                              // the third index
-                const double rxm = (r == cc) ? 0.0 : ((d == 1 || d == -2) ? -u[o] : u[o]);
+                const double uo = o == 0 ? rx : o == 1 ? ry : rz;
+                const double rxm = (r == cc) ? 0.0 : ((d == 1 || d == -2) ? -uo : uo);
                 v = c * (r == cc ? 1.0 : 0.0) + c1 * rrt + s * rxm;
             }
             sc->Rt[lane] = v;
@@ -799,15 +800,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         const float* __restrict__ nextDepth = J.lastDepth[level];      // reference quirk: both pyramids derive from vmaps_tmp (RGBDOdometry.cpp:187-215)
         const uint8_t* __restrict__ lastImage = J.lastImage[level];
         const uint8_t* __restrict__ nextImage = J.nextImage[level];
-        uint8_t* __restrict__ rgbValid = J.rgbValid[level];
+        const uint8_t* __restrict__ rgbValid = J.rgbValid[level];         // pose-independent validity, written by k_sobel
         if (threadIdx.x < 32) {
             if (threadIdx.x == 0) { st->levelBreak = 0; st->lastRGBError = FLT_MAX; }
-            if (threadIdx.x < 9) { const double K[9] = {cam.fx, 0, cam.cx, 0, cam.fy, cam.cy, 0, 0, 1}; sc.Kinv[threadIdx.x] = inv3dEntry(K, threadIdx.x); }
+            if (threadIdx.x < 9) {
+                const int r = threadIdx.x / 3, cc = threadIdx.x % 3;
+                sc.K[threadIdx.x] = r == cc ? (r == 0 ? (double)cam.fx : r == 1 ? (double)cam.fy : 1.0) : (cc == 2 ? (r == 0 ? (double)cam.cx : (double)cam.cy) : 0.0);
+            }
+            __syncwarp();
+            if (threadIdx.x < 9) sc.Kinv[threadIdx.x] = inv3dEntry<3>(sc.K, threadIdx.x);
             __syncwarp();
             if (tp.rgb) computeWarpCoop(st, cam, &sc, threadIdx.x);
         }
-        if (tp.rgb)                                                     // validity is pose independent: once per level, same thread reads it back
-            for (int r = 0; r < rounds; ++r) { const int k = tid + r * nthr; rgbValid[k] = rgbValidPixel(nextImage, grad, W, H, k, tp.minScale[level]) ? 1 : 0; }
         __syncthreads();
 
         // pose-independent inputs of pixel k
@@ -1018,6 +1022,13 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
 }
 
 // ------------------------------ host launchers ----------------------------------------
+float track_min_scale(int level)
+{
+    const float minGrad[3] = {5, 3, 1};
+    const float sobelScale = (float)(1.0 / 8.0);
+    return (float)(pow((double)minGrad[level], 2.0) / pow((double)sobelScale, 2.0));
+}
+
 static int trackBlocks(int N, int numSMs)
 {
     int need = (N + TRK_THREADS - 1) / TRK_THREADS;
@@ -1045,8 +1056,7 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     tp.icpWeight = icpWeight;
     tp.angleThres = (float)sin(20.f * 3.14159254f / 180.f);
     tp.distThres = 0.10f; tp.sobelScale = (float)(1.0 / 8.0); tp.maxDepthDelta = 0.07f;
-    const float minGrad[3] = {5, 3, 1};
-    for (int l = 0; l < 3; ++l) tp.minScale[l] = (float)(pow((double)minGrad[l], 2.0) / pow((double)tp.sobelScale, 2.0));
+    for (int l = 0; l < 3; ++l) tp.minScale[l] = track_min_scale(l);
     int G = numSMs / nJobs;                      // one CTA per SM, the SMs split between the tracked models
     if (G * nJobs > coResident) G = coResident / nJobs;
     if (G > TRACK_MAX_BLOCKS / 2) G = TRACK_MAX_BLOCKS / 2;
