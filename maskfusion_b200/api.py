@@ -62,9 +62,13 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
-        raise MFError(f"{LIB_PATH} not found: run `python -m maskfusion_b200.build` (there is no CPU fallback)")
-    L = C.CDLL(LIB_PATH)
+    path = LIB_PATH
+    tag = os.environ.get("MFB200_TAG")          # A/B builds of the same library (maskfusion_b200/build.py), e.g. another CTA shape
+    if tag:
+        path = LIB_PATH.replace(".so", f"_{tag}.so")
+    if not os.path.exists(path):
+        raise MFError(f"{path} not found: run `python -m maskfusion_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(path)
     L.mf_last_error.restype = C.c_char_p
     L.mf_create.restype = C.c_void_p
     L.mf_create.argtypes = [C.POINTER(Config), C.c_int, C.c_void_p]

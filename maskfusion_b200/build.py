@@ -18,8 +18,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libmaskfusion_b200.so")
-OBJ_DIR = os.path.join(HERE, "build")
+# A/B experiments: MFB200_DEFINES="-DPT_THREADS=544 ..." MFB200_TAG=alt builds libmaskfusion_b200_alt.so next to the default library
+TAG = os.environ.get("MFB200_TAG", "")
+EXTRA_DEFINES = os.environ.get("MFB200_DEFINES", "").split()
+OUT = os.path.join(HERE, "libmaskfusion_b200%s.so" % ("_" + TAG if TAG else ""))
+OBJ_DIR = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -54,7 +57,7 @@ def _compile(src: str, verbose: bool):
     hdrs.append(os.path.join(HERE, "..", "include", "maskfusion_b200.h"))
     if os.path.exists(obj) and all(os.path.getmtime(obj) > os.path.getmtime(d) for d in [srcp, __file__] + hdrs):
         return obj
-    cmd = [NVCC] + ARCH + COMMON + SOURCES[src] + ["-c", srcp, "-o", obj]
+    cmd = [NVCC] + ARCH + COMMON + SOURCES[src] + EXTRA_DEFINES + ["-c", srcp, "-o", obj]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)

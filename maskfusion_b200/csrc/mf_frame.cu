@@ -103,13 +103,91 @@ __global__ void k_pyrdown_u8(const uint8_t* __restrict__ src, int sw, int sh, ui
     dst[y * dw + x] = (r != r) ? 0 : (uint8_t)(int)r;
 }
 
+// Two pyramid levels in ONE launch: a block owns a PY_TX x PY_TY tile of the coarse level; it first evaluates the (2*PY_TX+3) x
+// (2*PY_TY+3) patch of the middle level that tile reads (same arithmetic as the single-level kernels, straight from the fine
+// level), keeps it in shared memory, writes the part it owns, then decimates the patch.  Bit-identical outputs, half the launches
+// (these images are 76 800 / 19 200 pixels: the launches, not the arithmetic, were the cost -- 8 of them per frame).
+#define PY_TX 16
+#define PY_TY 8
+struct PyrF {
+    typedef float T;
+    static __device__ __forceinline__ bool ok(float v) { return !isnan(v); }
+    static __device__ __forceinline__ float val(float v) { return v; }
+    static __device__ __forceinline__ float fin(float sum, int count) { return sum / (float)count; }
+};
+struct PyrU8 {
+    typedef uint8_t T;
+    static __device__ __forceinline__ bool ok(uint8_t v) { return v > 0; }
+    static __device__ __forceinline__ float val(uint8_t v) { return (float)v; }
+    static __device__ __forceinline__ uint8_t fin(float sum, int count) { float r = sum / (float)count; return (r != r) ? 0 : (uint8_t)(int)r; }
+};
+template <typename TR, typename Src>
+MF_D typename TR::T pyrPixel(Src src, int sw, int sh, int x, int y)
+{
+    const int D = 5;
+    int tx = min(2 * x - D / 2 + D, sw - 1), ty = min(2 * y - D / 2 + D, sh - 1);
+    float sum = 0; int count = 0;
+    for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
+        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
+            typename TR::T v = src(cx, cy);
+            if (TR::ok(v)) {
+                float g = c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
+                sum += TR::val(v) * g;
+                count = (int)((float)count + g);
+            }
+        }
+    return TR::fin(sum, count);
+}
+template <typename TR>
+__global__ void __launch_bounds__(256) k_pyrdown2(const typename TR::T* __restrict__ src, int sw, int sh, typename TR::T* __restrict__ dst1,
+                                                  typename TR::T* __restrict__ dst2)
+{
+    typedef typename TR::T T;
+    constexpr int MW = 2 * PY_TX + 3, MH = 2 * PY_TY + 3;
+    __shared__ T mid[MH][MW + 1];
+    const int w1 = sw / 2, h1 = sh / 2, w2 = w1 / 2, h2 = h1 / 2;
+    const int X0 = blockIdx.x * PY_TX, Y0 = blockIdx.y * PY_TY;              // coarse tile origin
+    const int mx0 = 2 * X0 - 2, my0 = 2 * Y0 - 2;                            // middle-level patch origin
+    for (int t = threadIdx.x; t < MW * MH; t += blockDim.x) {
+        const int py = t / MW, px = t - py * MW;
+        const int x = mx0 + px, y = my0 + py;
+        T v = T(0);
+        if (x >= 0 && y >= 0 && x < w1 && y < h1) {
+            v = pyrPixel<TR>([&](int cx, int cy) { return src[cy * sw + cx]; }, sw, sh, x, y);
+            if (px >= 2 && px < 2 + 2 * PY_TX && py >= 2 && py < 2 + 2 * PY_TY) dst1[y * w1 + x] = v;      // owned part of the middle level
+        }
+        mid[py][px] = v;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < PY_TX * PY_TY; t += blockDim.x) {
+        const int ly = t / PY_TX, lx = t - ly * PY_TX;
+        const int x = X0 + lx, y = Y0 + ly;
+        if (x < w2 && y < h2) dst2[y * w2 + x] = pyrPixel<TR>([&](int cx, int cy) { return mid[cy - my0][cx - mx0]; }, w1, h1, x, y);
+    }
+}
+
+// three pyramid levels of one per-pixel kernel in a single launch: blockIdx.z = level
+struct Maps3 { const float* depth[3]; float4* vmap[3]; float4* nmap[3]; float4* cloud[3]; const uint8_t* img[3]; short2* grad[3]; uint8_t* valid[3]; float minScale[3]; };
+
 // depth -> vertex map + forward-difference normal map in ONE pass (the three vertices a
 // normal needs are rebuilt from depth; saves the vmap round trip through HBM).
+MF_D void vmapNmapPixel(const float* __restrict__ depth, int W, int H, Cam cam, float cutoff, float4* __restrict__ vmap, float4* __restrict__ nmap, int u, int v);
 __global__ void k_vmap_nmap(const float* __restrict__ depth, int W, int H, Cam cam, float cutoff,
                             float4* __restrict__ vmap, float4* __restrict__ nmap)
 {
     int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
     if (u >= W || v >= H) return;
+    vmapNmapPixel(depth, W, H, cam, cutoff, vmap, nmap, u, v);
+}
+__global__ void k_vmap_nmap3(Maps3 m, int W0, int H0, Cam cam0, float cutoff)
+{
+    const int l = blockIdx.z, W = W0 >> l, H = H0 >> l;
+    int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
+    if (u >= W || v >= H) return;
+    vmapNmapPixel(m.depth[l], W, H, camLevel(cam0, l), cutoff, m.vmap[l], m.nmap[l], u, v);
+}
+MF_D void vmapNmapPixel(const float* __restrict__ depth, int W, int H, Cam cam, float cutoff, float4* __restrict__ vmap, float4* __restrict__ nmap, int u, int v)
+{
     const float fx_inv = 1.f / cam.fx, fy_inv = 1.f / cam.fy;
     auto vert = [&](int uu, int vv, float3& o) -> bool {
         float z = depth[vv * W + uu];
@@ -157,10 +235,22 @@ __constant__ float c_soby[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f
 // + the pose-independent half of residualKernel (reduce.cu:821-845): a pixel can enter the photometric term only if its 4x4
 // neighbourhood of intensities is non-zero and its own gradient magnitude passes the level's gate.  Frame-side, shared by all
 // models and all Gauss-Newton iterations (the tracker used to re-derive it per model per level).
+MF_D void sobelPixel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad, float minScale, uint8_t* __restrict__ rgbValid, int x, int y);
 __global__ void k_sobel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad, float minScale, uint8_t* __restrict__ rgbValid)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
+    sobelPixel(src, W, H, grad, minScale, rgbValid, x, y);
+}
+__global__ void k_sobel3(Maps3 m, int W0, int H0)
+{
+    const int l = blockIdx.z, W = W0 >> l, H = H0 >> l;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    sobelPixel(m.img[l], W, H, m.grad[l], m.minScale[l], m.valid[l], x, y);
+}
+MF_D void sobelPixel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad, float minScale, uint8_t* __restrict__ rgbValid, int x, int y)
+{
     float dxv = 0, dyv = 0; int k = 8;
     for (int j = max(y - 1, 0); j <= min(y + 1, H - 1); ++j)
         for (int i = max(x - 1, 0); i <= min(x + 1, W - 1); ++i) {
@@ -291,6 +381,16 @@ __global__ void k_project_points(const float* __restrict__ depth, int W, int H, 
     float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
     cloud[y * W + x] = make_float4(((float)x - cam.cx) * z * ifx, ((float)y - cam.cy) * z * ify, z, 0.f);   // cudafuncs.cu:718-736
 }
+__global__ void k_project_points3(Maps3 m, int W0, int H0, Cam cam0)
+{
+    const int l = blockIdx.z, W = W0 >> l, H = H0 >> l;
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    const Cam cam = camLevel(cam0, l);
+    float z = m.depth[l][y * W + x];
+    float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
+    m.cloud[l][y * W + x] = make_float4(((float)x - cam.cx) * z * ifx, ((float)y - cam.cy) * z * ify, z, 0.f);
+}
 
 // ------------------------------ host launchers ----------------------------------------
 static inline dim3 grid2(int w, int h, dim3 b) { return dim3((w + b.x - 1) / b.x, (h + b.y - 1) / b.y); }
@@ -310,6 +410,37 @@ void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStr
 {
     dim3 b(32, 8);
     prof_mark(s, "k_pyrdown_u8"); k_pyrdown_u8<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
+}
+void launch_pyrdown2_f(const float* src, int sw, int sh, float* dst1, float* dst2, cudaStream_t s)
+{
+    dim3 g((sw / 4 + PY_TX - 1) / PY_TX, (sh / 4 + PY_TY - 1) / PY_TY);
+    prof_mark(s, "k_pyrdown2_f"); k_pyrdown2<PyrF><<<g, 256, 0, s>>>(src, sw, sh, dst1, dst2);
+}
+void launch_pyrdown2_u8(const uint8_t* src, int sw, int sh, uint8_t* dst1, uint8_t* dst2, cudaStream_t s)
+{
+    dim3 g((sw / 4 + PY_TX - 1) / PY_TX, (sh / 4 + PY_TY - 1) / PY_TY);
+    prof_mark(s, "k_pyrdown2_u8"); k_pyrdown2<PyrU8><<<g, 256, 0, s>>>(src, sw, sh, dst1, dst2);
+}
+void launch_vmap_nmap3(const float* const* depth, int W, int H, Cam cam, float cutoff, float4* const* vmap, float4* const* nmap, cudaStream_t s)
+{
+    Maps3 m = {};
+    for (int l = 0; l < 3; ++l) { m.depth[l] = depth[l]; m.vmap[l] = vmap[l]; m.nmap[l] = nmap[l]; }
+    dim3 b(32, 8), g = grid2(W, H, b); g.z = 3;
+    prof_mark(s, "k_vmap_nmap3"); k_vmap_nmap3<<<g, b, 0, s>>>(m, W, H, cam, cutoff);
+}
+void launch_sobel3(const uint8_t* const* img, int W, int H, short2* const* grad, uint8_t* const* rgbValid, cudaStream_t s)
+{
+    Maps3 m = {};
+    for (int l = 0; l < 3; ++l) { m.img[l] = img[l]; m.grad[l] = grad[l]; m.valid[l] = rgbValid[l]; m.minScale[l] = track_min_scale(l); }
+    dim3 b(32, 8), g = grid2(W, H, b); g.z = 3;
+    prof_mark(s, "k_sobel3"); k_sobel3<<<g, b, 0, s>>>(m, W, H);
+}
+void launch_project_points3(const float* const* depth, int W, int H, Cam cam, float4* const* cloud, cudaStream_t s)
+{
+    Maps3 m = {};
+    for (int l = 0; l < 3; ++l) { m.depth[l] = depth[l]; m.cloud[l] = cloud[l]; }
+    dim3 b(32, 8), g = grid2(W, H, b); g.z = 3;
+    prof_mark(s, "k_project_points3"); k_project_points3<<<g, b, 0, s>>>(m, W, H, cam);
 }
 void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s)
 {

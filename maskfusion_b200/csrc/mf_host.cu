@@ -147,7 +147,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     }
     lastNextImage2.alloc((size_t)(W >> 2) * (H >> 2)); lastNextImage2.zero(s);
     trackState.alloc(1); trackState.zero(s);
-    partial.alloc((size_t)TRACK_MAX_BLOCKS * 64);
+    partial.alloc((size_t)TRACK_MAX_BLOCKS * 64); partial.zero(s);      // row tags start at 0: never a valid tag
     dpose.alloc(1); pushPose();
     o->launches += 3;
 }
@@ -197,11 +197,13 @@ void Model::prepareTracking()
     o->launches += 1;
     const bool rgb = o->cfg.rgbOnly || o->cfg.icpWeight < 100;
     if (rgb) {
-        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_f(lastDepth[l], W >> l, H >> l, lastDepth[l + 1], s);
+        launch_pyrdown2_f(lastDepth[0], W, H, lastDepth[1], lastDepth[2], s);
         launch_intensity_select(splatImage, fillIn ? fillImage.p : splatImage.p, nb, denom, (o->cfg.frameToFrameRGB && fillIn) ? 1 : 0, o->P, lastImage[0], s);
-        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(lastImage[l], W >> l, H >> l, lastImage[l + 1], s);
-        for (int l = 0; l < 3; ++l) launch_project_points(lastDepth[l], W >> l, H >> l, camLevel(o->cam, l), cloud[l], s);
-        o->launches += 8;
+        launch_pyrdown2_u8(lastImage[0], W, H, lastImage[1], lastImage[2], s);
+        const float* d3[3] = {lastDepth[0].p, lastDepth[1].p, lastDepth[2].p};
+        float4* c3[3] = {cloud[0].p, cloud[1].p, cloud[2].p};
+        launch_project_points3(d3, W, H, o->cam, c3, s);
+        o->launches += 4;
     }
 }
 
@@ -342,9 +344,11 @@ void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint
 void MaskFusion::generateCUDATextures()
 {
     const float* d[3] = {depthFilt.p, depthPyr[1].p, depthPyr[2].p};
-    for (int l = 1; l < 3; ++l) launch_pyrdown_f(d[l - 1], W >> (l - 1), H >> (l - 1), depthPyr[l], stream);
-    for (int l = 0; l < 3; ++l) launch_vmap_nmap(d[l], W >> l, H >> l, camLevel(cam, l), cfg.depthCutoff, vmap[l], nmap[l], stream);
-    launches += 5;
+    float4* v3[3] = {vmap[0].p, vmap[1].p, vmap[2].p};
+    float4* n3[3] = {nmap[0].p, nmap[1].p, nmap[2].p};
+    launch_pyrdown2_f(depthFilt, W, H, depthPyr[1], depthPyr[2], stream);
+    launch_vmap_nmap3(d, W, H, cam, cfg.depthCutoff, v3, n3, stream);
+    launches += 2;
     frameMapsValid = true;
 }
 
@@ -358,9 +362,15 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
     if ((rgbTerm || cfg.so3) && !intensityValid) {
         // frame side of RGBDOdometry::initRGB (RGBDOdometry.cpp:212-215): shared by all models
         launch_intensity(rgb, P, nextImage[0], stream);
-        for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
-        launches += 3;
-        if (rgbTerm) { for (int l = 0; l < 3; ++l) launch_sobel(nextImage[l], W >> l, H >> l, nextGrad[l], track_min_scale(l), rgbValid[l], stream); launches += 3; }
+        launch_pyrdown2_u8(nextImage[0], W, H, nextImage[1], nextImage[2], stream);
+        launches += 2;
+        if (rgbTerm) {
+            const uint8_t* i3[3] = {nextImage[0].p, nextImage[1].p, nextImage[2].p};
+            short2* g3[3] = {nextGrad[0].p, nextGrad[1].p, nextGrad[2].p};
+            uint8_t* r3[3] = {rgbValid[0].p, rgbValid[1].p, rgbValid[2].p};
+            launch_sobel3(i3, W, H, g3, r3, stream);
+            launches += 1;
+        }
         intensityValid = true;
     }
     for (size_t j = 0; j < ms.size(); ++j) {

@@ -125,6 +125,12 @@ void launch_unpack_rgb(const uint8_t* rgb3, uchar4* out, int P, cudaStream_t s);
 void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t s);
 void launch_pyrdown_f(const float* src, int sw, int sh, float* dst, cudaStream_t s);
 void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStream_t s);
+// fused variants: two pyramid levels per launch; three levels of a per-pixel kernel per launch (blockIdx.z = level)
+void launch_pyrdown2_f(const float* src, int sw, int sh, float* dst1, float* dst2, cudaStream_t s);
+void launch_pyrdown2_u8(const uint8_t* src, int sw, int sh, uint8_t* dst1, uint8_t* dst2, cudaStream_t s);
+void launch_vmap_nmap3(const float* const* depth, int W, int H, Cam cam, float cutoff, float4* const* vmap, float4* const* nmap, cudaStream_t s);
+void launch_sobel3(const uint8_t* const* img, int W, int H, short2* const* grad, uint8_t* const* rgbValid, cudaStream_t s);
+void launch_project_points3(const float* const* depth, int W, int H, Cam cam, float4* const* cloud, cudaStream_t s);
 void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s);
 void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s);
 void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s);

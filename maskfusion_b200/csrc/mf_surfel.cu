@@ -267,22 +267,43 @@ MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const float4* _
 #pragma unroll
         for (int c = 0; c < 5; ++c) { mxs[a] += (txs[c] == txs[a]) ? 1 : 0; mys[a] += (tys[c] == tys[a]) ? 1 : 0; }
     }
-    count = 0; zCount = 0;
+    // The tap coordinates are monotone and span two texels: at most three DISTINCT columns / rows, equal ones adjacent.
+    // Compact them (texel, multiplicity) so that the loads of a whole window row can be issued together: walked one texel at a
+    // time every tap paid a full L2 round trip before the next address was even formed (54 % of this kernel, ncu r01g).
+    int ux[3] = {0, 0, 0}, wx[3] = {0, 0, 0}, uy[3] = {0, 0, 0}, wy[3] = {0, 0, 0};
+    int nux = 0, nuy = 0;
 #pragma unroll
     for (int a = 0; a < 5; ++a) {
-        if (txs[a] < 0 || (a > 0 && txs[a] == txs[a - 1])) continue;
+        if (!(txs[a] < 0 || (a > 0 && txs[a] == txs[a - 1]))) {
 #pragma unroll
-        for (int b = 0; b < 5; ++b) {
-            if (tys[b] < 0 || (b > 0 && tys[b] == tys[b - 1])) continue;
-            const int q = tys[b] * W + txs[a];
-            const float4 mc = __ldg(cleanTex + 2 * q), tt = __ldg(cleanTex + 2 * q + 1);
-            if (tt.z == 0.f) continue;                                   // idx == 0: empty texel (or surfel 0, N2)
-            float4 ct; ct.z = tt.x; ct.w = tt.y;
-            float ddx = mc.x - e.lx, ddy = mc.y - e.ly;
-            if (ct.z < e.init && mc.w > P.confThreshold && mc.z > e.lz && mc.z - e.lz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < e.rad * 1.4f)
-                count += mxs[a] * mys[b];
-            if (ct.w == ftime && mc.w > P.confThreshold && mc.z > e.lz && mc.z - e.lz > 0.01f && e.lnz > 0.85f)
-                zCount += mxs[a] * mys[b];
+            for (int k = 0; k < 3; ++k) if (k == nux) { ux[k] = txs[a]; wx[k] = mxs[a]; }
+            ++nux;
+        }
+        if (!(tys[a] < 0 || (a > 0 && tys[a] == tys[a - 1]))) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) if (k == nuy) { uy[k] = tys[a]; wy[k] = mys[a]; }
+            ++nuy;
+        }
+    }
+    count = 0; zCount = 0;
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        if (b >= nuy) break;
+        float4 mc[3], tt[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                        // slots beyond nux repeat column 0 (weight 0): the loads are unconditional
+            const int q = uy[b] * W + ux[k];
+            mc[k] = __ldg(cleanTex + 2 * q); tt[k] = __ldg(cleanTex + 2 * q + 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (k >= nux || tt[k].z == 0.f) continue;        // idx == 0: empty texel (or surfel 0, N2)
+            const float initT = tt[k].x, lastT = tt[k].y;
+            const float ddx = mc[k].x - e.lx, ddy = mc[k].y - e.ly;
+            if (initT < e.init && mc[k].w > P.confThreshold && mc[k].z > e.lz && mc[k].z - e.lz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < e.rad * 1.4f)
+                count += wx[k] * wy[b];
+            if (lastT == ftime && mc[k].w > P.confThreshold && mc[k].z > e.lz && mc[k].z - e.lz > 0.01f && e.lnz > 0.85f)
+                zCount += wx[k] * wy[b];
         }
     }
 }
@@ -379,7 +400,7 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
 }
 
 // clean, pass 1b: one thread per candidate: index-map window (copy_unstable.vert:86-113) + the rest of the shader
-__global__ void __launch_bounds__(256) k_clean_p2(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
+__global__ void __launch_bounds__(256, 4) k_clean_p2(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
                                                   const uint32_t* __restrict__ countPtr, float4* __restrict__ m0, float4* __restrict__ m1,
                                                   const float4* __restrict__ m2, CleanParams P, const DevPose* __restrict__ dpose, const float4* __restrict__ cleanTex,
                                                   const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask, uint8_t* __restrict__ keep,
@@ -569,7 +590,10 @@ MF_D void splatRange(const SplatVS& v, int W, int H, int& x0, int& x1, int& y0, 
 }
 
 #define SPLAT_SEG 8
-__global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
+#ifndef SPLAT_BS
+#define SPLAT_BS 128               // surfels (= threads) per block round: smaller rounds interleave the load phase of one block with the raster phase of another
+#endif
+__global__ void __launch_bounds__(SPLAT_BS) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
                                                        const uint32_t* __restrict__ countPtr, const DevPose* __restrict__ dpose, Cam cam, int W, int H,
                                                        float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
                                                        uint32_t drawBase, const float4* __restrict__ rayTab, unsigned long long* __restrict__ key)
@@ -583,18 +607,23 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
     // table.  (One search + one integer division + one ray normalisation per FRAGMENT made this kernel instruction bound:
     // 139 M warp instructions, ncu r01e; a per-thread pixel loop before that ran with ~5 of 32 lanes active.)
     struct Entry { float px, py, pz, nx, ny, nz, rad; int x0, y0, w; uint32_t id; };
-    __shared__ Entry ent[256];
-    __shared__ int offs[257];
-    __shared__ int wtot[8], wcnt[8];
+    constexpr int NW = SPLAT_BS / 32;
+    __shared__ Entry ent[SPLAT_BS];
+    __shared__ int offs[SPLAT_BS + 1];
+    __shared__ int wtot[NW], wcnt[NW];
     const uint32_t count = *countPtr;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t stride = gridDim.x * blockDim.x;
+    const float inv2md = 1.0f / (2 * maxDepth);
+    float4 pNext = make_float4(0, 0, 0, 0);
+    if (blockIdx.x * blockDim.x + threadIdx.x < count) pNext = ldStream(pos + blockIdx.x * blockDim.x + threadIdx.x);
     for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += stride) {
         const uint32_t id = base + threadIdx.x;
         SplatVS v; v.ok = false;
         int x0 = 0, x1 = -1, y0 = 0, y1 = -1;
+        const float4 p = pNext;
+        if (id + stride < count) pNext = ldStream(pos + id + stride);      // next round's position streams in behind this round's raster
         if (id < count) {
-            float4 p = ldStream(pos + id);
             // cheap rejects before touching the other two planes
             float3 ph = xform(tinv, make_float3(p.x, p.y, p.z));
             // ... including the point-clipping test on the projected centre (same arithmetic as splatVertex), which most
@@ -618,7 +647,7 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
         __syncthreads();
         int fbase = 0, sbase = 0, total = 0, nent = 0;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { if (w < warp) { fbase += wtot[w]; sbase += wcnt[w]; } total += wtot[w]; nent += wcnt[w]; }
+        for (int w = 0; w < NW; ++w) { if (w < warp) { fbase += wtot[w]; sbase += wcnt[w]; } total += wtot[w]; nent += wcnt[w]; }
         if (draw) {
             const int slot = sbase + __popc(db & ((1u << lane) - 1));
             Entry e; e.px = v.pos.x; e.py = v.pos.y; e.pz = v.pos.z; e.nx = v.n.x; e.ny = v.n.y; e.nz = v.n.z; e.rad = v.rad;
@@ -640,14 +669,31 @@ __global__ void __launch_bounds__(256) k_splat_project(const float4* __restrict_
             SplatVS sv; sv.pos = make_float3(e.px, e.py, e.pz); sv.n = make_float3(e.nx, e.ny, e.nz); sv.rad = e.rad;
             const float4* __restrict__ ray = rayTab + py * W;
             unsigned long long* __restrict__ krow = key + py * W;
+            const float pn = dot3(sv.pos, sv.n);
             for (int px = xs; px < xe; ++px) {
                 const float4 l4 = __ldg(ray + px);
+                const float3 l = make_float3(l4.x, l4.y, l4.z);
+                // Conservative pre-tests in fast arithmetic.  With ~100 fragments per pixel almost every fragment loses the depth
+                // test or misses its disc: those are recognised with an approximate ray parameter (error < 1e-6 relative, margins
+                // 10x larger) and skipped; only a fragment that can still win runs the IEEE path below, so the key image is
+                // bit-identical.  A stale (larger) key from L1 only makes the pre-test pass more often.
+                const unsigned long long cur = krow[px];
+                const float ta = __fdividef(pn, dot3(l, sv.n));
+                if (cur != KEY_EMPTY) {
+                    const float fda = __fmaf_rn(ta * l.z, inv2md, 0.5f);
+                    if (fda > __uint_as_float((unsigned)(cur >> 32)) * 1.00001f) continue;          // clearly behind the current winner
+                }
+                {
+                    const float ax = __fmaf_rn(ta, l.x, -sv.pos.x), ay = __fmaf_rn(ta, l.y, -sv.pos.y), az = __fmaf_rn(ta, l.z, -sv.pos.z);
+                    const float re = sv.rad + 8e-6f * fabsf(ta);
+                    if (__fmaf_rn(ax, ax, __fmaf_rn(ay, ay, az * az)) > re * re * 1.0001f) continue;  // clearly outside the disc
+                }
                 float3 cp;
-                if (!splatFragmentRay(sv, make_float3(l4.x, l4.y, l4.z), cp)) continue;
+                if (!splatFragmentRay(sv, l, cp)) continue;
                 float fd = (cp.z / (2 * maxDepth)) + 0.5f;
                 if (!(fd >= 0.0f && fd < 1.0f)) continue;
                 unsigned long long k = ((unsigned long long)__float_as_uint(fd) << 32) | e.id;
-                if (k < krow[px]) atomicMin(krow + px, k);
+                if (k < cur) atomicMin(krow + px, k);
             }
         }
         __syncthreads();
@@ -912,7 +958,7 @@ void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, cons
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
                              uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s)
 {
-    prof_mark(s, "k_splat_project"); k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
+    prof_mark(s, "k_splat_project"); k_splat_project<<<persistentBlocks(8 * 256 / SPLAT_BS), SPLAT_BS, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
                                                         (float)maxTime, (float)timeDelta, 0u, rayTab, (unsigned long long*)key);
     if (nonBlackSamples) cudaMemsetAsync(nonBlackSamples, 0, sizeof(uint32_t), s);
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
@@ -944,7 +990,7 @@ void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, co
                                int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s)
 {
     prof_mark(s, "k_splat_project_ids");
-    k_splat_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
+    k_splat_project<<<persistentBlocks(8 * 256 / SPLAT_BS), SPLAT_BS, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
                                                         (float)maxTime, (float)timeDelta, drawBase, rayTab, (unsigned long long*)key);
 }
 }  // namespace mfb

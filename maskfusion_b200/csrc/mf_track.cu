@@ -298,7 +298,9 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restri
 // take identical break decisions without a second barrier or a broadcast.  Per-pixel data that a later phase needs
 // (photometric correspondences, validity) is written and re-read by the same thread.
 // =======================================================================================
+#ifndef PT_THREADS
 #define PT_THREADS 512
+#endif
 #define PT_WARPS (PT_THREADS / 32)
 #define ROWF 32                        // floats per partial row: one 128-byte line per CTA per reduction
 
