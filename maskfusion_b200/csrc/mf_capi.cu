@@ -209,7 +209,7 @@ static void planarOut(MaskFusion* o, const float4* map, int P, float* out)
 }
 extern "C" int mf_download_filtered_depth(mf_context* ctx, float* out)
 {
-    MF_TRY MF_NEED(ctx) d2h(ctx->mf, out, ctx->mf->depthFilt.p, ctx->mf->P); ctx->mf->sync(); return 0; MF_CATCH(-1)
+    MF_TRY MF_NEED(ctx) d2h(ctx->mf, out, ctx->mf->depthFilt, ctx->mf->P); ctx->mf->sync(); return 0; MF_CATCH(-1)
 }
 extern "C" int mf_download_frame_maps(mf_context* ctx, int level, float* depth, float* vmap, float* nmap)
 {
@@ -217,7 +217,7 @@ extern "C" int mf_download_frame_maps(mf_context* ctx, int level, float* depth, 
     MaskFusion* o = ctx->mf;
     if (level < 0 || level > 2) { g_err = "level out of range"; return -2; }
     int Pl = (o->W >> level) * (o->H >> level);
-    d2h(o, depth, level == 0 ? o->depthFilt.p : o->depthPyr[level].p, Pl); o->sync();
+    d2h(o, depth, level == 0 ? o->depthFilt : o->depthPyr[level].p, Pl); o->sync();
     planarOut(o, o->vmap[level], Pl, vmap);
     planarOut(o, o->nmap[level], Pl, nmap);
     return 0;

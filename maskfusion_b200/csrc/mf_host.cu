@@ -222,11 +222,11 @@ float Model::computeFusionWeight(float weightMultiplier) const
     return (w > minWeight ? w : minWeight) * weightMultiplier;
 }
 
-void Model::predictIndices(int time, float depthCutoff, int timeDelta)
+void Model::predictIndices(int time, float depthCutoff, int timeDelta, bool forClean)
 {
     MaskFusion* o = owner;
     launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, time, timeDelta, key, idx, vertConf,
-                           colorTime, normRad, cleanTex, o->stream);
+                           colorTime, normRad, forClean ? cleanTex.p : nullptr, o->stream);
     o->launches += 2;
 }
 
@@ -278,7 +278,12 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     ownStream = (st == nullptr);
     if (ownStream) cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"); else stream = st;
     g_prof = &prof;
-    rgb3.alloc((size_t)P * 3); rgb.alloc(P); depthRaw.alloc(P); depthFilt.alloc(P); mask.alloc(P); mask.zero(stream);
+    for (int k = 0; k < 2; ++k) { rgb3Buf[k].alloc((size_t)P * 3); rgbBuf[k].alloc(P); depthRawBuf[k].alloc(P); depthFiltBuf[k].alloc(P); }
+    selectSet(0);
+    mask.alloc(P); mask.zero(stream);
+    cudaCheck(cudaStreamCreateWithFlags(&preStream, cudaStreamNonBlocking), "cudaStreamCreate");
+    cudaCheck(cudaEventCreateWithFlags(&preDone, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventCreateWithFlags(&inputsCopied, cudaEventDisableTiming), "cudaEventCreate");
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
         if (l > 0) depthPyr[l].alloc(Pl);
@@ -310,6 +315,9 @@ MaskFusion::~MaskFusion()
     if (g_prof == &prof) g_prof = nullptr;
     for (cudaEvent_t e : prof.events) cudaEventDestroy(e);
     if (trackDone) cudaEventDestroy(trackDone);
+    if (preStream) { cudaStreamSynchronize(preStream); cudaStreamDestroy(preStream); }
+    if (preDone) cudaEventDestroy(preDone);
+    if (inputsCopied) cudaEventDestroy(inputsCopied);
     models.clear();
     if (hJobs) cudaFreeHost(hJobs);
     if (hSmall) cudaFreeHost(hSmall);
@@ -325,31 +333,53 @@ void MaskFusion::sync()
 }
 
 // textureRGB / textureDepthMetric upload + filterDepth (MaskFusion.cpp:212-217, 650-657)
-void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint8_t* maskIn, bool onDevice)
+void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint8_t* maskIn, bool onDevice, cudaStream_t s)
 {
+    if (!s) s = stream;
     cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     g_prof = &prof;
-    prof_mark(stream, onDevice ? "copy_d2d_frame" : "copy_h2d_frame");
-    cudaCheck(cudaMemcpyAsync(rgb3, rgbIn, (size_t)P * 3, kind, stream), "rgb upload");
-    cudaCheck(cudaMemcpyAsync(depthRaw, depthIn, (size_t)P * sizeof(float), kind, stream), "depth upload");
-    if (maskIn) cudaCheck(cudaMemcpyAsync(mask, maskIn, (size_t)P, kind, stream), "mask upload");
-    launch_unpack_rgb(rgb3, rgb, P, stream);
-    launch_bilateral(depthRaw, depthFilt, W, H, stream);
+    prof_mark(s, onDevice ? "copy_d2d_frame" : "copy_h2d_frame");
+    cudaCheck(cudaMemcpyAsync(rgb3, rgbIn, (size_t)P * 3, kind, s), "rgb upload");
+    cudaCheck(cudaMemcpyAsync(depthRaw, depthIn, (size_t)P * sizeof(float), kind, s), "depth upload");
+    if (maskIn) cudaCheck(cudaMemcpyAsync(mask, maskIn, (size_t)P, kind, s), "mask upload");
+    // host inputs belong to the caller again when processFrame returns (the reference uploads synchronously): see frameBegin
+    if (!onDevice) { cudaCheck(cudaEventRecord(inputsCopied, s), "cudaEventRecord"); copyPending = true; }
+    launch_unpack_rgb(rgb3, rgb, P, s);
+    launch_bilateral(depthRaw, depthFilt, W, H, s);
     launches += 2;
     frameMapsValid = false; intensityValid = false;
 }
 
 // Model::generateCUDATextures (Model.cpp:350-389): level 0 aliases the filtered depth.
 // The mask pyramid of the reference is dead (N10) and not built.
-void MaskFusion::generateCUDATextures()
+void MaskFusion::generateCUDATextures(cudaStream_t s)
 {
-    const float* d[3] = {depthFilt.p, depthPyr[1].p, depthPyr[2].p};
+    if (!s) s = stream;
+    const float* d[3] = {depthFilt, depthPyr[1].p, depthPyr[2].p};
     float4* v3[3] = {vmap[0].p, vmap[1].p, vmap[2].p};
     float4* n3[3] = {nmap[0].p, nmap[1].p, nmap[2].p};
-    launch_pyrdown2_f(depthFilt, W, H, depthPyr[1], depthPyr[2], stream);
-    launch_vmap_nmap3(d, W, H, cam, cfg.depthCutoff, v3, n3, stream);
+    launch_pyrdown2_f(depthFilt, W, H, depthPyr[1], depthPyr[2], s);
+    launch_vmap_nmap3(d, W, H, cam, cfg.depthCutoff, v3, n3, s);
     launches += 2;
     frameMapsValid = true;
+}
+
+// frame side of RGBDOdometry::initRGB (RGBDOdometry.cpp:212-215): intensity pyramid, Sobel derivatives, photometric validity; shared by all models
+void MaskFusion::frameIntensity(cudaStream_t s)
+{
+    if (!s) s = stream;
+    const bool rgbTerm = cfg.rgbOnly || cfg.icpWeight < 100;
+    launch_intensity(rgb, P, nextImage[0], s);
+    launch_pyrdown2_u8(nextImage[0], W, H, nextImage[1], nextImage[2], s);
+    launches += 2;
+    if (rgbTerm) {
+        const uint8_t* i3[3] = {nextImage[0].p, nextImage[1].p, nextImage[2].p};
+        short2* g3[3] = {nextGrad[0].p, nextGrad[1].p, nextGrad[2].p};
+        uint8_t* r3[3] = {rgbValid[0].p, rgbValid[1].p, rgbValid[2].p};
+        launch_sobel3(i3, W, H, g3, r3, s);
+        launches += 1;
+    }
+    intensityValid = true;
 }
 
 // Model::performTracking for a batch of models: one launch sequence, blockIdx.y = model
@@ -359,20 +389,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
     if ((int)ms.size() > TRACK_MAX_JOBS) throw CudaError{"too many tracked models for one batch"};
     const bool rgbTerm = cfg.rgbOnly || cfg.icpWeight < 100;
     if (!frameMapsValid) generateCUDATextures();
-    if ((rgbTerm || cfg.so3) && !intensityValid) {
-        // frame side of RGBDOdometry::initRGB (RGBDOdometry.cpp:212-215): shared by all models
-        launch_intensity(rgb, P, nextImage[0], stream);
-        launch_pyrdown2_u8(nextImage[0], W, H, nextImage[1], nextImage[2], stream);
-        launches += 2;
-        if (rgbTerm) {
-            const uint8_t* i3[3] = {nextImage[0].p, nextImage[1].p, nextImage[2].p};
-            short2* g3[3] = {nextGrad[0].p, nextGrad[1].p, nextGrad[2].p};
-            uint8_t* r3[3] = {rgbValid[0].p, rgbValid[1].p, rgbValid[2].p};
-            launch_sobel3(i3, W, H, g3, r3, stream);
-            launches += 1;
-        }
-        intensityValid = true;
-    }
+    if ((rgbTerm || cfg.so3) && !intensityValid) frameIntensity();
     for (size_t j = 0; j < ms.size(); ++j) {
         Model* m = ms[j];
         m->lastPose = m->pose;                                       // Model.cpp:430
@@ -385,6 +402,10 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
         }
         J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.bar = trackBars.p + j * 32;
         J.dpose = m->dpose;
+    }
+    if (preWaitPending) {            // the frame's preprocessing ran on preStream: the tracker is the first consumer on the main stream
+        cudaCheck(cudaStreamWaitEvent(stream, preDone, 0), "cudaStreamWaitEvent");
+        preWaitPending = false;
     }
     prof_mark(stream, "copy_jobs");
     cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
@@ -574,7 +595,7 @@ Model* MaskFusion::spawnObjectModel()
         // newModel->getFrameOdometry().initFirstRGB(textureRGB)
         if (!intensityValid) {
             launch_intensity(rgb, P, nextImage[0], stream);
-            for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
+            launch_pyrdown2_u8(nextImage[0], W, H, nextImage[1], nextImage[2], stream);
             launches += 3; intensityValid = true;
         }
         cudaCheck(cudaMemcpyAsync(nm->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
@@ -634,6 +655,10 @@ bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_
     frameBegin(rgbIn, depthIn, timestamp, maskIn, inPose, bootstrap, onDevice);
     frameProject();
     frameEnd(weightMultiplier);
+    if (copyPending) {               // the caller's host buffers are free again on return, as with the reference's synchronous upload
+        cudaCheck(cudaEventSynchronize(inputsCopied), "cudaEventSynchronize");
+        copyPending = false;
+    }
     return false;
 }
 
@@ -645,7 +670,20 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
     if (world > 1 && inPose) throw CudaError{"sharded mode tracks every frame (no external poses)"};
     finalisePending();                                  // previous frame's tracked pose + pose-log entry (its event lies mid-frame: the GPU still has work queued)
     fTimestamp = timestamp; fHasPose = inPose != nullptr; if (inPose) fInPose = *inPose; fBootstrap = bootstrap;
-    setFrame(rgbIn, depthIn, nullptr, onDevice);        // -static: textureMask stays all zero (MaskFusion.cpp:223-230); multi: keeps the last segmentation
+    // -static tracking frames: upload + bilateral + pyramids + maps + intensity/Sobel of THIS frame go to preStream and into the other
+    // input set, so they run next to the surfel passes of the previous frame that are still queued on the main stream (those read the
+    // previous frame's images; the copy engine and the issue-bound bilateral overlap well with the HBM-bound clean/scatter).
+    // Safe without further events: finalisePending() above has waited for the previous frame's tracker, the last reader of the maps.
+    const bool overlap = !multi && world == 1 && tick > 1 && (bootstrap || !inPose) && !prof.on;
+    if (overlap) {
+        selectSet(curSet ^ 1);
+        setFrame(rgbIn, depthIn, nullptr, onDevice, preStream);
+        generateCUDATextures(preStream);
+        if (cfg.rgbOnly || cfg.icpWeight < 100 || cfg.so3) frameIntensity(preStream);
+        cudaCheck(cudaEventRecord(preDone, preStream), "cudaEventRecord");
+        preWaitPending = true;
+    } else
+        setFrame(rgbIn, depthIn, nullptr, onDevice);    // -static: textureMask stays all zero (MaskFusion.cpp:223-230); multi: keeps the last segmentation
     frameHasMask = false;
     if (multi && maskIn) {
         cudaCheck(cudaMemcpyAsync(frameMask, maskIn, (size_t)P, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream), "mask upload");
@@ -657,12 +695,12 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
             g->initialise(tick);
             // globalModel->getFrameOdometry().initFirstRGB (MaskFusion.cpp:238)
             launch_intensity(rgb, P, nextImage[0], stream);
-            for (int l = 0; l + 1 < 3; ++l) launch_pyrdown_u8(nextImage[l], W >> l, H >> l, nextImage[l + 1], stream);
+            launch_pyrdown2_u8(nextImage[0], W, H, nextImage[1], nextImage[2], stream);
             cudaCheck(cudaMemcpyAsync(g->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
             launches += 3;
         }
     } else if (bootstrap || !inPose) {
-        generateCUDATextures();
+        if (!frameMapsValid) generateCUDATextures();
         // MaskFusion.cpp:247-276: the global model and every tracked object share one batched launch sequence
         std::vector<Model*> tracked;
         for (size_t i = 0; i < models.size(); ++i)
@@ -722,7 +760,7 @@ void MaskFusion::frameEnd(float weightMultiplier)
             g->overridePose(fInPose);
         }
         if (!cfg.rgbOnly) {
-            for (auto& m : models) if (m->owned) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
+            for (auto& m : models) if (m->owned) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta, false);
             for (auto& m : models) if (m->owned) m->fuse(tick, cfg.depthCutoff, weightMultiplier);
             for (auto& m : models) if (m->owned) m->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
             for (auto& m : models) if (m->owned) m->clean(tick, cfg.timeDelta, cfg.maxDepthProcessed);

@@ -59,7 +59,7 @@ public:
     // ---- reference API (Core/Model/Model.h:128-164) ----
     void initialise(int time);                                        // Model::initialise (+ computeFeedbackBuffers)
     void prepareTracking();                                           // Model::initICP (model side)
-    void predictIndices(int time, float depthCutoff, int timeDelta);  // Model::predictIndices
+    void predictIndices(int time, float depthCutoff, int timeDelta, bool forClean = true);  // Model::predictIndices (forClean: also the packed window texels)
     void fuse(int time, float depthCutoff, float weightMultiplier);   // Model::fuse
     void clean(int time, int timeDelta, float depthCutoff);           // Model::clean
     void combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta);   // Model::combinedPredict + performFillIn
@@ -114,8 +114,10 @@ public:
     // bool MaskFusion::processFrame(FrameDataPointer, const Eigen::Matrix4f* inPose, float weightMultiplier, bool bootstrap)
     bool processFrame(const uint8_t* rgb, const float* depth, int64_t timestamp, const uint8_t* mask, const Mat4* inPose,
                       float weightMultiplier, bool bootstrap, bool inputsOnDevice);
-    void setFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool onDevice);   // upload + filterDepth
-    void generateCUDATextures();                                                                  // Model::generateCUDATextures
+    // upload + filterDepth; generateCUDATextures; frame side of initRGB.  `s` = stream to enqueue on (nullptr: the main stream)
+    void setFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool onDevice, cudaStream_t s = nullptr);
+    void generateCUDATextures(cudaStream_t s = nullptr);                                          // Model::generateCUDATextures
+    void frameIntensity(cudaStream_t s = nullptr);                                                // RGBDOdometry::initRGB (frame side) + Sobel + validity
     void trackModels(const std::vector<Model*>& ms);                                              // performTracking for a batch
     void predict();                                                                               // MaskFusion::predict
     void sync();
@@ -153,7 +155,14 @@ public:
     std::vector<std::unique_ptr<Model>> models;
     unsigned char nextID = 0;
     // frame
-    DevBuf<uint8_t> rgb3; DevBuf<uchar4> rgb; DevBuf<float> depthRaw, depthFilt; DevBuf<uint8_t> mask;
+    // Frame inputs exist twice: in the -static schedule the upload and preprocessing of frame t+1 run on their own stream
+    // (preStream) while the surfel passes of frame t, which still read frame t's images, occupy the main stream.
+    DevBuf<uint8_t> rgb3Buf[2]; DevBuf<uchar4> rgbBuf[2]; DevBuf<float> depthRawBuf[2], depthFiltBuf[2];
+    uint8_t* rgb3 = nullptr; uchar4* rgb = nullptr; float* depthRaw = nullptr; float* depthFilt = nullptr;   // the current set
+    int curSet = 0;
+    void selectSet(int k) { curSet = k; rgb3 = rgb3Buf[k]; rgb = rgbBuf[k]; depthRaw = depthRawBuf[k]; depthFilt = depthFiltBuf[k]; }
+    cudaStream_t preStream = nullptr; cudaEvent_t preDone = nullptr, inputsCopied = nullptr; bool preWaitPending = false, copyPending = false;
+    DevBuf<uint8_t> mask;
     DevBuf<float> depthPyr[3]; DevBuf<float4> vmap[3], nmap[3];
     DevBuf<uint8_t> nextImage[3]; DevBuf<short2> nextGrad[3]; DevBuf<uint8_t> rgbValid[3];
     DevBuf<float> edgeMap; DevBuf<uint8_t> edgeBinary, edgeBuf, edgeInv;

@@ -64,7 +64,7 @@ __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __
         idx[i] = 0;
         float4 z = make_float4(0, 0, 0, 0);
         vertConf[i] = z; colorTime[i] = z; normRad[i] = z;
-        cleanTex[2 * i] = z; cleanTex[2 * i + 1] = z;
+        if (cleanTex) { cleanTex[2 * i] = z; cleanTex[2 * i + 1] = z; }
         return;
     }
     key[i] = KEY_EMPTY;
@@ -76,8 +76,10 @@ __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __
     vertConf[i] = make_float4(ph.x, ph.y, ph.z, p.w);
     colorTime[i] = c;
     normRad[i] = make_float4(nn.x, nn.y, nn.z, n.w);
-    cleanTex[2 * i] = make_float4(ph.x, ph.y, ph.z, p.w);
-    cleanTex[2 * i + 1] = make_float4(c.z, c.w, id != 0u ? 1.f : 0.f, 0.f);
+    if (cleanTex) {
+        cleanTex[2 * i] = make_float4(ph.x, ph.y, ph.z, p.w);
+        cleanTex[2 * i + 1] = make_float4(c.z, c.w, id != 0u ? 1.f : 0.f, 0.f);
+    }
 }
 
 // ---------------------------------------------------------------------------------------

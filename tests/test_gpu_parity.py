@@ -262,3 +262,56 @@ def test_process_frame_error_behaviour():
     with pytest.raises(mfb.MFError):
         mf.processFrame(np.zeros((H, W, 3), np.uint8), np.zeros((H, W), np.float32), timestamp=-1)
     mf.close()
+
+
+def test_sequence_720p_matches_oracle():
+    """BASELINE configs[4] resolution (1280x720, fx=fy=792): free-running GUI-default replay against the oracle -- the pyramid,
+    tracker (12+ pixel rounds per thread, correspondences in 49 KB of dynamic shared memory), index map and clean paths at the
+    largest size the configs name; per-frame translation within 1 mm, surfel counts equal, final index map identical"""
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene
+    W2, H2 = 1280, 720
+    sc = SynthScene(W2, H2, n_objects=0, seed=2)
+    kw = dict(capacityGlobal=2200000, fx=792.0, fy=792.0, cx=640.0, cy=360.0)       # the "-cal" intrinsics of SURVEY 8(d)
+    orc = ol.OraclePipeline(ol.default_config(W2, H2, **kw))
+    mf = mfb.MaskFusion(mfb.default_config(W2, H2, **kw))
+    for t in range(5):
+        rgb, depth, *_ = sc.render(t)
+        orc.process_frame(rgb, depth, t * 33333)
+        mf.processFrame(rgb, depth, t * 33333)
+        dp = float(np.abs(orc.pose(0) - mf.getBackgroundModel().getPose()).max())
+        assert dp < 2e-5, (t, dp)
+        co, cc = orc.count(0), mf.getBackgroundModel().lastCount()
+        assert abs(co - cc) <= max(30, co // 2000), (t, co, cc)
+    lo = np.array([orc.model(0).log[i] for i in range(orc.model(0).nlog * 8)]).reshape(-1, 8)
+    lc = mf.getBackgroundModel().poseLog()
+    ate = float(np.sqrt(np.mean(np.sum((lo[:, 1:4] - lc[:, 1:4]) ** 2, axis=1))))
+    assert ate < 1e-3, f"ATE-RMSE {ate*1e3:.4f} mm"
+    mf.close()
+
+
+def test_degenerate_frames_match_oracle():
+    """edge cases of the inputs, free-running against the oracle: an all-zero depth frame (no vertex, no correspondence: singular
+    normal equations, Eigen's zero-pivot convention => no motion), a frame with 60 % holes, and a surfel store that is full
+    (capacity == first frame: every later insertion is clamped exactly like the reference's fixed-size VBO)"""
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene
+    sc = SynthScene(W, H, n_objects=0, seed=4)
+    kw = dict(capacityGlobal=307200, icpWeight=100.0, so3=0)
+    orc = ol.OraclePipeline(ol.default_config(W, H, **kw))
+    mf = mfb.MaskFusion(mfb.default_config(W, H, **kw))
+    rng = np.random.default_rng(0)
+    for t in range(6):
+        rgb, depth, *_ = sc.render(t)
+        if t == 2:
+            depth = np.zeros_like(depth)
+        if t == 4:
+            depth = depth.copy(); depth[rng.random(depth.shape) < 0.6] = 0
+        orc.process_frame(rgb, depth, t * 33333)
+        mf.processFrame(rgb, depth, t * 33333)
+        Po, Pc = orc.pose(0), mf.getBackgroundModel().getPose()
+        assert np.all(np.isfinite(Pc)), t
+        assert float(np.abs(Po - Pc).max()) < 2e-5, (t, float(np.abs(Po - Pc).max()))
+        co, cc = orc.count(0), mf.getBackgroundModel().lastCount()
+        assert cc <= 307200 and abs(co - cc) <= max(30, co // 2000), (t, co, cc)
+    mf.close()
