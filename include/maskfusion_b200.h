@@ -159,6 +159,23 @@ int mf_backbone_download(mf_backbone* h, int level, void* host_bf16);
 double mf_backbone_flops(mf_backbone* h);
 int mf_backbone_num_gemms(mf_backbone* h);
 
+/* ---- image-directory loader ("-dir", GUI/Tools/ImageLogReader.{h,cpp}; GUI/MainController.cpp:150-176) ----
+ * colour .png/.ppm, depth 16-bit .png (x 0.001), masks 8-bit .png/.pgm + "<mask>.txt" (class ids, boxes); .jpg/.exr are refused
+ * (no libjpeg / OpenEXR in this build).  hasMore() lets the last frame through (ImageLogReader.cpp:326), unlike the .klg reader. */
+typedef struct mf_dir mf_dir;
+mf_dir* mf_dir_open(const char* color_dir, const char* depth_dir, const char* mask_dir /* NULL: no masks */, int index_width /* <=0: 4 */,
+                    const char* color_prefix, const char* depth_prefix, const char* mask_prefix);   /* ImageLogReader::ImageLogReader */
+int mf_dir_num_frames(mf_dir* r);                                       /* ImageLogReader::getNumFrames */
+int mf_dir_has_more(mf_dir* r);                                         /* ImageLogReader::hasMore */
+int mf_dir_has_masks(mf_dir* r);                                        /* LogReader::hasMasks */
+int mf_dir_set_max_masks(mf_dir* r, int n);                             /* ImageLogReader::setMaxMasks ("-nm") */
+int mf_dir_size(mf_dir* r, int* width, int* height);                    /* size of the first colour image */
+/* ImageLogReader::getNext + loadFrameFromDrive: rgb HxWx3, depth HxW metres; mask/class_ids/boxes may be NULL.  *n_class_ids: in =
+ * capacity, out = ids read (classIDs[0] == 0, ImageLogReader.cpp:306); boxes = cv::Rect x,y,w,h per object.  Returns 1 if a mask was
+ * delivered, 0 if not, < 0 on error; timestamp = index * 1000 / 24 (ImageLogReader.cpp:283). */
+int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* mask, int32_t* class_ids, int32_t* boxes, int* n_class_ids, int64_t* timestamp);
+void mf_dir_close(mf_dir* r);
+
 /* ---- .klg log reader / writer (GUI/Tools/KlgLogReader.cpp:29-113) ---- */
 typedef struct mf_klg mf_klg;
 mf_klg* mf_klg_open(const char* path, int width, int height, int flip_colors);

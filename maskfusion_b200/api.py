@@ -49,7 +49,8 @@ EXPORTS = [
     "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
     "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
-    "mf_klg_close", "mf_klg_write", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
+    "mf_klg_close", "mf_klg_write", "mf_dir_open", "mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks", "mf_dir_set_max_masks", "mf_dir_size",
+    "mf_dir_get_next", "mf_dir_close", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
     "mf_shard_configure", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
@@ -117,6 +118,14 @@ def load_library():
     L.mf_klg_close.restype = None
     L.mf_klg_get_next.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.mf_klg_write.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_dir_open.restype = C.c_void_p
+    L.mf_dir_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p]
+    for name in ("mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks"):
+        getattr(L, name).argtypes = [C.c_void_p]
+    L.mf_dir_set_max_masks.argtypes = [C.c_void_p, C.c_int]
+    L.mf_dir_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.mf_dir_get_next.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+    L.mf_dir_close.argtypes = [C.c_void_p]
     L.mf_cnn_last_error.restype = C.c_char_p
     L.mf_gemm_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 4 + [C.c_void_p]
     L.mf_conv3x3_bf16.argtypes = [C.c_void_p] * 5 + [C.c_int] * 5 + [C.c_void_p]
@@ -413,6 +422,50 @@ class KlgLogReader:
         if self.k:
             self.L.mf_klg_close(self.k)
             self.k = None
+
+
+class ImageLogReader:
+    """reference: class ImageLogReader (GUI/Tools/ImageLogReader.{h,cpp}), the "-dir" loader: colour / depth / optional mask images
+    named <prefix><zero-padded index><ext> (+ "<mask>.txt" with class ids and boxes)"""
+
+    def __init__(self, colorDirectory: str, depthDirectory: str | None = None, maskDirectory: str | None = None, indexWidth: int = 4,
+                 colorPrefix: str = "", depthPrefix: str = "", maskPrefix: str = ""):
+        self.L = load_library()
+        enc = lambda v: v.encode() if v else None          # noqa: E731
+        self.r = self.L.mf_dir_open(colorDirectory.encode(), enc(depthDirectory), enc(maskDirectory), indexWidth, colorPrefix.encode(),
+                                    depthPrefix.encode(), maskPrefix.encode())
+        if not self.r:
+            raise MFError(self.L.mf_last_error().decode())
+        w, h = C.c_int(0), C.c_int(0)
+        self.L.mf_dir_size(self.r, C.byref(w), C.byref(h))
+        self.W, self.H = w.value, h.value
+
+    def getNumFrames(self):
+        return self.L.mf_dir_num_frames(self.r)
+
+    def hasMore(self):
+        return bool(self.L.mf_dir_has_more(self.r))
+
+    def hasMasks(self):
+        return bool(self.L.mf_dir_has_masks(self.r))
+
+    def setMaxMasks(self, n: int):
+        self.L.mf_dir_set_max_masks(self.r, n)
+
+    def getNext(self):
+        """-> rgb, depth, timestamp, mask or None, classIDs or None, rois (n,4 as x,y,w,h) or None   (FrameData fields)"""
+        rgb = np.zeros((self.H, self.W, 3), np.uint8); depth = np.zeros((self.H, self.W), np.float32); mask = np.zeros((self.H, self.W), np.uint8)
+        ids = np.zeros(256, np.int32); boxes = np.zeros((255, 4), np.int32); n = C.c_int(256); ts = C.c_int64(0)
+        rc = self.L.mf_dir_get_next(self.r, _p(rgb), _p(depth), _p(mask), _p(ids), _p(boxes), C.byref(n), C.byref(ts))
+        if rc < 0:
+            raise MFError(self.L.mf_last_error().decode())
+        cls = ids[:n.value].copy() if n.value else None
+        return rgb, depth, ts.value, (mask if rc == 1 else None), cls, (boxes[:n.value - 1].copy() if n.value > 1 else None)
+
+    def close(self):
+        if self.r:
+            self.L.mf_dir_close(self.r)
+            self.r = None
 
 
 def write_klg(path: str, timestamps, depth_mm: np.ndarray, rgb: np.ndarray):

@@ -35,6 +35,7 @@ SOURCES = {
     "mf_track.cu": ["-fmad=false"],
     "mf_host.cu": ["-fmad=false"],
     "mf_capi.cu": ["-fmad=false"],
+    "mf_loader.cu": [],                   # host code only: image-directory loader (PNG/PNM decode, zlib)
     "mf_cnn.cu": [],                      # tensor-core GEMMs: no bit-exactness contract, FMA contraction on
 }
 

@@ -15,6 +15,7 @@ struct mf_context { MaskFusion* mf; };
 
 static thread_local std::string g_err;
 extern "C" const char* mf_last_error(void) { return g_err.c_str(); }
+void mf_set_error(const std::string& e) { g_err = e; }          // for the other translation units behind the same ABI (mf_loader.cu)
 extern "C" int mf_abi_version(void) { return MF_ABI_VERSION; }
 
 #define MF_TRY try {

@@ -1,0 +1,307 @@
+// mf_loader.cu -- image-directory loader behind the C ABI (host code only).
+//   mf_dir_*  <-  ImageLogReader  (GUI/Tools/ImageLogReader.{h,cpp}; constructed at GUI/MainController.cpp:150-176 for "-dir")
+// File discovery (prefix + one extension per stream, start index 0 or 1, zero-padded index of width indexW), the default
+// "Color"/"Depth"/"Mask" prefixes when directories overlap, the mask description file (class ids + boxes), the depth
+// conversions and the timestamps (index * 1000 / 24 Hz, :283) follow the reference.  The reference decodes with OpenCV
+// (cv::imread); OpenCV, libpng and libjpeg do not exist in this build, so PNG (zlib is here) and binary PNM are decoded by the
+// code below and the rest is refused with a message:
+//   colour  .png .ppm   (-> 8-bit RGB in file order: cv::imread gives BGR and the reader swaps unconditionally, :247-248)   .jpg: no
+//   depth   .png 16-bit gray (-> 0.001f * v, :262-268)                                                                     .exr: no
+//   mask    .png / .pgm 8-bit gray (cv::IMREAD_GRAYSCALE of a gray file is the identity)
+// Unlike KlgLogReader, hasMore() lets the LAST frame through (currentFrame starts at -1, :145,:326).
+// The reference's background buffering thread (:203-220) is an I/O detail and is not reproduced: frames are decoded on demand.
+#include "../../include/maskfusion_b200.h"
+#include <dirent.h>
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <zlib.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+extern void mf_set_error(const std::string& e);          // mf_capi.cu (thread-local message behind mf_last_error)
+
+namespace {
+
+struct Image { int w = 0, h = 0, channels = 0, bits = 0; std::vector<uint8_t> data; };   // 16-bit samples in host byte order
+
+bool readFile(const std::string& path, std::vector<uint8_t>& out)
+{
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) return false;
+    fseek(fp, 0, SEEK_END); long n = ftell(fp); fseek(fp, 0, SEEK_SET);
+    out.resize(n > 0 ? (size_t)n : 0);
+    bool ok = n <= 0 || fread(out.data(), 1, (size_t)n, fp) == (size_t)n;
+    fclose(fp);
+    return ok;
+}
+
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+// PNG (ISO/IEC 15948): non-interlaced, colour types 0/2/3/4/6, bit depths 8/16 (1/2/4 for gray and palette)
+bool decodePNG(const std::vector<uint8_t>& f, Image& im, std::string& err)
+{
+    static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+    if (f.size() < 33 || memcmp(f.data(), sig, 8) != 0) { err = "not a PNG file"; return false; }
+    size_t pos = 8;
+    int W = 0, H = 0, bits = 0, ctype = 0, interlace = 0;
+    std::vector<uint8_t> idat, plte;
+    bool gotHdr = false;
+    while (pos + 12 <= f.size()) {
+        uint32_t len = be32(&f[pos]);
+        const uint8_t* type = &f[pos + 4];
+        if (pos + 12 + (size_t)len > f.size()) { err = "truncated PNG chunk"; return false; }
+        const uint8_t* d = &f[pos + 8];
+        if (!memcmp(type, "IHDR", 4)) {
+            if (len < 13) { err = "bad IHDR"; return false; }
+            W = (int)be32(d); H = (int)be32(d + 4); bits = d[8]; ctype = d[9]; interlace = d[12]; gotHdr = true;
+        } else if (!memcmp(type, "PLTE", 4)) plte.assign(d, d + len);
+        else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), d, d + len);
+        else if (!memcmp(type, "IEND", 4)) break;
+        pos += 12 + (size_t)len;
+    }
+    if (!gotHdr || W <= 0 || H <= 0) { err = "PNG without a valid IHDR"; return false; }
+    if (interlace) { err = "interlaced PNG is not supported"; return false; }
+    int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+    if (!ch || !(bits == 8 || bits == 16 || ((ctype == 0 || ctype == 3) && (bits == 1 || bits == 2 || bits == 4)))) { err = "unsupported PNG colour type / bit depth"; return false; }
+    const size_t bpp = std::max<size_t>(1, (size_t)ch * bits / 8);            // filter distance in bytes
+    const size_t rowBytes = ((size_t)W * ch * bits + 7) / 8;
+    std::vector<uint8_t> raw((rowBytes + 1) * (size_t)H);
+    unsigned long rawLen = (unsigned long)raw.size();
+    if (uncompress(raw.data(), &rawLen, idat.data(), (unsigned long)idat.size()) != Z_OK || rawLen != raw.size()) { err = "PNG: zlib stream does not decode to the image size"; return false; }
+    std::vector<uint8_t> pix(rowBytes * (size_t)H);
+    for (int y = 0; y < H; ++y) {
+        const uint8_t ft = raw[(rowBytes + 1) * y];
+        const uint8_t* src = &raw[(rowBytes + 1) * y + 1];
+        uint8_t* cur = &pix[rowBytes * y];
+        const uint8_t* up = y ? &pix[rowBytes * (y - 1)] : nullptr;
+        for (size_t i = 0; i < rowBytes; ++i) {
+            const int a = i >= bpp ? cur[i - bpp] : 0, b = up ? up[i] : 0, c = (up && i >= bpp) ? up[i - bpp] : 0;
+            int v = src[i];
+            switch (ft) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) >> 1; break;
+                case 4: { int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); v += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+                default: err = "PNG: bad filter type"; return false;
+            }
+            cur[i] = (uint8_t)v;
+        }
+    }
+    // unpack to 8- or 16-bit samples, expand palette / low bit depths
+    im.w = W; im.h = H;
+    if (ctype == 3) {
+        im.channels = 3; im.bits = 8; im.data.resize((size_t)W * H * 3);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                int idx;
+                if (bits == 8) idx = pix[rowBytes * y + x];
+                else { int per = 8 / bits, sh = (per - 1 - x % per) * bits; idx = (pix[rowBytes * y + x / per] >> sh) & ((1 << bits) - 1); }
+                for (int c = 0; c < 3; ++c) im.data[((size_t)y * W + x) * 3 + c] = (size_t)idx * 3 + c < plte.size() ? plte[idx * 3 + c] : 0;
+            }
+        return true;
+    }
+    im.channels = ch;
+    if (bits < 8) {          // gray 1/2/4 -> 8 bit, scaled to the full range like libpng's expand
+        im.bits = 8; im.data.resize((size_t)W * H);
+        const int per = 8 / bits, maxv = (1 << bits) - 1;
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) { int sh = (per - 1 - x % per) * bits; int v = (pix[rowBytes * y + x / per] >> sh) & maxv; im.data[(size_t)y * W + x] = (uint8_t)(v * 255 / maxv); }
+        return true;
+    }
+    im.bits = bits;
+    if (bits == 8) { im.data.swap(pix); return true; }
+    im.data.resize(pix.size());
+    for (size_t i = 0; i + 1 < pix.size(); i += 2) { uint16_t v = (uint16_t)((pix[i] << 8) | pix[i + 1]); memcpy(&im.data[i], &v, 2); }   // big endian -> host
+    return true;
+}
+
+// binary PNM: P5 (gray) / P6 (rgb), maxval < 65536
+bool decodePNM(const std::vector<uint8_t>& f, Image& im, std::string& err)
+{
+    if (f.size() < 7 || f[0] != 'P' || (f[1] != '5' && f[1] != '6')) { err = "not a binary PGM/PPM file"; return false; }
+    size_t pos = 2; long vals[3]; int got = 0;
+    while (got < 3 && pos < f.size()) {
+        if (f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') ++pos; continue; }
+        if (isspace(f[pos])) { ++pos; continue; }
+        long v = 0; bool any = false;
+        while (pos < f.size() && isdigit(f[pos])) { v = v * 10 + (f[pos] - '0'); ++pos; any = true; }
+        if (!any) { err = "bad PNM header"; return false; }
+        vals[got++] = v;
+    }
+    if (got < 3 || pos >= f.size()) { err = "bad PNM header"; return false; }
+    ++pos;   // single whitespace after maxval
+    im.w = (int)vals[0]; im.h = (int)vals[1]; im.channels = f[1] == '6' ? 3 : 1; im.bits = vals[2] > 255 ? 16 : 8;
+    const size_t n = (size_t)im.w * im.h * im.channels * (im.bits / 8);
+    if (im.w <= 0 || im.h <= 0 || pos + n > f.size()) { err = "truncated PNM data"; return false; }
+    im.data.assign(f.begin() + pos, f.begin() + pos + n);
+    if (im.bits == 16) for (size_t i = 0; i + 1 < n; i += 2) { uint16_t v = (uint16_t)((im.data[i] << 8) | im.data[i + 1]); memcpy(&im.data[i], &v, 2); }
+    return true;
+}
+
+bool loadImage(const std::string& path, const std::string& ext, Image& im, std::string& err)
+{
+    std::vector<uint8_t> f;
+    if (!readFile(path, f)) { err = "cannot read " + path; return false; }
+    if (ext == ".png") return decodePNG(f, im, err);
+    if (ext == ".ppm" || ext == ".pgm") return decodePNM(f, im, err);
+    err = "decoding " + ext + " files needs " + std::string(ext == ".exr" ? "OpenEXR" : "libjpeg") + ", which this build does not have (supported: .png, .ppm, .pgm)";
+    return false;
+}
+
+bool exists(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
+
+std::string withSlash(const char* d) { std::string s = d ? d : ""; if (!s.empty() && s.back() != '/') s += '/'; return s; }
+
+std::string indexString(unsigned width, size_t index)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%0*zu", (int)width, index);
+    return buf;
+}
+
+}  // namespace
+
+struct mf_dir {
+    std::string colorDir, depthDir, maskDir, colorPre, depthPre, maskPre, colorExt, depthExt, maskExt;
+    unsigned indexW = 4, startIndex = 0;
+    int numFrames = 0, currentFrame = -1, W = 0, H = 0;
+    bool hasMasks = false; size_t maxMasks = 0;
+    float rateHz = 24;                                   // ImageLogReader.h:92
+};
+
+// countFilesInDir of the reference constructor (:86-114): files whose stem starts with `prefix` and whose (lower-cased) extension is in
+// the list; all of them must share one extension.  Returns -1 on a mixed set.
+static int countFiles(const std::string& dir, const std::string& prefix, const std::vector<std::string>& exts, std::string& outExt, std::string& err)
+{
+    outExt.clear();
+    DIR* d = opendir(dir.c_str());
+    if (!d) { err = "cannot open directory " + dir; return -1; }
+    int n = 0;
+    while (struct dirent* e = readdir(d)) {
+        std::string name = e->d_name;
+        if (!exists(dir + name)) continue;
+        size_t dot = name.find_last_of('.');
+        if (dot == std::string::npos || dot == 0) continue;
+        std::string stem = name.substr(0, dot), ext = name.substr(dot);
+        std::transform(ext.begin(), ext.end(), ext.begin(), [](unsigned char c) { return (char)tolower(c); });
+        if (stem.compare(0, prefix.size(), prefix) != 0) continue;
+        if (std::find(exts.begin(), exts.end(), ext) == exts.end()) continue;
+        if (outExt.empty()) outExt = ext;
+        else if (outExt != ext) { closedir(d); err = "Error: Files in the dataset ( " + dir + ", " + prefix + ") are required to have the same extension."; return -1; }
+        ++n;
+    }
+    closedir(d);
+    return n;
+}
+
+extern "C" mf_dir* mf_dir_open(const char* color_dir, const char* depth_dir, const char* mask_dir, int index_width, const char* color_prefix,
+                               const char* depth_prefix, const char* mask_prefix)
+{
+    mf_dir* r = new mf_dir;
+    r->colorDir = withSlash(color_dir); r->depthDir = withSlash(depth_dir && *depth_dir ? depth_dir : color_dir);
+    r->maskDir = withSlash(mask_dir && *mask_dir ? mask_dir : "");
+    r->colorPre = color_prefix ? color_prefix : ""; r->depthPre = depth_prefix ? depth_prefix : ""; r->maskPre = mask_prefix ? mask_prefix : "";
+    r->indexW = index_width > 0 ? (unsigned)index_width : 4;
+    const bool noMaskDir = r->maskDir.empty();
+    // overlapping directories but no distinct prefixes: default prefixes (:79-84)
+    if (((r->depthDir == r->colorDir) || (r->maskDir == r->colorDir) || (r->maskDir == r->depthDir)) &&
+        (r->depthPre == r->colorPre && r->maskPre == r->colorPre)) { r->colorPre = "Color"; r->depthPre = "Depth"; r->maskPre = "Mask"; }
+    std::string err;
+    int nc = countFiles(r->colorDir, r->colorPre, {".jpg", ".png", ".ppm"}, r->colorExt, err);
+    int nd = nc < 0 ? -1 : countFiles(r->depthDir, r->depthPre, {".exr", ".png"}, r->depthExt, err);
+    int nm = (nd < 0 || noMaskDir) ? 0 : countFiles(r->maskDir, r->maskPre, {".png", ".pgm"}, r->maskExt, err);
+    if (nc < 0 || nd < 0 || nm < 0) { mf_set_error(err); delete r; return nullptr; }
+    if (nm > 0) { r->hasMasks = true; r->maxMasks = (size_t)nm; }
+    if (nc != nd) { mf_set_error("Error: Number of RGB-frames != Depth-frames!"); delete r; return nullptr; }
+    if (r->hasMasks && nc != nm) { mf_set_error("Error: Number of RGB-frames != Mask-frames!"); delete r; return nullptr; }
+    r->numFrames = nc;
+    int index = 0;
+    for (; index < 2; ++index)
+        if (exists(r->colorDir + r->colorPre + indexString(r->indexW, (size_t)index) + r->colorExt)) { r->startIndex = (unsigned)index; break; }
+    if (index == 2) { mf_set_error("Error: Could not find start index."); delete r; return nullptr; }
+    // image size from the first colour frame (the reference takes it from Resolution::getInstance())
+    Image im;
+    if (!loadImage(r->colorDir + r->colorPre + indexString(r->indexW, r->startIndex) + r->colorExt, r->colorExt, im, err)) { mf_set_error(err); delete r; return nullptr; }
+    r->W = im.w; r->H = im.h;
+    return r;
+}
+extern "C" void mf_dir_close(mf_dir* r) { delete r; }
+extern "C" int mf_dir_num_frames(mf_dir* r) { return r ? r->numFrames : -1; }
+extern "C" int mf_dir_has_more(mf_dir* r) { return r ? (r->currentFrame + 1 < r->numFrames) : 0; }      // :326
+extern "C" int mf_dir_has_masks(mf_dir* r) { return r && r->hasMasks ? 1 : 0; }
+extern "C" int mf_dir_set_max_masks(mf_dir* r, int n) { if (!r) return -1; r->maxMasks = n < 0 ? 0 : (size_t)n; return 0; }   // "-nm", MainController.cpp:168-173
+extern "C" int mf_dir_size(mf_dir* r, int* w, int* h) { if (!r) return -1; if (w) *w = r->W; if (h) *h = r->H; return 0; }
+
+// ImageLogReader::getNext + loadFrameFromDrive (:222-288).  mask / class_ids / boxes may be NULL.  *n_class_ids: in = capacity of
+// class_ids (and of boxes / 4), out = number of ids read (0 when the frame has no description file).  Returns 1 when a mask was
+// delivered, 0 when not, < 0 on error.
+extern "C" int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* mask, int32_t* class_ids, int32_t* boxes, int* n_class_ids,
+                               int64_t* timestamp)
+{
+    if (!r) { mf_set_error("null reader"); return -1; }
+    if (r->currentFrame + 1 >= r->numFrames) { mf_set_error("no more frames"); return -2; }
+    const size_t index = (size_t)(r->currentFrame + 1);
+    const std::string idx = indexString(r->indexW, index + r->startIndex);
+    const std::string depthPath = r->depthDir + r->depthPre + idx + r->depthExt, rgbPath = r->colorDir + r->colorPre + idx + r->colorExt;
+    if (!exists(depthPath)) { mf_set_error("Could not find depth-image file: " + depthPath); return -3; }
+    if (!exists(rgbPath)) { mf_set_error("Could not find rgb-image file: " + rgbPath); return -3; }
+    const std::string maskBase = r->maskDir + r->maskPre + idx, maskPath = maskBase + r->maskExt, descr = maskBase + ".txt";
+    const int cap = n_class_ids ? *n_class_ids : 0;
+    if (n_class_ids) *n_class_ids = 0;
+    if (r->hasMasks) {
+        if (!exists(maskPath)) { mf_set_error("Could not find mask-image file: " + maskPath); return -3; }
+        if (exists(descr) && class_ids) {              // loadMaskIDs (:302-322)
+            FILE* fp = fopen(descr.c_str(), "r");
+            std::string first; int ch;
+            while (fp && (ch = fgetc(fp)) != EOF && ch != '\n') first += (char)ch;
+            std::vector<int> ids{0};                   // mask 0 is always background
+            size_t p = 0;
+            while (p < first.size()) {
+                while (p < first.size() && first[p] == ' ') ++p;
+                size_t q = p; while (q < first.size() && first[q] != ' ') ++q;
+                if (q > p) ids.push_back(atoi(first.substr(p, q - p).c_str()));
+                p = q;
+            }
+            std::vector<int> bx; int a, b, c, d;
+            while (fp && fscanf(fp, "%d %d %d %d", &a, &b, &c, &d) == 4) { bx.push_back(b); bx.push_back(a); bx.push_back(d - b); bx.push_back(c - a); }   // cv::Rect(b, a, d-b, c-a)
+            if (fp) fclose(fp);
+            if (!bx.empty() && bx.size() / 4 != ids.size() - 1) { mf_set_error("Bounding-boxes provided, but number does not match class ids."); return -4; }
+            if ((int)ids.size() > cap) { mf_set_error("class id buffer too small"); return -5; }
+            for (size_t i = 0; i < ids.size(); ++i) class_ids[i] = ids[i];
+            if (boxes) for (size_t i = 0; i < bx.size(); ++i) boxes[i] = bx[i];
+            *n_class_ids = (int)ids.size();
+        }
+    }
+    std::string err; Image im;
+    // colour: cv::imread(path) == 8-bit, 3 channels; gray is replicated, alpha dropped, 16-bit scaled by >> 8
+    if (!loadImage(rgbPath, r->colorExt, im, err)) { mf_set_error("Could not read rgb-image file. (" + err + ")"); return -6; }
+    if (im.w != r->W || im.h != r->H) { mf_set_error("rgb-image size differs from the first frame"); return -6; }
+    const size_t P = (size_t)r->W * r->H;
+    for (size_t i = 0; i < P; ++i)
+        for (int c = 0; c < 3; ++c) {
+            const int sc = im.channels >= 3 ? c : 0;
+            const size_t e = i * im.channels + sc;
+            uint8_t v;
+            if (im.bits == 16) { uint16_t t; memcpy(&t, &im.data[e * 2], 2); v = (uint8_t)(t >> 8); } else v = im.data[e];
+            rgb[i * 3 + c] = v;
+        }
+    // depth: cv::imread(path, IMREAD_UNCHANGED); only CV_16UC1 is decodable here (:262-268)
+    if (!loadImage(depthPath, r->depthExt, im, err)) { mf_set_error("Could not read depth-image file. (" + err + ")"); return -7; }
+    if (im.w != r->W || im.h != r->H) { mf_set_error("depth-image size differs from the colour image"); return -7; }
+    if (!(im.bits == 16 && im.channels == 1)) { mf_set_error(std::string("Unsupported depth-files: ") + (im.bits == 16 ? "16U" : "8U") + "C" + std::to_string(im.channels)); return -7; }
+    for (size_t i = 0; i < P; ++i) { uint16_t t; memcpy(&t, &im.data[i * 2], 2); depth[i] = 0.001f * (float)t; }
+    int gotMask = 0;
+    if (r->hasMasks && index < r->maxMasks && mask) {
+        if (!loadImage(maskPath, r->maskExt, im, err) || (size_t)im.w * im.h != P) { mf_set_error("Could not read mask-image file."); return -8; }
+        if (im.channels != 1 || im.bits != 8) { mf_set_error("Incompatible mask image."); return -8; }
+        memcpy(mask, im.data.data(), P);
+        gotMask = 1;
+    }
+    if (timestamp) *timestamp = (int64_t)((float)index * 1000.0f / r->rateHz);        // :283 (float product truncated into the int64 field)
+    r->currentFrame++;
+    return gotMask;
+}

@@ -1,0 +1,170 @@
+"""Image-directory loader (mf_dir_*, the reference's ImageLogReader / "-dir" mode) on the CPU: file discovery, start index,
+default prefixes, depth scale, mask description files, last-frame behaviour, error messages -- and the PNG decoder itself against
+OpenCV (the library the reference decodes with) when cv2 is importable."""
+from __future__ import annotations
+
+import os
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+
+def _chunk(t, d):
+    return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+
+
+def write_png(path, a, filt=0):
+    """minimal PNG writer (numpy + zlib): uint8 HxW / HxWx3 / HxWx4 or uint16 HxW; one filter type for all rows"""
+    a = np.ascontiguousarray(a)
+    h, w = a.shape[:2]
+    ch = 1 if a.ndim == 2 else a.shape[2]
+    bits = 16 if a.dtype == np.uint16 else 8
+    ctype = {1: 0, 3: 2, 4: 6, 2: 4}[ch]
+    raw = a.astype(">u2").tobytes() if bits == 16 else a.tobytes()
+    row = w * ch * bits // 8
+    bpp = max(1, ch * bits // 8)
+    rows = np.frombuffer(raw, np.uint8).reshape(h, row).astype(np.int32)
+    out = bytearray()
+    prev = np.zeros(row, np.int32)
+    for y in range(h):
+        cur = rows[y]
+        left = np.concatenate([np.zeros(bpp, np.int32), cur[:-bpp]])
+        ul = np.concatenate([np.zeros(bpp, np.int32), prev[:-bpp]])
+        if filt == 0:
+            f = cur
+        elif filt == 1:
+            f = cur - left
+        elif filt == 2:
+            f = cur - prev
+        elif filt == 3:
+            f = cur - ((left + prev) >> 1)
+        else:
+            p = left + prev - ul
+            pa, pb, pc = np.abs(p - left), np.abs(p - prev), np.abs(p - ul)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, prev, ul))
+            f = cur - pred
+        out += bytes([filt]) + (f & 255).astype(np.uint8).tobytes()
+        prev = cur
+    with open(path, "wb") as fp:
+        fp.write(b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, bits, ctype, 0, 0, 0)))
+        z = zlib.compress(bytes(out), 6)
+        fp.write(_chunk(b"IDAT", z[: len(z) // 2]) + _chunk(b"IDAT", z[len(z) // 2:]) + _chunk(b"IEND", b""))
+
+
+def make_dataset(root, n=5, start=1, W=64, H=48, masks=True, same_dir=False, seed=0):
+    rng = np.random.default_rng(seed)
+    cdir = os.path.join(root, "all" if same_dir else "rgb"); ddir = cdir if same_dir else os.path.join(root, "depth")
+    mdir = cdir if same_dir else os.path.join(root, "mask")
+    for d in {cdir, ddir, mdir}:
+        os.makedirs(d, exist_ok=True)
+    pre = ("Color", "Depth", "Mask") if same_dir else ("", "", "")
+    frames = []
+    for i in range(n):
+        rgb = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        d16 = rng.integers(0, 6000, (H, W), dtype=np.uint16); d16[rng.random((H, W)) < 0.1] = 0
+        m = rng.integers(0, 3, (H, W), dtype=np.uint8)
+        idx = f"{i + start:04d}"
+        write_png(os.path.join(cdir, pre[0] + idx + ".png"), rgb, filt=i % 5)
+        write_png(os.path.join(ddir, pre[1] + idx + ".png"), d16, filt=(i + 2) % 5)
+        if masks:
+            with open(os.path.join(mdir, pre[2] + idx + ".pgm"), "wb") as fp:
+                fp.write(b"P5\n# made by the test\n%d %d\n255\n" % (W, H) + m.tobytes())
+            with open(os.path.join(mdir, pre[2] + idx + ".txt"), "w") as fp:
+                fp.write("41 77\n1 2 30 40\n5 6 20 25\n")
+        frames.append((rgb, d16, m))
+    return cdir, ddir, (mdir if masks else None), frames
+
+
+def test_dir_reader_roundtrip(product_lib, tmp_path):
+    import maskfusion_b200 as mfb
+    cdir, ddir, mdir, frames = make_dataset(str(tmp_path), n=5, start=1)
+    rd = mfb.ImageLogReader(cdir, ddir, mdir)
+    assert (rd.W, rd.H) == (64, 48) and rd.getNumFrames() == 5 and rd.hasMasks()
+    got = 0
+    while rd.hasMore():                                             # all five frames: no hidden last frame (ImageLogReader.cpp:326)
+        rgb, depth, ts, mask, cls, rois = rd.getNext()
+        r0, d0, m0 = frames[got]
+        assert np.array_equal(rgb, r0)                              # file order RGB (imread BGR + unconditional swap, :247-248)
+        assert np.array_equal(depth, np.float32(0.001) * d0.astype(np.float32))      # :262-268
+        assert np.array_equal(mask, m0)
+        assert cls.tolist() == [0, 41, 77]                          # leading background id (:306)
+        assert rois.tolist() == [[2, 1, 38, 29], [6, 5, 19, 15]]    # cv::Rect(b, a, d-b, c-a) (:317)
+        assert ts == int(np.float32(got) * np.float32(1000.0) / np.float32(24.0))    # :283
+        got += 1
+    assert got == 5
+    with pytest.raises(mfb.MFError):
+        rd.getNext()
+    rd.close()
+
+
+def test_dir_reader_default_prefixes_and_max_masks(product_lib, tmp_path):
+    import maskfusion_b200 as mfb
+    cdir, ddir, mdir, frames = make_dataset(str(tmp_path), n=4, start=0, same_dir=True)
+    rd = mfb.ImageLogReader(cdir, ddir, mdir)                       # one directory, no prefixes given => Color/Depth/Mask (:79-84)
+    assert rd.getNumFrames() == 4
+    rd.setMaxMasks(2)                                               # "-nm 2": masks only for the first two frames (:271)
+    seen = []
+    while rd.hasMore():
+        rgb, depth, ts, mask, cls, rois = rd.getNext()
+        seen.append(mask is not None)
+        assert np.array_equal(rgb, frames[len(seen) - 1][0])
+    assert seen == [True, True, False, False]
+    rd.close()
+
+
+def test_dir_reader_errors(product_lib, tmp_path):
+    import maskfusion_b200 as mfb
+    cdir, ddir, mdir, frames = make_dataset(str(tmp_path), n=3, start=1, masks=False)
+    os.remove(os.path.join(ddir, "0003.png"))
+    with pytest.raises(mfb.MFError, match="RGB-frames != Depth-frames"):
+        mfb.ImageLogReader(cdir, ddir)
+    write_png(os.path.join(ddir, "0003.png"), np.zeros((48, 64), np.uint8))          # 8-bit depth: "Unsupported depth-files: 8UC1"
+    rd = mfb.ImageLogReader(cdir, ddir)
+    rd.getNext(); rd.getNext()
+    with pytest.raises(mfb.MFError, match="Unsupported depth-files: 8UC1"):
+        rd.getNext()
+    rd.close()
+    os.rename(os.path.join(cdir, "0002.png"), os.path.join(cdir, "0002.jpg"))
+    with pytest.raises(mfb.MFError, match="same extension"):
+        mfb.ImageLogReader(cdir, ddir)
+    other = tmp_path / "x"; os.makedirs(other / "rgb"); os.makedirs(other / "depth")
+    write_png(str(other / "rgb" / "0005.png"), np.zeros((4, 4, 3), np.uint8)); write_png(str(other / "depth" / "0005.png"), np.zeros((4, 4), np.uint16))
+    with pytest.raises(mfb.MFError, match="start index"):
+        mfb.ImageLogReader(str(other / "rgb"), str(other / "depth"))
+
+
+def test_png_decoder_matches_opencv(product_lib, tmp_path):
+    """pin the decoder against OpenCV -- the reference's decoder (cv::imread) -- on files OpenCV itself wrote (its own filter choice and
+    compression): colour, 16-bit depth, gray mask, RGBA and gray colour inputs"""
+    cv2 = pytest.importorskip("cv2")
+    import maskfusion_b200 as mfb
+    rng = np.random.default_rng(3)
+    W, H = 80, 60
+    root = str(tmp_path)
+    for sub in ("rgb", "depth", "mask"):
+        os.makedirs(os.path.join(root, sub))
+    yy, xx = np.mgrid[0:H, 0:W]
+    for i in range(3):
+        bgr = np.stack([(xx * 3 + i * 20) % 256, (yy * 4 + xx) % 256, rng.integers(0, 256, (H, W))], -1).astype(np.uint8)
+        if i == 1:
+            bgr = np.concatenate([bgr, rng.integers(0, 256, (H, W, 1), dtype=np.uint8)], -1)       # BGRA file: imread drops alpha
+        if i == 2:
+            bgr = ((xx + yy) % 256).astype(np.uint8)                                             # gray file: imread replicates
+        d16 = ((xx * 37 + yy * 91 + i * 1000) % 65536).astype(np.uint16)
+        m = ((xx // 20 + yy // 20) % 4).astype(np.uint8)
+        assert cv2.imwrite(os.path.join(root, "rgb", f"{i:04d}.png"), bgr)
+        assert cv2.imwrite(os.path.join(root, "depth", f"{i:04d}.png"), d16)
+        assert cv2.imwrite(os.path.join(root, "mask", f"{i:04d}.png"), m)
+    rd = mfb.ImageLogReader(os.path.join(root, "rgb"), os.path.join(root, "depth"), os.path.join(root, "mask"))
+    for i in range(3):
+        rgb, depth, ts, mask, cls, rois = rd.getNext()
+        ref_rgb = cv2.imread(os.path.join(root, "rgb", f"{i:04d}.png"))[:, :, ::-1]              # imread + flipColors()
+        ref_d = cv2.imread(os.path.join(root, "depth", f"{i:04d}.png"), cv2.IMREAD_UNCHANGED)
+        ref_m = cv2.imread(os.path.join(root, "mask", f"{i:04d}.png"), cv2.IMREAD_GRAYSCALE)
+        assert np.array_equal(rgb, ref_rgb), i
+        assert np.array_equal(depth, np.float32(0.001) * ref_d.astype(np.float32)), i
+        assert np.array_equal(mask, ref_m), i
+        assert cls is None
+    rd.close()
