@@ -254,7 +254,8 @@ def run_ours(args, rank, world):
         b = algorithmic_bytes(k, S_live, P)
         if b and n:
             g = (b / 1e9) / (ms / n / 1e3)
-            per_kernel[k] = {"launches_per_step": round(n / (K + Wm), 2),      # the stage timer also sees the warm-up frames of its pass "avg_ms": round(ms / n, 5), "GBps": round(g, 1), "frac": round(g / peak, 4)}
+            # (the stage timer also sees the warm-up frames of its pass)
+            per_kernel[k] = {"launches_per_step": round(n / (K + Wm), 2), "avg_ms": round(ms / n, 5), "GBps": round(g, 1), "frac": round(g / peak, 4)}
     out = {
         "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -276,6 +277,19 @@ def run_ours(args, rank, world):
     if rank == 0 and world == 1:
         out["cpu_baseline"] = cpu_baseline(sample_frames=4)
     mf.close()
+    if world == 1:
+        # secondary legs, reported next to the main line and never instead of it: BASELINE configs[2] (3 tracked objects + the
+        # Mask R-CNN backbone on the same GPU; masks are inputs as in the reference's -maskdir mode: the R-CNN heads are not built)
+        try:
+            out["multi_object"] = multi_object_leg(torch, stream)
+        except Exception as e:          # noqa: BLE001
+            out["multi_object"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_cnn
+            out["backbone"] = bench_cnn.run(1024, iters=5, warm=2)
+        except Exception as e:          # noqa: BLE001
+            out["backbone"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world > 1:
         # secondary leg (BASELINE configs[3] shape): ONE replay with tracked object models sharded over the ranks --
         # frame broadcast, pose all-gather and ID-projection key merge over NCCL.  Reported next to the replica number, never instead of it.
@@ -288,6 +302,34 @@ def run_ours(args, rank, world):
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def multi_object_leg(torch, stream, n_frames=84, timed_from=24):
+    """configs[2] shape on one GPU: 3 objects spawn at frames 6/12/18 and are tracked (ICP+RGB, batched with the background in the
+    persistent tracking kernel); global ID projection, edge segmentation + GPU connected components / voting every frame;
+    frames/s of frames [timed_from, n_frames) through processFrame with host inputs"""
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene
+    cfg = mfb.default_config(W, H, capacityGlobal=1000000, capacityObject=600000, enableMultipleModels=1, icpWeight=20.0, so3=0,
+                             trackAllModels=1, modelSpawnOffset=6)
+    mf = mfb.MaskFusion(cfg, stream=stream.cuda_stream)
+    sc = SynthScene(W, H, n_objects=3, seed=0)
+    cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
+    frames = [sc.render(t)[:3] for t in range(n_frames)]
+    for t in range(timed_from):
+        mf.processFrame(frames[t][0], frames[t][1], t * 33333, mask=np.ascontiguousarray(frames[t][2]), classIDs=cls)
+    mf.sync(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for t in range(timed_from, n_frames):
+        mf.processFrame(frames[t][0], frames[t][1], t * 33333, mask=np.ascontiguousarray(frames[t][2]), classIDs=cls)
+    e1.record(stream)
+    mf.sync(); torch.cuda.synchronize()
+    models = mf.getModels()
+    res = {"value": round((n_frames - timed_from) / (e0.elapsed_time(e1) / 1e3), 2), "unit": "frames/s", "frames": n_frames - timed_from,
+           "models": len(models), "surfels": [m.lastCount() for m in models], "workload": "configs[2] shape: 3 tracked objects, 640x480, masks as inputs"}
+    mf.close()
+    return res
 
 
 def sharded_leg(torch, local, rank, world, n_frames=84, timed_from=24):

@@ -307,3 +307,13 @@ def test_klg_roundtrip_and_reader_quirks(product_lib, tmp_path):
     r.close()
     with pytest.raises(product_lib.MFError):
         product_lib.KlgLogReader(str(tmp_path / "missing.klg"), w, h)
+
+
+def test_entry_scripts_compile():
+    """bench.py / __graft_entry__.py / scripts are only executed on the GPU box: a syntax error there would cost a round"""
+    import glob
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for f in [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "scripts", "*.py")) + \
+            glob.glob(os.path.join(root, "maskfusion_b200", "*.py")) + glob.glob(os.path.join(root, "tests", "*.py")):
+        py_compile.compile(f, doraise=True)
