@@ -160,8 +160,8 @@ double mf_backbone_flops(mf_backbone* h);
 int mf_backbone_num_gemms(mf_backbone* h);
 
 /* ---- image-directory loader ("-dir", GUI/Tools/ImageLogReader.{h,cpp}; GUI/MainController.cpp:150-176) ----
- * colour .png/.ppm, depth 16-bit .png (x 0.001), masks 8-bit .png/.pgm + "<mask>.txt" (class ids, boxes); .jpg/.exr are refused
- * (no libjpeg / OpenEXR in this build).  hasMore() lets the last frame through (ImageLogReader.cpp:326), unlike the .klg reader. */
+ * colour .png/.ppm/.jpg, depth 16-bit .png (x 0.001), masks 8-bit .png/.pgm + "<mask>.txt" (class ids, boxes); .exr depth is refused
+ * (no OpenEXR in this build).  hasMore() lets the last frame through (ImageLogReader.cpp:326), unlike the .klg reader. */
 typedef struct mf_dir mf_dir;
 mf_dir* mf_dir_open(const char* color_dir, const char* depth_dir, const char* mask_dir /* NULL: no masks */, int index_width /* <=0: 4 */,
                     const char* color_prefix, const char* depth_prefix, const char* mask_prefix);   /* ImageLogReader::ImageLogReader */
@@ -175,6 +175,10 @@ int mf_dir_size(mf_dir* r, int* width, int* height);                    /* size 
  * delivered, 0 if not, < 0 on error; timestamp = index * 1000 / 24 (ImageLogReader.cpp:283). */
 int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* mask, int32_t* class_ids, int32_t* boxes, int* n_class_ids, int64_t* timestamp);
 void mf_dir_close(mf_dir* r);
+
+/* baseline JPEG -> 8-bit RGB exactly as libjpeg's default decode path produces it (islow IDCT, fancy upsampling; mf_jpeg.cu).
+ * out == NULL: only the size.  Used by both loaders; exported for the decoder's own parity test. */
+int mf_decode_jpeg(const uint8_t* data, int size, uint8_t* out, int capacity, int* width, int* height);
 
 /* ---- .klg log reader / writer (GUI/Tools/KlgLogReader.cpp:29-113) ---- */
 typedef struct mf_klg mf_klg;

@@ -35,6 +35,7 @@ SOURCES = {
     "mf_track.cu": ["-fmad=false"],
     "mf_host.cu": ["-fmad=false"],
     "mf_capi.cu": ["-fmad=false"],
+    "mf_jpeg.cu": [],                     # host code only: baseline JPEG decode, libjpeg's default path restated
     "mf_loader.cu": [],                   # host code only: image-directory loader (PNG/PNM decode, zlib)
     "mf_cnn.cu": [],                      # tensor-core GEMMs: no bit-exactness contract, FMA contraction on
 }

@@ -10,6 +10,7 @@
 #include <stack>
 
 using namespace mfb;
+namespace mfb { bool decodeJPEG(const uint8_t* data, size_t size, int& W, int& H, std::vector<uint8_t>& rgb, std::string& err); }   // mf_jpeg.cu
 
 struct mf_context { MaskFusion* mf; };
 
@@ -400,8 +401,8 @@ extern "C" int mf_icp_step(mf_context* ctx, int i, int level, const float* Rcurr
 }
 
 // ======================================================================================
-// .klg reader / writer (GUI/Tools/KlgLogReader.cpp:29-113).  JPEG-compressed colour is
-// not supported (no libjpeg in this build); zlib-compressed depth is.
+// .klg reader / writer (GUI/Tools/KlgLogReader.cpp:29-113): raw or zlib-compressed depth, raw or JPEG-compressed colour
+// (decoded by mf_jpeg.cu, a restatement of libjpeg's default decode path).
 // ======================================================================================
 struct mf_klg {
     FILE* fp; int W, H, numFrames, currentFrame; int flip;
@@ -438,8 +439,13 @@ extern "C" int mf_klg_get_next(mf_klg* k, uint8_t* rgb, float* depth, int64_t* t
     }
     for (size_t i = 0; i < P; ++i) depth[i] = (float)((double)d16[i] * 0.001);         // convertTo(CV_32FC1, 0.001), KlgLogReader.cpp:68-70
     if (rsz > 0) {
-        if ((size_t)rsz != P * 3) { g_err = "klg: JPEG colour not supported in this build (no libjpeg)"; return -5; }
-        memcpy(rgb, k->rbuf.data(), P * 3);
+        if ((size_t)rsz != P * 3) {
+            // JPEG colour (KlgLogReader.cpp:72-79 -> JPEGLoader::readData): libjpeg's RGB rows with R and B exchanged (JPEGLoader.h:72-81)
+            int jw = 0, jh = 0; std::vector<uint8_t> dec; std::string err;
+            if (!mfb::decodeJPEG(k->rbuf.data(), (size_t)rsz, jw, jh, dec, err)) { g_err = "klg: " + err; return -5; }
+            if (jw != k->W || jh != k->H) { g_err = "klg: JPEG frame size differs from the reader's resolution"; return -5; }
+            for (size_t i = 0; i < P * 3; i += 3) { rgb[i] = dec[i + 2]; rgb[i + 1] = dec[i + 1]; rgb[i + 2] = dec[i]; }
+        } else memcpy(rgb, k->rbuf.data(), P * 3);
     } else memset(rgb, 0, P * 3);
     if (k->flip) for (size_t i = 0; i < P * 3; i += 3) { uint8_t t = rgb[i]; rgb[i] = rgb[i + 2]; rgb[i + 2] = t; }
     if (timestamp) *timestamp = ts;

@@ -3,9 +3,9 @@
 // File discovery (prefix + one extension per stream, start index 0 or 1, zero-padded index of width indexW), the default
 // "Color"/"Depth"/"Mask" prefixes when directories overlap, the mask description file (class ids + boxes), the depth
 // conversions and the timestamps (index * 1000 / 24 Hz, :283) follow the reference.  The reference decodes with OpenCV
-// (cv::imread); OpenCV, libpng and libjpeg do not exist in this build, so PNG (zlib is here) and binary PNM are decoded by the
-// code below and the rest is refused with a message:
-//   colour  .png .ppm   (-> 8-bit RGB in file order: cv::imread gives BGR and the reader swaps unconditionally, :247-248)   .jpg: no
+// (cv::imread); OpenCV, libpng and libjpeg do not exist in this build, so PNG (zlib is here), binary PNM and baseline JPEG are
+// decoded in-tree and the rest is refused with a message:
+//   colour  .png .ppm .jpg (-> 8-bit RGB in file order: cv::imread gives BGR and the reader swaps unconditionally, :247-248; JPEG: mf_jpeg.cu)
 //   depth   .png 16-bit gray (-> 0.001f * v, :262-268)                                                                     .exr: no
 //   mask    .png / .pgm 8-bit gray (cv::IMREAD_GRAYSCALE of a gray file is the identity)
 // Unlike KlgLogReader, hasMore() lets the LAST frame through (currentFrame starts at -1, :145,:326).
@@ -22,6 +22,7 @@
 #include <vector>
 
 extern void mf_set_error(const std::string& e);          // mf_capi.cu (thread-local message behind mf_last_error)
+namespace mfb { bool decodeJPEG(const uint8_t* data, size_t size, int& W, int& H, std::vector<uint8_t>& rgb, std::string& err); }   // mf_jpeg.cu
 
 namespace {
 
@@ -148,7 +149,13 @@ bool loadImage(const std::string& path, const std::string& ext, Image& im, std::
     if (!readFile(path, f)) { err = "cannot read " + path; return false; }
     if (ext == ".png") return decodePNG(f, im, err);
     if (ext == ".ppm" || ext == ".pgm") return decodePNM(f, im, err);
-    err = "decoding " + ext + " files needs " + std::string(ext == ".exr" ? "OpenEXR" : "libjpeg") + ", which this build does not have (supported: .png, .ppm, .pgm)";
+    if (ext == ".jpg") {
+        std::vector<uint8_t> rgb;
+        if (!mfb::decodeJPEG(f.data(), f.size(), im.w, im.h, rgb, err)) return false;
+        im.channels = 3; im.bits = 8; im.data.swap(rgb);
+        return true;
+    }
+    err = "decoding " + ext + " files needs OpenEXR, which this build does not have (supported: .png, .jpg, .ppm, .pgm)";
     return false;
 }
 

@@ -168,3 +168,81 @@ def test_png_decoder_matches_opencv(product_lib, tmp_path):
         assert np.array_equal(mask, ref_m), i
         assert cls is None
     rd.close()
+
+
+def test_jpeg_decoder_matches_libjpeg(product_lib):
+    """the in-tree baseline JPEG decoder restates libjpeg's default path (islow IDCT, fancy upsampling, fixed-point colour
+    conversion): bit-identical to OpenCV's decoder (libjpeg-turbo) over sampling modes, qualities, restart intervals, odd sizes"""
+    cv2 = pytest.importorskip("cv2")
+    from maskfusion_b200.api import decode_jpeg
+    import maskfusion_b200 as mfb
+    rng = np.random.default_rng(0)
+    n = 0
+    for (W, H) in [(64, 48), (67, 45), (17, 9), (1, 1), (320, 240)]:
+        yy, xx = np.mgrid[0:H, 0:W]
+        for a in (rng.integers(0, 256, (H, W, 3), dtype=np.uint8),
+                  np.stack([128 + 100 * np.sin(xx / 7.0) * np.cos(yy / 5.0), 128 + 120 * np.sin((xx + yy) / 11.0), (xx * yy) % 256], -1).clip(0, 255).astype(np.uint8)):
+            for q in (30, 90, 100):
+                for sf in (cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420):
+                    for rst in (0, 3):
+                        ok, buf = cv2.imencode(".jpg", a, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf, cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+                        assert ok
+                        ref = cv2.imdecode(buf, cv2.IMREAD_COLOR)[:, :, ::-1]
+                        assert np.array_equal(decode_jpeg(buf.tobytes()), ref), (W, H, q, sf, rst)
+                        n += 1
+    ok, buf = cv2.imencode(".jpg", rng.integers(0, 256, (30, 41), dtype=np.uint8), [cv2.IMWRITE_JPEG_QUALITY, 80])       # single component
+    assert np.array_equal(decode_jpeg(buf.tobytes()), cv2.imdecode(buf, cv2.IMREAD_COLOR)[:, :, ::-1])
+    ok, buf = cv2.imencode(".jpg", rng.integers(0, 256, (32, 32, 3), dtype=np.uint8), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    with pytest.raises(mfb.MFError, match="progressive"):
+        decode_jpeg(buf.tobytes())
+    assert n == 180
+
+
+def test_klg_with_jpeg_colour_and_zlib_depth(product_lib, tmp_path):
+    """the compressed .klg layout Logger2 writes (KlgLogReader.cpp:53-89): zlib depth, JPEG colour decoded as JPEGLoader.h does
+    (libjpeg RGB rows with R and B exchanged, :72-81), then the optional -f flip"""
+    cv2 = pytest.importorskip("cv2")
+    import maskfusion_b200 as mfb
+    W, H, n = 64, 48, 3
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[0:H, 0:W]
+    path = str(tmp_path / "c.klg")
+    frames = []
+    with open(path, "wb") as fp:
+        fp.write(struct.pack("<i", n + 1))
+        for i in range(n + 1):
+            d16 = rng.integers(0, 5000, (H, W), dtype=np.uint16)
+            img = np.stack([(xx * 3 + i * 9) % 256, (yy * 5) % 256, (xx + yy) % 256], -1).astype(np.uint8)
+            ok, jpg = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, 90])
+            z = zlib.compress(d16.tobytes())
+            fp.write(struct.pack("<qii", 1000 * i, len(z), len(jpg)) + z + jpg.tobytes())
+            frames.append((d16, cv2.imdecode(jpg, cv2.IMREAD_COLOR)))       # BGR == libjpeg RGB with R/B exchanged
+    for flip in (False, True):
+        rd = mfb.KlgLogReader(path, W, H, flipColors=flip)
+        k = 0
+        while rd.hasMore():
+            rgb, depth, ts = rd.getNext()
+            d16, bgr = frames[k]
+            assert ts == 1000 * k
+            assert np.array_equal(depth, (d16.astype(np.float64) * 0.001).astype(np.float32))
+            assert np.array_equal(rgb, bgr[:, :, ::-1] if flip else bgr)
+            k += 1
+        assert k == n                                                       # the last frame of a .klg is never delivered (N11)
+        rd.close()
+
+
+def test_dir_reader_jpeg_colour(product_lib, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    import maskfusion_b200 as mfb
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "rgb")); os.makedirs(os.path.join(root, "depth"))
+    rng = np.random.default_rng(2)
+    for i in range(2):
+        cv2.imwrite(os.path.join(root, "rgb", f"{i:04d}.jpg"), rng.integers(0, 256, (50, 70, 3), dtype=np.uint8))
+        cv2.imwrite(os.path.join(root, "depth", f"{i:04d}.png"), rng.integers(0, 4000, (50, 70), dtype=np.uint16))
+    rd = mfb.ImageLogReader(os.path.join(root, "rgb"), os.path.join(root, "depth"))
+    for i in range(2):
+        rgb, depth, ts, mask, cls, rois = rd.getNext()
+        assert np.array_equal(rgb, cv2.imread(os.path.join(root, "rgb", f"{i:04d}.jpg"))[:, :, ::-1])
+        assert mask is None
+    rd.close()
