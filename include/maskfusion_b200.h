@@ -176,6 +176,10 @@ int mf_dir_size(mf_dir* r, int* width, int* height);                    /* size 
 int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* mask, int32_t* class_ids, int32_t* boxes, int* n_class_ids, int64_t* timestamp);
 void mf_dir_close(mf_dir* r);
 
+/* MaskFusion::exportPoses (Core/MaskFusion.cpp:849-881): writes <export_dir>poses-<model id>.txt for every active model
+ * ("seconds x y z qx qy qz qw", fixed notation, 6 decimals); returns the number of files written. */
+int mf_export_poses(mf_context* ctx, const char* export_dir);
+
 /* baseline JPEG -> 8-bit RGB exactly as libjpeg's default decode path produces it (islow IDCT, fancy upsampling; mf_jpeg.cu).
  * out == NULL: only the size.  Used by both loaders; exported for the decoder's own parity test. */
 int mf_decode_jpeg(const uint8_t* data, int size, uint8_t* out, int capacity, int* width, int* height);

@@ -143,6 +143,29 @@ extern "C" int mf_get_pose_log(mf_context* ctx, int i, double* out8, int max_ent
     return n;
 }
 
+// MaskFusion::exportPoses (MaskFusion.cpp:849-881): "<dir>poses-<id>.txt", one line per frame: seconds x y z qx qy qz qw, fixed, 6 decimals
+extern "C" int mf_export_poses(mf_context* ctx, const char* export_dir)
+{
+    MF_TRY MF_NEED(ctx)
+    if (!export_dir) { g_err = "export_poses: null directory"; return -2; }
+    ctx->mf->sync();
+    int written = 0;
+    for (auto& m : ctx->mf->models) {
+        const std::string filename = std::string(export_dir) + "poses-" + std::to_string((int)m->id) + ".txt";
+        FILE* fp = fopen(filename.c_str(), "w");
+        if (!fp) { g_err = "cannot write " + filename; return -3; }
+        for (size_t e = 0; e + 8 <= m->poseLog.size(); e += 8) {
+            fprintf(fp, "%.6f", m->poseLog[e] * 1e-6);
+            for (int k = 1; k < 8; ++k) fprintf(fp, " %.6f", (double)(float)m->poseLog[e + k]);      // the log holds Eigen floats (Model.h pose log)
+            fprintf(fp, "\n");
+        }
+        fclose(fp);
+        ++written;
+    }
+    return written;
+    MF_CATCH(-1)
+}
+
 // ---- per-stage entry points ----
 extern "C" int mf_set_frame(mf_context* ctx, const uint8_t* rgb, const float* depth, const uint8_t* mask)
 {

@@ -62,46 +62,7 @@ __constant__ float c_gauss5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 2
 
 // NaN-skipping 5x5 Gaussian decimation; window clamp excludes the last row/column and
 // the weight sum is an int, exactly as the reference (rule N9).
-__global__ void k_pyrdown_f(const float* __restrict__ src, int sw, int sh, float* __restrict__ dst)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    int dw = sw / 2, dh = sh / 2;
-    if (x >= dw || y >= dh) return;
-    const int D = 5;
-    int tx = min(2 * x - D / 2 + D, sw - 1), ty = min(2 * y - D / 2 + D, sh - 1);
-    float sum = 0; int count = 0;
-    for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
-        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
-            float v = src[cy * sw + cx];
-            if (!isnan(v)) {
-                float g = c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
-                sum += v * g;
-                count = (int)((float)count + g);
-            }
-        }
-    dst[y * dw + x] = sum / (float)count;
-}
 
-__global__ void k_pyrdown_u8(const uint8_t* __restrict__ src, int sw, int sh, uint8_t* __restrict__ dst)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    int dw = sw / 2, dh = sh / 2;
-    if (x >= dw || y >= dh) return;
-    const int D = 5;
-    int tx = min(2 * x - D / 2 + D, sw - 1), ty = min(2 * y - D / 2 + D, sh - 1);
-    float sum = 0; int count = 0;
-    for (int cy = max(0, 2 * y - D / 2); cy < ty; ++cy)
-        for (int cx = max(0, 2 * x - D / 2); cx < tx; ++cx) {
-            uint8_t v = src[cy * sw + cx];
-            if (v > 0) {
-                float g = c_gauss5[(ty - cy - 1) * 5 + (tx - cx - 1)];
-                sum += (float)v * g;
-                count = (int)((float)count + g);
-            }
-        }
-    float r = sum / (float)count;
-    dst[y * dw + x] = (r != r) ? 0 : (uint8_t)(int)r;
-}
 
 // Two pyramid levels in ONE launch: a block owns a PY_TX x PY_TY tile of the coarse level; it first evaluates the (2*PY_TX+3) x
 // (2*PY_TY+3) patch of the middle level that tile reads (same arithmetic as the single-level kernels, straight from the fine
@@ -172,13 +133,6 @@ struct Maps3 { const float* depth[3]; float4* vmap[3]; float4* nmap[3]; float4* 
 // depth -> vertex map + forward-difference normal map in ONE pass (the three vertices a
 // normal needs are rebuilt from depth; saves the vmap round trip through HBM).
 MF_D void vmapNmapPixel(const float* __restrict__ depth, int W, int H, Cam cam, float cutoff, float4* __restrict__ vmap, float4* __restrict__ nmap, int u, int v);
-__global__ void k_vmap_nmap(const float* __restrict__ depth, int W, int H, Cam cam, float cutoff,
-                            float4* __restrict__ vmap, float4* __restrict__ nmap)
-{
-    int u = blockIdx.x * blockDim.x + threadIdx.x, v = blockIdx.y * blockDim.y + threadIdx.y;
-    if (u >= W || v >= H) return;
-    vmapNmapPixel(depth, W, H, cam, cutoff, vmap, nmap, u, v);
-}
 __global__ void k_vmap_nmap3(Maps3 m, int W0, int H0, Cam cam0, float cutoff)
 {
     const int l = blockIdx.z, W = W0 >> l, H = H0 >> l;
@@ -236,12 +190,6 @@ __constant__ float c_soby[9] = {0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f
 // neighbourhood of intensities is non-zero and its own gradient magnitude passes the level's gate.  Frame-side, shared by all
 // models and all Gauss-Newton iterations (the tracker used to re-derive it per model per level).
 MF_D void sobelPixel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad, float minScale, uint8_t* __restrict__ rgbValid, int x, int y);
-__global__ void k_sobel(const uint8_t* __restrict__ src, int W, int H, short2* __restrict__ grad, float minScale, uint8_t* __restrict__ rgbValid)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    sobelPixel(src, W, H, grad, minScale, rgbValid, x, y);
-}
 __global__ void k_sobel3(Maps3 m, int W0, int H0)
 {
     const int l = blockIdx.z, W = W0 >> l, H = H0 >> l;
@@ -373,14 +321,6 @@ __global__ void k_map_to_planar(const float4* __restrict__ m, int P, float* __re
     out[i] = v.x; out[P + i] = v.y; out[2 * P + i] = v.z;
 }
 
-__global__ void k_project_points(const float* __restrict__ depth, int W, int H, Cam cam, float4* __restrict__ cloud)
-{
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    float z = depth[y * W + x];
-    float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
-    cloud[y * W + x] = make_float4(((float)x - cam.cx) * z * ifx, ((float)y - cam.cy) * z * ify, z, 0.f);   // cudafuncs.cu:718-736
-}
 __global__ void k_project_points3(Maps3 m, int W0, int H0, Cam cam0)
 {
     const int l = blockIdx.z, W = W0 >> l, H = H0 >> l;
@@ -400,16 +340,6 @@ void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t
 {
     dim3 b(BIL_BX, BIL_BY);
     prof_mark(s, "k_bilateral"); k_bilateral<<<grid2(W, H, b), b, 0, s>>>(depth, out, W, H);
-}
-void launch_pyrdown_f(const float* src, int sw, int sh, float* dst, cudaStream_t s)
-{
-    dim3 b(32, 8);
-    prof_mark(s, "k_pyrdown_f"); k_pyrdown_f<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
-}
-void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStream_t s)
-{
-    dim3 b(32, 8);
-    prof_mark(s, "k_pyrdown_u8"); k_pyrdown_u8<<<grid2(sw / 2, sh / 2, b), b, 0, s>>>(src, sw, sh, dst);
 }
 void launch_pyrdown2_f(const float* src, int sw, int sh, float* dst1, float* dst2, cudaStream_t s)
 {
@@ -442,20 +372,10 @@ void launch_project_points3(const float* const* depth, int W, int H, Cam cam, fl
     dim3 b(32, 8), g = grid2(W, H, b); g.z = 3;
     prof_mark(s, "k_project_points3"); k_project_points3<<<g, b, 0, s>>>(m, W, H, cam);
 }
-void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s)
-{
-    dim3 b(32, 8);
-    prof_mark(s, "k_vmap_nmap"); k_vmap_nmap<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cutoff, vmap, nmap);
-}
 void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s) { k_intensity<<<(P + 255) / 256, 256, 0, s>>>(img, P, out); }
 void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s)
 {
     prof_mark(s, "k_intensity_select"); k_intensity_select<<<(P + 255) / 256, 256, 0, s>>>(imgPred, imgFill, nonBlack, denom, forceFill, P, out);
-}
-void launch_sobel(const uint8_t* src, int W, int H, short2* grad, float minScale, uint8_t* rgbValid, cudaStream_t s)
-{
-    dim3 b(32, 8);
-    prof_mark(s, "k_sobel"); k_sobel<<<grid2(W, H, b), b, 0, s>>>(src, W, H, grad, minScale, rgbValid);
 }
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
                        int W, int H, const DevPose* pose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s)
@@ -465,10 +385,5 @@ void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* s
                                                        v[0], n[0], v[1], n[1], v[2], n[2], depth0);
 }
 void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s) { k_map_to_planar<<<(P + 255) / 256, 256, 0, s>>>(m, P, out); }
-void launch_project_points(const float* depth, int W, int H, Cam cam, float4* cloud, cudaStream_t s)
-{
-    dim3 b(32, 8);
-    prof_mark(s, "k_project_points"); k_project_points<<<grid2(W, H, b), b, 0, s>>>(depth, W, H, cam, cloud);
-}
 
 }  // namespace mfb

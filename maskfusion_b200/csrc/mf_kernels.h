@@ -123,23 +123,18 @@ void prof_mark(cudaStream_t s, const char* name);
 // ---- mf_frame.cu ----
 void launch_unpack_rgb(const uint8_t* rgb3, uchar4* out, int P, cudaStream_t s);
 void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t s);
-void launch_pyrdown_f(const float* src, int sw, int sh, float* dst, cudaStream_t s);
-void launch_pyrdown_u8(const uint8_t* src, int sw, int sh, uint8_t* dst, cudaStream_t s);
 // fused variants: two pyramid levels per launch; three levels of a per-pixel kernel per launch (blockIdx.z = level)
 void launch_pyrdown2_f(const float* src, int sw, int sh, float* dst1, float* dst2, cudaStream_t s);
 void launch_pyrdown2_u8(const uint8_t* src, int sw, int sh, uint8_t* dst1, uint8_t* dst2, cudaStream_t s);
 void launch_vmap_nmap3(const float* const* depth, int W, int H, Cam cam, float cutoff, float4* const* vmap, float4* const* nmap, cudaStream_t s);
 void launch_sobel3(const uint8_t* const* img, int W, int H, short2* const* grad, uint8_t* const* rgbValid, cudaStream_t s);
 void launch_project_points3(const float* const* depth, int W, int H, Cam cam, float4* const* cloud, cudaStream_t s);
-void launch_vmap_nmap(const float* depth, int W, int H, Cam cam, float cutoff, float4* vmap, float4* nmap, cudaStream_t s);
 void launch_intensity(const uchar4* img, int P, uint8_t* out, cudaStream_t s);
 void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const uint32_t* nonBlack, float denom, int forceFill, int P, uint8_t* out, cudaStream_t s);
-void launch_sobel(const uint8_t* src, int W, int H, short2* grad, float minScale, uint8_t* rgbValid, cudaStream_t s);
 float track_min_scale(int level);          // gradient-magnitude gate of the photometric term at a pyramid level (RGBDOdometry.cpp:44-49)
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
                        int W, int H, const DevPose* dpose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s);
 void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s);
-void launch_project_points(const float* depth, int W, int H, Cam cam, float4* cloud, cudaStream_t s);
 
 // ---- mf_surfel.cu ----
 void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s);

@@ -416,24 +416,6 @@ MF_D void gradU8(const uint8_t* __restrict__ img, int W, int x, int y, float& gx
 }
 
 
-// pose-independent part of residualKernel (reduce.cu:821-845): 4x4 window of non-zero intensities + gradient-magnitude gate
-MF_D bool rgbValidPixel(const uint8_t* __restrict__ nextImage, const short2* __restrict__ grad, int W, int H, int k, float minScale)
-{
-    int i = k / W, j0 = k - i * W;
-    bool valid = false;
-    if (j0 < W - 5 && i < H - 1) {
-        valid = true;
-        for (int u = max(i - 2, 0); u < min(i + 2, H); ++u)
-            for (int v = max(j0 - 2, 0); v < min(j0 + 2, W); ++v) valid = valid && (nextImage[u * W + v] > 0);
-        if (valid) {
-            short2 g = grad[k];
-            float mTwo = (float)(((int)g.x * (int)g.x) + ((int)g.y * (int)g.y));
-            valid = mTwo >= minScale;
-        }
-    }
-    return valid;
-}
-
 // unpivoted, unrolled 3x3 LDL^T for the SO(3) step (same contract as ldltSolve6Fast)
 __device__ __forceinline__ bool ldltSolve3Fast(const double* A, const double* b, double* x)
 {

@@ -176,6 +176,12 @@ def _run_sequences(n, **kw):
     mf.sync()
     lo = np.array([orc.model(0).log[i] for i in range(orc.model(0).nlog * 8)]).reshape(-1, 8)
     lc = mf.getBackgroundModel().poseLog()
+    # MaskFusion::exportPoses: the file holds the same log, seconds first, 6 decimals
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        assert mf.exportPoses(d + "/") == 1
+        txt = np.loadtxt(os.path.join(d, "poses-0.txt")).reshape(-1, 8)
+    assert txt.shape == lc.shape and np.allclose(txt[:, 0], lc[:, 0] * 1e-6, atol=1e-6) and np.allclose(txt[:, 1:], lc[:, 1:], atol=1e-6)
     counts = (orc.count(0), mf.getBackgroundModel().lastCount())
     # index-map agreement on the final state (free-running, no teacher forcing)
     mf.getBackgroundModel().predictIndices(mf.getTick())
