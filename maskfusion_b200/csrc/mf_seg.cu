@@ -129,13 +129,21 @@ __global__ void k_cc_number(int* __restrict__ L, int P, int* __restrict__ dense,
     if (i >= P) return;
     if (L[i] == i) dense[i] = (int)atomicAdd(counter, 1u) + 1;
 }
+// Integer histogram update with one atomic per distinct bin per warp: neighbouring pixels mostly hit the same bin (one component /
+// one model covers most of the image), and 300 k atomics on ONE address serialise (k_seg_hist, k_mask_overlap and this kernel took
+// 200-300 us each, ncu r01i).  key < 0: this lane adds nothing.  All 32 lanes must call.  Sums of integers: order-free, results identical.
+MF_D void warpAggAdd(int* __restrict__ bins, int key)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&bins[key], __popc(peers));
+}
 __global__ void k_cc_relabel(const int* __restrict__ L, const int* __restrict__ dense, int P, int* __restrict__ lab, int* __restrict__ area)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    int l = 0;
-    if (L[i] >= 0) { l = dense[ccFind(L, i)]; atomicAdd(&area[l], 1); }
-    lab[i] = l;
+    int l = 0, key = -1;
+    if (i < P && L[i] >= 0) { l = dense[ccFind(L, i)]; key = l; }
+    warpAggAdd(area, key);
+    if (i < P) lab[i] = l;
 }
 // one Jacobi sweep of the edge-removal loop (MfSegmentation.cpp:243-291): reads the previous labels only
 __global__ void k_remove_edges(const int* __restrict__ labIn, int* __restrict__ labOut, const float* __restrict__ depth,
@@ -161,10 +169,10 @@ __global__ void k_seg_hist(const int* __restrict__ lab, const uint8_t* __restric
                            const uint8_t* __restrict__ idToIndex, int nModels, int nMasks, int* __restrict__ compModel, int* __restrict__ compMask)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    int c = lab[i];
-    atomicAdd(&compModel[(size_t)c * nModels + idToIndex[projID[i]]], 1);
-    if (nMasks) atomicAdd(&compMask[(size_t)c * nMasks + mask[i]], 1);
+    const bool in = i < P;
+    const int c = in ? lab[i] : 0;
+    warpAggAdd(compModel, in ? c * nModels + (int)idToIndex[projID[i]] : -1);
+    if (nMasks) warpAggAdd(compMask, in ? c * nMasks + (int)mask[i] : -1);
 }
 __global__ void k_component_map(int nComponents, const int* __restrict__ area, const int* __restrict__ compModel, const int* __restrict__ compMask,
                                 int nModels, int nMasks, const uint8_t* __restrict__ indexToId, int minMappedComponentSize,
@@ -198,9 +206,9 @@ __global__ void k_mask_overlap(const uint8_t* __restrict__ seg, const uint8_t* _
                                const uint8_t* __restrict__ isModelId, int P, unsigned* __restrict__ maskOverlap)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    uint8_t id = projID[i];
-    if (isModelId[id]) atomicAdd(&maskOverlap[(int)idToIndex[id] * 256 + seg[i]], 1u);
+    int key = -1;
+    if (i < P) { uint8_t id = projID[i]; if (isModelId[id]) key = (int)idToIndex[id] * 256 + seg[i]; }
+    warpAggAdd(reinterpret_cast<int*>(maskOverlap), key);
 }
 __global__ void k_seg_final(const uint8_t* __restrict__ seg, const int* __restrict__ lab, const int* __restrict__ mapToMask,
                             const int* __restrict__ absorb, const uint8_t* __restrict__ maskToID, int P, uint8_t* __restrict__ out)

@@ -15,6 +15,8 @@ echo "== bench" ; timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_
 if [ "$MODE" = "full" ]; then
   echo "== bench reference arm" ; timeout 600 python bench.py --impl reference --steps 3 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ; tail -c 1200 gpurun_out/bench_ref.json
   echo "== ncu launch list" ; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 330 --csv --log-file gpurun_out/launches.csv python bench.py --steps 3 --warmup 2 > gpurun_out/ncu_bench.log 2>&1 ; echo "ncu rc=$?"
+  echo "== backbone" ; timeout 300 python scripts/bench_cnn.py 1024 10 > gpurun_out/bench_cnn.json 2> gpurun_out/bench_cnn.err ; tail -c 400 gpurun_out/bench_cnn.json
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm -s 40 -c 12 -f -o gpurun_out/prof_k_gemm python scripts/bench_cnn.py 1024 2 > gpurun_out/ncu_k_gemm.log 2>&1 ; echo "ncu gemm rc=$?"
   for K in "$@"; do
     echo "== ncu full $K" ; timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o gpurun_out/prof_$K python bench.py --steps 3 --warmup 2 > gpurun_out/ncu_$K.log 2>&1 ; echo "rc=$?"
   done
