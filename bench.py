@@ -398,7 +398,7 @@ def cpu_baseline(sample_frames):
         p.process_frame(r, d, (i + 1) * 33333)
     dt = time.time() - t0
     return {"value": round(sample_frames / dt, 4), "unit": "frames/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_frames} frames of the same replay, {allv.shape[0]} surfels; OpenMP only in the bilateral and association passes, surfel passes scalar"}
+            "sample": f"{sample_frames} frames of the same replay, {allv.shape[0]} surfels; OpenMP in every per-pixel / per-surfel pass (sums and ordered compaction keep the sequential order, results bit-identical to one thread)"}
 
 
 def run_reference(args, rank, world):

@@ -122,6 +122,7 @@ void orc_pyrdown_gauss_f(const float* src, int sw, int sh, float* dst)
 {
     int dw = sw / 2, dh = sh / 2;
     const int D = 5;
+    #pragma omp parallel for schedule(static)
     for (int y = 0; y < dh; ++y)
         for (int x = 0; x < dw; ++x) {
             int tx = imin(2 * x - D / 2 + D, sw - 1);
@@ -145,6 +146,7 @@ void orc_pyrdown_gauss_u8(const uint8_t* src, int sw, int sh, uint8_t* dst)
 {
     int dw = sw / 2, dh = sh / 2;
     const int D = 5;
+    #pragma omp parallel for schedule(static)
     for (int y = 0; y < dh; ++y)
         for (int x = 0; x < dw; ++x) {
             int tx = imin(2 * x - D / 2 + D, sw - 1);
@@ -169,6 +171,7 @@ void orc_pyrdown_gauss_u8(const uint8_t* src, int sw, int sh, uint8_t* dst)
 void orc_vmap(const float* depth, int W, int H, orc_cam cam, float cutoff, float* vmap)
 {
     float fx_inv = 1.f / cam.fx, fy_inv = 1.f / cam.fy;
+    #pragma omp parallel for schedule(static)
     for (int v = 0; v < H; ++v)
         for (int u = 0; u < W; ++u) {
             float z = depth[v * W + u];
@@ -189,6 +192,7 @@ void orc_vmap(const float* depth, int W, int H, orc_cam cam, float cutoff, float
 void orc_nmap(const float* vmap, int W, int H, float* nmap)
 {
     const float* X = vmap; const float* Y = vmap + H * W; const float* Z = vmap + 2 * H * W;
+    #pragma omp parallel for schedule(static)
     for (int v = 0; v < H; ++v)
         for (int u = 0; u < W; ++u) {
             float* nx = &nmap[(0 * H + v) * W + u];
@@ -211,6 +215,7 @@ void orc_nmap(const float* vmap, int W, int H, float* nmap)
 /* cudafuncs.cu:271-311 */
 void orc_copy_maps(const float* vt, const float* nt, int W, int H, float* vmap, float* nmap)
 {
+    #pragma omp parallel for schedule(static)
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             const float* vs = &vt[(y * W + x) * 4];
@@ -227,6 +232,7 @@ void orc_copy_maps(const float* vt, const float* nt, int W, int H, float* vmap, 
 void orc_resize_map(const float* in, int sw, int sh, int normalize, float* out)
 {
     int dw = sw / 2, dh = sh / 2;
+    #pragma omp parallel for schedule(static)
     for (int y = 0; y < dh; ++y)
         for (int x = 0; x < dw; ++x) {
             int xs = 2 * x, ys = 2 * y;
@@ -256,6 +262,7 @@ void orc_resize_map(const float* in, int sw, int sh, int normalize, float* out)
 void orc_transform_maps(float* vmap, float* nmap, int W, int H, const float* R, const float* t)
 {
     int P = W * H;
+    #pragma omp parallel for schedule(static)
     for (int i = 0; i < P; ++i) {
         float x = vmap[i];
         if (!isnan(x)) {
@@ -277,6 +284,7 @@ void orc_transform_maps(float* vmap, float* nmap, int W, int H, const float* R, 
 /* cudafuncs.cu:602-613 */
 void orc_vertices_to_depth(const float* vt, int W, int H, float cutoff, float* depth)
 {
+    #pragma omp parallel for schedule(static)
     for (int i = 0; i < W * H; ++i) {
         float z = vt[i * 4 + 2];
         depth[i] = (z > cutoff || z <= 0) ? qnan() : z;
@@ -286,6 +294,7 @@ void orc_vertices_to_depth(const float* vt, int W, int H, float cutoff, float* d
 /* cudafuncs.cu:626-639: texel (x,y,z) = the three uploaded channels in order */
 void orc_rgb_to_intensity(const uint8_t* rgb, int W, int H, uint8_t* out)
 {
+    #pragma omp parallel for schedule(static)
     for (int i = 0; i < W * H; ++i) {
         float v = ((float)rgb[i * 3 + 0] * 0.114f + (float)rgb[i * 3 + 1] * 0.299f) + (float)rgb[i * 3 + 2] * 0.587f;
         out[i] = (uint8_t)(int)v;
@@ -297,6 +306,7 @@ void orc_sobel(const uint8_t* src, int W, int H, int16_t* dx, int16_t* dy)
 {
     static const float gx[9] = { 0.52201f, 0.00000f, -0.52201f, 0.79451f, -0.00000f, -0.79451f, 0.52201f, 0.00000f, -0.52201f };
     static const float gy[9] = { 0.52201f, 0.79451f, 0.52201f, 0.00000f, 0.00000f, 0.00000f, -0.52201f, -0.79451f, -0.52201f };
+    #pragma omp parallel for schedule(static)
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             float dxv = 0, dyv = 0; int k = 8;
@@ -315,6 +325,7 @@ void orc_sobel(const uint8_t* src, int W, int H, int16_t* dx, int16_t* dy)
 void orc_project_points(const float* depth, int W, int H, orc_cam cam, float* cloud)
 {
     float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
+    #pragma omp parallel for schedule(static)
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             float z = depth[y * W + x];

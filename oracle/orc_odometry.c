@@ -31,6 +31,28 @@ static void accumulate(const float* row, int n, int found, double* out)
     out[k] += found ? 1.0 : 0.0;
 }
 
+/* Multi-threaded evaluation with the SEQUENTIAL sums kept bit for bit: the per-pixel rows (the expensive part: gathers, divisions,
+ * square roots) are computed by all threads into a buffer of 8 floats per pixel (row[0..n], ..., flag in [7]); the accumulators are
+ * then distributed over the threads, each one summing ITS accumulator over the pixels in the original order -- the same additions
+ * in the same order as accumulate() in a single loop (a pixel that contributes nothing adds +0.0, the identity, and is skipped). */
+static void accumulate_rows(const float* rows, int P, int n, double* out)
+{
+    int pi[32], pj[32], nq = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = i; j < n + 1; ++j) { pi[nq] = i; pj[nq] = j; ++nq; }
+    pi[nq] = n; pj[nq] = n; ++nq;
+#pragma omp parallel for schedule(static, 1)
+    for (int q = 0; q <= nq; ++q) {
+        double s = 0.0;
+        if (q < nq) {
+            const int a = pi[q], b = pj[q];
+            for (int p = 0; p < P; ++p) { const float* r = rows + (size_t)p * 8; if (r[7] != 0.f) s += (double)(r[a] * r[b]); }
+        } else
+            for (int p = 0; p < P; ++p) s += rows[(size_t)p * 8 + 7] != 0.f ? 1.0 : 0.0;
+        out[q] = s;
+    }
+}
+
 /* reduce.cu:259-444 */
 void orc_icp_step(const float* Rcurr, const float* tcurr, const float* vmap_curr, const float* nmap_curr,
                   const float* Rprev_inv, const float* tprev, orc_cam cam,
@@ -38,9 +60,9 @@ void orc_icp_step(const float* Rcurr, const float* tcurr, const float* vmap_curr
                   float distThres, float angleThres, int W, int H, double* out29)
 {
     int P = W * H;
-    memset(out29, 0, 29 * sizeof(double));
+    float* rows = (float*)malloc((size_t)P * 8 * sizeof(float));
+#pragma omp parallel for schedule(static)
     for (int i = 0; i < P; ++i) {
-        int y = i / W, x = i - y * W;
         float row[7] = { 0, 0, 0, 0, 0, 0, 0 };
         int found = 0;
         float vcurr[3] = { vmap_curr[i], vmap_curr[P + i], vmap_curr[2 * P + i] };
@@ -80,8 +102,12 @@ void orc_icp_step(const float* Rcurr, const float* tcurr, const float* vmap_curr
                 row[6] = (n_cp[0] * (s_cp[0] - d_cp[0]) + n_cp[1] * (s_cp[1] - d_cp[1])) + n_cp[2] * (s_cp[2] - d_cp[2]);
             }
         }
-        accumulate(row, 6, found, out29);
+        float* r = rows + (size_t)i * 8;
+        for (int k = 0; k < 7; ++k) r[k] = row[k];
+        r[7] = found ? 1.f : 0.f;
     }
+    accumulate_rows(rows, P, 6, out29);
+    free(rows);
 }
 
 /* reduce.cu:774-997 */
@@ -91,7 +117,8 @@ void orc_rgb_residual(float minScale, const int16_t* dIdx, const int16_t* dIdy,
                       orc_dataterm* corresImg, float maxDepthDelta, const float* kt,
                       const float* K, int W, int H, int* count, int* sigmaSum)
 {
-    int cnt = 0, sig = 0;
+    int cnt = 0, sig = 0;                 /* integer sums: any order gives the same totals */
+#pragma omp parallel for schedule(static) reduction(+ : cnt, sig)
     for (int k = 0; k < W * H; ++k) {
         int i = k / W, j0 = k - i * W;
         orc_dataterm c; memset(&c, 0, sizeof c);
@@ -135,8 +162,10 @@ void orc_rgb_residual(float minScale, const int16_t* dIdx, const int16_t* dIdy,
 void orc_rgb_step(const orc_dataterm* corres, float sigma, const float* cloud, float fx, float fy,
                   const int16_t* dIdx, const int16_t* dIdy, float sobelScale, int W, int H, double* out29)
 {
-    memset(out29, 0, 29 * sizeof(double));
-    for (int i = 0; i < W * H; ++i) {
+    const int P = W * H;
+    float* rows = (float*)malloc((size_t)P * 8 * sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; ++i) {
         const orc_dataterm* c = &corres[i];
         float row[7] = { 0, 0, 0, 0, 0, 0, 0 };
         if (c->valid) {
@@ -156,8 +185,12 @@ void orc_rgb_step(const orc_dataterm* corres, float sigma, const float* cloud, f
             row[4] = cp[2] * v0 - cp[0] * v2;
             row[5] = -cp[1] * v0 + cp[0] * v1;
         }
-        accumulate(row, 6, c->valid, out29);
+        float* r = rows + (size_t)i * 8;
+        for (int k = 0; k < 7; ++k) r[k] = row[k];
+        r[7] = c->valid ? 1.f : 0.f;
     }
+    accumulate_rows(rows, P, 6, out29);
+    free(rows);
 }
 
 /* reduce.cu:999-1202 */
@@ -172,8 +205,10 @@ static void grad_u8(const uint8_t* img, int W, int x, int y, float* gx, float* g
 void orc_so3_step(const uint8_t* lastImage, const uint8_t* nextImage, const float* B, const float* kinv,
                   const float* krlr, int W, int H, double* out11)
 {
-    memset(out11, 0, 11 * sizeof(double));
-    for (int k = 0; k < W * H; ++k) {
+    const int P = W * H;
+    float* rows = (float*)malloc((size_t)P * 8 * sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < P; ++k) {
         int y = k / W, x = k - y * W;
         float ur[3] = { (float)x, (float)y, 1.0f }, wr[3];
         m3v(B, ur, wr);
@@ -200,8 +235,13 @@ void orc_so3_step(const uint8_t* lastImage, const uint8_t* nextImage, const floa
             row[2] = l[0] * p[1] - l[1] * p[0];
             row[3] = -((float)nextImage[wy * W + wx] - (float)lastImage[k]);
         }
-        accumulate(row, 3, found, out11);
+        float* r = rows + (size_t)k * 8;
+        for (int q = 0; q < 4; ++q) r[q] = row[q];
+        r[4] = r[5] = r[6] = 0.f;
+        r[7] = found ? 1.f : 0.f;
     }
+    accumulate_rows(rows, P, 3, out11);
+    free(rows);
 }
 
 /* ------------------------------------------------------------------------- */

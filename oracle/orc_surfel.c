@@ -32,6 +32,13 @@ static inline void rot(const float* T, const float* n, float* o)
     o[1] = (T[4] * n[0] + T[5] * n[1]) + T[6] * n[2];
     o[2] = (T[8] * n[0] + T[9] * n[1]) + T[10] * n[2];
 }
+/* depth-tested key images are built by all threads: min over 64-bit keys is order-free, the winner is the one a sequential loop finds */
+static inline void atomic_min_u64(uint64_t* p, uint64_t v)
+{
+    uint64_t o = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < o && !__atomic_compare_exchange_n(p, &o, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+}
+
 static inline float dot3(const float* a, const float* b) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
 static inline void normalize3(float* v)
 {
@@ -128,6 +135,7 @@ void orc_predict_indices(const float* surfels, int count, const float* pose, orc
     size_t P = (size_t)W * H;
     uint64_t* key = (uint64_t*)malloc(P * sizeof(uint64_t));
     for (size_t i = 0; i < P; ++i) key[i] = ~0ull;
+#pragma omp parallel for schedule(static)
     for (int id = 0; id < count; ++id) {
         const float* s = surfels + (size_t)id * 12;
         float ph[3];
@@ -141,8 +149,9 @@ void orc_predict_indices(const float* surfels, int count, const float* pose, orc
         if (!(fx_ >= 0 && fy_ >= 0 && fx_ < (float)W && fy_ < (float)H)) continue;
         int px = (int)fx_, py = (int)fy_;
         uint64_t k = ((uint64_t)fbits(zn) << 32) | (uint32_t)id;
-        if (k < key[py * W + px]) key[py * W + px] = k;
+        atomic_min_u64(&key[py * W + px], k);
     }
+#pragma omp parallel for schedule(static)
     for (size_t i = 0; i < P; ++i) {
         float* vc = vertConf4 + i * 4; float* ct = colorTime4 + i * 4; float* nr = normRad4 + i * 4;
         if (key[i] == ~0ull) {
@@ -342,16 +351,34 @@ int orc_clean(const float* surfels, int count, const uint8_t* updateId, const fl
 {
     float tinv[16];
     orc_pose_inverse(pose, tinv);
+    /* The per-vertex test is independent of the others; only the ORDER of the survivors matters (N5).  Chunks of vertices are
+     * evaluated by all threads into a scratch buffer, then copied out in order -- the same output as the single loop, including the
+     * stop at `capacity` (vertices behind the stop have no side effects). */
+    enum { CHUNK = 1 << 18 };
+    float* tmp = (float*)malloc((size_t)CHUNK * 12 * sizeof(float));
+    uint8_t* kept = (uint8_t*)malloc(CHUNK);
     int n = 0;
-    for (int i = 0; i < count && n < capacity; ++i)
-        n += clean_vertex(surfels + (size_t)i * 12, out + (size_t)n * 12, idx, vertConf4, colorTime4, depthFilt, mask,
-                          tinv, cam, W, H, time, timeDelta, confThreshold, outlierCoeff, maskID);
     size_t P = (size_t)W * H;
-    for (size_t p = 0; p < P && n < capacity; ++p) {
-        if (updateId[p] == 0) continue;        /* merges (w=-1) are emitted into the buffer but always fail the test */
-        n += clean_vertex(meas + p * 12, out + (size_t)n * 12, idx, vertConf4, colorTime4, depthFilt, mask,
-                          tinv, cam, W, H, time, timeDelta, confThreshold, outlierCoeff, maskID);
+    const size_t total = (size_t)count + P;          /* old surfels, then the per-pixel new-vertex slots in x-major order */
+    for (size_t base = 0; base < total && n < capacity; base += CHUNK) {
+        const size_t m = total - base < (size_t)CHUNK ? total - base : (size_t)CHUNK;
+#pragma omp parallel for schedule(static)
+        for (size_t j = 0; j < m; ++j) {
+            const size_t e = base + j;
+            const float* in;
+            if (e < (size_t)count) in = surfels + e * 12;
+            else {
+                const size_t p = e - (size_t)count;
+                if (updateId[p] == 0) { kept[j] = 0; continue; }      /* merges (w=-1) are emitted into the buffer but always fail the test */
+                in = meas + p * 12;
+            }
+            kept[j] = (uint8_t)clean_vertex(in, tmp + j * 12, idx, vertConf4, colorTime4, depthFilt, mask,
+                                            tinv, cam, W, H, time, timeDelta, confThreshold, outlierCoeff, maskID);
+        }
+        for (size_t j = 0; j < m && n < capacity; ++j)
+            if (kept[j]) { memcpy(out + (size_t)n * 12, tmp + j * 12, 12 * sizeof(float)); ++n; }
     }
+    free(tmp); free(kept);
     return n;
 }
 
@@ -424,6 +451,7 @@ static void splat_keys(const float* surfels, int count, const float* tinv, orc_c
                        float maxDepth, float confThreshold, int time, int maxTime, int timeDelta,
                        uint32_t drawBase, uint64_t* key)
 {
+#pragma omp parallel for schedule(dynamic, 4096)
     for (int id = 0; id < count; ++id) {
         splat_vs v;
         splat_vertex(surfels + (size_t)id * 12, tinv, cam, W, H, maxDepth, confThreshold, time, maxTime, timeDelta, &v);
@@ -437,7 +465,7 @@ static void splat_keys(const float* surfels, int count, const float* tinv, orc_c
                 float fd = (cp[2] / (2 * maxDepth)) + 0.5f;
                 if (!(fd >= 0.0f && fd < 1.0f)) continue;          /* depth clamp + GL_LESS vs cleared 1.0; NaN fails */
                 uint64_t k = ((uint64_t)fbits(fd) << 32) | (uint32_t)(drawBase + (uint32_t)id);
-                if (k < key[py * W + px]) key[py * W + px] = k;
+                atomic_min_u64(&key[py * W + px], k);
             }
     }
 }
@@ -454,6 +482,7 @@ void orc_combined_predict(const float* surfels, int count, const float* pose, or
     uint64_t* key = (uint64_t*)malloc(P * sizeof(uint64_t));
     for (size_t i = 0; i < P; ++i) key[i] = ~0ull;
     splat_keys(surfels, count, tinv, cam, W, H, maxDepth, confThreshold, time, maxTime, timeDelta, 0, key);
+#pragma omp parallel for schedule(static)
     for (int py = 0; py < H; ++py)
         for (int px = 0; px < W; ++px) {
             size_t i = (size_t)py * W + px;
