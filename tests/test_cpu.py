@@ -317,3 +317,27 @@ def test_entry_scripts_compile():
     for f in [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")] + glob.glob(os.path.join(root, "scripts", "*.py")) + \
             glob.glob(os.path.join(root, "maskfusion_b200", "*.py")) + glob.glob(os.path.join(root, "tests", "*.py")):
         py_compile.compile(f, doraise=True)
+
+
+def test_oracle_is_thread_count_invariant():
+    """the oracle's OpenMP sections keep the sequential semantics (order-free 64-bit min for the depth tests, one thread per
+    accumulator for the sums, ordered copy-out for the compaction): 1 thread and 5 threads must give the same bits"""
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from tests import oracle_lib as ol\n"
+        "from maskfusion_b200.synth import SynthScene\n"
+        "sc = SynthScene(160, 120, n_objects=0, seed=5)\n"
+        "p = ol.OraclePipeline(ol.default_config(160, 120, capacityGlobal=60000))\n"
+        "for t in range(4):\n"
+        "    rgb, depth, *_ = sc.render(t); p.process_frame(rgb, depth, t * 33333)\n"
+        "print(hashlib.sha1(p.surfels(0).tobytes()).hexdigest(), hashlib.sha1(p.pose(0).tobytes()).hexdigest(), hashlib.sha1(p.tex(0, 'splatVertex').tobytes()).hexdigest(), p.count(0))\n")
+    outs = []
+    for n in ("1", "5"):
+        env = dict(os.environ, OMP_NUM_THREADS=n)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stderr[-800:]
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1], outs
