@@ -425,7 +425,11 @@ def main():
     ap.add_argument("--impl", default="ours")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
-    os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 32)))      # oracle's OpenMP sections (cpu_baseline)
+    if args.impl == "reference":
+        # the CPU arm uses all host threads it can, also under torchrun (which exports OMP_NUM_THREADS=1 for its workers)
+        os.environ["OMP_NUM_THREADS"] = str(min(os.cpu_count() or 1, 32))
+    else:
+        os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 32)))  # oracle's OpenMP sections (cpu_baseline)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:
