@@ -246,3 +246,24 @@ def test_dir_reader_jpeg_colour(product_lib, tmp_path):
         assert np.array_equal(rgb, cv2.imread(os.path.join(root, "rgb", f"{i:04d}.jpg"))[:, :, ::-1])
         assert mask is None
     rd.close()
+
+
+def test_decoders_match_committed_opencv_vectors(product_lib, tmp_path):
+    """the same pin without cv2: byte streams encoded AND decoded by OpenCV, committed by tests/golden/make_loader_golden.py"""
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.api import decode_jpeg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loader_golden.npz"))
+    for k in range(int(g["njpg"])):
+        assert np.array_equal(decode_jpeg(g[f"jpg{k}"].tobytes()), g[f"jpg{k}_rgb"]), k
+    # the PNG decoder is reached through the directory reader: colour / BGRA colour + 16-bit depth + 8-bit mask
+    for ci, cname in enumerate(("png_rgb", "png_rgba")):
+        root = tmp_path / f"set{ci}"
+        for sub, name in (("rgb", cname), ("depth", "png_d16"), ("mask", "png_m8")):
+            os.makedirs(root / sub, exist_ok=True)
+            (root / sub / "0000.png").write_bytes(g[name].tobytes())
+        rd = mfb.ImageLogReader(str(root / "rgb"), str(root / "depth"), str(root / "mask"))
+        rgb, depth, ts, mask, cls, rois = rd.getNext()
+        assert np.array_equal(rgb, g[cname + "_dec"])
+        assert np.array_equal(depth, np.float32(0.001) * g["png_d16_dec"].astype(np.float32))
+        assert np.array_equal(mask, g["png_m8_dec"])
+        rd.close()
