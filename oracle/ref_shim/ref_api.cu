@@ -80,6 +80,33 @@ int ref_icp_step(const float* Rcurr9, const float* tcurr3, const float* vmap_cur
     return (int)cudaGetLastError();
 }
 
+// The reference's own calling pattern for the ICP term (RGBDOdometry.cpp:403-430): one icpStep per Gauss-Newton iteration, each with its
+// two launches, cudaDeviceSynchronize and 116-byte D2H inside (reduce.cu:446-525).  `iters` calls on resident maps, timed with CUDA events:
+// the "reference's own CUDA kernels on this GPU" baseline for the tracker.  Returns ms per call, < 0 on error.
+float ref_icp_step_time_ms(const float* Rcurr9, const float* tcurr3, const float* vmap_curr, const float* nmap_curr, const float* Rprev_inv9,
+                           const float* tprev3, float fx, float fy, float cx, float cy, const float* vmap_g, const float* nmap_g, float distThres,
+                           float angleThres, int W, int H, int threads, int blocks, int iters)
+{
+    DeviceArray2D<float> vc, nc, vg, ng;
+    vc.upload(vmap_curr, W * sizeof(float), H * 3, W); nc.upload(nmap_curr, W * sizeof(float), H * 3, W);
+    vg.upload(vmap_g, W * sizeof(float), H * 3, W); ng.upload(nmap_g, W * sizeof(float), H * 3, W);
+    DeviceArray<JtJJtrSE3> sum, out; sum.create(MAX_THREADS); out.create(1);
+    DeviceArray2D<unsigned char> mask; mask.create(H, W);
+    float A36[36], b6[6], res2[2];
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int w = 0; w < 3; ++w)
+        icpStep(toMat(Rcurr9), make_float3(tcurr3[0], tcurr3[1], tcurr3[2]), vc, nc, toMat(Rprev_inv9), make_float3(tprev3[0], tprev3[1], tprev3[2]),
+                CameraModel(fx, fy, cx, cy), vg, ng, distThres, angleThres, sum, out, A36, b6, res2, threads, blocks, 0, mask, 0);
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i)
+        icpStep(toMat(Rcurr9), make_float3(tcurr3[0], tcurr3[1], tcurr3[2]), vc, nc, toMat(Rprev_inv9), make_float3(tprev3[0], tprev3[1], tprev3[2]),
+                CameraModel(fx, fy, cx, cy), vg, ng, distThres, angleThres, sum, out, A36, b6, res2, threads, blocks, 0, mask, 0);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return cudaGetLastError() == cudaSuccess ? ms / (float)iters : -1.f;
+}
+
 int ref_sobel(const unsigned char* img, int W, int H, short* dx, short* dy)
 {
     DeviceArray2D<unsigned char> s; DeviceArray2D<short> gx, gy;
