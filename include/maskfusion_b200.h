@@ -180,6 +180,13 @@ void mf_dir_close(mf_dir* r);
  * ("seconds x y z qx qy qz qw", fixed notation, 6 decimals); returns the number of files written. */
 int mf_export_poses(mf_context* ctx, const char* export_dir);
 
+/* Mask R-CNN post-processing (Core/Segmentation/MaskRCNN/helpers.py:70-98 generate_id_image): detections (masks HxWxN u8, N fastest;
+ * scores; class ids; rois N x 4) -> id image HxW (ids 1..n in export order, later detections overwrite earlier ones), exported class ids
+ * and rois.  class_filter / special_assignments may be NULL with count 0.  Returns the number of exported detections. */
+int mf_generate_id_image(const uint8_t* masks, int H, int W, int N, const float* scores, const int32_t* class_ids, const int32_t* rois,
+                         double min_score, const int32_t* class_filter, int n_filter, const int32_t* special_assignments, int n_special,
+                         uint8_t* id_image, int32_t* exported_class_ids, int32_t* exported_rois);
+
 /* baseline JPEG -> 8-bit RGB exactly as libjpeg's default decode path produces it (islow IDCT, fancy upsampling; mf_jpeg.cu).
  * out == NULL: only the size.  Used by both loaders; exported for the decoder's own parity test. */
 int mf_decode_jpeg(const uint8_t* data, int size, uint8_t* out, int capacity, int* width, int* height);

@@ -50,7 +50,7 @@ EXPORTS = [
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
     "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write", "mf_dir_open", "mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks", "mf_dir_set_max_masks", "mf_dir_size",
-    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_export_poses", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
+    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_export_poses", "mf_generate_id_image", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
     "mf_shard_configure", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
@@ -427,6 +427,25 @@ class KlgLogReader:
         if self.k:
             self.L.mf_klg_close(self.k)
             self.k = None
+
+
+def generate_id_image(result: dict, min_score: float, class_filter=(), special_assignments=()):
+    """reference: generate_id_image(result, min_score, class_filter, special_assignments), MaskRCNN/helpers.py:70-98.
+    result = {'masks': HxWxN uint8, 'scores': N, 'class_ids': N, 'rois': Nx4} -> (id_image HxW uint8, class ids, rois)"""
+    L = load_library()
+    masks = np.ascontiguousarray(result["masks"], np.uint8)
+    H, W, N = masks.shape
+    scores = np.ascontiguousarray(result["scores"], np.float32); cls = np.ascontiguousarray(result["class_ids"], np.int32)
+    rois = np.ascontiguousarray(result["rois"], np.int32).reshape(N, 4)
+    cf = np.ascontiguousarray(list(class_filter), np.int32); sa = np.ascontiguousarray(list(special_assignments), np.int32)
+    img = np.zeros((H, W), np.uint8); ec = np.zeros(max(N, 1), np.int32); er = np.zeros((max(N, 1), 4), np.int32)
+    L.mf_generate_id_image.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.mf_generate_id_image(_p(masks), H, W, N, _p(scores), _p(cls), _p(rois), float(min_score), _p(cf) if cf.size else None, int(cf.size),
+                               _p(sa) if sa.size else None, int(sa.size), _p(img), _p(ec), _p(er))
+    if n < 0:
+        raise MFError(L.mf_last_error().decode())
+    return img, ec[:n].tolist(), er[:n].tolist()
 
 
 def decode_jpeg(buf: bytes) -> np.ndarray:

@@ -312,3 +312,40 @@ extern "C" int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* m
     r->currentFrame++;
     return gotMask;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Mask R-CNN post-processing: detections -> id image   <- generate_id_image, Core/Segmentation/MaskRCNN/helpers.py:70-98
+// (called by MaskRCNN.py.in:105-111 after model.detect; the id image, class list and boxes are what MaskRCNN.cpp:83-151 reads back).
+// masks: H x W x N uint8 (the network's layout, N fastest), scores / class_ids / rois (N x 4, y1 x1 y2 x2) per detection.
+// Detections are written in order: a later detection overwrites an earlier one where they overlap; ids are 1..n in export order
+// unless `special_assignments` maps the class (a list indexed BY CLASS ID, used when the class id occurs IN the list, helpers.py:91-92).
+// Returns the number of exported detections, < 0 on error.  Pinned against the reference's own Python function (tests/test_cpu_loader.py).
+extern "C" int mf_generate_id_image(const uint8_t* masks, int H, int W, int N, const float* scores, const int32_t* class_ids, const int32_t* rois,
+                                    double min_score, const int32_t* class_filter, int n_filter, const int32_t* special_assignments, int n_special,
+                                    uint8_t* id_image, int32_t* exported_class_ids, int32_t* exported_rois)
+{
+    if (N > 256) { mf_set_error("Too many masks in image."); return -1; }                 // helpers.py:78-79
+    if (!id_image || (N > 0 && (!masks || !scores || !class_ids || !rois))) { mf_set_error("generate_id_image: null argument"); return -2; }
+    const size_t P = (size_t)H * W;
+    memset(id_image, 0, P);
+    int n = 0;
+    for (int m = 0; m < N; ++m) {
+        const int cid = class_ids[m];
+        bool pass = n_filter == 0;
+        for (int k = 0; k < n_filter && !pass; ++k) pass = class_filter[k] == cid;
+        if (!pass || !((double)scores[m] >= min_score)) continue;      // the float32 score against a double, as NumPy 1.x (the reference's TF-1.8-era environment) compares them
+        int val = n + 1;
+        bool special = false;
+        for (int k = 0; k < n_special && !special; ++k) special = special_assignments[k] == cid;   // "class_id in special_assignments"
+        if (special) {
+            if (cid < 0 || cid >= n_special) { mf_set_error("generate_id_image: special_assignments[class_id] out of range"); return -3; }   // Python: IndexError
+            val = special_assignments[cid];
+        }
+        const uint8_t v = (uint8_t)val;                                                 // numpy assignment into a uint8 image wraps
+        for (size_t p = 0; p < P; ++p) if (masks[p * N + m] == 1) id_image[p] = v;
+        if (exported_class_ids) exported_class_ids[n] = cid;
+        if (exported_rois) for (int k = 0; k < 4; ++k) exported_rois[n * 4 + k] = rois[m * 4 + k];
+        ++n;
+    }
+    return n;
+}

@@ -267,3 +267,53 @@ def test_decoders_match_committed_opencv_vectors(product_lib, tmp_path):
         assert np.array_equal(depth, np.float32(0.001) * g["png_d16_dec"].astype(np.float32))
         assert np.array_equal(mask, g["png_m8_dec"])
         rd.close()
+
+
+def test_generate_id_image_matches_reference_python(product_lib):
+    """Mask R-CNN post-processing (MaskRCNN/helpers.py:70-98) against vectors produced by importing the reference's own function
+    (tests/golden/make_idimage_golden.py): score threshold, class filter,
+    special assignments, overwrite order, nothing exported"""
+    from maskfusion_b200.api import generate_id_image
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "idimage_golden.npz"))
+    for k in range(int(g["ncases"])):
+        r = {"masks": g[f"c{k}_masks"], "scores": g[f"c{k}_scores"], "class_ids": g[f"c{k}_class_ids"], "rois": g[f"c{k}_rois"]}
+        img, cls, rois = generate_id_image(r, float(g[f"c{k}_min_score"]), g[f"c{k}_filter"].tolist(), g[f"c{k}_special"].tolist())
+        assert np.array_equal(img, g[f"c{k}_img"]), k
+        assert cls == g[f"c{k}_out_cls"].tolist(), k
+        assert np.array_equal(np.array(rois, np.int32).reshape(-1, 4), g[f"c{k}_out_rois"]), k
+    if os.path.isdir("/root/reference/Core/Segmentation/MaskRCNN"):            # live, when the reference tree is present
+        import sys
+        sys.path.insert(0, "/root/reference/Core/Segmentation/MaskRCNN")
+        import helpers
+        rng = np.random.default_rng(99)
+        for _ in range(20):
+            N = int(rng.integers(0, 9)); H, W = 30, 40
+            r = {"masks": (rng.random((H, W, N)) < 0.2), "scores": rng.uniform(0, 1, N).astype(np.float32),
+                 "class_ids": rng.integers(1, 5, N).astype(np.int32), "rois": rng.integers(0, 30, (N, 4)).astype(np.int32)}
+            cf = [1, 3] if rng.random() < 0.5 else []
+            ms = float(rng.uniform(0, 1))
+            a = helpers.generate_id_image(dict(r), ms, cf)
+            b = generate_id_image({**r, "masks": r["masks"].astype(np.uint8)}, ms, cf)
+            assert np.array_equal(a[0], b[0]) and a[1] == b[1] and [list(map(int, x)) for x in a[2]] == b[2]
+
+
+def test_dir_reader_reads_what_the_reference_writes(product_lib, tmp_path):
+    """the mask image + description file written by the reference's save_id_image (MaskRCNN/helpers.py:101-113, the -maskdir
+    data produced by offline_runner.py) come back through the directory reader as the same id image, class ids and boxes"""
+    import maskfusion_b200 as mfb
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "idimage_golden.npz"))
+    H, W = g["saved_img"].shape
+    for sub in ("rgb", "depth", "mask"):
+        os.makedirs(tmp_path / sub)
+    write_png(str(tmp_path / "rgb" / "0000.png"), np.zeros((H, W, 3), np.uint8))
+    write_png(str(tmp_path / "depth" / "0000.png"), np.zeros((H, W), np.uint16))
+    (tmp_path / "mask" / "0000.png").write_bytes(g["saved_png"].tobytes())
+    (tmp_path / "mask" / "0000.txt").write_bytes(g["saved_txt"].tobytes())
+    rd = mfb.ImageLogReader(str(tmp_path / "rgb"), str(tmp_path / "depth"), str(tmp_path / "mask"))
+    rgb, depth, ts, mask, cls, rois = rd.getNext()
+    assert np.array_equal(mask, g["saved_img"])
+    assert cls.tolist() == [0] + g["saved_cls"].tolist()
+    # the file holds y1 x1 y2 x2 (helpers.py:111-113); the reader builds cv::Rect(x1, y1, x2 - x1, y2 - y1) (ImageLogReader.cpp:314-317)
+    y1, x1, y2, x2 = g["saved_rois"].T
+    assert np.array_equal(rois, np.stack([x1, y1, x2 - x1, y2 - y1], 1))
+    rd.close()
