@@ -180,6 +180,10 @@ void mf_dir_close(mf_dir* r);
  * ("seconds x y z qx qy qz qw", fixed notation, 6 decimals); returns the number of files written. */
 int mf_export_poses(mf_context* ctx, const char* export_dir);
 
+/* PLY export of one model's surfels as MaskFusion::savePly writes it (Core/MaskFusion.cpp:733-848): vertices with conf > threshold,
+ * binary little endian, x y z | r g b | -nx -ny -nz | radius.  surfels = n x 12 floats as mf_download_surfels returns them. */
+int mf_write_ply(const char* path, const float* surfels, int n, float conf_threshold);
+
 /* Mask R-CNN post-processing (Core/Segmentation/MaskRCNN/helpers.py:70-98 generate_id_image): detections (masks HxWxN u8, N fastest;
  * scores; class ids; rois N x 4) -> id image HxW (ids 1..n in export order, later detections overwrite earlier ones), exported class ids
  * and rois.  class_filter / special_assignments may be NULL with count 0.  Returns the number of exported detections. */

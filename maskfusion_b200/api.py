@@ -50,7 +50,7 @@ EXPORTS = [
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
     "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write", "mf_dir_open", "mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks", "mf_dir_set_max_masks", "mf_dir_size",
-    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_export_poses", "mf_generate_id_image", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
+    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_export_poses", "mf_generate_id_image", "mf_write_ply", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
     "mf_shard_configure", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
@@ -427,6 +427,17 @@ class KlgLogReader:
         if self.k:
             self.L.mf_klg_close(self.k)
             self.k = None
+
+
+def write_ply(path: str, surfels: np.ndarray, conf_threshold: float) -> int:
+    """one model's cloud as MaskFusion::savePly writes it (MaskFusion.cpp:733-848); surfels = Model.downloadMap()"""
+    L = load_library()
+    a = np.ascontiguousarray(surfels, np.float32).reshape(-1, 12)
+    L.mf_write_ply.argtypes = [C.c_char_p, C.c_void_p, C.c_int, C.c_float]
+    n = L.mf_write_ply(path.encode(), _p(a) if a.size else None, int(a.shape[0]), float(conf_threshold))
+    if n < 0:
+        raise MFError(L.mf_last_error().decode())
+    return n
 
 
 def generate_id_image(result: dict, min_score: float, class_filter=(), special_assignments=()):

@@ -349,3 +349,32 @@ extern "C" int mf_generate_id_image(const uint8_t* masks, int H, int W, int N, c
     }
     return n;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// PLY export of one model   <- the lambda in MaskFusion::savePly, Core/MaskFusion.cpp:733-848
+// surfels: n x 12 floats in the reference's layout (Model.h:190-192: position|conf, colour|-|initTime|lastTime, normal|radius), as
+// mf_download_surfels returns them.  Vertices with conf > threshold are written as x y z (float) r g b (uchar, from the packed colour)
+// nx ny nz (float, NEGATED as the reference does) radius (float), binary little endian.  Returns the number of vertices written.
+extern "C" int mf_write_ply(const char* path, const float* surfels, int n, float conf_threshold)
+{
+    if (!path || (n > 0 && !surfels) || n < 0) { mf_set_error("write_ply: bad arguments"); return -1; }
+    int valid = 0;
+    for (int i = 0; i < n; ++i) if (surfels[(size_t)i * 12 + 3] > conf_threshold) ++valid;      // SurfelMap::countValid
+    FILE* fp = fopen(path, "wb");
+    if (!fp) { mf_set_error(std::string("cannot write ") + path); return -2; }
+    fprintf(fp, "ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z"
+                "\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nproperty float nx\nproperty float ny\nproperty float nz"
+                "\nproperty float radius\nend_header\n", valid);
+    for (int i = 0; i < n; ++i) {
+        const float* s = surfels + (size_t)i * 12;
+        if (!(s[3] > conf_threshold)) continue;
+        fwrite(s, sizeof(float), 3, fp);
+        const int c = (int)s[4];
+        const unsigned char rgb[3] = {(unsigned char)(c >> 16 & 0xFF), (unsigned char)(c >> 8 & 0xFF), (unsigned char)(c & 0xFF)};
+        fwrite(rgb, 1, 3, fp);
+        const float nr[4] = {s[8] * -1, s[9] * -1, s[10] * -1, s[11]};
+        fwrite(nr, sizeof(float), 4, fp);
+    }
+    fclose(fp);
+    return valid;
+}

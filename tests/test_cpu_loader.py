@@ -317,3 +317,29 @@ def test_dir_reader_reads_what_the_reference_writes(product_lib, tmp_path):
     y1, x1, y2, x2 = g["saved_rois"].T
     assert np.array_equal(rois, np.stack([x1, y1, x2 - x1, y2 - y1], 1))
     rd.close()
+
+
+def test_write_ply_layout(product_lib, tmp_path):
+    """MaskFusion::savePly (MaskFusion.cpp:733-848): header, confidence gate, packed colour -> r g b, negated normals, radius"""
+    from maskfusion_b200.api import write_ply
+    rng = np.random.default_rng(5)
+    n = 50
+    s = rng.normal(size=(n, 12)).astype(np.float32)
+    s[:, 3] = rng.uniform(0, 20, n)                                   # confidence
+    col = rng.integers(0, 256, (n, 3))
+    s[:, 4] = ((col[:, 0] << 16) + (col[:, 1] << 8) + col[:, 2]).astype(np.float32)
+    s[:, 11] = rng.uniform(0.001, 0.02, n)
+    path = str(tmp_path / "cloud-0.ply")
+    kept = s[:, 3] > 10.0
+    assert write_ply(path, s, 10.0) == int(kept.sum())
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert head.decode().split("\n")[:3] == ["ply", "format binary_little_endian 1.0", f"element vertex {int(kept.sum())}"]
+    assert [l for l in head.decode().split("\n") if l.startswith("property")] == [
+        "property float x", "property float y", "property float z", "property uchar red", "property uchar green", "property uchar blue",
+        "property float nx", "property float ny", "property float nz", "property float radius"]
+    rec = np.dtype([("p", "<f4", 3), ("c", "u1", 3), ("n", "<f4", 3), ("r", "<f4")])
+    v = np.frombuffer(body, rec)
+    assert len(v) == int(kept.sum())
+    assert np.array_equal(v["p"], s[kept, 0:3]) and np.array_equal(v["c"], col[kept].astype(np.uint8))
+    assert np.array_equal(v["n"], -s[kept, 8:11]) and np.array_equal(v["r"], s[kept, 11])
