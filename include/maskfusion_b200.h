@@ -67,9 +67,18 @@ void mf_destroy(mf_context* ctx);
  * Host buffers; the H2D copies are part of the call. mask / in_pose may be NULL. */
 int mf_process_frame(mf_context* ctx, const uint8_t* rgb, const float* depth, int64_t timestamp,
                      const uint8_t* mask, const float* in_pose, float weight_multiplier, int bootstrap);
-/* Same, inputs already resident in device memory (rgb: packed 3 bytes/pixel). */
+/* Same, inputs already resident in device memory (rgb: packed 3 bytes/pixel).
+ * Lifetime / ordering of device inputs: the library copies them into its own frame set at the START of the call; on -static
+ * tracking frames that copy runs on a private pre-processing stream next to the previous frame's surfel passes, NOT behind
+ * the work queued on the context stream.  Therefore (a) the buffers must be completely written when the call is made -- or
+ * the producer's completion event is handed over with mf_set_input_event before the call; (b) work the caller enqueues on
+ * the CONTEXT stream after the call returns is ordered after the copies (the context stream waits for them), so the buffers
+ * may be overwritten from there; a caller writing them from another stream waits for mf_sync or the next call's return. */
 int mf_process_frame_device(mf_context* ctx, const void* d_rgb, const void* d_depth, int64_t timestamp,
                             const void* d_mask, const float* in_pose, float weight_multiplier, int bootstrap);
+/* cudaEvent_t that the NEXT mf_process_frame_device waits on (on whichever stream it copies from) before it reads its
+ * device inputs; consumed by that call.  NULL clears it. */
+int mf_set_input_event(mf_context* ctx, void* cuda_event);
 int mf_sync(mf_context* ctx);                       /* wait for everything enqueued so far */
 int mf_tick(mf_context* ctx);                       /* MaskFusion::getTick */
 int64_t mf_kernel_launches(mf_context* ctx);        /* kernels launched since creation */
@@ -105,6 +114,9 @@ int mf_download_fill_in(mf_context* ctx, int i, uint8_t* image4, float* vertex4,
 int mf_download_association(mf_context* ctx, int i, uint8_t* update_id, uint32_t* best, float* meas12); /* x-major pixel order, Model.cpp:179-183 */
 int mf_download_track_stats(mf_context* ctx, int i, double* A36, double* b6, float* err_count6);   /* RGBDOdometry::lastA/lastb, lastICPError,... */
 int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binary);                           /* MfSegmentation floatEdgeMap / binary edge map */
+/* test hook: morphological close of a host image (W x H of the context, in place). ellipse != 0: cv::morphologyEx(MORPH_CLOSE, MORPH_ELLIPSE) of the
+ * mask-id image (MfSegmentation.cpp:424-426); ellipse == 0: the binary edge-map close (segmentation.cu:217-255,334-354), `inverted` = 255 - result. */
+int mf_morph_close(mf_context* ctx, uint8_t* image, int radius, int iterations, int ellipse, uint8_t* inverted);
 
 /* ---- stand-alone kernels exposed for parity tests (device work, host buffers) ---- */
 /* ---- multi-model inputs / outputs ---- */

@@ -42,13 +42,13 @@ class Config(C.Structure):
 
 EXPORTS = [
     "mf_last_error", "mf_abi_version", "mf_config_defaults", "mf_create", "mf_destroy", "mf_process_frame",
-    "mf_process_frame_device", "mf_sync", "mf_tick", "mf_kernel_launches", "mf_model_count", "mf_model_id", "mf_get_pose",
+    "mf_process_frame_device", "mf_set_input_event", "mf_sync", "mf_tick", "mf_kernel_launches", "mf_model_count", "mf_model_id", "mf_get_pose",
     "mf_set_pose", "mf_model_surfel_count", "mf_model_set_conf_threshold", "mf_download_surfels", "mf_upload_surfels",
     "mf_pose_log_size", "mf_get_pose_log", "mf_set_frame", "mf_model_perform_tracking", "mf_model_predict_indices",
     "mf_model_fuse", "mf_model_clean", "mf_model_combined_predict", "mf_model_init_from_frame",
     "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
-    "mf_download_edge_map", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
+    "mf_download_edge_map", "mf_morph_close", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write", "mf_dir_open", "mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks", "mf_dir_set_max_masks", "mf_dir_size",
     "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_export_poses", "mf_generate_id_image", "mf_write_ply", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
@@ -77,6 +77,7 @@ def load_library():
     L.mf_config_defaults.argtypes = [C.POINTER(Config), C.c_int, C.c_int]
     L.mf_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
     L.mf_process_frame_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_float, C.c_int]
+    L.mf_set_input_event.argtypes = [C.c_void_p, C.c_void_p]
     L.mf_kernel_launches.restype = C.c_int64
     for name in ("mf_sync", "mf_tick", "mf_kernel_launches", "mf_model_count"):
         getattr(L, name).argtypes = [C.c_void_p]
@@ -104,6 +105,7 @@ def load_library():
     L.mf_download_association.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_track_stats.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_edge_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_morph_close.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.mf_set_frame_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.mf_download_segmentation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.mf_model_class_id.argtypes = [C.c_void_p, C.c_int]
@@ -398,6 +400,15 @@ class MaskFusion:
         e = np.zeros((self.H, self.W), np.float32); b = np.zeros((self.H, self.W), np.uint8)
         self._ck(self.L.mf_download_edge_map(self.h, _p(e), _p(b)))
         return e, b
+
+    def morphClose(self, image, radius: int, iterations: int, ellipse: bool = True):
+        """test hook: GPU close of a host image; ellipse=True: the mask-id close (MfSegmentation.cpp:424-426), False: the binary
+        edge-map close (segmentation.cu:217-255) -> (closed, inverted)"""
+        a = np.ascontiguousarray(image, np.uint8).copy()
+        assert a.shape == (self.H, self.W)
+        inv = np.zeros_like(a)
+        self._ck(self.L.mf_morph_close(self.h, _p(a), int(radius), int(iterations), int(ellipse), None if ellipse else _p(inv)))
+        return a if ellipse else (a, inv)
 
 
 class KlgLogReader:

@@ -27,7 +27,11 @@ extern "C" int mf_abi_version(void) { return MF_ABI_VERSION; }
 // every entry point first picks up a tracked pose that is still in flight (-static frames return before it has arrived)
 static int mf_finalise(mf_context* ctx)
 {
-    try { ctx->mf->finalisePending(); return 0; }
+    try {
+        // the calling thread may have another device current (several contexts per process): every entry point selects its own
+        cudaCheck(cudaSetDevice(ctx->mf->device), "cudaSetDevice");
+        ctx->mf->finalisePending(); return 0;
+    }
     catch (const CudaError& e) { g_err = e.what; return -1; }
     catch (...) { g_err = "unknown error"; return -1; }
 }
@@ -92,6 +96,7 @@ extern "C" int mf_process_frame_device(mf_context* ctx, const void* d_rgb, const
     return 0;
     MF_CATCH(-1)
 }
+extern "C" int mf_set_input_event(mf_context* ctx, void* ev) { if (!ctx || !ctx->mf) { g_err = "null context"; return -1; } ctx->mf->inputReady = (cudaEvent_t)ev; return 0; }
 extern "C" int mf_sync(mf_context* ctx) { MF_TRY MF_NEED(ctx) ctx->mf->sync(); return 0; MF_CATCH(-1) }
 extern "C" int mf_tick(mf_context* ctx) { if (!ctx || !ctx->mf) return -1; return ctx->mf->tick; }
 extern "C" int64_t mf_kernel_launches(mf_context* ctx) { if (!ctx || !ctx->mf) return -1; return ctx->mf->launches; }
@@ -325,6 +330,25 @@ extern "C" int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binar
     MF_CATCH(-1)
 }
 
+// test hook: the two morphological closes of the segmentation on a caller-given image (host, W x H of the context, in place).
+//   ellipse != 0: gray-level close with OpenCV's elliptic element (mask-id image, MfSegmentation.cpp:424-426)
+//   ellipse == 0: the binary close of the edge map (dilate_Kernel / erode_Kernel, segmentation.cu:217-255, host :334-354); `inverted` (may be
+//                 NULL) receives 255 - result like MfSegmentation.cpp:208
+extern "C" int mf_morph_close(mf_context* ctx, uint8_t* image, int radius, int iterations, int ellipse, uint8_t* inverted)
+{
+    MF_TRY MF_NEED(ctx)
+    if (!image || radius < 0 || iterations < 0) { g_err = "morph_close: bad arguments"; return -3; }
+    MaskFusion* o = ctx->mf;
+    DevBuf<uint8_t> a, b, c; a.alloc(o->P); b.alloc(o->P); c.alloc(o->P);
+    cudaCheck(cudaMemcpyAsync(a.p, image, o->P, cudaMemcpyHostToDevice, o->stream), "H2D");
+    if (ellipse) o->launches += launch_morph_close_ellipse(a, b, o->W, o->H, radius, iterations, o->stream);
+    else { launch_morph_close_invert(a, b, o->W, o->H, radius, iterations, c, o->stream); o->launches += 1 + 2 * iterations; }
+    d2h(o, image, a.p, o->P);
+    if (inverted && !ellipse) d2h(o, inverted, c.p, o->P);
+    o->sync(); return 0;
+    MF_CATCH(-1)
+}
+
 extern "C" int mf_set_frame_classes(mf_context* ctx, const int32_t* class_ids, int n)
 {
     MF_TRY MF_NEED(ctx)
@@ -433,21 +457,27 @@ struct mf_klg {
 };
 extern "C" mf_klg* mf_klg_open(const char* path, int width, int height, int flip_colors)
 {
+    if (!path) { g_err = "mf_klg_open: null path"; return nullptr; }
+    if (width <= 0 || height <= 0 || width > 16384 || height > 16384) { g_err = "mf_klg_open: width/height must be in 1..16384"; return nullptr; }
     FILE* fp = fopen(path, "rb");
     if (!fp) { g_err = std::string("Could not open log-file: ") + path; return nullptr; }
     int32_t n = 0;
     if (!fread(&n, sizeof(int32_t), 1, fp)) { fclose(fp); g_err = std::string("Could not open log-file: ") + path; return nullptr; }
-    mf_klg* k = new mf_klg;
-    k->fp = fp; k->W = width; k->H = height; k->numFrames = n; k->currentFrame = 0; k->flip = flip_colors;
-    size_t P = (size_t)width * height;
-    k->dbuf.resize(P * 2 + 1024); k->rbuf.resize(P * 3 + 1024); k->dec.resize(P * 2);
+    mf_klg* k = nullptr;
+    try {
+        k = new mf_klg;
+        k->fp = fp; k->W = width; k->H = height; k->numFrames = n; k->currentFrame = 0; k->flip = flip_colors;
+        size_t P = (size_t)width * height;
+        k->dbuf.resize(P * 2 + 1024); k->rbuf.resize(P * 3 + 1024); k->dec.resize(P * 2);
+    } catch (...) { fclose(fp); delete k; g_err = "mf_klg_open: out of memory"; return nullptr; }
     return k;
 }
 extern "C" int mf_klg_num_frames(mf_klg* k) { return k ? k->numFrames : -1; }
 extern "C" int mf_klg_has_more(mf_klg* k) { return k ? (k->currentFrame + 1 < k->numFrames) : 0; }   // KlgLogReader.cpp:113 (N11)
 extern "C" int mf_klg_get_next(mf_klg* k, uint8_t* rgb, float* depth, int64_t* timestamp)
 {
-    if (!k) { g_err = "null reader"; return -1; }
+    if (!k || !rgb || !depth) { g_err = "mf_klg_get_next: null reader or output buffer"; return -1; }
+    MF_TRY
     const size_t P = (size_t)k->W * k->H;
     int64_t ts; int32_t dsz, rsz;
     if (!fread(&ts, sizeof ts, 1, k->fp) || !fread(&dsz, sizeof dsz, 1, k->fp) || !fread(&rsz, sizeof rsz, 1, k->fp)) { g_err = "klg: truncated frame header"; return -2; }
@@ -474,10 +504,12 @@ extern "C" int mf_klg_get_next(mf_klg* k, uint8_t* rgb, float* depth, int64_t* t
     if (timestamp) *timestamp = ts;
     k->currentFrame++;
     return 0;
+    MF_CATCH(-6)
 }
 extern "C" void mf_klg_close(mf_klg* k) { if (k) { if (k->fp) fclose(k->fp); delete k; } }
 extern "C" int mf_klg_write(const char* path, int width, int height, int num_frames, const int64_t* timestamps, const uint16_t* depth_mm, const uint8_t* rgb)
 {
+    if (!path || width <= 0 || height <= 0 || num_frames < 0 || (num_frames > 0 && (!timestamps || !depth_mm || !rgb))) { g_err = "mf_klg_write: bad arguments"; return -1; }
     FILE* fp = fopen(path, "wb");
     if (!fp) { g_err = std::string("cannot write ") + path; return -1; }
     const size_t P = (size_t)width * height;

@@ -339,11 +339,15 @@ void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint
     cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     g_prof = &prof;
     prof_mark(s, onDevice ? "copy_d2d_frame" : "copy_h2d_frame");
+    if (onDevice && inputReady) { cudaCheck(cudaStreamWaitEvent(s, inputReady, 0), "cudaStreamWaitEvent"); inputReady = nullptr; }   // caller's producer
     cudaCheck(cudaMemcpyAsync(rgb3, rgbIn, (size_t)P * 3, kind, s), "rgb upload");
     cudaCheck(cudaMemcpyAsync(depthRaw, depthIn, (size_t)P * sizeof(float), kind, s), "depth upload");
     if (maskIn) cudaCheck(cudaMemcpyAsync(mask, maskIn, (size_t)P, kind, s), "mask upload");
-    // host inputs belong to the caller again when processFrame returns (the reference uploads synchronously): see frameBegin
+    // host inputs belong to the caller again when processFrame returns (the reference uploads synchronously): see processFrame.
+    // Device inputs copied on the pre-processing stream: the context stream waits for the copies, so whatever the caller queues
+    // there after this call (e.g. the producer of the next frame writing the same buffers) is ordered behind them.
     if (!onDevice) { cudaCheck(cudaEventRecord(inputsCopied, s), "cudaEventRecord"); copyPending = true; }
+    else if (s != stream) { cudaCheck(cudaEventRecord(inputsCopied, s), "cudaEventRecord"); cudaCheck(cudaStreamWaitEvent(stream, inputsCopied, 0), "cudaStreamWaitEvent"); }
     launch_unpack_rgb(rgb3, rgb, P, s);
     launch_bilateral(depthRaw, depthFilt, W, H, s);
     launches += 2;
@@ -529,7 +533,8 @@ MaskFusion::SegmentationResult MaskFusion::performSegmentation(bool allowNew)
     launch_seg_assign(lab, mapToMask, ignoreMap, P, segTmp, stream);
     launches += 3;
     if (nMasks) {
-        if (cfg.segMorphMaskIterations > 0) throw CudaError{"morphological closing of the mask image (morphMaskIterations > 0) is not built yet (GUI default 0)"};
+        // closing of the mask-id image with an elliptic element (:424-426); edgeBuf is free again at this point
+        launches += launch_morph_close_ellipse(segTmp, edgeBuf, W, H, cfg.segMorphMaskRadius, cfg.segMorphMaskIterations, stream);
         // mask -> model vote (:433-492): two small tables to the host
         if ((size_t)nModels * 256 > maskOverlap.n) maskOverlap.alloc((size_t)nModels * 256);
         maskOverlap.zero(stream);

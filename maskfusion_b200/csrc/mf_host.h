@@ -162,6 +162,7 @@ public:
     int curSet = 0;
     void selectSet(int k) { curSet = k; rgb3 = rgb3Buf[k]; rgb = rgbBuf[k]; depthRaw = depthRawBuf[k]; depthFilt = depthFiltBuf[k]; }
     cudaStream_t preStream = nullptr; cudaEvent_t preDone = nullptr, inputsCopied = nullptr; bool preWaitPending = false, copyPending = false;
+    cudaEvent_t inputReady = nullptr;        // caller's producer event for device inputs (mf_set_input_event): waited on before the next frame's copies
     DevBuf<uint8_t> mask;
     DevBuf<float> depthPyr[3]; DevBuf<float4> vmap[3], nmap[3];
     DevBuf<uint8_t> nextImage[3]; DevBuf<short2> nextGrad[3]; DevBuf<uint8_t> rgbValid[3];

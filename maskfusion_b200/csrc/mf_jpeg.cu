@@ -21,7 +21,7 @@ namespace {
 
 struct Huff { uint8_t bits[17]; uint8_t vals[256]; int mincode[17], maxcode[18], valptr[17]; bool present = false; };
 
-struct Comp { int id, h, v, tq, td, ta; int wBlocks, hBlocks; std::vector<int16_t> coef; int dcPred; int dsW, dsH; std::vector<uint8_t> plane; int planeW, planeH; };
+struct Comp { int id = 0, h = 0, v = 0, tq = 0, td = 0, ta = 0; int inScan = 0; int wBlocks = 0, hBlocks = 0; std::vector<int16_t> coef; int dcPred = 0; int dsW = 0, dsH = 0; std::vector<uint8_t> plane; int planeW = 0, planeH = 0; };
 
 struct BitReader {
     const uint8_t* p; const uint8_t* end; uint32_t buf = 0; int cnt = 0; bool hitMarker = false;
@@ -165,6 +165,7 @@ bool decodeJPEG(const uint8_t* data, size_t size, int& W, int& H, std::vector<ui
             H = be16(seg + 1); W = be16(seg + 3);
             const int nc = seg[5];
             if (!(nc == 1 || nc == 3) || n < 6 + 3 * nc || W <= 0 || H <= 0) { err = "JPEG: unsupported number of components"; return false; }
+            if (W > 16384 || H > 16384) { err = "JPEG: image side above 16384"; return false; }
             comps.resize(nc);
             for (int c = 0; c < nc; ++c) {
                 comps[c].id = seg[6 + 3 * c]; comps[c].h = seg[7 + 3 * c] >> 4; comps[c].v = seg[7 + 3 * c] & 15; comps[c].tq = seg[8 + 3 * c];
@@ -190,14 +191,19 @@ bool decodeJPEG(const uint8_t* data, size_t size, int& W, int& H, std::vector<ui
         } else if (m == 0xDD) { if (n >= 2) restartInterval = be16(seg); }          // DRI
         else if (m == 0xDA) {                                                        // SOS: the (single) scan follows
             if (!gotSOF) { err = "JPEG: scan before frame header"; return false; }
+            if (n < 1) { err = "JPEG: empty scan header"; return false; }
             const int ns = seg[0];
             if (ns != (int)comps.size() || n < 1 + 2 * ns + 3) { err = "JPEG: non-interleaved multi-scan files are not supported"; return false; }
             for (int k = 0; k < ns; ++k) {
                 const int cid = seg[1 + 2 * k];
+                const int td = seg[2 + 2 * k] >> 4, ta = seg[2 + 2 * k] & 15;
+                if (td > 3 || ta > 3) { err = "JPEG: scan selects a Huffman table outside 0..3"; return false; }
+                // the first frame component with this id that no earlier scan entry took (duplicate ids in the SOF stay distinct)
                 bool found = false;
-                for (auto& c : comps) if (c.id == cid) { c.td = seg[2 + 2 * k] >> 4; c.ta = seg[2 + 2 * k] & 15; found = true; }
+                for (auto& c : comps) if (c.id == cid && !c.inScan) { c.td = td; c.ta = ta; c.inScan = 1; found = true; break; }
                 if (!found) { err = "JPEG: scan references an unknown component"; return false; }
             }
+            for (auto& c : comps) if (!c.inScan) { err = "JPEG: a frame component is missing from the scan"; return false; }
             pos += len;
             break;
         }
@@ -331,8 +337,9 @@ bool decodeJPEG(const uint8_t* data, size_t size, int& W, int& H, std::vector<ui
 extern void mf_set_error(const std::string& e);
 extern "C" int mf_decode_jpeg(const uint8_t* data, int size, uint8_t* out, int capacity, int* width, int* height)
 {
-    int W = 0, H = 0; std::vector<uint8_t> rgb; std::string err;
     if (!data || size <= 0) { mf_set_error("decode_jpeg: empty input"); return -1; }
+    try {
+    int W = 0, H = 0; std::vector<uint8_t> rgb; std::string err;
     if (!mfb::decodeJPEG(data, (size_t)size, W, H, rgb, err)) { mf_set_error(err); return -2; }
     if (width) *width = W;
     if (height) *height = H;
@@ -341,4 +348,6 @@ extern "C" int mf_decode_jpeg(const uint8_t* data, int size, uint8_t* out, int c
         memcpy(out, rgb.data(), rgb.size());
     }
     return 0;
+    } catch (const std::exception& e) { mf_set_error(std::string("decode_jpeg: ") + e.what()); return -4; }
+    catch (...) { mf_set_error("decode_jpeg: unknown error"); return -4; }
 }

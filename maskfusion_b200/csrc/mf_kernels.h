@@ -171,6 +171,7 @@ void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vma
 
 // ---- mf_seg.cu ----
 void launch_geometric_edges(const float4* vmap, const float4* nmap, int W, int H, float wD, float wC, float thr, float* edge, uint8_t* binary, cudaStream_t s);
+int launch_morph_close_ellipse(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, cudaStream_t s);   // MfSegmentation.cpp:424-426; returns the number of launches
 void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, uint8_t* inverted, cudaStream_t s);
 
 }  // namespace mfb

@@ -22,6 +22,7 @@
 #include <vector>
 
 extern void mf_set_error(const std::string& e);          // mf_capi.cu (thread-local message behind mf_last_error)
+#define MF_MAX_IMAGE_SIDE 16384          // decoders refuse larger headers before allocating (a crafted IHDR must not throw across the C ABI)
 namespace mfb { bool decodeJPEG(const uint8_t* data, size_t size, int& W, int& H, std::vector<uint8_t>& rgb, std::string& err); }   // mf_jpeg.cu
 
 namespace {
@@ -64,6 +65,7 @@ bool decodePNG(const std::vector<uint8_t>& f, Image& im, std::string& err)
         pos += 12 + (size_t)len;
     }
     if (!gotHdr || W <= 0 || H <= 0) { err = "PNG without a valid IHDR"; return false; }
+    if (W > MF_MAX_IMAGE_SIDE || H > MF_MAX_IMAGE_SIDE) { err = "PNG: image side above 16384"; return false; }
     if (interlace) { err = "interlaced PNG is not supported"; return false; }
     int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
     if (!ch || !(bits == 8 || bits == 16 || ((ctype == 0 || ctype == 3) && (bits == 1 || bits == 2 || bits == 4)))) { err = "unsupported PNG colour type / bit depth"; return false; }
@@ -129,12 +131,13 @@ bool decodePNM(const std::vector<uint8_t>& f, Image& im, std::string& err)
         if (f[pos] == '#') { while (pos < f.size() && f[pos] != '\n') ++pos; continue; }
         if (isspace(f[pos])) { ++pos; continue; }
         long v = 0; bool any = false;
-        while (pos < f.size() && isdigit(f[pos])) { v = v * 10 + (f[pos] - '0'); ++pos; any = true; }
+        while (pos < f.size() && isdigit(f[pos])) { v = v * 10 + (f[pos] - '0'); if (v > 65535) v = 65536; ++pos; any = true; }
         if (!any) { err = "bad PNM header"; return false; }
         vals[got++] = v;
     }
     if (got < 3 || pos >= f.size()) { err = "bad PNM header"; return false; }
     ++pos;   // single whitespace after maxval
+    if (vals[0] > MF_MAX_IMAGE_SIDE || vals[1] > MF_MAX_IMAGE_SIDE || vals[2] < 1 || vals[2] > 65535) { err = "PNM: image side above 16384 or bad maxval"; return false; }
     im.w = (int)vals[0]; im.h = (int)vals[1]; im.channels = f[1] == '6' ? 3 : 1; im.bits = vals[2] > 255 ? 16 : 8;
     const size_t n = (size_t)im.w * im.h * im.channels * (im.bits / 8);
     if (im.w <= 0 || im.h <= 0 || pos + n > f.size()) { err = "truncated PNM data"; return false; }
@@ -208,7 +211,10 @@ static int countFiles(const std::string& dir, const std::string& prefix, const s
 extern "C" mf_dir* mf_dir_open(const char* color_dir, const char* depth_dir, const char* mask_dir, int index_width, const char* color_prefix,
                                const char* depth_prefix, const char* mask_prefix)
 {
-    mf_dir* r = new mf_dir;
+    if (!color_dir) { mf_set_error("mf_dir_open: null colour directory"); return nullptr; }
+    mf_dir* r = nullptr;
+    try {
+    r = new mf_dir;
     r->colorDir = withSlash(color_dir); r->depthDir = withSlash(depth_dir && *depth_dir ? depth_dir : color_dir);
     r->maskDir = withSlash(mask_dir && *mask_dir ? mask_dir : "");
     r->colorPre = color_prefix ? color_prefix : ""; r->depthPre = depth_prefix ? depth_prefix : ""; r->maskPre = mask_prefix ? mask_prefix : "";
@@ -235,6 +241,8 @@ extern "C" mf_dir* mf_dir_open(const char* color_dir, const char* depth_dir, con
     if (!loadImage(r->colorDir + r->colorPre + indexString(r->indexW, r->startIndex) + r->colorExt, r->colorExt, im, err)) { mf_set_error(err); delete r; return nullptr; }
     r->W = im.w; r->H = im.h;
     return r;
+    } catch (const std::exception& e) { mf_set_error(std::string("mf_dir_open: ") + e.what()); delete r; return nullptr; }
+    catch (...) { mf_set_error("mf_dir_open: unknown error"); delete r; return nullptr; }
 }
 extern "C" void mf_dir_close(mf_dir* r) { delete r; }
 extern "C" int mf_dir_num_frames(mf_dir* r) { return r ? r->numFrames : -1; }
@@ -250,6 +258,8 @@ extern "C" int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* m
                                int64_t* timestamp)
 {
     if (!r) { mf_set_error("null reader"); return -1; }
+    if (!rgb || !depth) { mf_set_error("mf_dir_get_next: null output buffer"); return -1; }
+    try {
     if (r->currentFrame + 1 >= r->numFrames) { mf_set_error("no more frames"); return -2; }
     const size_t index = (size_t)(r->currentFrame + 1);
     const std::string idx = indexString(r->indexW, index + r->startIndex);
@@ -311,6 +321,8 @@ extern "C" int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* m
     if (timestamp) *timestamp = (int64_t)((float)index * 1000.0f / r->rateHz);        // :283 (float product truncated into the int64 field)
     r->currentFrame++;
     return gotMask;
+    } catch (const std::exception& e) { mf_set_error(std::string("mf_dir_get_next: ") + e.what()); return -9; }
+    catch (...) { mf_set_error("mf_dir_get_next: unknown error"); return -9; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------------

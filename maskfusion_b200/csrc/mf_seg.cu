@@ -6,6 +6,8 @@
 // the reference feeds it: MfSegmentation.cpp:149-151, REUSE_FILTERED_MAPS).
 #include "mf_common.cuh"
 #include "mf_kernels.h"
+#include "mf_host.h"
+#include <math.h>
 
 namespace mfb {
 
@@ -58,6 +60,49 @@ __global__ void k_invert(const uint8_t* __restrict__ in, int n, uint8_t* __restr
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (uint8_t)(255 - in[i]);
+}
+
+// gray-level dilate / erode with OpenCV's elliptic structuring element (cv::getStructuringElement(MORPH_ELLIPSE, (2r+1)^2)):
+// row dy of the element spans columns -hw[dy+r] .. +hw[dy+r]; taps outside the image are ignored (morphologyDefaultBorderValue).
+// One step of cv::morphologyEx(MORPH_CLOSE) on the mask-id image (MfSegmentation.cpp:424-426).
+struct EllipseRows { int r; int hw[33]; };
+__global__ void k_morph_ellipse(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, int H, EllipseRows e, int dilate)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H) return;
+    int best = dilate ? 0 : 255;
+    for (int dy = -e.r; dy <= e.r; ++dy) {
+        const int yy = y + dy;
+        if (yy < 0 || yy >= H) continue;
+        const int hw = e.hw[dy + e.r];
+        const int x1 = max(x - hw, 0), x2 = min(x + hw, W - 1);
+        for (int xx = x1; xx <= x2; ++xx) {
+            const int v = in[yy * W + xx];
+            best = dilate ? max(best, v) : min(best, v);
+        }
+    }
+    out[y * W + x] = (uint8_t)best;
+}
+// closes `data` in place (buf: scratch of the same size): dilate x iterations, then erode x iterations
+int launch_morph_close_ellipse(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, cudaStream_t s)
+{
+    if (iterations <= 0) return 0;
+    if (radius < 0 || radius > 16) throw CudaError{"morphMaskRadius must be in 0..16"};
+    EllipseRows e; e.r = radius;
+    const double inv_r2 = radius ? 1.0 / ((double)radius * radius) : 0.0;
+    for (int i = 0; i < 2 * radius + 1; ++i) {
+        const int dy = i - radius;
+        e.hw[i] = (int)lrint(radius * sqrt((double)(radius * radius - dy * dy) * inv_r2));     // cv::getStructuringElement, MORPH_ELLIPSE
+    }
+    dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
+    uint8_t* src = data; uint8_t* dst = buf;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < iterations; ++i) {
+            prof_mark(s, "k_morph_ellipse"); k_morph_ellipse<<<g, b, 0, s>>>(src, dst, W, H, e, pass == 0);
+            uint8_t* t = src; src = dst; dst = t;
+        }
+    // 2 * iterations launches: the result is back in `data`
+    return 2 * iterations;
 }
 
 void launch_geometric_edges(const float4* vmap, const float4* nmap, int W, int H, float wD, float wC, float thr, float* edge, uint8_t* binary, cudaStream_t s)

@@ -1024,13 +1024,24 @@ static int trackBlocks(int N, int numSMs)
 int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
                     bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s)
 {
-    static int coResident = -1;                 // CTAs of k_track_persistent the device can hold at once
-    if (coResident < 0) {
+    // per-device launch limits (several contexts on different GPUs may live in one process): occupancy and the opt-in
+    // dynamic shared memory attribute are properties of (function, device)
+    static int coResidentDev[64]; static size_t dynMaxDev[64]; static bool devInit[64];
+    int dev = 0; cudaCheck(cudaGetDevice(&dev), "cudaGetDevice");
+    if (dev < 0 || dev >= 64) throw CudaError{"device ordinal above 63"};
+    if (!devInit[dev]) {
         int perSM = 0;
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_track_persistent, PT_THREADS, 0);
         if (e != cudaSuccess || perSM < 1) throw CudaError{std::string("k_track_persistent does not fit on an SM: ") + cudaGetErrorString(e)};
-        coResident = perSM * numSMs;
+        coResidentDev[dev] = perSM * numSMs;
+        cudaFuncAttributes fa; cudaCheck(cudaFuncGetAttributes(&fa, k_track_persistent), "cudaFuncGetAttributes");
+        int optin = 0; cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        dynMaxDev[dev] = (size_t)optin > fa.sharedSizeBytes + 2048 ? (size_t)optin - fa.sharedSizeBytes - 2048 : 0;
+        cudaCheck(cudaFuncSetAttribute(k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMaxDev[dev]), "cudaFuncSetAttribute");
+        devInit[dev] = true;
     }
+    const int coResident = coResidentDev[dev];
+    const size_t dynMax = dynMaxDev[dev];
     TrackParams tp;
     tp.W = W; tp.H = H; tp.cam = cam;
     tp.icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
@@ -1048,13 +1059,6 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     // photometric correspondences stay in shared memory when the per-CTA pixel share fits (8 B per pixel slot)
     const int rounds0 = (W * H + G * PT_THREADS - 1) / (G * PT_THREADS);
     size_t dyn = (size_t)rounds0 * PT_THREADS * sizeof(int2);
-    static size_t dynMax = 0;
-    if (dynMax == 0) {
-        cudaFuncAttributes fa; cudaCheck(cudaFuncGetAttributes(&fa, k_track_persistent), "cudaFuncGetAttributes");
-        int optin = 0, dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-        dynMax = (size_t)optin > fa.sharedSizeBytes + 2048 ? (size_t)optin - fa.sharedSizeBytes - 2048 : 0;
-        cudaCheck(cudaFuncSetAttribute(k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMax), "cudaFuncSetAttribute");
-    }
     if (tp.rgb && dyn <= dynMax) tp.corrSlots = rounds0 * PT_THREADS; else { tp.corrSlots = 0; dyn = 0; }
     cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
     prof_mark(s, "k_track_persistent");

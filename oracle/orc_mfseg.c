@@ -16,6 +16,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* BASELINE configs[0] / SURVEY 8(d)(i) times this file on ONE core (the reference is single-threaded here) and with "a
+ * straightforward OpenMP split" over the host cores: every per-pixel sweep below is an `omp parallel for` that is only active
+ * when orc_mfseg_set_threads(n > 1) was called; integer histograms use atomic adds (order-free), the Jacobi sweeps read the
+ * previous labels only, the two-pass connected-component labelling stays sequential.  Results are identical for any n. */
+static int g_threads = 1;
+void orc_mfseg_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+#define PAR _Pragma("omp parallel for schedule(static) num_threads(g_threads) if (g_threads > 1)")
+
 static int uf_find(int* p, int x) { while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; } return x; }
 
 /* 4-connected components of the non-zero pixels; labels[] gets 0 for background, 1..n-1 otherwise;
@@ -86,6 +94,7 @@ static void ellipse_element(int r, uint8_t* k)
 static void morph_gray(const uint8_t* in, uint8_t* out, int W, int H, int r, const uint8_t* k, int dilate)
 {
     int n = 2 * r + 1;
+    PAR
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) {
             int best = dilate ? 0 : 255;
@@ -138,11 +147,13 @@ void orc_mfseg_cpu(orc_mfseg_state* st, const orc_mfseg_in* in, orc_mfseg_out* o
 
     /* :221-235 ignore map */
     if (nMasks) {
+        PAR
         for (size_t i = 0; i < total; ++i) {
             if (in->classIDs[in->mask[i]] == st->personClassID) { st->semanticIgnoreMap[i] = 255; buf[i] = 0; }
             else st->semanticIgnoreMap[i] = 0;
         }
     } else {
+        PAR
         for (size_t i = 0; i < total; ++i) if (st->semanticIgnoreMap[i]) buf[i] = 0;
     }
     /* :238-239 */
@@ -157,6 +168,7 @@ void orc_mfseg_cpu(orc_mfseg_state* st, const orc_mfseg_in* in, orc_mfseg_out* o
         static const int oy[8] = { -1, -1, -1, 0, 0, 1, 1, 1 }, ox[8] = { -1, 0, 1, -1, 1, -1, 0, 1 };
         for (int it = 0; it < iters; ++it) {
             memcpy(r, labels, total * sizeof(int32_t));
+            PAR
             for (int y = 1; y < H - 1; ++y)
                 for (int x = 1; x < W - 1; ++x) {
                     int c = r[y * W + x];
@@ -179,9 +191,29 @@ void orc_mfseg_cpu(orc_mfseg_state* st, const orc_mfseg_in* in, orc_mfseg_out* o
     int* maskComponentPixels = (int*)calloc((size_t)(nMasks > 0 ? nMasks : 1), sizeof(int));
     int* compMaskOverlap = (int*)calloc((size_t)nComponents * (nMasks > 0 ? nMasks : 1), sizeof(int));
     int* compModelOverlap = (int*)calloc((size_t)nComponents * (nModels + 1), sizeof(int));
-    for (size_t i = 0; i < total; ++i) compModelOverlap[(size_t)labels[i] * (nModels + 1) + modelIDToIndex[in->projectedIDs[i]]]++;
+    /* histograms: one private copy per thread, merged in thread order (integer sums: order-free) */
+    {
+        const size_t nA = (size_t)nComponents * (nModels + 1), nB = nMasks ? (size_t)nComponents * nMasks : 0;
+        #pragma omp parallel num_threads(g_threads) if (g_threads > 1)
+        {
+            int* ha = g_threads > 1 ? (int*)calloc(nA + nB + 1, sizeof(int)) : compModelOverlap;
+            int* hb = g_threads > 1 ? ha + nA : compMaskOverlap;
+            #pragma omp for schedule(static) nowait
+            for (size_t i = 0; i < total; ++i) {
+                ha[(size_t)labels[i] * (nModels + 1) + modelIDToIndex[in->projectedIDs[i]]]++;
+                if (nMasks) hb[(size_t)labels[i] * nMasks + in->mask[i]]++;
+            }
+            if (g_threads > 1) {
+                #pragma omp critical
+                {
+                    for (size_t q = 0; q < nA; ++q) compModelOverlap[q] += ha[q];
+                    for (size_t q = 0; q < nB; ++q) compMaskOverlap[q] += hb[q];
+                }
+                free(ha);
+            }
+        }
+    }
     if (nMasks) {
-        for (size_t i = 0; i < total; ++i) compMaskOverlap[(size_t)labels[i] * nMasks + in->mask[i]]++;
         const float overlap_threshold = 0.65f;
         for (int c = 1; c < nComponents; ++c) {
             int csize = stats[c * 5 + 4];
@@ -192,7 +224,9 @@ void orc_mfseg_cpu(orc_mfseg_state* st, const orc_mfseg_in* in, orc_mfseg_out* o
             } else mapComponentToMask[c] = 0;
         }
     }
+    PAR
     for (size_t i = 0; i < total; ++i) seg[i] = (uint8_t)mapComponentToMask[labels[i]];
+    PAR
     for (size_t i = 0; i < total; ++i) if (st->semanticIgnoreMap[i]) seg[i] = 255;           /* :360-362 */
 
     if (nMasks) {
@@ -200,9 +234,19 @@ void orc_mfseg_cpu(orc_mfseg_state* st, const orc_mfseg_in* in, orc_mfseg_out* o
         for (int m = 1; m < nMasks; ++m) { st->maskToID[m] = 0; if (in->classIDs[m] == st->personClassID) st->maskToID[m] = 255; }
         /* overlap of each (closed) mask with each projected model */
         unsigned* maskOverlap = (unsigned*)calloc((size_t)nModels * 256, sizeof(unsigned));
-        for (size_t i = 0; i < total; ++i) {
-            uint8_t mk = seg[i];
-            for (int b = 0; b < nModels; ++b) if (in->projectedIDs[i] == in->modelIDs[b]) maskOverlap[b * 256 + mk]++;
+        #pragma omp parallel num_threads(g_threads) if (g_threads > 1)
+        {
+            unsigned* hm = g_threads > 1 ? (unsigned*)calloc((size_t)nModels * 256, sizeof(unsigned)) : maskOverlap;
+            #pragma omp for schedule(static) nowait
+            for (size_t i = 0; i < total; ++i) {
+                uint8_t mk = seg[i];
+                for (int b = 0; b < nModels; ++b) if (in->projectedIDs[i] == in->modelIDs[b]) hm[b * 256 + mk]++;
+            }
+            if (g_threads > 1) {
+                #pragma omp critical
+                for (int q = 0; q < nModels * 256; ++q) maskOverlap[q] += hm[q];
+                free(hm);
+            }
         }
         for (int midx = 1; midx < nMasks; ++midx) {
             if (st->maskToID[midx] == 255) continue;
@@ -221,6 +265,7 @@ void orc_mfseg_cpu(orc_mfseg_state* st, const orc_mfseg_in* in, orc_mfseg_out* o
         }
         free(maskOverlap);
     }
+    PAR
     for (size_t i = 0; i < total; ++i) seg[i] = st->maskToID[seg[i]];                         /* :495-496 */
 
     /* :498-522 unused components absorbed by the model they overlap */

@@ -36,6 +36,7 @@ typedef struct {
     int32_t nComponents;
 } orc_mfseg_out;
 
+void orc_mfseg_set_threads(int n);        /* 1 (default) = the reference's single-threaded sweeps; n > 1 = OpenMP split, same results */
 void orc_mfseg_state_init(orc_mfseg_state* s, int W, int H);
 void orc_mfseg_state_free(orc_mfseg_state* s);
 void orc_mfseg_cpu(orc_mfseg_state* st, const orc_mfseg_in* in, orc_mfseg_out* out);

@@ -155,3 +155,67 @@ class OraclePipeline:
                 "updateId": ((self.W, self.H), np.uint8), "best": ((self.W, self.H), np.uint32),
                 "meas": ((self.W, self.H, 12), np.float32)}[name]
         return arr(getattr(m, name), spec[0], spec[1])
+
+
+# ---- MfSegmentation CPU tail (oracle/orc_mfseg.h): used by the thread-invariance test and by bench.py's configs[0] leg ----
+class MfsegState(C.Structure):
+    _fields_ = [("semanticIgnoreMap", u8p), ("maskToID", C.c_uint8 * 256), ("minMaskModelOverlap", C.c_float),
+                ("minMappedComponentSize", C.c_int32), ("personClassID", C.c_int32), ("removeEdges", C.c_int32)]
+
+
+class MfsegIn(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("edgesInv", u8p), ("depth", f32p), ("mask", u8p), ("nMasks", C.c_int32),
+                ("classIDs", C.POINTER(C.c_int32)), ("projectedIDs", u8p), ("nModels", C.c_int32), ("modelIDs", u8p),
+                ("modelClassIDs", C.POINTER(C.c_int32)), ("nextModelID", C.c_uint8), ("allowNew", C.c_int32),
+                ("minRelSizeNew", C.c_float), ("maxRelSizeNew", C.c_float), ("morphMaskRadius", C.c_int32), ("morphMaskIterations", C.c_int32)]
+
+
+class MfsegOut(C.Structure):
+    _fields_ = [("fullSegmentation", u8p), ("hasNewLabel", C.c_int32), ("newClassID", C.c_int32), ("isEmpty", C.c_int32 * 256),
+                ("pixelCount", C.c_int32 * 256), ("labels", C.POINTER(C.c_int32)), ("nComponents", C.c_int32)]
+
+
+def segmentation_frame(W=640, H=480, n_objects=3, seed=0, t=8):
+    """inputs of MfSegmentation::performSegmentation's CPU part for one synthetic frame: inverted edge map (edge-ness on the oracle's
+    frame maps, threshold 0.3, no close), raw depth, the frame's instance mask + class ids, and a projected-ID image as the global
+    projection of already-spawned models would give it (the previous frame's instances)"""
+    from maskfusion_b200.synth import SynthScene
+    from tests.stagewise import OracleStages
+    sc = SynthScene(W, H, n_objects=n_objects, seed=seed)
+    rgb, depth, mask, *_ = sc.render(t)
+    _, _, prev, *_ = sc.render(t - 1)
+    st = OracleStages(default_config(W, H, capacityGlobal=1000))
+    st.set_frame(rgb, depth); st.generate_maps()
+    fa = st.frame_arrays()
+    L = lib()
+    e = np.zeros((H, W), np.float32); b = np.zeros((H, W), np.uint8); inv = np.zeros((H, W), np.uint8)
+    L.orc_geometric_edges(ptr(fa["vmap0"]), ptr(fa["nmap0"]), W, H, C.c_float(150.0), C.c_float(2.8), ptr(e))
+    L.orc_threshold(ptr(e), W * H, C.c_float(0.3), ptr(b)); L.orc_invert(ptr(b), W * H, ptr(inv))
+    cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
+    return {"W": W, "H": H, "edgesInv": inv, "depth": np.ascontiguousarray(depth), "mask": np.ascontiguousarray(mask), "classIDs": cls,
+            "projectedIDs": np.ascontiguousarray(prev), "modelIDs": np.arange(1 + n_objects, dtype=np.uint8),
+            "modelClassIDs": cls.copy()}
+
+
+def run_mfseg_cpu(fr, threads=1, repeats=1, morphMaskIterations=0):
+    """orc_mfseg_cpu on a segmentation_frame(); returns (fullSegmentation, nComponents, hasNewLabel, seconds per call)"""
+    import time
+    L = lib()
+    L.orc_mfseg_set_threads(int(threads))
+    W, H = fr["W"], fr["H"]
+    st = MfsegState(); L.orc_mfseg_state_init(C.byref(st), W, H)
+    seg = np.zeros((H, W), np.uint8)
+    dt = []
+    for _ in range(repeats):
+        edges = fr["edgesInv"].copy()                    # the call overwrites its edge buffer
+        i = MfsegIn(W, H, edges.ctypes.data_as(u8p), fr["depth"].ctypes.data_as(f32p), fr["mask"].ctypes.data_as(u8p), len(fr["classIDs"]),
+                    fr["classIDs"].ctypes.data_as(C.POINTER(C.c_int32)), fr["projectedIDs"].ctypes.data_as(u8p), len(fr["modelIDs"]),
+                    fr["modelIDs"].ctypes.data_as(u8p), fr["modelClassIDs"].ctypes.data_as(C.POINTER(C.c_int32)), 200, 1, 0.015, 0.4, 2,
+                    morphMaskIterations)
+        o = MfsegOut(); o.fullSegmentation = seg.ctypes.data_as(u8p); o.labels = None
+        t0 = time.perf_counter()
+        L.orc_mfseg_cpu(C.byref(st), C.byref(i), C.byref(o))
+        dt.append(time.perf_counter() - t0)
+    L.orc_mfseg_state_free(C.byref(st))
+    L.orc_mfseg_set_threads(1)
+    return seg, int(o.nComponents), int(o.hasNewLabel), float(np.median(dt))

@@ -341,3 +341,65 @@ def test_oracle_is_thread_count_invariant():
         assert r.returncode == 0, r.stderr[-800:]
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1], outs
+
+
+def test_oracle_opencv_restatements_match_cv2(oracle):
+    """the OpenCV semantics restated in oracle/orc_mfseg.c -- connectedComponentsWithStats(4-connectivity) and
+    morphologyEx(MORPH_CLOSE, MORPH_ELLIPSE, iterations) -- against the cv2 that is importable here (4.13; upstream pins 3.4.1).
+    Labels are compared up to a permutation (the reference's results do not depend on the numbering), stats exactly."""
+    cv2 = pytest.importorskip("cv2")
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_connected_components4.restype = C.c_int
+    L.orc_connected_components4.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.POINTER(C.c_int32))]
+    L.orc_morph_close_ellipse.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+    libc = C.CDLL(None)
+    libc.free.argtypes = [C.c_void_p]
+    rng = np.random.default_rng(3)
+    for (W, H, p) in [(64, 48, 0.55), (97, 61, 0.7), (640, 480, 0.62), (33, 17, 0.9), (16, 16, 0.0), (16, 16, 1.0)]:
+        img = (rng.random((H, W)) < p).astype(np.uint8) * 255
+        if W == 640:                      # realistic: blobs with thin bridges
+            yy, xx = np.mgrid[0:H, 0:W]
+            img = (((np.sin(xx / 9.0) * np.cos(yy / 7.0) > -0.2) & (rng.random((H, W)) < 0.97)) * 255).astype(np.uint8)
+        labels = np.zeros((H, W), np.int32)
+        stats_p = C.POINTER(C.c_int32)()
+        n = L.orc_connected_components4(oracle.ptr(img), W, H, oracle.ptr(labels), C.byref(stats_p))
+        stats = np.ctypeslib.as_array(stats_p, shape=(n, 5)).copy()
+        libc.free(stats_p)
+        n_cv, lab_cv, stats_cv, _ = cv2.connectedComponentsWithStats(img, connectivity=4, ltype=cv2.CV_32S)
+        assert n == n_cv, (W, H, n, n_cv)
+        assert np.array_equal(labels == 0, lab_cv == 0)
+        # one-to-one label correspondence
+        pairs = np.unique(np.stack([labels.ravel(), lab_cv.ravel()], 1), axis=0)
+        present = n if (labels == 0).any() else n - 1          # label 0 has no pixel when the image has no zero
+        assert pairs.shape[0] == present and len(set(pairs[:, 0])) == present and len(set(pairs[:, 1])) == present
+        remap = np.zeros(n, np.int64); remap[pairs[:, 0]] = pairs[:, 1]
+        # stats columns: left, top, width, height, area (background row: cv2 reports the bounding box of the zero pixels too)
+        assert np.array_equal(stats[1:], stats_cv[remap[1:]]), (W, H)
+        assert stats[0, 4] == stats_cv[0, 4]
+    for (W, H) in [(64, 48), (640, 480)]:
+        seg = np.zeros((H, W), np.uint8)
+        for k in range(1, 6):             # mask-id image: a few labelled blobs with holes and gaps, plus 255 (ignored) pixels
+            cx, cy, r = rng.integers(8, W - 8), rng.integers(8, H - 8), rng.integers(4, max(5, H // 5))
+            yy, xx = np.mgrid[0:H, 0:W]
+            seg[(xx - cx) ** 2 + (yy - cy) ** 2 < r * r] = k
+        seg[rng.random((H, W)) < 0.08] = 0
+        seg[rng.random((H, W)) < 0.01] = 255
+        for r in (0, 1, 2, 3, 5):
+            for it in (0, 1, 2, 3):
+                a = seg.copy()
+                L.orc_morph_close_ellipse(oracle.ptr(a), W, H, r, it)
+                el = cv2.getStructuringElement(cv2.MORPH_ELLIPSE, (2 * r + 1, 2 * r + 1), (r, r))
+                ref = cv2.morphologyEx(seg, cv2.MORPH_CLOSE, el, anchor=(-1, -1), iterations=it) if it > 0 else seg
+                assert np.array_equal(a, ref), (W, H, r, it, int((a != ref).sum()))
+
+
+def test_mfseg_tail_thread_invariant_and_sane(oracle):
+    """BASELINE configs[0] workload (one 640x480 frame through the CPU part of MfSegmentation::performSegmentation): the OpenMP
+    split used for the all-cores timing gives the single-threaded result bit for bit, with and without the mask close"""
+    fr = oracle.segmentation_frame()
+    for it in (0, 2):
+        s1, n1, h1, _ = oracle.run_mfseg_cpu(fr, threads=1, morphMaskIterations=it)
+        s4, n4, h4, _ = oracle.run_mfseg_cpu(fr, threads=4, morphMaskIterations=it)
+        assert n1 == n4 and h1 == h4 and np.array_equal(s1, s4)
+        assert n1 > 5 and set(np.unique(s1)) >= {0, 1, 2, 3}           # background + the three instances mapped to their models

@@ -343,3 +343,55 @@ def test_write_ply_layout(product_lib, tmp_path):
     assert len(v) == int(kept.sum())
     assert np.array_equal(v["p"], s[kept, 0:3]) and np.array_equal(v["c"], col[kept].astype(np.uint8))
     assert np.array_equal(v["n"], -s[kept, 8:11]) and np.array_equal(v["r"], s[kept, 11])
+
+
+def test_corrupt_streams_are_rejected_not_crashed(product_lib, tmp_path):
+    """malformed JPEG / PNG / PNM headers: table selectors above 3 in the scan header, a frame component the scan
+    never names, duplicate component ids, an empty SOS, implausible image sizes -- every case returns an error (or, for random
+    bit flips, any result) through the C ABI; nothing reads out of bounds, throws across the boundary or terminates"""
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.api import decode_jpeg
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "loader_golden.npz"))
+    good = bytearray(g["jpg0"].tobytes())
+    sos = good.find(b"\xff\xda")
+    sof = good.find(b"\xff\xc0")
+    assert sos > 0 and sof > 0 and good[sos + 4] == 3
+    bad = bytearray(good); bad[sos + 6] = 0xF0                      # td = 15 for the first component
+    with pytest.raises(mfb.MFError, match="Huffman table outside"):
+        decode_jpeg(bytes(bad))
+    bad = bytearray(good); bad[sos + 6] = 0x0F                      # ta = 15
+    with pytest.raises(mfb.MFError, match="Huffman table outside"):
+        decode_jpeg(bytes(bad))
+    bad = bytearray(good); bad[sos + 7] = bad[sos + 5]              # the scan names component 1 twice, component 2 never
+    with pytest.raises(mfb.MFError, match="unknown component|missing from the scan"):
+        decode_jpeg(bytes(bad))
+    bad = bytearray(good); bad[sof + 13] = bad[sof + 10]            # duplicate component ids in the frame header: the scan's id-2 entry finds no taker
+    with pytest.raises(mfb.MFError, match="unknown component|missing from the scan"):
+        decode_jpeg(bytes(bad))
+    bad = bytearray(good[:sos]) + b"\xff\xda\x00\x02" + good[sos + 4:]     # SOS with an empty body
+    with pytest.raises(mfb.MFError):
+        decode_jpeg(bytes(bad))
+    bad = bytearray(good); bad[sof + 5:sof + 9] = b"\xff\xff\xff\xff"      # 65535 x 65535
+    with pytest.raises(mfb.MFError, match="16384"):
+        decode_jpeg(bytes(bad))
+    rng = np.random.default_rng(7)
+    for _ in range(300):                                                     # random byte damage after the SOI marker
+        b = bytearray(good)
+        for p in rng.integers(2, len(b), rng.integers(1, 6)):
+            b[p] = int(rng.integers(0, 256))
+        try:
+            decode_jpeg(bytes(b))
+        except mfb.MFError:
+            pass
+    # PNG with a 2^31-1 IHDR and a PGM with a huge header reach the directory reader
+    for name, payload in (("0000.png", b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", 0x7fffffff, 0x7fffffff, 8, 2, 0, 0, 0)) + _chunk(b"IDAT", zlib.compress(b"\0")) + _chunk(b"IEND", b"")),
+                          ("0000.ppm", b"P6\n99999999999 99999999999\n255\n" + b"\0" * 64)):
+        root = tmp_path / name.replace(".", "_")
+        os.makedirs(root / "rgb"); os.makedirs(root / "depth")
+        (root / "rgb" / name).write_bytes(payload)
+        write_png(str(root / "depth" / "0000.png"), np.zeros((4, 4), np.uint16))
+        with pytest.raises(mfb.MFError, match="16384"):
+            mfb.ImageLogReader(str(root / "rgb"), str(root / "depth"), None)
+    L = mfb.load_library()
+    assert not L.mf_klg_open(None, 640, 480, 0)
+    assert not L.mf_klg_open(b"/nonexistent.klg", -1, 480, 0)

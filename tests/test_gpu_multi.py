@@ -25,7 +25,7 @@ class MFS(C.Structure):
                 ("projKeys", C.c_void_p), ("projectedIDs", ol.u8p), ("fullSeg", ol.u8p)]
 
 
-def run(nframes, track_all, **over):
+def run(nframes, track_all, tag="", **over):
     import maskfusion_b200 as mfb
     from maskfusion_b200.synth import SynthScene
     kw = dict(capacityGlobal=1000000, capacityObject=200000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all))
@@ -57,7 +57,7 @@ def run(nframes, track_all, **over):
         log.append(rec)
     mf.close()
     os.makedirs(OUT, exist_ok=True)
-    with open(os.path.join(OUT, f"multi_trackall{int(track_all)}_w{int(kw['icpWeight'])}.json"), "w") as f:
+    with open(os.path.join(OUT, f"multi_trackall{int(track_all)}_w{int(kw['icpWeight'])}{tag}.json"), "w") as f:
         json.dump(log, f)
     return log
 

@@ -191,3 +191,61 @@ def test_geometric_edges(ref, state):
     assert bad.mean() < 5e-3, float(bad.mean())
     assert np.median(np.abs(e - eo)) < 1e-6
     assert (inv != io).mean() < 2e-3, float((inv != io).mean())
+
+
+def test_rgb_residual_and_step(ref, state):
+    """a6 + a7 pinned: computeRgbResidual (reduce.cu:774-997) + projectToPointCloud (cudafuncs.cu:718-751) + rgbStep
+    (reduce.cu:529-713) of the reference, one Gauss-Newton iteration per pyramid level on the oracle's own odometry state
+    (Sobel images, depth/intensity pyramids of the tracked frame), against orc_rgb_residual / orc_project_points / orc_rgb_step.
+    The correspondence count and the integer sum of squared differences are decided per pixel (a pixel whose projection lands on
+    x.5 may flip under the reference's fast division), the 6x6 system is an fp32 launch-shape-ordered sum: tolerances as for icpStep."""
+    sc, orc, _ = state
+    od = orc.odom(0)
+    L = orc.L
+
+    class DataTerm(C.Structure):
+        _fields_ = [("zx", C.c_int16), ("zy", C.c_int16), ("ox", C.c_int16), ("oy", C.c_int16), ("diff", C.c_float), ("valid", C.c_int32)]
+    sobelScale = np.float32(1.0 / 8.0)
+    minGrad = [5.0, 3.0, 1.0]
+    # a small rigid motion as the current estimate (resultRt), turned into K R^-1 K^-1 and K t exactly as RGBDOdometry.cpp:364-376
+    ang = np.array([0.004, -0.006, 0.003]); th = np.linalg.norm(ang); k = ang / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    R = np.eye(3) + np.sin(th) * Kx + (1 - np.cos(th)) * Kx @ Kx
+    t = np.array([0.004, -0.003, 0.005])
+    for l in range(3):
+        w, h = W >> l, H >> l
+        fx, fy, cx, cy = 528.0 / (1 << l), 528.0 / (1 << l), 320.0 / (1 << l), 240.0 / (1 << l)
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+        Ri = np.linalg.inv(R); ti = -Ri @ t
+        krk = np.ascontiguousarray((K @ Ri @ np.linalg.inv(K)).astype(np.float32)); kt = np.ascontiguousarray((K @ ti).astype(np.float32))
+        minScale = np.float32(minGrad[l] ** 2 / float(sobelScale) ** 2)
+        gx = np.ascontiguousarray(ol.arr(od.dIdx[l], (h, w), np.int16)); gy = np.ascontiguousarray(ol.arr(od.dIdy[l], (h, w), np.int16))
+        ld = np.ascontiguousarray(ol.arr(od.lastDepth[l], (h, w), np.float32)); nd = np.ascontiguousarray(ol.arr(od.nextDepth[l], (h, w), np.float32))
+        li = np.ascontiguousarray(ol.arr(od.lastImage[l], (h, w), np.uint8)); ni = np.ascontiguousarray(ol.arr(od.nextImage[l], (h, w), np.uint8))
+        # --- oracle ---
+        corres = (DataTerm * (w * h))()
+        cnt_o, sig_o = C.c_int(0), C.c_int(0)
+        L.orc_rgb_residual(C.c_float(minScale), ol.ptr(gx), ol.ptr(gy), ol.ptr(ld), ol.ptr(nd), ol.ptr(li), ol.ptr(ni), corres, C.c_float(0.07),
+                           ol.ptr(kt), ol.ptr(krk), w, h, C.byref(cnt_o), C.byref(sig_o))
+        cloud = np.zeros((h, w, 3), np.float32)
+        L.orc_project_points(ol.ptr(ld), w, h, ol.cam(fx, fy, cx, cy), ol.ptr(cloud))
+        out = np.zeros(29)
+        L.orc_rgb_step(corres, C.c_float(float(cnt_o.value)), ol.ptr(cloud), C.c_float(fx), C.c_float(fy), ol.ptr(gx), ol.ptr(gy), C.c_float(sobelScale), w, h, ol.ptr(out))
+        Ao = np.zeros((6, 6)); bo = np.zeros(6); q = 0
+        for i in range(6):
+            for j in range(i, 7):
+                if j == 6: bo[i] = out[q]
+                else: Ao[i, j] = Ao[j, i] = out[q]
+                q += 1
+        # --- reference kernels; the weights use the ORACLE's sigma so that the two systems are comparable term by term ---
+        cnt_r, sig_r = C.c_int(0), C.c_int(0)
+        A = np.zeros(36, np.float32); b = np.zeros(6, np.float32)
+        rc = ref.ref_rgb_iteration(C.c_float(minScale), ol.ptr(gx), ol.ptr(gy), ol.ptr(ld), ol.ptr(nd), ol.ptr(li), ol.ptr(ni), C.c_float(0.07), ol.ptr(kt),
+                                   ol.ptr(krk), C.c_float(float(cnt_o.value)), C.c_float(fx), C.c_float(fy), C.c_float(cx), C.c_float(cy), l,
+                                   C.c_float(sobelScale), w, h, C.byref(cnt_r), C.byref(sig_r), ol.ptr(A), ol.ptr(b))
+        assert rc == 0
+        assert cnt_o.value > (2000 >> (2 * l)), (l, cnt_o.value)                 # the term is actually exercised
+        assert abs(cnt_r.value - cnt_o.value) <= max(3, 2e-4 * cnt_o.value), (l, cnt_r.value, cnt_o.value)
+        assert abs(sig_r.value - sig_o.value) <= max(400, 2e-3 * sig_o.value), (l, sig_r.value, sig_o.value)
+        assert rel(A.reshape(6, 6), Ao) < 3e-3, (l, rel(A.reshape(6, 6), Ao))
+        assert np.abs(b - bo).max() < 3e-3 * np.abs(bo).max() + 1e-3 * np.abs(Ao).max() ** 0.5, (l, b, bo)
