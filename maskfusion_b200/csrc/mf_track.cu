@@ -69,53 +69,126 @@ __device__ void ldltSolve(const double* Ain, const double* b, int n, double* x)
     for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
 }
 
-// Fast path for the 6x6 normal equations: unpivoted LDL^T, fully unrolled so the factor lives in
-// registers (the pivoted routine above indexes its arrays dynamically -> local memory, ~15 us of
-// dependent latency per Gauss-Newton iteration on one thread).  For the SPD, well-conditioned systems
-// ICP produces both give the same solution to ~1e-15 relative; if any pivot is small relative to the
-// largest diagonal (or not positive) this returns false and the caller falls back to the pivoted solve.
-__device__ __forceinline__ bool ldltSolve6Fast(const double* A, const double* b, double* x)
+// R-SINCOS: one fixed Taylor polynomial (Horner, no contraction: this file is compiled -fmad=false) for the tiny update
+// angles of the Gauss-Newton steps, the same on both sides of the parity contract (oracle/orc_odometry.c: orc_det_sincos);
+// the library beyond |x| = 0.8 (never reached by a converging tracker).
+__device__ __forceinline__ void detSincos(double x, double* s, double* c)
 {
-    double L[6][6], d[6], y[6];
-    double maxDiag = 0;
+    if (!(fabs(x) <= 0.8)) { sincos(x, s, c); return; }
+    const double z = x * x;
+    double ps = -1.0 / 51090942171709440000.0;
+    ps = ps * z + 1.0 / 121645100408832000.0;
+    ps = ps * z - 1.0 / 355687428096000.0;
+    ps = ps * z + 1.0 / 1307674368000.0;
+    ps = ps * z - 1.0 / 6227020800.0;
+    ps = ps * z + 1.0 / 39916800.0;
+    ps = ps * z - 1.0 / 362880.0;
+    ps = ps * z + 1.0 / 5040.0;
+    ps = ps * z - 1.0 / 120.0;
+    ps = ps * z + 1.0 / 6.0;
+    *s = x - x * (z * ps);
+    double pc = 1.0 / 2432902008176640000.0;
+    pc = pc * z - 1.0 / 6402373705728000.0;
+    pc = pc * z + 1.0 / 20922789888000.0;
+    pc = pc * z - 1.0 / 87178291200.0;
+    pc = pc * z + 1.0 / 479001600.0;
+    pc = pc * z - 1.0 / 3628800.0;
+    pc = pc * z + 1.0 / 40320.0;
+    pc = pc * z - 1.0 / 720.0;
+    pc = pc * z + 1.0 / 24.0;
+    pc = pc * z - 1.0 / 2.0;
+    *c = 1.0 + z * pc;
+}
+
+MF_D double shflD(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
+// N x N (N = 3 or 6) symmetric system by ONE WARP with exactly the arithmetic of the sequential pivoted LDL^T above (= the oracle's
+// orc_ldlt_solve = Eigen's conventions): lane i < N keeps row i of the FULL matrix in registers; pivot search, symmetric row/column
+// swap, column scaling (IEEE division), trailing update A[i][j] -= (A[i][k] * d) * A[j][k], symmetric fill, the two substitutions --
+// every element sees the same operations in the same order as in the sequential routine, so the solution is BIT-IDENTICAL to it
+// (parity contract: with fp64 sums that round to the oracle's floats, the whole Gauss-Newton trajectory is reproduced bit for bit).
+// All 32 lanes must call; A (N*N, row-major) and b (N) are read from shared memory, x (N) is written there.
+template <int N>
+MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restrict__ b, double* x)
+{
+    const int lane = threadIdx.x & 31;
+    const bool act = lane < N;
+    const int r = act ? lane : N - 1;                      // idle lanes mirror the last row; they only ever supply nothing
+    double a[N];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) maxDiag = fmax(maxDiag, fabs(A[i * 6 + i]));
-    const double tiny = maxDiag * 1e-12;
-    bool ok = maxDiag > 0;
+    for (int j = 0; j < N; ++j) a[j] = A[r * N + j];
+    int perm = r;
+    int kend = N;
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        double dj = A[j * 6 + j];
+    for (int k = 0; k < N; ++k) {
+        if (k < kend) {                                    // warp uniform
+            double dg = a[0];                              // this lane's diagonal entry A[r][r]
 #pragma unroll
-        for (int k = 0; k < j; ++k) dj -= L[j][k] * L[j][k] * d[k];
-        d[j] = dj;
-        ok = ok && (dj > tiny);
-        const double inv = 1.0 / dj;
+            for (int j = 1; j < N; ++j) if (r == j) dg = a[j];
+            int piv = k; double best = fabs(shflD(dg, k));
 #pragma unroll
-        for (int i = j + 1; i < 6; ++i) {
-            double v = A[i * 6 + j];
+            for (int i = k + 1; i < N; ++i) { const double v = fabs(shflD(dg, i)); if (v > best) { best = v; piv = i; } }
+            if (piv != k) {                                // warp uniform
+                const int src = lane == k ? piv : (lane == piv ? k : lane);
 #pragma unroll
-            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k] * d[k];
-            L[i][j] = v * inv;
+                for (int j = 0; j < N; ++j) a[j] = shflD(a[j], src);                  // rows k <-> piv
+                perm = __shfl_sync(0xffffffffu, perm, src);
+                const double ak = a[k];
+                double ap = ak;
+#pragma unroll
+                for (int q = k + 1; q < N; ++q) if (piv == q) ap = a[q];
+                a[k] = ap;                                                          // columns k <-> piv
+#pragma unroll
+                for (int q = k + 1; q < N; ++q) if (piv == q) a[q] = ak;
+            }
+            const double d = shflD(a[k], k);
+            if (fabs(d) <= DBL_MIN) kend = k;
+            else {
+                if (act && lane > k) a[k] = a[k] / d;
+#pragma unroll
+                for (int j = k + 1; j < N; ++j) {
+                    const double ajk = shflD(a[k], j);                              // A[j][k] (scaled)
+                    if (act && lane >= j) a[j] = a[j] - (a[k] * d) * ajk;
+                }
+#pragma unroll
+                for (int j = k + 1; j < N; ++j)
+#pragma unroll
+                    for (int i = j + 1; i < N; ++i) { const double v = shflD(a[j], i); if (lane == j) a[i] = v; }   // A[j][i] = A[i][j]
+            }
         }
     }
-    if (!ok) return false;
+    if (kend < N) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        double v = b[i];
+        for (int j = 0; j < N; ++j) if (act && lane >= kend && j >= kend && j < lane) a[j] = 0.0;
+    }
+    double y = b[perm];
 #pragma unroll
-        for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
-        y[i] = v;
+    for (int j = 0; j < N - 1; ++j) {
+        const double yj = shflD(y, j);
+        if (act && lane > j && j < kend) y = y - a[j] * yj;
+    }
+    {
+        double dg = a[0];
+#pragma unroll
+        for (int j = 1; j < N; ++j) if (r == j) dg = a[j];
+        const double dd = lane < kend ? dg : 0.0;
+        y = (fabs(dd) > DBL_MIN) ? y / dd : 0.0;
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) y[i] /= d[i];
+    for (int i = N - 2; i >= 0; --i)
 #pragma unroll
-    for (int i = 5; i >= 0; --i) {
-        double v = y[i];
-#pragma unroll
-        for (int k = i + 1; k < 6; ++k) v -= L[k][i] * x[k];
-        x[i] = v;
-    }
-    return true;
+        for (int j = i + 1; j < N; ++j) {
+            const double v = shflD(a[i], j);               // A[j][i]
+            const double yj = shflD(y, j);
+            if (lane == i && i < kend) y = y - v * yj;
+        }
+    if (act) x[perm] = y;
+    __syncwarp();
 }
 
 __device__ void rodrigues(const double* src, double* R)
@@ -124,7 +197,8 @@ __device__ void rodrigues(const double* src, double* R)
     double theta = sqrt(rx * rx + ry * ry + rz * rz);
     for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
     if (theta >= DBL_EPSILON) {
-        double c = cos(theta), s = sin(theta), c1 = 1. - c, it = theta ? 1. / theta : 0.;
+        double c, s; detSincos(theta, &s, &c);
+        double c1 = 1. - c, it = theta ? 1. / theta : 0.;
         rx *= it; ry *= it; rz *= it;
         double rrt[9] = {rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz};
         double rxm[9] = {0, -rz, ry, rz, 0, -rx, -ry, rx, 0};
@@ -171,43 +245,39 @@ __device__ void computeWarp(TrackState* st, Cam c)
 // block reduction helpers
 // ---------------------------------------------------------------------------------------
 template <int N>
-MF_D void blockReduceStore(float* acc, float* partialOut)
+MF_D void blockReduceStore(double* acc, double* partialOut)
 {
-    __shared__ float sh[TRK_THREADS / 32][N];
+    __shared__ double sh[TRK_THREADS / 32][N];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        float v = acc[k];
+        double v = acc[k];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        for (int off = 16; off > 0; off >>= 1) v += __hiloint2double(__shfl_down_sync(0xffffffffu, __double2hiint(v), off), __shfl_down_sync(0xffffffffu, __double2loint(v), off));
         if (lane == 0) sh[warp][k] = v;
     }
     __syncthreads();
     if (threadIdx.x < N) {
-        float s = 0;
+        double s = 0;
 #pragma unroll
         for (int w = 0; w < TRK_THREADS / 32; ++w) s += sh[w][threadIdx.x];
         partialOut[threadIdx.x] = s;
     }
 }
 
-// Sum the per-block partials (rows of 64 floats, N used) with the WHOLE last block: warp w takes blocks
+// Sum the per-block partials (rows of 32 doubles, N used) with the WHOLE last block: warp w takes blocks
 // w, w+8, ...; lanes take columns lane and lane+32 (coalesced 128-byte rows, independent loads), doubles
 // throughout; the 8 warp sums are combined in fixed order.  Deterministic for a fixed launch shape.
 // (A single thread per column walking all partials serially cost ~10 us of exposed L2 latency per step.)
 template <int N>
-MF_D void sumPartials(const float* __restrict__ partial, unsigned nblocks, double* tot /* shared, >= N */)
+MF_D void sumPartials(const double* __restrict__ partial, unsigned nblocks, double* tot /* shared, >= N */)
 {
-    __shared__ double ws[TRK_THREADS / 32][64];
+    __shared__ double ws[TRK_THREADS / 32][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double a0 = 0, a1 = 0;
+    double a0 = 0;
 #pragma unroll 4
-    for (unsigned b = warp; b < nblocks; b += TRK_THREADS / 32) {
-        const float* row = partial + (size_t)b * 64;
-        a0 += (double)row[lane];
-        if (N > 32) a1 += (double)row[32 + lane];
-    }
-    ws[warp][lane] = a0; ws[warp][32 + lane] = a1;
+    for (unsigned b = warp; b < nblocks; b += TRK_THREADS / 32) a0 += partial[(size_t)b * 32 + lane];
+    ws[warp][lane] = a0;
     __syncthreads();
     if (threadIdx.x < N) {
         double s = 0;
@@ -238,12 +308,12 @@ MF_D bool lastBlock(unsigned* ticket)
 __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restrict__ vmapC, const float4* __restrict__ nmapC,
                                                           const float4* __restrict__ vmapG, const float4* __restrict__ nmapG,
                                                           int W, int H, Cam cam, TrackPoses pp, float distThres, float angleThres,
-                                                          float* __restrict__ partial, unsigned* ticket, float* out29)
+                                                          double* __restrict__ partial, unsigned* ticket, float* out29)
 {
     // pp.p[0] = Rcurr(9) tcurr(3); pp.p[1] = RprevInv(9) tprev(3)
-    float acc[NACC_ICP];
+    double acc[NACC_ICP];
 #pragma unroll
-    for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.f;
+    for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.0;
     const float* Rc = pp.p[0]; const float* tc = pp.p[0] + 9; const float* Rpi = pp.p[1]; const float* tp = pp.p[1] + 9;
     const float3 tprev = make_float3(tp[0], tp[1], tp[2]);
     const int N = W * H;
@@ -275,11 +345,11 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restri
 #pragma unroll
         for (int a = 0; a < 6; ++a)
 #pragma unroll
-            for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
-        acc[27] += row[6] * row[6];
-        acc[28] += 1.0f;
+            for (int b = a; b < 7; ++b) { acc[q] = fma((double)row[a], (double)row[b], acc[q]); ++q; }
+        acc[27] = fma((double)row[6], (double)row[6], acc[27]);
+        acc[28] += 1.0;
     }
-    blockReduceStore<NACC_ICP>(acc, partial + (size_t)blockIdx.x * 64);
+    blockReduceStore<NACC_ICP>(acc, partial + (size_t)blockIdx.x * 32);
     if (!lastBlock(ticket)) return;
     __shared__ double tot[NACC_ICP];
     sumPartials<NACC_ICP>(partial, gridDim.x, tot);
@@ -302,7 +372,7 @@ __global__ void __launch_bounds__(TRK_THREADS) k_icp_only(const float4* __restri
 #define PT_THREADS 512
 #endif
 #define PT_WARPS (PT_THREADS / 32)
-#define ROWF 32                        // floats per partial row: one 128-byte line per CTA per reduction
+#define ROWF 32                        // doubles per partial row: two 128-byte lines per CTA per reduction
 
 struct TrackParams {
     int W, H; Cam cam;
@@ -313,9 +383,13 @@ struct TrackParams {
     int corrSlots;                     // photometric correspondences kept per CTA in shared memory (0: global scratch instead)
 };
 
-// sum of 32 per-lane values over the warp with 31 shuffles instead of 5*32: each step exchanges HALF of the remaining
+// sum of 32 per-lane values over the warp with 31 (64-bit) shuffles instead of 5*32: each step exchanges HALF of the remaining
 // values with the xor partner.  Lane l ends with the total of value l.
-MF_D void warpReduceHalving32(float* v)
+MF_D double shflXorD(double v, int m)
+{
+    return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), m), __shfl_xor_sync(0xffffffffu, __double2loint(v), m));
+}
+MF_D void warpReduceHalving32(double* v)
 {
     const int lane = threadIdx.x & 31;
 #pragma unroll
@@ -324,42 +398,33 @@ MF_D void warpReduceHalving32(float* v)
         const bool up = (lane & off) != 0;
 #pragma unroll
         for (int k = 0; k < h; ++k) {
-            float keep = up ? v[k + h] : v[k];
-            float send = up ? v[k] : v[k + h];
-            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            double keep = up ? v[k + h] : v[k];
+            double send = up ? v[k] : v[k + h];
+            v[k] = keep + shflXorD(send, off);
         }
     }
 }
 
-// CTA-wide sum of N (<= 29) accumulators -> one row of 32 floats in global memory (row = this CTA's partial);
-// two exact integer counters ride in columns 29 and 30
+// CTA-wide fp64 sum of N (<= 29) accumulators -> one row of 32 doubles in global memory (row = this CTA's partial); two integer
+// counters ride in columns 29 and 30 (exact in fp64).  Accumulating the exact products of floats in fp64 makes the totals agree with
+// a sequential fp64 sum to ~1e-15 relative whatever the order: rounded to float (the reference's result record) they are the
+// oracle's values bit for bit, which is what keeps tracked trajectories identical instead of merely close.
 template <int N>
-MF_D void ctaReduceStore(const float* acc, float (*red)[ROWF], float* __restrict__ rowOut, int extra0 = 0, int extra1 = 0, bool hasExtra = false)
+MF_D void ctaReduceStore(const double* acc, double (*red)[ROWF], double* __restrict__ rowOut, int extra0 = 0, int extra1 = 0)
 {
-    float v[32];
+    double v[32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) v[k] = k < N ? acc[k] : 0.f;
+    for (int k = 0; k < 32; ++k) v[k] = k < N ? acc[k] : 0.0;
+    v[29] = (double)extra0; v[30] = (double)extra1;
     warpReduceHalving32(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     red[warp][lane] = v[0];
-    __syncwarp();
-    if (hasExtra) {
-        int e0 = extra0, e1 = extra1;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) { e0 += __shfl_down_sync(0xffffffffu, e0, off); e1 += __shfl_down_sync(0xffffffffu, e1, off); }
-        if (lane == 0) { red[warp][29] = __int_as_float(e0); red[warp][30] = __int_as_float(e1); }
-    }
     __syncthreads();
-    if (threadIdx.x < N) {
-        float s = 0;
+    if (threadIdx.x < ROWF) {
+        double s = 0;
 #pragma unroll
         for (int w = 0; w < PT_WARPS; ++w) s += red[w][threadIdx.x];
         rowOut[threadIdx.x] = s;
-    } else if (hasExtra && (threadIdx.x == 29 || threadIdx.x == 30)) {
-        int s = 0;
-#pragma unroll
-        for (int w = 0; w < PT_WARPS; ++w) s += __float_as_int(red[w][threadIdx.x]);
-        rowOut[threadIdx.x] = __int_as_float(s);
     }
 }
 
@@ -376,25 +441,22 @@ MF_D void gridBarrier(unsigned* bar, unsigned target)
     __syncthreads();
 }
 
-// every CTA: sum the R partial rows (fixed order, double) -> tot[0..32); columns 29/30 carry exact integers when EXTRA.
+// every CTA: sum the R partial rows (fixed order, fp64) -> tot[0..32); columns 29/30 carry the integer counters.
 // Warp w owns rows w, w+16, ...; the rows of a batch are all loaded before the first add (one L2 round trip for R <= 160).
 #define SUM_BATCH 10
-template <int N, bool EXTRA>
-MF_D void sumRows(const float* __restrict__ rows, unsigned R, double (*ws)[ROWF], double* tot)
+MF_D void sumRows(const double* __restrict__ rows, unsigned R, double (*ws)[ROWF], double* tot)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool isInt = EXTRA && (lane == 29 || lane == 30);
-    const bool used = lane < N || isInt;
     double a0 = 0;
     for (unsigned base = warp; base < R; base += PT_WARPS * SUM_BATCH) {
-        float x[SUM_BATCH];
+        double x[SUM_BATCH];
 #pragma unroll
         for (int i = 0; i < SUM_BATCH; ++i) {
             const unsigned b = base + (unsigned)i * PT_WARPS;
-            x[i] = (b < R && used) ? __ldcg(rows + (size_t)b * ROWF + lane) : 0.f;
+            x[i] = b < R ? __ldcg(rows + (size_t)b * ROWF + lane) : 0.0;
         }
 #pragma unroll
-        for (int i = 0; i < SUM_BATCH; ++i) a0 += isInt ? (double)__float_as_int(x[i]) : (double)x[i];
+        for (int i = 0; i < SUM_BATCH; ++i) a0 += x[i];
     }
     ws[warp][lane] = a0;
     __syncthreads();
@@ -416,25 +478,6 @@ MF_D void gradU8(const uint8_t* __restrict__ img, int W, int x, int y, float& gx
 }
 
 
-// unpivoted, unrolled 3x3 LDL^T for the SO(3) step (same contract as ldltSolve6Fast)
-__device__ __forceinline__ bool ldltSolve3Fast(const double* A, const double* b, double* x)
-{
-    double maxDiag = fmax(fabs(A[0]), fmax(fabs(A[4]), fabs(A[8])));
-    const double tiny = maxDiag * 1e-12;
-    double d0 = A[0];
-    if (!(maxDiag > 0) || !(d0 > tiny)) return false;
-    double l10 = A[3] / d0, l20 = A[6] / d0;
-    double d1 = A[4] - l10 * l10 * d0;
-    if (!(d1 > tiny)) return false;
-    double l21 = (A[7] - l20 * l10 * d0) / d1;
-    double d2 = A[8] - l20 * l20 * d0 - l21 * l21 * d1;
-    if (!(d2 > tiny)) return false;
-    double y0 = b[0], y1 = b[1] - l10 * y0, y2 = b[2] - l20 * y0 - l21 * y1;
-    y0 /= d0; y1 /= d1; y2 /= d2;
-    x[2] = y2; x[1] = y1 - l21 * x[2]; x[0] = y0 - l10 * x[1] - l20 * x[2];
-    return true;
-}
-
 // entry e = (r, c) of the inverse of a 3x3: cofactor(c, r) / det with cyclic indices (no sign bookkeeping, no divergent
 // switch: a 9-way switch serialised the nine lanes, ncu r01d).  Products and differences are the ones inv3d forms.
 // M is read in place with row stride LD (3 for a 3x3, 4 for the rotation block of a 4x4): no local copies.
@@ -451,68 +494,6 @@ MF_D double inv3dEntry(const double* M, int e)
 }
 
 struct SolveScratch { double A[36], b[6], x[6], Rt[16], nr[16], Ri[9], K[9], Kinv[9], tmp[9], ti[3]; float trR[9], trT[3], iR[9], iT[3]; int fast; };
-
-MF_D double shflD(double v, int src)
-{
-    int lo = __double2loint(v), hi = __double2hiint(v);
-    lo = __shfl_sync(0xffffffffu, lo, src); hi = __shfl_sync(0xffffffffu, hi, src);
-    return __hiloint2double(hi, lo);
-}
-
-// 6x6 normal equations by one warp: lane r < 6 keeps row r of A and b_r in registers; right-looking unpivoted LDL^T with the
-// forward substitution folded into the elimination and the pivots broadcast by shuffle.  The dependent chain per column is
-// one reciprocal and two multiply-adds (a single thread walking the whole factorisation took ~2.4 us per Gauss-Newton
-// iteration, ncu r01d).  Returns false (warp uniform) when a pivot is not safely positive: the caller then runs the pivoted solve.
-// Differences to a sequential LDL^T are at the 1e-16 level (fused multiply-adds, reciprocal instead of division); parity of the
-// solver is a tolerance contract (DESIGN.md R-LDLT).
-MF_D bool ldltSolve6Warp(const double* __restrict__ A, const double* __restrict__ b, double* x /* shared, 6 */)
-{
-    const int lane = threadIdx.x & 31;
-    const int r = lane < 6 ? lane : 5;
-    double a[6], y = b[r];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) a[k] = A[r * 6 + k];
-    double maxDiag = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) maxDiag = fmax(maxDiag, fabs(A[k * 6 + k]));
-    const double tiny = maxDiag * 1e-12;
-    bool ok = maxDiag > 0;
-    double myInv = 0;                                      // reciprocal of this lane's own pivot
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-        // row j is final: broadcast its pivot, its tail and its right-hand side
-        const double dj = shflD(a[j], j);
-        ok = ok && (dj > tiny);
-        const double inv = 1.0 / dj;
-        if (lane == j) myInv = inv;
-        const double yj = shflD(y, j);
-        double rowj[6];
-#pragma unroll
-        for (int k = j + 1; k < 6; ++k) rowj[k] = shflD(a[k], j);
-        const double l = a[j] * inv;                       // L[r][j] for rows below the pivot
-        if (lane > j) {
-#pragma unroll
-            for (int k = j + 1; k < 6; ++k) a[k] = fma(-l, rowj[k], a[k]);
-            y = fma(-l, yj, y);
-            a[j] = l;                                      // keep the factor in place
-        }
-    }
-    if (!ok) return false;
-    // lane r now holds y_r (of L y = b), the pivots' reciprocals and row r of L; z = D^-1 y, then L^T x = z from the last row up
-    double z = y * myInv;
-#pragma unroll
-    for (int i = 5; i >= 1; --i) {
-        const double xi = shflD(z, i);
-#pragma unroll
-        for (int k = 0; k < i; ++k) {
-            const double lik = shflD(a[k], i);             // L[i][k] lives in lane i
-            if (lane == k) z = fma(-lik, xi, z);
-        }
-    }
-    if (lane < 6) x[lane] = z;
-    __syncwarp();
-    return true;
-}
 
 // computeWarp (RGBDOdometry.cpp:364-376) by one warp: every matrix entry keeps the scalar routine's formula, lanes take entries.
 // sc->Kinv holds the inverse intrinsics of the level (set once per level).
@@ -549,10 +530,7 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
     }
     if (ICP && lane == 31) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
     __syncwarp();
-    if (!ldltSolve6Warp(sc->A, sc->b, sc->x)) {
-        if (lane == 0) ldltSolve(sc->A, sc->b, 6, sc->x);
-        __syncwarp();
-    }
+    ldltSolvePivWarp<6>(sc->A, sc->b, sc->x);              // bit-identical to the sequential pivoted routine (Eigen's ldlt().solve conventions)
     // computeUpdateSE3 (OdometryProvider.h:69-90): Rt = [rodrigues(x[3..5]) | x[0..2]]; every lane evaluates the (cheap, identical)
     // scalar part, lanes < 16 assemble one entry each
     {
@@ -560,7 +538,7 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
         const double theta = sqrt(rx * rx + ry * ry + rz * rz);
         double c = 1.0, s = 0.0, c1 = 0.0;
         const bool rot = theta >= DBL_EPSILON;
-        if (rot) { sincos(theta, &s, &c); c1 = 1. - c; const double it = 1. / theta; rx *= it; ry *= it; rz *= it; }
+        if (rot) { detSincos(theta, &s, &c); c1 = 1. - c; const double it = 1. / theta; rx *= it; ry *= it; rz *= it; }
         if (lane < 16) {
             const int r = lane >> 2, cc = lane & 3;
             double v;
@@ -622,7 +600,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     __shared__ TrackJob J;
     __shared__ TrackState S;
     __shared__ SolveScratch sc;
-    __shared__ float red[PT_WARPS][ROWF];
+    __shared__ double red[PT_WARPS][ROWF];
     __shared__ double ws[PT_WARPS][ROWF];
     __shared__ double tot[64];
     __shared__ double totR[ROWF];
@@ -655,7 +633,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         for (int k = 0; k < 6; ++k) st->lastb[k] = 0;
     }
     __syncthreads();
-    float* const rowsBuf[2] = {J.partial, J.partial + (size_t)G * ROWF};
+    double* const rowsBuf[2] = {reinterpret_cast<double*>(J.partial), reinterpret_cast<double*>(J.partial) + (size_t)G * ROWF};
     unsigned* const bar = J.bar;
     // photometric correspondences of this thread's pixels, slot = round * PT_THREADS + thread: written in phase A, read in phase B
     // by the same thread.  Shared memory when the launch reserved enough, else a private stripe of the model's scratch buffer.
@@ -688,9 +666,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 so3B[threadIdx.x] = (float)(kr[0] * so3KinvD[cc] + kr[1] * so3KinvD[3 + cc] + kr[2] * so3KinvD[6 + cc]);
             }
             __syncthreads();
-            float* rows = rowsBuf[gen & 1];
+            double* rows = rowsBuf[gen & 1];
             if (active) {
-                float acc[11];
+                double acc[11];
 #pragma unroll
                 for (int k = 0; k < 11; ++k) acc[k] = 0;
                 for (int k = tid; k < N; k += nthr) {
@@ -720,41 +698,51 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
 #pragma unroll
                         for (int ii = 0; ii < 3; ++ii)
 #pragma unroll
-                            for (int jj = ii; jj < 4; ++jj) acc[q++] += row[ii] * row[jj];
-                        acc[9] += row[3] * row[3];
-                        acc[10] += 1.0f;
+                            for (int jj = ii; jj < 4; ++jj) { acc[q] = fma((double)row[ii], (double)row[jj], acc[q]); ++q; }
+                        acc[9] = fma((double)row[3], (double)row[3], acc[9]);
+                        acc[10] += 1.0;
                     }
                 }
                 ctaReduceStore<11>(acc, red, rows + (size_t)blockIdx.x * ROWF);
             }
             ++gen; gridBarrier(bar, gen * G);
-            sumRows<11, false>(rows, Gact, ws, tot);
-            if (threadIdx.x == 0) {
-                // host logic of RGBDOdometry.cpp:301-324
-                int done = 0;
-                float res0 = (float)tot[9], res1 = (float)tot[10];
-                st->lastSO3Error = sqrtf(res0) / res1; st->lastSO3Count = res1;
-                if (st->lastSO3Error < st->so3LastError && fabsf(st->so3LastError - st->lastSO3Count) < 0.001f) done = 1;
-                else if (st->lastSO3Error > st->so3LastError + 0.001f) {
-                    st->lastSO3Error = st->so3LastError; st->lastSO3Count = st->so3LastCount;
-                    for (int q = 0; q < 9; ++q) st->resultR[q] = st->lastResultR[q];
-                    done = 1;
-                } else {
-                    st->so3LastError = st->lastSO3Error; st->so3LastCount = st->lastSO3Count;
-                    for (int q = 0; q < 9; ++q) st->lastResultR[q] = st->resultR[q];
-                    double A[9], bb[3], delta[3];
-                    A[0] = (double)(float)tot[0]; A[1] = A[3] = (double)(float)tot[1]; A[2] = A[6] = (double)(float)tot[2]; bb[0] = (double)(float)tot[3];
-                    A[4] = (double)(float)tot[4]; A[5] = A[7] = (double)(float)tot[5]; bb[1] = (double)(float)tot[6];
-                    A[8] = (double)(float)tot[7]; bb[2] = (double)(float)tot[8];
-                    if (!ldltSolve3Fast(A, bb, delta)) ldltSolve(A, bb, 3, delta);
-                    for (int k = 0; k < 3; ++k) delta[k] = (double)(float)delta[k];
-                    double ru[9]; rodrigues(delta, ru);
-                    float ruf[9], n[9];
-                    for (int k = 0; k < 9; ++k) ruf[k] = (float)ru[k];
-                    for (int r = 0; r < 3; ++r) for (int cc2 = 0; cc2 < 3; ++cc2) n[r * 3 + cc2] = (ruf[r * 3] * st->R_lr[cc2] + ruf[r * 3 + 1] * st->R_lr[3 + cc2]) + ruf[r * 3 + 2] * st->R_lr[6 + cc2];
-                    for (int k = 0; k < 9; ++k) { st->R_lr[k] = n[k]; st->resultR[k] = n[k]; }
+            sumRows(rows, Gact, ws, tot);
+            if (threadIdx.x < 32) {
+                // host logic of RGBDOdometry.cpp:301-324 on warp 0: lane 0 takes the decisions, the 3x3 solve is warp-cooperative
+                int mode = 0;                                  // 0: converged, 1: diverged (restore), 2: step
+                if (threadIdx.x == 0) {
+                    float res0 = (float)tot[9], res1 = (float)tot[10];
+                    st->lastSO3Error = sqrtf(res0) / res1; st->lastSO3Count = res1;
+                    if (st->lastSO3Error < st->so3LastError && fabsf(st->so3LastError - st->lastSO3Count) < 0.001f) mode = 0;
+                    else if (st->lastSO3Error > st->so3LastError + 0.001f) {
+                        st->lastSO3Error = st->so3LastError; st->lastSO3Count = st->so3LastCount;
+                        for (int q = 0; q < 9; ++q) st->resultR[q] = st->lastResultR[q];
+                        mode = 1;
+                    } else {
+                        st->so3LastError = st->lastSO3Error; st->so3LastCount = st->lastSO3Count;
+                        for (int q = 0; q < 9; ++q) st->lastResultR[q] = st->resultR[q];
+                        double* A = sc.A; double* bb = sc.b;
+                        A[0] = (double)(float)tot[0]; A[1] = A[3] = (double)(float)tot[1]; A[2] = A[6] = (double)(float)tot[2]; bb[0] = (double)(float)tot[3];
+                        A[4] = (double)(float)tot[4]; A[5] = A[7] = (double)(float)tot[5]; bb[1] = (double)(float)tot[6];
+                        A[8] = (double)(float)tot[7]; bb[2] = (double)(float)tot[8];
+                        mode = 2;
+                    }
                 }
-                flag = done;
+                mode = __shfl_sync(0xffffffffu, mode, 0);
+                if (mode == 2) {
+                    __syncwarp();
+                    ldltSolvePivWarp<3>(sc.A, sc.b, sc.x);
+                    if (threadIdx.x == 0) {
+                        double delta[3];
+                        for (int k = 0; k < 3; ++k) delta[k] = (double)(float)sc.x[k];
+                        double ru[9]; rodrigues(delta, ru);
+                        float ruf[9], n[9];
+                        for (int k = 0; k < 9; ++k) ruf[k] = (float)ru[k];
+                        for (int r = 0; r < 3; ++r) for (int cc2 = 0; cc2 < 3; ++cc2) n[r * 3 + cc2] = (ruf[r * 3] * st->R_lr[cc2] + ruf[r * 3 + 1] * st->R_lr[3 + cc2]) + ruf[r * 3 + 2] * st->R_lr[6 + cc2];
+                        for (int k = 0; k < 9; ++k) { st->R_lr[k] = n[k]; st->resultR[k] = n[k]; }
+                    }
+                }
+                if (threadIdx.x == 0) flag = mode != 2;
             }
             __syncthreads();
             if (flag) break;
@@ -837,11 +825,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
 
         for (int it = 0; it < tp.iterations[level]; ++it) {
             // ---- phase A: photometric correspondences + statistics, ICP normal equations ----
-            float* rowsA = rowsBuf[gen & 1];
+            double* rowsA = rowsBuf[gen & 1];
             if (active) {
-                float acc[NACC_ICP];
+                double acc[NACC_ICP];
 #pragma unroll
-                for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.f;
+                for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.0;
                 int cnt = 0, sig = 0;
                 const float3 tprev = make_float3(st->tprev[0], st->tprev[1], st->tprev[2]);
                 // arithmetic of one pixel (same order of accumulation as a one-pixel-at-a-time loop: a before b, rounds ascending)
@@ -879,9 +867,9 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
 #pragma unroll
                             for (int a = 0; a < 6; ++a)
 #pragma unroll
-                                for (int b = a; b < 7; ++b) acc[q++] += row[a] * row[b];
-                            acc[27] += row[6] * row[6];
-                            acc[28] += 1.0f;
+                                for (int b = a; b < 7; ++b) { acc[q] = fma((double)row[a], (double)row[b], acc[q]); ++q; }
+                            acc[27] = fma((double)row[6], (double)row[6], acc[27]);
+                            acc[28] += 1.0;
                         }
                     }
                 };
@@ -904,10 +892,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                     stage3(a, k0, r * PT_THREADS + threadIdx.x);
                     if (two) stage3(b, k1, (r + 1) * PT_THREADS + threadIdx.x);
                 }
-                ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * ROWF, cnt, sig, true);
+                ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * ROWF, cnt, sig);
             }
             ++gen; gridBarrier(bar, gen * G);
-            sumRows<NACC_ICP, true>(rowsA, Gact, ws, tot);
+            sumRows(rowsA, Gact, ws, tot);
             if (tp.rgb) {
                 if (threadIdx.x == 0) {
                     // RGBDOdometry.cpp:388-401
@@ -926,11 +914,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 __syncthreads();
                 if (flag) break;                                        // uniform over the whole grid: every CTA holds the same state
                 // ---- phase B: photometric normal equations with the weights of this iteration ----
-                float* rowsB = rowsBuf[gen & 1];
+                double* rowsB = rowsBuf[gen & 1];
                 if (active) {
-                    float accR[NACC_RGB];
+                    double accR[NACC_RGB];
 #pragma unroll
-                    for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.f;
+                    for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.0;
                     const float sigmaSh = st->sigmaVal;
                     auto rgbRow = [&](int2 c, short2 g, float4 cp) {
                         const float diff = __int_as_float(c.y);
@@ -953,7 +941,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
 #pragma unroll
                         for (int a = 0; a < 6; ++a)
 #pragma unroll
-                            for (int b = a; b < 7; ++b) accR[q++] += row[a] * row[b];
+                            for (int b = a; b < 7; ++b) { accR[q] = fma((double)row[a], (double)row[b], accR[q]); ++q; }
                     };
                     for (int r = 0; r < rounds; r += 2) {
                         const int k0 = tid + r * nthr, k1 = k0 + nthr;
@@ -971,7 +959,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 }
                 ++gen; gridBarrier(bar, gen * G);
                 // ICP totals stay in tot[0..28]; the photometric ones go behind them
-                sumRows<NACC_RGB, false>(rowsB, Gact, ws, totR);
+                sumRows(rowsB, Gact, ws, totR);
                 if (threadIdx.x < NACC_RGB) tot[NACC_ICP + threadIdx.x] = totR[threadIdx.x];
                 __syncthreads();
             }
@@ -1072,7 +1060,7 @@ void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vma
                      const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s)
 {
     const float angleThres = (float)sin(20.f * 3.14159254f / 180.f);
-    prof_mark(s, "k_icp_only"); k_icp_only<<<trackBlocks(W * H, numSMs), TRK_THREADS, 0, s>>>(vmapC, nmapC, vmapG, nmapG, W, H, cam, pp, 0.10f, angleThres, partial, ticket, out29);
+    prof_mark(s, "k_icp_only"); k_icp_only<<<trackBlocks(W * H, numSMs), TRK_THREADS, 0, s>>>(vmapC, nmapC, vmapG, nmapG, W, H, cam, pp, 0.10f, angleThres, reinterpret_cast<double*>(partial), ticket, out29);
 }
 
 }  // namespace mfb

@@ -39,13 +39,19 @@ class SynthObject:
     vel: np.ndarray      # world translation per frame once moving (3,)
     start: int           # first moving frame
     class_id: int = 1
+    # "table" layout only: extra primitives rigidly attached to the body (kind, size, 4x4 part->object), bounded oscillating motion
+    parts: list = dataclasses.field(default_factory=list)
+    amp: np.ndarray = None       # world-frame oscillation amplitude (3,) once moving: pose0.t + amp * sin(omega * (t - start) + phase)
+    omega: float = 0.0
+    phase: np.ndarray = None
+    yaw_amp: float = 0.0         # oscillating rotation about the object's vertical axis (rad)
 
 
 class SynthScene:
     """Room 4 x 3 x 4 m around the origin, camera near the origin looking down +z."""
 
     def __init__(self, width=640, height=480, n_objects=0, seed=0, noise=False, holes=0.0,
-                 max_step_mm=4.0, move_after=30):
+                 max_step_mm=4.0, move_after=30, layout="room", max_object_step_mm=8.0):
         self.W, self.H = width, height
         self.fx, self.fy, self.cx, self.cy = default_intrinsics(width, height)
         self.rng = np.random.default_rng(seed)
@@ -61,6 +67,12 @@ class SynthScene:
                          ((0.1, -0.55, 2.3), (0.45, 0.12, 0.2), (0.2, 0.3, 0.0))):
             T = np.eye(4); T[:3, :3] = _rot(*r); T[:3, 3] = c
             self.furniture.append(SynthObject("box", np.array(hs), T, np.zeros(3), 1 << 30, 0))
+        self.layout = layout
+        if layout == "table":
+            self._build_table(n_objects, move_after, max_object_step_mm * 1e-3)
+            n_objects = 0                  # the loop below builds the "room" layout
+        elif layout != "room":
+            raise ValueError("layout must be 'room' or 'table'")
         for k in range(n_objects):
             ang = (k + 0.5) / max(n_objects, 1) * 2.0 - 1.0
             centre = np.array([ang * 0.7, 0.3 - 0.22 * (k % 3), 1.1 + 0.2 * (k % 4)])
@@ -79,6 +91,50 @@ class SynthScene:
         self.dirs = np.stack([(u - self.cx) / self.fx, (v - self.cy) / self.fy, np.ones_like(u)], -1)
         self.max_step = max_step_mm * 1e-3
 
+    # ---- SURVEY 8(d) scene: N rigid objects of 0.15-0.4 m on a table / a shelf at 0.8-2 m, static for `move_after` frames, then
+    # each moves <= max_object_step per frame (bounded oscillation so that a 300-frame sequence stays in view and collision free).
+    # An object is a box body (three faces visible: all six degrees of freedom are observable for point-to-plane ICP) and, for
+    # every second object, a sphere "head" rigidly attached to it.  Every object covers >= ~10 k pixels at VGA.
+    # The bodies hover 6 cm above their support: the reference's edge-ness runs on the bilateral-FILTERED maps (MfSegmentation.cpp:149-151),
+    # which round a concave contact crease at ~1 m below the 0.3 threshold, so an object resting on the table would never be split from it
+    # geometrically; the gap gives the depth discontinuity that real scenes have around graspable objects.
+    def _build_table(self, n_objects, move_after, max_obj_step):
+        rng = self.rng
+        wide = self.W / self.fx > 1.4                        # 720p intrinsics see +-39 degrees, VGA +-31
+        def slab(c, hs):
+            T = np.eye(4); T[:3, 3] = c
+            self.furniture.append(SynthObject("box", np.array(hs), T, np.zeros(3), 1 << 30, 0))
+        # rows: (z of the object centres, y of the supporting surface, half-extent range, x half-span)
+        if n_objects <= 8:
+            rows = [(1.15, 0.40, (0.10, 0.13), 0.52), (1.90, 0.05, (0.16, 0.20), 0.80)]
+        else:
+            rows = [(1.10, 0.42, (0.085, 0.11), 0.62 if wide else 0.50), (1.75, 0.12, (0.13, 0.16), 0.95 if wide else 0.74),
+                    (2.35, -0.33, (0.16, 0.19), 1.0)]
+        slab((0.0, rows[0][1] + 0.04, 1.25), (1.05, 0.04, 0.45))                       # table top
+        for (z, ytop, _, _) in rows[1:]:
+            slab((0.0, ytop + 0.03, z + 0.05), (1.08, 0.03, 0.28))                     # shelves behind it
+        per = [n_objects // len(rows) + (1 if r < n_objects % len(rows) else 0) for r in range(len(rows))]
+        k = 0
+        for (z, ytop, (lo, hi), span), n in zip(rows, per):
+            for j in range(n):
+                x = 0.0 if n == 1 else -span + 2 * span * j / (n - 1)
+                hs = rng.uniform(lo, hi, 3); hs[1] = rng.uniform(lo, hi) * 1.15
+                T = np.eye(4)
+                T[:3, :3] = _rot(0.0, rng.uniform(0.45, 0.95) * (1 if (k % 2) else -1), 0.0)    # yaw: two vertical faces + the top face are seen
+                T[:3, 3] = [x, ytop - hs[1] - 0.06, z]     # 6 cm clear of the support (see the docstring)
+                parts = []
+                if k % 2 == 0:                                                             # sphere head on top of the body
+                    r = 0.55 * min(hs[0], hs[2])
+                    Tp = np.eye(4); Tp[:3, 3] = [0.0, -(hs[1] + 0.8 * r), 0.0]
+                    parts.append(("sphere", np.array([r]), Tp))
+                gap = (2 * span / max(n - 1, 1)) if n > 1 else 1.0
+                ax = max(0.0, min(0.06, 0.5 * (gap - 2.9 * max(hs[0], hs[2]))))           # stay clear of the neighbours (yawed footprint)
+                amp = np.array([ax, 0.0, 0.035])
+                omega = max_obj_step / max(np.linalg.norm(amp), 1e-6) * rng.uniform(0.6, 0.95)
+                self.objects.append(SynthObject("box", hs, T, np.zeros(3), move_after, class_id=1 + k % 5, parts=parts, amp=amp,
+                                                omega=float(omega), phase=rng.uniform(0, 2 * np.pi, 3) * 0.0, yaw_amp=0.12))
+                k += 1
+
     # ---- trajectories -------------------------------------------------
     def camera_pose(self, t: int) -> np.ndarray:
         """camera->world, smooth Lissajous: <= ~max_step per frame and <= 0.3 deg per frame."""
@@ -92,6 +148,12 @@ class SynthScene:
         o = self.objects[k]
         T = o.pose0.copy()
         dt = max(0, t - o.start)
+        if o.amp is not None:
+            # starts from rest at its spawn pose: 1 - cos for the translation (zero velocity at dt = 0), sin^2-free yaw the same way
+            s = 1.0 - np.cos(o.omega * dt)
+            T[:3, 3] = T[:3, 3] + o.amp * s * np.array([1.0, 1.0, -1.0 if k % 2 else 1.0])
+            T[:3, :3] = T[:3, :3] @ _rot(0.0, o.yaw_amp * 0.5 * s * (1 if k % 3 else -1), 0.0)
+            return T
         T[:3, 3] = T[:3, 3] + o.vel * dt
         return T
 
@@ -128,11 +190,18 @@ class SynthScene:
         mask = np.zeros(N, dtype=np.uint8)
         hit_local = o[None, :] + np.where(np.isfinite(tbest), tbest, 0.0)[:, None] * d
         nf = len(self.furniture)
+        prims = []                                           # (kind, size, 4x4 primitive->world, instance id, surface id)
         for k, ob in enumerate(self.furniture + self.objects):
             To = ob.pose0 if k < nf else self.object_pose(k - nf, t)
+            inst = max(0, k - nf + 1)
+            prims.append((ob.kind, ob.size, To, inst, 10 + k))
+            for pi, (pk, ps, Tp) in enumerate(ob.parts):
+                prims.append((pk, ps, To @ Tp, inst, 10 + k + 101 * (pi + 1)))
+        for (kind, size, To, inst, surf) in prims:
             Ro, to = To[:3, :3], To[:3, 3]
             ol = (o - to) @ Ro
             dl = d @ Ro
+            ob = SynthObject(kind, size, To, None, 0)
             if ob.kind == "sphere":
                 r = ob.size[0]
                 b = dl @ ol
@@ -152,8 +221,8 @@ class SynthScene:
                 tt = tn
                 ok = (tn < tf) & (tn > 1e-6) & (tn < tbest)
             tbest = np.where(ok, tt, tbest)
-            sid = np.where(ok, 10 + k, sid)
-            mask = np.where(ok, max(0, k - nf + 1), mask).astype(np.uint8)
+            sid = np.where(ok, surf, sid)
+            mask = np.where(ok, inst, mask).astype(np.uint8)
             with np.errstate(invalid="ignore"):
                 pl = ol[None, :] + tt[:, None] * dl
             hit_local = np.where(ok[:, None], pl, hit_local)

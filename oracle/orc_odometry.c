@@ -26,8 +26,8 @@ static void accumulate(const float* row, int n, int found, double* out)
 {
     int k = 0;
     for (int i = 0; i < n; ++i)
-        for (int j = i; j < n + 1; ++j) out[k++] += (double)(row[i] * row[j]);
-    out[k++] += (double)(row[n] * row[n]);
+        for (int j = i; j < n + 1; ++j) out[k++] += (double)row[i] * (double)row[j];
+    out[k++] += (double)row[n] * (double)row[n];
     out[k] += found ? 1.0 : 0.0;
 }
 
@@ -46,7 +46,11 @@ static void accumulate_rows(const float* rows, int P, int n, double* out)
         double s = 0.0;
         if (q < nq) {
             const int a = pi[q], b = pj[q];
-            for (int p = 0; p < P; ++p) { const float* r = rows + (size_t)p * 8; if (r[7] != 0.f) s += (double)(r[a] * r[b]); }
+            /* the product of two floats is exact in double: the sum is the fp64 sum of the exact products (the reference's kernels
+             * contract product and add into an fp32 FMA, i.e. also add the unrounded product).  An fp64 sum in ANY order agrees with
+             * this one to ~1e-15 relative, so after the rounding to float that the reference's 29-float result record imposes, a
+             * parallel fp64 reduction (the CUDA path) reproduces these values bit for bit except with probability ~1e-7 per value. */
+            for (int p = 0; p < P; ++p) { const float* r = rows + (size_t)p * 8; if (r[7] != 0.f) s += (double)r[a] * (double)r[b]; }
         } else
             for (int p = 0; p < P; ++p) s += rows[(size_t)p * 8 + 7] != 0.f ? 1.0 : 0.0;
         out[q] = s;
@@ -284,6 +288,37 @@ void orc_ldlt_solve(const double* Ain, const double* b, int n, double* x)
     for (int i = 0; i < n; ++i) x[perm[i]] = y[i];
 }
 
+/* R-SINCOS: libm's and CUDA's double sin/cos are both within 1 ulp but not bit-identical; the update angles of the
+ * Gauss-Newton steps are tiny, so both sides evaluate one fixed Taylor polynomial (Horner, no contraction) for |x| <= 0.8 and
+ * fall back to the library beyond (never reached by a converging tracker; a mismatch there would be a 1-ulp effect). */
+void orc_det_sincos(double x, double* s, double* c)
+{
+    if (!(fabs(x) <= 0.8)) { *s = sin(x); *c = cos(x); return; }
+    const double z = x * x;
+    double ps = -1.0 / 51090942171709440000.0;                    /* -1/21! */
+    ps = ps * z + 1.0 / 121645100408832000.0;                      /*  1/19! */
+    ps = ps * z - 1.0 / 355687428096000.0;                         /* -1/17! */
+    ps = ps * z + 1.0 / 1307674368000.0;                           /*  1/15! */
+    ps = ps * z - 1.0 / 6227020800.0;                              /* -1/13! */
+    ps = ps * z + 1.0 / 39916800.0;                                /*  1/11! */
+    ps = ps * z - 1.0 / 362880.0;                                  /* -1/9!  */
+    ps = ps * z + 1.0 / 5040.0;                                    /*  1/7!  */
+    ps = ps * z - 1.0 / 120.0;                                     /* -1/5!  */
+    ps = ps * z + 1.0 / 6.0;                                       /*  1/3!  */
+    *s = x - x * (z * ps);
+    double pc = 1.0 / 2432902008176640000.0;                       /*  1/20! */
+    pc = pc * z - 1.0 / 6402373705728000.0;                        /* -1/18! */
+    pc = pc * z + 1.0 / 20922789888000.0;                          /*  1/16! */
+    pc = pc * z - 1.0 / 87178291200.0;                             /* -1/14! */
+    pc = pc * z + 1.0 / 479001600.0;                               /*  1/12! */
+    pc = pc * z - 1.0 / 3628800.0;                                 /* -1/10! */
+    pc = pc * z + 1.0 / 40320.0;                                   /*  1/8!  */
+    pc = pc * z - 1.0 / 720.0;                                     /* -1/6!  */
+    pc = pc * z + 1.0 / 24.0;                                      /*  1/4!  */
+    pc = pc * z - 1.0 / 2.0;                                       /* -1/2!  */
+    *c = 1.0 + z * pc;
+}
+
 /* OdometryProvider.h:32-66 */
 void orc_rodrigues(const double* src, double* R)
 {
@@ -292,7 +327,8 @@ void orc_rodrigues(const double* src, double* R)
     for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
     if (theta >= DBL_EPSILON) {
         const double I[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
-        double c = cos(theta), s = sin(theta), c1 = 1. - c, it = theta ? 1. / theta : 0.;
+        double c, s; orc_det_sincos(theta, &s, &c);
+        double c1 = 1. - c, it = theta ? 1. / theta : 0.;
         rx *= it; ry *= it; rz *= it;
         double rrt[9] = { rx * rx, rx * ry, rx * rz, rx * ry, ry * ry, ry * rz, rx * rz, ry * rz, rz * rz };
         double rxm[9] = { 0, -rz, ry, rz, 0, -rx, -ry, rx, 0 };

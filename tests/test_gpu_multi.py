@@ -25,12 +25,12 @@ class MFS(C.Structure):
                 ("projKeys", C.c_void_p), ("projectedIDs", ol.u8p), ("fullSeg", ol.u8p)]
 
 
-def run(nframes, track_all, tag="", **over):
+def run(nframes, track_all, tag="", n_objects=3, layout="room", **over):
     import maskfusion_b200 as mfb
     from maskfusion_b200.synth import SynthScene
     kw = dict(capacityGlobal=1000000, capacityObject=200000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all))
     kw.update(over)
-    sc = SynthScene(W, H, n_objects=3, seed=0)
+    sc = SynthScene(W, H, n_objects=n_objects, seed=0, layout=layout)
     orc = ol.OraclePipeline(ol.default_config(W, H, **kw))
     L = orc.L
     L.orc_mf_process_frame_ex.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
@@ -55,11 +55,45 @@ def run(nframes, track_all, tag="", **over):
             rec["dpose"] = [float(np.abs(orc.pose(i) - models_c[i].getPose()).max()) for i in range(rec["n_o"])]
         rec["pose_o"] = [orc.pose(i).tolist() for i in range(s.nmodels)]
         log.append(rec)
+    # exported trajectories (MaskFusion.cpp:577-592: background pose, object poses as globalPose * objPose^-1), both sides
+    n_final = int(C.cast(orc.h, C.POINTER(MFS)).contents.nmodels)
+    traj = {"oracle": [np.array([orc.model(i).log[k] for k in range(orc.model(i).nlog * 8)]).reshape(-1, 8) for i in range(n_final)],
+            "cuda": [m.poseLog() for m in mf.getModels()]}
+    for r in log:
+        r["traj"] = None
+    log[-1]["traj"] = traj
     mf.close()
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, f"multi_trackall{int(track_all)}_w{int(kw['icpWeight'])}{tag}.json"), "w") as f:
-        json.dump(log, f)
+        json.dump([{k: v for k, v in r.items() if k != "traj"} for r in log], f)
     return log
+
+
+def ate_rmse(traj):
+    """per-model ATE-RMSE (translation, entries matched by timestamp, no alignment: both runs start at identity) in metres"""
+    out = []
+    for lo, lc in zip(traj["oracle"], traj["cuda"]):
+        to = {int(r[0]): r[1:4] for r in lo}; tc = {int(r[0]): r[1:4] for r in lc}
+        common = sorted(set(to) & set(tc))
+        assert len(common) >= max(1, min(len(to), len(tc)) - 1), (len(to), len(tc), len(common))
+        d = np.array([to[k] - tc[k] for k in common])
+        out.append(float(np.sqrt(np.mean(np.sum(d * d, axis=1)))))
+    return out
+
+
+def check_exact(log, min_models):
+    """fp64 sums + the oracle's solver reproduced operation for operation: EVERY model's pose, the segmentation, the projected-ID image
+    and the surfel counts equal the oracle's on every frame (tracked objects included), hence ATE-RMSE = 0 <= 1 mm"""
+    assert max(r["n_o"] for r in log) >= min_models, "oracle never spawned enough object models"
+    for r in log:
+        rec = {k: v for k, v in r.items() if k not in ("pose_o", "traj")}
+        assert r["n_o"] == r["n_c"] and r["ids_o"] == r["ids_c"] and r["cls_o"] == r["cls_c"], rec
+        assert max(r["dpose"]) == 0.0, rec
+        assert r["seg_diff"] == 0 and r["proj_diff"] == 0, rec
+        assert r["cnt_o"] == r["cnt_c"], rec
+    ate = ate_rmse(log[-1]["traj"])
+    assert max(ate) <= 1e-3, ate
+    return ate
 
 
 def oracle_poses(nframes, eps, **over):
@@ -122,6 +156,7 @@ def test_multi_model_static_objects():
     """GUI default: objects are spawned from the masks and follow the camera (trackAllModels=false, N13)"""
     log = run(26, track_all=False)
     check(log, 2)
+    check_exact(log, 2)
 
 
 def test_multi_model_tracked_objects():
@@ -130,6 +165,7 @@ def test_multi_model_tracked_objects():
     (MaskFusion.cpp:268-272) removes it on the next frame -- the lifecycle (spawn, inactivate) must match the oracle exactly."""
     log = run(27, track_all=True)
     check(log, 2)
+    check_exact(log, 2)
     assert log[-1]["n_c"] == 1
 
 
@@ -138,10 +174,27 @@ def test_multi_model_three_tracked_objects():
     batched persistent tracking kernel; a spawn every 6 frames so that all three exist after 18 frames and are tracked for 6 more"""
     over = dict(icpWeight=20.0, modelSpawnOffset=6)
     log = run(24, track_all=True, **over)
-    ref = [[np.array(p, np.float32) for p in r["pose_o"]] for r in log]
-    per = oracle_poses(24, 1e-7, **over)
-    envelope = [[float(np.abs(a - b).max()) for a, b in zip(pa, pb)] for pa, pb in zip(ref, per)]
-    with open(os.path.join(OUT, "multi_envelope_w20.json"), "w") as f:
-        json.dump({"envelope": envelope, "cuda_vs_oracle": [r.get("dpose") for r in log]}, f)
-    check(log, 4, envelope)
     assert log[-1]["n_c"] == 4
+    try:
+        check_exact(log, 4)
+    except AssertionError:
+        # diagnostic only (round-1 envelope probe): how far rounding-size noise moves the oracle's own poses on this sequence
+        ref = [[np.array(p, np.float32) for p in r["pose_o"]] for r in log]
+        per = oracle_poses(24, 1e-7, **over)
+        envelope = [[float(np.abs(a - b).max()) for a, b in zip(pa, pb)] for pa, pb in zip(ref, per)]
+        with open(os.path.join(OUT, "multi_envelope_w20.json"), "w") as f:
+            json.dump({"envelope": envelope, "cuda_vs_oracle": [r.get("dpose") for r in log]}, f)
+        raise
+
+
+def test_table_scene_eight_tracked_objects():
+    """BASELINE configs[3] scene: eight objects of 0.2-0.4 m on a table / shelf at 1-2 m (17-23 k pixels each), static for
+    30 frames and then moving <= 8 mm per frame, each tracked with ICP + photometric term next to the background.  Every pose of every
+    model on every frame, the segmentation and ID images and the surfel counts must equal the oracle's; per-object ATE-RMSE of the
+    exported trajectories (MaskFusion.cpp:577-592) <= 1 mm follows (it is 0).  MF_LONG=1 runs the 300-frame sequence of SURVEY 8(d)."""
+    n = 300 if os.environ.get("MF_LONG") == "1" else 64
+    log = run(n, track_all=True, tag=f"_table8_{n}", n_objects=8, layout="table", icpWeight=20.0, modelSpawnOffset=3)
+    assert log[-1]["n_c"] == 9, log[-1]["n_c"]
+    ate = check_exact(log, 9)
+    with open(os.path.join(OUT, f"ate_table8_{n}.json"), "w") as f:
+        json.dump({"frames": n, "ate_rmse_m": ate, "models": log[-1]["n_c"]}, f)
