@@ -3,19 +3,28 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A step is one processFrame call (one pass of the per-frame dense hot path) on one frame of
-a seeded synthetic replay.  Workload = BASELINE.json configs[1]: "-static" single-model
-path, 640x480, the background store pre-populated to ~4.7M surfels (capacity 2176^2, the
-reference's rounding of 5M, Model.cpp:101-106).
+A step is one processFrame call (one pass of the per-frame dense hot path) on one frame of a seeded synthetic replay.
+
+N = 1  workload = BASELINE.json configs[1]: "-static" single-model path, 640x480, the background store pre-populated to ~4.7M
+       surfels (capacity 2176^2, the reference's rounding of 5M, Model.cpp:101-106).
   value : frames/s with every frame already resident in HBM when the timed region starts
-  e2e   : frames/s through the reference-facing C-ABI call mf_process_frame with pinned HOST
-          buffers (H2D copies of rgb+depth and the D2H pose read-back inside the timed region)
-  roofline     : dominant kernel (largest share of device time, measured live with CUDA events
-                 on the launching stream) as algorithmic GB/s against MEASURED_PEAKS.json
-  cpu_baseline : the CPU oracle (oracle/, a restatement of the reference; the reference's own
-                 GL/CUDA program cannot run here) on a bounded sample of the same workload
-Multi-GPU (N>1, torchrun): the -static path has a single model and does not shard
-("replicas only"): every rank replays its own copy; value = total frames/s.
+  e2e   : frames/s through the reference-facing C-ABI call mf_process_frame with pinned HOST buffers (H2D copies of rgb+depth and
+          the D2H pose read-back inside the timed region)
+  roofline     : dominant kernel (largest share of device time, measured live with CUDA events on the launching stream) as
+                 algorithmic GB/s against MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (oracle/, a restatement of the reference; the reference's own GL/CUDA program cannot run here)
+                 on a bounded sample of the same workload
+  legs next to the main line (never instead of it): cpu_seg (configs[0]: the CPU part of MfSegmentation on 1 core / all cores),
+  ref_cuda (the reference's own CUDA kernels recompiled, one model-frame of tracking in its calling pattern), multi_object
+  (configs[2]: 3 tracked objects + the Mask R-CNN backbone on the same GPU), eight_objects (configs[3] on one GPU), ate (ATE-RMSE of
+  every model's exported trajectory against the oracle on the first frames of the 8-object replay), backbone.
+
+N > 1  (torchrun) workload = configs[3]: ONE 640x480 replay with 8 tracked objects, the object Models sharded over the N GPUs
+       (strong scaling: the replay is the same for every N).  The three exchanges of a frame -- frame-packet broadcast, pose-row
+       all-gather, 64-bit MIN all-reduce of the ID-projection keys -- are NCCL calls issued inside the library on its stream.
+  value : frames/s, inputs resident in rank 0's HBM; e2e: the same with pinned host inputs on rank 0 and the pose read back
+  single_process_same_workload : the same replay through one context on rank 0's GPU (the baseline the sharding is measured against)
+  replicas : secondary leg, N independent configs[1] replays (the -static path has one model and does not shard)
 """
 from __future__ import annotations
 
@@ -163,15 +172,8 @@ def ncu_traffic(kernel):
     return int(tot), os.path.basename(files[-1])
 
 
-def run_ours(args, rank, world):
-    import torch
-    import maskfusion_b200 as mfb
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    K, Wm = args.steps, args.warmup
+def static_leg(torch, mfb, stream, local, rank, world, K, Wm):
+    """configs[1]: the main line at N = 1, the `replicas` leg at N > 1"""
     n_need = 1 + 3 * (Wm + K) + 2
     sc, frames = make_replay(n_need, seed=rank)
     nu = len(frames)
@@ -180,14 +182,11 @@ def run_ours(args, rank, world):
         period = 2 * (nu - 1)
         r = j % period
         return r if r < nu else period - r
-    stream = torch.cuda.Stream()          # explicit: the default stream's NULL handle would make mf_create open a private stream the events cannot see
-    torch.cuda.set_stream(stream)
     cfg = mfb.default_config(W, H, capacityGlobal=CAPACITY)        # GUI defaults: ICP+RGB (w=20), SO3, -static
     mf = mfb.MaskFusion(cfg, device=local, stream=stream.cuda_stream)
     rgb0, d0, ts0 = frames[0]
     mf.processFrame(rgb0, d0, ts0)
-    S0 = prepopulate(mf, sc)
-
+    prepopulate(mf, sc)
     # pinned host staging (e2e) and device-resident copies (value)
     host_rgb = [torch.from_numpy(f[0]).pin_memory() for f in frames]
     host_d = [torch.from_numpy(f[1]).pin_memory() for f in frames]
@@ -217,28 +216,31 @@ def run_ours(args, rank, world):
         e1.record(stream)
         mf.sync()
         barrier()
-        ms = e0.elapsed_time(e1)
-        return ms, mf.kernelLaunches() - l0
+        return e0.elapsed_time(e1), mf.kernelLaunches() - l0
 
     sampler = ClockSampler(local); sampler.start()
-    ms_dev, launches = timed(1, True)                      # value: inputs resident in HBM
+    dev_runs = [timed(1, True)]
     ms_e2e, _ = timed(1 + Wm + K, False)                   # e2e: pinned host buffers through the C ABI
+    dev_runs.append(timed(1, True))                        # the device-resident region twice more: the spread of the timed region is reported
+    dev_runs.append(timed(1, True))
     clocks = sampler.stop()
     mf.setProfiling(True)                                  # same region again with the in-stream CUDA-event stage timer
     ms_prof, _ = timed(1 + 2 * (Wm + K), True)
     stages = mf.stageTimes()
     mf.setProfiling(False)
     S_live = mf.getBackgroundModel().lastCount()
-
+    ms_all = sorted(r[0] for r in dev_runs)
+    ms_dev, launches = ms_all[1], dev_runs[0][1]           # median of three passes
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e], device="cuda", dtype=torch.float64)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         ms_dev, ms_e2e = float(t[0]), float(t[1])
+    mf.close()
+    return {"ms_dev": ms_dev, "ms_e2e": ms_e2e, "ms_prof": ms_prof, "ms_passes": ms_all, "launches": launches, "clocks": clocks, "stages": stages, "S_live": S_live}
 
-    fps = world * K / (ms_dev / 1e3)
-    fps_e2e = world * K / (ms_e2e / 1e3)
+
+def roofline_of(stages, S_live, K, Wm, ms_prof):
     P = W * H
-    # dominant kernel by total device time inside the timed region
     kern = {k: v for k, v in stages.items() if k.startswith("k_")}
     total_ms = sum(v[1] for v in stages.values())
     dom = max(kern, key=lambda k: kern[k][1])
@@ -248,129 +250,325 @@ def run_ours(args, rank, world):
     achieved = (ab / 1e9) / (avg_ms / 1e3) if ab else None
     shares = {k: round(v[1] / total_ms, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][1])[:12]}
     traffic, traffic_src = ncu_traffic(dom)
-    # every kernel with a stated algorithmic byte count: average launch time inside the timed region -> GB/s against the same peak
     per_kernel = {}
     for k, (n, ms) in kern.items():
         b = algorithmic_bytes(k, S_live, P)
         if b and n:
             g = (b / 1e9) / (ms / n / 1e3)
-            # (the stage timer also sees the warm-up frames of its pass)
             per_kernel[k] = {"launches_per_step": round(n / (K + Wm), 2), "avg_ms": round(ms / n, 5), "GBps": round(g, 1), "frac": round(g / peak, 4)}
-    out = {
-        "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
-        "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: -static single model, 640x480 synthetic .klg replay, ICP+RGB+SO3 tracking + surfel fuse, 1 B200",
-                   "surfels_live": int(S_live), "surfel_capacity": CAPACITY, "tracking": "GUI defaults icpWeight=20 so3=1 pyramid=1",
-                   "l2": "surfel store 2x227 MB + per-frame maps exceed the 126 MB L2 between steps (no explicit flush)",
-                   "parallelism": "replicas only" if world > 1 else "single"},
-        "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": P * 3 + P * 4, "d2h_bytes_per_step": 160 + 64},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": peak_src,
-                     "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
-                     "traffic_source": traffic_src, "avg_launch_ms": round(avg_ms, 5), "algorithmic_bytes_per_launch": ab,
-                     "note": "the tracking kernel walks 29 dependent Gauss-Newton reductions over maps that stay in L2 (DRAM traffic << algorithmic bytes): "
-                             "it is bound by that serial chain, not by HBM; the streaming surfel passes are listed in `kernels`",
-                     "time_shares": shares, "kernels": per_kernel, "profiled_ms_per_step": round(ms_prof / K, 4)},
-    }
-    if rank == 0 and world == 1:
-        out["cpu_baseline"] = cpu_baseline(sample_frames=4)
-    mf.close()
-    if world == 1:
-        # secondary legs, reported next to the main line and never instead of it: BASELINE configs[2] (3 tracked objects + the
-        # Mask R-CNN backbone on the same GPU; masks are inputs as in the reference's -maskdir mode: the R-CNN heads are not built)
-        try:
-            out["multi_object"] = multi_object_leg(torch, stream)
-        except Exception as e:          # noqa: BLE001
-            out["multi_object"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "scripts"))
-            import bench_cnn
-            out["backbone"] = bench_cnn.run(1024, iters=5, warm=2)
-        except Exception as e:          # noqa: BLE001
-            out["backbone"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-    if world > 1:
-        # secondary leg (BASELINE configs[3] shape): ONE replay with tracked object models sharded over the ranks --
-        # frame broadcast, pose all-gather and ID-projection key merge over NCCL.  Reported next to the replica number, never instead of it.
-        try:
-            sh = sharded_leg(torch, local, rank, world)
-        except Exception as e:          # noqa: BLE001  (the main line must survive a failure of the optional leg)
-            sh = {"error": f"{type(e).__name__}: {e}"[:300]}
-        out["object_sharded"] = sh
-    if rank == 0:
-        print(json.dumps(out))
-    if world > 1:
-        torch.distributed.destroy_process_group()
+    return {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": peak_src,
+            "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
+            "traffic_source": traffic_src, "avg_launch_ms": round(avg_ms, 5), "algorithmic_bytes_per_launch": ab,
+            "note": "the tracking kernels walk 29 dependent Gauss-Newton reductions over maps that stay in L2 (DRAM traffic << algorithmic bytes): "
+                    "bound by that serial chain, not by HBM; the streaming surfel passes are listed in `kernels`",
+            "time_shares": shares, "kernels": per_kernel, "profiled_ms_per_step": round(ms_prof / K, 4)}
 
 
-def multi_object_leg(torch, stream, n_frames=84, timed_from=24):
-    """configs[2] shape on one GPU: 3 objects spawn at frames 6/12/18 and are tracked (ICP+RGB, batched with the background in the
-    persistent tracking kernel); global ID projection, edge segmentation + GPU connected components / voting every frame;
-    frames/s of frames [timed_from, n_frames) through processFrame with host inputs"""
-    import maskfusion_b200 as mfb
-    from maskfusion_b200.synth import SynthScene
-    cfg = mfb.default_config(W, H, capacityGlobal=1000000, capacityObject=600000, enableMultipleModels=1, icpWeight=20.0, so3=0,
-                             trackAllModels=1, modelSpawnOffset=6)
-    mf = mfb.MaskFusion(cfg, stream=stream.cuda_stream)
-    sc = SynthScene(W, H, n_objects=3, seed=0)
+# ------------------------------------------------------------------------------------------------------------------------------
+# multi-object replays (configs[2] / configs[3]): SURVEY 8(d) table scene, masks as inputs (the reference's -maskdir mode)
+# ------------------------------------------------------------------------------------------------------------------------------
+MULTI_KW = dict(capacityGlobal=1000000, capacityObject=262144, enableMultipleModels=1, icpWeight=20.0, so3=1, trackAllModels=1, modelSpawnOffset=3)
+
+
+def multi_frames(n_objects, n_frames):
+    from maskfusion_b200.synth import render_sequence, SynthScene
+    fr = render_sequence(range(n_frames), width=W, height=H, n_objects=n_objects, seed=0, layout="table")
+    sc = SynthScene(W, H, n_objects=n_objects, seed=0, layout="table")
     cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
-    frames = [sc.render(t)[:3] for t in range(n_frames)]
-    for t in range(timed_from):
-        mf.processFrame(frames[t][0], frames[t][1], t * 33333, mask=np.ascontiguousarray(frames[t][2]), classIDs=cls)
+    return [(f[0], f[1], f[2]) for f in fr], cls
+
+
+def single_process_multi(torch, mfb, stream, local, frames, cls, timed_from, backbone_every=0, want_poses=False):
+    """one context, all models on this GPU; frames [timed_from, end) timed twice: device-resident inputs, then pinned host inputs + pose
+    read-back per frame.  backbone_every = k > 0: the ResNet-101-FPN backbone runs on a second stream every k-th frame (configs[2])"""
+    cfg = mfb.default_config(W, H, **MULTI_KW)
+    mf = mfb.MaskFusion(cfg, device=local, stream=stream.cuda_stream)
+    n = len(frames)
+    host = [(torch.from_numpy(f[0]).pin_memory(), torch.from_numpy(f[1]).pin_memory(), torch.from_numpy(np.ascontiguousarray(f[2])).pin_memory()) for f in frames]
+    dev = [(a.cuda(), b.cuda(), c.cuda()) for a, b, c in host]
+    bb = None
+    if backbone_every:
+        bstream = torch.cuda.Stream()
+        bb = mfb.Backbone(1024, seed=1, stream=bstream.cuda_stream)
+        mf.attachBackbone(bb, backbone_every)
+    torch.cuda.synchronize()
+    mf.setFrameClasses(cls)
+
+    def run(lo, hi, on_device, read_pose):
+        src = dev if on_device else host
+        for t in range(lo, hi):
+            mf.processFramePtr(src[t][0].data_ptr(), src[t][1].data_ptr(), t * 33333, on_device, mask_ptr=src[t][2].data_ptr())
+            if read_pose:
+                mf.getBackgroundModel().getPose()
+    run(0, timed_from, True, False)
     mf.sync(); torch.cuda.synchronize()
+    l0 = mf.kernelLaunches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for t in range(timed_from, n_frames):
-        mf.processFrame(frames[t][0], frames[t][1], t * 33333, mask=np.ascontiguousarray(frames[t][2]), classIDs=cls)
+    run(timed_from, n, True, False)
     e1.record(stream)
     mf.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = mf.kernelLaunches() - l0
     models = mf.getModels()
-    res = {"value": round((n_frames - timed_from) / (e0.elapsed_time(e1) / 1e3), 2), "unit": "frames/s", "frames": n_frames - timed_from,
-           "models": len(models), "surfels": [m.lastCount() for m in models], "workload": "configs[2] shape: 3 tracked objects, 640x480, masks as inputs"}
+    res = {"value": round((n - timed_from) / (ms / 1e3), 2), "unit": "frames/s", "ms_per_step": round(ms / (n - timed_from), 4), "frames": n - timed_from,
+           "models": len(models), "surfels": [m.lastCount() for m in models], "gpu_launches": int(launches)}
+    if want_poses:
+        res["_poselogs"] = [m.poseLog() for m in models]
     mf.close()
+    if bb is not None:
+        bb.close()
     return res
 
 
-def sharded_leg(torch, local, rank, world, n_frames=84, timed_from=24):
-    """object-sharded pipeline on a 3-object replay (objects spawn at frames 6/12/18, each tracked with ICP+RGB on the rank that
-    owns its surfel store); frames/s of frames [timed_from, n_frames), max over ranks"""
-    import torch.distributed as dist
+def oracle_multi_poselogs(frames, cls, n):
+    """the CPU oracle on the first n frames of a multi-object replay -> per-model pose logs (test infrastructure: the ATE checker)"""
+    import ctypes as C
+    from tests import oracle_lib as ol
+    orc = ol.OraclePipeline(ol.default_config(W, H, **MULTI_KW))
+    L = orc.L
+    L.orc_mf_process_frame_ex.argtypes = [C.c_void_p] * 3 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+    t0 = time.time()
+    for t in range(n):
+        rgb, depth, mask = frames[t]
+        L.orc_mf_process_frame_ex(orc.h, ol.ptr(np.ascontiguousarray(rgb)), ol.ptr(np.ascontiguousarray(depth)), t * 33333, ol.ptr(np.ascontiguousarray(mask)),
+                                  ol.ptr(cls), len(cls))
+    dt = time.time() - t0
+    logs = []
+    i = 0
+    while True:
+        try:
+            m = orc.model(i)
+        except Exception:          # noqa: BLE001
+            break
+        if i >= 64 or m.nlog <= 0 or not m.log:
+            break
+        logs.append(np.array([m.log[k] for k in range(m.nlog * 8)]).reshape(-1, 8))
+        i += 1
+        if i >= _oracle_nmodels(orc):
+            break
+    return logs, dt
+
+
+def _oracle_nmodels(orc):
+    import ctypes as C
+    from tests.test_gpu_multi import MFS
+    return int(C.cast(orc.h, C.POINTER(MFS)).contents.nmodels)
+
+
+def ate_rmse(lo, lc):
+    to = {int(r[0]): r[1:4] for r in lo}; tc = {int(r[0]): r[1:4] for r in lc}
+    common = sorted(set(to) & set(tc))
+    if not common:
+        return None
+    d = np.array([to[k] - tc[k] for k in common])
+    return float(np.sqrt(np.mean(np.sum(d * d, axis=1))))
+
+
+def cpu_seg_baseline():
+    """BASELINE configs[0] / SURVEY 8(d)(i): the CPU part of MfSegmentation::performSegmentation (MfSegmentation.cpp:208-538, restated in
+    oracle/orc_mfseg.c, its OpenCV pieces pinned against cv2) on ONE 640x480 frame of the 3-object scene: one core (the reference is
+    single-threaded there) and all host cores with a straightforward OpenMP split"""
+    from tests import oracle_lib as ol
+    fr = ol.segmentation_frame()
+    cores = min(os.cpu_count() or 1, 32)
+    _, ncomp, _, t1 = ol.run_mfseg_cpu(fr, threads=1, repeats=15)
+    _, _, _, tn = ol.run_mfseg_cpu(fr, threads=cores, repeats=15)
+    return {"workload": "configs[0]: single 640x480 RGB-D frame, CPU geometric-segmentation tail (connected components, edge removal, overlap voting)",
+            "one_core_ms": round(t1 * 1e3, 3), "all_cores_ms": round(tn * 1e3, 3), "cores": cores, "components": ncomp, "kind": "port",
+            "frames_per_s_one_core": round(1.0 / t1, 1), "frames_per_s_all_cores": round(1.0 / tn, 1)}
+
+
+def run_ours(args, rank, world):
+    import torch
     import maskfusion_b200 as mfb
-    from maskfusion_b200.sharding import ShardedMaskFusion
-    from maskfusion_b200.synth import SynthScene
-    cfg = mfb.default_config(W, H, capacityGlobal=1000000, capacityObject=600000, enableMultipleModels=1, icpWeight=20.0, so3=0,
-                             trackAllModels=1, modelSpawnOffset=6)
-    smf = ShardedMaskFusion(cfg, device=local)
-    sc = SynthScene(W, H, n_objects=3, seed=0)
-    cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
-    frames = [sc.render(t)[:3] for t in range(n_frames)] if rank == 0 else None
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    K, Wm = args.steps, args.warmup
+    stream = torch.cuda.Stream()          # explicit: the default stream's NULL handle would make mf_create open a private stream the events cannot see
+    torch.cuda.set_stream(stream)
+    if world > 1:
+        return run_sharded(args, rank, world, torch, mfb, stream, local)
+    st = static_leg(torch, mfb, stream, local, rank, world, K, Wm)
+    P = W * H
+    fps = K / (st["ms_dev"] / 1e3)
+    fps_e2e = K / (st["ms_e2e"] / 1e3)
+    out = {
+        "metric": METRIC, "value": round(fps, 3), "unit": "frames/s", "n_gpus": 1, "steps": K, "warmup": Wm,
+        "ms_per_step": round(st["ms_dev"] / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: -static single model, 640x480 synthetic .klg replay, ICP+RGB+SO3 tracking + surfel fuse, 1 B200",
+                   "surfels_live": int(st["S_live"]), "surfel_capacity": CAPACITY, "tracking": "GUI defaults icpWeight=20 so3=1 pyramid=1",
+                   "l2": "surfel store 2x227 MB + per-frame maps exceed the 126 MB L2 between steps (no explicit flush)",
+                   "parallelism": "single", "numerics": "fp32 per element; Gauss-Newton sums in fp64 of exact products, rounded to the reference's float record"},
+        "timed_region": {"passes_ms": [round(m, 3) for m in st["ms_passes"]], "value_from": "median of three device-resident passes",
+                         "min_ms_per_step": round(st["ms_passes"][0] / K, 4), "max_ms_per_step": round(st["ms_passes"][-1] / K, 4)},
+        "e2e": {"value": round(fps_e2e, 3), "unit": "frames/s", "h2d_bytes_per_step": P * 3 + P * 4, "d2h_bytes_per_step": 160 + 64},
+        "gpu_launches": int(st["launches"]),
+        "clocks": st["clocks"],
+        "roofline": roofline_of(st["stages"], st["S_live"], K, Wm, st["ms_prof"]),
+    }
+    out["cpu_baseline"] = cpu_baseline(sample_frames=4)
 
-    def step(t):
+    def leg(name, fn):
+        try:
+            out[name] = fn()
+        except Exception as e:          # noqa: BLE001  (the main line must survive a failure of an optional leg)
+            out[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    leg("cpu_seg", cpu_seg_baseline)
+
+    def ref_cuda():
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import time_ref_track
+        r = time_ref_track.run(10)
+        trk = sum(v[1] for k, v in st["stages"].items() if k.startswith("k_track")) / max(1, st["stages"].get("k_track_persistent", (1, 0))[0])
+        r["this_library_tracking_us_per_model_frame"] = round(trk * 1e3, 1)
+        return r
+    leg("ref_cuda", ref_cuda)
+    n8 = 72
+    frames8 = cls8 = None
+
+    def eight():
+        nonlocal frames8, cls8
+        frames8, cls8 = multi_frames(8, n8)
+        r = single_process_multi(torch, mfb, stream, local, frames8, cls8, timed_from=34, want_poses=True)
+        r["workload"] = "configs[3] on ONE GPU: 8 tracked objects (17-23 k pixels each, table scene of SURVEY 8d) + background, 640x480, masks as inputs"
+        return r
+    leg("eight_objects", eight)
+
+    def ate():
+        logs_c = out["eight_objects"].pop("_poselogs")
+        n_ate = 40
+        logs_o, dt = oracle_multi_poselogs(frames8, cls8, n_ate)
+        vals = [ate_rmse(lo, lc) for lo, lc in zip(logs_o, logs_c)]
+        return {"unit": "m", "frames": n_ate, "models": len(vals), "background_ate_rmse": vals[0], "worst_object_ate_rmse": max(vals[1:]) if len(vals) > 1 else None,
+                "per_model": vals, "bit_identical_poses": bool(all(v == 0.0 for v in vals)),
+                "against": f"CPU oracle (restatement of the reference) on the first {n_ate} frames of the 8-object replay ({dt:.0f} s on {os.environ.get('OMP_NUM_THREADS')} threads); "
+                           "exported trajectories as MaskFusion.cpp:577-592 logs them, no alignment"}
+    leg("ate", ate)
+    if isinstance(out.get("eight_objects"), dict):
+        out["eight_objects"].pop("_poselogs", None)
+
+    def three():
+        fr3, cls3 = multi_frames(3, 60)
+        r = single_process_multi(torch, mfb, stream, local, fr3, cls3, timed_from=20)
+        try:
+            rb = single_process_multi(torch, mfb, stream, local, fr3, cls3, timed_from=20, backbone_every=5)
+            r["with_backbone_every_5th_frame"] = {"value": rb["value"], "ms_per_step": rb["ms_per_step"],
+                                                  "note": "ResNet-101-FPN forward (1024x1024, synthetic weights) enqueued on a second stream every 5th frame (the reference's sidecar runs at ~5 Hz)"}
+        except Exception as e:          # noqa: BLE001
+            r["with_backbone_every_5th_frame"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        r["workload"] = "configs[2]: 3 tracked objects, 640x480, 1 B200, Mask R-CNN backbone on the same GPU; masks are inputs (-maskdir mode: the R-CNN heads are not built)"
+        return r
+    leg("multi_object", three)
+
+    def backbone():
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        import bench_cnn
+        return bench_cnn.run(1024, iters=5, warm=2)
+    leg("backbone", backbone)
+    print(json.dumps(out))
+
+
+def run_sharded(args, rank, world, torch, mfb, stream, local):
+    """N > 1: configs[3], object Models sharded over the ranks (in-library NCCL exchange); replicas of configs[1] as the secondary leg"""
+    import torch.distributed as dist
+    from maskfusion_b200.sharding import ShardedMaskFusion
+    K, Wm = args.steps, args.warmup
+    warm_to = 34                                            # 8 objects spawned (one every 3 frames), 30 static frames over
+    n = min(warm_to + Wm + K, 160)
+    K = n - warm_to - Wm
+    frames = cls = None
+    single = None
+    if rank == 0:
+        frames, cls = multi_frames(8, n)
+        single = single_process_multi(torch, mfb, stream, local, frames, cls, timed_from=warm_to + Wm)
+    dist.barrier()
+    cfg = mfb.default_config(W, H, **MULTI_KW)
+    smf = ShardedMaskFusion(cfg, device=local)
+    clsp = None
+    if rank == 0:
+        host = [(torch.from_numpy(f[0]).pin_memory(), torch.from_numpy(f[1]).pin_memory(), torch.from_numpy(np.ascontiguousarray(f[2])).pin_memory()) for f in frames]
+        dev = [(a.cuda(), b.cuda(), c.cuda()) for a, b, c in host]
+        clsp = np.ascontiguousarray(cls, np.int32)
+    torch.cuda.synchronize()
+
+    def step(t, on_device, read_pose=False):
         if rank == 0:
-            rgb, depth, mask = frames[t]
-            smf.processFrame(rgb, depth, t * 33333, mask=np.ascontiguousarray(mask), classIDs=cls)
+            src = dev if on_device else host
+            smf.processFramePtr(src[t][0].data_ptr(), src[t][1].data_ptr(), t * 33333, src[t][2].data_ptr(), clsp.ctypes.data, len(clsp), on_device)
         else:
-            smf.processFrame()
-    for t in range(timed_from):
-        step(t)
-    smf.mf.sync(); dist.barrier(); torch.cuda.synchronize()
-    b0 = smf.bytes_collective
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(smf.stream)
-    for t in range(timed_from, n_frames):
-        step(t)
-    e1.record(smf.stream)
-    smf.mf.sync(); dist.barrier(); torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            smf.processFramePtr(0, 0, 0, 0, 0, 0, False)
+        if read_pose:
+            smf.mf.getBackgroundModel().getPose()
+
+    def timed(lo, hi, on_device, read_pose):
+        smf.mf.sync(); dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(smf.stream)
+        for t in range(lo, hi):
+            step(t, on_device, read_pose)
+        e1.record(smf.stream)
+        smf.mf.sync(); dist.barrier(); torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+    sampler = ClockSampler(local); sampler.start()
+    for t in range(warm_to + Wm):
+        step(t, True)
+    s0 = smf.stats()
+    l0 = smf.mf.kernelLaunches()
+    ms_dev = timed(warm_to + Wm, n, True, False)
+    launches = smf.mf.kernelLaunches() - l0
+    s1 = smf.stats()
+    clocks = sampler.stop()
+    # e2e: the same frames again are not available (the replay has moved on): time the NEXT K frames with host inputs would need more
+    # frames; instead a second sharded context replays the whole sequence with pinned host inputs and a pose read-back per frame
     models = smf.models()
-    res = {"value": round((n_frames - timed_from) / (float(ms[0]) / 1e3), 2), "unit": "frames/s", "frames": n_frames - timed_from,
-           "models": len(models), "owners": [smf.owner(i) for i in range(len(models))],
-           "collective_bytes_per_frame": int((smf.bytes_collective - b0) / (n_frames - timed_from)),
-           "note": "host-driven schedule (python torch.distributed plumbing above the C ABI): three small syncs per frame; inputs start on the host of rank 0"}
+    owners = [smf.owner(i) for i in range(len(models))]
     smf.close()
-    return res
+    smf2 = ShardedMaskFusion(cfg, device=local)
+    smf_keep = smf
+    smf = smf2
+    for t in range(warm_to + Wm):
+        step(t, False)
+    ms_e2e = timed(warm_to + Wm, n, False, True)
+    smf.close()
+    del smf_keep
+    # secondary leg: replicas of configs[1]
+    try:
+        st = static_leg(torch, mfb, stream, local, rank, world, min(args.steps, 60), args.warmup)
+        kk = min(args.steps, 60)
+        replicas = {"value": round(world * kk / (st["ms_dev"] / 1e3), 2), "unit": "frames/s", "ms_per_step": round(st["ms_dev"] / kk, 4),
+                    "e2e": round(world * kk / (st["ms_e2e"] / 1e3), 2),
+                    "workload": "configs[1] -static, one independent replay per GPU (no collective on the data path), total frames/s"}
+    except Exception as e:          # noqa: BLE001
+        replicas = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0:
+        P = W * H
+        per_frame = (s1["bytes"] - s0["bytes"]) / K
+        out = {
+            "metric": METRIC, "value": round(K / (ms_dev / 1e3), 3), "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": round(ms_dev / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[3]: 8 tracked objects, 640x480 synthetic replay (table scene, SURVEY 8d), object Models sharded across the GPUs, "
+                                   "NCCL RGB-D broadcast + pose gather + ID-key MIN all-reduce issued inside the library",
+                       "parallelism": "object-sharded", "models": len(models), "owners": owners, "tracking": "ICP+RGB (w=20) + SO3, every model tracked",
+                       "l2": "per-rank working set (frame maps + stores of the local models) fits L2; every frame is new input", "masks": "inputs (-maskdir mode)"},
+            "e2e": {"value": round(K / (ms_e2e / 1e3), 3), "unit": "frames/s", "h2d_bytes_per_step": P * 8 + 1040, "d2h_bytes_per_step": 8464},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "collectives": {"transport": s1["transport"], "comm_nranks_seen": s1["nranks"], "nccl_version": s1["nccl_version"],
+                            "calls_per_frame": round((s1["calls"] - s0["calls"]) / K, 2), "bytes_per_frame": int(per_frame),
+                            "what": "ncclBroadcast frame packet (2.46 MB) + ncclAllGather pose rows (8 KB per rank) + ncclAllReduce(min, u64) projection keys (2.46 MB)"},
+            "single_process_same_workload": single,
+            "speedup_vs_single_process": round((K / (ms_dev / 1e3)) / single["value"], 3) if single else None,
+            "replicas": replicas,
+        }
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def cpu_baseline(sample_frames):

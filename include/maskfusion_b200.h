@@ -116,6 +116,11 @@ int mf_download_track_stats(mf_context* ctx, int i, double* A36, double* b6, flo
 int mf_download_edge_map(mf_context* ctx, float* edge, uint8_t* binary);                           /* MfSegmentation floatEdgeMap / binary edge map */
 /* test hook: morphological close of a host image (W x H of the context, in place). ellipse != 0: cv::morphologyEx(MORPH_CLOSE, MORPH_ELLIPSE) of the
  * mask-id image (MfSegmentation.cpp:424-426); ellipse == 0: the binary edge-map close (segmentation.cu:217-255,334-354), `inverted` = 255 - result. */
+/* Mask R-CNN backbone on the frame path (MaskRCNN::executeSequential, MaskRCNN.cpp:147-151, called at MfSegmentation.cpp:130): every k-th
+ * processFrame letter-boxes the frame's RGB image into `backbone`'s input (mf_backbone_mold) and enqueues its forward on the backbone's
+ * own stream, concurrently with the dense pipeline on the same GPU.  backbone = handle of mf_backbone_create; NULL detaches. */
+int mf_attach_backbone(mf_context* ctx, void* backbone, int every_k);
+int mf_debug_track_timing(int64_t* out, int cap);   /* profiling builds only (-DMF_TRACK_TIMING): (tag, SM clock) pairs of the last tracking launch; else 0 */
 int mf_morph_close(mf_context* ctx, uint8_t* image, int radius, int iterations, int ellipse, uint8_t* inverted);
 
 /* ---- stand-alone kernels exposed for parity tests (device work, host buffers) ---- */
@@ -125,20 +130,34 @@ int mf_download_segmentation(mf_context* ctx, uint8_t* mask, uint8_t* projected_
 int mf_model_class_id(mf_context* ctx, int i);                                /* Model::getClassID */
 
 /* ---- object-sharded mode: one context per GPU/rank, object Models (and their surfel stores) partitioned over the ranks
- *      (BASELINE.json north_star "Object Models ... shard one-per-GPU"; couplings per frame are exactly those of
- *      MaskFusion.cpp:274 (global pose -> static objects), GlobalProjection.cpp:66-95 (one depth-tested ID image) and
- *      MaskFusion.cpp:296-297 (one segmentation).  One frame on every rank =
- *          [broadcast rgb/depth/mask/classIDs]  mf_set_frame_classes; mf_shard_frame_begin;
- *          mf_shard_get_poses -> [all-gather] -> mf_shard_set_poses;
- *          mf_shard_project -> [all-reduce MIN over the uint64 keys at mf_shard_projection_keys] ;
- *          mf_shard_frame_end
- *      The collectives themselves run above this ABI (NCCL through torch.distributed, maskfusion_b200/sharding.py) on the
- *      context's stream.  With world == 1 the three calls are exactly mf_process_frame. ---- */
+ *      (BASELINE.json north_star "Object Models ... shard one-per-GPU"); the couplings of a frame are exactly those of
+ *      MaskFusion.cpp:212-217 (every model reads the frame), :257-276 (tracked poses decide inactivation; static objects follow the
+ *      global pose), GlobalProjection.cpp:66-95 (one depth-tested ID image) and MaskFusion.cpp:296-297 (one segmentation, evaluated
+ *      identically on every rank from the merged image).
+ *
+ *      (1) In-library exchange (the product path): after mf_shard_comm_init every rank calls mf_shard_process_frame once per frame;
+ *          only rank 0 passes inputs.  The library issues, on the context's stream and without any host synchronisation inside the
+ *          frame: ncclBroadcast of the frame packet (rgb | depth | mask | header, one buffer), ncclAllGather of the pose rows of the
+ *          tracked models, ncclAllReduce(ncclMin, ncclUint64) of the ID-projection keys.  libnccl.so.2 is opened at run time.
+ *          Bootstrap: rank 0 calls mf_shard_unique_id and distributes the 128 bytes by any side channel (the tests and bench.py use
+ *          torch.distributed's store); the communicator lives in the context.
+ *      (2) Transport-agnostic phases (tests over gloo, one GPU or none of the NCCL requirements): the caller moves the data itself
+ *              [frame to every rank]  mf_set_frame_classes; mf_shard_frame_begin;
+ *              mf_shard_get_poses -> [all-gather of 64 x 32 floats] -> mf_shard_set_poses;
+ *              mf_shard_project -> [MIN all-reduce of the uint64 keys at mf_shard_projection_keys];
+ *              mf_shard_frame_end
+ *      With world == 1 the three phase calls are exactly mf_process_frame. ---- */
 int mf_shard_configure(mf_context* ctx, int rank, int world);                 /* before the first frame; rank 0 owns the background model */
+int mf_shard_unique_id(uint8_t* out128);                                      /* ncclGetUniqueId (rank 0) */
+int mf_shard_comm_init(mf_context* ctx, const uint8_t* id128, int rank, int world);   /* ncclCommInitRank on the context's device (+ mf_shard_configure) */
+int mf_shard_process_frame(mf_context* ctx, const uint8_t* rgb, const float* depth, int64_t timestamp, const uint8_t* mask,
+                           const int32_t* class_ids, int n_class_ids, float weight_multiplier,
+                           int inputs_on_device);   /* inputs are read on rank 0 only (class_ids always from the host) */
+int mf_shard_stats(mf_context* ctx, int64_t* out4);                           /* collective bytes moved, NCCL calls, communicator size, NCCL version */
 int mf_shard_frame_begin(mf_context* ctx, const void* rgb, const void* depth, int64_t timestamp, const void* mask, int on_device);
-int mf_shard_get_poses(mf_context* ctx, float* out_nmodels_x32, int capacity_models);   /* returns nModels; row = pose(16) lastTransform(16), row-major; ghost rows = 0 */
-int mf_shard_set_poses(mf_context* ctx, const float* gathered_world_x_nmodels_x32);
-int mf_shard_project(mf_context* ctx);                                        /* lifecycle after tracking + local models into the key image */
+int mf_shard_get_poses(mf_context* ctx, float* out_64x32, int capacity_models);   /* returns nModels; row i = pose(16) lastTransform(16) of model i if it is tracked here, else 0 */
+int mf_shard_set_poses(mf_context* ctx, const float* gathered_world_x_64_x32);
+int mf_shard_project(mf_context* ctx);                                        /* device-side lifecycle after tracking + local models into the key image */
 void* mf_shard_projection_keys(mf_context* ctx);                              /* device pointer, width*height uint64 (depth bits << 32 | model index << 26 | surfel) */
 int mf_shard_frame_end(mf_context* ctx, float weight_multiplier);
 int mf_model_owner(mf_context* ctx, int i);                                   /* rank holding model i's surfels */
@@ -164,6 +183,7 @@ int mf_backbone_num_layers(mf_backbone* h);
 int mf_backbone_layer(mf_backbone* h, int i, int* cin_cout_k_stride_pad_kpad);
 int mf_backbone_get_weights(mf_backbone* h, int i, float* w_cout_kpad, float* bias);
 int mf_backbone_mold(mf_backbone* h, const void* d_rgba, int W, int H);            /* letter-box + mean subtraction -> network input */
+void* mf_backbone_stream(mf_backbone* h);   /* the cudaStream_t the backbone enqueues on */
 void* mf_backbone_input_buffer(mf_backbone* h);
 int mf_backbone_forward(mf_backbone* h, const void* d_input_nhwc_bf16);
 void* mf_backbone_output(mf_backbone* h, int level, int* dims_hwc);               /* 0..3 = C2..C5, 4..8 = P2..P6 (device, NHWC bf16) */
@@ -189,7 +209,8 @@ int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* mask, int32_
 void mf_dir_close(mf_dir* r);
 
 /* MaskFusion::exportPoses (Core/MaskFusion.cpp:849-881): writes <export_dir>poses-<model id>.txt for every active model
- * ("seconds x y z qx qy qz qw", fixed notation, 6 decimals); returns the number of files written. */
+ * and for every inactivated model the reference's keep rule retained (inactivateModel, MaskFusion.cpp:699-713: smart delete keeps a model
+ * with >= 4000 surfels and confidence threshold > 0.3) ("seconds x y z qx qy qz qw", fixed notation, 6 decimals); returns the number of files. */
 int mf_export_poses(mf_context* ctx, const char* export_dir);
 
 /* PLY export of one model's surfels as MaskFusion::savePly writes it (Core/MaskFusion.cpp:733-848): vertices with conf > threshold,

@@ -48,12 +48,12 @@ EXPORTS = [
     "mf_model_fuse", "mf_model_clean", "mf_model_combined_predict", "mf_model_init_from_frame",
     "mf_download_filtered_depth", "mf_download_frame_maps", "mf_download_model_maps", "mf_download_index_map",
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
-    "mf_download_edge_map", "mf_morph_close", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
+    "mf_download_edge_map", "mf_morph_close", "mf_debug_track_timing", "mf_attach_backbone", "mf_backbone_stream", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write", "mf_dir_open", "mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks", "mf_dir_set_max_masks", "mf_dir_size",
     "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_export_poses", "mf_generate_id_image", "mf_write_ply", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
-    "mf_shard_configure", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
+    "mf_shard_configure", "mf_shard_unique_id", "mf_shard_comm_init", "mf_shard_process_frame", "mf_shard_stats", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
     "mf_shard_projection_keys", "mf_shard_frame_end", "mf_model_owner", "mf_shard_pick_owner",
 ]
 
@@ -105,6 +105,9 @@ def load_library():
     L.mf_download_association.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_track_stats.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
     L.mf_download_edge_map.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.mf_debug_track_timing.argtypes = [C.c_void_p, C.c_int]
+    L.mf_attach_backbone.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.mf_backbone_stream.restype = C.c_void_p; L.mf_backbone_stream.argtypes = [C.c_void_p]
     L.mf_morph_close.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.mf_set_frame_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.mf_download_segmentation.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -146,6 +149,10 @@ def load_library():
     L.mf_backbone_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     L.mf_shard_configure.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.mf_shard_frame_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]
+    L.mf_shard_unique_id.argtypes = [C.c_void_p]
+    L.mf_shard_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.mf_shard_process_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
+    L.mf_shard_stats.argtypes = [C.c_void_p, C.c_void_p]
     L.mf_shard_get_poses.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     L.mf_shard_set_poses.argtypes = [C.c_void_p, C.c_void_p]
     L.mf_shard_project.argtypes = [C.c_void_p]
@@ -343,10 +350,18 @@ class MaskFusion:
                                          _p(mask), _p(ip), float(weightMultiplier), int(bootstrap)))
         return False
 
-    def processFramePtr(self, rgb_ptr: int, depth_ptr: int, timestamp: int = 0, on_device: bool = False):
-        """raw-pointer variant (pinned host or device memory), used by bench.py"""
+    def processFramePtr(self, rgb_ptr: int, depth_ptr: int, timestamp: int = 0, on_device: bool = False, mask_ptr: int = 0):
+        """raw-pointer variant (pinned host or device memory), used by bench.py; class ids through setFrameClasses"""
         fn = self.L.mf_process_frame_device if on_device else self.L.mf_process_frame
-        self._ck(fn(self.h, C.c_void_p(rgb_ptr), C.c_void_p(depth_ptr), int(timestamp), None, None, 1.0, 0))
+        self._ck(fn(self.h, C.c_void_p(rgb_ptr), C.c_void_p(depth_ptr), int(timestamp), C.c_void_p(mask_ptr) if mask_ptr else None, None, 1.0, 0))
+
+    def attachBackbone(self, backbone, every_k: int = 5):
+        """Mask R-CNN backbone on the frame path: every k-th processFrame enqueues mold + forward on the backbone's stream"""
+        self._ck(self.L.mf_attach_backbone(self.h, C.c_void_p(backbone.h) if backbone is not None else None, int(every_k)))
+
+    def setFrameClasses(self, classIDs):
+        c = np.ascontiguousarray(classIDs, np.int32)
+        self._ck(self.L.mf_set_frame_classes(self.h, c.ctypes.data_as(C.c_void_p), int(c.shape[0])))
 
     def setFrame(self, rgb, depth, mask=None):
         self._ck(self.L.mf_set_frame(self.h, _p(np.ascontiguousarray(rgb)), _p(np.ascontiguousarray(depth)), _p(mask)))

@@ -34,6 +34,7 @@ SOURCES = {
     "mf_seg.cu": ["-fmad=false"],
     "mf_track.cu": ["-fmad=false"],
     "mf_host.cu": ["-fmad=false"],
+    "mf_sched.cu": ["-fmad=false"],       # device-side lifecycle of the multi-model schedule + the NCCL exchange (libnccl via dlopen)
     "mf_capi.cu": ["-fmad=false"],
     "mf_jpeg.cu": [],                     # host code only: baseline JPEG decode, libjpeg's default path restated
     "mf_loader.cu": [],                   # host code only: image-directory loader (PNG/PNM decode, zlib)
@@ -79,7 +80,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             os.remove(os.path.join(OBJ_DIR, f))
     with ThreadPoolExecutor(max_workers=6) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), SOURCES))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lz", "-lcudart"]
+    cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lz", "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

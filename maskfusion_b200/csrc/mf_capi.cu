@@ -155,7 +155,11 @@ extern "C" int mf_export_poses(mf_context* ctx, const char* export_dir)
     if (!export_dir) { g_err = "export_poses: null directory"; return -2; }
     ctx->mf->sync();
     int written = 0;
-    for (auto& m : ctx->mf->models) {
+    // active models, then the inactivated ones the keep rule retained (MaskFusion.cpp:849-881 walks models and inactiveModels)
+    std::vector<Model*> all;
+    for (auto& m : ctx->mf->models) all.push_back(m.get());
+    for (auto& m : ctx->mf->inactiveModels) all.push_back(m.get());
+    for (Model* m : all) {
         const std::string filename = std::string(export_dir) + "poses-" + std::to_string((int)m->id) + ".txt";
         FILE* fp = fopen(filename.c_str(), "w");
         if (!fp) { g_err = "cannot write " + filename; return -3; }
@@ -341,13 +345,25 @@ extern "C" int mf_morph_close(mf_context* ctx, uint8_t* image, int radius, int i
     MaskFusion* o = ctx->mf;
     DevBuf<uint8_t> a, b, c; a.alloc(o->P); b.alloc(o->P); c.alloc(o->P);
     cudaCheck(cudaMemcpyAsync(a.p, image, o->P, cudaMemcpyHostToDevice, o->stream), "H2D");
-    if (ellipse) o->launches += launch_morph_close_ellipse(a, b, o->W, o->H, radius, iterations, o->stream);
+    if (ellipse) o->launches += launch_morph_close_ellipse(a, b, o->W, o->H, radius, iterations, nullptr, o->stream);
     else { launch_morph_close_invert(a, b, o->W, o->H, radius, iterations, c, o->stream); o->launches += 1 + 2 * iterations; }
     d2h(o, image, a.p, o->P);
     if (inverted && !ellipse) d2h(o, inverted, c.p, o->P);
     o->sync(); return 0;
     MF_CATCH(-1)
 }
+
+// Mask R-CNN backbone on the frame path: every k-th processFrame enqueues mold_inputs + the ResNet-101-FPN forward of `backbone`
+// (mf_backbone_create) on the backbone's own stream (MaskRCNN::executeSequential is called from MfSegmentation.cpp:130). NULL detaches.
+extern "C" int mf_attach_backbone(mf_context* ctx, void* backbone, int every_k)
+{
+    MF_TRY MF_NEED(ctx)
+    ctx->mf->attachBackbone(backbone, every_k); return 0;
+    MF_CATCH(-1)
+}
+
+// stage clock of the last tracking launch: (tag, SM clock) pairs; 0 unless the library was built with -DMF_TRACK_TIMING (A/B builds)
+extern "C" int mf_debug_track_timing(int64_t* out, int cap) { return debug_track_timing((long long*)out, cap); }
 
 extern "C" int mf_set_frame_classes(mf_context* ctx, const int32_t* class_ids, int n)
 {
@@ -379,10 +395,46 @@ extern "C" int mf_shard_frame_begin(mf_context* ctx, const void* rgb, const void
 extern "C" int mf_shard_get_poses(mf_context* ctx, float* out, int capacity_models)
 {
     MF_TRY MF_NEED(ctx)
-    if ((int)ctx->mf->models.size() > capacity_models) { g_err = "get_poses: buffer too small"; return -2; }
+    if (capacity_models < MF_MAX_MODELS) { g_err = "get_poses: the buffer must hold 64 rows of 32 floats"; return -2; }
     ctx->mf->getShardPoses(out);
     return (int)ctx->mf->models.size();
     MF_CATCH(-1)
+}
+extern "C" int mf_shard_unique_id(uint8_t* out128)
+{
+    MF_TRY
+    if (!out128) { g_err = "null buffer"; return -1; }
+    shardUniqueId(out128); return 0;
+    MF_CATCH(-1)
+}
+extern "C" int mf_shard_comm_init(mf_context* ctx, const uint8_t* id128, int rank, int world)
+{
+    MF_TRY MF_NEED(ctx)
+    if (!id128) { g_err = "null id"; return -1; }
+    ctx->mf->initShardComm(id128, rank, world); return 0;
+    MF_CATCH(-1)
+}
+extern "C" int mf_shard_process_frame(mf_context* ctx, const uint8_t* rgb, const float* depth, int64_t ts, const uint8_t* mask, const int32_t* class_ids,
+                                      int n_class_ids, float weight_multiplier, int inputs_on_device)
+{
+    MF_TRY MF_NEED(ctx)
+    MaskFusion* o = ctx->mf;
+    if (!o->shardNccl) { g_err = "mf_shard_process_frame needs a communicator (mf_shard_comm_init)"; return -2; }
+    if (o->rank == 0) {
+        if (!rgb || !depth || ts < 0) { g_err = "processFrame: rgb/depth must be non-null and timestamp >= 0 on the loader rank"; return -3; }
+        if (n_class_ids < 0 || n_class_ids > 256) { g_err = "class id list must have 0..256 entries"; return -3; }
+        o->setFrameClasses(class_ids, class_ids ? n_class_ids : 0);
+    }
+    o->processFrame(rgb, depth, ts, mask, nullptr, weight_multiplier, false, inputs_on_device != 0);
+    return 0;
+    MF_CATCH(-1)
+}
+extern "C" int mf_shard_stats(mf_context* ctx, int64_t* out4)
+{
+    if (!ctx || !ctx->mf || !out4) { g_err = "null argument"; return -1; }
+    MaskFusion* o = ctx->mf;
+    out4[0] = (int64_t)o->shard.bytesMoved; out4[1] = o->shard.calls; out4[2] = o->shardNccl ? o->shard.world : 0; out4[3] = o->shard.version;
+    return 0;
 }
 extern "C" int mf_shard_set_poses(mf_context* ctx, const float* gathered) { MF_TRY MF_NEED(ctx) ctx->mf->setShardPoses(gathered); return 0; MF_CATCH(-1) }
 extern "C" int mf_shard_project(mf_context* ctx) { MF_TRY MF_NEED(ctx) ctx->mf->frameProject(); return 0; MF_CATCH(-1) }

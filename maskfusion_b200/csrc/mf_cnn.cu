@@ -625,6 +625,7 @@ extern "C" int mf_backbone_forward(mf_backbone* h, const void* d_input)
 extern "C" double mf_backbone_flops(mf_backbone* h) { return h ? h->b.flops : 0; }
 extern "C" int mf_backbone_num_gemms(mf_backbone* h) { return h ? h->b.gemms : 0; }
 extern "C" void* mf_backbone_input_buffer(mf_backbone* h) { return h ? h->b.input : nullptr; }
+extern "C" void* mf_backbone_stream(mf_backbone* h) { return h ? (void*)h->stream : nullptr; }
 // level 0..3 = C2..C5, 4..8 = P2..P6; returns device pointer, fills dims (H, W, C)
 extern "C" void* mf_backbone_output(mf_backbone* h, int level, int* dims3)
 {

@@ -278,7 +278,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     ownStream = (st == nullptr);
     if (ownStream) cudaCheck(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking), "cudaStreamCreate"); else stream = st;
     g_prof = &prof;
-    for (int k = 0; k < 2; ++k) { rgb3Buf[k].alloc((size_t)P * 3); rgbBuf[k].alloc(P); depthRawBuf[k].alloc(P); depthFiltBuf[k].alloc(P); }
+    for (int k = 0; k < 2; ++k) { inBuf[k].alloc(packetBytes()); inBuf[k].zero(stream); rgbBuf[k].alloc(P); depthFiltBuf[k].alloc(P); }
     selectSet(0);
     mask.alloc(P); mask.zero(stream);
     cudaCheck(cudaStreamCreateWithFlags(&preStream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -296,14 +296,21 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     scratch.alloc((size_t)P * 4);
     rayTab.alloc(P); launch_ray_table(cam, W, H, rayTab, stream);
     if (c.enableMultipleModels) {
-        frameMask.alloc(P); frameMask.zero(stream);
+        dRes.alloc(1); dRes.zero(stream);
+        cudaCheck(cudaMallocHost((void**)&hRes, sizeof(FrameResult)), "cudaMallocHost"); memset(hRes, 0, sizeof(FrameResult));
+        cudaCheck(cudaEventCreateWithFlags(&resEvt, cudaEventDisableTiming), "cudaEventCreate");
+        poseTable.alloc((size_t)MF_MAX_MODELS * 32); poseTable.zero(stream);
+        gathered.alloc((size_t)64 * MF_MAX_MODELS * 32); gathered.zero(stream);
+        // component histograms for the worst case (every second pixel its own component): the counts of a frame live on the device
+        compModel.alloc(((size_t)P / 2 + 2) * MF_MAX_MODELS); compMask.alloc(((size_t)P / 2 + 2) * 256);
         projKeys.alloc(P); launch_fill_u64(projKeys, KEY_EMPTY, P, stream); projectedIDs.alloc(P); projectedIDs.zero(stream);
         ccL.alloc(P); ccDense.alloc(P); ccLabA.alloc(P); ccLabB.alloc(P); ccArea.alloc((size_t)P + 1); mapToMask.alloc((size_t)P / 2 + 2); absorbId.alloc((size_t)P / 2 + 2);
-        maskPixels.alloc(256); ccCounter.alloc(1); maskOverlap.alloc(64 * 256);
+        maskPixels.alloc(256); ccCounter.alloc(1); ccCounter.zero(stream);
         segTmp.alloc(P); ignoreMap.alloc(P); ignoreMap.zero(stream);
         tblIdToIndex.alloc(256); tblIndexToId.alloc(256); tblIsModel.alloc(256); tblMaskToID.alloc(256); tblIsPerson.alloc(256);
-        cudaCheck(cudaMallocHost((void**)&hSmall, (64 * 256 + 1024) * sizeof(uint32_t)), "cudaMallocHost");
-        memset(maskToID, 0, sizeof maskToID); maskToID[255] = 255;                             // MfSegmentation.cpp:70-71
+        tblIdToIndex.zero(stream); tblIndexToId.zero(stream); tblIsModel.zero(stream); tblIsPerson.zero(stream);
+        tblMaskToID.zero(stream); cudaCheck(cudaMemsetAsync(tblMaskToID.p + 255, 255, 1, stream), "memset");   // maskToID[255] = 255, MfSegmentation.cpp:70-71 (persists across frames)
+        maskOverlap.alloc((size_t)MF_MAX_MODELS * 256);
     }
     models.emplace_back(new Model(this, nextID++, c.confGlobal, true, c.capacityGlobal));    // MaskFusion.cpp:80-81
     sync();
@@ -319,8 +326,12 @@ MaskFusion::~MaskFusion()
     if (preDone) cudaEventDestroy(preDone);
     if (inputsCopied) cudaEventDestroy(inputsCopied);
     models.clear();
+    inactiveModels.clear();
     if (hJobs) cudaFreeHost(hJobs);
-    if (hSmall) cudaFreeHost(hSmall);
+    if (hRes) cudaFreeHost(hRes);
+    if (resEvt) cudaEventDestroy(resEvt);
+    if (bbFrameReady) cudaEventDestroy(bbFrameReady);
+    if (bbMoldDone) cudaEventDestroy(bbMoldDone);
     if (ownStream) cudaStreamDestroy(stream);
 }
 
@@ -332,8 +343,8 @@ void MaskFusion::sync()
     finalisePending();
 }
 
-// textureRGB / textureDepthMetric upload + filterDepth (MaskFusion.cpp:212-217, 650-657)
-void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint8_t* maskIn, bool onDevice, cudaStream_t s)
+// textureRGB / textureDepthMetric (+ FrameData::mask, classIDs) upload into the current input set (MaskFusion.cpp:212-217)
+void MaskFusion::uploadInputs(const uint8_t* rgbIn, const float* depthIn, const uint8_t* maskIn, int64_t timestamp, bool onDevice, cudaStream_t s)
 {
     if (!s) s = stream;
     cudaMemcpyKind kind = onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -342,16 +353,43 @@ void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint
     if (onDevice && inputReady) { cudaCheck(cudaStreamWaitEvent(s, inputReady, 0), "cudaStreamWaitEvent"); inputReady = nullptr; }   // caller's producer
     cudaCheck(cudaMemcpyAsync(rgb3, rgbIn, (size_t)P * 3, kind, s), "rgb upload");
     cudaCheck(cudaMemcpyAsync(depthRaw, depthIn, (size_t)P * sizeof(float), kind, s), "depth upload");
-    if (maskIn) cudaCheck(cudaMemcpyAsync(mask, maskIn, (size_t)P, kind, s), "mask upload");
+    if (cfg.enableMultipleModels) {
+        // instance masks + their class list ride with the images: the header is a kernel argument (no staging buffer to keep alive)
+        FrameHdr h; memset(&h, 0, sizeof h);
+        h.timestamp = timestamp;
+        if (maskIn && !classIDs.empty()) {
+            if (classIDs.size() > 256) throw CudaError{"more than 256 mask labels"};
+            cudaCheck(cudaMemcpyAsync(frameMask, maskIn, (size_t)P, kind, s), "mask upload");
+            h.nMasks = (int)classIDs.size();
+            for (size_t i = 0; i < classIDs.size(); ++i) h.classIDs[i] = classIDs[i];
+        }
+        launch_frame_header(h, dHdr, s);
+        launches += 1;
+    }
     // host inputs belong to the caller again when processFrame returns (the reference uploads synchronously): see processFrame.
     // Device inputs copied on the pre-processing stream: the context stream waits for the copies, so whatever the caller queues
     // there after this call (e.g. the producer of the next frame writing the same buffers) is ordered behind them.
     if (!onDevice) { cudaCheck(cudaEventRecord(inputsCopied, s), "cudaEventRecord"); copyPending = true; }
     else if (s != stream) { cudaCheck(cudaEventRecord(inputsCopied, s), "cudaEventRecord"); cudaCheck(cudaStreamWaitEvent(stream, inputsCopied, 0), "cudaStreamWaitEvent"); }
+}
+
+// filterDepth (MaskFusion.cpp:650-657) + the RGBA copy every later pass reads
+void MaskFusion::preprocess(cudaStream_t s)
+{
+    if (!s) s = stream;
     launch_unpack_rgb(rgb3, rgb, P, s);
     launch_bilateral(depthRaw, depthFilt, W, H, s);
     launches += 2;
     frameMapsValid = false; intensityValid = false;
+}
+
+void MaskFusion::setFrame(const uint8_t* rgbIn, const float* depthIn, const uint8_t* maskIn, bool onDevice, cudaStream_t s)
+{
+    if (!s) s = stream;
+    // stage-wise test entry (mf_set_frame): the optional mask goes straight into textureMask like the reference's upload
+    if (maskIn) cudaCheck(cudaMemcpyAsync(mask, maskIn, (size_t)P, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s), "mask upload");
+    uploadInputs(rgbIn, depthIn, nullptr, 0, onDevice, s);
+    preprocess(s);
 }
 
 // Model::generateCUDATextures (Model.cpp:350-389): level 0 aliases the filtered depth.
@@ -386,8 +424,10 @@ void MaskFusion::frameIntensity(cudaStream_t s)
     intensityValid = true;
 }
 
-// Model::performTracking for a batch of models: one launch sequence, blockIdx.y = model
-void MaskFusion::trackModels(const std::vector<Model*>& ms)
+// Model::performTracking for a batch of models: one launch sequence, blockIdx.y = model.
+// viaResult: the multi-model schedule reads the tracked poses back inside the frame's FrameResult (applyFrameResult) instead of the
+// -static path's dedicated copy behind the tracking kernel.
+void MaskFusion::trackModels(const std::vector<Model*>& ms, bool viaResult)
 {
     if (ms.empty()) return;
     if ((int)ms.size() > TRACK_MAX_JOBS) throw CudaError{"too many tracked models for one batch"};
@@ -396,7 +436,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
     if ((rgbTerm || cfg.so3) && !intensityValid) frameIntensity();
     for (size_t j = 0; j < ms.size(); ++j) {
         Model* m = ms[j];
-        m->lastPose = m->pose;                                       // Model.cpp:430
+        if (!viaResult) m->lastPose = m->pose;                       // Model.cpp:430 (multi-model: applied with the result)
         m->prepareTracking();
         TrackJob& J = hJobs[j];
         for (int l = 0; l < 3; ++l) {
@@ -412,22 +452,26 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms)
         preWaitPending = false;
     }
     prof_mark(stream, "copy_jobs");
+    // hJobs is reused every frame: the next frameBegin first waits (finalisePending) for an event recorded behind this copy
     cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
     launches += launch_tracking(dJobs, (int)ms.size(), W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
                                 cfg.so3 != 0, numSMs, trackBars, stream);
     prof_mark(stream, "copy_pose_d2h");
     for (Model* m : ms) {
-        cudaCheck(cudaMemcpyAsync(m->hTrackOut, (const char*)m->trackState.p + offsetof(TrackState, out), 40 * sizeof(float),
-                                  cudaMemcpyDeviceToHost, stream), "pose D2H");
+        if (!viaResult)
+            cudaCheck(cudaMemcpyAsync(m->hTrackOut, (const char*)m->trackState.p + offsetof(TrackState, out), 40 * sizeof(float),
+                                      cudaMemcpyDeviceToHost, stream), "pose D2H");
         if (cfg.so3)   // std::swap(lastNextImage, nextImage) (RGBDOdometry.cpp:484-488): only level 2 is ever read
             cudaCheck(cudaMemcpyAsync(m->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "so3 swap");
     }
+    if (viaResult) return;
     if (!trackDone) cudaCheck(cudaEventCreateWithFlags(&trackDone, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventRecord(trackDone, stream), "cudaEventRecord");
     pendingModels = ms; pendingTrack = true;
 }
 
-// host copies of the tracked poses: waits for the event behind the tracking kernel only, not for the rest of the frame
+// host copies of the tracked poses (and, multi-model, of everything else a frame decides): waits for an event that lies MID-frame
+// (behind the tracking kernel / the vote kernel), not for the rest of the frame
 void MaskFusion::finalisePending()
 {
     if (pendingTrack) {
@@ -438,6 +482,7 @@ void MaskFusion::finalisePending()
         }
         pendingTrack = false; pendingModels.clear();
     }
+    if (pendingResult) applyFrameResult();
     if (pendingLog) { pendingLog = false; logPoses(pendingTimestamp); }
 }
 
@@ -462,12 +507,22 @@ void MaskFusion::predict()
 
 // GlobalProjection::project (GlobalProjection.cpp:43-107): all models into one depth-tested key image; the key's low word
 // is (model list index << 26 | surfel id), i.e. the reference's draw order.  The ID image stays on the device.
-void MaskFusion::globalProjection() { projectLocal(); projectResolve(); }
+void MaskFusion::globalProjection() { segTables(); projectLocal(); projectResolve(); }
+
+// id <-> list-index tables of this frame's model list, as a kernel argument (no staging buffer, no synchronisation)
+void MaskFusion::segTables()
+{
+    if (models.size() > MF_MAX_MODELS - 1) throw CudaError{"global projection / segmentation support up to 63 models"};
+    SegTables t; memset(&t, 0, sizeof t);
+    for (size_t i = 0; i < models.size(); ++i) { t.idToIndex[models[i]->id] = (uint8_t)i; t.indexToId[i] = models[i]->id; t.isModel[models[i]->id] = 1; }
+    launch_seg_tables(t, tblIdToIndex, tblIndexToId, tblIsModel, stream);
+    launches += 1;
+}
 
 // local half: every model whose surfels live here goes into the key image (ghost models arrive through the min all-reduce)
 void MaskFusion::projectLocal()
 {
-    if (models.size() > 63) throw CudaError{"global projection supports up to 63 models"};
+    if (models.size() > MF_MAX_MODELS - 1) throw CudaError{"global projection supports up to 63 models"};
     for (size_t i = 0; i < models.size(); ++i) {
         Model* m = models[i].get();
         if (!m->owned) continue;
@@ -479,95 +534,48 @@ void MaskFusion::projectLocal()
 
 void MaskFusion::projectResolve()
 {
-    uint8_t idx2id[256]; memset(idx2id, 0, sizeof idx2id);
-    for (size_t i = 0; i < models.size(); ++i) idx2id[i] = models[i]->id;
-    memcpy(hSmall, idx2id, 256);
-    cudaCheck(cudaMemcpyAsync(tblIndexToId, hSmall, 256, cudaMemcpyHostToDevice, stream), "tbl upload");
-    sync();      // hSmall is reused below
     launch_proj_resolve(projKeys, P, tblIndexToId, projectedIDs, stream);
     launches += 1;
 }
 
-// MfSegmentation::performSegmentation (MfSegmentation.cpp:83-538) with the CPU tail on the GPU (mf_seg.cu).
-MaskFusion::SegmentationResult MaskFusion::performSegmentation(bool allowNew)
+// MfSegmentation::performSegmentation (MfSegmentation.cpp:83-538) with the CPU tail on the GPU (mf_seg.cu) and NO host round trip:
+// the number of components, the number of masks and their classes are read by the kernels from device memory; the mask -> model vote
+// (:433-492) is a kernel; its decision (new label?) travels to the host inside the FrameResult and is applied by applyFrameResult().
+void MaskFusion::performSegmentation(bool allowNew)
 {
-    SegmentationResult res;
-    const int nMasks = frameHasMask ? (int)classIDs.size() : 0;
     const int nModels = (int)models.size();
-    if (nMasks > 256) throw CudaError{"more than 256 mask labels"};
     if (!frameMapsValid) generateCUDATextures();
     // edge-ness -> threshold -> close -> invert (MfSegmentation.cpp:149-208)
     launch_geometric_edges(vmap[0], nmap[0], W, H, cfg.segWeightDistance, cfg.segWeightConvexity, cfg.segThreshold, edgeMap, edgeBinary, stream);
     launch_morph_close_invert(edgeBinary, edgeBuf, W, H, cfg.segMorphEdgeRadius, cfg.segMorphEdgeIterations, edgeInv, stream);
     launches += 2 + 2 * cfg.segMorphEdgeIterations;
-    // small tables
-    uint8_t* t = (uint8_t*)hSmall;
-    uint8_t* id2idx = t, *idx2id = t + 256, *isModel = t + 512, *isPerson = t + 768;
-    memset(t, 0, 1024);
-    for (int i = 0; i < nModels; ++i) { id2idx[models[i]->id] = (uint8_t)i; idx2id[i] = models[i]->id; isModel[models[i]->id] = 1; }
-    bool anyPerson = false;
-    for (int m = 0; m < nMasks; ++m) if (classIDs[m] == personClassID) { isPerson[m] = 1; anyPerson = true; }
-    cudaCheck(cudaMemcpyAsync(tblIdToIndex, id2idx, 256, cudaMemcpyHostToDevice, stream), "tbl");
-    cudaCheck(cudaMemcpyAsync(tblIndexToId, idx2id, 256, cudaMemcpyHostToDevice, stream), "tbl");
-    cudaCheck(cudaMemcpyAsync(tblIsModel, isModel, 256, cudaMemcpyHostToDevice, stream), "tbl");
-    cudaCheck(cudaMemcpyAsync(tblIsPerson, isPerson, 256, cudaMemcpyHostToDevice, stream), "tbl");
     // ignore map (:221-235)
-    launch_apply_ignore(frameMask, tblIsPerson, nMasks, P, ignoreMap, edgeInv, stream);
-    (void)anyPerson;
+    launch_person_table(dHdr, personClassID, tblIsPerson, stream);
+    launch_apply_ignore(frameMask, tblIsPerson, dHdr, P, ignoreMap, edgeInv, stream);
     // connected components + 5 edge-removal sweeps (:238-291)
     launch_cc(edgeInv, W, H, ccL, ccDense, ccLabA, ccArea, ccCounter, stream);
     launch_remove_edges(ccLabA, ccLabB, depthRaw, ccArea, W, H, 5, stream);
     int* lab = ccLabB;                                     // odd number of sweeps ends in B
-    launches += 10;
-    cudaCheck(cudaMemcpyAsync(hSmall + 512, ccCounter, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream), "ncomp D2H");
-    sync();
-    const int nComponents = (int)hSmall[512] + 1;
     // overlap histograms (:303-346)
-    if (compModel.n < (size_t)nComponents * nModels) compModel.alloc((size_t)nComponents * nModels * 2);
-    if (nMasks && compMask.n < (size_t)nComponents * nMasks) compMask.alloc((size_t)nComponents * nMasks * 2);
-    cudaCheck(cudaMemsetAsync(compModel, 0, (size_t)nComponents * nModels * sizeof(int), stream), "memset");
-    if (nMasks) cudaCheck(cudaMemsetAsync(compMask, 0, (size_t)nComponents * nMasks * sizeof(int), stream), "memset");
+    launch_clear_hist(ccCounter, dHdr, nModels, compModel, compMask, stream);
     maskPixels.zero(stream);
-    launch_seg_hist(lab, projectedIDs, frameMask, P, tblIdToIndex, nModels, nMasks, compModel, compMask, stream);
-    launch_component_map(nComponents, ccArea, compModel, compMask, nModels, nMasks, tblIndexToId, minMappedComponentSize, mapToMask, absorbId, maskPixels, stream);
+    launch_seg_hist(lab, projectedIDs, frameMask, P, tblIdToIndex, nModels, dHdr, compModel, compMask, stream);
+    launch_component_map(ccCounter, ccArea, compModel, compMask, nModels, dHdr, tblIndexToId, minMappedComponentSize, mapToMask, absorbId, maskPixels, stream);
     launch_seg_assign(lab, mapToMask, ignoreMap, P, segTmp, stream);
-    launches += 3;
-    if (nMasks) {
-        // closing of the mask-id image with an elliptic element (:424-426); edgeBuf is free again at this point
-        launches += launch_morph_close_ellipse(segTmp, edgeBuf, W, H, cfg.segMorphMaskRadius, cfg.segMorphMaskIterations, stream);
-        // mask -> model vote (:433-492): two small tables to the host
-        if ((size_t)nModels * 256 > maskOverlap.n) maskOverlap.alloc((size_t)nModels * 256);
-        maskOverlap.zero(stream);
-        launch_mask_overlap(segTmp, projectedIDs, tblIdToIndex, tblIsModel, P, maskOverlap, stream);
-        launches += 1;
-        cudaCheck(cudaMemcpyAsync(hSmall, maskPixels, 256 * sizeof(int), cudaMemcpyDeviceToHost, stream), "D2H");
-        cudaCheck(cudaMemcpyAsync(hSmall + 256, maskOverlap, (size_t)nModels * 256 * sizeof(unsigned), cudaMemcpyDeviceToHost, stream), "D2H");
-        sync();
-        const int* maskComponentPixels = (const int*)hSmall;
-        const unsigned* ov = (const unsigned*)(hSmall + 256);
-        const size_t total = (size_t)P;
-        const size_t minNew = (size_t)(cfg.minRelSizeNew * total), maxNew = (size_t)(cfg.maxRelSizeNew * total);
-        const unsigned char nextModelID = getNextModelID(false);
-        for (int midx = 1; midx < nMasks; ++midx) { maskToID[midx] = 0; if (classIDs[midx] == personClassID) maskToID[midx] = 255; }
-        for (int midx = 1; midx < nMasks; ++midx) {
-            if (maskToID[midx] == 255) continue;
-            int bestModelIndex = 0; unsigned bestOverlap = 0;
-            const int maskClassID = classIDs[midx];
-            for (int j = 1; j < nModels; ++j) { unsigned o = ov[(size_t)j * 256 + midx]; if (o > bestOverlap) { bestOverlap = o; bestModelIndex = j; } }
-            const bool matches = models[bestModelIndex]->classID == maskClassID;
-            if (bestOverlap < minMaskModelOverlap * maskComponentPixels[midx]) bestModelIndex = 0;
-            if (bestModelIndex != 0 && matches) maskToID[midx] = models[bestModelIndex]->id;
-            else if (!res.hasNewLabel && allowNew && (size_t)maskComponentPixels[midx] > minNew && (size_t)maskComponentPixels[midx] < maxNew && bestModelIndex == 0) {
-                maskToID[midx] = nextModelID; res.hasNewLabel = true; res.newClassID = maskClassID;
-            } else maskToID[midx] = 255;
-        }
-    }
-    memcpy(hSmall, maskToID, 256);
-    cudaCheck(cudaMemcpyAsync(tblMaskToID, hSmall, 256, cudaMemcpyHostToDevice, stream), "tbl");
+    launches += 16;
+    // closing of the mask-id image with an elliptic element (:424-426, inside `if (nMasks)`); edgeBuf is free again at this point
+    launches += launch_morph_close_ellipse(segTmp, edgeBuf, W, H, cfg.segMorphMaskRadius, cfg.segMorphMaskIterations, dHdr, stream);
+    // mask -> model vote (:433-492)
+    cudaCheck(cudaMemsetAsync(maskOverlap, 0, (size_t)nModels * 256 * sizeof(unsigned), stream), "memset");
+    launch_mask_overlap(segTmp, projectedIDs, tblIdToIndex, tblIsModel, P, maskOverlap, stream);
+    VoteParams vp; memset(&vp, 0, sizeof vp);
+    vp.nModels = nModels; vp.allowNew = allowNew ? 1 : 0; vp.personClassID = personClassID;
+    vp.minNew = (unsigned)(size_t)(cfg.minRelSizeNew * (size_t)P); vp.maxNew = (unsigned)(size_t)(cfg.maxRelSizeNew * (size_t)P);
+    vp.minMaskModelOverlap = minMaskModelOverlap; vp.nextModelID = getNextModelID(false);
+    for (int i = 0; i < nModels; ++i) { vp.modelClass[i] = models[i]->classID; vp.modelID[i] = models[i]->id; }
+    launch_vote(dHdr, vp, maskPixels, maskOverlap, ccCounter, tblMaskToID, dRes, stream);
     launch_seg_final(segTmp, lab, mapToMask, absorbId, tblMaskToID, P, mask, stream);      // writes textureMask directly (:297)
-    launches += 1;
-    sync();                                                                                  // hSmall reused by the next stage
-    return res;
+    launches += 3;
 }
 
 // MaskFusion::getNextModelID (MaskFusion.cpp:712-730)
@@ -629,34 +637,79 @@ void MaskFusion::configureShard(int rank_, int world_)
     }
 }
 
-// [nModels][32] row-major pose + lastTransform of the models tracked here
-void MaskFusion::getShardPoses(float* out) const
+// communicator of the shards (mf_shard_comm_init): from here on the three exchanges of a frame are NCCL calls on the context's stream
+void MaskFusion::initShardComm(const unsigned char* id128, int rank_, int world_)
 {
-    for (size_t i = 0; i < models.size(); ++i) {
-        const Model* m = models[i].get();
-        if (m->owned) { memcpy(out + i * 32, m->pose.m, 64); memcpy(out + i * 32 + 16, m->lastTransform.m, 64); }
-        else memset(out + i * 32, 0, 128);
+    if (world == 1 && world_ > 1) configureShard(rank_, world_);
+    if (rank_ != rank || world_ != world) throw CudaError{"initShardComm: rank / world differ from configureShard"};
+    cudaCheck(cudaSetDevice(device), "cudaSetDevice");
+    shard.init(id128, rank_, world_);
+    shardNccl = true;
+}
+
+extern "C" int mf_backbone_mold(struct mf_backbone* h, const void* d_rgba, int W, int H);
+extern "C" int mf_backbone_forward(struct mf_backbone* h, const void* d_input);
+extern "C" void* mf_backbone_input_buffer(struct mf_backbone* h);
+extern "C" void* mf_backbone_stream(struct mf_backbone* h);
+
+void MaskFusion::attachBackbone(void* bb, int everyK)
+{
+    backbone = bb; backboneEvery = bb ? (everyK > 0 ? everyK : 1) : 0;
+    if (bb && !bbFrameReady) {
+        cudaCheck(cudaEventCreateWithFlags(&bbFrameReady, cudaEventDisableTiming), "cudaEventCreate");
+        cudaCheck(cudaEventCreateWithFlags(&bbMoldDone, cudaEventDisableTiming), "cudaEventCreate");
     }
 }
 
+// every k-th frame: RGBA image of this frame -> letter-boxed network input -> backbone forward, all on the backbone's stream
+void MaskFusion::runBackbone()
+{
+    if (!backbone || backboneEvery <= 0 || (tick % backboneEvery) != 0) return;
+    mf_backbone* bb = (mf_backbone*)backbone;
+    cudaStream_t bs = (cudaStream_t)mf_backbone_stream(bb);
+    cudaCheck(cudaEventRecord(bbFrameReady, stream), "cudaEventRecord");            // the RGBA copy of this frame exists
+    cudaCheck(cudaStreamWaitEvent(bs, bbFrameReady, 0), "cudaStreamWaitEvent");
+    if (mf_backbone_mold(bb, rgb, W, H) != 0) throw CudaError{"backbone: mold_inputs failed"};
+    cudaCheck(cudaEventRecord(bbMoldDone, bs), "cudaEventRecord");                   // the frame's image is free again once the input is molded
+    bbMoldPending = true;
+    if (mf_backbone_forward(bb, mf_backbone_input_buffer(bb)) != 0) throw CudaError{"backbone: forward failed"};
+}
+
+// the models of the frame in flight as the lifecycle kernels see them
+LifeParams MaskFusion::lifeParams() const
+{
+    LifeParams lp; memset(&lp, 0, sizeof lp);
+    if (models.size() > MF_MAX_MODELS) throw CudaError{"more than 64 models"};
+    lp.nModels = (int)models.size(); lp.rank = rank;
+    for (size_t i = 0; i < models.size(); ++i) {
+        const Model* m = models[i].get();
+        LifeModel& L = lp.m[i];
+        L.tracked = m->tracked ? 1 : 0; L.owned = m->owned ? 1 : 0; L.ownerRank = m->ownerRank;
+        if (m->owned) {
+            L.dpose = m->dpose.p; L.count = m->dCount();
+            L.trackOut = reinterpret_cast<const float*>(reinterpret_cast<const char*>(m->trackState.p) + offsetof(TrackState, out));
+        }
+        memcpy(L.initialC2Winv, m->initialC2Winv.m, sizeof L.initialC2Winv);
+    }
+    return lp;
+}
+
+// external transport (no NCCL communicator): this rank's rows to the host / the gathered rows of all ranks back to the device
+void MaskFusion::getShardPoses(float* out)
+{
+    cudaCheck(cudaMemcpyAsync(out, poseTable.p, (size_t)MF_MAX_MODELS * 32 * sizeof(float), cudaMemcpyDeviceToHost, stream), "rows D2H");
+    cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
+}
 void MaskFusion::setShardPoses(const float* all)
 {
-    const size_t n = models.size();
-    for (size_t i = 0; i < n; ++i) {
-        Model* m = models[i].get();
-        if (m->owned) continue;
-        const bool tracked = i == 0 || m->nonstatic || cfg.trackAllModels;
-        if (!tracked) continue;                                        // static objects are re-posed from the background pose below
-        const float* row = all + ((size_t)m->ownerRank * n + i) * 32;
-        m->lastPose = m->pose;
-        memcpy(m->pose.m, row, 64); memcpy(m->lastTransform.m, row + 16, 64);
-    }
+    cudaCheck(cudaMemcpyAsync(gathered.p, all, (size_t)world * MF_MAX_MODELS * 32 * sizeof(float), cudaMemcpyHostToDevice, stream), "rows H2D");
+    cudaCheck(cudaStreamSynchronize(stream), "cudaStreamSynchronize");
 }
 
 bool MaskFusion::processFrame(const uint8_t* rgbIn, const float* depthIn, int64_t timestamp, const uint8_t* maskIn, const Mat4* inPose,
                               float weightMultiplier, bool bootstrap, bool onDevice)
 {
-    if (world > 1) throw CudaError{"processFrame: this context is one shard of several; drive it through the frame_begin/project/end phases"};
+    if (world > 1 && !shardNccl) throw CudaError{"processFrame: this context is one shard of several without a communicator; call mf_shard_comm_init, or drive the frame_begin/project/end phases and move the rows / keys yourself"};
     frameBegin(rgbIn, depthIn, timestamp, maskIn, inPose, bootstrap, onDevice);
     frameProject();
     frameEnd(weightMultiplier);
@@ -673,28 +726,40 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
 {
     const bool multi = cfg.enableMultipleModels != 0;
     if (world > 1 && inPose) throw CudaError{"sharded mode tracks every frame (no external poses)"};
-    finalisePending();                                  // previous frame's tracked pose + pose-log entry (its event lies mid-frame: the GPU still has work queued)
+    if (multi && bootstrap && inPose) throw CudaError{"bootstrap poses are supported by the -static schedule only"};
+    finalisePending();                                  // previous frame: tracked poses, pose log, (multi) inactivations and the deferred spawn
     fTimestamp = timestamp; fHasPose = inPose != nullptr; if (inPose) fInPose = *inPose; fBootstrap = bootstrap;
+    const bool tracking = tick > 1 && (bootstrap || !inPose);
     // -static tracking frames: upload + bilateral + pyramids + maps + intensity/Sobel of THIS frame go to preStream and into the other
     // input set, so they run next to the surfel passes of the previous frame that are still queued on the main stream (those read the
     // previous frame's images; the copy engine and the issue-bound bilateral overlap well with the HBM-bound clean/scatter).
     // Safe without further events: finalisePending() above has waited for the previous frame's tracker, the last reader of the maps.
-    const bool overlap = !multi && world == 1 && tick > 1 && (bootstrap || !inPose) && !prof.on;
+    const bool overlap = !multi && world == 1 && tracking && !prof.on;
     if (overlap) {
         selectSet(curSet ^ 1);
-        setFrame(rgbIn, depthIn, nullptr, onDevice, preStream);
+        uploadInputs(rgbIn, depthIn, nullptr, timestamp, onDevice, preStream);
+        preprocess(preStream);
         generateCUDATextures(preStream);
         if (cfg.rgbOnly || cfg.icpWeight < 100 || cfg.so3) frameIntensity(preStream);
         cudaCheck(cudaEventRecord(preDone, preStream), "cudaEventRecord");
         preWaitPending = true;
-    } else
-        setFrame(rgbIn, depthIn, nullptr, onDevice);    // -static: textureMask stays all zero (MaskFusion.cpp:223-230); multi: keeps the last segmentation
-    frameHasMask = false;
-    if (multi && maskIn) {
-        cudaCheck(cudaMemcpyAsync(frameMask, maskIn, (size_t)P, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream), "mask upload");
-        frameHasMask = !classIDs.empty();
+    } else {
+        // multi-model: the previous frame's input set stays intact (a spawn decided by that frame has just been carried out from it)
+        if (multi) selectSet(curSet ^ 1);
+        if (bbMoldPending) { cudaCheck(cudaStreamWaitEvent(stream, bbMoldDone, 0), "cudaStreamWaitEvent"); bbMoldPending = false; }   // an older frame's image is being read
+        if (shardNccl) {
+            // object-sharded: rank 0 holds the loader; the frame packet (images + mask + header, one buffer) goes to every rank over NVLink
+            if (rank == 0) uploadInputs(rgbIn, depthIn, maskIn, timestamp, onDevice);
+            prof_mark(stream, "nccl_broadcast_packet");
+            shard.broadcast(inBuf[curSet].p, packetBytes(), 0, stream);
+        } else
+            uploadInputs(rgbIn, depthIn, maskIn, timestamp, onDevice);     // -static: textureMask stays all zero (MaskFusion.cpp:223-230)
+        preprocess();
+        runBackbone();
     }
     Model* g = models[0].get();
+    fTracked = false;
+    for (auto& m : models) m->tracked = false;
     if (tick == 1) {
         if (g->owned) {
             g->initialise(tick);
@@ -704,58 +769,59 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
             cudaCheck(cudaMemcpyAsync(g->lastNextImage2, nextImage[2], (size_t)(W >> 2) * (H >> 2), cudaMemcpyDeviceToDevice, stream), "initFirstRGB");
             launches += 3;
         }
-    } else if (bootstrap || !inPose) {
+    } else if (tracking) {
         if (!frameMapsValid) generateCUDATextures();
         // MaskFusion.cpp:247-276: the global model and every tracked object share one batched launch sequence
         std::vector<Model*> tracked;
-        for (size_t i = 0; i < models.size(); ++i)
-            if (models[i]->owned && (i == 0 || models[i]->nonstatic || cfg.trackAllModels)) tracked.push_back(models[i].get());
-        trackModels(tracked);
-        // the multi-model schedule takes host decisions on the tracked poses (inactivation, static poses, spawn); so does bootstrap mode
-        if (multi || world > 1 || (bootstrap && inPose)) finalisePending();
+        for (size_t i = 0; i < models.size(); ++i) {
+            Model* m = models[i].get();
+            m->tracked = (i == 0 || m->nonstatic || cfg.trackAllModels);
+            if (m->owned && m->tracked) tracked.push_back(m);
+        }
+        trackModels(tracked, multi);
+        fTracked = true;
+        if (multi) {
+            // pose rows of the models tracked here; with a communicator every rank receives every rank's rows (all-gather)
+            launch_pack_rows(lifeParams(), poseTable, stream);
+            launches += 1;
+            if (shardNccl) { prof_mark(stream, "nccl_allgather_poses"); shard.allGatherFloats(poseTable, gathered, (size_t)MF_MAX_MODELS * 32, stream); }
+        } else if (bootstrap && inPose) finalisePending();     // -static bootstrap: the host composes the tracked pose with the given one
     }
 }
 
-// MaskFusion.cpp:257-290 after the poses are known everywhere: inactivation, static poses, local part of the ID projection
+// MaskFusion.cpp:257-290 after the poses are known everywhere: inactivation, static poses (device side), local part of the ID projection
 void MaskFusion::frameProject()
 {
-    if (tick == 1 || !(fBootstrap || !fHasPose)) return;
-    Model* g = models[0].get();
-    for (size_t i = 1; i < models.size(); ++i) {
-        Model* m = models[i].get();
-        if (m->nonstatic || cfg.trackAllModels) {
-            const float* T = m->lastTransform.m;
-            float d = sqrtf((T[3] * T[3] + T[7] * T[7]) + T[11] * T[11]);
-            if (d > 0.2f) { models.erase(models.begin() + i); --i; }          // inactivateModel (:268-272)
-        } else m->updateStaticPose(g->pose);
+    if (!fTracked) return;
+    if (!cfg.enableMultipleModels) {
+        if (fBootstrap && fHasPose) { Model* g = models[0].get(); g->overridePose(mul(g->pose, fInPose)); }
+        return;
     }
-    if (fBootstrap && fHasPose) g->overridePose(mul(g->pose, fInPose));
-    if (cfg.enableMultipleModels) projectLocal();                              // :289-290
+    launch_lifecycle(lifeParams(), world > 1 ? gathered.p : poseTable.p, dRes, stream);
+    launches += 1;
+    projectLocal();                                                            // :289-290
 }
 
-// MaskFusion.cpp:290-607: segmentation (replicated: every rank holds the same merged key image), spawn, fusion of the local stores
+// MaskFusion.cpp:290-607: segmentation (replicated: every rank holds the same merged key image), fusion of the local stores, prediction
 void MaskFusion::frameEnd(float weightMultiplier)
 {
     const bool multi = cfg.enableMultipleModels != 0;
     Model* g = models[0].get();
+    fWeight = weightMultiplier;
     if (tick > 1) {
-        if (fBootstrap || !fHasPose) {
+        if (fTracked) {
             if (multi) {
+                if (shardNccl) { prof_mark(stream, "nccl_allreduce_keys"); shard.allReduceMinU64(projKeys, (size_t)P, stream); }
+                segTables();
                 projectResolve();
                 if (spawnOffset < cfg.modelSpawnOffset) spawnOffset++;
-                SegmentationResult seg = performSegmentation(spawnOffset >= cfg.modelSpawnOffset);
-                Model* nm = nullptr;
-                if (seg.hasNewLabel) {                                                 // :313-334
-                    nm = spawnObjectModel();
-                    spawnOffset = 0;
-                    nm->classID = seg.newClassID;
-                }
+                performSegmentation(spawnOffset >= cfg.modelSpawnOffset);
+                // what the host needs from this frame, in one copy behind the vote kernel; picked up by the next finalisePending()
+                prof_mark(stream, "copy_result_d2h");
+                cudaCheck(cudaMemcpyAsync(hRes, dRes.p, sizeof(FrameResult), cudaMemcpyDeviceToHost, stream), "result D2H");
+                cudaCheck(cudaEventRecord(resEvt, stream), "cudaEventRecord");
+                pendingResult = true;
                 for (size_t i = 1; i < models.size(); ++i) models[i]->maxDepth = 30.0f + 30.0f * 1.2f;   // getMaxDepth(30, 30), :292,337-341
-                if (nm && nm->owned) {                                                 // :344-353
-                    nm->predictIndices(tick, cfg.maxDepthProcessed, cfg.timeDelta);
-                    nm->fuse(tick, cfg.maxDepthProcessed, 100.0f);
-                    nm->clean(tick, cfg.timeDelta, cfg.maxDepthProcessed);
-                }
                 for (size_t i = 1; i < models.size(); ++i) {                           // :369-374
                     float f = (float)models[i]->age / 25.0f;
                     models[i]->confidenceThreshold = f < 4.5f ? f : 4.5f;
@@ -772,10 +838,63 @@ void MaskFusion::frameEnd(float weightMultiplier)
         }
     }
     predict();          // MaskFusion.cpp:569 (the call at :423 is dead in open-loop mode: its outputs are overwritten here)
+    fTick = tick;
     tick++;
-    if (pendingTrack) { pendingLog = true; pendingTimestamp = fTimestamp; }    // -static: the entry is written when the pose arrives
+    if (pendingResult) { /* the pose-log entry is written by applyFrameResult, after the spawn it may carry out */ }
+    else if (pendingTrack) { pendingLog = true; pendingTimestamp = fTimestamp; }    // -static: the entry is written when the pose arrives
     else logPoses(fTimestamp);
     for (auto& m : models) m->age++;
+}
+
+// Everything the host learns from a multi-model frame, applied at the start of the next one (or by any query in between), in the
+// order of the reference's frame: tracked poses (Model.cpp:427-447) -> inactivation (MaskFusion.cpp:268-272, 699-713) -> spawn of the
+// model MfSegmentation asked for and its first fusion FROM THAT FRAME'S DATA (:313-353; the input set, textureMask and the intensity
+// pyramid of the frame are still untouched) -> pose log (:577-592).  Identical on every rank of a sharded run (replicated inputs).
+void MaskFusion::applyFrameResult()
+{
+    cudaCheck(cudaEventSynchronize(resEvt), "cudaEventSynchronize");
+    pendingResult = false;
+    const FrameResult& R = *hRes;
+    for (size_t i = 0; i < models.size(); ++i) {
+        Model* m = models[i].get();
+        if (!m->tracked && i == 0) continue;
+        m->lastPose = m->pose;
+        memcpy(m->pose.m, R.poses[i], 16 * sizeof(float));
+        if (m->tracked) memcpy(m->lastTransform.m, R.poses[i] + 16, 16 * sizeof(float));
+    }
+    for (size_t i = models.size(); i-- > 1;) {
+        if (!R.dead[i]) continue;
+        Model* m = models[i].get();
+        const unsigned cnt = m->owned ? R.deadCount[i] : modelKeepMinSurfels;
+        if (!enableSmartModelDelete || (cnt >= modelKeepMinSurfels && m->confidenceThreshold > modelKeepConfThreshold)) {
+            if (m->owned) { launch_set_count(m->dCount(), cnt, stream); launches += 1; }       // the store as it was when the model left
+            inactiveModels.push_back(std::move(models[i]));
+        }
+        models.erase(models.begin() + i);
+    }
+    if (R.hasNewLabel) {                                                                       // :313-334
+        Model* nm = spawnObjectModel();
+        spawnOffset = 0;
+        nm->classID = R.newClassID;
+        nm->maxDepth = 30.0f + 30.0f * 1.2f;
+        if (nm->owned) {                                                                       // :344-353, with the frame's own tick / weight
+            const int t = fTick;
+            nm->predictIndices(t, cfg.maxDepthProcessed, cfg.timeDelta);
+            nm->fuse(t, cfg.maxDepthProcessed, 100.0f);
+            nm->clean(t, cfg.timeDelta, cfg.maxDepthProcessed);
+            nm->confidenceThreshold = 0.0f;                                                    // age 0 (:369-374)
+            if (!cfg.rgbOnly) {
+                nm->predictIndices(t, cfg.maxDepthProcessed, cfg.timeDelta, false);
+                nm->fuse(t, cfg.depthCutoff, fWeight);
+                nm->predictIndices(t, cfg.maxDepthProcessed, cfg.timeDelta);
+                nm->clean(t, cfg.timeDelta, cfg.maxDepthProcessed);
+            }
+            nm->combinedPredict(cfg.maxDepthProcessed, t, t, cfg.timeDelta);
+        }
+        nm->confidenceThreshold = 0.0f;
+        nm->age = 1;
+    }
+    logPoses(R.timestamp);
 }
 
 }  // namespace mfb

@@ -49,6 +49,20 @@ extern Profiler* g_prof;
 
 class MaskFusion;
 
+// object-sharded mode: NCCL communicator of the ranks that share one replay (mf_sched.cu; libnccl is opened at run time)
+struct ShardComm {
+    void* comm = nullptr; int rank = 0, world = 1, version = 0; size_t bytesMoved = 0; long calls = 0;
+    ~ShardComm();
+    void init(const unsigned char* id128, int rank, int world);
+    void broadcast(void* buf, size_t bytes, int root, cudaStream_t s);                               // frame packet (MaskFusion.cpp:212-217)
+    void allGatherFloats(const float* send, float* recv, size_t countPerRank, cudaStream_t s);       // pose rows (MaskFusion.cpp:257-276)
+    void allReduceMinU64(uint64_t* buf, size_t count, cudaStream_t s);                               // ID-projection keys (GlobalProjection.cpp:66-95)
+};
+void shardUniqueId(unsigned char* out128);
+void launch_pack_rows(const LifeParams& lp, float* table, cudaStream_t s);
+void launch_lifecycle(const LifeParams& lp, const float* gathered, FrameResult* res, cudaStream_t s);
+void launch_set_count(uint32_t* c, uint32_t v, cudaStream_t s);
+
 class Model {
 public:
     // ghost = replica of a model whose surfel store lives on another rank: pose, ids and age only, no device buffers
@@ -104,6 +118,7 @@ public:
     float* hTrackOut = nullptr;             // pinned: pose(16) transform(16) stats(8)
     Mat4 lastTransform;
     std::vector<double> poseLog;            // 8 doubles per entry
+    bool tracked = false;                   // took part in the tracking launch of the frame in flight (deferred bookkeeping)
 };
 
 class MaskFusion {
@@ -116,9 +131,11 @@ public:
                       float weightMultiplier, bool bootstrap, bool inputsOnDevice);
     // upload + filterDepth; generateCUDATextures; frame side of initRGB.  `s` = stream to enqueue on (nullptr: the main stream)
     void setFrame(const uint8_t* rgb, const float* depth, const uint8_t* mask, bool onDevice, cudaStream_t s = nullptr);
+    void uploadInputs(const uint8_t* rgb, const float* depth, const uint8_t* mask, int64_t timestamp, bool onDevice, cudaStream_t s = nullptr);
+    void preprocess(cudaStream_t s = nullptr);
     void generateCUDATextures(cudaStream_t s = nullptr);                                          // Model::generateCUDATextures
     void frameIntensity(cudaStream_t s = nullptr);                                                // RGBDOdometry::initRGB (frame side) + Sobel + validity
-    void trackModels(const std::vector<Model*>& ms);                                              // performTracking for a batch
+    void trackModels(const std::vector<Model*>& ms, bool viaResult = false);                      // performTracking for a batch
     void predict();                                                                               // MaskFusion::predict
     void sync();
     // The tracked pose reaches the host through an asynchronous copy + event recorded right after the tracking kernel.  The -static
@@ -128,21 +145,43 @@ public:
     void logPoses(int64_t timestamp);
     bool pendingTrack = false, pendingLog = false; int64_t pendingTimestamp = 0; std::vector<Model*> pendingModels; cudaEvent_t trackDone = nullptr;
     // ---- multi-model path (MaskFusion.cpp:287-375) ----
-    struct SegmentationResult { bool hasNewLabel = false; int newClassID = -1; };                 // SegmentationResult.h:32-73 (fields the schedule reads)
     void globalProjection();                                                                      // GlobalProjection::project + downloadDirect (stays on the device)
-    SegmentationResult performSegmentation(bool allowNew);                                        // MfSegmentation::performSegmentation
+    void segTables();
+    void performSegmentation(bool allowNew);                                                      // MfSegmentation::performSegmentation (result -> FrameResult)
     unsigned char getNextModelID(bool assign);                                                    // MaskFusion::getNextModelID
     Model* spawnObjectModel();                                                                    // MaskFusion::spawnObjectModel + moveNewModelToList
     void setFrameClasses(const int32_t* ids, int n) { classIDs.assign(ids, ids + n); }            // FrameData::classIDs
 
-    // ---- object-sharded mode: processFrame == frameBegin; [pose all-gather]; frameProject; [u64 min all-reduce of the
-    // projection keys]; frameEnd.  The collectives run in the host layer above the C ABI (torch.distributed), on this stream.
+    // ---- a frame in three phases; between them sit the two exchanges of the object-sharded mode:
+    //   frameBegin  inputs (+ frame-packet broadcast), preprocessing, tracking of the models whose store lives here, pose rows
+    //   [pose-row all-gather]
+    //   frameProject  device-side lifecycle (inactivation, static poses), local part of the global ID projection
+    //   [64-bit MIN all-reduce of the projection keys]
+    //   frameEnd  resolve, segmentation + vote (device driven), FrameResult copy, fusion of the local stores, prediction
+    // With an NCCL communicator (initShardComm) the exchanges are issued from here on the context's stream and NOTHING in a frame
+    // waits for the host; without one the caller moves the rows / keys itself between the phase calls (any transport: the gloo tests).
     void configureShard(int rank, int world);
+    void initShardComm(const unsigned char* id128, int rank, int world);
     void frameBegin(const uint8_t* rgb, const float* depth, int64_t timestamp, const uint8_t* mask, const Mat4* inPose, bool bootstrap, bool onDevice);
-    void getShardPoses(float* out) const;                       // [nModels][32]: pose, lastTransform (row-major); rows of ghosts are zero
-    void setShardPoses(const float* gathered);                  // [world][nModels][32]: every model takes its owner's row
-    void frameProject();                                        // lifecycle after tracking + local part of the global ID projection
+    void getShardPoses(float* out);                             // [MF_MAX_MODELS][32] rows of this rank (external transport; synchronises)
+    void setShardPoses(const float* gathered);                  // [world][MF_MAX_MODELS][32] -> device (external transport)
+    void frameProject();
     void frameEnd(float weightMultiplier);
+    // deferred bookkeeping of the multi-model schedule: applied at the start of the next frame (or by any query in between)
+    void applyFrameResult();
+    LifeParams lifeParams() const;
+    ShardComm shard; bool shardNccl = false;
+    // Mask R-CNN backbone on the frame path (MaskRCNN::executeSequential, MaskRCNN.cpp:147-151, is called from MfSegmentation.cpp:130):
+    // every k-th frame the RGB image is letter-boxed into the backbone's input and the ResNet-101-FPN forward is enqueued on the
+    // backbone's own stream, next to the dense pipeline of the same GPU (the reference runs its network as a ~5 Hz sidecar)
+    void* backbone = nullptr; int backboneEvery = 0; cudaEvent_t bbFrameReady = nullptr, bbMoldDone = nullptr; bool bbMoldPending = false;
+    void attachBackbone(void* bb, int everyK);
+    void runBackbone();
+    FrameResult* hRes = nullptr; DevBuf<FrameResult> dRes; cudaEvent_t resEvt = nullptr; bool pendingResult = false;
+    DevBuf<float> poseTable, gathered;
+    float fWeight = 1.f; int fTick = 0; bool fTracked = false;
+    std::vector<std::unique_ptr<Model>> inactiveModels;        // MaskFusion::inactiveModels (MaskFusion.cpp:699-713): kept for exportPoses / savePly
+    bool enableSmartModelDelete = true; unsigned modelKeepMinSurfels = 4000; float modelKeepConfThreshold = 0.3f;   // MaskFusion.h:398,414-415
     void projectLocal(); void projectResolve();                 // the two halves of globalProjection()
     static int pickOwner(const int64_t* loads, int world);      // least-loaded rank (by owned surfel capacity), ties -> highest rank
     int rank = 0, world = 1;
@@ -157,10 +196,18 @@ public:
     // frame
     // Frame inputs exist twice: in the -static schedule the upload and preprocessing of frame t+1 run on their own stream
     // (preStream) while the surfel passes of frame t, which still read frame t's images, occupy the main stream.
-    DevBuf<uint8_t> rgb3Buf[2]; DevBuf<uchar4> rgbBuf[2]; DevBuf<float> depthRawBuf[2], depthFiltBuf[2];
+    // The loader's data of one frame is ONE contiguous device buffer -- rgb (3P) | raw depth (4P) | instance mask (P) | FrameHdr -- which
+    // is exactly the frame packet the object-sharded mode broadcasts (MaskFusion.cpp:212-217).
+    DevBuf<uint8_t> inBuf[2]; DevBuf<uchar4> rgbBuf[2]; DevBuf<float> depthFiltBuf[2];
     uint8_t* rgb3 = nullptr; uchar4* rgb = nullptr; float* depthRaw = nullptr; float* depthFilt = nullptr;   // the current set
+    uint8_t* frameMask = nullptr; FrameHdr* dHdr = nullptr;                                                   // FrameData::mask / classIDs of the current set
     int curSet = 0;
-    void selectSet(int k) { curSet = k; rgb3 = rgb3Buf[k]; rgb = rgbBuf[k]; depthRaw = depthRawBuf[k]; depthFilt = depthFiltBuf[k]; }
+    size_t packetBytes() const { return (size_t)P * 8 + sizeof(FrameHdr); }
+    void selectSet(int k)
+    {
+        curSet = k; rgb3 = inBuf[k].p; depthRaw = reinterpret_cast<float*>(inBuf[k].p + (size_t)P * 3); frameMask = inBuf[k].p + (size_t)P * 7;
+        dHdr = reinterpret_cast<FrameHdr*>(inBuf[k].p + (size_t)P * 8); rgb = rgbBuf[k]; depthFilt = depthFiltBuf[k];
+    }
     cudaStream_t preStream = nullptr; cudaEvent_t preDone = nullptr, inputsCopied = nullptr; bool preWaitPending = false, copyPending = false;
     cudaEvent_t inputReady = nullptr;        // caller's producer event for device inputs (mf_set_input_event): waited on before the next frame's copies
     DevBuf<uint8_t> mask;
@@ -175,15 +222,11 @@ public:
     Profiler prof;
     // multi-model state
     std::vector<int32_t> classIDs;          // of the frame being processed
-    bool frameHasMask = false;
     int spawnOffset = 0;
-    DevBuf<uint8_t> frameMask;              // FrameData::mask (external instance masks)
     DevBuf<uint64_t> projKeys; DevBuf<uint8_t> projectedIDs;
     DevBuf<int> ccL, ccDense, ccLabA, ccLabB, ccArea, mapToMask, absorbId, maskPixels, compModel, compMask;
     DevBuf<uint32_t> ccCounter; DevBuf<unsigned> maskOverlap;
     DevBuf<uint8_t> segTmp, ignoreMap, tblIdToIndex, tblIndexToId, tblIsModel, tblMaskToID, tblIsPerson;
-    uint8_t maskToID[256];
-    uint32_t* hSmall = nullptr;             // pinned scratch for the small tables
     float minMaskModelOverlap = 0.05f; int minMappedComponentSize = 160; int personClassID = 255;   // MfSegmentation.cpp:43, MfSegmentation.h:58
 };
 

@@ -85,6 +85,26 @@ __device__ inline void derivePose(DevPose* d, const float* m, const float* last)
 }
 #endif
 
+// ---- device-resident frame bookkeeping of the multi-model schedule: nothing in a frame waits for the host ----
+// FrameHdr: what the loader knows about the frame besides the images; in the object-sharded mode it is the tail of the broadcast
+// frame packet, so the ranks that never saw the host inputs read it where the kernels read it: on the device.
+struct FrameHdr { long long timestamp; int nMasks; int pad; int classIDs[256]; };          // nMasks == 0: the frame carries no instance masks
+// FrameResult: everything the host learns from a frame (one asynchronous copy behind the vote kernel; read at the START of the next
+// frame): the spawn decision of MfSegmentation, which tracked models jumped > 0.2 m (MaskFusion.cpp:268-272), every model's pose.
+#define MF_MAX_MODELS 64
+struct FrameResult {
+    int hasNewLabel, newClassID, nMasks, nComponents; long long timestamp;
+    int dead[MF_MAX_MODELS]; unsigned deadCount[MF_MAX_MODELS];
+    float poses[MF_MAX_MODELS][32];                       // pose (row-major 4x4) | last incremental transform
+};
+struct SegTables { unsigned char idToIndex[256], indexToId[256], isModel[256]; };
+struct VoteParams {
+    int nModels, allowNew, personClassID; unsigned minNew, maxNew; float minMaskModelOverlap; unsigned char nextModelID;
+    int modelClass[MF_MAX_MODELS]; unsigned char modelID[MF_MAX_MODELS];
+};
+struct LifeModel { int tracked, owned, ownerRank, pad; DevPose* dpose; const float* trackOut; unsigned* count; float initialC2Winv[16]; };
+struct LifeParams { int nModels, rank; LifeModel m[MF_MAX_MODELS]; };
+
 // Gauss-Newton state of one tracked model; lives in device memory for the whole frame
 struct TrackState {
     float Rprev[9], tprev[3], RprevInv[9];
@@ -166,12 +186,13 @@ void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, 
 // ---- mf_track.cu ----
 int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
                     bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s);
+int debug_track_timing(long long* out, int cap);
 void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,
                      const TrackPoses& pp, float* partial, unsigned* ticket, float* out29, int numSMs, cudaStream_t s);
 
 // ---- mf_seg.cu ----
 void launch_geometric_edges(const float4* vmap, const float4* nmap, int W, int H, float wD, float wC, float thr, float* edge, uint8_t* binary, cudaStream_t s);
-int launch_morph_close_ellipse(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, cudaStream_t s);   // MfSegmentation.cpp:424-426; returns the number of launches
+int launch_morph_close_ellipse(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, const FrameHdr* onlyIfMasks, cudaStream_t s);   // MfSegmentation.cpp:424-426; returns the number of launches
 void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, uint8_t* inverted, cudaStream_t s);
 
 }  // namespace mfb
@@ -180,14 +201,20 @@ namespace mfb {
 // ---- mf_seg.cu: GPU segmentation tail + global projection resolve ----
 void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, uint32_t* counter, cudaStream_t s);
 void launch_remove_edges(int* labA, int* labB, const float* depth, const int* area, int W, int H, int iterations, cudaStream_t s);
-void launch_seg_hist(const int* lab, const uint8_t* projID, const uint8_t* mask, int P, const uint8_t* idToIndex, int nModels, int nMasks,
+void launch_seg_tables(const SegTables& t, uint8_t* idToIndex, uint8_t* indexToId, uint8_t* isModel, cudaStream_t s);
+void launch_frame_header(const FrameHdr& h, FrameHdr* d, cudaStream_t s);                       // single-process path: the header by value
+void launch_person_table(const FrameHdr* hdr, int personClassID, uint8_t* isPerson, cudaStream_t s);
+void launch_clear_hist(const uint32_t* ccCounter, const FrameHdr* hdr, int nModels, int* compModel, int* compMask, cudaStream_t s);
+void launch_seg_hist(const int* lab, const uint8_t* projID, const uint8_t* mask, int P, const uint8_t* idToIndex, int nModels, const FrameHdr* hdr,
                      int* compModel, int* compMask, cudaStream_t s);
-void launch_component_map(int nComponents, const int* area, const int* compModel, const int* compMask, int nModels, int nMasks,
+void launch_component_map(const uint32_t* ccCounter, const int* area, const int* compModel, const int* compMask, int nModels, const FrameHdr* hdr,
                           const uint8_t* indexToId, int minMapped, int* mapToMask, int* absorb, int* maskPixels, cudaStream_t s);
+void launch_vote(const FrameHdr* hdr, const VoteParams& vp, const int* maskPixels, const unsigned* maskOverlap, const uint32_t* ccCounter,
+                 uint8_t* maskToID, FrameResult* res, cudaStream_t s);
 void launch_seg_assign(const int* lab, const int* mapToMask, const uint8_t* ignore, int P, uint8_t* seg, cudaStream_t s);
 void launch_mask_overlap(const uint8_t* seg, const uint8_t* projID, const uint8_t* idToIndex, const uint8_t* isModelId, int P, unsigned* maskOverlap, cudaStream_t s);
 void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, int P, uint8_t* out, cudaStream_t s);
-void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, int nMasks, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s);
+void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, const FrameHdr* hdr, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s);
 void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s);
 void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, float confThreshold,
                                int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s);

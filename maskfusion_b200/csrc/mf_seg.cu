@@ -66,10 +66,12 @@ __global__ void k_invert(const uint8_t* __restrict__ in, int n, uint8_t* __restr
 // row dy of the element spans columns -hw[dy+r] .. +hw[dy+r]; taps outside the image are ignored (morphologyDefaultBorderValue).
 // One step of cv::morphologyEx(MORPH_CLOSE) on the mask-id image (MfSegmentation.cpp:424-426).
 struct EllipseRows { int r; int hw[33]; };
-__global__ void k_morph_ellipse(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, int H, EllipseRows e, int dilate)
+__global__ void k_morph_ellipse(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int W, int H, EllipseRows e, int dilate,
+                                const FrameHdr* __restrict__ onlyIfMasks)
 {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
+    if (onlyIfMasks && onlyIfMasks->nMasks == 0) { out[y * W + x] = in[y * W + x]; return; }     // the reference closes only inside `if (nMasks)` (:420-426)
     int best = dilate ? 0 : 255;
     for (int dy = -e.r; dy <= e.r; ++dy) {
         const int yy = y + dy;
@@ -84,7 +86,7 @@ __global__ void k_morph_ellipse(const uint8_t* __restrict__ in, uint8_t* __restr
     out[y * W + x] = (uint8_t)best;
 }
 // closes `data` in place (buf: scratch of the same size): dilate x iterations, then erode x iterations
-int launch_morph_close_ellipse(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, cudaStream_t s)
+int launch_morph_close_ellipse(uint8_t* data, uint8_t* buf, int W, int H, int radius, int iterations, const FrameHdr* onlyIfMasks, cudaStream_t s)
 {
     if (iterations <= 0) return 0;
     if (radius < 0 || radius > 16) throw CudaError{"morphMaskRadius must be in 0..16"};
@@ -98,7 +100,7 @@ int launch_morph_close_ellipse(uint8_t* data, uint8_t* buf, int W, int H, int ra
     uint8_t* src = data; uint8_t* dst = buf;
     for (int pass = 0; pass < 2; ++pass)
         for (int i = 0; i < iterations; ++i) {
-            prof_mark(s, "k_morph_ellipse"); k_morph_ellipse<<<g, b, 0, s>>>(src, dst, W, H, e, pass == 0);
+            prof_mark(s, "k_morph_ellipse"); k_morph_ellipse<<<g, b, 0, s>>>(src, dst, W, H, e, pass == 0, onlyIfMasks);
             uint8_t* t = src; src = dst; dst = t;
         }
     // 2 * iterations launches: the result is back in `data`
@@ -211,34 +213,86 @@ __global__ void k_remove_edges(const int* __restrict__ labIn, int* __restrict__ 
     labOut[i] = c;
 }
 __global__ void k_seg_hist(const int* __restrict__ lab, const uint8_t* __restrict__ projID, const uint8_t* __restrict__ mask, int P,
-                           const uint8_t* __restrict__ idToIndex, int nModels, int nMasks, int* __restrict__ compModel, int* __restrict__ compMask)
+                           const uint8_t* __restrict__ idToIndex, int nModels, const FrameHdr* __restrict__ hdr, int* __restrict__ compModel, int* __restrict__ compMask)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nMasks = hdr->nMasks;
     const bool in = i < P;
     const int c = in ? lab[i] : 0;
     warpAggAdd(compModel, in ? c * nModels + (int)idToIndex[projID[i]] : -1);
     if (nMasks) warpAggAdd(compMask, in ? c * nMasks + (int)mask[i] : -1);
 }
-__global__ void k_component_map(int nComponents, const int* __restrict__ area, const int* __restrict__ compModel, const int* __restrict__ compMask,
-                                int nModels, int nMasks, const uint8_t* __restrict__ indexToId, int minMappedComponentSize,
+// the two component histograms are sized for the worst case (P/2 + 2 components x 64 models / 256 masks: memory is not the
+// constraint on a 180 GB part); only the rows this frame uses are cleared, the counts come from the device
+__global__ void k_clear_hist(const uint32_t* __restrict__ ccCounter, const FrameHdr* __restrict__ hdr, int nModels, int* __restrict__ compModel, int* __restrict__ compMask)
+{
+    const size_t nC = (size_t)*ccCounter + 1, nA = nC * nModels, nB = nC * hdr->nMasks;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nA + nB; i += (size_t)gridDim.x * blockDim.x) {
+        if (i < nA) compModel[i] = 0; else compMask[i - nA] = 0;
+    }
+}
+__global__ void k_component_map(const uint32_t* __restrict__ ccCounter, const int* __restrict__ area, const int* __restrict__ compModel, const int* __restrict__ compMask,
+                                int nModels, const FrameHdr* __restrict__ hdr, const uint8_t* __restrict__ indexToId, int minMappedComponentSize,
                                 int* __restrict__ mapToMask, int* __restrict__ absorb, int* __restrict__ maskPixels)
 {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= nComponents) return;
-    int m2m = 0, ab = 0;
-    if (c >= 1) {
-        int csize = area[c];
-        if (nMasks && csize > minMappedComponentSize) {
-            int t = (int)(0.65f * csize);
-            for (int m = 1; m < nMasks; ++m)
-                if (compMask[(size_t)c * nMasks + m] > t) { m2m = m; atomicAdd(&maskPixels[m], csize); }
+    const int nComponents = (int)*ccCounter + 1, nMasks = hdr->nMasks;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < nComponents; c += gridDim.x * blockDim.x) {
+        int m2m = 0, ab = 0;
+        if (c >= 1) {
+            int csize = area[c];
+            if (nMasks && csize > minMappedComponentSize) {
+                int t = (int)(0.65f * csize);
+                for (int m = 1; m < nMasks; ++m)
+                    if (compMask[(size_t)c * nMasks + m] > t) { m2m = m; atomicAdd(&maskPixels[m], csize); }
+            }
+            int best = compModel[(size_t)c * nModels], bi = 0;
+            for (int m = 1; m < nModels; ++m) { int v = compModel[(size_t)c * nModels + m]; if (v > best) { best = v; bi = m; } }
+            int id = indexToId[bi];
+            if (id > 0 && best > 0.6f * csize) ab = id;
         }
-        int best = compModel[(size_t)c * nModels], bi = 0;
-        for (int m = 1; m < nModels; ++m) { int v = compModel[(size_t)c * nModels + m]; if (v > best) { best = v; bi = m; } }
-        int id = indexToId[bi];
-        if (id > 0 && best > 0.6f * csize) ab = id;
+        mapToMask[c] = m2m; absorb[c] = ab;
     }
-    mapToMask[c] = m2m; absorb[c] = ab;
+}
+// mask -> model vote of MfSegmentation.cpp:433-492 on the device (one thread: the "first new label wins" rule is sequential; the
+// tables are <= 256 x 64 entries).  maskToID persists across frames like the member of the reference class.
+__global__ void k_vote(const FrameHdr* __restrict__ hdr, VoteParams vp, const int* __restrict__ maskPixels, const unsigned* __restrict__ maskOverlap,
+                       const uint32_t* __restrict__ ccCounter, uint8_t* __restrict__ maskToID, FrameResult* __restrict__ res)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nMasks = hdr->nMasks;
+    int hasNew = 0, newClass = -1;
+    if (nMasks) {
+        for (int midx = 1; midx < nMasks; ++midx) { maskToID[midx] = 0; if (hdr->classIDs[midx] == vp.personClassID) maskToID[midx] = 255; }
+        for (int midx = 1; midx < nMasks; ++midx) {
+            if (maskToID[midx] == 255) continue;
+            int bestModelIndex = 0; unsigned bestOverlap = 0;
+            const int maskClassID = hdr->classIDs[midx];
+            for (int j = 1; j < vp.nModels; ++j) { unsigned o = maskOverlap[(size_t)j * 256 + midx]; if (o > bestOverlap) { bestOverlap = o; bestModelIndex = j; } }
+            const bool matches = vp.modelClass[bestModelIndex] == maskClassID;
+            if (bestOverlap < vp.minMaskModelOverlap * maskPixels[midx]) bestModelIndex = 0;
+            if (bestModelIndex != 0 && matches) maskToID[midx] = vp.modelID[bestModelIndex];
+            else if (!hasNew && vp.allowNew && (unsigned)maskPixels[midx] > vp.minNew && (unsigned)maskPixels[midx] < vp.maxNew && bestModelIndex == 0) {
+                maskToID[midx] = vp.nextModelID; hasNew = 1; newClass = maskClassID;
+            } else maskToID[midx] = 255;
+        }
+    }
+    res->hasNewLabel = hasNew; res->newClassID = newClass; res->nMasks = nMasks; res->nComponents = (int)*ccCounter + 1; res->timestamp = hdr->timestamp;
+}
+__global__ void k_seg_tables(SegTables t, uint8_t* __restrict__ idToIndex, uint8_t* __restrict__ indexToId, uint8_t* __restrict__ isModel)
+{
+    const int i = threadIdx.x;
+    idToIndex[i] = t.idToIndex[i]; indexToId[i] = t.indexToId[i]; isModel[i] = t.isModel[i];
+}
+__global__ void k_frame_header(FrameHdr h, FrameHdr* __restrict__ d)
+{
+    const int i = threadIdx.x;
+    if (i == 0) { d->timestamp = h.timestamp; d->nMasks = h.nMasks; d->pad = 0; }
+    d->classIDs[i] = h.classIDs[i];
+}
+__global__ void k_person_table(const FrameHdr* __restrict__ hdr, int personClassID, uint8_t* __restrict__ isPerson)
+{
+    const int i = threadIdx.x;
+    isPerson[i] = (i < hdr->nMasks && hdr->classIDs[i] == personClassID) ? 1 : 0;
 }
 __global__ void k_seg_assign(const int* __restrict__ lab, const int* __restrict__ mapToMask, const uint8_t* __restrict__ ignore, int P,
                              uint8_t* __restrict__ seg)
@@ -265,12 +319,12 @@ __global__ void k_seg_final(const uint8_t* __restrict__ seg, const int* __restri
     if (c > 0 && mapToMask[c] == 0 && absorb[c] > 0) s = (uint8_t)absorb[c];
     out[i] = s;
 }
-__global__ void k_apply_ignore(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ isPerson, int nMasks, int P,
+__global__ void k_apply_ignore(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ isPerson, const FrameHdr* __restrict__ hdr, int P,
                                uint8_t* __restrict__ ignore, uint8_t* __restrict__ edges)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    if (nMasks) ignore[i] = isPerson[mask[i]] ? 255 : 0;
+    if (hdr->nMasks) ignore[i] = isPerson[mask[i]] ? 255 : 0;
     if (ignore[i]) edges[i] = 0;
 }
 // model-ID image from the global-projection keys (GlobalProjection.cpp:43-111): low word = modelIndex << 26 | surfel id
@@ -299,15 +353,33 @@ void launch_remove_edges(int* labA, int* labB, const float* depth, const int* ar
         prof_mark(s, "k_remove_edges"); k_remove_edges<<<g, b, 0, s>>>(i % 2 == 0 ? labA : labB, i % 2 == 0 ? labB : labA, depth, area, W, H);
     }
 }
-void launch_seg_hist(const int* lab, const uint8_t* projID, const uint8_t* mask, int P, const uint8_t* idToIndex, int nModels, int nMasks,
+void launch_seg_hist(const int* lab, const uint8_t* projID, const uint8_t* mask, int P, const uint8_t* idToIndex, int nModels, const FrameHdr* hdr,
                      int* compModel, int* compMask, cudaStream_t s)
 {
-    prof_mark(s, "k_seg_hist"); k_seg_hist<<<(P + 255) / 256, 256, 0, s>>>(lab, projID, mask, P, idToIndex, nModels, nMasks, compModel, compMask);
+    prof_mark(s, "k_seg_hist"); k_seg_hist<<<(P + 255) / 256, 256, 0, s>>>(lab, projID, mask, P, idToIndex, nModels, hdr, compModel, compMask);
 }
-void launch_component_map(int nComponents, const int* area, const int* compModel, const int* compMask, int nModels, int nMasks,
+void launch_clear_hist(const uint32_t* ccCounter, const FrameHdr* hdr, int nModels, int* compModel, int* compMask, cudaStream_t s)
+{
+    prof_mark(s, "k_clear_hist"); k_clear_hist<<<148, 256, 0, s>>>(ccCounter, hdr, nModels, compModel, compMask);
+}
+void launch_component_map(const uint32_t* ccCounter, const int* area, const int* compModel, const int* compMask, int nModels, const FrameHdr* hdr,
                           const uint8_t* indexToId, int minMapped, int* mapToMask, int* absorb, int* maskPixels, cudaStream_t s)
 {
-    prof_mark(s, "k_component_map"); k_component_map<<<(nComponents + 127) / 128, 128, 0, s>>>(nComponents, area, compModel, compMask, nModels, nMasks, indexToId, minMapped, mapToMask, absorb, maskPixels);
+    prof_mark(s, "k_component_map"); k_component_map<<<148, 128, 0, s>>>(ccCounter, area, compModel, compMask, nModels, hdr, indexToId, minMapped, mapToMask, absorb, maskPixels);
+}
+void launch_vote(const FrameHdr* hdr, const VoteParams& vp, const int* maskPixels, const unsigned* maskOverlap, const uint32_t* ccCounter,
+                 uint8_t* maskToID, FrameResult* res, cudaStream_t s)
+{
+    prof_mark(s, "k_vote"); k_vote<<<1, 32, 0, s>>>(hdr, vp, maskPixels, maskOverlap, ccCounter, maskToID, res);
+}
+void launch_seg_tables(const SegTables& t, uint8_t* idToIndex, uint8_t* indexToId, uint8_t* isModel, cudaStream_t s)
+{
+    prof_mark(s, "k_seg_tables"); k_seg_tables<<<1, 256, 0, s>>>(t, idToIndex, indexToId, isModel);
+}
+void launch_frame_header(const FrameHdr& h, FrameHdr* d, cudaStream_t s) { prof_mark(s, "k_frame_header"); k_frame_header<<<1, 256, 0, s>>>(h, d); }
+void launch_person_table(const FrameHdr* hdr, int personClassID, uint8_t* isPerson, cudaStream_t s)
+{
+    prof_mark(s, "k_person_table"); k_person_table<<<1, 256, 0, s>>>(hdr, personClassID, isPerson);
 }
 void launch_seg_assign(const int* lab, const int* mapToMask, const uint8_t* ignore, int P, uint8_t* seg, cudaStream_t s)
 {
@@ -321,9 +393,9 @@ void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, 
 {
     prof_mark(s, "k_seg_final"); k_seg_final<<<(P + 255) / 256, 256, 0, s>>>(seg, lab, mapToMask, absorb, maskToID, P, out);
 }
-void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, int nMasks, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s)
+void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, const FrameHdr* hdr, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s)
 {
-    prof_mark(s, "k_apply_ignore"); k_apply_ignore<<<(P + 255) / 256, 256, 0, s>>>(mask, isPerson, nMasks, P, ignore, edges);
+    prof_mark(s, "k_apply_ignore"); k_apply_ignore<<<(P + 255) / 256, 256, 0, s>>>(mask, isPerson, hdr, P, ignore, edges);
 }
 void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s)
 {

@@ -17,6 +17,8 @@
 #include "mf_kernels.h"
 #include "mf_host.h"
 #include <float.h>
+#include <stdlib.h>
+#include <string.h>
 #include <string>
 
 namespace mfb {
@@ -381,6 +383,7 @@ struct TrackParams {
     float icpWeight, angleThres, distThres, sobelScale, maxDepthDelta;
     float minScale[3];
     int corrSlots;                     // photometric correspondences kept per CTA in shared memory (0: global scratch instead)
+    int phase;                         // 0: whole schedule in this launch; 1: SO(3) + level 2 only (cluster kernel); 2: resume at level 1
 };
 
 // sum of 32 per-lane values over the warp with 31 (64-bit) shuffles instead of 5*32: each step exchanges HALF of the remaining
@@ -441,6 +444,22 @@ MF_D void gridBarrier(unsigned* bar, unsigned target)
     __syncthreads();
 }
 
+// ---- thread-block cluster primitives (sm_90+): hardware barrier over the CTAs of a cluster, loads from a peer CTA's shared memory ----
+MF_D void clusterSync()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+MF_D unsigned clusterSize() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+MF_D double ldClusterF64(const double* localShared, unsigned rank)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(localShared);
+    unsigned ra; double v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(ra) : "memory");
+    return v;
+}
+
 // every CTA: sum the R partial rows (fixed order, fp64) -> tot[0..32); columns 29/30 carry the integer counters.
 // Warp w owns rows w, w+16, ...; the rows of a batch are all loaded before the first add (one L2 round trip for R <= 160).
 #define SUM_BATCH 10
@@ -467,6 +486,36 @@ MF_D void sumRows(const double* __restrict__ rows, unsigned R, double (*ws)[ROWF
         tot[threadIdx.x] = s2;
     }
     __syncthreads();
+}
+
+// One reduction of the schedule: CTA partial -> exchange -> every CTA holds the same totals (replicated solver state, no broadcast).
+//   CL == false: partial rows in global memory + software grid barrier over the G CTAs of the model (any grid size)
+//   CL == true : the G CTAs of the model form ONE thread-block cluster: the partial row stays in the CTA's shared memory
+//                (double-buffered), barrier.cluster replaces the L2 round trips of the software barrier, the rows of the peers are read
+//                through distributed shared memory.  Used for SO(3) pre-alignment and level 2 (19 k pixels: 14 iterations whose cost
+//                is the reduction, not the pixels).
+struct RedCtx { double* rowsBuf[2]; unsigned* bar; unsigned G, Gact, gen; };
+template <bool CL, int N>
+MF_D void reduceStep(const double* acc, int e0, int e1, bool active, RedCtx& rc, double (*red)[ROWF], double (*ws)[ROWF], double (*rowSh)[ROWF], double* tot)
+{
+    if (CL) {
+        ctaReduceStore<N>(acc, red, rowSh[rc.gen & 1], e0, e1);
+        const double* mine = rowSh[rc.gen & 1];
+        ++rc.gen;
+        __syncthreads();
+        clusterSync();
+        if (threadIdx.x < ROWF) {
+            double s2 = 0;
+            for (unsigned r = 0; r < rc.G; ++r) s2 += ldClusterF64(mine + threadIdx.x, r);
+            tot[threadIdx.x] = s2;
+        }
+        __syncthreads();
+    } else {
+        double* rows = rc.rowsBuf[rc.gen & 1];
+        if (active) ctaReduceStore<N>(acc, red, rows + (size_t)blockIdx.x * ROWF, e0, e1);
+        ++rc.gen; gridBarrier(rc.bar, rc.gen * rc.G);
+        sumRows(rows, rc.Gact, ws, tot);
+    }
 }
 
 MF_D void gradU8(const uint8_t* __restrict__ img, int W, int x, int y, float& gx, float& gy)
@@ -595,7 +644,18 @@ struct PixA {
 
 extern __shared__ int2 corrShared[];
 
-__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackParams tp)
+// optional stage clock of the persistent kernel (A/B build -DMF_TRACK_TIMING; read back by mf_debug_track_timing): CTA 0 of model 0
+// appends (tag, clock64) pairs at the stage boundaries of every reduction
+#ifdef MF_TRACK_TIMING
+__device__ long long g_trackTiming[8192];
+__device__ int g_trackTimingN;
+#define TT(tag) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { int q_ = g_trackTimingN; if (q_ + 2 <= 8192) { g_trackTiming[q_] = (tag); g_trackTiming[q_ + 1] = clock64(); g_trackTimingN = q_ + 2; } } } while (0)
+#else
+#define TT(tag) do { } while (0)
+#endif
+
+template <bool CL>
+MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
 {
     __shared__ TrackJob J;
     __shared__ TrackState S;
@@ -604,6 +664,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     __shared__ double ws[PT_WARPS][ROWF];
     __shared__ double tot[64];
     __shared__ double totR[ROWF];
+    __shared__ double rowSh[2][ROWF];                                  // cluster variant: this CTA's partial row, double buffered
     __shared__ float so3B[9], so3Kinv[9], so3Krlr[9];
     __shared__ double so3K[9], so3KinvD[9];
     __shared__ int flag;
@@ -613,10 +674,18 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         for (int k = threadIdx.x; k < (int)(sizeof(TrackJob) / 4); k += PT_THREADS) dst[k] = src[k];
     }
     TrackState* st = &S;
-    const unsigned G = gridDim.x;
-    unsigned gen = 0;                                                  // barriers passed (uniform)
+#ifdef MF_TRACK_TIMING
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_trackTimingN = 0;
+#endif
+    TT(1);
+    const unsigned G = gridDim.x;                                      // CTAs of this model (cluster variant: == cluster size)
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tp.phase == 2) {
+        // second launch of the frame: the replicated solver state as the cluster kernel left it
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(J.st);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&S);
+        for (int k = threadIdx.x; k < (int)(sizeof(TrackState) / 4); k += PT_THREADS) dst[k] = __ldcg(src + k);
+    } else if (threadIdx.x == 0) {
         // RGBDOdometry.cpp:331-345 initial state; the model's pose is device resident (written by the previous frame's epilogue or k_set_pose)
         const float* P = J.dpose->pose.m;
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) st->Rprev[r * 3 + c] = P[r * 4 + c]; st->tprev[r] = P[r * 4 + 3]; }
@@ -633,14 +702,15 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
         for (int k = 0; k < 6; ++k) st->lastb[k] = 0;
     }
     __syncthreads();
-    double* const rowsBuf[2] = {reinterpret_cast<double*>(J.partial), reinterpret_cast<double*>(J.partial) + (size_t)G * ROWF};
-    unsigned* const bar = J.bar;
+    RedCtx rc;
+    rc.rowsBuf[0] = reinterpret_cast<double*>(J.partial); rc.rowsBuf[1] = reinterpret_cast<double*>(J.partial) + (size_t)G * ROWF;
+    rc.bar = J.bar; rc.G = G; rc.Gact = G; rc.gen = 0;
     // photometric correspondences of this thread's pixels, slot = round * PT_THREADS + thread: written in phase A, read in phase B
     // by the same thread.  Shared memory when the launch reserved enough, else a private stripe of the model's scratch buffer.
     int2* const corr = tp.corrSlots ? corrShared : reinterpret_cast<int2*>(J.corres[0]) + (size_t)blockIdx.x * ((size_t)((tp.W * tp.H + G * PT_THREADS - 1) / (G * PT_THREADS)) * PT_THREADS);
 
     // ---------------- SO(3) pre-alignment on level-2 intensities (RGBDOdometry.cpp:272-345) ----------------
-    if (tp.so3) {
+    if (tp.so3 && tp.phase != 2) {
         const int W = tp.W >> 2, H = tp.H >> 2, N = W * H;
         // CTAs beyond the pixel count only wait at the barriers: fewer partial rows to sum
         const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
@@ -666,11 +736,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 so3B[threadIdx.x] = (float)(kr[0] * so3KinvD[cc] + kr[1] * so3KinvD[3 + cc] + kr[2] * so3KinvD[6 + cc]);
             }
             __syncthreads();
-            double* rows = rowsBuf[gen & 1];
-            if (active) {
-                double acc[11];
+            TT(11);
+            double acc[11];
 #pragma unroll
-                for (int k = 0; k < 11; ++k) acc[k] = 0;
+            for (int k = 0; k < 11; ++k) acc[k] = 0;
+            if (active) {
                 for (int k = tid; k < N; k += nthr) {
                     int y = k / W, x = k - y * W;
                     float3 ur = make_float3((float)x, (float)y, 1.0f);
@@ -703,10 +773,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                         acc[10] += 1.0;
                     }
                 }
-                ctaReduceStore<11>(acc, red, rows + (size_t)blockIdx.x * ROWF);
             }
-            ++gen; gridBarrier(bar, gen * G);
-            sumRows(rows, Gact, ws, tot);
+            TT(12);
+            rc.Gact = Gact;
+            reduceStep<CL, 11>(acc, 0, 0, active, rc, red, ws, rowSh, tot);
+            TT(15);
             if (threadIdx.x < 32) {
                 // host logic of RGBDOdometry.cpp:301-324 on warp 0: lane 0 takes the decisions, the 3x3 solve is warp-cooperative
                 int mode = 0;                                  // 0: converged, 1: diverged (restore), 2: step
@@ -744,6 +815,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 }
                 if (threadIdx.x == 0) flag = mode != 2;
             }
+            TT(16);
             __syncthreads();
             if (flag) break;
         }
@@ -754,7 +826,7 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     }
 
     // ---------------- pyramid levels, coarse to fine (RGBDOdometry.cpp:347-476) ----------------
-    for (int level = 2; level >= 0; --level) {
+    for (int level = (tp.phase == 2 ? 1 : 2); level >= (tp.phase == 1 ? 2 : 0); --level) {
         if (tp.iterations[level] == 0) continue;
         const int W = tp.W >> level, H = tp.H >> level, N = W * H;
         const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
@@ -825,12 +897,12 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
 
         for (int it = 0; it < tp.iterations[level]; ++it) {
             // ---- phase A: photometric correspondences + statistics, ICP normal equations ----
-            double* rowsA = rowsBuf[gen & 1];
-            if (active) {
-                double acc[NACC_ICP];
+            TT(100 + level);
+            double acc[NACC_ICP];
 #pragma unroll
-                for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.0;
-                int cnt = 0, sig = 0;
+            for (int k = 0; k < NACC_ICP; ++k) acc[k] = 0.0;
+            int cnt = 0, sig = 0;
+            if (active) {
                 const float3 tprev = make_float3(st->tprev[0], st->tprev[1], st->tprev[2]);
                 // arithmetic of one pixel (same order of accumulation as a one-pixel-at-a-time loop: a before b, rounds ascending)
                 auto stage3 = [&](const PixA& p, int k, int slot) {
@@ -892,10 +964,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                     stage3(a, k0, r * PT_THREADS + threadIdx.x);
                     if (two) stage3(b, k1, (r + 1) * PT_THREADS + threadIdx.x);
                 }
-                ctaReduceStore<NACC_ICP>(acc, red, rowsA + (size_t)blockIdx.x * ROWF, cnt, sig);
             }
-            ++gen; gridBarrier(bar, gen * G);
-            sumRows(rowsA, Gact, ws, tot);
+            TT(2);
+            rc.Gact = Gact;
+            reduceStep<CL, NACC_ICP>(acc, cnt, sig, active, rc, red, ws, rowSh, tot);
+            TT(5);
             if (tp.rgb) {
                 if (threadIdx.x == 0) {
                     // RGBDOdometry.cpp:388-401
@@ -914,11 +987,10 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                 __syncthreads();
                 if (flag) break;                                        // uniform over the whole grid: every CTA holds the same state
                 // ---- phase B: photometric normal equations with the weights of this iteration ----
-                double* rowsB = rowsBuf[gen & 1];
-                if (active) {
-                    double accR[NACC_RGB];
+                double accR[NACC_RGB];
 #pragma unroll
-                    for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.0;
+                for (int k = 0; k < NACC_RGB; ++k) accR[k] = 0.0;
+                if (active) {
                     const float sigmaSh = st->sigmaVal;
                     auto rgbRow = [&](int2 c, short2 g, float4 cp) {
                         const float diff = __int_as_float(c.y);
@@ -955,20 +1027,34 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
                         if (c0.x != -1) rgbRow(c0, g0, p0);
                         if (c1.x != -1) rgbRow(c1, g1, p1);
                     }
-                    ctaReduceStore<NACC_RGB>(accR, red, rowsB + (size_t)blockIdx.x * ROWF);
                 }
-                ++gen; gridBarrier(bar, gen * G);
+                TT(6);
                 // ICP totals stay in tot[0..28]; the photometric ones go behind them
-                sumRows(rowsB, Gact, ws, totR);
+                reduceStep<CL, NACC_RGB>(accR, 0, 0, active, rc, red, ws, rowSh, totR);
+                TT(9);
                 if (threadIdx.x < NACC_RGB) tot[NACC_ICP + threadIdx.x] = totR[threadIdx.x];
                 __syncthreads();
             }
             if (threadIdx.x < 32) solveAndUpdate(st, tot, tp.icp != 0, tp.rgb != 0, tp.icpWeight, cam, &sc);
             __syncthreads();
+            TT(10);
         }
         __syncthreads();
     }
 
+    TT(99);
+    if (tp.phase == 1) {
+        // hand the replicated state to the second launch (every CTA holds the same bits: rank 0 writes); a CTA must not exit while a
+        // peer may still read its shared memory
+        __syncthreads();
+        if (blockIdx.x == 0) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(&S);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(J.st);
+            for (int k = threadIdx.x; k < (int)(sizeof(TrackState) / 4); k += PT_THREADS) dst[k] = src[k];
+        }
+        if (CL) clusterSync();
+        return;
+    }
     // ---------------- result (RGBDOdometry.cpp:478-497) ----------------
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         float dx = st->tcurr[0] - st->tprev[0], dy = st->tcurr[1] - st->tprev[1], dz = st->tcurr[2] - st->tprev[2];
@@ -993,6 +1079,11 @@ __global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJ
     }
 }
 
+// whole schedule (phase 0) or levels 1..0 (phase 2): cooperative launch, one CTA per SM, software grid barrier
+__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackParams tp) { trackBody<false>(jobs, tp); }
+// SO(3) pre-alignment + level 2 (phase 1): one thread-block cluster per tracked model
+__global__ void __launch_bounds__(PT_THREADS, 1) k_track_cluster(const TrackJob* __restrict__ jobs, TrackParams tp) { trackBody<true>(jobs, tp); }
+
 // ------------------------------ host launchers ----------------------------------------
 float track_min_scale(int level)
 {
@@ -1014,7 +1105,7 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
 {
     // per-device launch limits (several contexts on different GPUs may live in one process): occupancy and the opt-in
     // dynamic shared memory attribute are properties of (function, device)
-    static int coResidentDev[64]; static size_t dynMaxDev[64]; static bool devInit[64];
+    static int coResidentDev[64]; static size_t dynMaxDev[64], dynMaxClDev[64]; static bool devInit[64]; static int clusterOkDev[64];
     int dev = 0; cudaCheck(cudaGetDevice(&dev), "cudaGetDevice");
     if (dev < 0 || dev >= 64) throw CudaError{"device ordinal above 63"};
     if (!devInit[dev]) {
@@ -1022,14 +1113,21 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_track_persistent, PT_THREADS, 0);
         if (e != cudaSuccess || perSM < 1) throw CudaError{std::string("k_track_persistent does not fit on an SM: ") + cudaGetErrorString(e)};
         coResidentDev[dev] = perSM * numSMs;
-        cudaFuncAttributes fa; cudaCheck(cudaFuncGetAttributes(&fa, k_track_persistent), "cudaFuncGetAttributes");
         int optin = 0; cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaFuncAttributes fa; cudaCheck(cudaFuncGetAttributes(&fa, k_track_persistent), "cudaFuncGetAttributes");
         dynMaxDev[dev] = (size_t)optin > fa.sharedSizeBytes + 2048 ? (size_t)optin - fa.sharedSizeBytes - 2048 : 0;
         cudaCheck(cudaFuncSetAttribute(k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMaxDev[dev]), "cudaFuncSetAttribute");
+        cudaCheck(cudaFuncGetAttributes(&fa, k_track_cluster), "cudaFuncGetAttributes");
+        dynMaxClDev[dev] = (size_t)optin > fa.sharedSizeBytes + 2048 ? (size_t)optin - fa.sharedSizeBytes - 2048 : 0;
+        // clusters of 16 CTAs are a non-portable size: opt in; if either attribute is refused the frame runs as one cooperative launch
+        clusterOkDev[dev] = 1;
+        if (cudaFuncSetAttribute(k_track_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMaxClDev[dev]) != cudaSuccess) clusterOkDev[dev] = 0;
+        if (cudaFuncSetAttribute(k_track_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) clusterOkDev[dev] = 0;
+        cudaGetLastError();
+        if (const char* env = getenv("MFB200_TRACK_CLUSTER")) if (env[0] == '0') clusterOkDev[dev] = 0;
         devInit[dev] = true;
     }
     const int coResident = coResidentDev[dev];
-    const size_t dynMax = dynMaxDev[dev];
     TrackParams tp;
     tp.W = W; tp.H = H; tp.cam = cam;
     tp.icp = (!rgbOnly && icpWeight > 0) ? 1 : 0;
@@ -1040,20 +1138,63 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     tp.angleThres = (float)sin(20.f * 3.14159254f / 180.f);
     tp.distThres = 0.10f; tp.sobelScale = (float)(1.0 / 8.0); tp.maxDepthDelta = 0.07f;
     for (int l = 0; l < 3; ++l) tp.minScale[l] = track_min_scale(l);
+    tp.phase = 0;
     int G = numSMs / nJobs;                      // one CTA per SM, the SMs split between the tracked models
     if (G * nJobs > coResident) G = coResident / nJobs;
     if (G > TRACK_MAX_BLOCKS / 2) G = TRACK_MAX_BLOCKS / 2;
     if (G < 1) throw CudaError{"too many tracked models for one cooperative launch"};
+    int launches = 0;
+    const TrackJob* jp = d_jobs;
+    // ---- SO(3) pre-alignment + level 2 on one thread-block cluster per model (hardware barrier + distributed shared memory) ----
+    bool clustered = false;
+    if (clusterOkDev[dev] && (tp.so3 || tp.iterations[2] > 0)) {
+        TrackParams t1 = tp; t1.phase = 1;
+        const int N2 = (W >> 2) * (H >> 2);
+        for (int C = 16; C >= 8 && !clustered; C >>= 1) {
+            const int roundsC = (N2 + C * PT_THREADS - 1) / (C * PT_THREADS);
+            size_t dynC = (size_t)roundsC * PT_THREADS * sizeof(int2);
+            if (t1.rgb && dynC <= dynMaxClDev[dev]) t1.corrSlots = roundsC * PT_THREADS; else { t1.corrSlots = 0; dynC = 0; }
+            if (t1.rgb && t1.corrSlots == 0) break;             // the global scratch stripe is sized for the persistent grid only
+            cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
+            cfg.gridDim = dim3(C, nJobs); cfg.blockDim = dim3(PT_THREADS); cfg.dynamicSmemBytes = dynC; cfg.stream = s;
+            cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int maxClusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&maxClusters, k_track_cluster, &cfg) != cudaSuccess || maxClusters < 1) { cudaGetLastError(); continue; }
+            if (maxClusters < nJobs && C > 8) continue;        // all models' clusters should be co-resident: try the smaller cluster
+            prof_mark(s, "k_track_cluster");
+            cudaError_t e = cudaLaunchKernelEx(&cfg, k_track_cluster, jp, t1);
+            if (e != cudaSuccess) { cudaGetLastError(); continue; }
+            clustered = true; ++launches;
+        }
+        if (!clustered) clusterOkDev[dev] = clusterOkDev[dev];  // keep trying on later frames: the failure may depend on nJobs
+    }
+    tp.phase = clustered ? 2 : 0;
     // photometric correspondences stay in shared memory when the per-CTA pixel share fits (8 B per pixel slot)
     const int rounds0 = (W * H + G * PT_THREADS - 1) / (G * PT_THREADS);
     size_t dyn = (size_t)rounds0 * PT_THREADS * sizeof(int2);
-    if (tp.rgb && dyn <= dynMax) tp.corrSlots = rounds0 * PT_THREADS; else { tp.corrSlots = 0; dyn = 0; }
+    if (tp.rgb && dyn <= dynMaxDev[dev]) tp.corrSlots = rounds0 * PT_THREADS; else { tp.corrSlots = 0; dyn = 0; }
     cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
     prof_mark(s, "k_track_persistent");
-    const TrackJob* jp = d_jobs;
     void* args[] = {(void*)&jp, (void*)&tp};
     cudaCheck(cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(G, nJobs), dim3(PT_THREADS), args, dyn, s), "cooperative launch (tracking)");
-    return 1;
+    return launches + 1;
+}
+
+// (tag, clock64) pairs of the last tracking launch (A/B build -DMF_TRACK_TIMING only); returns the number of int64 values written
+int debug_track_timing(long long* out, int cap)
+{
+#ifdef MF_TRACK_TIMING
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_trackTimingN, sizeof n);
+    if (n > cap) n = cap;
+    if (n > 0) cudaMemcpyFromSymbol(out, g_trackTiming, (size_t)n * sizeof(long long));
+    return n;
+#else
+    (void)out; (void)cap;
+    return 0;
+#endif
 }
 
 void launch_icp_only(const float4* vmapC, const float4* nmapC, const float4* vmapG, const float4* nmapG, int W, int H, Cam cam,

@@ -197,35 +197,50 @@ class SynthScene:
             prims.append((ob.kind, ob.size, To, inst, 10 + k))
             for pi, (pk, ps, Tp) in enumerate(ob.parts):
                 prims.append((pk, ps, To @ Tp, inst, 10 + k + 101 * (pi + 1)))
+        cull = self.layout == "table"          # per-primitive screen rectangle (the room layout keeps the full-image evaluation it was pinned with)
         for (kind, size, To, inst, surf) in prims:
             Ro, to = To[:3, :3], To[:3, 3]
+            sel = slice(None)
+            if cull:
+                rad = float(np.linalg.norm(size)) if kind == "box" else float(size[0])
+                pc = R.T @ (to - o)                                # primitive centre in the camera frame
+                if pc[2] - rad > 0.05:
+                    zn = pc[2] - rad
+                    u0 = int(np.floor(self.fx * (pc[0] - rad) / (zn if pc[0] - rad < 0 else pc[2] + rad) + self.cx)) - 2
+                    u1 = int(np.ceil(self.fx * (pc[0] + rad) / (zn if pc[0] + rad > 0 else pc[2] + rad) + self.cx)) + 2
+                    v0 = int(np.floor(self.fy * (pc[1] - rad) / (zn if pc[1] - rad < 0 else pc[2] + rad) + self.cy)) - 2
+                    v1 = int(np.ceil(self.fy * (pc[1] + rad) / (zn if pc[1] + rad > 0 else pc[2] + rad) + self.cy)) + 2
+                    u0, u1, v0, v1 = max(u0, 0), min(u1, W - 1), max(v0, 0), min(v1, H - 1)
+                    if u0 > u1 or v0 > v1:
+                        continue
+                    sel = (np.arange(v0, v1 + 1)[:, None] * W + np.arange(u0, u1 + 1)[None, :]).reshape(-1)
             ol = (o - to) @ Ro
-            dl = d @ Ro
-            ob = SynthObject(kind, size, To, None, 0)
-            if ob.kind == "sphere":
-                r = ob.size[0]
+            dl = d[sel] @ Ro
+            tb = tbest[sel]
+            if kind == "sphere":
+                r = size[0]
                 b = dl @ ol
                 a = np.einsum("ij,ij->i", dl, dl)
                 c = ol @ ol - r * r
                 disc = b * b - a * c
                 with np.errstate(invalid="ignore"):
                     tt = (-b - np.sqrt(disc)) / a
-                ok = (disc > 0) & (tt > 1e-6) & (tt < tbest)
+                ok = (disc > 0) & (tt > 1e-6) & (tt < tb)
             else:
                 with np.errstate(divide="ignore", invalid="ignore"):
-                    t1 = (-ob.size[None, :] - ol[None, :]) / dl
-                    t2 = (ob.size[None, :] - ol[None, :]) / dl
+                    t1 = (-size[None, :] - ol[None, :]) / dl
+                    t2 = (size[None, :] - ol[None, :]) / dl
                 with np.errstate(invalid="ignore"):
                     tn = np.max(np.minimum(t1, t2), axis=1)
                 tf = np.min(np.maximum(t1, t2), axis=1)
                 tt = tn
-                ok = (tn < tf) & (tn > 1e-6) & (tn < tbest)
-            tbest = np.where(ok, tt, tbest)
-            sid = np.where(ok, surf, sid)
-            mask = np.where(ok, inst, mask).astype(np.uint8)
+                ok = (tn < tf) & (tn > 1e-6) & (tn < tb)
+            tbest[sel] = np.where(ok, tt, tb)
+            sid[sel] = np.where(ok, surf, sid[sel])
+            mask[sel] = np.where(ok, inst, mask[sel]).astype(np.uint8)
             with np.errstate(invalid="ignore"):
                 pl = ol[None, :] + tt[:, None] * dl
-            hit_local = np.where(ok[:, None], pl, hit_local)
+            hit_local[sel] = np.where(ok[:, None], pl, hit_local[sel])
         depth = np.where(np.isfinite(tbest), tbest, 0.0)          # dirs.z == 1 -> camera-frame z == t
         if self.noise:
             rng = np.random.default_rng(self.seed * 100003 + t)
@@ -280,3 +295,28 @@ def dense_room_surfels(scene: SynthScene, n_target: int, time: int = 1, conf: fl
         out[k:k + n, 11] = spacing * 1.5
         k += n
     return out
+
+
+def _render_one(args):
+    kw, t = args
+    sc = _render_one.cache.get(repr(kw))
+    if sc is None:
+        sc = _render_one.cache[repr(kw)] = SynthScene(**kw)
+    rgb, depth, mask, Tc, d16 = sc.render(t)
+    return rgb, depth, np.ascontiguousarray(mask), d16
+
+
+_render_one.cache = {}
+
+
+def render_sequence(frames, workers=None, **scene_kw):
+    """[(rgb, depth, mask, d16)] for the frame indices in `frames`, rendered by a pool of processes (the ray caster is numpy and takes
+    ~0.6 s per 8-object VGA frame); the results do not depend on the number of workers"""
+    import multiprocessing as mp
+    import os
+    frames = list(frames)
+    workers = workers or min(len(frames), os.cpu_count() or 1, 16)
+    if workers <= 1 or len(frames) < 4:
+        return [_render_one((scene_kw, t)) for t in frames]
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_render_one, [(scene_kw, t) for t in frames], chunksize=max(1, len(frames) // (workers * 2)))

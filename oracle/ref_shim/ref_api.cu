@@ -161,4 +161,92 @@ int ref_geometric_edges(const float* vmap, const float* nmap, int W, int H, floa
     return (int)cudaGetLastError();
 }
 
+
+// SURVEY 8(d)(iii) "B-ref-cuda": the reference's OWN kernels for one model-frame of tracking, in the reference's calling pattern
+// (RGBDOdometry.cpp:153-225, 254-476; GPUConfig.h:51-58 fallback launch shapes): model-map preparation (copyMaps, 2 resizes per map,
+// 3 tranformMaps), the photometric pyramids (verticesToDepth, 2+2 pyrDowns, 3 Sobel pairs, 3 projectToPointCloud), <= 10 so3Step on
+// level 2, then 4/5/10 iterations of computeRgbResidual + icpStep + rgbStep on levels 2/1/0 -- every call with the launches,
+// cudaDeviceSynchronize, cudaMalloc/cudaFree and D2H copies it contains.  The host Eigen solve between the iterations is NOT included
+// (a few microseconds; it cannot be compiled here), the pose is held fixed.  Inputs are uploaded once; `reps` repetitions are timed.
+// Returns the total milliseconds per model-frame in ms[0] and the parts in ms[1..4] = maps, pyramids, so3, levels.  < 0 on error.
+int ref_track_schedule_time_ms(const float* vtex4, const float* ntex4, const float* vmapC[3], const float* nmapC[3], const unsigned char* lastImage0,
+                               const unsigned char* nextImage0, const float* R9, const float* t3, float fx, float fy, float cx, float cy, int W, int H,
+                               int so3Iters, int reps, float* ms)
+{
+    DeviceArray<float> vt, nt; vt.upload(vtex4, (size_t)W * H * 4); nt.upload(ntex4, (size_t)W * H * 4);
+    DeviceArray2D<float> vg[3], ng[3], vc[3], nc[3], lastDepth[3], nextDepth[3];
+    DeviceArray2D<unsigned char> lastImg[3], nextImg[3], mask[3];
+    DeviceArray2D<short> gx[3], gy[3];
+    DeviceArray2D<float3> cloud[3];
+    DeviceArray2D<DataTerm> corres[3];
+    for (int l = 0; l < 3; ++l) {
+        const int w = W >> l, h = H >> l;
+        vg[l].create(h * 3, w); ng[l].create(h * 3, w);
+        vc[l].upload(vmapC[l], w * sizeof(float), h * 3, w); nc[l].upload(nmapC[l], w * sizeof(float), h * 3, w);
+        lastDepth[l].create(h, w); nextDepth[l].create(h, w); lastImg[l].create(h, w); nextImg[l].create(h, w); mask[l].create(h, w);
+        gx[l].create(h, w); gy[l].create(h, w); cloud[l].create(h, w); corres[l].create(h, w);
+    }
+    lastImg[0].upload(lastImage0, W, H, W); nextImg[0].upload(nextImage0, W, H, W);
+    DeviceArray<JtJJtrSE3> sumSE3, outSE3; sumSE3.create(MAX_THREADS); outSE3.create(1);
+    DeviceArray<JtJJtrSO3> sumSO3, outSO3; sumSO3.create(MAX_THREADS); outSO3.create(1);
+    DeviceArray<int2> sumRes; sumRes.create(MAX_THREADS);
+    const mat33 R = toMat(R9); const float3 t = make_float3(t3[0], t3[1], t3[2]);
+    float Ri9[9]; for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ri9[r * 3 + c] = R9[c * 3 + r];
+    const mat33 Rinv = toMat(Ri9);
+    const float I9[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    float A36[36], b6[6], res2[2], A9[9], b3[3];
+    const int iterations[3] = {10, 5, 4};
+    const float minGrad[3] = {5, 3, 1};
+    const float sobelScale = 1.0f / 8.0f;
+    cudaEvent_t e[5]; for (int k = 0; k < 5; ++k) cudaEventCreate(&e[k]);
+    float acc[5] = {0, 0, 0, 0, 0};
+    for (int rep = -1; rep < reps; ++rep) {                        // rep -1: warm-up
+        cudaEventRecord(e[0]);
+        // RGBDOdometry::initICPModel (RGBDOdometry.cpp:153-185)
+        copyMaps(vt, nt, vg[0], ng[0]);
+        for (int l = 1; l < 3; ++l) { resizeVMap(vg[l - 1], vg[l]); resizeNMap(ng[l - 1], ng[l]); }
+        for (int l = 0; l < 3; ++l) tranformMaps(vg[l], ng[l], R, t, vg[l], ng[l]);
+        cudaDeviceSynchronize();
+        cudaEventRecord(e[1]);
+        // populateRGBDData x2 + derivative images + clouds (RGBDOdometry.cpp:187-225, 245-250, 349); the BGR->intensity kernel reads a
+        // texture reference that CUDA 12 removed, so the intensity images are given
+        verticesToDepth(vt, lastDepth[0], 6.0f); verticesToDepth(vt, nextDepth[0], 6.0f);
+        for (int l = 0; l + 1 < 3; ++l) {
+            pyrDownGaussF(lastDepth[l], lastDepth[l + 1]); pyrDownGaussF(nextDepth[l], nextDepth[l + 1]);
+            pyrDownUcharGauss(lastImg[l], lastImg[l + 1]); pyrDownUcharGauss(nextImg[l], nextImg[l + 1]);
+        }
+        for (int l = 0; l < 3; ++l) computeDerivativeImages(nextImg[l], gx[l], gy[l]);
+        for (int l = 0; l < 3; ++l) { CameraModel intr(fx, fy, cx, cy); projectToPointCloud(lastDepth[l], cloud[l], intr, l); }
+        cudaDeviceSynchronize();
+        cudaEventRecord(e[2]);
+        // SO(3) pre-alignment (RGBDOdometry.cpp:272-345), level 2
+        {
+            const int l = 2; const float s = 1.0f / (1 << l);
+            const float K[9] = {fx * s, 0, cx * s, 0, fy * s, cy * s, 0, 0, 1};
+            const float Kinv[9] = {1 / (fx * s), 0, -cx / fx, 0, 1 / (fy * s), -cy / fy, 0, 0, 1};
+            for (int i = 0; i < so3Iters; ++i) so3Step(lastImg[l], nextImg[l], toMat(I9), toMat(Kinv), toMat(K), sumSO3, outSO3, A9, b3, res2, 160, 64);
+        }
+        cudaEventRecord(e[3]);
+        // pyramid levels (RGBDOdometry.cpp:347-476)
+        for (int l = 2; l >= 0; --l) {
+            const float s = 1.0f / (1 << l);
+            const CameraModel intr(fx * s, fy * s, cx * s, cy * s);
+            const float kt[3] = {0, 0, 0};
+            const float minScale = (minGrad[l] * minGrad[l]) / (sobelScale * sobelScale);
+            for (int j = 0; j < iterations[l]; ++j) {
+                int sigma = 0, count = 0;
+                computeRgbResidual(minScale, gx[l], gy[l], lastDepth[l], nextDepth[l], lastImg[l], nextImg[l], mask[l], mask[l], corres[l], sumRes, 0.07f,
+                                   make_float3(kt[0], kt[1], kt[2]), toMat(I9), sigma, count, 256, 336, 0, 0);
+                icpStep(R, t, vc[l], nc[l], Rinv, t, intr, vg[l], ng[l], 0.10f, 0.342020143f, sumSE3, outSE3, A36, b6, res2, 128, 112, 0, mask[l], 0);
+                rgbStep(corres[l], (float)(count > 0 ? count : 1), cloud[l], intr.fx, intr.fy, gx[l], gy[l], sobelScale, sumSE3, outSE3, A36, b6, 128, 112);
+            }
+        }
+        cudaDeviceSynchronize();
+        cudaEventRecord(e[4]); cudaEventSynchronize(e[4]);
+        if (rep >= 0) for (int k = 0; k < 4; ++k) { float m = 0; cudaEventElapsedTime(&m, e[k], e[k + 1]); acc[k + 1] += m; acc[0] += m; }
+    }
+    for (int k = 0; k < 5; ++k) { ms[k] = acc[k] / (float)reps; cudaEventDestroy(e[k]); }
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 }  // extern "C"

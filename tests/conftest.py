@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# The CPU oracle's OpenMP sections scale to ~32 threads; on a 128-core GPU box the runtime's default (one thread per core) makes the
+# many short parallel regions slower, not faster.  Read by libgomp when the oracle library is loaded.
+os.environ.setdefault("OMP_NUM_THREADS", str(min(os.cpu_count() or 1, 32)))
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

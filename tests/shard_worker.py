@@ -135,7 +135,8 @@ def gpu_mode(out_dir, nframes, track_all):
     for i, m in enumerate(models):
         if smf.owner(i) == rank:
             out[f"map{i}"] = m.downloadMap()
-    out["bytes_collective"] = np.array(smf.bytes_collective)
+    st = smf.stats()
+    out["bytes_collective"] = np.array(st["bytes"]); out["transport"] = np.array(st["transport"]); out["nranks"] = np.array(st["nranks"])
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **out)
     smf.close()
     dist.destroy_process_group()

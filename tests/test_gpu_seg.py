@@ -66,5 +66,8 @@ def test_multi_model_with_both_closes():
     """the multi-model schedule with morphEdgeIterations = 3 and morphMaskIterations = 2 (the CUDA path used to throw on the
     latter): lifecycle, segmentation and ID images against the free-running oracle"""
     from tests.test_gpu_multi import run, check
-    log = run(20, track_all=False, segMorphEdgeIterations=3, segMorphEdgeRadius=1, segMorphMaskIterations=2, segMorphMaskRadius=2, tag="closes")
+    from tests.test_gpu_multi import check_exact
+    log = run(20, track_all=False, segMorphEdgeIterations=3, segMorphEdgeRadius=1, segMorphMaskIterations=2, segMorphMaskRadius=2, modelSpawnOffset=5,
+              tag="closes")
     check(log, 2)
+    check_exact(log, 2)

@@ -1,7 +1,8 @@
 """Object-sharded pipeline against the single-process pipeline on the same replay: the shards must
 reproduce it BIT FOR BIT (same kernels on the same inputs; the only cross-rank arithmetic is an integer MIN).
-Two ranks: NCCL with one GPU each when the box has two GPUs, else gloo with both ranks on cuda:0 (host-staged
-collectives, same C-ABI phases) -- so the round-end single-GPU run covers the sharded code path as well."""
+Two ranks: with two GPUs the in-library NCCL exchange (mf_shard_process_frame: broadcast / all-gather / 64-bit MIN all-reduce issued
+by the library on its stream), else gloo with both ranks on cuda:0 (host-staged transport over the phase-split ABI, same kernels) --
+so the round-end single-GPU run covers the sharded code path as well."""
 from __future__ import annotations
 
 import numpy as np
@@ -51,26 +52,15 @@ def test_two_shards_equal_one_process(tmp_path, track_all):
     for t in range(nframes):
         for k in ("ids", "cls", "pose", "seg", "segsum", "own"):                  # replicated state is identical on every rank
             assert np.array_equal(ranks[0][f"{k}{t}"], ranks[1][f"{k}{t}"]), (t, k)
-    if not track_all:
-        # only the background is tracked, alone in its launch in both runs: same launch shape, same reduction order => bit for bit
-        for t in range(nframes):
-            z = ranks[0]
-            for k in ("ids", "cls", "pose", "seg", "segsum"):
-                assert np.array_equal(z[f"{k}{t}"], ref[f"{k}{t}"]), (t, k)
-            cnt = np.where(ranks[0][f"cnt{t}"] >= 0, ranks[0][f"cnt{t}"], ranks[1][f"cnt{t}"])
-            assert np.array_equal(cnt, ref[f"cnt{t}"]), (t, cnt, ref[f"cnt{t}"])
-        for i in range(nmodels_final):                                            # the surfel stores themselves
-            m = ranks[int(owners[i])][f"map{i}"]
-            assert m.shape == ref[f"map{i}"].shape and np.array_equal(m.view(np.uint32), ref[f"map{i}"].view(np.uint32)), i
-    else:
-        # tracked objects: one process batches all models into one launch (SMs split between them), a shard tracks only its own with
-        # the whole GPU: different partial-sum shapes, i.e. rounding-size differences in the normal equations.  The background follows
-        # to ~1e-7; a fresh object model is near singular (tests/test_gpu_multi.py measures the oracle's own envelope: 1e-4 .. 1e-2).
-        for t in range(nframes):
-            z = ranks[0]
-            assert np.array_equal(z[f"ids{t}"], ref[f"ids{t}"]) and np.array_equal(z[f"cls{t}"], ref[f"cls{t}"]), t
-            d = np.abs(z[f"pose{t}"] - ref[f"pose{t}"]).reshape(len(z[f"ids{t}"]), -1).max(1)
-            assert d[0] < 2e-5, (t, d)
-            assert np.all(d < 5e-2), (t, d)
-            cnt = np.where(ranks[0][f"cnt{t}"] >= 0, ranks[0][f"cnt{t}"], ranks[1][f"cnt{t}"])
-            assert np.all(np.abs(cnt - ref[f"cnt{t}"]) <= np.maximum(60, ref[f"cnt{t}"] // 20)), (t, cnt, ref[f"cnt{t}"])
+    # fp64 sums rounded to float do not depend on the launch shape (one process batches all tracked models into one launch with the SMs
+    # split between them, a shard tracks only its own models with the whole GPU): the shards reproduce the single process BIT FOR BIT,
+    # tracked objects included -- poses, ids, segmentation, counts on every frame and the surfel stores at the end.
+    for t in range(nframes):
+        z = ranks[0]
+        for k in ("ids", "cls", "pose", "seg", "segsum"):
+            assert np.array_equal(z[f"{k}{t}"], ref[f"{k}{t}"]), (t, k)
+        cnt = np.where(ranks[0][f"cnt{t}"] >= 0, ranks[0][f"cnt{t}"], ranks[1][f"cnt{t}"])
+        assert np.array_equal(cnt, ref[f"cnt{t}"]), (t, cnt, ref[f"cnt{t}"])
+    for i in range(nmodels_final):                                            # the surfel stores themselves
+        m = ranks[int(owners[i])][f"map{i}"]
+        assert m.shape == ref[f"map{i}"].shape and np.array_equal(m.view(np.uint32), ref[f"map{i}"].view(np.uint32)), i
