@@ -411,6 +411,9 @@ def run_ours(args, rank, world):
         "clocks": st["clocks"],
         "roofline": roofline_of(st["stages"], st["S_live"], K, Wm, st["ms_prof"]),
     }
+    if os.environ.get("MFB200_BENCH_LEGS", "1") == "0":          # A/B runs of the main line only
+        print(json.dumps(out))
+        return
     out["cpu_baseline"] = cpu_baseline(sample_frames=4)
 
     def leg(name, fn):

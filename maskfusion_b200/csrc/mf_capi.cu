@@ -272,6 +272,7 @@ extern "C" int mf_download_index_map(mf_context* ctx, int i, uint32_t* idx, floa
 {
     MF_TRY MF_NEED(ctx) MF_MODEL(ctx, i) MF_OWNED(m)
     MaskFusion* o = ctx->mf;
+    m->flushIndex();
     d2h(o, idx, m->idx.p, o->P); d2h(o, vc, m->vertConf.p, o->P); d2h(o, ct, m->colorTime.p, o->P); d2h(o, nr, m->normRad.p, o->P);
     o->sync(); return 0;
     MF_CATCH(-1)

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <stdio.h>
 #include <limits.h>
+#include <stdlib.h>
 
 namespace mfb {
 
@@ -225,14 +226,29 @@ float Model::computeFusionWeight(float weightMultiplier) const
 void Model::predictIndices(int time, float depthCutoff, int timeDelta, bool forClean)
 {
     MaskFusion* o = owner;
+    if (forClean && o->fuseIndexIntoClean) {                          // lazily: see idxDeferred
+        idxDeferred = true; idxTime = time; idxDelta = timeDelta; idxDepth = depthCutoff;
+        return;
+    }
+    idxDeferred = false;
     launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, time, timeDelta, key, idx, vertConf,
                            colorTime, normRad, forClean ? cleanTex.p : nullptr, o->stream);
+    o->launches += 2;
+}
+
+void Model::flushIndex()
+{
+    if (!idxDeferred) return;
+    idxDeferred = false;
+    MaskFusion* o = owner;
+    launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, idxDepth, idxTime, idxDelta, key, idx, vertConf, colorTime, normRad, cleanTex.p, o->stream);
     o->launches += 2;
 }
 
 void Model::fuse(int time, float depthCutoff, float weightMultiplier)
 {
     MaskFusion* o = owner;
+    flushIndex();
     float md = depthCutoff < maxDepth ? depthCutoff : maxDepth;      // Model.cpp:527 (headless: bounding box empty, N7)
     float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
     launch_associate(o->rgb, o->depthRaw, o->depthFilt, o->mask, idx, vertConf, normRad, dpose, o->cam, o->W, o->H, md, time,
@@ -246,11 +262,16 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
     MaskFusion* o = owner;
     float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
     int other = 1 - target, otherCount = 1 - countSel;
+    // the pending index projection rides in pass 1 when it uses this call's time gate (always, in the frame schedule)
+    const bool fused = idxDeferred && idxTime == time && idxDelta == timeDelta && (size_t)capacity + (size_t)o->P < 0x80000000ull;   // bit 31 of a candidate entry is a flag
+    if (!fused) flushIndex();
+    IndexFused f{key.p, idx.p, vertConf.p, colorTime.p, normRad.p, cleanTex.p, idxDepth};
+    idxDeferred = false;
     launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, dpose, o->cam, o->W, o->H,
                  time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, cleanTex, o->depthFilt, o->mask, keep, blockSums,
-                 cand, candCount, o->stream);
+                 cand, candCount, o->stream, fused ? &f : nullptr);
     target = other; countSel = otherCount;
-    o->launches += 5;
+    o->launches += fused ? 6 : 5;
 }
 
 void Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDelta)
@@ -272,6 +293,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     cudaCheck(cudaGetDeviceProperties(&prop, dev), "cudaGetDeviceProperties");
     numSMs = prop.multiProcessorCount;
     set_num_sms(numSMs);
+    if (const char* env = getenv("MFB200_FUSE_INDEX")) fuseIndexIntoClean = env[0] != '0';
     W = c.width; H = c.height; P = W * H;
     if (W % 4 || H % 4) throw CudaError{"width and height must be multiples of 4 (3-level pyramid)"};
     cam = Cam{c.fx, c.fy, c.cx, c.cy};

@@ -119,6 +119,10 @@ public:
     Mat4 lastTransform;
     std::vector<double> poseLog;            // 8 doubles per entry
     bool tracked = false;                   // took part in the tracking launch of the frame in flight (deferred bookkeeping)
+    // predictIndices(forClean) is lazy: when Model::clean follows with the same time gate (the frame schedule, MaskFusion.cpp:550-562) the
+    // projection rides inside the clean pass; any reader of the index map in between (fuse, the read-backs) runs it stand-alone first
+    bool idxDeferred = false; int idxTime = 0, idxDelta = 0; float idxDepth = 0.f;
+    void flushIndex();
 };
 
 class MaskFusion {
@@ -189,6 +193,7 @@ public:
 
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;
+    bool fuseIndexIntoClean = true;         // A/B: MFB200_FUSE_INDEX=0 keeps Model::predictIndices + Model::clean as two streams over the store
     int tick = 1;
     int64_t launches = 0;
     std::vector<std::unique_ptr<Model>> models;

@@ -168,10 +168,13 @@ void launch_associate(const uchar4* rgb, const float* depthRaw, const float* dep
                       float weightMultiplier, uint8_t maskID, uint8_t* flag, uint32_t* best, float4* const* meas, uint32_t* slot, cudaStream_t s);
 void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const* meas, uint32_t* slot, int P, int time,
                         const SurfelPlanes& sp, cudaStream_t s);
+// index-map outputs of a Model::predictIndices that is carried out INSIDE the clean pass (one stream over the store instead of two)
+struct IndexFused { uint64_t* key; uint32_t* idx; float4* vertConf; float4* colorTime; float4* normRad; float4* cleanTex; float maxDepth; };
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* dpose, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const float4* cleanTex,
-                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s);
+                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s,
+                  const IndexFused* fused = nullptr);
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth,
                              float confThreshold, int time, int maxTime, int timeDelta, const float4* rayTab, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,

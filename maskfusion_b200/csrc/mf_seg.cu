@@ -135,7 +135,7 @@ void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int ra
 namespace mfb {
 
 // ---- 4-connected components: union-find with atomicMin (root = smallest pixel index) ----
-MF_D int ccFind(const int* __restrict__ L, int x)
+MF_D int ccFind(const int* L, int x)       // (no __restrict__: L is being modified by other threads' atomics while we walk it)
 {
     int p = L[x];
     while (p != x) { x = p; p = L[x]; }
@@ -152,22 +152,50 @@ MF_D void ccUnion(int* L, int a, int b)
         a = old;
     }
 }
-__global__ void k_cc_init(const uint8_t* __restrict__ img, int P, int* __restrict__ L, int* __restrict__ area, uint32_t* counter)
+// Two-level union-find (the single global pass over all pixels took 300 us: every pixel hooked roots through L2 atomics, ncu r01i):
+//   k_cc_tile   : one 32x16 tile per CTA, union-find in SHARED memory over the tile's pixels (left / up neighbours inside the tile);
+//                 every pixel leaves with the GLOBAL index of its tile-local root (roots are the smallest index, and local raster order is
+//                 global raster order inside a tile, so the invariant "root = smallest pixel index of the set" holds for the global pass)
+//   k_cc_border : only the pixels on a tile's left / top edge union with their neighbour across the edge, in global memory
+#define CC_TW 32
+#define CC_TH 16
+__global__ void __launch_bounds__(CC_TW * CC_TH) k_cc_tile(const uint8_t* __restrict__ img, int W, int H, int* __restrict__ L, int* __restrict__ area, uint32_t* counter)
 {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *counter = 0;
-    if (i >= P) return;
-    L[i] = img[i] ? i : -1;
-    area[i] = 0;
+    __shared__ int sl[CC_TW * CC_TH];
+    __shared__ uint8_t sf[CC_TW * CC_TH];
+    const int tx = threadIdx.x & (CC_TW - 1), ty = threadIdx.x / CC_TW, t = threadIdx.x;
+    const int x = blockIdx.x * CC_TW + tx, y = blockIdx.y * CC_TH + ty;
+    const bool in = x < W && y < H;
+    const int i = y * W + x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && t == 0) *counter = 0;
+    const uint8_t f = in ? img[i] : 0;
+    sf[t] = f; sl[t] = t;
+    __syncthreads();
+    if (f) {
+        if (tx > 0 && sf[t - 1]) ccUnion(sl, t, t - 1);
+        if (ty > 0 && sf[t - CC_TW]) ccUnion(sl, t, t - CC_TW);
+    }
+    __syncthreads();
+    if (in) {
+        int r = -1;
+        if (f) { const int lr = ccFind(sl, t); r = (blockIdx.y * CC_TH + lr / CC_TW) * W + blockIdx.x * CC_TW + (lr & (CC_TW - 1)); }
+        L[i] = r;
+        area[i] = 0;
+    }
 }
-__global__ void k_cc_merge(const uint8_t* __restrict__ img, int W, int H, int* L)
+__global__ void k_cc_border(const uint8_t* __restrict__ img, int W, int H, int* L)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= W || y >= H) return;
-    int i = y * W + x;
-    if (!img[i]) return;
-    if (x > 0 && img[i - 1]) ccUnion(L, i, i - 1);
-    if (y > 0 && img[i - W]) ccUnion(L, i, i - W);
+    // thread k < nV: a pixel on a vertical tile edge (column multiple of CC_TW); else one on a horizontal edge (row multiple of CC_TH)
+    const int nCols = (W - 1) / CC_TW, nRows = (H - 1) / CC_TH;
+    const int nV = nCols * H, nH = nRows * W;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nV) {
+        const int y = k / nCols, x = (k - y * nCols + 1) * CC_TW, i = y * W + x;
+        if (img[i] && img[i - 1]) ccUnion(L, i, i - 1);
+    } else if (k < nV + nH) {
+        const int q = k - nV, r = q / W, x = q - r * W, y = (r + 1) * CC_TH, i = y * W + x;
+        if (img[i] && img[i - W]) ccUnion(L, i, i - W);
+    }
 }
 // roots get a dense id 1..n-1 (0 = background/edge); area is accumulated per dense id
 __global__ void k_cc_number(int* __restrict__ L, int P, int* __restrict__ dense, uint32_t* counter)
@@ -340,9 +368,11 @@ __global__ void k_proj_resolve(unsigned long long* __restrict__ key, int P, cons
 
 void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, uint32_t* counter, cudaStream_t s)
 {
-    int P = W * H; dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
-    prof_mark(s, "k_cc_init"); k_cc_init<<<(P + 255) / 256, 256, 0, s>>>(img, P, L, area, counter);
-    prof_mark(s, "k_cc_merge"); k_cc_merge<<<g, b, 0, s>>>(img, W, H, L);
+    int P = W * H;
+    dim3 gt((W + CC_TW - 1) / CC_TW, (H + CC_TH - 1) / CC_TH);
+    prof_mark(s, "k_cc_tile"); k_cc_tile<<<gt, CC_TW * CC_TH, 0, s>>>(img, W, H, L, area, counter);
+    const int nEdge = ((W - 1) / CC_TW) * H + ((H - 1) / CC_TH) * W;
+    if (nEdge > 0) { prof_mark(s, "k_cc_border"); k_cc_border<<<(nEdge + 255) / 256, 256, 0, s>>>(img, W, H, L); }
     prof_mark(s, "k_cc_number"); k_cc_number<<<(P + 255) / 256, 256, 0, s>>>(L, P, dense, counter);
     prof_mark(s, "k_cc_relabel"); k_cc_relabel<<<(P + 255) / 256, 256, 0, s>>>(L, dense, P, lab, area);
 }

@@ -344,8 +344,13 @@ MF_D bool cleanFinish(float4& vp, float4& vc, float x, float y, float lpz, int c
 __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, float4* __restrict__ col, const uint32_t* __restrict__ countPtr,
                                                   const uint8_t* __restrict__ aflag, float4* __restrict__ m0, float4* __restrict__ m1, int Ppix,
                                                   CleanParams P, const DevPose* __restrict__ dpose, const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
-                                                  uint8_t* __restrict__ keep, uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount)
+                                                  uint8_t* __restrict__ keep, uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount,
+                                                  unsigned long long* __restrict__ indexKey, float indexMaxDepth)
 {
+    // indexKey != nullptr: this pass ALSO is the index-map projection of Model::predictIndices that precedes Model::clean in the frame
+    // (MaskFusion.cpp:550-562: same store, same pose, same time gate): one 32-byte-per-surfel stream instead of two.  The index map is
+    // resolved after this kernel and read by pass 2 only.  A surfel that is drawn into the index map but needs no window (x or y exactly
+    // 0, time gate at equality) is finished by pass 2 as well (flag bit 31): its confidence must not change before the resolve reads it.
     // candidates are staged per block in shared memory and flushed in chunks: one device-wide atomic per ~2k candidates
     // (a warp-aggregated global append put ~130k returning atomics on ONE L2 address: 62 % busy slice, ncu r01b)
     __shared__ uint32_t sBuf[CAND_BUF];
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
     uint32_t staged = 0;                                                 // block-uniform copy of sCount
     for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
         const uint32_t e = base + threadIdx.x;
-        bool valid = false, need = false;
+        bool valid = false, need = false, noWindow = false;
         const bool isOld = e < count;
         float4 vp = make_float4(0, 0, 0, 0), vc = vp;
         if (isOld) { vp = pos[e]; vc = col[e]; valid = true; }
@@ -370,6 +375,16 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
             float x = ((P.cam.fx * lp.x) / lp.z) + P.cam.cx;
             float y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
             need = ftime - vc.w < P.ftimeDelta && lp.z > 0 && x > 0 && y > 0 && x < cols && y < rows;
+            if (indexKey && isOld && !(lp.z > indexMaxDepth || lp.z <= 0 || ftime - vc.w > P.ftimeDelta)) {      // k_index_project, verbatim
+                const float zn = lp.z / indexMaxDepth;
+                const float fx_ = floorf(x), fy_ = floorf(y);
+                if (zn < 1.0f && fx_ >= 0 && fy_ >= 0 && fx_ < cols && fy_ < rows) {
+                    const unsigned long long k = ((unsigned long long)__float_as_uint(zn) << 32) | e;
+                    unsigned long long* dst = indexKey + ((int)fy_ * P.W + (int)fx_);
+                    if (k < *dst) atomicMin(dst, k);
+                    if (!need) { need = true; noWindow = true; }
+                }
+            }
             if (!need) {
                 const float w0 = vp.w, t0 = vc.w;
                 bool k = cleanFinish(vp, vc, x, y, lp.z, 0, 0, P, depthFilt, mask);
@@ -383,7 +398,7 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
             uint32_t wbase = 0;
             if (lane == 0) wbase = atomicAdd(&sCount, (uint32_t)__popc(nb));
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (need) sBuf[wbase + __popc(nb & ((1u << lane) - 1))] = e;
+            if (need) sBuf[wbase + __popc(nb & ((1u << lane) - 1))] = noWindow ? (e | 0x80000000u) : e;
         }
         staged += (uint32_t)__syncthreads_count(need);
         if (staged > CAND_BUF - 256) {                                   // uniform: the next iteration might not fit
@@ -412,7 +427,9 @@ __global__ void __launch_bounds__(256, 4) k_clean_p2(float4* __restrict__ pos, f
     const uint32_t count = *countPtr, n = *candCount;
     const float cols = (float)P.W, rows = (float)P.H;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t e = cand[j];
+        const uint32_t ce_ = cand[j];
+        const bool noWindow = (ce_ >> 31) != 0;                        // drawn into the index map by pass 1 but outside the window's domain
+        const uint32_t e = ce_ & 0x7fffffffu;
         const bool isOld = e < count;
         const uint32_t p = e - count;
         float4 vp, vc, vn;
@@ -423,8 +440,8 @@ __global__ void __launch_bounds__(256, 4) k_clean_p2(float4* __restrict__ pos, f
         float y = ((P.cam.fy * lp.y) / lp.z) + P.cam.cy;
         float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
         CleanEntry ce; ce.xn = x / cols; ce.yn = y / rows; ce.lx = lp.x; ce.ly = lp.y; ce.lz = lp.z; ce.init = vc.z; ce.rad = vn.w; ce.lnz = fabsf(ln.z);
-        int c1, c2;
-        cleanWindow(ce, P, cleanTex, c1, c2);
+        int c1 = 0, c2 = 0;
+        if (!noWindow) cleanWindow(ce, P, cleanTex, c1, c2);
         bool k = cleanFinish(vp, vc, x, y, lp.z, c1, c2, P, depthFilt, mask);
         if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
         else { m0[p].w = vp.w; m1[p].w = vc.w; }
@@ -932,7 +949,8 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const float4* cleanTex,
-                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s)
+                  const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s,
+                  const IndexFused* fused)
 {
     CleanParams P;
     P.tinv = Rt{};                          // filled from the device-resident pose inside the kernels
@@ -940,7 +958,12 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
     P.outlierCoeff = outlierCoeff; P.maskID = maskID;
     int Ppix = W * H;
     int blocks = persistentBlocks(4);
-    prof_mark(s, "k_clean_p1"); k_clean_p1<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, count, aflag, meas[0], meas[1], Ppix, P, tinv, depthFilt, mask, keep, cand, candCount);
+    prof_mark(s, "k_clean_p1"); k_clean_p1<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, count, aflag, meas[0], meas[1], Ppix, P, tinv, depthFilt, mask, keep, cand, candCount,
+                                                                               fused ? (unsigned long long*)fused->key : nullptr, fused ? fused->maxDepth : 0.f);
+    if (fused) {           // Model::predictIndices, second half: the index map of the store as clean sees it
+        prof_mark(s, "k_index_resolve"); k_index_resolve<<<(Ppix + 255) / 256, 256, 0, s>>>(src.pos, src.col, src.nrm, tinv, Ppix, (unsigned long long*)fused->key, fused->idx, fused->vertConf,
+                                                                                          fused->colorTime, fused->normRad, fused->cleanTex);
+    }
     prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, cleanTex, depthFilt,
                                                                                mask, keep, cand, candCount);
     prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<blocks, SCAN_BLOCK, 0, s>>>(keep, count, Ppix, blockSums, candCount);
