@@ -383,15 +383,21 @@ def run_ours(args, rank, world):
     import torch
     import maskfusion_b200 as mfb
     local = int(os.environ.get("LOCAL_RANK", 0))
+    pre = None
+    if world > 1 and rank == 0:
+        # the loader rank renders the replay before CUDA / NCCL exist in this process (the renderer forks worker processes)
+        n_pre = min(34 + args.warmup + args.steps, 160)
+        pre = multi_frames(8, n_pre)
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(minutes=20))
     K, Wm = args.steps, args.warmup
     stream = torch.cuda.Stream()          # explicit: the default stream's NULL handle would make mf_create open a private stream the events cannot see
     torch.cuda.set_stream(stream)
     if world > 1:
-        return run_sharded(args, rank, world, torch, mfb, stream, local)
+        return run_sharded(args, rank, world, torch, mfb, stream, local, pre)
     st = static_leg(torch, mfb, stream, local, rank, world, K, Wm)
     P = W * H
     fps = K / (st["ms_dev"] / 1e3)
@@ -476,7 +482,7 @@ def run_ours(args, rank, world):
     print(json.dumps(out))
 
 
-def run_sharded(args, rank, world, torch, mfb, stream, local):
+def run_sharded(args, rank, world, torch, mfb, stream, local, pre):
     """N > 1: configs[3], object Models sharded over the ranks (in-library NCCL exchange); replicas of configs[1] as the secondary leg"""
     import torch.distributed as dist
     from maskfusion_b200.sharding import ShardedMaskFusion
@@ -487,7 +493,8 @@ def run_sharded(args, rank, world, torch, mfb, stream, local):
     frames = cls = None
     single = None
     if rank == 0:
-        frames, cls = multi_frames(8, n)
+        frames, cls = pre
+        frames = frames[:n]
         single = single_process_multi(torch, mfb, stream, local, frames, cls, timed_from=warm_to + Wm)
     dist.barrier()
     cfg = mfb.default_config(W, H, **MULTI_KW)

@@ -26,6 +26,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
+#include <array>
 
 namespace mfb {
 
@@ -356,6 +358,28 @@ static bool make_map_nhwc(CUtensorMap* m, const void* ptr, int C, int W, int H, 
     return true;
 }
 
+// Tensor maps are pure functions of (pointer, geometry): the backbone's buffers never move, so every map is encoded ONCE (first forward) and
+// reused by all later launches (round 1 encoded two maps per GEMM per forward on the host: 224 driver calls in front of 112 launches).
+static std::map<std::array<uint64_t, 6>, CUtensorMap> g_mapCache;
+static bool cached_map(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t K, uint32_t boxRows)
+{
+    const std::array<uint64_t, 6> key = {(uint64_t)(uintptr_t)ptr, rows, K, boxRows, 0, 0};
+    auto it = g_mapCache.find(key);
+    if (it != g_mapCache.end()) { *m = it->second; return true; }
+    if (!make_map(m, ptr, rows, K, boxRows)) return false;
+    if (g_mapCache.size() < 4096) g_mapCache[key] = *m;
+    return true;
+}
+static bool cached_map_nhwc(CUtensorMap* m, const void* ptr, int Cin, int Wimg, int Himg, int Wbox, int Hbox)
+{
+    const std::array<uint64_t, 6> key = {(uint64_t)(uintptr_t)ptr, (uint64_t)Cin, (uint64_t)Wimg, (uint64_t)Himg, (uint64_t)Wbox, (uint64_t)Hbox + 1};
+    auto it = g_mapCache.find(key);
+    if (it != g_mapCache.end()) { *m = it->second; return true; }
+    if (!make_map_nhwc(m, ptr, Cin, Wimg, Himg, Wbox, Hbox)) return false;
+    if (g_mapCache.size() < 4096) g_mapCache[key] = *m;
+    return true;
+}
+
 template <int BN>
 static size_t gemm_smem_bytes() { return (size_t)GEMM_STAGES * (GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2) + 256 + 1024; }
 
@@ -377,9 +401,9 @@ int launch_gemm_bf16(const void* A, const void* B, const float* bias, const void
         const int Wimg = conv3x3[0], Himg = conv3x3[1], Cin = conv3x3[2];
         geo.mode = 1; geo.Wimg = Wimg; geo.Himg = Himg; geo.Wbox = Wimg >= 128 ? 128 : Wimg; geo.Hbox = 128 / geo.Wbox; geo.cblocks = Cin / 64;
         if (Wimg % geo.Wbox || Himg % geo.Hbox || Cin % 64 || K != 9 * Cin) { g_cnn_err = "conv3x3: unsupported geometry"; return -2; }
-        if (!make_map_nhwc(&mA, A, Cin, Wimg, Himg, geo.Wbox, geo.Hbox)) return -3;
-    } else if (!make_map(&mA, A, (uint64_t)M, (uint64_t)K, GEMM_BM)) return -3;
-    if (!make_map(&mB, B, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return -3;
+        if (!cached_map_nhwc(&mA, A, Cin, Wimg, Himg, geo.Wbox, geo.Hbox)) return -3;
+    } else if (!cached_map(&mA, A, (uint64_t)M, (uint64_t)K, GEMM_BM)) return -3;
+    if (!cached_map(&mB, B, (uint64_t)N, (uint64_t)K, (uint32_t)BN)) return -3;
     dim3 grid(mtiles, N / BN);
     prof_mark(s, BN == 128 ? "k_gemm_bf16_tcgen05_n128" : "k_gemm_bf16_tcgen05_n64");
     if (BN == 128) {

@@ -152,15 +152,17 @@ MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restric
             if (fabs(d) <= DBL_MIN) kend = k;
             else {
                 if (act && lane > k) a[k] = a[k] / d;
+                // Trailing update of BOTH halves, each entry with the sequential routine's operand order: the lower entry (i, j <= i) is
+                // A[i][j] - (A[i][k] * d) * A[j][k]; the upper entry (i, j > i) mirrors the lower entry (j, i) = A[j][i] - (A[j][k] * d) * A[i][k],
+                // so it is evaluated as exactly that product.  The two halves therefore stay bit-identical without the copy
+                // A[j][i] = A[i][j] of the sequential routine (which cost 2 shuffles per pair here).
+                const double ad = a[k] * d;
 #pragma unroll
                 for (int j = k + 1; j < N; ++j) {
-                    const double ajk = shflD(a[k], j);                              // A[j][k] (scaled)
-                    if (act && lane >= j) a[j] = a[j] - (a[k] * d) * ajk;
+                    const double cj = shflD(a[k], j);                               // A[j][k] (scaled)
+                    const double lo = a[j] - ad * cj, up = a[j] - (cj * d) * a[k];
+                    if (act && lane > k) a[j] = (j <= lane) ? lo : up;
                 }
-#pragma unroll
-                for (int j = k + 1; j < N; ++j)
-#pragma unroll
-                    for (int i = j + 1; i < N; ++i) { const double v = shflD(a[j], i); if (lane == j) a[i] = v; }   // A[j][i] = A[i][j]
             }
         }
     }
@@ -168,6 +170,9 @@ MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restric
 #pragma unroll
         for (int j = 0; j < N; ++j) if (act && lane >= kend && j >= kend && j < lane) a[j] = 0.0;
     }
+    double dg = a[0];                                      // this lane's pivot d_r
+#pragma unroll
+    for (int j = 1; j < N; ++j) if (r == j) dg = a[j];
     double y = b[perm];
 #pragma unroll
     for (int j = 0; j < N - 1; ++j) {
@@ -175,20 +180,25 @@ MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restric
         if (act && lane > j && j < kend) y = y - a[j] * yj;
     }
     {
-        double dg = a[0];
-#pragma unroll
-        for (int j = 1; j < N; ++j) if (r == j) dg = a[j];
         const double dd = lane < kend ? dg : 0.0;
         y = (fabs(dd) > DBL_MIN) ? y / dd : 0.0;
     }
+    // L^T x = z.  Row i of L^T is column i of L: L[j][i] = (entry (j, i) before its scaling) / d_i, and that unscaled value is what
+    // this lane's own UPPER entry (i, j) still holds (it was last touched at step i - 1).  Same operands, same division => same bits
+    // as the stored factor, and no shuffles of the factor.
+    double lt[N];
 #pragma unroll
-    for (int i = N - 2; i >= 0; --i)
+    for (int j = 1; j < N; ++j) lt[j] = a[j] / dg;
+    double yf[N];
+    yf[N - 1] = shflD(y, N - 1);
 #pragma unroll
-        for (int j = i + 1; j < N; ++j) {
-            const double v = shflD(a[i], j);               // A[j][i]
-            const double yj = shflD(y, j);
-            if (lane == i && i < kend) y = y - v * yj;
+    for (int i = N - 2; i >= 0; --i) {
+        if (lane == i && i < kend) {
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) y = y - lt[j] * yf[j];                  // ascending j, as the sequential loop
         }
+        yf[i] = shflD(y, i);
+    }
     if (act) x[perm] = y;
     __syncwarp();
 }
@@ -967,6 +977,8 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
             }
             TT(2);
             rc.Gact = Gact;
+            // phase B's first streaming inputs (pose independent) -> L1 while this CTA waits at the reduction
+            if (tp.rgb && rounds > 0) { prefetchL1(grad + tid); if (rounds > 1) prefetchL1(grad + tid + nthr); }
             reduceStep<CL, NACC_ICP>(acc, cnt, sig, active, rc, red, ws, rowSh, tot);
             TT(5);
             if (tp.rgb) {
@@ -1029,6 +1041,13 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                     }
                 }
                 TT(6);
+                // the next iteration's first pixel pair (pose-independent inputs) -> L1 across the reduction and the solve
+                for (int q = 0; q < 2; ++q)
+                    if (q < rounds) {
+                        const int kn = tid + q * nthr;
+                        if (tp.icp) { prefetchL1(vmapC + kn); prefetchL1(nmapC + kn); }
+                        prefetchL1(nextDepth + kn);
+                    }
                 // ICP totals stay in tot[0..28]; the photometric ones go behind them
                 reduceStep<CL, NACC_RGB>(accR, 0, 0, active, rc, red, ws, rowSh, totR);
                 TT(9);

@@ -403,3 +403,80 @@ def test_mfseg_tail_thread_invariant_and_sane(oracle):
         s4, n4, h4, _ = oracle.run_mfseg_cpu(fr, threads=4, morphMaskIterations=it)
         assert n1 == n4 and h1 == h4 and np.array_equal(s1, s4)
         assert n1 > 5 and set(np.unique(s1)) >= {0, 1, 2, 3}           # background + the three instances mapped to their models
+
+
+def test_warp_ldlt_scheme_is_bit_identical_to_the_sequential_routine(oracle):
+    """The CUDA solver (csrc/mf_track.cu: ldltSolvePivWarp) distributes the oracle's pivoted LDL^T over the lanes of a warp: lane i owns
+    row i of the FULL matrix, the trailing update writes both halves (the upper entry with the operand order of its mirror image) and the
+    back substitution derives L[j][i] from the lane's own upper entries.  This emulates that data flow operation for operation in
+    numpy float64 and checks the solution against orc_ldlt_solve BIT FOR BIT on SPD, ill-conditioned and singular systems -- the
+    argument for why tracked trajectories can be identical, runnable without a GPU (the kernel itself is covered by the GPU tests)."""
+    import ctypes as C
+    L = oracle.lib()
+    L.orc_ldlt_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    tiny = np.finfo(np.float64).tiny
+
+    def warp(Ain, b):
+        n = len(b)
+        a = [[np.float64(Ain[i][j]) for j in range(n)] for i in range(n)]
+        perm = list(range(n)); kend = n
+        for k in range(n):
+            piv = k; best = abs(a[k][k])
+            for i in range(k + 1, n):
+                if abs(a[i][i]) > best:
+                    best = abs(a[i][i]); piv = i
+            if piv != k:
+                a[k], a[piv] = a[piv], a[k]
+                perm[k], perm[piv] = perm[piv], perm[k]
+                for r in range(n):
+                    a[r][k], a[r][piv] = a[r][piv], a[r][k]
+            d = a[k][k]
+            if abs(d) <= tiny:
+                kend = k
+                break
+            for i in range(k + 1, n):
+                a[i][k] = a[i][k] / d
+            col = [a[j][k] for j in range(n)]
+            for r in range(k + 1, n):
+                ad = a[r][k] * d
+                for j in range(k + 1, n):
+                    a[r][j] = a[r][j] - ad * col[j] if j <= r else a[r][j] - (col[j] * d) * a[r][k]
+        for i in range(kend, n):
+            for j in range(kend, i):
+                a[i][j] = np.float64(0)
+        y = [np.float64(b[perm[i]]) for i in range(n)]
+        for j in range(n - 1):
+            for i in range(j + 1, n):
+                if j < kend:
+                    y[i] = y[i] - a[i][j] * y[j]
+        for i in range(n):
+            dd = a[i][i] if i < kend else np.float64(0)
+            y[i] = y[i] / dd if abs(dd) > tiny else np.float64(0)
+        for i in range(n - 2, -1, -1):
+            if i < kend:
+                for j in range(i + 1, n):
+                    y[i] = y[i] - (a[i][j] / a[i][i]) * y[j]
+        x = np.zeros(n)
+        for i in range(n):
+            x[perm[i]] = y[i]
+        return x
+
+    rng = np.random.default_rng(0)
+    with np.errstate(all="ignore"):
+        for trial in range(600):
+            n = 6 if trial % 4 else 3
+            m = int(rng.integers(n, 40))
+            J = rng.normal(size=(m, n)) * rng.uniform(0.01, 10, size=(1, n))
+            if trial % 7 == 0:
+                J[:, rng.integers(0, n)] = 0
+            if trial % 11 == 0:
+                J[:, 1] = J[:, 0] * 2
+            A = np.float64(np.float32(J.T @ J))
+            for i in range(n):
+                for j in range(i):
+                    A[i][j] = A[j][i]
+            b = np.float64(np.float32(J.T @ rng.normal(size=m)))
+            A = np.ascontiguousarray(A); b = np.ascontiguousarray(b)
+            xo = np.zeros(n)
+            L.orc_ldlt_solve(A.ctypes.data, b.ctypes.data, n, xo.ctypes.data)
+            assert np.array_equal(xo.view(np.uint64), warp(A, b).view(np.uint64)), trial

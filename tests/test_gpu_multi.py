@@ -25,11 +25,12 @@ class MFS(C.Structure):
                 ("projKeys", C.c_void_p), ("projectedIDs", ol.u8p), ("fullSeg", ol.u8p)]
 
 
-def run(nframes, track_all, tag="", n_objects=3, layout="room", **over):
+def run(nframes, track_all, tag="", n_objects=3, layout="room", size=None, **over):
     import maskfusion_b200 as mfb
     from maskfusion_b200.synth import SynthScene
     kw = dict(capacityGlobal=1000000, capacityObject=200000, enableMultipleModels=1, icpWeight=100.0, so3=0, trackAllModels=int(track_all))
     kw.update(over)
+    W, H = size or (640, 480)
     sc = SynthScene(W, H, n_objects=n_objects, seed=0, layout=layout)
     orc = ol.OraclePipeline(ol.default_config(W, H, **kw))
     L = orc.L
@@ -198,3 +199,13 @@ def test_table_scene_eight_tracked_objects():
     ate = check_exact(log, 9)
     with open(os.path.join(OUT, f"ate_table8_{n}.json"), "w") as f:
         json.dump({"frames": n, "ate_rmse_m": ate, "models": log[-1]["n_c"]}, f)
+
+
+@pytest.mark.skipif(os.environ.get("MF_LONG") != "1", reason="BASELINE configs[4] scene: ~10 s of CPU oracle per frame; run with MF_LONG=1")
+def test_table_scene_720p_sixteen_objects():
+    """BASELINE configs[4] shape on one GPU: 1280x720 (the -cal intrinsics 792/792/640/360), sixteen objects on three rows, every model
+    tracked; one spawn per frame.  Same exactness contract as the VGA scene."""
+    log = run(26, track_all=True, tag="_table16_720p", n_objects=16, layout="table", size=(1280, 720), icpWeight=20.0, modelSpawnOffset=1,
+              fx=792.0, fy=792.0, cx=640.0, cy=360.0, capacityGlobal=2200000, capacityObject=262144)
+    assert log[-1]["n_c"] >= 12, log[-1]["n_c"]          # the partly occluded back-row objects stay below minRelSizeNew (1.5 % of the image)
+    check_exact(log, 12)
