@@ -193,7 +193,7 @@ public:
 
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;
-    bool fuseIndexIntoClean = true;         // A/B: MFB200_FUSE_INDEX=0 keeps Model::predictIndices + Model::clean as two streams over the store
+    bool fuseIndexIntoClean = false;        // MFB200_FUSE_INDEX=1: Model::predictIndices rides inside the following Model::clean (one stream over the store)
     int tick = 1;
     int64_t launches = 0;
     std::vector<std::unique_ptr<Model>> models;

@@ -389,7 +389,7 @@ void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, i
 {
     int P = W * H;
     static int tiled = -1;
-    if (tiled < 0) { const char* e = getenv("MFB200_CC_TILE"); tiled = (e && e[0] == '0') ? 0 : 1; }
+    if (tiled < 0) { const char* e = getenv("MFB200_CC_TILE"); tiled = e ? (e[0] != '0') : 0; }
     if (tiled) {
         dim3 gt((W + CC_TW - 1) / CC_TW, (H + CC_TH - 1) / CC_TH);
         prof_mark(s, "k_cc_tile"); k_cc_tile<<<gt, CC_TW * CC_TH, 0, s>>>(img, W, H, L, area, counter);

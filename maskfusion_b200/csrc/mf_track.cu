@@ -23,6 +23,10 @@
 
 namespace mfb {
 
+// feature defaults (each has an A/B environment switch)
+#ifndef MFB200_DEFAULT_TRACK_CLUSTER
+#define MFB200_DEFAULT_TRACK_CLUSTER 0
+#endif
 #define TRK_THREADS 256
 #define NACC_ICP 29
 #define NACC_RGB 27
@@ -1143,7 +1147,7 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
         if (cudaFuncSetAttribute(k_track_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMaxClDev[dev]) != cudaSuccess) clusterOkDev[dev] = 0;
         if (cudaFuncSetAttribute(k_track_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) clusterOkDev[dev] = 0;
         cudaGetLastError();
-        if (const char* env = getenv("MFB200_TRACK_CLUSTER")) if (env[0] == '0') clusterOkDev[dev] = 0;
+        { const char* env = getenv("MFB200_TRACK_CLUSTER"); if (!(env ? env[0] != '0' : MFB200_DEFAULT_TRACK_CLUSTER)) clusterOkDev[dev] = 0; }
         devInit[dev] = true;
     }
     const int coResident = coResidentDev[dev];

@@ -27,8 +27,8 @@ def main():
     n = mf.L.mf_debug_track_timing(buf.ctypes.data, 8192)
     ev = buf[:n].reshape(-1, 2)
     ghz = 1.965
-    names = {2: "A pixels", 3: "A cta-reduce", 4: "A barrier", 5: "A sum rows", 6: "B pixels", 7: "B cta-reduce", 8: "B barrier", 9: "B sum rows",
-             10: "solve", 12: "so3 pixels", 13: "so3 cta-reduce", 14: "so3 barrier", 15: "so3 sum rows", 16: "so3 solve"}
+    names = {2: "A pixels", 5: "A reduce+exchange+sum", 6: "B pixels (+sigma)", 9: "B reduce+exchange+sum", 10: "solve + pose update",
+             12: "so3 pixels", 15: "so3 reduce+exchange+sum", 16: "so3 solve"}
     acc = collections.defaultdict(lambda: [0, 0.0])
     level = "so3"
     prev = None
