@@ -306,6 +306,9 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     cudaCheck(cudaStreamCreateWithFlags(&preStream, cudaStreamNonBlocking), "cudaStreamCreate");
     cudaCheck(cudaEventCreateWithFlags(&preDone, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&inputsCopied, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventCreateWithFlags(&evMain, cudaEventDisableTiming), "cudaEventCreate");
+    cudaCheck(cudaEventCreateWithFlags(&evComm, cudaEventDisableTiming), "cudaEventCreate");
+    if (const char* env = getenv("MFB200_MULTI_OVERLAP")) multiOverlap = env[0] != '0';
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
         if (l > 0) depthPyr[l].alloc(Pl);
@@ -347,6 +350,8 @@ MaskFusion::~MaskFusion()
     if (preStream) { cudaStreamSynchronize(preStream); cudaStreamDestroy(preStream); }
     if (preDone) cudaEventDestroy(preDone);
     if (inputsCopied) cudaEventDestroy(inputsCopied);
+    if (evMain) cudaEventDestroy(evMain);
+    if (evComm) cudaEventDestroy(evComm);
     models.clear();
     inactiveModels.clear();
     if (hJobs) cudaFreeHost(hJobs);
@@ -684,12 +689,13 @@ void MaskFusion::attachBackbone(void* bb, int everyK)
 }
 
 // every k-th frame: RGBA image of this frame -> letter-boxed network input -> backbone forward, all on the backbone's stream
-void MaskFusion::runBackbone()
+void MaskFusion::runBackbone(cudaStream_t producer)
 {
     if (!backbone || backboneEvery <= 0 || (tick % backboneEvery) != 0) return;
+    if (!producer) producer = stream;
     mf_backbone* bb = (mf_backbone*)backbone;
     cudaStream_t bs = (cudaStream_t)mf_backbone_stream(bb);
-    cudaCheck(cudaEventRecord(bbFrameReady, stream), "cudaEventRecord");            // the RGBA copy of this frame exists
+    cudaCheck(cudaEventRecord(bbFrameReady, producer), "cudaEventRecord");          // the RGBA copy of this frame exists
     cudaCheck(cudaStreamWaitEvent(bs, bbFrameReady, 0), "cudaStreamWaitEvent");
     if (mf_backbone_mold(bb, rgb, W, H) != 0) throw CudaError{"backbone: mold_inputs failed"};
     cudaCheck(cudaEventRecord(bbMoldDone, bs), "cudaEventRecord");                   // the frame's image is free again once the input is molded
@@ -757,6 +763,10 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
     // previous frame's images; the copy engine and the issue-bound bilateral overlap well with the HBM-bound clean/scatter).
     // Safe without further events: finalisePending() above has waited for the previous frame's tracker, the last reader of the maps.
     const bool overlap = !multi && world == 1 && tracking && !prof.on;
+    // multi-model frames (MFB200_MULTI_OVERLAP=1): the same idea -- the frame's inputs and preprocessing run on preStream next to the
+    // previous frame's fusion / clean / prediction tail.  With a communicator ALL collectives are issued on preStream (one stream per
+    // communicator: their order is the same on every rank by construction) and tied to the main stream by events.
+    const bool moverlap = multi && multiOverlap && tracking && !prof.on && (world == 1 || shardNccl);
     if (overlap) {
         selectSet(curSet ^ 1);
         uploadInputs(rgbIn, depthIn, nullptr, timestamp, onDevice, preStream);
@@ -765,9 +775,31 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
         if (cfg.rgbOnly || cfg.icpWeight < 100 || cfg.so3) frameIntensity(preStream);
         cudaCheck(cudaEventRecord(preDone, preStream), "cudaEventRecord");
         preWaitPending = true;
+    } else if (moverlap) {
+        selectSet(curSet ^ 1);
+        if (spawnedInApply) {
+            // the spawn that finalisePending() just carried out reads the previous frame's intensity pyramid (initFirstRGB), which this
+            // frame's preprocessing overwrites: on such (rare) frames the preprocessing waits for the main stream
+            cudaCheck(cudaEventRecord(evMain, stream), "cudaEventRecord");
+            cudaCheck(cudaStreamWaitEvent(preStream, evMain, 0), "cudaStreamWaitEvent");
+            spawnedInApply = false;
+        }
+        if (bbMoldPending) { cudaCheck(cudaStreamWaitEvent(preStream, bbMoldDone, 0), "cudaStreamWaitEvent"); bbMoldPending = false; }
+        if (shardNccl) {
+            if (rank == 0) uploadInputs(rgbIn, depthIn, maskIn, timestamp, onDevice, preStream);
+            shard.broadcast(inBuf[curSet].p, packetBytes(), 0, preStream);
+        } else
+            uploadInputs(rgbIn, depthIn, maskIn, timestamp, onDevice, preStream);
+        preprocess(preStream);
+        runBackbone(preStream);
+        generateCUDATextures(preStream);
+        if (cfg.rgbOnly || cfg.icpWeight < 100 || cfg.so3) frameIntensity(preStream);
+        cudaCheck(cudaEventRecord(preDone, preStream), "cudaEventRecord");
+        preWaitPending = true;
     } else {
         // multi-model: the previous frame's input set stays intact (a spawn decided by that frame has just been carried out from it)
         if (multi) selectSet(curSet ^ 1);
+        spawnedInApply = false;
         if (bbMoldPending) { cudaCheck(cudaStreamWaitEvent(stream, bbMoldDone, 0), "cudaStreamWaitEvent"); bbMoldPending = false; }   // an older frame's image is being read
         if (shardNccl) {
             // object-sharded: rank 0 holds the loader; the frame packet (images + mask + header, one buffer) goes to every rank over NVLink
@@ -779,6 +811,7 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
         preprocess();
         runBackbone();
     }
+    commOnPre = moverlap && shardNccl;
     Model* g = models[0].get();
     fTracked = false;
     for (auto& m : models) m->tracked = false;
@@ -801,12 +834,24 @@ void MaskFusion::frameBegin(const uint8_t* rgbIn, const float* depthIn, int64_t 
             if (m->owned && m->tracked) tracked.push_back(m);
         }
         trackModels(tracked, multi);
+        if (preWaitPending) {            // no model is tracked here (a shard without stores): the later passes still read this frame's maps
+            cudaCheck(cudaStreamWaitEvent(stream, preDone, 0), "cudaStreamWaitEvent");
+            preWaitPending = false;
+        }
         fTracked = true;
         if (multi) {
             // pose rows of the models tracked here; with a communicator every rank receives every rank's rows (all-gather)
             launch_pack_rows(lifeParams(), poseTable, stream);
             launches += 1;
-            if (shardNccl) { prof_mark(stream, "nccl_allgather_poses"); shard.allGatherFloats(poseTable, gathered, (size_t)MF_MAX_MODELS * 32, stream); }
+            if (shardNccl) {
+                prof_mark(stream, "nccl_allgather_poses");
+                if (commOnPre) {
+                    cudaCheck(cudaEventRecord(evMain, stream), "cudaEventRecord"); cudaCheck(cudaStreamWaitEvent(preStream, evMain, 0), "cudaStreamWaitEvent");
+                    shard.allGatherFloats(poseTable, gathered, (size_t)MF_MAX_MODELS * 32, preStream);
+                    cudaCheck(cudaEventRecord(evComm, preStream), "cudaEventRecord"); cudaCheck(cudaStreamWaitEvent(stream, evComm, 0), "cudaStreamWaitEvent");
+                } else
+                    shard.allGatherFloats(poseTable, gathered, (size_t)MF_MAX_MODELS * 32, stream);
+            }
         } else if (bootstrap && inPose) finalisePending();     // -static bootstrap: the host composes the tracked pose with the given one
     }
 }
@@ -833,7 +878,15 @@ void MaskFusion::frameEnd(float weightMultiplier)
     if (tick > 1) {
         if (fTracked) {
             if (multi) {
-                if (shardNccl) { prof_mark(stream, "nccl_allreduce_keys"); shard.allReduceMinU64(projKeys, (size_t)P, stream); }
+                if (shardNccl) {
+                    prof_mark(stream, "nccl_allreduce_keys");
+                    if (commOnPre) {
+                        cudaCheck(cudaEventRecord(evMain, stream), "cudaEventRecord"); cudaCheck(cudaStreamWaitEvent(preStream, evMain, 0), "cudaStreamWaitEvent");
+                        shard.allReduceMinU64(projKeys, (size_t)P, preStream);
+                        cudaCheck(cudaEventRecord(evComm, preStream), "cudaEventRecord"); cudaCheck(cudaStreamWaitEvent(stream, evComm, 0), "cudaStreamWaitEvent");
+                    } else
+                        shard.allReduceMinU64(projKeys, (size_t)P, stream);
+                }
                 segTables();
                 projectResolve();
                 if (spawnOffset < cfg.modelSpawnOffset) spawnOffset++;
@@ -896,6 +949,7 @@ void MaskFusion::applyFrameResult()
     }
     if (R.hasNewLabel) {                                                                       // :313-334
         Model* nm = spawnObjectModel();
+        spawnedInApply = true;
         spawnOffset = 0;
         nm->classID = R.newClassID;
         nm->maxDepth = 30.0f + 30.0f * 1.2f;

@@ -180,7 +180,9 @@ public:
     // backbone's own stream, next to the dense pipeline of the same GPU (the reference runs its network as a ~5 Hz sidecar)
     void* backbone = nullptr; int backboneEvery = 0; cudaEvent_t bbFrameReady = nullptr, bbMoldDone = nullptr; bool bbMoldPending = false;
     void attachBackbone(void* bb, int everyK);
-    void runBackbone();
+    void runBackbone(cudaStream_t producer = nullptr);
+    // multi-model frames with the inputs / preprocessing (and, sharded, every collective) on preStream: MFB200_MULTI_OVERLAP=1
+    bool multiOverlap = false, spawnedInApply = false, commOnPre = false; cudaEvent_t evMain = nullptr, evComm = nullptr;
     FrameResult* hRes = nullptr; DevBuf<FrameResult> dRes; cudaEvent_t resEvt = nullptr; bool pendingResult = false;
     DevBuf<float> poseTable, gathered;
     float fWeight = 1.f; int fTick = 0; bool fTracked = false;
