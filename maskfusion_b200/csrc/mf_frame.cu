@@ -75,23 +75,25 @@ __global__ void __launch_bounds__(BIL_BX* BIL_BY) k_bilateral_tma(const __grid_c
     const int x0 = blockIdx.x * BIL_BX - BIL_R, y0 = blockIdx.y * BIL_BY - BIL_R;
     const int tid = threadIdx.y * BIL_BX + threadIdx.x;
     const unsigned barAddr = (unsigned)__cvta_generic_to_shared(&bar), tileAddr = (unsigned)__cvta_generic_to_shared(&tile[0][0]);
+    // (operand forms as in the tensor-core GEMM of mf_cnn.cu, which runs on this hardware: register counts / parities, no immediates)
+    const unsigned one = 1u, txBytes = (unsigned)(BIL_TW * BIL_TH * sizeof(float)), parity = 0u;
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barAddr));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barAddr), "r"(one));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"((unsigned)(BIL_TW * BIL_TH * sizeof(float))) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(txBytes) : "memory");
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                      ::"r"(tileAddr), "l"(&depthMap), "r"(barAddr), "r"(x0), "r"(y0) : "memory");
     }
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "BIL_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@p bra BIL_DONE;\n\t"
         "bra BIL_WAIT;\n\t"
-        "BIL_DONE:\n\t}" ::"r"(barAddr) : "memory");
+        "BIL_DONE:\n\t}" ::"r"(barAddr), "r"(parity) : "memory");
     const int x = blockIdx.x * BIL_BX + threadIdx.x, y = blockIdx.y * BIL_BY + threadIdx.y;
     if (x >= W || y >= H) return;
     const float value = tile[threadIdx.y + BIL_R][threadIdx.x + BIL_R];

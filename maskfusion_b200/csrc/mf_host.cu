@@ -329,7 +329,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
         // component histograms for the worst case (every second pixel its own component): the counts of a frame live on the device
         compModel.alloc(((size_t)P / 2 + 2) * MF_MAX_MODELS); compMask.alloc(((size_t)P / 2 + 2) * 256);
         projKeys.alloc(P); launch_fill_u64(projKeys, KEY_EMPTY, P, stream); projectedIDs.alloc(P); projectedIDs.zero(stream);
-        ccL.alloc(P); ccDense.alloc(P); ccLabA.alloc(P); ccLabB.alloc(P); ccArea.alloc((size_t)P + 1); mapToMask.alloc((size_t)P / 2 + 2); absorbId.alloc((size_t)P / 2 + 2);
+        ccL.alloc(P); ccDense.alloc(P); ccLabA.alloc(P); ccLabB.alloc(P); ccArea.alloc((size_t)P + 1); ccBox.alloc(((size_t)P / 2 + 2) * 4); mapToMask.alloc((size_t)P / 2 + 2); absorbId.alloc((size_t)P / 2 + 2);
         maskPixels.alloc(256); ccCounter.alloc(1); ccCounter.zero(stream);
         segTmp.alloc(P); ignoreMap.alloc(P); ignoreMap.zero(stream);
         tblIdToIndex.alloc(256); tblIndexToId.alloc(256); tblIsModel.alloc(256); tblMaskToID.alloc(256); tblIsPerson.alloc(256);
@@ -580,7 +580,7 @@ void MaskFusion::performSegmentation(bool allowNew)
     launch_person_table(dHdr, personClassID, tblIsPerson, stream);
     launch_apply_ignore(frameMask, tblIsPerson, dHdr, P, ignoreMap, edgeInv, stream);
     // connected components + 5 edge-removal sweeps (:238-291)
-    launch_cc(edgeInv, W, H, ccL, ccDense, ccLabA, ccArea, ccCounter, stream);
+    launch_cc(edgeInv, W, H, ccL, ccDense, ccLabA, ccArea, ccBox, ccCounter, stream);
     launch_remove_edges(ccLabA, ccLabB, depthRaw, ccArea, W, H, 5, stream);
     int* lab = ccLabB;                                     // odd number of sweeps ends in B
     // overlap histograms (:303-346)
@@ -601,7 +601,7 @@ void MaskFusion::performSegmentation(bool allowNew)
     vp.minMaskModelOverlap = minMaskModelOverlap; vp.nextModelID = getNextModelID(false);
     for (int i = 0; i < nModels; ++i) { vp.modelClass[i] = models[i]->classID; vp.modelID[i] = models[i]->id; }
     launch_vote(dHdr, vp, maskPixels, maskOverlap, ccCounter, tblMaskToID, dRes, stream);
-    launch_seg_final(segTmp, lab, mapToMask, absorbId, tblMaskToID, P, mask, stream);      // writes textureMask directly (:297)
+    launch_seg_final(segTmp, lab, mapToMask, absorbId, tblMaskToID, ccBox, P, W, mask, stream);      // writes textureMask directly (:297)
     launches += 3;
 }
 

@@ -195,7 +195,7 @@ public:
 
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;
-    bool fuseIndexIntoClean = false;        // MFB200_FUSE_INDEX=1: Model::predictIndices rides inside the following Model::clean (one stream over the store)
+    bool fuseIndexIntoClean = true;         // Model::predictIndices rides inside the following Model::clean (one stream over the store); MFB200_FUSE_INDEX=0: two passes (A/B)
     int tick = 1;
     int64_t launches = 0;
     std::vector<std::unique_ptr<Model>> models;
@@ -231,7 +231,7 @@ public:
     std::vector<int32_t> classIDs;          // of the frame being processed
     int spawnOffset = 0;
     DevBuf<uint64_t> projKeys; DevBuf<uint8_t> projectedIDs;
-    DevBuf<int> ccL, ccDense, ccLabA, ccLabB, ccArea, mapToMask, absorbId, maskPixels, compModel, compMask;
+    DevBuf<int> ccL, ccDense, ccLabA, ccLabB, ccArea, ccBox, mapToMask, absorbId, maskPixels, compModel, compMask;
     DevBuf<uint32_t> ccCounter; DevBuf<unsigned> maskOverlap;
     DevBuf<uint8_t> segTmp, ignoreMap, tblIdToIndex, tblIndexToId, tblIsModel, tblMaskToID, tblIsPerson;
     float minMaskModelOverlap = 0.05f; int minMappedComponentSize = 160; int personClassID = 255;   // MfSegmentation.cpp:43, MfSegmentation.h:58

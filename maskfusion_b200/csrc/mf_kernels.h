@@ -202,7 +202,7 @@ void launch_morph_close_invert(uint8_t* data, uint8_t* buf, int W, int H, int ra
 
 namespace mfb {
 // ---- mf_seg.cu: GPU segmentation tail + global projection resolve ----
-void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, uint32_t* counter, cudaStream_t s);
+void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, int* box, uint32_t* counter, cudaStream_t s);   // box: left, top, right, bottom per component
 void launch_remove_edges(int* labA, int* labB, const float* depth, const int* area, int W, int H, int iterations, cudaStream_t s);
 void launch_seg_tables(const SegTables& t, uint8_t* idToIndex, uint8_t* indexToId, uint8_t* isModel, cudaStream_t s);
 void launch_frame_header(const FrameHdr& h, FrameHdr* d, cudaStream_t s);                       // single-process path: the header by value
@@ -216,7 +216,8 @@ void launch_vote(const FrameHdr* hdr, const VoteParams& vp, const int* maskPixel
                  uint8_t* maskToID, FrameResult* res, cudaStream_t s);
 void launch_seg_assign(const int* lab, const int* mapToMask, const uint8_t* ignore, int P, uint8_t* seg, cudaStream_t s);
 void launch_mask_overlap(const uint8_t* seg, const uint8_t* projID, const uint8_t* idToIndex, const uint8_t* isModelId, int P, unsigned* maskOverlap, cudaStream_t s);
-void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, int P, uint8_t* out, cudaStream_t s);
+void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, const int* box, int P, int W,
+                      uint8_t* out, cudaStream_t s);
 void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, const FrameHdr* hdr, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s);
 void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s);
 void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, float confThreshold,

@@ -217,11 +217,15 @@ __global__ void k_cc_border(const uint8_t* __restrict__ img, int W, int H, int* 
     }
 }
 // roots get a dense id 1..n-1 (0 = background/edge); area is accumulated per dense id
-__global__ void k_cc_number(int* __restrict__ L, int P, int* __restrict__ dense, uint32_t* counter)
+__global__ void k_cc_number(int* __restrict__ L, int P, int* __restrict__ dense, uint32_t* counter, int* __restrict__ box)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
-    if (L[i] == i) dense[i] = (int)atomicAdd(counter, 1u) + 1;
+    if (L[i] == i) {
+        const int d = (int)atomicAdd(counter, 1u) + 1;
+        dense[i] = d;
+        box[4 * d] = 0x7fffffff; box[4 * d + 1] = 0x7fffffff; box[4 * d + 2] = -1; box[4 * d + 3] = -1;     // left, top, right, bottom of the component
+    }
 }
 // Integer histogram update with one atomic per distinct bin per warp: neighbouring pixels mostly hit the same bin (one component /
 // one model covers most of the image), and 300 k atomics on ONE address serialise (k_seg_hist, k_mask_overlap and this kernel took
@@ -231,12 +235,21 @@ MF_D void warpAggAdd(int* __restrict__ bins, int key)
     const unsigned peers = __match_any_sync(0xffffffffu, key);
     if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&bins[key], __popc(peers));
 }
-__global__ void k_cc_relabel(const int* __restrict__ L, const int* __restrict__ dense, int P, int* __restrict__ lab, int* __restrict__ area)
+// labels + per-component area and bounding box (the `stats` of cv::connectedComponentsWithStats, MfSegmentation.cpp:239), one atomic per
+// distinct component per warp
+__global__ void k_cc_relabel(const int* __restrict__ L, const int* __restrict__ dense, int P, int W, int* __restrict__ lab, int* __restrict__ area,
+                             int* __restrict__ box)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int l = 0, key = -1;
     if (i < P && L[i] >= 0) { l = dense[ccFind(L, i)]; key = l; }
-    warpAggAdd(area, key);
+    const int y = i / W, x = i - y * W;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int mnx = __reduce_min_sync(peers, x), mxx = __reduce_max_sync(peers, x), mny = __reduce_min_sync(peers, y), mxy = __reduce_max_sync(peers, y);
+    if (key >= 0 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+        atomicAdd(&area[key], __popc(peers));
+        atomicMin(&box[4 * key], mnx); atomicMin(&box[4 * key + 1], mny); atomicMax(&box[4 * key + 2], mxx); atomicMax(&box[4 * key + 3], mxy);
+    }
     if (i < P) lab[i] = l;
 }
 // one Jacobi sweep of the edge-removal loop (MfSegmentation.cpp:243-291): reads the previous labels only
@@ -356,14 +369,21 @@ __global__ void k_mask_overlap(const uint8_t* __restrict__ seg, const uint8_t* _
     if (i < P) { uint8_t id = projID[i]; if (isModelId[id]) key = (int)idToIndex[id] * 256 + seg[i]; }
     warpAggAdd(reinterpret_cast<int*>(maskOverlap), key);
 }
+// maskToID lookup + "unused components are absorbed by the model they overlap" (MfSegmentation.cpp:495-522).  The reference relabels a
+// component inside the rectangle [left, left + width] x [top, top + height] of its connected-components statistics, i.e. of the component
+// BEFORE the edge-removal sweeps grew it: pixels the sweeps attached outside that rectangle keep their mask value.
 __global__ void k_seg_final(const uint8_t* __restrict__ seg, const int* __restrict__ lab, const int* __restrict__ mapToMask,
-                            const int* __restrict__ absorb, const uint8_t* __restrict__ maskToID, int P, uint8_t* __restrict__ out)
+                            const int* __restrict__ absorb, const uint8_t* __restrict__ maskToID, const int* __restrict__ box, int P, int W,
+                            uint8_t* __restrict__ out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
     uint8_t s = maskToID[seg[i]];
     int c = lab[i];
-    if (c > 0 && mapToMask[c] == 0 && absorb[c] > 0) s = (uint8_t)absorb[c];
+    if (c > 0 && mapToMask[c] == 0 && absorb[c] > 0) {
+        const int y = i / W, x = i - y * W;
+        if (x >= box[4 * c] && x <= box[4 * c + 2] + 1 && y >= box[4 * c + 1] && y <= box[4 * c + 3] + 1) s = (uint8_t)absorb[c];
+    }
     out[i] = s;
 }
 __global__ void k_apply_ignore(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ isPerson, const FrameHdr* __restrict__ hdr, int P,
@@ -385,11 +405,11 @@ __global__ void k_proj_resolve(unsigned long long* __restrict__ key, int P, cons
     out[i] = id;
 }
 
-void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, uint32_t* counter, cudaStream_t s)
+void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, int* area, int* box, uint32_t* counter, cudaStream_t s)
 {
     int P = W * H;
     static int tiled = -1;
-    if (tiled < 0) { const char* e = getenv("MFB200_CC_TILE"); tiled = e ? (e[0] != '0') : 0; }
+    if (tiled < 0) { const char* e = getenv("MFB200_CC_TILE"); tiled = e ? (e[0] != '0') : 1; }
     if (tiled) {
         dim3 gt((W + CC_TW - 1) / CC_TW, (H + CC_TH - 1) / CC_TH);
         prof_mark(s, "k_cc_tile"); k_cc_tile<<<gt, CC_TW * CC_TH, 0, s>>>(img, W, H, L, area, counter);
@@ -400,8 +420,8 @@ void launch_cc(const uint8_t* img, int W, int H, int* L, int* dense, int* lab, i
         prof_mark(s, "k_cc_init"); k_cc_init<<<(P + 255) / 256, 256, 0, s>>>(img, P, L, area, counter);
         prof_mark(s, "k_cc_merge"); k_cc_merge<<<g, b, 0, s>>>(img, W, H, L);
     }
-    prof_mark(s, "k_cc_number"); k_cc_number<<<(P + 255) / 256, 256, 0, s>>>(L, P, dense, counter);
-    prof_mark(s, "k_cc_relabel"); k_cc_relabel<<<(P + 255) / 256, 256, 0, s>>>(L, dense, P, lab, area);
+    prof_mark(s, "k_cc_number"); k_cc_number<<<(P + 255) / 256, 256, 0, s>>>(L, P, dense, counter, box);
+    prof_mark(s, "k_cc_relabel"); k_cc_relabel<<<(P + 255) / 256, 256, 0, s>>>(L, dense, P, W, lab, area, box);
 }
 void launch_remove_edges(int* labA, int* labB, const float* depth, const int* area, int W, int H, int iterations, cudaStream_t s)
 {
@@ -446,9 +466,10 @@ void launch_mask_overlap(const uint8_t* seg, const uint8_t* projID, const uint8_
 {
     prof_mark(s, "k_mask_overlap"); k_mask_overlap<<<(P + 255) / 256, 256, 0, s>>>(seg, projID, idToIndex, isModelId, P, maskOverlap);
 }
-void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, int P, uint8_t* out, cudaStream_t s)
+void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, const int* absorb, const uint8_t* maskToID, const int* box, int P, int W,
+                      uint8_t* out, cudaStream_t s)
 {
-    prof_mark(s, "k_seg_final"); k_seg_final<<<(P + 255) / 256, 256, 0, s>>>(seg, lab, mapToMask, absorb, maskToID, P, out);
+    prof_mark(s, "k_seg_final"); k_seg_final<<<(P + 255) / 256, 256, 0, s>>>(seg, lab, mapToMask, absorb, maskToID, box, P, W, out);
 }
 void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, const FrameHdr* hdr, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s)
 {

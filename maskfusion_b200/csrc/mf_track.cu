@@ -17,6 +17,7 @@
 #include "mf_kernels.h"
 #include "mf_host.h"
 #include <float.h>
+#include <algorithm>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -27,6 +28,10 @@ namespace mfb {
 #ifndef MFB200_DEFAULT_TRACK_CLUSTER
 #define MFB200_DEFAULT_TRACK_CLUSTER 0
 #endif
+#ifndef MFB200_DEFAULT_TRACK_CACHE
+#define MFB200_DEFAULT_TRACK_CACHE 0
+#endif
+#define CACHE_BYTES_PER_SLOT 44        // float4 vertex + float4 normal + depth + packed (valid, intensity, x, y) + Sobel gradient
 #define TRK_THREADS 256
 #define NACC_ICP 29
 #define NACC_RGB 27
@@ -397,6 +402,7 @@ struct TrackParams {
     float icpWeight, angleThres, distThres, sobelScale, maxDepthDelta;
     float minScale[3];
     int corrSlots;                     // photometric correspondences kept per CTA in shared memory (0: global scratch instead)
+    int cacheRounds;                   // pixel rounds per thread whose pose-independent inputs are kept in shared memory across the iterations of a level
     int phase;                         // 0: whole schedule in this launch; 1: SO(3) + level 2 only (cluster kernel); 2: resume at level 1
 };
 
@@ -651,7 +657,7 @@ MF_D void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::
 
 // one pixel of phase A through its four stages; two of these are in flight per thread (their gathers overlap)
 struct PixA {
-    float4 vc, nc; float d1; int valid, ni;                       // pose-independent inputs
+    float4 vc, nc; float d1; int valid, ni, x, y;                 // pose-independent inputs
     bool rOK, iOK; int jr, ji, u0, v0; float td1; float3 vg, vcp;  // projections under the current estimate
     float d0; int li; float4 vp4, np4;                             // gathered model data
 };
@@ -722,6 +728,18 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
     // photometric correspondences of this thread's pixels, slot = round * PT_THREADS + thread: written in phase A, read in phase B
     // by the same thread.  Shared memory when the launch reserved enough, else a private stripe of the model's scratch buffer.
     int2* const corr = tp.corrSlots ? corrShared : reinterpret_cast<int2*>(J.corres[0]) + (size_t)blockIdx.x * ((size_t)((tp.W * tp.H + G * PT_THREADS - 1) / (G * PT_THREADS)) * PT_THREADS);
+    // Pose-independent inputs of this thread's pixels (frame vertex / normal, depth of the photometric pyramid, intensity, validity, image
+    // gradient, pixel coordinates) are the same in every iteration of a level: they are read from global memory ONCE per level into
+    // shared memory (slot = round * PT_THREADS + thread, structure of arrays: conflict-free 16-byte accesses) and the Gauss-Newton
+    // iterations re-read them from there.  Phase A then issues only its pose-dependent gathers: one L2 round trip instead of two, ~40 %
+    // fewer instructions per pixel (stage clock, profiles/r02_track_timing*.json).  Rounds beyond tp.cacheRounds (720p level 0) use global memory.
+    const int cacheSlots = tp.cacheRounds * PT_THREADS;
+    unsigned char* const cacheBase = reinterpret_cast<unsigned char*>(corrShared) + (((size_t)tp.corrSlots * sizeof(int2) + 15) & ~(size_t)15);
+    float4* const vcS = reinterpret_cast<float4*>(cacheBase);
+    float4* const ncS = vcS + cacheSlots;
+    float* const d1S = reinterpret_cast<float*>(ncS + cacheSlots);
+    uint32_t* const pkS = reinterpret_cast<uint32_t*>(d1S + cacheSlots);          // valid | intensity << 1 | x << 9 | y << 20
+    uint32_t* const gS = pkS + cacheSlots;                                         // Sobel gradient (short2 bits)
 
     // ---------------- SO(3) pre-alignment on level-2 intensities (RGBDOdometry.cpp:272-345) ----------------
     if (tp.so3 && tp.phase != 2) {
@@ -873,8 +891,27 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         __syncthreads();
 
         // pose-independent inputs of pixel k
-        auto stage0 = [&](PixA& p, int k) {
+        // fill the per-level cache (see cacheSlots above)
+        const int cRounds = min(rounds, tp.cacheRounds);
+        for (int r = 0; r < cRounds; ++r) {
+            const int k = tid + r * nthr, slot = r * PT_THREADS + threadIdx.x;
+            const int y = k / W, x = k - y * W;
+            uint32_t pk = ((uint32_t)x << 9) | ((uint32_t)y << 20);
+            float d1 = 0.f; float4 vc = make_float4(0, 0, 0, 0), nc = vc; uint32_t g = 0;
+            if (tp.rgb) { pk |= (rgbValid[k] ? 1u : 0u) | ((uint32_t)nextImage[k] << 1); d1 = nextDepth[k]; const short2 gg = grad[k]; g = (uint32_t)(uint16_t)gg.x | ((uint32_t)(uint16_t)gg.y << 16); }
+            if (tp.icp) { vc = vmapC[k]; nc = nmapC[k]; }
+            vcS[slot] = vc; ncS[slot] = nc; d1S[slot] = d1; pkS[slot] = pk; gS[slot] = g;
+        }
+        auto stage0 = [&](PixA& p, int k, int r) {
+            if (r < cRounds) {
+                const int slot = r * PT_THREADS + threadIdx.x;
+                const uint32_t pk = pkS[slot];
+                p.valid = (int)(pk & 1u); p.ni = (int)((pk >> 1) & 0xffu); p.x = (int)((pk >> 9) & 0x7ffu); p.y = (int)(pk >> 20);
+                p.d1 = d1S[slot]; p.vc = vcS[slot]; p.nc = ncS[slot];
+                return;
+            }
             p.valid = 0; p.d1 = 0.f; p.ni = 0; p.vc = make_float4(0, 0, 0, 0); p.nc = p.vc;
+            p.y = k / W; p.x = k - p.y * W;
             if (tp.rgb) { p.valid = rgbValid[k]; p.d1 = nextDepth[k]; p.ni = nextImage[k]; }
             if (tp.icp) { p.vc = vmapC[k]; p.nc = nmapC[k]; }
         };
@@ -882,7 +919,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         auto stage1 = [&](PixA& p, int k, const float3 tprev) {
             p.rOK = false; p.iOK = false; p.jr = 0; p.ji = 0; p.u0 = 0; p.v0 = 0; p.td1 = 0.f;
             p.vg = make_float3(0, 0, 0); p.vcp = p.vg;
-            const int y = k / W, x = k - y * W;
+            const int y = p.y, x = p.x;
             if (tp.rgb && p.valid && !isnan(p.d1)) {
                 const float* K = st->krk; const float* kt = st->kt;
                 const float d1 = p.d1;
@@ -962,16 +999,16 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                 for (int r = 0; r < rounds; r += 2) {
                     const int k0 = tid + r * nthr, k1 = k0 + nthr;
                     const bool two = r + 1 < rounds;
-                    // next pair's streaming inputs -> L1 while this pair's dependent gathers are in flight
+                    // next pair's streaming inputs -> L1 while this pair's dependent gathers are in flight (rounds not held in shared memory)
                     for (int q = 2; q < 4; ++q)
-                        if (r + q < rounds) {
+                        if (r + q < rounds && r + q >= cRounds) {
                             const int kn = k0 + q * nthr;
                             if (tp.icp) { prefetchL1(vmapC + kn); prefetchL1(nmapC + kn); }
                             if (tp.rgb) { prefetchL1(nextDepth + kn); }
                         }
                     PixA a, b;
-                    stage0(a, k0);
-                    if (two) stage0(b, k1); else { b.valid = 0; b.d1 = 0.f; b.ni = 0; b.vc = make_float4(0, 0, 0, 0); b.nc = b.vc; }
+                    stage0(a, k0, r);
+                    if (two) stage0(b, k1, r + 1); else { b.valid = 0; b.d1 = 0.f; b.ni = 0; b.x = 0; b.y = 0; b.vc = make_float4(0, 0, 0, 0); b.nc = b.vc; }
                     stage1(a, k0, tprev);
                     if (two) stage1(b, k1, tprev); else { b.rOK = false; b.iOK = false; b.jr = 0; b.ji = 0; b.u0 = 0; b.v0 = 0; b.td1 = 0.f; b.vg = make_float3(0, 0, 0); b.vcp = b.vg; }
                     stage2(a); stage2(b);
@@ -982,7 +1019,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
             TT(2);
             rc.Gact = Gact;
             // phase B's first streaming inputs (pose independent) -> L1 while this CTA waits at the reduction
-            if (tp.rgb && rounds > 0) { prefetchL1(grad + tid); if (rounds > 1) prefetchL1(grad + tid + nthr); }
+            if (tp.rgb && rounds > cRounds) { prefetchL1(grad + tid + cRounds * nthr); }
             reduceStep<CL, NACC_ICP>(acc, cnt, sig, active, rc, red, ws, rowSh, tot);
             TT(5);
             if (tp.rgb) {
@@ -1038,15 +1075,19 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                         const int2 c1 = two ? corr[(r + 1) * PT_THREADS + threadIdx.x] : make_int2(-1, 0);
                         short2 g0 = make_short2(0, 0), g1 = g0;
                         float4 p0 = make_float4(0, 0, 1, 0), p1 = p0;
-                        if (c0.x != -1) { g0 = grad[k0]; p0 = cloud[(c0.x >> 16) * W + (c0.x & 0xffff)]; }
-                        if (c1.x != -1) { g1 = grad[k1]; p1 = cloud[(c1.x >> 16) * W + (c1.x & 0xffff)]; }
+                        auto gradOf = [&](int k, int rr) -> short2 {
+                            if (rr < cRounds) { const uint32_t g = gS[rr * PT_THREADS + threadIdx.x]; return make_short2((short)(g & 0xffffu), (short)(g >> 16)); }
+                            return grad[k];
+                        };
+                        if (c0.x != -1) { g0 = gradOf(k0, r); p0 = cloud[(c0.x >> 16) * W + (c0.x & 0xffff)]; }
+                        if (c1.x != -1) { g1 = gradOf(k1, r + 1); p1 = cloud[(c1.x >> 16) * W + (c1.x & 0xffff)]; }
                         if (c0.x != -1) rgbRow(c0, g0, p0);
                         if (c1.x != -1) rgbRow(c1, g1, p1);
                     }
                 }
                 TT(6);
                 // the next iteration's first pixel pair (pose-independent inputs) -> L1 across the reduction and the solve
-                for (int q = 0; q < 2; ++q)
+                for (int q = cRounds; q < cRounds + 2; ++q)
                     if (q < rounds) {
                         const int kn = tid + q * nthr;
                         if (tp.icp) { prefetchL1(vmapC + kn); prefetchL1(nmapC + kn); }
@@ -1161,7 +1202,9 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     tp.angleThres = (float)sin(20.f * 3.14159254f / 180.f);
     tp.distThres = 0.10f; tp.sobelScale = (float)(1.0 / 8.0); tp.maxDepthDelta = 0.07f;
     for (int l = 0; l < 3; ++l) tp.minScale[l] = track_min_scale(l);
-    tp.phase = 0;
+    tp.phase = 0; tp.cacheRounds = 0;
+    static int cacheOn = -1;        // MFB200_TRACK_CACHE=0: every iteration re-reads its pose-independent inputs from global memory (A/B)
+    if (cacheOn < 0) { const char* e = getenv("MFB200_TRACK_CACHE"); cacheOn = e ? (e[0] != '0') : MFB200_DEFAULT_TRACK_CACHE; }
     int G = numSMs / nJobs;                      // one CTA per SM, the SMs split between the tracked models
     if (G * nJobs > coResident) G = coResident / nJobs;
     if (G > TRACK_MAX_BLOCKS / 2) G = TRACK_MAX_BLOCKS / 2;
@@ -1178,6 +1221,9 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
             size_t dynC = (size_t)roundsC * PT_THREADS * sizeof(int2);
             if (t1.rgb && dynC <= dynMaxClDev[dev]) t1.corrSlots = roundsC * PT_THREADS; else { t1.corrSlots = 0; dynC = 0; }
             if (t1.rgb && t1.corrSlots == 0) break;             // the global scratch stripe is sized for the persistent grid only
+            dynC = (dynC + 15) & ~(size_t)15;
+            t1.cacheRounds = cacheOn ? (int)std::min<size_t>((size_t)roundsC, (dynMaxClDev[dev] - dynC) / ((size_t)PT_THREADS * CACHE_BYTES_PER_SLOT)) : 0;
+            dynC += (size_t)t1.cacheRounds * PT_THREADS * CACHE_BYTES_PER_SLOT;
             cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
             cfg.gridDim = dim3(C, nJobs); cfg.blockDim = dim3(PT_THREADS); cfg.dynamicSmemBytes = dynC; cfg.stream = s;
             cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1197,6 +1243,9 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     const int rounds0 = (W * H + G * PT_THREADS - 1) / (G * PT_THREADS);
     size_t dyn = (size_t)rounds0 * PT_THREADS * sizeof(int2);
     if (tp.rgb && dyn <= dynMaxDev[dev]) tp.corrSlots = rounds0 * PT_THREADS; else { tp.corrSlots = 0; dyn = 0; }
+    dyn = (dyn + 15) & ~(size_t)15;
+    tp.cacheRounds = cacheOn ? (int)std::min<size_t>((size_t)rounds0, (dynMaxDev[dev] - dyn) / ((size_t)PT_THREADS * CACHE_BYTES_PER_SLOT)) : 0;
+    dyn += (size_t)tp.cacheRounds * PT_THREADS * CACHE_BYTES_PER_SLOT;
     cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
     prof_mark(s, "k_track_persistent");
     void* args[] = {(void*)&jp, (void*)&tp};
