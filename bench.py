@@ -555,6 +555,8 @@ def run_sharded(args, rank, world, torch, mfb, stream, local, pre):
     del smf_keep
     # secondary leg: replicas of configs[1]
     try:
+        if os.environ.get("MFB200_BENCH_LEGS", "1") == "0":
+            raise RuntimeError("skipped (MFB200_BENCH_LEGS=0)")
         st = static_leg(torch, mfb, stream, local, rank, world, min(args.steps, 60), args.warmup)
         kk = min(args.steps, 60)
         replicas = {"value": round(world * kk / (st["ms_dev"] / 1e3), 2), "unit": "frames/s", "ms_per_step": round(st["ms_dev"] / kk, 4),

@@ -8,10 +8,6 @@
 // 3*rows x cols, NaN in the x plane); all loads are 16-byte, coalesced along rows.
 #include "mf_common.cuh"
 #include "mf_kernels.h"
-#include "mf_host.h"
-#include <cuda.h>
-#include <stdlib.h>
-#include <string>
 
 namespace mfb {
 
@@ -60,88 +56,6 @@ __global__ void __launch_bounds__(BIL_BX* BIL_BY) k_bilateral(const float* __res
         }
     }
     out[y * W + x] = sum1 / sum2;
-}
-
-// ---- the same filter with the halo tile staged by TMA (north_star: "depth tiles staged through TMA into shared memory") ----
-// One cp.async.bulk.tensor.2d per CTA brings the (32+12) x (8+12) box of the depth image into shared memory; coordinates left of / above
-// the image and beyond its right / bottom edge are filled with zeros by the copy engine (tiled mode, OOB fill NONE), which is what the
-// bounds branches of the hand-rolled staging loop wrote.  The arithmetic (and its order) is the one of k_bilateral: same bits out.
-#define BIL_TW (BIL_BX + 2 * BIL_R)
-#define BIL_TH (BIL_BY + 2 * BIL_R)
-__global__ void __launch_bounds__(BIL_BX* BIL_BY) k_bilateral_tma(const __grid_constant__ CUtensorMap depthMap, float* __restrict__ out, int W, int H)
-{
-    __shared__ __align__(128) float tile[BIL_TH][BIL_TW];
-    __shared__ __align__(8) unsigned long long bar;
-    const int x0 = blockIdx.x * BIL_BX - BIL_R, y0 = blockIdx.y * BIL_BY - BIL_R;
-    const int tid = threadIdx.y * BIL_BX + threadIdx.x;
-    const unsigned barAddr = (unsigned)__cvta_generic_to_shared(&bar), tileAddr = (unsigned)__cvta_generic_to_shared(&tile[0][0]);
-    // (operand forms as in the tensor-core GEMM of mf_cnn.cu, which runs on this hardware: register counts / parities, no immediates)
-    const unsigned one = 1u, txBytes = (unsigned)(BIL_TW * BIL_TH * sizeof(float)), parity = 0u;
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(barAddr), "r"(one));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barAddr), "r"(txBytes) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                     ::"r"(tileAddr), "l"(&depthMap), "r"(barAddr), "r"(x0), "r"(y0) : "memory");
-    }
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "BIL_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra BIL_DONE;\n\t"
-        "bra BIL_WAIT;\n\t"
-        "BIL_DONE:\n\t}" ::"r"(barAddr), "r"(parity) : "memory");
-    const int x = blockIdx.x * BIL_BX + threadIdx.x, y = blockIdx.y * BIL_BY + threadIdx.y;
-    if (x >= W || y >= H) return;
-    const float value = tile[threadIdx.y + BIL_R][threadIdx.x + BIL_R];
-    if (value <= 0.03f) { out[y * W + x] = 0.0f; return; }
-    const float sigma_space2_inv_half = 0.024691358f, sigma_color2_inv_half = 555.556f;
-    const int D = 2 * BIL_R + 1;
-    const int tx = min(x - D / 2 + D, W), ty = min(y - D / 2 + D, H);
-    float sum1 = 0.f, sum2 = 0.f;
-    for (int cy = max(y - D / 2, 0); cy < ty; ++cy) {
-        const float dy = (float)y - (float)cy;
-        const float* row = tile[cy - y0];
-        for (int cx = max(x - D / 2, 0); cx < tx; ++cx) {
-            float tmp = row[cx - x0];
-            float dx = (float)x - (float)cx;
-            float space2 = dx * dx + dy * dy;
-            float dc = value - tmp;
-            float color2 = dc * dc;
-            float weight = det_expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
-            sum1 += tmp * weight;
-            sum2 += weight;
-        }
-    }
-    out[y * W + x] = sum1 / sum2;
-}
-
-// tensor maps of the depth images the filter is applied to (two input sets per context + the test entry points): encoded once per pointer
-typedef CUresult (*PFN_encodeTiledF)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static bool depthTensorMap(const float* depth, int W, int H, CUtensorMap* out)
-{
-    struct Entry { const float* p; int W, H; CUtensorMap m; };
-    static Entry cache[16]; static int n = 0; static PFN_encodeTiledF enc = nullptr; static bool failed = false;
-    if (failed) return false;
-    for (int i = 0; i < n; ++i) if (cache[i].p == depth && cache[i].W == W && cache[i].H == H) { *out = cache[i].m; return true; }
-    if (!enc) {
-        void* fn = nullptr; cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { failed = true; return false; }
-        enc = (PFN_encodeTiledF)fn;
-    }
-    cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H}; cuuint64_t strides[1] = {(cuuint64_t)W * sizeof(float)};
-    cuuint32_t box[2] = {BIL_TW, BIL_TH}, estr[2] = {1, 1};
-    CUtensorMap m;
-    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(depth), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
-    Entry& e = cache[n < 16 ? n++ : 15];
-    e.p = depth; e.W = W; e.H = H; e.m = m;
-    *out = m;
-    return true;
 }
 
 __constant__ float c_gauss5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
@@ -425,13 +339,6 @@ void launch_unpack_rgb(const uint8_t* rgb3, uchar4* out, int P, cudaStream_t s) 
 void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t s)
 {
     dim3 b(BIL_BX, BIL_BY);
-    static int useTma = -1;          // MFB200_BILATERAL_TMA=1: halo tile through the TMA unit (k_bilateral_tma); identical results
-    if (useTma < 0) { const char* e = getenv("MFB200_BILATERAL_TMA"); useTma = (e && e[0] == '1') ? 1 : 0; }
-    CUtensorMap m;
-    if (useTma && (W % 4) == 0 && depthTensorMap(depth, W, H, &m)) {
-        prof_mark(s, "k_bilateral"); k_bilateral_tma<<<grid2(W, H, b), b, 0, s>>>(m, out, W, H);
-        return;
-    }
     prof_mark(s, "k_bilateral"); k_bilateral<<<grid2(W, H, b), b, 0, s>>>(depth, out, W, H);
 }
 void launch_pyrdown2_f(const float* src, int sw, int sh, float* dst1, float* dst2, cudaStream_t s)
