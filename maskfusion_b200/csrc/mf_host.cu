@@ -308,6 +308,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     cudaCheck(cudaEventCreateWithFlags(&inputsCopied, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evMain, cudaEventDisableTiming), "cudaEventCreate");
     cudaCheck(cudaEventCreateWithFlags(&evComm, cudaEventDisableTiming), "cudaEventCreate");
+    multiOverlap = true;             // validated bit-exact (single process and 2-rank NCCL); MFB200_MULTI_OVERLAP=0 keeps everything on one stream (A/B)
     if (const char* env = getenv("MFB200_MULTI_OVERLAP")) multiOverlap = env[0] != '0';
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
@@ -627,7 +628,9 @@ Model* MaskFusion::spawnObjectModel()
     Model* g = models[0].get();
     // sharded mode: the new store goes to the least-loaded rank; every rank evaluates the same rule on the same replicated list
     int64_t loads[64] = {0};
-    for (auto& m : models) loads[m->ownerRank] += m->capacity;
+    // load of a rank = (number of models it tracks, their surfel capacity): every tracked model walks the whole image in the tracker, so
+    // the model count dominates; the capacity breaks ties (the background's store is the big one)
+    for (auto& m : models) loads[m->ownerRank] += ((int64_t)1 << 32) + m->capacity;
     const int ownerRank = world > 1 ? pickOwner(loads, world) : 0;
     models.emplace_back(new Model(this, getNextModelID(true), cfg.confObject, false, cfg.capacityObject, ownerRank, ownerRank != rank));
     Model* nm = models.back().get();
