@@ -49,8 +49,9 @@ MF_D float3 add3(float3 a, float3 b) { return make_float3(a.x + b.x, a.y + b.y, 
 
 // exp(x): Cody-Waite reduction + degree-6 polynomial (Cephes expf coefficients)
 MF_D float det_expf(float x) {
-    if (!(x > -87.0f)) return (x != x) ? x : 0.0f;
-    if (x > 88.0f) return __int_as_float(0x7f800000);
+    // the two range cases are applied as selects AFTER the (always evaluated) polynomial: no branches in the 169-tap loops
+    const float xin = x;
+    x = fminf(fmaxf(x, -87.0f), 88.0f);                 // keeps n + 127 in range for the discarded evaluations (NaN -> -87)
     float t = x * 1.44269504088896341f;
     float n = floorf(t + 0.5f);
     float r = (x - n * 0.693359375f) - n * (-2.12194440e-4f);
@@ -62,7 +63,10 @@ MF_D float det_expf(float x) {
     p = p * r + 5.0000001201e-1f;
     float r2 = r * r;
     float y = (p * r2 + r) + 1.0f;
-    return y * __int_as_float((uint32_t)((int)n + 127) << 23);
+    float res = y * __int_as_float((uint32_t)((int)n + 127) << 23);
+    if (xin > 88.0f) res = __int_as_float(0x7f800000);
+    if (!(xin > -87.0f)) res = (xin != xin) ? xin : 0.0f;
+    return res;
 }
 // acos(x): Abramowitz & Stegun 4.4.46
 MF_D float det_acosf(float x) {

@@ -41,6 +41,29 @@ __global__ void __launch_bounds__(BIL_BX* BIL_BY) k_bilateral(const float* __res
     const int D = 2 * BIL_R + 1;
     const int tx = min(x - D / 2 + D, W), ty = min(y - D / 2 + D, H);
     float sum1 = 0.f, sum2 = 0.f;
+    if (x >= BIL_R && y >= BIL_R && x + BIL_R < W && y + BIL_R < H) {
+        // whole window inside the image (97 % of the pixels at 640x480): fixed trip counts, the row fully unrolled, the spatial term of a
+        // tap a compile-time constant per column.  Same operations on the same operands in the same order as the general loop below
+        // (dx, dy are small integers: (float)x - (float)cx == (float)(x - cx) exactly), so the result is the same bit pattern.
+        for (int iy = 0; iy < D; ++iy) {
+            const float dy = (float)(BIL_R - iy);
+            const float dy2 = dy * dy;
+            const float* row = &tile[threadIdx.y + iy][threadIdx.x];
+#pragma unroll
+            for (int ix = 0; ix < D; ++ix) {
+                const float tmp = row[ix];
+                const float dx = (float)(BIL_R - ix);
+                const float space2 = dx * dx + dy2;
+                const float dc = value - tmp;
+                const float color2 = dc * dc;
+                const float weight = det_expf(-(space2 * sigma_space2_inv_half + color2 * sigma_color2_inv_half));
+                sum1 += tmp * weight;
+                sum2 += weight;
+            }
+        }
+        out[y * W + x] = sum1 / sum2;
+        return;
+    }
     for (int cy = max(y - D / 2, 0); cy < ty; ++cy) {
         const float dy = (float)y - (float)cy;
         const float* row = tile[cy - y0];
@@ -68,7 +91,7 @@ __constant__ float c_gauss5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 2
 // (2*PY_TY+3) patch of the middle level that tile reads (same arithmetic as the single-level kernels, straight from the fine
 // level), keeps it in shared memory, writes the part it owns, then decimates the patch.  Bit-identical outputs, half the launches
 // (these images are 76 800 / 19 200 pixels: the launches, not the arithmetic, were the cost -- 8 of them per frame).
-#define PY_TX 16
+#define PY_TX 8                          // 8x8 coarse tiles: 600 blocks per 640x480 image, all resident at once (16x8: 150 blocks, one per SM, three serial patch rounds)
 #define PY_TY 8
 struct PyrF {
     typedef float T;
@@ -100,8 +123,7 @@ MF_D typename TR::T pyrPixel(Src src, int sw, int sh, int x, int y)
     return TR::fin(sum, count);
 }
 template <typename TR>
-__global__ void __launch_bounds__(256) k_pyrdown2(const typename TR::T* __restrict__ src, int sw, int sh, typename TR::T* __restrict__ dst1,
-                                                  typename TR::T* __restrict__ dst2)
+MF_D void pyrdown2Body(const typename TR::T* __restrict__ src, int sw, int sh, typename TR::T* __restrict__ dst1, typename TR::T* __restrict__ dst2)
 {
     typedef typename TR::T T;
     constexpr int MW = 2 * PY_TX + 3, MH = 2 * PY_TY + 3;
@@ -125,6 +147,19 @@ __global__ void __launch_bounds__(256) k_pyrdown2(const typename TR::T* __restri
         const int x = X0 + lx, y = Y0 + ly;
         if (x < w2 && y < h2) dst2[y * w2 + x] = pyrPixel<TR>([&](int cx, int cy) { return mid[cy - my0][cx - mx0]; }, w1, h1, x, y);
     }
+}
+template <typename TR>
+__global__ void __launch_bounds__(256) k_pyrdown2(const typename TR::T* __restrict__ src, int sw, int sh, typename TR::T* __restrict__ dst1,
+                                                  typename TR::T* __restrict__ dst2)
+{
+    pyrdown2Body<TR>(src, sw, sh, dst1, dst2);
+}
+// depth (float) and intensity (u8) pyramids of the same image size in one launch: blockIdx.z picks the image
+__global__ void __launch_bounds__(256) k_pyrdown2_pair(const float* __restrict__ srcF, float* __restrict__ dstF1, float* __restrict__ dstF2,
+                                                       const uint8_t* __restrict__ srcU, uint8_t* __restrict__ dstU1, uint8_t* __restrict__ dstU2, int sw, int sh)
+{
+    if (blockIdx.z == 0) pyrdown2Body<PyrF>(srcF, sw, sh, dstF1, dstF2);
+    else pyrdown2Body<PyrU8>(srcU, sw, sh, dstU1, dstU2);
 }
 
 // three pyramid levels of one per-pixel kernel in a single launch: blockIdx.z = level
@@ -346,6 +381,11 @@ void launch_pyrdown2_f(const float* src, int sw, int sh, float* dst1, float* dst
     dim3 g((sw / 4 + PY_TX - 1) / PY_TX, (sh / 4 + PY_TY - 1) / PY_TY);
     prof_mark(s, "k_pyrdown2_f"); k_pyrdown2<PyrF><<<g, 256, 0, s>>>(src, sw, sh, dst1, dst2);
 }
+void launch_pyrdown2_pair(const float* srcF, float* dstF1, float* dstF2, const uint8_t* srcU, uint8_t* dstU1, uint8_t* dstU2, int sw, int sh, cudaStream_t s)
+{
+    dim3 g((sw / 4 + PY_TX - 1) / PY_TX, (sh / 4 + PY_TY - 1) / PY_TY, 2);
+    prof_mark(s, "k_pyrdown2_pair"); k_pyrdown2_pair<<<g, 256, 0, s>>>(srcF, dstF1, dstF2, srcU, dstU1, dstU2, sw, sh);
+}
 void launch_pyrdown2_u8(const uint8_t* src, int sw, int sh, uint8_t* dst1, uint8_t* dst2, cudaStream_t s)
 {
     dim3 g((sw / 4 + PY_TX - 1) / PY_TX, (sh / 4 + PY_TY - 1) / PY_TY);
@@ -383,6 +423,29 @@ void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* s
     int threads = (W / 4) * (H / 4) * 4;
     prof_mark(s, "k_model_maps"); k_model_maps<<<(threads + 127) / 128, 128, 0, s>>>(srcVp, srcNp, srcVf, srcNf, nonBlack, denom, W, H, pose, maxDepthRGB,
                                                        v[0], n[0], v[1], n[1], v[2], n[2], depth0);
+}
+// validity bitmask of a model's normal maps, three levels in one launch (blockIdx.y = level): the tracker tests the bit of the pixel a
+// frame vertex projects to BEFORE gathering the model vertex / normal there.  An object model covers a few per cent of the image, so
+// nearly every projection of a frame pixel lands on an invalid texel: the ICP correspondence test (reduce.cu:330-360) would reject it on
+// isnan(normal) after two 16-byte gathers; the bit says the same thing from shared memory.
+__global__ void k_valid_bits3(const float4* __restrict__ n0, const float4* __restrict__ n1, const float4* __restrict__ n2, int N0,
+                              uint32_t* __restrict__ b0, uint32_t* __restrict__ b1, uint32_t* __restrict__ b2)
+{
+    const int l = blockIdx.y;
+    const float4* n = l == 0 ? n0 : l == 1 ? n1 : n2;
+    uint32_t* b = l == 0 ? b0 : l == 1 ? b1 : b2;
+    const int N = N0 >> (2 * l);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((i & ~31) >= N) return;
+    const bool ok = i < N && !isnan(n[i].x);
+    const unsigned m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) b[i >> 5] = m;
+}
+void launch_valid_bits3(const float4* const* nmap, int W, int H, uint32_t* const* bits, cudaStream_t s)
+{
+    const int N0 = W * H;
+    dim3 g((N0 + 255) / 256, 3);
+    prof_mark(s, "k_valid_bits3"); k_valid_bits3<<<g, 256, 0, s>>>(nmap[0], nmap[1], nmap[2], N0, bits[0], bits[1], bits[2]);
 }
 void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s) { k_map_to_planar<<<(P + 255) / 256, 256, 0, s>>>(m, P, out); }
 

@@ -146,6 +146,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
         vmapG[l].alloc(Pl); nmapG[l].alloc(Pl); cloud[l].alloc(Pl); lastDepth[l].alloc(Pl); lastImage[l].alloc(Pl); corres[l].alloc(l == 0 ? Pl + (size_t)o->numSMs * 512 : 1);   // level 0 only: scratch when the correspondences do not fit in shared memory
         vmapG[l].zero(s); nmapG[l].zero(s); lastDepth[l].zero(s); lastImage[l].zero(s);
     }
+    if (id_ != 0) for (int l = 0; l < 3; ++l) { validBits[l].alloc(((size_t)(W >> l) * (H >> l) + 31) / 32 + 1); validBits[l].zero(s); }
     lastNextImage2.alloc((size_t)(W >> 2) * (H >> 2)); lastNextImage2.zero(s);
     trackState.alloc(1); trackState.zero(s);
     partial.alloc((size_t)TRACK_MAX_BLOCKS * 64); partial.zero(s);      // row tags start at 0: never a valid tag
@@ -196,15 +197,19 @@ void Model::prepareTracking()
     launch_model_maps(splatVertex, splatNormal, fillIn ? fillVertex.p : splatVertex.p, fillIn ? fillNormal.p : splatNormal.p, nb, denom, W, H,
                       dpose, 6.0f /* maxDepthRGB, RGBDOdometry.cpp:34 */, v, n, lastDepth[0], s);
     o->launches += 1;
+    if (validBits[0].p && o->trackValidBits) {
+        uint32_t* b3[3] = {validBits[0].p, validBits[1].p, validBits[2].p};
+        launch_valid_bits3(n, W, H, b3, s);
+        o->launches += 1;
+    }
     const bool rgb = o->cfg.rgbOnly || o->cfg.icpWeight < 100;
     if (rgb) {
-        launch_pyrdown2_f(lastDepth[0], W, H, lastDepth[1], lastDepth[2], s);
         launch_intensity_select(splatImage, fillIn ? fillImage.p : splatImage.p, nb, denom, (o->cfg.frameToFrameRGB && fillIn) ? 1 : 0, o->P, lastImage[0], s);
-        launch_pyrdown2_u8(lastImage[0], W, H, lastImage[1], lastImage[2], s);
+        launch_pyrdown2_pair(lastDepth[0], lastDepth[1], lastDepth[2], lastImage[0], lastImage[1], lastImage[2], W, H, s);
         const float* d3[3] = {lastDepth[0].p, lastDepth[1].p, lastDepth[2].p};
         float4* c3[3] = {cloud[0].p, cloud[1].p, cloud[2].p};
         launch_project_points3(d3, W, H, o->cam, c3, s);
-        o->launches += 4;
+        o->launches += 3;
     }
 }
 
@@ -294,6 +299,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     numSMs = prop.multiProcessorCount;
     set_num_sms(numSMs);
     if (const char* env = getenv("MFB200_FUSE_INDEX")) fuseIndexIntoClean = env[0] != '0';
+    if (const char* env = getenv("MFB200_TRACK_BITS")) trackValidBits = env[0] != '0';
     W = c.width; H = c.height; P = W * H;
     if (W % 4 || H % 4) throw CudaError{"width and height must be multiples of 4 (3-level pyramid)"};
     cam = Cam{c.fx, c.fy, c.cx, c.cy};
@@ -474,6 +480,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms, bool viaResult)
         }
         J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.bar = trackBars.p + j * 32;
         J.dpose = m->dpose;
+        for (int l = 0; l < 3; ++l) J.validBits[l] = (m->validBits[l].p && trackValidBits) ? m->validBits[l].p : nullptr;
     }
     if (preWaitPending) {            // the frame's preprocessing ran on preStream: the tracker is the first consumer on the main stream
         cudaCheck(cudaStreamWaitEvent(stream, preDone, 0), "cudaStreamWaitEvent");

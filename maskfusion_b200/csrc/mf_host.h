@@ -113,6 +113,7 @@ public:
     DevBuf<float4> vmapG[3], nmapG[3], cloud[3];
     DevBuf<float> lastDepth[3]; DevBuf<uint8_t> lastImage[3]; DevBuf<uint8_t> lastNextImage2;
     DevBuf<DataTerm> corres[3];
+    DevBuf<uint32_t> validBits[3];           // object models: validity bitmask of nmapG (see k_valid_bits3)
     DevBuf<TrackState> trackState; DevBuf<float> partial;
     DevBuf<DevPose> dpose;                  // what every kernel reads: pose, inverse, fusion weight (device resident)
     float* hTrackOut = nullptr;             // pinned: pose(16) transform(16) stats(8)
@@ -196,6 +197,7 @@ public:
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;
     bool fuseIndexIntoClean = true;         // Model::predictIndices rides inside the following Model::clean (one stream over the store); MFB200_FUSE_INDEX=0: two passes (A/B)
+    bool trackValidBits = false;            // MFB200_TRACK_BITS=1: object models carry a validity bitmask of their model maps for the tracker's early reject
     int tick = 1;
     int64_t launches = 0;
     std::vector<std::unique_ptr<Model>> models;

@@ -134,6 +134,7 @@ struct TrackJob {
     TrackState* st;
     float* partial;       // 2 x (TRACK_MAX_BLOCKS / 2) rows of 64 floats: per-CTA partial sums, ping-pong between reductions
     unsigned* bar;        // grid barrier counter of this job (own 128-byte line)
+    const uint32_t* validBits[3];   // object models: one bit per model-map pixel, set where the model normal is valid (nullptr: not used)
 };
 
 void set_num_sms(int n);
@@ -146,6 +147,7 @@ void launch_bilateral(const float* depth, float* out, int W, int H, cudaStream_t
 // fused variants: two pyramid levels per launch; three levels of a per-pixel kernel per launch (blockIdx.z = level)
 void launch_pyrdown2_f(const float* src, int sw, int sh, float* dst1, float* dst2, cudaStream_t s);
 void launch_pyrdown2_u8(const uint8_t* src, int sw, int sh, uint8_t* dst1, uint8_t* dst2, cudaStream_t s);
+void launch_pyrdown2_pair(const float* srcF, float* dstF1, float* dstF2, const uint8_t* srcU, uint8_t* dstU1, uint8_t* dstU2, int sw, int sh, cudaStream_t s);
 void launch_vmap_nmap3(const float* const* depth, int W, int H, Cam cam, float cutoff, float4* const* vmap, float4* const* nmap, cudaStream_t s);
 void launch_sobel3(const uint8_t* const* img, int W, int H, short2* const* grad, uint8_t* const* rgbValid, cudaStream_t s);
 void launch_project_points3(const float* const* depth, int W, int H, Cam cam, float4* const* cloud, cudaStream_t s);
@@ -154,6 +156,7 @@ void launch_intensity_select(const uchar4* imgPred, const uchar4* imgFill, const
 float track_min_scale(int level);          // gradient-magnitude gate of the photometric term at a pyramid level (RGBDOdometry.cpp:44-49)
 void launch_model_maps(const float4* srcVp, const float4* srcNp, const float4* srcVf, const float4* srcNf, const uint32_t* nonBlack, float denom,
                        int W, int H, const DevPose* dpose, float maxDepthRGB, float4* const* v, float4* const* n, float* depth0, cudaStream_t s);
+void launch_valid_bits3(const float4* const* nmap, int W, int H, uint32_t* const* bits, cudaStream_t s);    // bit i of level l = !isnan(nmap[l][i].x)
 void launch_map_to_planar(const float4* m, int P, float* out, cudaStream_t s);
 
 // ---- mf_surfel.cu ----

@@ -402,6 +402,7 @@ struct TrackParams {
     float icpWeight, angleThres, distThres, sobelScale, maxDepthDelta;
     float minScale[3];
     int corrSlots;                     // photometric correspondences kept per CTA in shared memory (0: global scratch instead)
+    int bitWords;                      // shared-memory words reserved for the model-map validity bitmask of a level (0: none)
     int cacheRounds;                   // pixel rounds per thread whose pose-independent inputs are kept in shared memory across the iterations of a level
     int phase;                         // 0: whole schedule in this launch; 1: SO(3) + level 2 only (cluster kernel); 2: resume at level 1
 };
@@ -740,6 +741,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
     float* const d1S = reinterpret_cast<float*>(ncS + cacheSlots);
     uint32_t* const pkS = reinterpret_cast<uint32_t*>(d1S + cacheSlots);          // valid | intensity << 1 | x << 9 | y << 20
     uint32_t* const gS = pkS + cacheSlots;                                         // Sobel gradient (short2 bits)
+    uint32_t* const bitsS = gS + cacheSlots;                                       // validity bitmask of the model's normal map at this level
 
     // ---------------- SO(3) pre-alignment on level-2 intensities (RGBDOdometry.cpp:272-345) ----------------
     if (tp.so3 && tp.phase != 2) {
@@ -864,7 +866,20 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
         const bool active = blockIdx.x < Gact;
         const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
-        const int rounds = (active && tid < N) ? (N - tid + nthr - 1) / nthr : 0;      // pixels of this thread: tid + r * nthr
+        // Pixels of this thread: tid + r * nthr for the fullRounds rounds every thread has, plus at most one pixel of the tail
+        // (N - fullRounds * nthr pixels).  The tail is dealt out by warps of 32 pixels ACROSS the CTAs (tail warp j -> CTA j % Gact,
+        // warp j / Gact): at 640x480 on 148 CTAs the 4096 tail pixels become one extra pixel for ONE warp of 128 CTAs instead of a
+        // fifth round (= a third pair of the two-deep pipeline below) for ALL warps of CTAs 0..7, which every other CTA then waited
+        // for at the grid barrier of each of the ten iterations.
+        const int fullRounds = N / nthr;
+        int kTail = -1;
+        if (active) {
+            const int j = (threadIdx.x >> 5) * (int)Gact + (int)blockIdx.x;
+            const int kt = fullRounds * nthr + j * 32 + (threadIdx.x & 31);
+            if (kt < N) kTail = kt;
+        }
+        const int rounds = active ? fullRounds + (kTail >= 0 ? 1 : 0) : 0;
+        auto kOf = [&](int r) { return r < fullRounds ? tid + r * nthr : kTail; };
         const Cam cam = camLevel(tp.cam, level);
         const float4* __restrict__ vmapC = J.vmapC[level];
         const float4* __restrict__ nmapC = J.nmapC[level];
@@ -891,10 +906,17 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         __syncthreads();
 
         // pose-independent inputs of pixel k
+        // object models: validity bitmask of this level's model maps -> shared memory (every CTA holds the whole level: gathers go anywhere)
+        const bool useBits = tp.icp && tp.bitWords > 0 && J.validBits[level] != nullptr && (N + 31) / 32 <= tp.bitWords;
+        if (useBits) {
+            const uint32_t* __restrict__ src = J.validBits[level];
+            for (int k = threadIdx.x; k < (N + 31) / 32; k += PT_THREADS) bitsS[k] = __ldg(src + k);
+        }
+        __syncthreads();
         // fill the per-level cache (see cacheSlots above)
         const int cRounds = min(rounds, tp.cacheRounds);
         for (int r = 0; r < cRounds; ++r) {
-            const int k = tid + r * nthr, slot = r * PT_THREADS + threadIdx.x;
+            const int k = kOf(r), slot = r * PT_THREADS + threadIdx.x;
             const int y = k / W, x = k - y * W;
             uint32_t pk = ((uint32_t)x << 9) | ((uint32_t)y << 20);
             float d1 = 0.f; float4 vc = make_float4(0, 0, 0, 0), nc = vc; uint32_t g = 0;
@@ -936,7 +958,11 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                 float3 vcp = m3v(st->RprevInv, sub3(vg, tprev));
                 int ux = __float2int_rn(vcp.x * cam.fx / vcp.z + cam.cx);
                 int uy = __float2int_rn(vcp.y * cam.fy / vcp.z + cam.cy);
-                if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) { p.iOK = true; p.ji = uy * W + ux; }
+                if (!(ux < 0 || uy < 0 || ux >= W || uy >= H || vcp.z < 0)) {
+                    p.ji = uy * W + ux;
+                    // the correspondence needs a valid model normal at ji (reduce.cu:346-352): known from the bitmask without the gathers
+                    p.iOK = !useBits || ((bitsS[p.ji >> 5] >> (p.ji & 31)) & 1u);
+                }
                 p.vg = vg; p.vcp = vcp;
             }
         };
@@ -997,12 +1023,12 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                     }
                 };
                 for (int r = 0; r < rounds; r += 2) {
-                    const int k0 = tid + r * nthr, k1 = k0 + nthr;
                     const bool two = r + 1 < rounds;
+                    const int k0 = kOf(r), k1 = two ? kOf(r + 1) : k0;
                     // next pair's streaming inputs -> L1 while this pair's dependent gathers are in flight (rounds not held in shared memory)
                     for (int q = 2; q < 4; ++q)
                         if (r + q < rounds && r + q >= cRounds) {
-                            const int kn = k0 + q * nthr;
+                            const int kn = kOf(r + q);
                             if (tp.icp) { prefetchL1(vmapC + kn); prefetchL1(nmapC + kn); }
                             if (tp.rgb) { prefetchL1(nextDepth + kn); }
                         }
@@ -1019,7 +1045,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
             TT(2);
             rc.Gact = Gact;
             // phase B's first streaming inputs (pose independent) -> L1 while this CTA waits at the reduction
-            if (tp.rgb && rounds > cRounds) { prefetchL1(grad + tid + cRounds * nthr); }
+            if (tp.rgb && rounds > cRounds) { prefetchL1(grad + kOf(cRounds)); }
             reduceStep<CL, NACC_ICP>(acc, cnt, sig, active, rc, red, ws, rowSh, tot);
             TT(5);
             if (tp.rgb) {
@@ -1069,8 +1095,8 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                             for (int b = a; b < 7; ++b) { accR[q] = fma((double)row[a], (double)row[b], accR[q]); ++q; }
                     };
                     for (int r = 0; r < rounds; r += 2) {
-                        const int k0 = tid + r * nthr, k1 = k0 + nthr;
                         const bool two = r + 1 < rounds;
+                        const int k0 = kOf(r), k1 = two ? kOf(r + 1) : k0;
                         const int2 c0 = corr[r * PT_THREADS + threadIdx.x];
                         const int2 c1 = two ? corr[(r + 1) * PT_THREADS + threadIdx.x] : make_int2(-1, 0);
                         short2 g0 = make_short2(0, 0), g1 = g0;
@@ -1089,7 +1115,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                 // the next iteration's first pixel pair (pose-independent inputs) -> L1 across the reduction and the solve
                 for (int q = cRounds; q < cRounds + 2; ++q)
                     if (q < rounds) {
-                        const int kn = tid + q * nthr;
+                        const int kn = kOf(q);
                         if (tp.icp) { prefetchL1(vmapC + kn); prefetchL1(nmapC + kn); }
                         prefetchL1(nextDepth + kn);
                     }
@@ -1202,7 +1228,8 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     tp.angleThres = (float)sin(20.f * 3.14159254f / 180.f);
     tp.distThres = 0.10f; tp.sobelScale = (float)(1.0 / 8.0); tp.maxDepthDelta = 0.07f;
     for (int l = 0; l < 3; ++l) tp.minScale[l] = track_min_scale(l);
-    tp.phase = 0; tp.cacheRounds = 0;
+    tp.phase = 0; tp.cacheRounds = 0; tp.bitWords = 0;
+    const bool bitsOn = nJobs > 1 || true;            // the words are only used by jobs that carry a bitmask (object models)
     static int cacheOn = -1;        // MFB200_TRACK_CACHE=0: every iteration re-reads its pose-independent inputs from global memory (A/B)
     if (cacheOn < 0) { const char* e = getenv("MFB200_TRACK_CACHE"); cacheOn = e ? (e[0] != '0') : MFB200_DEFAULT_TRACK_CACHE; }
     int G = numSMs / nJobs;                      // one CTA per SM, the SMs split between the tracked models
@@ -1222,8 +1249,11 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
             if (t1.rgb && dynC <= dynMaxClDev[dev]) t1.corrSlots = roundsC * PT_THREADS; else { t1.corrSlots = 0; dynC = 0; }
             if (t1.rgb && t1.corrSlots == 0) break;             // the global scratch stripe is sized for the persistent grid only
             dynC = (dynC + 15) & ~(size_t)15;
-            t1.cacheRounds = cacheOn ? (int)std::min<size_t>((size_t)roundsC, (dynMaxClDev[dev] - dynC) / ((size_t)PT_THREADS * CACHE_BYTES_PER_SLOT)) : 0;
-            dynC += (size_t)t1.cacheRounds * PT_THREADS * CACHE_BYTES_PER_SLOT;
+            t1.bitWords = bitsOn ? (N2 + 31) / 32 : 0;
+            const size_t bitBytesC = ((size_t)t1.bitWords * 4 + 15) & ~(size_t)15;
+            if (dynC + bitBytesC > dynMaxClDev[dev]) { t1.bitWords = 0; }
+            t1.cacheRounds = cacheOn ? (int)std::min<size_t>((size_t)roundsC, (dynMaxClDev[dev] - dynC - (t1.bitWords ? bitBytesC : 0)) / ((size_t)PT_THREADS * CACHE_BYTES_PER_SLOT)) : 0;
+            dynC += (size_t)t1.cacheRounds * PT_THREADS * CACHE_BYTES_PER_SLOT + (t1.bitWords ? bitBytesC : 0);
             cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof cfg);
             cfg.gridDim = dim3(C, nJobs); cfg.blockDim = dim3(PT_THREADS); cfg.dynamicSmemBytes = dynC; cfg.stream = s;
             cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -1244,8 +1274,11 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     size_t dyn = (size_t)rounds0 * PT_THREADS * sizeof(int2);
     if (tp.rgb && dyn <= dynMaxDev[dev]) tp.corrSlots = rounds0 * PT_THREADS; else { tp.corrSlots = 0; dyn = 0; }
     dyn = (dyn + 15) & ~(size_t)15;
-    tp.cacheRounds = cacheOn ? (int)std::min<size_t>((size_t)rounds0, (dynMaxDev[dev] - dyn) / ((size_t)PT_THREADS * CACHE_BYTES_PER_SLOT)) : 0;
-    dyn += (size_t)tp.cacheRounds * PT_THREADS * CACHE_BYTES_PER_SLOT;
+    tp.bitWords = bitsOn ? (W * H + 31) / 32 : 0;
+    const size_t bitBytes = ((size_t)tp.bitWords * 4 + 15) & ~(size_t)15;
+    if (dyn + bitBytes > dynMaxDev[dev]) tp.bitWords = 0;
+    tp.cacheRounds = cacheOn ? (int)std::min<size_t>((size_t)rounds0, (dynMaxDev[dev] - dyn - (tp.bitWords ? bitBytes : 0)) / ((size_t)PT_THREADS * CACHE_BYTES_PER_SLOT)) : 0;
+    dyn += (size_t)tp.cacheRounds * PT_THREADS * CACHE_BYTES_PER_SLOT + (tp.bitWords ? bitBytes : 0);
     cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
     prof_mark(s, "k_track_persistent");
     void* args[] = {(void*)&jp, (void*)&tp};
