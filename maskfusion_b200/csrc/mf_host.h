@@ -197,7 +197,7 @@ public:
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;
     bool fuseIndexIntoClean = true;         // Model::predictIndices rides inside the following Model::clean (one stream over the store); MFB200_FUSE_INDEX=0: two passes (A/B)
-    bool trackValidBits = false;            // MFB200_TRACK_BITS=1: object models carry a validity bitmask of their model maps for the tracker's early reject
+    bool trackValidBits = true;             // MFB200_TRACK_BITS=0 switches it off: object models carry a validity bitmask of their model maps for the tracker's early reject
     int tick = 1;
     int64_t launches = 0;
     std::vector<std::unique_ptr<Model>> models;

@@ -1191,7 +1191,7 @@ static int trackBlocks(int N, int numSMs)
 }
 
 int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
-                    bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s)
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s, bool anyValidBits)
 {
     // per-device launch limits (several contexts on different GPUs may live in one process): occupancy and the opt-in
     // dynamic shared memory attribute are properties of (function, device)
@@ -1229,7 +1229,7 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     tp.distThres = 0.10f; tp.sobelScale = (float)(1.0 / 8.0); tp.maxDepthDelta = 0.07f;
     for (int l = 0; l < 3; ++l) tp.minScale[l] = track_min_scale(l);
     tp.phase = 0; tp.cacheRounds = 0; tp.bitWords = 0;
-    const bool bitsOn = nJobs > 1 || true;            // the words are only used by jobs that carry a bitmask (object models)
+    const bool bitsOn = anyValidBits;                 // shared-memory words for the bitmask of a level: only when a job carries one (object models)
     static int cacheOn = -1;        // MFB200_TRACK_CACHE=0: every iteration re-reads its pose-independent inputs from global memory (A/B)
     if (cacheOn < 0) { const char* e = getenv("MFB200_TRACK_CACHE"); cacheOn = e ? (e[0] != '0') : MFB200_DEFAULT_TRACK_CACHE; }
     int G = numSMs / nJobs;                      // one CTA per SM, the SMs split between the tracked models
