@@ -149,7 +149,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     if (id_ != 0) for (int l = 0; l < 3; ++l) { validBits[l].alloc(((size_t)(W >> l) * (H >> l) + 31) / 32 + 1); validBits[l].zero(s); }
     lastNextImage2.alloc((size_t)(W >> 2) * (H >> 2)); lastNextImage2.zero(s);
     trackState.alloc(1); trackState.zero(s);
-    partial.alloc((size_t)TRACK_MAX_BLOCKS * 64); partial.zero(s);      // row tags start at 0: never a valid tag
+    partial.alloc((size_t)TRACK_MAX_BLOCKS * 128); partial.zero(s);     // 2 x 512 rows x 32 x 16 B (flagged words); flags start at 0: never a valid flag
     dpose.alloc(1); pushPose();
     o->launches += 3;
 }

@@ -132,7 +132,7 @@ struct TrackJob {
     DataTerm* corres[3];
     DevPose* dpose;       // initial pose in, tracked pose + derived quantities out
     TrackState* st;
-    float* partial;       // 2 x (TRACK_MAX_BLOCKS / 2) rows of 64 floats: per-CTA partial sums, ping-pong between reductions
+    float* partial;       // 2 x (TRACK_MAX_BLOCKS / 2) rows of 32 x 16 bytes: per-CTA partial sums (fp64 value + flags), ping-pong between reductions
     unsigned* bar;        // grid barrier counter of this job (own 128-byte line)
     const uint32_t* validBits[3];   // object models: one bit per model-map pixel, set where the model normal is valid (nullptr: not used)
 };

@@ -31,6 +31,9 @@ namespace mfb {
 #ifndef MFB200_DEFAULT_TRACK_CACHE
 #define MFB200_DEFAULT_TRACK_CACHE 0
 #endif
+#ifndef MFB200_DEFAULT_TRACK_LL
+#define MFB200_DEFAULT_TRACK_LL 1
+#endif
 #define CACHE_BYTES_PER_SLOT 44        // float4 vertex + float4 normal + depth + packed (valid, intensity, x, y) + Sobel gradient
 #define TRK_THREADS 256
 #define NACC_ICP 29
@@ -405,6 +408,7 @@ struct TrackParams {
     int bitWords;                      // shared-memory words reserved for the model-map validity bitmask of a level (0: none)
     int cacheRounds;                   // pixel rounds per thread whose pose-independent inputs are kept in shared memory across the iterations of a level
     int phase;                         // 0: whole schedule in this launch; 1: SO(3) + level 2 only (cluster kernel); 2: resume at level 1
+    unsigned llBase;                   // != 0: the partial rows are exchanged as flagged words (flag = llBase + index of the reduction in the launch)
 };
 
 // sum of 32 per-lane values over the warp with 31 (64-bit) shuffles instead of 5*32: each step exchanges HALF of the remaining
@@ -515,7 +519,74 @@ MF_D void sumRows(const double* __restrict__ rows, unsigned R, double (*ws)[ROWF
 //                (double-buffered), barrier.cluster replaces the L2 round trips of the software barrier, the rows of the peers are read
 //                through distributed shared memory.  Used for SO(3) pre-alignment and level 2 (19 k pixels: 14 iterations whose cost
 //                is the reduction, not the pixels).
-struct RedCtx { double* rowsBuf[2]; unsigned* bar; unsigned G, Gact, gen; };
+// ---- flagged exchange of the partial rows (the LL scheme of collective libraries) ----
+// A row travels as 32 x 16 bytes {value.lo, flag, value.hi, flag}: every 8-byte half carries the flag of THIS reduction, 8-byte stores
+// are single transactions, so a reader that finds both flags holds the value -- no release fence on the producer, no arrival counter,
+// no second round trip for the data: the consumers poll the rows themselves.  The software barrier cost one fence + one atomic + one
+// polled counter + one row read per reduction (~2.6-3.5 us of L2 latency, 48 reductions per frame); this costs the row read alone.
+// Flags are unique per reduction and launch (llBase advances by 64 per launch, 0 is never used), rows ping-pong between two buffers:
+// a CTA writes reduction g + 2 only after it has consumed g + 1 from every peer, which every peer produced after consuming g.
+MF_D void llStore(uint4* p, double v, unsigned flag)
+{
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)__double2loint(v)), "r"(flag), "r"((unsigned)__double2hiint(v)), "r"(flag) : "memory");
+}
+MF_D uint4 llLoad(const uint4* p)
+{
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+template <int N>
+MF_D void ctaReduceStoreLL(const double* acc, double (*red)[ROWF], uint4* __restrict__ rowOut, unsigned flag, int extra0, int extra1)
+{
+    double v[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) v[k] = k < N ? acc[k] : 0.0;
+    v[29] = (double)extra0; v[30] = (double)extra1;
+    warpReduceHalving32(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    red[warp][lane] = v[0];
+    __syncthreads();
+    if (threadIdx.x < ROWF) {
+        double s = 0;
+#pragma unroll
+        for (int w = 0; w < PT_WARPS; ++w) s += red[w][threadIdx.x];
+        llStore(rowOut + threadIdx.x, s, flag);
+    }
+}
+// same summation order as sumRows (warp w: rows w, w + 16, ... ascending; then the 16 warp sums ascending)
+MF_D void sumRowsLL(const uint4* __restrict__ rows, unsigned R, unsigned flag, double (*ws)[ROWF], double* tot)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double a0 = 0;
+    for (unsigned base = warp; base < R; base += PT_WARPS * SUM_BATCH) {
+        uint4 x[SUM_BATCH];
+        unsigned pending = 0;                                              // warp uniform: rows of the batch not yet seen complete
+#pragma unroll
+        for (int i = 0; i < SUM_BATCH; ++i) { x[i] = make_uint4(0, 0, 0, 0); if (base + (unsigned)i * PT_WARPS < R) pending |= 1u << i; }
+        while (pending) {
+#pragma unroll
+            for (int i = 0; i < SUM_BATCH; ++i)
+                if ((pending >> i) & 1u) x[i] = llLoad(rows + (size_t)(base + (unsigned)i * PT_WARPS) * ROWF + lane);
+#pragma unroll
+            for (int i = 0; i < SUM_BATCH; ++i)
+                if ((pending >> i) & 1u) { if (__all_sync(0xffffffffu, x[i].y == flag && x[i].w == flag)) pending &= ~(1u << i); }
+        }
+#pragma unroll
+        for (int i = 0; i < SUM_BATCH; ++i) a0 += __hiloint2double((int)x[i].z, (int)x[i].x);      // rows beyond R contribute +0.0 as in sumRows
+    }
+    ws[warp][lane] = a0;
+    __syncthreads();
+    if (threadIdx.x < ROWF) {
+        double s2 = 0;
+#pragma unroll
+        for (int w = 0; w < PT_WARPS; ++w) s2 += ws[w][threadIdx.x];
+        tot[threadIdx.x] = s2;
+    }
+    __syncthreads();
+}
+
+struct RedCtx { double* rowsBuf[2]; unsigned* bar; unsigned G, Gact, gen, llBase; };
 template <bool CL, int N>
 MF_D void reduceStep(const double* acc, int e0, int e1, bool active, RedCtx& rc, double (*red)[ROWF], double (*ws)[ROWF], double (*rowSh)[ROWF], double* tot)
 {
@@ -532,10 +603,19 @@ MF_D void reduceStep(const double* acc, int e0, int e1, bool active, RedCtx& rc,
         }
         __syncthreads();
     } else {
-        double* rows = rc.rowsBuf[rc.gen & 1];
-        if (active) ctaReduceStore<N>(acc, red, rows + (size_t)blockIdx.x * ROWF, e0, e1);
-        ++rc.gen; gridBarrier(rc.bar, rc.gen * rc.G);
-        sumRows(rows, rc.Gact, ws, tot);
+        if (rc.llBase) {
+            // 16 bytes per value: the two ping-pong buffers are 2 * G * ROWF doubles each
+            uint4* rows = reinterpret_cast<uint4*>(rc.rowsBuf[0]) + (size_t)(rc.gen & 1) * rc.G * ROWF;
+            ++rc.gen;
+            const unsigned flag = rc.llBase + rc.gen;
+            if (active) ctaReduceStoreLL<N>(acc, red, rows + (size_t)blockIdx.x * ROWF, flag, e0, e1);
+            sumRowsLL(rows, rc.Gact, flag, ws, tot);
+        } else {
+            double* rows = rc.rowsBuf[rc.gen & 1];
+            if (active) ctaReduceStore<N>(acc, red, rows + (size_t)blockIdx.x * ROWF, e0, e1);
+            ++rc.gen; gridBarrier(rc.bar, rc.gen * rc.G);
+            sumRows(rows, rc.Gact, ws, tot);
+        }
     }
 }
 
@@ -562,6 +642,16 @@ MF_D double inv3dEntry(const double* M, int e)
     const double det = M[0] * c00 + M[1] * c01 + M[2] * c02;
     return cof * (1.0 / det);
 }
+
+// optional stage clock of the persistent kernel (A/B build -DMF_TRACK_TIMING; read back by mf_debug_track_timing): CTA 0 of model 0
+// appends (tag, clock64) pairs at the stage boundaries of every reduction
+#ifdef MF_TRACK_TIMING
+__device__ long long g_trackTiming[8192];
+__device__ int g_trackTimingN;
+#define TT(tag) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { int q_ = g_trackTimingN; if (q_ + 2 <= 8192) { g_trackTiming[q_] = (tag); g_trackTiming[q_ + 1] = clock64(); g_trackTimingN = q_ + 2; } } } while (0)
+#else
+#define TT(tag) do { } while (0)
+#endif
 
 struct SolveScratch { double A[36], b[6], x[6], Rt[16], nr[16], Ri[9], K[9], Kinv[9], tmp[9], ti[3]; float trR[9], trT[3], iR[9], iT[3]; int fast; };
 
@@ -600,7 +690,9 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
     }
     if (ICP && lane == 31) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
     __syncwarp();
-    ldltSolvePivWarp<6>(sc->A, sc->b, sc->x);              // bit-identical to the sequential pivoted routine (Eigen's ldlt().solve conventions)
+    TT(20);
+    ldltSolvePivWarp<6>(sc->A, sc->b, sc->x);
+    TT(21);              // bit-identical to the sequential pivoted routine (Eigen's ldlt().solve conventions)
     // computeUpdateSE3 (OdometryProvider.h:69-90): Rt = [rodrigues(x[3..5]) | x[0..2]]; every lane evaluates the (cheap, identical)
     // scalar part, lanes < 16 assemble one entry each
     {
@@ -629,6 +721,7 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
         }
     }
     __syncwarp();
+    TT(22);
     double nrv = 0;
     if (lane < 16) {
         int r = lane >> 2, c = lane & 3;
@@ -651,6 +744,7 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
     if (lane < 9) { int r = lane / 3, c = lane % 3; st->Rcurr[lane] = (st->Rprev[r * 3] * sc->iR[c] + st->Rprev[r * 3 + 1] * sc->iR[3 + c]) + st->Rprev[r * 3 + 2] * sc->iR[6 + c]; }
     else if (lane < 12) { int r = lane - 9; st->tcurr[r] = ((st->Rprev[r * 3] * sc->iT[0] + st->Rprev[r * 3 + 1] * sc->iT[1]) + st->Rprev[r * 3 + 2] * sc->iT[2]) + st->tprev[r]; }
     __syncwarp();
+    TT(23);
     if (RGB) computeWarpCoop(st, cam, sc, lane);          // warp constants for the next iteration's residuals
 }
 
@@ -665,15 +759,6 @@ struct PixA {
 
 extern __shared__ int2 corrShared[];
 
-// optional stage clock of the persistent kernel (A/B build -DMF_TRACK_TIMING; read back by mf_debug_track_timing): CTA 0 of model 0
-// appends (tag, clock64) pairs at the stage boundaries of every reduction
-#ifdef MF_TRACK_TIMING
-__device__ long long g_trackTiming[8192];
-__device__ int g_trackTimingN;
-#define TT(tag) do { if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { int q_ = g_trackTimingN; if (q_ + 2 <= 8192) { g_trackTiming[q_] = (tag); g_trackTiming[q_ + 1] = clock64(); g_trackTimingN = q_ + 2; } } } while (0)
-#else
-#define TT(tag) do { } while (0)
-#endif
 
 template <bool CL>
 MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
@@ -725,7 +810,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
     __syncthreads();
     RedCtx rc;
     rc.rowsBuf[0] = reinterpret_cast<double*>(J.partial); rc.rowsBuf[1] = reinterpret_cast<double*>(J.partial) + (size_t)G * ROWF;
-    rc.bar = J.bar; rc.G = G; rc.Gact = G; rc.gen = 0;
+    rc.bar = J.bar; rc.G = G; rc.Gact = G; rc.gen = 0; rc.llBase = CL ? 0u : tp.llBase;
     // photometric correspondences of this thread's pixels, slot = round * PT_THREADS + thread: written in phase A, read in phase B
     // by the same thread.  Shared memory when the launch reserved enough, else a private stripe of the model's scratch buffer.
     int2* const corr = tp.corrSlots ? corrShared : reinterpret_cast<int2*>(J.corres[0]) + (size_t)blockIdx.x * ((size_t)((tp.W * tp.H + G * PT_THREADS - 1) / (G * PT_THREADS)) * PT_THREADS);
@@ -1228,7 +1313,15 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     tp.angleThres = (float)sin(20.f * 3.14159254f / 180.f);
     tp.distThres = 0.10f; tp.sobelScale = (float)(1.0 / 8.0); tp.maxDepthDelta = 0.07f;
     for (int l = 0; l < 3; ++l) tp.minScale[l] = track_min_scale(l);
-    tp.phase = 0; tp.cacheRounds = 0; tp.bitWords = 0;
+    tp.phase = 0; tp.cacheRounds = 0; tp.bitWords = 0; tp.llBase = 0;
+    static int llOn = -1;           // MFB200_TRACK_LL=0: counter barrier + plain rows instead of the flagged exchange (A/B)
+    if (llOn < 0) { const char* e = getenv("MFB200_TRACK_LL"); llOn = e ? (e[0] != '0') : MFB200_DEFAULT_TRACK_LL; }
+    static unsigned llEpoch[64];    // per device; every launch owns 64 flag values
+    if (llOn) {
+        unsigned ep = ++llEpoch[dev];
+        if ((ep << 6) == 0u) ep = ++llEpoch[dev];           // flag 0 means "never written"
+        tp.llBase = ep << 6;
+    }
     const bool bitsOn = anyValidBits;                 // shared-memory words for the bitmask of a level: only when a job carries one (object models)
     static int cacheOn = -1;        // MFB200_TRACK_CACHE=0: every iteration re-reads its pose-independent inputs from global memory (A/B)
     if (cacheOn < 0) { const char* e = getenv("MFB200_TRACK_CACHE"); cacheOn = e ? (e[0] != '0') : MFB200_DEFAULT_TRACK_CACHE; }

@@ -27,7 +27,7 @@ def main():
     n = mf.L.mf_debug_track_timing(buf.ctypes.data, 8192)
     ev = buf[:n].reshape(-1, 2)
     ghz = 1.965
-    names = {2: "A pixels", 5: "A reduce+exchange+sum", 6: "B pixels (+sigma)", 9: "B reduce+exchange+sum", 10: "solve + pose update",
+    names = {2: "A pixels", 5: "A reduce+exchange+sum", 6: "B pixels (+sigma)", 9: "B reduce+exchange+sum", 20: "solve: assemble A, b", 21: "solve: pivoted LDLT", 22: "solve: rodrigues", 23: "solve: pose composition", 10: "solve: warp constants + barrier",
              12: "so3 pixels", 15: "so3 reduce+exchange+sum", 16: "so3 solve"}
     acc = collections.defaultdict(lambda: [0, 0.0])
     level = "so3"
