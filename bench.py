@@ -144,7 +144,8 @@ def algorithmic_bytes(name, S, P):
         "k_index_resolve": 8 * P + 52 * P,
         "k_clean_p1": 32 * S + 1 * (S + P),       # position + colour/time planes, keep flag (round 2: the index projection rides in the same stream)
         "k_clean_p2": 48 * P + 4 * P,              # ~one candidate per pixel neighbourhood; window reads hit L2 (the candidate list is ~S/3 long: see DESIGN.md)
-        "k_clean_scatter": 48 * S + 48 * S + 1 * (S + P),
+        "k_clean_scatter": 48 * S + 48 * S + 1 * (S + P),       # ping-pong copy of the whole store (MFB200_CLEAN_INPLACE=0)
+        "k_clean_compact": 1 * (S + P),                      # in-place compaction: keep flags; the moved tail (96 B per surfel behind the first removal) is data dependent
         "k_splat_project": 16 * S,                   # position plane for every surfel; +32 B only for in-frustum stable ones
         "k_splat_resolve": 8 * P + 38 * P + 36 * P,
         "k_associate": 13 * P + 93 * P,

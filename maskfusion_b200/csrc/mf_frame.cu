@@ -364,7 +364,9 @@ __global__ void k_project_points3(Maps3 m, int W0, int H0, Cam cam0)
     const Cam cam = camLevel(cam0, l);
     float z = m.depth[l][y * W + x];
     float ifx = 1.0f / cam.fx, ify = 1.0f / cam.fy;
-    m.cloud[l][y * W + x] = make_float4(((float)x - cam.cx) * z * ifx, ((float)y - cam.cy) * z * ify, z, 0.f);
+    // .w: the 1.0 / cloudPoint.z of rgbKernel (reduce.cu:574, a double-precision reciprocal rounded to float), which depends on the map alone:
+    // evaluated here once per frame instead of once per photometric row in each of the 19 Gauss-Newton iterations
+    m.cloud[l][y * W + x] = make_float4(((float)x - cam.cx) * z * ifx, ((float)y - cam.cy) * z * ify, z, (float)(1.0 / (double)z));
 }
 
 // ------------------------------ host launchers ----------------------------------------

@@ -123,7 +123,8 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     const int W = o->W, H = o->H, P = o->P;
     cudaStream_t s = o->stream;
     if (ghost) return;
-    for (int b = 0; b < 2; ++b) { pos[b].alloc(capacity); col[b].alloc(capacity); nrm[b].alloc(capacity); }
+    // in-place clean (default): ONE copy of the store; the ping-pong pair only for the A/B path MFB200_CLEAN_INPLACE=0
+    for (int b = 0; b < (o->cleanInPlace ? 1 : 2); ++b) { pos[b].alloc(capacity); col[b].alloc(capacity); nrm[b].alloc(capacity); }
     count.alloc(2); count.zero(s);
     cudaCheck(cudaMallocHost((void**)&hCount, 2 * sizeof(uint32_t)), "cudaMallocHost"); hCount[0] = hCount[1] = 0;
     cudaCheck(cudaMallocHost((void**)&hTrackOut, 40 * sizeof(float)), "cudaMallocHost");
@@ -140,6 +141,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     keep.alloc((size_t)capacity + P);
     size_t nblk = ((size_t)capacity + P + 511) / 512 + 1;
     blockSums.alloc(nblk); blockSums2.alloc(nblk);
+    if (o->cleanInPlace) { cleanTicket.alloc(2); cleanTicket.zero(s); cleanLoaded.alloc(nblk); cleanLoaded.zero(s); }
     cand.alloc((size_t)capacity + P); candCount.alloc(1); candCount.zero(s);
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
@@ -266,15 +268,18 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
 {
     MaskFusion* o = owner;
     float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
-    int other = 1 - target, otherCount = 1 - countSel;
+    const bool inPlace = o->cleanInPlace;
+    int other = inPlace ? target : 1 - target, otherCount = 1 - countSel;
     // the pending index projection rides in pass 1 when it uses this call's time gate (always, in the frame schedule)
     const bool fused = idxDeferred && idxTime == time && idxDelta == timeDelta && (size_t)capacity + (size_t)o->P < 0x80000000ull;   // bit 31 of a candidate entry is a flag
     if (!fused) flushIndex();
     IndexFused f{key.p, idx.p, vertConf.p, colorTime.p, normRad.p, cleanTex.p, idxDepth};
     idxDeferred = false;
+    if (++cleanEpoch == 0) ++cleanEpoch;                              // 0 = "never published"
+    CleanInPlace ip{cleanTicket.p, cleanLoaded.p, cleanTicket.p + 1, cleanEpoch};
     launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, dpose, o->cam, o->W, o->H,
                  time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, cleanTex, o->depthFilt, o->mask, keep, blockSums,
-                 cand, candCount, o->stream, fused ? &f : nullptr);
+                 cand, candCount, o->stream, fused ? &f : nullptr, inPlace ? &ip : nullptr);
     target = other; countSel = otherCount;
     o->launches += fused ? 6 : 5;
 }
@@ -300,6 +305,7 @@ MaskFusion::MaskFusion(const mf_config& c, int dev, cudaStream_t st) : cfg(c), d
     set_num_sms(numSMs);
     if (const char* env = getenv("MFB200_FUSE_INDEX")) fuseIndexIntoClean = env[0] != '0';
     if (const char* env = getenv("MFB200_TRACK_BITS")) trackValidBits = env[0] != '0';
+    if (const char* env = getenv("MFB200_CLEAN_INPLACE")) cleanInPlace = env[0] != '0';
     W = c.width; H = c.height; P = W * H;
     if (W % 4 || H % 4) throw CudaError{"width and height must be multiples of 4 (3-level pyramid)"};
     cam = Cam{c.fx, c.fy, c.cx, c.cy};

@@ -109,6 +109,7 @@ public:
     // association
     DevBuf<uint8_t> aflag; DevBuf<uint32_t> abest; DevBuf<float4> meas[3]; DevBuf<uint32_t> slot;
     DevBuf<uint8_t> keep; DevBuf<uint32_t> blockSums, blockSums2, cand, candCount;
+    DevBuf<uint32_t> cleanTicket, cleanLoaded; uint32_t cleanEpoch = 0;     // in-place compaction of Model::clean: [0] ticket, [1] first moved sub-block; published epochs
     // tracking
     DevBuf<float4> vmapG[3], nmapG[3], cloud[3];
     DevBuf<float> lastDepth[3]; DevBuf<uint8_t> lastImage[3]; DevBuf<uint8_t> lastNextImage2;
@@ -197,6 +198,7 @@ public:
     mf_config cfg; Cam cam; int W, H, P; int device; cudaStream_t stream; bool ownStream;
     int numSMs = 148;
     bool fuseIndexIntoClean = true;         // Model::predictIndices rides inside the following Model::clean (one stream over the store); MFB200_FUSE_INDEX=0: two passes (A/B)
+    bool cleanInPlace = true;               // Model::clean compacts the store in place, touching only the tail behind the first removal; MFB200_CLEAN_INPLACE=0: ping-pong copy of the whole store (A/B)
     bool trackValidBits = true;             // MFB200_TRACK_BITS=0 switches it off: object models carry a validity bitmask of their model maps for the tracker's early reject
     int tick = 1;
     int64_t launches = 0;

@@ -173,11 +173,14 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
                         const SurfelPlanes& sp, cudaStream_t s);
 // index-map outputs of a Model::predictIndices that is carried out INSIDE the clean pass (one stream over the store instead of two)
 struct IndexFused { uint64_t* key; uint32_t* idx; float4* vertConf; float4* colorTime; float4* normRad; float4* cleanTex; float maxDepth; };
+// in-place ordered compaction of Model::clean (k_clean_compact): ticket (reset by the sums pass), one published-epoch word per 512-entry
+// sub-block, the first sub-block that holds a removal (written by the scan), the epoch of this call (never 0, changes with every call)
+struct CleanInPlace { uint32_t* ticket; uint32_t* loaded; uint32_t* firstMoved; uint32_t epoch; };
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* dpose, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const float4* cleanTex,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s,
-                  const IndexFused* fused = nullptr);
+                  const IndexFused* fused = nullptr, const CleanInPlace* inplace = nullptr);
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth,
                              float confThreshold, int time, int maxTime, int timeDelta, const float4* rayTab, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,

@@ -449,57 +449,66 @@ __global__ void __launch_bounds__(256, 4) k_clean_p2(float4* __restrict__ pos, f
     }
 }
 
-// per-512-element keep counts for the ordered compaction
-__global__ void __launch_bounds__(SCAN_BLOCK) k_keep_block_sums(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ countPtr, int Ppix,
-                                                                uint32_t* __restrict__ blockSums, uint32_t* __restrict__ candCount)
+// per-512-element keep counts for the ordered compaction: one WARP per sub-block (16 flag bytes per lane, no block barriers;
+// the block-per-sub-block version spent 14 us in two barriers and a serial 16-term sum per 512 flags)
+__global__ void __launch_bounds__(256) k_keep_block_sums(const uint8_t* __restrict__ keep, const uint32_t* __restrict__ countPtr, int Ppix,
+                                                         uint32_t* __restrict__ blockSums, uint32_t* __restrict__ candCount, uint32_t* __restrict__ ticket)
 {
     const uint32_t total = *countPtr + (uint32_t)Ppix;
     const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    __shared__ uint32_t wsum[SCAN_BLOCK / 32];
-    if (blockIdx.x == 0 && threadIdx.x == 0) *candCount = 0;          // self-cleaning: ready for the next clean
-    for (uint32_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
-        uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
-        bool k = e < total && keep[e];
-        unsigned bal = __ballot_sync(0xffffffffu, k);
-        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(bal);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t sum = 0;
-            for (int w = 0; w < SCAN_BLOCK / 32; ++w) sum += wsum[w];
-            blockSums[blk] = sum;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *candCount = 0; if (ticket) *ticket = 0; }       // self-cleaning: ready for the next clean / the compaction below
+    const uint32_t lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t blk = gw; blk < nblk; blk += nw) {
+        const uint32_t e0 = blk * SCAN_BLOCK + lane * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (e0 < total) v = *reinterpret_cast<const uint4*>(keep + e0);                           // flags are 0 / 1 bytes; the buffer is a multiple of 16 bytes
+        if (e0 < total && total - e0 < 16) {                                                      // flags beyond `total` were never written
+            const uint32_t r = total - e0;
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const uint32_t lo = (uint32_t)q * 4; w[q] = r <= lo ? 0u : (r - lo >= 4 ? w[q] : (w[q] & ((1u << (8 * (r - lo))) - 1u))); }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        __syncthreads();
+        uint32_t c = __popc(v.x & 0x01010101u) + __popc(v.y & 0x01010101u) + __popc(v.z & 0x01010101u) + __popc(v.w & 0x01010101u);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if (lane == 0) blockSums[blk] = c;
     }
 }
 
-// pass 2: exclusive scan of the block sums (single block) -> block offsets, new count
+// pass 2: exclusive scan of the block sums (single block: every thread owns a run of consecutive sums, the 1024 run totals are
+// scanned with shuffles) -> block offsets, new count, and the first sub-block that holds a removal (everything before it stays in place)
 __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* __restrict__ blockSums, const uint32_t* __restrict__ countPtr,
-                                                          int extra, uint32_t capacity, uint32_t* __restrict__ newCount)
+                                                          int extra, uint32_t capacity, uint32_t* __restrict__ newCount, uint32_t* __restrict__ firstMoved)
 {
     const uint32_t total = *countPtr + (uint32_t)extra;
     const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    __shared__ uint32_t sh[1024];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
+    __shared__ uint32_t wtot[32];
+    __shared__ uint32_t sFirst;
+    if (threadIdx.x == 0) sFirst = nblk;
     __syncthreads();
-    for (uint32_t base = 0; base < nblk; base += 1024) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t v = i < nblk ? blockSums[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int off = 1; off < 1024; off <<= 1) {
-            uint32_t t = threadIdx.x >= off ? sh[threadIdx.x - off] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
-        }
-        uint32_t incl = sh[threadIdx.x];
-        if (i < nblk) blockSums[i] = carry + incl - v;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry += incl;
-        __syncthreads();
+    const uint32_t per = (nblk + 1023) / 1024;
+    const uint32_t b0 = threadIdx.x * per, b1 = min(b0 + per, nblk);
+    uint32_t run = 0, first = 0xffffffffu;
+    for (uint32_t i = b0; i < b1; ++i) { const uint32_t v = blockSums[i]; run += v; if (v != SCAN_BLOCK && first == 0xffffffffu) first = i; }
+    if (first != 0xffffffffu) atomicMin(&sFirst, first);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = run;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = wtot[lane], wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, off); if (lane >= off) wi += t; }
+        wtot[lane] = wi - w;                                         // exclusive prefix of the warp totals
+        if (lane == 31) { *newCount = wi < capacity ? wi : capacity; }
     }
-    if (threadIdx.x == 0) *newCount = carry < capacity ? carry : capacity;
+    __syncthreads();
+    uint32_t offs = wtot[warp] + incl - run;
+    for (uint32_t i = b0; i < b1; ++i) { const uint32_t v = blockSums[i]; blockSums[i] = offs; offs += v; }
+    if (threadIdx.x == 0 && firstMoved) *firstMoved = sFirst;
 }
 
 // pass 3: ordered scatter of the survivors (old surfels in buffer order, then new vertices
@@ -532,6 +541,67 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_clean_scatter(const float4* __re
             stStream(opos + dst, a); stStream(ocol + dst, b); stStream(onrm + dst, c);
         }
         __syncthreads();
+    }
+}
+
+// pass 3, in place: Model::clean's ordered copy moves a survivor DOWN by the number of removals before it, so everything in front of
+// the first removal already sits where it belongs: only the tail behind it is touched (the ping-pong copy above rewrites the whole
+// store, 96 B per surfel, although removals concern the young surfels at its end).  Sub-blocks of 512 entries are handed out in
+// ascending order by a ticket, starting at the first one that holds a removal.  A sub-block (1) loads its survivors into registers,
+// (2) publishes `loaded[blk] = epoch` (release), (3) waits until the (at most two, lower) sub-blocks whose SOURCE range its
+// destination range overlaps have published theirs, (4) stores.  Waits only ever point to lower tickets, whose owners are running
+// and publish before they wait: no deadlock whatever the residency.  Same output order as the ping-pong copy, bit for bit.
+__global__ void __launch_bounds__(SCAN_BLOCK) k_clean_compact(float4* __restrict__ pos, float4* __restrict__ col, float4* __restrict__ nrm,
+                                                              const uint32_t* __restrict__ countPtr, const float4* __restrict__ m0,
+                                                              const float4* __restrict__ m1, const float4* __restrict__ m2, int Ppix,
+                                                              const uint8_t* __restrict__ keep, const uint32_t* __restrict__ blockOffs,
+                                                              uint32_t capacity, uint32_t* __restrict__ ticket, uint32_t* __restrict__ loaded,
+                                                              const uint32_t* __restrict__ firstMoved, uint32_t epoch)
+{
+    const uint32_t count = *countPtr;
+    const uint32_t total = count + (uint32_t)Ppix;
+    const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const uint32_t first = *firstMoved;
+    __shared__ uint32_t wsum[SCAN_BLOCK / 32];
+    __shared__ uint32_t sBlk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        if (threadIdx.x == 0) sBlk = first + atomicAdd(ticket, 1u);
+        __syncthreads();
+        const uint32_t blk = sBlk;
+        if (blk >= nblk) break;                                      // block uniform
+        const uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
+        const bool k = e < total && keep[e];
+        const unsigned bal = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t woff = 0, nb = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_BLOCK / 32; ++w) { const uint32_t c = wsum[w]; if (w < warp) woff += c; nb += c; }
+        const uint32_t off = blockOffs[blk];
+        const uint32_t dst = off + woff + __popc(bal & ((1u << lane) - 1));
+        const bool isOld = e < count;
+        const bool move = k && dst < capacity && !(isOld && dst == e);
+        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+        if (move) {
+            if (isOld) { a = __ldcg(pos + e); b = __ldcg(col + e); c = __ldcg(nrm + e); }      // coherent loads: the planes are written by this very kernel
+            else { const uint32_t p = e - count; a = m0[p]; b = m1[p]; c = m2[p]; }
+        }
+        __threadfence();                                             // this thread's loads are performed before the flag below can be observed
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(loaded + blk), "r"(epoch) : "memory");
+            if (nb) {
+                const uint32_t s0 = off / SCAN_BLOCK, s1 = (off + nb - 1) / SCAN_BLOCK;
+                for (uint32_t s = s0; s <= s1 && s < blk; ++s) {
+                    if (s < first) continue;                         // cannot happen (off >= first * 512); kept as a guard
+                    unsigned v;
+                    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(loaded + s) : "memory"); } while (v != epoch);
+                }
+            }
+        }
+        __syncthreads();
+        if (move) { stStream(pos + dst, a); stStream(col + dst, b); stStream(nrm + dst, c); }
     }
 }
 
@@ -950,7 +1020,7 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
                   const uint8_t* aflag, float4* const* meas, const DevPose* tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const float4* cleanTex,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s,
-                  const IndexFused* fused)
+                  const IndexFused* fused, const CleanInPlace* inplace)
 {
     CleanParams P;
     P.tinv = Rt{};                          // filled from the device-resident pose inside the kernels
@@ -966,10 +1036,15 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
     }
     prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, cleanTex, depthFilt,
                                                                                mask, keep, cand, candCount);
-    prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<blocks, SCAN_BLOCK, 0, s>>>(keep, count, Ppix, blockSums, candCount);
-    prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount);
-    prof_mark(s, "k_clean_scatter"); k_clean_scatter<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
-                                                  dst.pos, dst.col, dst.nrm);
+    prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<persistentBlocks(8), 256, 0, s>>>(keep, count, Ppix, blockSums, candCount, inplace ? inplace->ticket : nullptr);
+    prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount, inplace ? inplace->firstMoved : nullptr);
+    if (inplace) {
+        prof_mark(s, "k_clean_compact"); k_clean_compact<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
+                                                      inplace->ticket, inplace->loaded, inplace->firstMoved, inplace->epoch);
+    } else {
+        prof_mark(s, "k_clean_scatter"); k_clean_scatter<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
+                                                      dst.pos, dst.col, dst.nrm);
+    }
 }
 
 void launch_ray_table(Cam cam, int W, int H, float4* tab, cudaStream_t s)

@@ -1163,7 +1163,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                         if (sigmaSh == -1) w = 1;
                         float row[7];
                         row[6] = -w * diff;
-                        float invz = (float)(1.0 / (double)cp.z);
+                        const float invz = cp.w;                           // (float)(1.0 / (double)cp.z), precomputed by k_project_points3
                         float dIdx_v = w * tp.sobelScale * (float)g.x;      // grad[one]: `one` is this pixel (reduce.cu:934)
                         float dIdy_v = w * tp.sobelScale * (float)g.y;
                         float v0 = dIdx_v * cam.fx * invz;
