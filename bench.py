@@ -467,6 +467,52 @@ def run_ours(args, rank, world):
     if isinstance(out.get("eight_objects"), dict):
         out["eight_objects"].pop("_poselogs", None)
 
+    def configs4():
+        # BASELINE configs[4] on ONE GPU: 1280x720, 16 objects (table scene, three rows), capacities 50M global / 1M per object as the
+        # reference rounds them (Model.cpp:101-106: 7040^2 and 960^2), the background store pre-populated to ~30M live surfels
+        from maskfusion_b200.synth import render_sequence, SynthScene, dense_room_surfels
+        W4, H4, n4, t0 = 1280, 720, 36, 24
+        kw = dict(width=W4, height=H4, n_objects=16, seed=0, layout="table")
+        fr = render_sequence(range(n4), **kw)
+        sc = SynthScene(W4, H4, n_objects=16, seed=0, layout="table")
+        cls = np.array([0] + [o.class_id for o in sc.objects], np.int32)
+        cfg = mfb.default_config(W4, H4, capacityGlobal=7040 * 7040, capacityObject=960 * 960, enableMultipleModels=1, icpWeight=20.0, so3=1, trackAllModels=1,
+                                 modelSpawnOffset=1, fx=792.0, fy=792.0, cx=640.0, cy=360.0)
+        mf = mfb.MaskFusion(cfg, device=local, stream=stream.cuda_stream)
+        dev = [(torch.from_numpy(f[0]).cuda(), torch.from_numpy(f[1]).cuda(), torch.from_numpy(np.ascontiguousarray(f[2])).cuda()) for f in fr]
+        mf.setFrameClasses(cls)
+
+        def run(lo, hi):
+            for t in range(lo, hi):
+                mf.processFramePtr(dev[t][0].data_ptr(), dev[t][1].data_ptr(), t * 33333, True, mask_ptr=dev[t][2].data_ptr())
+        run(0, 1)
+        gm = mf.getBackgroundModel()
+        cur = gm.downloadMap()
+        room = dense_room_surfels(sc, 30_000_000, time=1, conf=20.0)
+        Tinv = np.linalg.inv(sc.camera_pose(0))
+        room[:, 0:3] = (room[:, 0:3].astype(np.float64) @ Tinv[:3, :3].T + Tinv[:3, 3]).astype(np.float32)
+        room[:, 8:11] = (room[:, 8:11].astype(np.float64) @ Tinv[:3, :3].T).astype(np.float32)
+        gm.uploadMap(np.concatenate([cur, room], 0))
+        del room
+        run(1, t0)
+        mf.sync(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(t0, n4)
+        e1.record(stream)
+        mf.sync(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        models = mf.getModels()
+        r = {"value": round((n4 - t0) / (ms / 1e3), 2), "unit": "frames/s", "ms_per_step": round(ms / (n4 - t0), 3), "frames": n4 - t0, "models": len(models),
+             "surfels": [m.lastCount() for m in models], "surfel_capacity": [7040 * 7040, 960 * 960],
+             "hbm_store_bytes": int(48 * (7040 * 7040 + (len(models) - 1) * 960 * 960)),
+             "workload": "configs[4] on ONE GPU: 1280x720, 16 objects (table scene) + background, 50M global / 1M per-object capacities, background pre-populated "
+                         "to ~30M live surfels, masks as inputs; inputs resident in HBM"}
+        mf.close()
+        return r
+    if os.environ.get("MFB200_BENCH_CONFIGS4", "1") != "0":
+        leg("configs4_720p_16_objects", configs4)
+
     def three():
         fr3, cls3 = multi_frames(3, 60)
         r = single_process_multi(torch, mfb, stream, local, fr3, cls3, timed_from=20)

@@ -228,6 +228,11 @@ int mf_generate_id_image(const uint8_t* masks, int H, int W, int N, const float*
  * out == NULL: only the size.  Used by both loaders; exported for the decoder's own parity test. */
 int mf_decode_jpeg(const uint8_t* data, int size, uint8_t* out, int capacity, int* width, int* height);
 
+/* OpenEXR scan-line file (HALF / FLOAT channels, compression NONE / RLE / ZIPS / ZIP) -> the float depth image the -dir reader delivers:
+ * what the reference keeps of cv::imread(path, IMREAD_UNCHANGED), GUI/Tools/ImageLogReader.cpp:251-258 (CV_32FC1 as is, element 0 = the
+ * B channel of a CV_32FC3 result).  capacity in floats; out == NULL: only the size.  Exported for the decoder's own parity test. */
+int mf_decode_exr_depth(const uint8_t* data, int size, float* out, int capacity, int* width, int* height);
+
 /* ---- .klg log reader / writer (GUI/Tools/KlgLogReader.cpp:29-113) ---- */
 typedef struct mf_klg mf_klg;
 mf_klg* mf_klg_open(const char* path, int width, int height, int flip_colors);

@@ -50,7 +50,7 @@ EXPORTS = [
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
     "mf_download_edge_map", "mf_morph_close", "mf_debug_track_timing", "mf_attach_backbone", "mf_backbone_stream", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write", "mf_dir_open", "mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks", "mf_dir_set_max_masks", "mf_dir_size",
-    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_export_poses", "mf_generate_id_image", "mf_write_ply", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
+    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_decode_exr_depth", "mf_export_poses", "mf_generate_id_image", "mf_write_ply", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
     "mf_shard_configure", "mf_shard_unique_id", "mf_shard_comm_init", "mf_shard_process_frame", "mf_shard_stats", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
@@ -483,6 +483,19 @@ def generate_id_image(result: dict, min_score: float, class_filter=(), special_a
     if n < 0:
         raise MFError(L.mf_last_error().decode())
     return img, ec[:n].tolist(), er[:n].tolist()
+
+
+def decode_exr_depth(buf: bytes) -> np.ndarray:
+    """OpenEXR scan-line file -> HxW float32 depth as the -dir reader delivers it (csrc/mf_loader.cu: decodeEXRDepth)"""
+    L = load_library()
+    w, h = C.c_int(0), C.c_int(0)
+    a = np.frombuffer(buf, np.uint8)
+    if L.mf_decode_exr_depth(_p(a), int(a.shape[0]), None, 0, C.byref(w), C.byref(h)) != 0:
+        raise MFError(L.mf_last_error().decode())
+    out = np.zeros((h.value, w.value), np.float32)
+    if L.mf_decode_exr_depth(_p(a), int(a.shape[0]), _p(out), out.size, C.byref(w), C.byref(h)) != 0:
+        raise MFError(L.mf_last_error().decode())
+    return out
 
 
 def decode_jpeg(buf: bytes) -> np.ndarray:

@@ -129,7 +129,7 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     cudaCheck(cudaMallocHost((void**)&hCount, 2 * sizeof(uint32_t)), "cudaMallocHost"); hCount[0] = hCount[1] = 0;
     cudaCheck(cudaMallocHost((void**)&hTrackOut, 40 * sizeof(float)), "cudaMallocHost");
     key.alloc(P); launch_fill_u64(key, KEY_EMPTY, P, s);
-    idx.alloc(P); vertConf.alloc(P); colorTime.alloc(P); normRad.alloc(P); cleanTex.alloc((size_t)P * 2); cleanTex.zero(s);
+    idx.alloc(P); vertConf.alloc(P); colorTime.alloc(P); normRad.alloc(P); cleanTex.alloc((size_t)P); cleanTex.zero(s);
     idx.zero(s); vertConf.zero(s); colorTime.zero(s); normRad.zero(s);
     splatImage.alloc(P); splatVertex.alloc(P); splatNormal.alloc(P); splatTime.alloc(P);
     splatImage.zero(s); splatVertex.zero(s); splatNormal.zero(s); splatTime.zero(s);
@@ -239,7 +239,8 @@ void Model::predictIndices(int time, float depthCutoff, int timeDelta, bool forC
     }
     idxDeferred = false;
     launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, time, timeDelta, key, idx, vertConf,
-                           colorTime, normRad, forClean ? cleanTex.p : nullptr, o->stream);
+                           colorTime, normRad, forClean ? cleanTex.p : nullptr, confidenceThreshold, o->stream);
+    if (forClean) { cleanTexTime = time; cleanTexConf = confidenceThreshold; }
     o->launches += 2;
 }
 
@@ -248,7 +249,8 @@ void Model::flushIndex()
     if (!idxDeferred) return;
     idxDeferred = false;
     MaskFusion* o = owner;
-    launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, idxDepth, idxTime, idxDelta, key, idx, vertConf, colorTime, normRad, cleanTex.p, o->stream);
+    launch_predict_indices(current(), dCount(), dpose, o->cam, o->W, o->H, idxDepth, idxTime, idxDelta, key, idx, vertConf, colorTime, normRad, cleanTex.p, confidenceThreshold, o->stream);
+    cleanTexTime = idxTime; cleanTexConf = confidenceThreshold;
     o->launches += 2;
 }
 
@@ -275,10 +277,14 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
     if (!fused) flushIndex();
     IndexFused f{key.p, idx.p, vertConf.p, colorTime.p, normRad.p, cleanTex.p, idxDepth};
     idxDeferred = false;
+    // the packed window texels carry two tests evaluated with a time and a confidence threshold: valid for this call when the index
+    // map is resolved inside it, or was resolved with the same two values (the frame schedule); else the window reads the images
+    const bool packedOK = fused || (cleanTexTime == time && cleanTexConf == confidenceThreshold);
+    CleanWindowImages win{packedOK ? cleanTex.p : nullptr, vertConf.p, colorTime.p, idx.p};
     if (++cleanEpoch == 0) ++cleanEpoch;                              // 0 = "never published"
     CleanInPlace ip{cleanTicket.p, cleanLoaded.p, cleanTicket.p + 1, cleanEpoch};
     launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, dpose, o->cam, o->W, o->H,
-                 time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, cleanTex, o->depthFilt, o->mask, keep, blockSums,
+                 time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, win, o->depthFilt, o->mask, keep, blockSums,
                  cand, candCount, o->stream, fused ? &f : nullptr, inPlace ? &ip : nullptr);
     target = other; countSel = otherCount;
     o->launches += fused ? 6 : 5;

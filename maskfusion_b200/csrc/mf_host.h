@@ -124,6 +124,7 @@ public:
     // predictIndices(forClean) is lazy: when Model::clean follows with the same time gate (the frame schedule, MaskFusion.cpp:550-562) the
     // projection rides inside the clean pass; any reader of the index map in between (fuse, the read-backs) runs it stand-alone first
     bool idxDeferred = false; int idxTime = 0, idxDelta = 0; float idxDepth = 0.f;
+    int cleanTexTime = -1; float cleanTexConf = -1.f;    // the time / confidence threshold the packed window texels (cleanTex) were written with
     void flushIndex();
 };
 

@@ -12,7 +12,7 @@ struct SurfelPlanes { float4* pos; float4* col; float4* nrm; };
 // photometric correspondence record (reference: DataTerm, Core/Cuda/types.cuh:75-81)
 struct DataTerm { short2 zero; short2 one; float diff; int valid; };
 
-#define TRACK_MAX_JOBS 16
+#define TRACK_MAX_JOBS 32        // tracked models of one batched launch (configs[4]: 16 objects + background)
 #define TRACK_MAX_BLOCKS 1024
 struct TrackPoses { float p[TRACK_MAX_JOBS][16]; };
 
@@ -164,7 +164,7 @@ void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s);
 void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s);
 void launch_set_pose(DevPose* d, const float* pose16, const float* lastPose16, cudaStream_t s);      // host-driven pose -> DevPose
 void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, int time,
-                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, float4* cleanTex,
+                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, float4* cleanTex, float cleanConf,
                             cudaStream_t s);
 void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
                       const float4* vertConf, const float4* normRad, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, int time,
@@ -172,13 +172,16 @@ void launch_associate(const uchar4* rgb, const float* depthRaw, const float* dep
 void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const* meas, uint32_t* slot, int P, int time,
                         const SurfelPlanes& sp, cudaStream_t s);
 // index-map outputs of a Model::predictIndices that is carried out INSIDE the clean pass (one stream over the store instead of two)
+// what the index-map window of Model::clean reads: the packed 16-byte texels (written by the index resolve for THIS call's time and
+// confidence threshold) or, packed == nullptr, the index-map images themselves
+struct CleanWindowImages { const float4* packed; const float4* vertConf; const float4* colorTime; const uint32_t* idx; };
 struct IndexFused { uint64_t* key; uint32_t* idx; float4* vertConf; float4* colorTime; float4* normRad; float4* cleanTex; float maxDepth; };
 // in-place ordered compaction of Model::clean (k_clean_compact): ticket (reset by the sums pass), one published-epoch word per 512-entry
 // sub-block, the first sub-block that holds a removal (written by the scan), the epoch of this call (never 0, changes with every call)
 struct CleanInPlace { uint32_t* ticket; uint32_t* loaded; uint32_t* firstMoved; uint32_t epoch; };
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* dpose, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
-                  float outlierCoeff, uint8_t maskID, const float4* cleanTex,
+                  float outlierCoeff, uint8_t maskID, const CleanWindowImages& win,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s,
                   const IndexFused* fused = nullptr, const CleanInPlace* inplace = nullptr);
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth,

@@ -3,10 +3,10 @@
 // File discovery (prefix + one extension per stream, start index 0 or 1, zero-padded index of width indexW), the default
 // "Color"/"Depth"/"Mask" prefixes when directories overlap, the mask description file (class ids + boxes), the depth
 // conversions and the timestamps (index * 1000 / 24 Hz, :283) follow the reference.  The reference decodes with OpenCV
-// (cv::imread); OpenCV, libpng and libjpeg do not exist in this build, so PNG (zlib is here), binary PNM and baseline JPEG are
-// decoded in-tree and the rest is refused with a message:
+// (cv::imread); OpenCV, libpng, libjpeg and OpenEXR do not exist in this build, so PNG (zlib is here), binary PNM, baseline JPEG and
+// scan-line OpenEXR are decoded in-tree and the rest is refused with a message:
 //   colour  .png .ppm .jpg (-> 8-bit RGB in file order: cv::imread gives BGR and the reader swaps unconditionally, :247-248; JPEG: mf_jpeg.cu)
-//   depth   .png 16-bit gray (-> 0.001f * v, :262-268)                                                                     .exr: no
+//   depth   .png 16-bit gray (-> 0.001f * v, :262-268); .exr scan-line HALF/FLOAT, NONE/RLE/ZIPS/ZIP (-> the gray channel, or B of R,G,B: :253-258)
 //   mask    .png / .pgm 8-bit gray (cv::IMREAD_GRAYSCALE of a gray file is the identity)
 // Unlike KlgLogReader, hasMore() lets the LAST frame through (currentFrame starts at -1, :145,:326).
 // The reference's background buffering thread (:203-220) is an I/O detail and is not reproduced: frames are decoded on demand.
@@ -146,6 +146,135 @@ bool decodePNM(const std::vector<uint8_t>& f, Image& im, std::string& err)
     return true;
 }
 
+// OpenEXR scan-line images (depth of the synthetic datasets; the reference reads them with cv::imread(IMREAD_UNCHANGED), ImageLogReader.cpp:251).
+// In-tree decoder of the subset a depth image uses: single-part scan-line files, compression NONE / RLE / ZIPS / ZIP, HALF or FLOAT
+// channels, no sub-sampling.  The depth is what the reference takes from OpenCV's result (:253-258): the only channel of a gray file
+// (CV_32FC1) or element [0] of a CV_32FC3 pixel, which in OpenCV's BGR order is the file's B channel.  Tiled, multi-part, deep and
+// PIZ / PXR24 / B44 / DWA files are refused with a message naming the feature.
+float halfToFloat(uint16_t h)
+{
+    const uint32_t sign = (uint32_t)(h >> 15) << 31, exp = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else { int e = -1; uint32_t m = man; do { ++e; m <<= 1; } while (!(m & 0x400u)); bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 0x3ffu) << 13); }
+    } else if (exp == 31) bits = sign | 0x7f800000u | (man << 13);
+    else bits = sign | ((exp + 112u) << 23) | (man << 13);
+    float f; memcpy(&f, &bits, 4); return f;
+}
+
+bool decodeEXRDepth(const std::vector<uint8_t>& f, int& W, int& H, std::vector<float>& depth, std::string& err)
+{
+    size_t pos = 0;
+    auto need = [&](size_t n) { return pos + n <= f.size(); };
+    auto rd32 = [&](size_t at) { uint32_t v; memcpy(&v, &f[at], 4); return v; };
+    if (f.size() < 8 || rd32(0) != 20000630u) { err = "not an OpenEXR file"; return false; }
+    const uint32_t ver = rd32(4);
+    if ((ver & 0xffu) != 2) { err = "EXR: unsupported file version"; return false; }
+    if (ver & 0x200u) { err = "EXR: tiled files are not supported"; return false; }
+    if (ver & 0x1800u) { err = "EXR: deep / multi-part files are not supported"; return false; }
+    pos = 8;
+    struct Chan { std::string name; int type; int xs, ys; };
+    std::vector<Chan> chans;
+    int compression = -1, lineOrder = 0; int dw[4] = {0, 0, -1, -1}; bool haveDW = false;
+    for (;;) {
+        size_t e = pos; while (e < f.size() && f[e]) ++e;
+        if (e >= f.size()) { err = "EXR: truncated header"; return false; }
+        if (e == pos) { ++pos; break; }                                   // empty name: end of header
+        std::string name((const char*)&f[pos], e - pos); pos = e + 1;
+        e = pos; while (e < f.size() && f[e]) ++e;
+        if (e >= f.size()) { err = "EXR: truncated header"; return false; }
+        std::string type((const char*)&f[pos], e - pos); pos = e + 1;
+        if (!need(4)) { err = "EXR: truncated header"; return false; }
+        const uint32_t sz = rd32(pos); pos += 4;
+        if (sz > f.size() || !need(sz)) { err = "EXR: truncated attribute"; return false; }
+        if (name == "channels" && type == "chlist") {
+            size_t q = pos; const size_t end = pos + sz;
+            while (q < end && f[q]) {
+                size_t z = q; while (z < end && f[z]) ++z;
+                if (z + 17 > end) { err = "EXR: bad channel list"; return false; }
+                Chan c; c.name.assign((const char*)&f[q], z - q); c.type = (int)rd32(z + 1); c.xs = (int)rd32(z + 9); c.ys = (int)rd32(z + 13);
+                chans.push_back(c); q = z + 17;
+            }
+        } else if (name == "compression" && sz >= 1) compression = f[pos];
+        else if (name == "dataWindow" && sz >= 16) { for (int k = 0; k < 4; ++k) dw[k] = (int)rd32(pos + 4 * k); haveDW = true; }
+        else if (name == "lineOrder" && sz >= 1) lineOrder = f[pos];
+        pos += sz;
+    }
+    (void)lineOrder;                                                      // chunks carry their y coordinate: any order decodes
+    if (chans.empty() || !haveDW || compression < 0) { err = "EXR: header lacks channels / dataWindow / compression"; return false; }
+    const long long w = (long long)dw[2] - dw[0] + 1, h = (long long)dw[3] - dw[1] + 1;
+    if (w <= 0 || h <= 0 || w > MF_MAX_IMAGE_SIDE || h > MF_MAX_IMAGE_SIDE) { err = "EXR: empty data window or image side above 16384"; return false; }
+    if (compression > 3) {
+        const char* nm[] = {"NONE", "RLE", "ZIPS", "ZIP", "PIZ", "PXR24", "B44", "B44A", "DWAA", "DWAB"};
+        err = std::string("EXR: compression ") + (compression < 10 ? nm[compression] : "?") + " is not supported (NONE, RLE, ZIPS, ZIP are)"; return false;
+    }
+    // which channel is the depth: "B" of an R,G,B file (OpenCV returns BGR; the reference reads element 0), else "Y", else the only channel
+    int pick = -1; bool hasR = false, hasG = false, hasB = false;
+    for (size_t i = 0; i < chans.size(); ++i) { hasR |= chans[i].name == "R"; hasG |= chans[i].name == "G"; hasB |= chans[i].name == "B"; }
+    for (size_t i = 0; i < chans.size(); ++i) {
+        if (hasR && hasG && hasB) { if (chans[i].name == "B") pick = (int)i; }
+        else if (chans[i].name == "Y") pick = (int)i;
+    }
+    if (pick < 0 && chans.size() == 1) pick = 0;
+    if (pick < 0) { err = "EXR: no R,G,B / Y / single channel to take the depth from"; return false; }
+    size_t lineBytes = 0, pickOff = 0;
+    for (size_t i = 0; i < chans.size(); ++i) {
+        if (chans[i].xs != 1 || chans[i].ys != 1) { err = "EXR: sub-sampled channels are not supported"; return false; }
+        if (chans[i].type < 0 || chans[i].type > 2) { err = "EXR: bad pixel type"; return false; }
+        if ((int)i == pick) pickOff = lineBytes;
+        lineBytes += (size_t)w * (chans[i].type == 1 ? 2 : 4);
+    }
+    if (chans[pick].type == 0) { err = "Unsupported depth-files: 32SC1"; return false; }      // UINT channel: the reference rejects the type (:269-271)
+    const int linesPerBlock = compression == 3 ? 16 : 1;
+    const size_t nChunks = ((size_t)h + linesPerBlock - 1) / linesPerBlock;
+    if (!need(nChunks * 8)) { err = "EXR: truncated offset table"; return false; }
+    W = (int)w; H = (int)h;
+    depth.assign((size_t)W * H, 0.f);
+    std::vector<uint8_t> raw, tmp;
+    for (size_t c = 0; c < nChunks; ++c) {
+        uint64_t off; memcpy(&off, &f[pos + c * 8], 8);
+        if (off > f.size() || off + 8 > f.size()) { err = "EXR: chunk offset beyond the file"; return false; }
+        const int y = (int)rd32((size_t)off); const uint32_t csz = rd32((size_t)off + 4);
+        const size_t data = (size_t)off + 8;
+        if (csz > f.size() || data + csz > f.size()) { err = "EXR: truncated chunk"; return false; }
+        const long long y0 = (long long)y - dw[1];
+        if (y0 < 0 || y0 >= h) { err = "EXR: chunk outside the data window"; return false; }
+        const int nl = (int)std::min<long long>(linesPerBlock, h - y0);
+        const size_t rawLen = lineBytes * (size_t)nl;
+        raw.resize(rawLen);
+        if (compression == 0 || csz == rawLen) {                           // stored uncompressed (also the escape of the compressors)
+            if (csz != rawLen) { err = "EXR: chunk size does not match the scan-line size"; return false; }
+            memcpy(raw.data(), &f[data], rawLen);
+        } else {
+            tmp.resize(rawLen);
+            if (compression == 1) {                                        // RLE (ImfRle.cpp): n < 0: -n literal bytes; n >= 0: next byte n + 1 times
+                size_t ip = data, op = 0; const size_t iend = data + csz;
+                while (ip < iend) {
+                    const int n = (int8_t)f[ip++];
+                    if (n < 0) { const size_t cnt = (size_t)(-n); if (ip + cnt > iend || op + cnt > rawLen) { err = "EXR: bad RLE stream"; return false; } memcpy(&tmp[op], &f[ip], cnt); ip += cnt; op += cnt; }
+                    else { const size_t cnt = (size_t)n + 1; if (ip >= iend || op + cnt > rawLen) { err = "EXR: bad RLE stream"; return false; } memset(&tmp[op], f[ip++], cnt); op += cnt; }
+                }
+                if (op != rawLen) { err = "EXR: RLE stream does not decode to the scan-line size"; return false; }
+            } else {
+                unsigned long outLen = (unsigned long)rawLen;
+                if (uncompress(tmp.data(), &outLen, &f[data], csz) != Z_OK || outLen != rawLen) { err = "EXR: zlib stream does not decode to the scan-line size"; return false; }
+            }
+            // undo the byte predictor, then the even/odd byte split (ImfZip.cpp / ImfRleCompressor.cpp)
+            for (size_t i = 1; i < rawLen; ++i) tmp[i] = (uint8_t)(tmp[i - 1] + tmp[i] - 128);
+            const size_t half = (rawLen + 1) / 2;
+            for (size_t i = 0; i < rawLen; ++i) raw[i] = (i & 1) ? tmp[half + i / 2] : tmp[i / 2];
+        }
+        for (int l = 0; l < nl; ++l) {
+            const uint8_t* src = raw.data() + (size_t)l * lineBytes + pickOff;
+            float* dst = &depth[(size_t)(y0 + l) * W];
+            if (chans[pick].type == 2) memcpy(dst, src, (size_t)W * 4);
+            else for (int x = 0; x < W; ++x) { uint16_t hv; memcpy(&hv, src + 2 * x, 2); dst[x] = halfToFloat(hv); }
+        }
+    }
+    return true;
+}
+
 bool loadImage(const std::string& path, const std::string& ext, Image& im, std::string& err)
 {
     std::vector<uint8_t> f;
@@ -158,7 +287,7 @@ bool loadImage(const std::string& path, const std::string& ext, Image& im, std::
         im.channels = 3; im.bits = 8; im.data.swap(rgb);
         return true;
     }
-    err = "decoding " + ext + " files needs OpenEXR, which this build does not have (supported: .png, .jpg, .ppm, .pgm)";
+    err = "no decoder for " + ext + " files (supported: .png, .jpg, .ppm, .pgm; .exr depth through decodeEXRDepth)";
     return false;
 }
 
@@ -251,6 +380,24 @@ extern "C" int mf_dir_has_masks(mf_dir* r) { return r && r->hasMasks ? 1 : 0; }
 extern "C" int mf_dir_set_max_masks(mf_dir* r, int n) { if (!r) return -1; r->maxMasks = n < 0 ? 0 : (size_t)n; return 0; }   // "-nm", MainController.cpp:168-173
 extern "C" int mf_dir_size(mf_dir* r, int* w, int* h) { if (!r) return -1; if (w) *w = r->W; if (h) *h = r->H; return 0; }
 
+// test hook behind the C ABI: an OpenEXR byte stream -> the float depth image the reader delivers (out == NULL: only the size)
+extern "C" int mf_decode_exr_depth(const uint8_t* data, int size, float* out, int capacity, int* width, int* height)
+{
+    if (!data || size <= 0) { mf_set_error("decode_exr_depth: empty input"); return -1; }
+    try {
+        std::vector<uint8_t> f(data, data + size); std::vector<float> d; int W = 0, H = 0; std::string err;
+        if (!decodeEXRDepth(f, W, H, d, err)) { mf_set_error(err); return -2; }
+        if (width) *width = W;
+        if (height) *height = H;
+        if (out) {
+            if ((size_t)capacity < d.size()) { mf_set_error("decode_exr_depth: output buffer too small"); return -3; }
+            memcpy(out, d.data(), d.size() * sizeof(float));
+        }
+        return 0;
+    } catch (const std::exception& e) { mf_set_error(std::string("decode_exr_depth: ") + e.what()); return -4; }
+    catch (...) { mf_set_error("decode_exr_depth: unknown error"); return -4; }
+}
+
 // ImageLogReader::getNext + loadFrameFromDrive (:222-288).  mask / class_ids / boxes may be NULL.  *n_class_ids: in = capacity of
 // class_ids (and of boxes / 4), out = number of ids read (0 when the frame has no description file).  Returns 1 when a mask was
 // delivered, 0 when not, < 0 on error.
@@ -307,10 +454,19 @@ extern "C" int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* m
             rgb[i * 3 + c] = v;
         }
     // depth: cv::imread(path, IMREAD_UNCHANGED); only CV_16UC1 is decodable here (:262-268)
+    if (r->depthExt == ".exr") {
+        // cv::imread(IMREAD_UNCHANGED) of an EXR file: CV_32FC1, or CV_32FC3 of which the reference keeps element 0 (:253-258)
+        std::vector<uint8_t> fb; std::vector<float> dz; int dwid = 0, dhei = 0;
+        if (!readFile(depthPath, fb)) { mf_set_error("Could not read depth-image file. (cannot read " + depthPath + ")"); return -7; }
+        if (!decodeEXRDepth(fb, dwid, dhei, dz, err)) { mf_set_error("Could not read depth-image file. (" + err + ")"); return -7; }
+        if (dwid != r->W || dhei != r->H) { mf_set_error("depth-image size differs from the colour image"); return -7; }
+        memcpy(depth, dz.data(), P * sizeof(float));
+    } else {
     if (!loadImage(depthPath, r->depthExt, im, err)) { mf_set_error("Could not read depth-image file. (" + err + ")"); return -7; }
     if (im.w != r->W || im.h != r->H) { mf_set_error("depth-image size differs from the colour image"); return -7; }
     if (!(im.bits == 16 && im.channels == 1)) { mf_set_error(std::string("Unsupported depth-files: ") + (im.bits == 16 ? "16U" : "8U") + "C" + std::to_string(im.channels)); return -7; }
     for (size_t i = 0; i < P; ++i) { uint16_t t; memcpy(&t, &im.data[i * 2], 2); depth[i] = 0.001f * (float)t; }
+    }
     int gotMask = 0;
     if (r->hasMasks && index < r->maxMasks && mask) {
         if (!loadImage(maskPath, r->maskExt, im, err) || (size_t)im.w * im.h != P) { mf_set_error("Could not read mask-image file."); return -8; }

@@ -52,10 +52,15 @@ __global__ void __launch_bounds__(256) k_index_project(const float4* __restrict_
 __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
                                 const DevPose* __restrict__ dpose, int P, unsigned long long* __restrict__ key, uint32_t* __restrict__ idx,
                                 float4* __restrict__ vertConf, float4* __restrict__ colorTime, float4* __restrict__ normRad,
-                                float4* __restrict__ cleanTex)
+                                float4* __restrict__ cleanTex, float cleanConf, float cleanTime)
 {
-    // cleanTex: what the clean pass reads per window texel, packed into ONE 32-byte sector
-    //   [2i] = vertConf, [2i+1] = (initTime, lastTime, idx != 0, -)   (three separate images cost three sectors per tap)
+    // cleanTex: what the window of the clean pass (copy_unstable.vert:86-113) reads per texel, packed into ONE 16-byte word:
+    //   (x, y, z | sign bit: conf > confThreshold,  initTime | sign bit: lastTime == time);  all zero = empty texel (or surfel 0, N2).
+    // z > 0 for every drawn surfel and initTime >= 0, so both sign bits are free; the two tests they carry are the only uses the
+    // window makes of the confidence and of the last-seen time, evaluated here with the thresholds of the clean call that follows
+    // (Model::clean falls back to the three index-map images when it is called with other thresholds).  Three images cost three
+    // sectors per tap, the 32-byte record of round 1 one; 16 bytes let a thread hold its whole 3x3 window in registers and issue the
+    // nine loads together.
     const Rt tinv = dpose->tinv;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P) return;
@@ -64,7 +69,7 @@ __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __
         idx[i] = 0;
         float4 z = make_float4(0, 0, 0, 0);
         vertConf[i] = z; colorTime[i] = z; normRad[i] = z;
-        if (cleanTex) { cleanTex[2 * i] = z; cleanTex[2 * i + 1] = z; }
+        if (cleanTex) cleanTex[i] = z;
         return;
     }
     key[i] = KEY_EMPTY;
@@ -77,8 +82,9 @@ __global__ void k_index_resolve(const float4* __restrict__ pos, const float4* __
     colorTime[i] = c;
     normRad[i] = make_float4(nn.x, nn.y, nn.z, n.w);
     if (cleanTex) {
-        cleanTex[2 * i] = make_float4(ph.x, ph.y, ph.z, p.w);
-        cleanTex[2 * i + 1] = make_float4(c.z, c.w, id != 0u ? 1.f : 0.f, 0.f);
+        const uint32_t zb = (__float_as_uint(ph.z) & 0x7fffffffu) | (p.w > cleanConf ? 0x80000000u : 0u);
+        const uint32_t tb = (__float_as_uint(c.z) & 0x7fffffffu) | (c.w == cleanTime ? 0x80000000u : 0u);
+        cleanTex[i] = id != 0u ? make_float4(ph.x, ph.y, __uint_as_float(zb), __uint_as_float(tb)) : make_float4(0, 0, 0, 0);
     }
 }
 
@@ -239,7 +245,11 @@ struct CleanEntry { float xn, yn, lx, ly, lz, init, rad, lnz; };
 // half-texel steps; the taps land on 2-3 distinct texels per axis and the per-tap tests depend on the texel
 // alone: run the literal float loops for the texel columns/rows, visit each DISTINCT texel once, weight by
 // its multiplicity (same counts as the tap loop, ~4x fewer loads).
-MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const float4* __restrict__ cleanTex, int& count, int& zCount)
+// window texels: the packed 16-byte records (PACKED) or, when the clean call's thresholds differ from the ones the records were
+// written with, the three index-map images themselves
+struct CleanTexels { const float4* packed; const float4* vertConf; const float4* colorTime; const uint32_t* idx; };
+template <bool PACKED>
+MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const CleanTexels& tx, int& count, int& zCount)
 {
     const int W = P.W, H = P.H;
     const float cols = (float)W, rows = (float)H, ftime = (float)P.time;
@@ -288,19 +298,42 @@ MF_D void cleanWindow(const CleanEntry& e, const CleanParams& P, const float4* _
         }
     }
     count = 0; zCount = 0;
+    if (PACKED) {
+        // the whole window at once: nine independent 16-byte loads (slots beyond nux / nuy repeat texel 0 with weight 0), one L2 round trip
+        float4 t[3][3];
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) t[b][k] = __ldg(tx.packed + (uy[b] * W + ux[k]));
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const uint32_t zb = __float_as_uint(t[b][k].z), tb = __float_as_uint(t[b][k].w);
+                if (b >= nuy || k >= nux || (zb & 0x7fffffffu) == 0u) continue;     // empty texel (or surfel 0, N2)
+                const float mz = __uint_as_float(zb & 0x7fffffffu), initT = __uint_as_float(tb & 0x7fffffffu);
+                const bool confOK = (zb >> 31) != 0u, lastNow = (tb >> 31) != 0u;
+                const float ddx = t[b][k].x - e.lx, ddy = t[b][k].y - e.ly;
+                if (initT < e.init && confOK && mz > e.lz && mz - e.lz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < e.rad * 1.4f)
+                    count += wx[k] * wy[b];
+                if (lastNow && confOK && mz > e.lz && mz - e.lz > 0.01f && e.lnz > 0.85f)
+                    zCount += wx[k] * wy[b];
+            }
+        return;
+    }
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
         if (b >= nuy) break;
-        float4 mc[3], tt[3];
+        float4 mc[3], tt[3]; uint32_t oc[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {                        // slots beyond nux repeat column 0 (weight 0): the loads are unconditional
             const int q = uy[b] * W + ux[k];
-            mc[k] = __ldg(cleanTex + 2 * q); tt[k] = __ldg(cleanTex + 2 * q + 1);
+            mc[k] = __ldg(tx.vertConf + q); tt[k] = __ldg(tx.colorTime + q); oc[k] = __ldg(tx.idx + q);
         }
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            if (k >= nux || tt[k].z == 0.f) continue;        // idx == 0: empty texel (or surfel 0, N2)
-            const float initT = tt[k].x, lastT = tt[k].y;
+            if (k >= nux || oc[k] == 0u) continue;           // idx == 0: empty texel (or surfel 0, N2)
+            const float initT = tt[k].z, lastT = tt[k].w;
             const float ddx = mc[k].x - e.lx, ddy = mc[k].y - e.ly;
             if (initT < e.init && mc[k].w > P.confThreshold && mc[k].z > e.lz && mc[k].z - e.lz < 0.01f && sqrtf(ddx * ddx + ddy * ddy) < e.rad * 1.4f)
                 count += wx[k] * wy[b];
@@ -353,22 +386,36 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
     // 0, time gate at equality) is finished by pass 2 as well (flag bit 31): its confidence must not change before the resolve reads it.
     // candidates are staged per block in shared memory and flushed in chunks: one device-wide atomic per ~2k candidates
     // (a warp-aggregated global append put ~130k returning atomics on ONE L2 address: 62 % busy slice, ncu r01b)
-    __shared__ uint32_t sBuf[CAND_BUF];
-    __shared__ uint32_t sCount, sBase;
+    // ... and, round 2, per WARP: a warp owns CAND_BUF / 8 slots, appends with a ballot and flushes on its own (one device-wide atomic
+    // per ~220 candidates, coalesced 128-byte copies): no block barrier in the streaming loop (two per round cost 45 % issue-active at
+    // 26 % of the DRAM peak when every surfel of a dense map is a candidate).  The order of the list is irrelevant to pass 2.
+    __shared__ uint32_t sBuf[8][CAND_BUF / 8];
     P.tinv = dpose->tinv;
     const uint32_t count = *countPtr;
     const uint32_t total = count + (uint32_t)Ppix;
     const float cols = (float)P.W, rows = (float)P.H, ftime = (float)P.time;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) sCount = 0;
-    __syncthreads();
-    uint32_t staged = 0;                                                 // block-uniform copy of sCount
-    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t staged = 0;                                                 // warp-uniform: entries waiting in this warp's slots
+    auto flush = [&]() {
+        uint32_t gbase = 0;
+        if (lane == 0) gbase = atomicAdd(candCount, staged);
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        for (uint32_t i = lane; i < staged; i += 32) cand[gbase + i] = sBuf[warp][i];
+        __syncwarp();
+        staged = 0;
+    };
+    // the next round's two planes stream in behind this round's arithmetic and block-wide staging (two barriers per round exposed the
+    // full DRAM latency of every round otherwise: 45 % issue-active at 26 % of the DRAM peak, ncu r02)
+    const uint32_t stride = gridDim.x * blockDim.x;
+    float4 vpN = make_float4(0, 0, 0, 0), vcN = vpN;
+    { const uint32_t e0 = blockIdx.x * blockDim.x + threadIdx.x; if (e0 < count) { vpN = pos[e0]; vcN = col[e0]; } }
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += stride) {
         const uint32_t e = base + threadIdx.x;
         bool valid = false, need = false, noWindow = false;
         const bool isOld = e < count;
-        float4 vp = make_float4(0, 0, 0, 0), vc = vp;
-        if (isOld) { vp = pos[e]; vc = col[e]; valid = true; }
+        float4 vp = vpN, vc = vcN;
+        if (e + stride < count) { vpN = pos[e + stride]; vcN = col[e + stride]; }
+        if (isOld) valid = true;
         else if (e < total) { uint32_t p = e - count; if (aflag[p] == 2) { vp = m0[p]; vc = m1[p]; valid = true; } }
         if (valid) {
             float3 lp = xform(P.tinv, make_float3(vp.x, vp.y, vp.z));
@@ -393,33 +440,22 @@ __global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, floa
                 keep[e] = k ? 1 : 0;
             }
         } else if (e < total) keep[e] = 0;
-        unsigned nb = __ballot_sync(0xffffffffu, need);
+        const unsigned nb = __ballot_sync(0xffffffffu, need);
         if (nb) {
-            uint32_t wbase = 0;
-            if (lane == 0) wbase = atomicAdd(&sCount, (uint32_t)__popc(nb));
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (need) sBuf[wbase + __popc(nb & ((1u << lane) - 1))] = noWindow ? (e | 0x80000000u) : e;
-        }
-        staged += (uint32_t)__syncthreads_count(need);
-        if (staged > CAND_BUF - 256) {                                   // uniform: the next iteration might not fit
-            if (threadIdx.x == 0) { sBase = atomicAdd(candCount, staged); sCount = 0; }
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < staged; i += blockDim.x) cand[sBase + i] = sBuf[i];
-            staged = 0;
-            __syncthreads();
+            if (staged + 32 > CAND_BUF / 8) flush();                    // warp uniform
+            if (need) sBuf[warp][staged + __popc(nb & ((1u << lane) - 1))] = noWindow ? (e | 0x80000000u) : e;
+            staged += (uint32_t)__popc(nb);
+            __syncwarp();
         }
     }
-    if (staged) {
-        if (threadIdx.x == 0) sBase = atomicAdd(candCount, staged);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < staged; i += blockDim.x) cand[sBase + i] = sBuf[i];
-    }
+    if (staged) flush();
 }
 
 // clean, pass 1b: one thread per candidate: index-map window (copy_unstable.vert:86-113) + the rest of the shader
+template <bool PACKED>
 __global__ void __launch_bounds__(256, 4) k_clean_p2(float4* __restrict__ pos, float4* __restrict__ col, const float4* __restrict__ nrm,
                                                   const uint32_t* __restrict__ countPtr, float4* __restrict__ m0, float4* __restrict__ m1,
-                                                  const float4* __restrict__ m2, CleanParams P, const DevPose* __restrict__ dpose, const float4* __restrict__ cleanTex,
+                                                  const float4* __restrict__ m2, CleanParams P, const DevPose* __restrict__ dpose, CleanTexels cleanTex,
                                                   const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask, uint8_t* __restrict__ keep,
                                                   const uint32_t* __restrict__ cand, const uint32_t* __restrict__ candCount)
 {
@@ -441,7 +477,7 @@ __global__ void __launch_bounds__(256, 4) k_clean_p2(float4* __restrict__ pos, f
         float3 ln = normalize3(rotate(P.tinv, make_float3(vn.x, vn.y, vn.z)));
         CleanEntry ce; ce.xn = x / cols; ce.yn = y / rows; ce.lx = lp.x; ce.ly = lp.y; ce.lz = lp.z; ce.init = vc.z; ce.rad = vn.w; ce.lnz = fabsf(ln.z);
         int c1 = 0, c2 = 0;
-        if (!noWindow) cleanWindow(ce, P, cleanTex, c1, c2);
+        if (!noWindow) cleanWindow<PACKED>(ce, P, cleanTex, c1, c2);
         bool k = cleanFinish(vp, vc, x, y, lp.z, c1, c2, P, depthFilt, mask);
         if (isOld) { if (vp.w != w0) pos[e].w = vp.w; if (vc.w != t0) col[e].w = vc.w; }
         else { m0[p].w = vp.w; m1[p].w = vc.w; }
@@ -992,12 +1028,12 @@ void launch_fill_u32(uint32_t* p, uint32_t v, size_t n, cudaStream_t s) { if (n)
 void launch_fill_u64(uint64_t* p, uint64_t v, size_t n, cudaStream_t s) { if (n) k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((unsigned long long*)p, v, n); }
 
 void launch_predict_indices(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth, int time,
-                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, float4* cleanTex, cudaStream_t s)
+                            int timeDelta, uint64_t* key, uint32_t* idx, float4* vertConf, float4* colorTime, float4* normRad, float4* cleanTex, float cleanConf, cudaStream_t s)
 {
     prof_mark(s, "k_index_project"); k_index_project<<<persistentBlocks(8), 256, 0, s>>>(sp.pos, sp.col, count, tinv, cam, W, H, maxDepth, (float)time, (float)timeDelta,
                                                         (unsigned long long*)key);
     int P = W * H;
-    prof_mark(s, "k_index_resolve"); k_index_resolve<<<(P + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, P, (unsigned long long*)key, idx, vertConf, colorTime, normRad, cleanTex);
+    prof_mark(s, "k_index_resolve"); k_index_resolve<<<(P + 255) / 256, 256, 0, s>>>(sp.pos, sp.col, sp.nrm, tinv, P, (unsigned long long*)key, idx, vertConf, colorTime, normRad, cleanTex, cleanConf, (float)time);
 }
 
 void launch_associate(const uchar4* rgb, const float* depthRaw, const float* depthFilt, const uint8_t* mask, const uint32_t* idx,
@@ -1018,10 +1054,11 @@ void launch_fuse_update(const uint8_t* flag, const uint32_t* best, float4* const
 
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* tinv, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
-                  float outlierCoeff, uint8_t maskID, const float4* cleanTex,
+                  float outlierCoeff, uint8_t maskID, const CleanWindowImages& win,
                   const float* depthFilt, const uint8_t* mask, uint8_t* keep, uint32_t* blockSums, uint32_t* cand, uint32_t* candCount, cudaStream_t s,
                   const IndexFused* fused, const CleanInPlace* inplace)
 {
+    const CleanTexels texels{win.packed, win.vertConf, win.colorTime, win.idx};
     CleanParams P;
     P.tinv = Rt{};                          // filled from the device-resident pose inside the kernels
     P.cam = cam; P.W = W; P.H = H; P.time = time; P.ftimeDelta = (float)timeDelta; P.confThreshold = confThreshold;
@@ -1032,10 +1069,11 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
                                                                                fused ? (unsigned long long*)fused->key : nullptr, fused ? fused->maxDepth : 0.f);
     if (fused) {           // Model::predictIndices, second half: the index map of the store as clean sees it
         prof_mark(s, "k_index_resolve"); k_index_resolve<<<(Ppix + 255) / 256, 256, 0, s>>>(src.pos, src.col, src.nrm, tinv, Ppix, (unsigned long long*)fused->key, fused->idx, fused->vertConf,
-                                                                                          fused->colorTime, fused->normRad, fused->cleanTex);
+                                                                                          fused->colorTime, fused->normRad, fused->cleanTex, confThreshold, (float)time);
     }
-    prof_mark(s, "k_clean_p2"); k_clean_p2<<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, cleanTex, depthFilt,
-                                                                               mask, keep, cand, candCount);
+    prof_mark(s, "k_clean_p2");
+    if (texels.packed) k_clean_p2<true><<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, texels, depthFilt, mask, keep, cand, candCount);
+    else k_clean_p2<false><<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, texels, depthFilt, mask, keep, cand, candCount);
     prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<persistentBlocks(8), 256, 0, s>>>(keep, count, Ppix, blockSums, candCount, inplace ? inplace->ticket : nullptr);
     prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount, inplace ? inplace->firstMoved : nullptr);
     if (inplace) {

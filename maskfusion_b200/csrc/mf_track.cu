@@ -127,15 +127,13 @@ MF_D double shflD(double v, int src)
 // every element sees the same operations in the same order as in the sequential routine, so the solution is BIT-IDENTICAL to it
 // (parity contract: with fp64 sums that round to the oracle's floats, the whole Gauss-Newton trajectory is reproduced bit for bit).
 // All 32 lanes must call; A (N*N, row-major) and b (N) are read from shared memory, x (N) is written there.
+// Register-fed core: lane i < N passes row i of the matrix in a[] and b[i] in bOwn (idle lanes mirror row N - 1).
 template <int N>
-MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restrict__ b, double* x)
+MF_D void ldltSolvePivWarpRegs(double (&a)[N], double bOwn, double* x)
 {
     const int lane = threadIdx.x & 31;
     const bool act = lane < N;
     const int r = act ? lane : N - 1;                      // idle lanes mirror the last row; they only ever supply nothing
-    double a[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) a[j] = A[r * N + j];
     int perm = r;
     int kend = N;
 #pragma unroll
@@ -185,7 +183,7 @@ MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restric
     double dg = a[0];                                      // this lane's pivot d_r
 #pragma unroll
     for (int j = 1; j < N; ++j) if (r == j) dg = a[j];
-    double y = b[perm];
+    double y = shflD(bOwn, perm);                          // b[perm]: the right-hand side of the row this lane now holds
 #pragma unroll
     for (int j = 0; j < N - 1; ++j) {
         const double yj = shflD(y, j);
@@ -213,6 +211,16 @@ MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restric
     }
     if (act) x[perm] = y;
     __syncwarp();
+}
+template <int N>
+MF_D void ldltSolvePivWarp(const double* __restrict__ A, const double* __restrict__ b, double* x)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = lane < N ? lane : N - 1;
+    double a[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) a[j] = A[r * N + j];
+    ldltSolvePivWarpRegs<N>(a, b[r], x);
 }
 
 __device__ void rodrigues(const double* src, double* R)
@@ -587,7 +595,7 @@ MF_D void sumRowsLL(const uint4* __restrict__ rows, unsigned R, unsigned flag, d
 }
 
 struct RedCtx { double* rowsBuf[2]; unsigned* bar; unsigned G, Gact, gen, llBase; };
-template <bool CL, int N>
+template <bool CL, bool LL, int N>
 MF_D void reduceStep(const double* acc, int e0, int e1, bool active, RedCtx& rc, double (*red)[ROWF], double (*ws)[ROWF], double (*rowSh)[ROWF], double* tot)
 {
     if (CL) {
@@ -603,7 +611,7 @@ MF_D void reduceStep(const double* acc, int e0, int e1, bool active, RedCtx& rc,
         }
         __syncthreads();
     } else {
-        if (rc.llBase) {
+        if (LL) {
             // 16 bytes per value: the two ping-pong buffers are 2 * G * ROWF doubles each
             uint4* rows = reinterpret_cast<uint4*>(rc.rowsBuf[0]) + (size_t)(rc.gen & 1) * rc.G * ROWF;
             ++rc.gen;
@@ -671,27 +679,40 @@ MF_D void computeWarpCoop(TrackState* st, Cam c, SolveScratch* sc, int lane)
     __syncwarp();
 }
 
-// host part of one Gauss-Newton iteration (RGBDOdometry.cpp:403-474) on the replicated state, executed by warp 0
+// host part of one Gauss-Newton iteration (RGBDOdometry.cpp:403-474) on the replicated state, executed by warp 0.
+// Latency is all that matters here (every CTA runs the same solve while its other 15 warps wait), so the routine is laid out as four
+// dependent stages instead of eleven: (1) every lane assembles ITS row of lastA / entry of lastb in registers straight from the totals and
+// feeds the warp LDLT; (2) computeUpdateSE3: the scalar part in every lane, one entry of [R|t] per lane; (3) resultRt = Rt * resultRt;
+// (4) everything derived from the new resultRt -- transform, its inverse, the current pose, and the photometric warp constants K R^-1 K^-1
+// and K t -- is evaluated per output entry in registers (the 3x3 inverse redundantly in each lane: 50 fp64 operations cost less than
+// the three shared-memory round trips they replace).  Every expression keeps the operand order of the staged version: same bits.
 __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, bool ICP, bool RGB, float icpWeight, Cam cam, SolveScratch* sc)
 {
     const int lane = threadIdx.x & 31;
     const double wgt = icpWeight;
-    for (int e = lane; e < 42; e += 32) {
-        const bool isA = e < 36;
-        int r = isA ? e / 6 : e - 36, c2 = isA ? e % 6 : 6;
-        int a = r < c2 ? r : c2, b = r < c2 ? c2 : r;
-        int q = 7 * a - (a * (a - 1)) / 2 + (b - a);
-        float vi = (float)tot[q], vr = (float)tot[NACC_ICP + q];
-        double v;
-        if (ICP && RGB) v = isA ? (double)vr + wgt * wgt * (double)vi : (double)vr + wgt * (double)vi;
-        else if (ICP) v = (double)vi;
-        else v = (double)vr;
-        if (isA) { sc->A[e] = v; st->lastA[e] = v; } else { sc->b[r] = v; st->lastb[r] = v; }
+    const int r6 = lane < 6 ? lane : 5;
+    double arow[6], bown;
+    {
+        auto comb = [&](int c2, bool isA) -> double {
+            const int a = r6 < c2 ? r6 : c2, b = r6 < c2 ? c2 : r6;
+            const int q = 7 * a - (a * (a - 1)) / 2 + (b - a);
+            const float vi = (float)tot[q], vr = (float)tot[NACC_ICP + q];
+            if (ICP && RGB) return isA ? (double)vr + wgt * wgt * (double)vi : (double)vr + wgt * (double)vi;
+            if (ICP) return (double)vi;
+            return (double)vr;
+        };
+#pragma unroll
+        for (int j = 0; j < 6; ++j) arow[j] = comb(j, true);
+        bown = comb(6, false);
+        if (lane < 6) {
+#pragma unroll
+            for (int j = 0; j < 6; ++j) st->lastA[lane * 6 + j] = arow[j];
+            st->lastb[lane] = bown;
+        }
     }
     if (ICP && lane == 31) { st->lastICPError = sqrtf((float)tot[27]) / (float)tot[28]; st->lastICPCount = (float)tot[28]; }
-    __syncwarp();
     TT(20);
-    ldltSolvePivWarp<6>(sc->A, sc->b, sc->x);
+    ldltSolvePivWarpRegs<6>(arow, bown, sc->x);
     TT(21);              // bit-identical to the sequential pivoted routine (Eigen's ldlt().solve conventions)
     // computeUpdateSE3 (OdometryProvider.h:69-90): Rt = [rodrigues(x[3..5]) | x[0..2]]; every lane evaluates the (cheap, identical)
     // scalar part, lanes < 16 assemble one entry each
@@ -722,30 +743,56 @@ __device__ __noinline__ void solveAndUpdate(TrackState* st, const double* tot, b
     }
     __syncwarp();
     TT(22);
-    double nrv = 0;
     if (lane < 16) {
-        int r = lane >> 2, c = lane & 3;
+        const int r = lane >> 2, c = lane & 3;
         double s2 = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) s2 += sc->Rt[r * 4 + k] * st->resultRt[k * 4 + c];
-        nrv = s2;
+        sc->nr[lane] = s2;                                 // the new resultRt (st->resultRt is still being read by the other lanes)
     }
     __syncwarp();
-    if (lane < 16) { st->resultRt[lane] = nrv; sc->nr[lane] = nrv; }
-    __syncwarp();
-    if (lane < 9) { float v = (float)sc->nr[(lane / 3) * 4 + lane % 3]; sc->trR[lane] = v; st->trR[lane] = v; }
-    else if (lane < 12) { float v = (float)sc->nr[(lane - 9) * 4 + 3]; sc->trT[lane - 9] = v; st->trT[lane - 9] = v; }
-    __syncwarp();
-    // currentT = [Rprev|tprev] * transform^-1   (RGBDOdometry.cpp:466-474)
-    if (lane < 9) sc->iR[lane] = sc->trR[(lane % 3) * 3 + lane / 3];
-    __syncwarp();
-    if (lane < 3) sc->iT[lane] = -((sc->iR[lane * 3] * sc->trT[0] + sc->iR[lane * 3 + 1] * sc->trT[1]) + sc->iR[lane * 3 + 2] * sc->trT[2]);
-    __syncwarp();
-    if (lane < 9) { int r = lane / 3, c = lane % 3; st->Rcurr[lane] = (st->Rprev[r * 3] * sc->iR[c] + st->Rprev[r * 3 + 1] * sc->iR[3 + c]) + st->Rprev[r * 3 + 2] * sc->iR[6 + c]; }
-    else if (lane < 12) { int r = lane - 9; st->tcurr[r] = ((st->Rprev[r * 3] * sc->iT[0] + st->Rprev[r * 3 + 1] * sc->iT[1]) + st->Rprev[r * 3 + 2] * sc->iT[2]) + st->tprev[r]; }
-    __syncwarp();
+    // ---- stage 4: every output entry from nr[] in registers ----
+    const double* T = sc->nr;
+    if (lane < 16) st->resultRt[lane] = T[lane];
+    // transform (float) = [trR | trT]; currentT = [Rprev|tprev] * transform^-1 (RGBDOdometry.cpp:466-474): iR = trR^T, iT = -iR trT
+    if (lane < 9) st->trR[lane] = (float)T[(lane / 3) * 4 + lane % 3];
+    else if (lane < 12) st->trT[lane - 9] = (float)T[(lane - 9) * 4 + 3];
+    if (lane < 9) {
+        const int r = lane / 3, c = lane % 3;
+        // iR[k][c] = trR[c][k]
+        const float i0 = (float)T[c * 4 + 0], i1 = (float)T[c * 4 + 1], i2 = (float)T[c * 4 + 2];
+        st->Rcurr[lane] = (st->Rprev[r * 3] * i0 + st->Rprev[r * 3 + 1] * i1) + st->Rprev[r * 3 + 2] * i2;
+    } else if (lane < 12) {
+        const int r = lane - 9;
+        const float t0 = (float)T[3], t1 = (float)T[7], t2 = (float)T[11];
+        float iT[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) iT[k] = -(((float)T[0 * 4 + k] * t0 + (float)T[1 * 4 + k] * t1) + (float)T[2 * 4 + k] * t2);
+        st->tcurr[r] = ((st->Rprev[r * 3] * iT[0] + st->Rprev[r * 3 + 1] * iT[1]) + st->Rprev[r * 3 + 2] * iT[2]) + st->tprev[r];
+    }
     TT(23);
-    if (RGB) computeWarpCoop(st, cam, sc, lane);          // warp constants for the next iteration's residuals
+    if (RGB && lane >= 16 && lane < 28) {
+        // computeWarp (RGBDOdometry.cpp:364-376): K R^-1 K^-1 and K t^-1 of the new estimate for the next iteration's residuals; lanes 16..24
+        // take one entry of KRK^-1 each, lanes 25..27 one entry of Kt (the lanes that are idle in the float part above)
+        const double* K = sc->K;
+        double Ri[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) Ri[e] = inv3dEntry<4>(T, e);
+        const int l = lane - 16;
+        if (l < 9) {
+            const int r = l / 3, cc = l % 3;
+            double tmp[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) tmp[j] = K[r * 3] * Ri[j] + K[r * 3 + 1] * Ri[3 + j] + K[r * 3 + 2] * Ri[6 + j];
+            st->krk[l] = (float)(tmp[0] * sc->Kinv[cc] + tmp[1] * sc->Kinv[3 + cc] + tmp[2] * sc->Kinv[6 + cc]);
+        } else {
+            const int q = l - 9;
+            double ti[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) ti[j] = -(Ri[j * 3] * T[3] + Ri[j * 3 + 1] * T[7] + Ri[j * 3 + 2] * T[11]);
+            st->kt[q] = (float)(K[q * 3] * ti[0] + K[q * 3 + 1] * ti[1] + K[q * 3 + 2] * ti[2]);
+        }
+    }
 }
 
 MF_D void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -760,7 +807,9 @@ struct PixA {
 extern __shared__ int2 corrShared[];
 
 
-template <bool CL>
+// LL: the partial rows travel as flagged words (compile-time: the other exchange is not even instantiated -- the kernel's loop body
+// has to stay inside the instruction cache)
+template <bool CL, bool LL>
 MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
 {
     __shared__ TrackJob J;
@@ -895,7 +944,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
             }
             TT(12);
             rc.Gact = Gact;
-            reduceStep<CL, 11>(acc, 0, 0, active, rc, red, ws, rowSh, tot);
+            reduceStep<CL, LL, 11>(acc, 0, 0, active, rc, red, ws, rowSh, tot);
             TT(15);
             if (threadIdx.x < 32) {
                 // host logic of RGBDOdometry.cpp:301-324 on warp 0: lane 0 takes the decisions, the 3x3 solve is warp-cooperative
@@ -1131,7 +1180,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
             rc.Gact = Gact;
             // phase B's first streaming inputs (pose independent) -> L1 while this CTA waits at the reduction
             if (tp.rgb && rounds > cRounds) { prefetchL1(grad + kOf(cRounds)); }
-            reduceStep<CL, NACC_ICP>(acc, cnt, sig, active, rc, red, ws, rowSh, tot);
+            reduceStep<CL, LL, NACC_ICP>(acc, cnt, sig, active, rc, red, ws, rowSh, tot);
             TT(5);
             if (tp.rgb) {
                 if (threadIdx.x == 0) {
@@ -1205,7 +1254,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
                         prefetchL1(nextDepth + kn);
                     }
                 // ICP totals stay in tot[0..28]; the photometric ones go behind them
-                reduceStep<CL, NACC_RGB>(accR, 0, 0, active, rc, red, ws, rowSh, totR);
+                reduceStep<CL, LL, NACC_RGB>(accR, 0, 0, active, rc, red, ws, rowSh, totR);
                 TT(9);
                 if (threadIdx.x < NACC_RGB) tot[NACC_ICP + threadIdx.x] = totR[threadIdx.x];
                 __syncthreads();
@@ -1255,9 +1304,11 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
 }
 
 // whole schedule (phase 0) or levels 1..0 (phase 2): cooperative launch, one CTA per SM, software grid barrier
-__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackParams tp) { trackBody<false>(jobs, tp); }
+__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent(const TrackJob* __restrict__ jobs, TrackParams tp) { trackBody<false, true>(jobs, tp); }
+// the same with the counter barrier + plain rows (MFB200_TRACK_LL=0, A/B)
+__global__ void __launch_bounds__(PT_THREADS, 1) k_track_persistent_bar(const TrackJob* __restrict__ jobs, TrackParams tp) { trackBody<false, false>(jobs, tp); }
 // SO(3) pre-alignment + level 2 (phase 1): one thread-block cluster per tracked model
-__global__ void __launch_bounds__(PT_THREADS, 1) k_track_cluster(const TrackJob* __restrict__ jobs, TrackParams tp) { trackBody<true>(jobs, tp); }
+__global__ void __launch_bounds__(PT_THREADS, 1) k_track_cluster(const TrackJob* __restrict__ jobs, TrackParams tp) { trackBody<true, false>(jobs, tp); }
 
 // ------------------------------ host launchers ----------------------------------------
 float track_min_scale(int level)
@@ -1292,6 +1343,7 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
         cudaFuncAttributes fa; cudaCheck(cudaFuncGetAttributes(&fa, k_track_persistent), "cudaFuncGetAttributes");
         dynMaxDev[dev] = (size_t)optin > fa.sharedSizeBytes + 2048 ? (size_t)optin - fa.sharedSizeBytes - 2048 : 0;
         cudaCheck(cudaFuncSetAttribute(k_track_persistent, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMaxDev[dev]), "cudaFuncSetAttribute");
+        cudaCheck(cudaFuncSetAttribute(k_track_persistent_bar, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dynMaxDev[dev]), "cudaFuncSetAttribute");
         cudaCheck(cudaFuncGetAttributes(&fa, k_track_cluster), "cudaFuncGetAttributes");
         dynMaxClDev[dev] = (size_t)optin > fa.sharedSizeBytes + 2048 ? (size_t)optin - fa.sharedSizeBytes - 2048 : 0;
         // clusters of 16 CTAs are a non-portable size: opt in; if either attribute is refused the frame runs as one cooperative launch
@@ -1375,7 +1427,7 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
     prof_mark(s, "k_track_persistent");
     void* args[] = {(void*)&jp, (void*)&tp};
-    cudaCheck(cudaLaunchCooperativeKernel((const void*)k_track_persistent, dim3(G, nJobs), dim3(PT_THREADS), args, dyn, s), "cooperative launch (tracking)");
+    cudaCheck(cudaLaunchCooperativeKernel(llOn ? (const void*)k_track_persistent : (const void*)k_track_persistent_bar, dim3(G, nJobs), dim3(PT_THREADS), args, dyn, s), "cooperative launch (tracking)");
     return launches + 1;
 }
 

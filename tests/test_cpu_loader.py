@@ -395,3 +395,36 @@ def test_corrupt_streams_are_rejected_not_crashed(product_lib, tmp_path):
     L = mfb.load_library()
     assert not L.mf_klg_open(None, 640, 480, 0)
     assert not L.mf_klg_open(b"/nonexistent.klg", -1, 480, 0)
+
+
+def test_exr_depth_decoder_matches_opencv_golden(tmp_path):
+    """in-tree OpenEXR scan-line decoder (HALF/FLOAT, NONE/RLE/ZIPS/ZIP, gray and R,G,B files) against OpenCV's decode of the same
+    streams (tests/golden/make_exr_golden.py), bit for bit; through the -dir reader as well (ImageLogReader.cpp:251-258)"""
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.api import decode_exr_depth, MFError
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "exr_golden.npz"))
+    n = int(g["nexr"])
+    assert n >= 40
+    for k in range(n):
+        d = decode_exr_depth(g[f"exr{k}"].tobytes())
+        ref = g[f"exr{k}_depth"]
+        assert d.shape == ref.shape and np.array_equal(d.view(np.uint32), ref.view(np.uint32)), k
+    with pytest.raises(MFError, match="PIZ"):
+        decode_exr_depth(g["exr_piz"].tobytes())
+    for bad in (b"", b"abcd" * 8, g["exr0"].tobytes()[:60], g["exr3"].tobytes()[:-9]):
+        with pytest.raises(MFError):
+            decode_exr_depth(bad)
+    # a two-frame image directory with EXR depth
+    ref = g["exr0_depth"]
+    H, W = ref.shape
+    rgb = (np.arange(H * W * 3) % 251).astype(np.uint8).reshape(H, W, 3)
+    for i in range(2):
+        with open(tmp_path / f"Color{i:04d}.ppm", "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (W, H)); f.write(rgb.tobytes())
+        with open(tmp_path / f"Depth{i:04d}.exr", "wb") as f:
+            f.write(g["exr0"].tobytes())
+    rd = mfb.ImageLogReader(str(tmp_path), indexWidth=4)
+    assert rd.getNumFrames() == 2
+    fr = rd.getNext()
+    assert np.array_equal(np.asarray(fr[1]).view(np.uint32), ref.view(np.uint32))
+    rd.close()
