@@ -480,7 +480,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms, bool viaResult)
     const bool rgbTerm = cfg.rgbOnly || cfg.icpWeight < 100;
     if (!frameMapsValid) generateCUDATextures();
     if ((rgbTerm || cfg.so3) && !intensityValid) frameIntensity();
-    bool anyBits = false;
+    unsigned lightMask = 0;          // jobs with a validity bitmask (object models): small share of the tracker's grid
     for (size_t j = 0; j < ms.size(); ++j) {
         Model* m = ms[j];
         if (!viaResult) m->lastPose = m->pose;                       // Model.cpp:430 (multi-model: applied with the result)
@@ -494,7 +494,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms, bool viaResult)
         J.lastNextImage2 = m->lastNextImage2; J.st = m->trackState; J.partial = m->partial; J.bar = trackBars.p + j * 32;
         J.dpose = m->dpose;
         for (int l = 0; l < 3; ++l) J.validBits[l] = (m->validBits[l].p && trackValidBits) ? m->validBits[l].p : nullptr;
-        anyBits = anyBits || J.validBits[0] != nullptr;
+        if (J.validBits[0] != nullptr) lightMask |= 1u << j;
     }
     if (preWaitPending) {            // the frame's preprocessing ran on preStream: the tracker is the first consumer on the main stream
         cudaCheck(cudaStreamWaitEvent(stream, preDone, 0), "cudaStreamWaitEvent");
@@ -504,7 +504,7 @@ void MaskFusion::trackModels(const std::vector<Model*>& ms, bool viaResult)
     // hJobs is reused every frame: the next frameBegin first waits (finalisePending) for an event recorded behind this copy
     cudaCheck(cudaMemcpyAsync(dJobs, hJobs, ms.size() * sizeof(TrackJob), cudaMemcpyHostToDevice, stream), "jobs upload");
     launches += launch_tracking(dJobs, (int)ms.size(), W, H, cam, cfg.rgbOnly != 0, cfg.icpWeight, cfg.pyramid != 0, cfg.fastOdom != 0,
-                                cfg.so3 != 0, numSMs, trackBars, stream, anyBits);
+                                cfg.so3 != 0, numSMs, trackBars, stream, lightMask);
     prof_mark(stream, "copy_pose_d2h");
     for (Model* m : ms) {
         if (!viaResult)

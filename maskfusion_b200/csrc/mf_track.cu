@@ -417,6 +417,10 @@ struct TrackParams {
     int cacheRounds;                   // pixel rounds per thread whose pose-independent inputs are kept in shared memory across the iterations of a level
     int phase;                         // 0: whole schedule in this launch; 1: SO(3) + level 2 only (cluster kernel); 2: resume at level 1
     unsigned llBase;                   // != 0: the partial rows are exchanged as flagged words (flag = llBase + index of the reduction in the launch)
+    // flat grid (persistent kernel): CTA b belongs to the job j with jobStart[j] <= b < jobStart[j + 1] -- the models of a batch get
+    // DIFFERENT numbers of CTAs (a full-frame model walks 307 k live pixels per iteration, an object model rejects nearly all of them on its
+    // validity bitmask); nJobs == 0: the rectangular grid (blockIdx.y = job) of the cluster kernel
+    int nJobs; unsigned short jobStart[TRACK_MAX_JOBS + 1];
 };
 
 // sum of 32 per-lane values over the warp with 31 (64-bit) shuffles instead of 5*32: each step exchanges HALF of the remaining
@@ -594,7 +598,7 @@ MF_D void sumRowsLL(const uint4* __restrict__ rows, unsigned R, unsigned flag, d
     __syncthreads();
 }
 
-struct RedCtx { double* rowsBuf[2]; unsigned* bar; unsigned G, Gact, gen, llBase; };
+struct RedCtx { double* rowsBuf[2]; unsigned* bar; unsigned G, Gact, gen, llBase, bx; };
 template <bool CL, bool LL, int N>
 MF_D void reduceStep(const double* acc, int e0, int e1, bool active, RedCtx& rc, double (*red)[ROWF], double (*ws)[ROWF], double (*rowSh)[ROWF], double* tot)
 {
@@ -616,11 +620,13 @@ MF_D void reduceStep(const double* acc, int e0, int e1, bool active, RedCtx& rc,
             uint4* rows = reinterpret_cast<uint4*>(rc.rowsBuf[0]) + (size_t)(rc.gen & 1) * rc.G * ROWF;
             ++rc.gen;
             const unsigned flag = rc.llBase + rc.gen;
-            if (active) ctaReduceStoreLL<N>(acc, red, rows + (size_t)blockIdx.x * ROWF, flag, e0, e1);
+            // (an out-of-line routine shared by the three reductions shrank the loop by 1700 instructions but cost more than it saved: the 32
+            // values travel through local memory: 412 -> 493 us, profiles/r02e_track_timing_outlined_exchange.json)
+            if (active) ctaReduceStoreLL<N>(acc, red, rows + (size_t)rc.bx * ROWF, flag, e0, e1);
             sumRowsLL(rows, rc.Gact, flag, ws, tot);
         } else {
             double* rows = rc.rowsBuf[rc.gen & 1];
-            if (active) ctaReduceStore<N>(acc, red, rows + (size_t)blockIdx.x * ROWF, e0, e1);
+            if (active) ctaReduceStore<N>(acc, red, rows + (size_t)rc.bx * ROWF, e0, e1);
             ++rc.gen; gridBarrier(rc.bar, rc.gen * rc.G);
             sumRows(rows, rc.Gact, ws, tot);
         }
@@ -823,8 +829,14 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
     __shared__ float so3B[9], so3Kinv[9], so3Krlr[9];
     __shared__ double so3K[9], so3KinvD[9];
     __shared__ int flag;
+    unsigned bx = blockIdx.x, by = blockIdx.y, Gj = gridDim.x;         // CTA index within its model, model, CTAs of the model
+    if (!CL && tp.nJobs > 0) {
+        by = 0;
+        while ((int)by + 1 < tp.nJobs && blockIdx.x >= tp.jobStart[by + 1]) ++by;
+        bx = blockIdx.x - tp.jobStart[by]; Gj = (unsigned)tp.jobStart[by + 1] - tp.jobStart[by];
+    }
     {   // job record -> shared memory (one coalesced read instead of dependent pointer chases in every phase)
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + blockIdx.y);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(jobs + by);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&J);
         for (int k = threadIdx.x; k < (int)(sizeof(TrackJob) / 4); k += PT_THREADS) dst[k] = src[k];
     }
@@ -833,7 +845,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) g_trackTimingN = 0;
 #endif
     TT(1);
-    const unsigned G = gridDim.x;                                      // CTAs of this model (cluster variant: == cluster size)
+    const unsigned G = Gj;                                             // CTAs of this model (cluster variant: == cluster size)
     __syncthreads();
     if (tp.phase == 2) {
         // second launch of the frame: the replicated solver state as the cluster kernel left it
@@ -859,10 +871,11 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
     __syncthreads();
     RedCtx rc;
     rc.rowsBuf[0] = reinterpret_cast<double*>(J.partial); rc.rowsBuf[1] = reinterpret_cast<double*>(J.partial) + (size_t)G * ROWF;
-    rc.bar = J.bar; rc.G = G; rc.Gact = G; rc.gen = 0; rc.llBase = CL ? 0u : tp.llBase;
+    rc.bar = J.bar; rc.G = G; rc.Gact = G; rc.gen = 0; rc.llBase = CL ? 0u : tp.llBase; rc.bx = bx;
     // photometric correspondences of this thread's pixels, slot = round * PT_THREADS + thread: written in phase A, read in phase B
     // by the same thread.  Shared memory when the launch reserved enough, else a private stripe of the model's scratch buffer.
-    int2* const corr = tp.corrSlots ? corrShared : reinterpret_cast<int2*>(J.corres[0]) + (size_t)blockIdx.x * ((size_t)((tp.W * tp.H + G * PT_THREADS - 1) / (G * PT_THREADS)) * PT_THREADS);
+    const size_t corrNeed = (size_t)((tp.W * tp.H + G * PT_THREADS - 1) / (G * PT_THREADS)) * PT_THREADS;      // slots of this CTA at level 0 (depends on the model's share of the grid)
+    int2* const corr = ((size_t)tp.corrSlots >= corrNeed && tp.corrSlots) ? corrShared : reinterpret_cast<int2*>(J.corres[0]) + (size_t)bx * corrNeed;
     // Pose-independent inputs of this thread's pixels (frame vertex / normal, depth of the photometric pyramid, intensity, validity, image
     // gradient, pixel coordinates) are the same in every iteration of a level: they are read from global memory ONCE per level into
     // shared memory (slot = round * PT_THREADS + thread, structure of arrays: conflict-free 16-byte accesses) and the Gauss-Newton
@@ -882,8 +895,8 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         const int W = tp.W >> 2, H = tp.H >> 2, N = W * H;
         // CTAs beyond the pixel count only wait at the barriers: fewer partial rows to sum
         const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
-        const bool active = blockIdx.x < Gact;
-        const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
+        const bool active = bx < Gact;
+        const int tid = (int)bx * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
         const Cam c = camLevel(tp.cam, 2);
         const uint8_t* __restrict__ lastImage = J.lastNextImage2;
         const uint8_t* __restrict__ nextImage = J.nextImage[2];
@@ -998,8 +1011,8 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         if (tp.iterations[level] == 0) continue;
         const int W = tp.W >> level, H = tp.H >> level, N = W * H;
         const unsigned Gact = min(G, (unsigned)((N + PT_THREADS - 1) / PT_THREADS));
-        const bool active = blockIdx.x < Gact;
-        const int tid = blockIdx.x * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
+        const bool active = bx < Gact;
+        const int tid = (int)bx * PT_THREADS + threadIdx.x, nthr = (int)Gact * PT_THREADS;
         // Pixels of this thread: tid + r * nthr for the fullRounds rounds every thread has, plus at most one pixel of the tail
         // (N - fullRounds * nthr pixels).  The tail is dealt out by warps of 32 pixels ACROSS the CTAs (tail warp j -> CTA j % Gact,
         // warp j / Gact): at 640x480 on 148 CTAs the 4096 tail pixels become one extra pixel for ONE warp of 128 CTAs instead of a
@@ -1008,7 +1021,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         const int fullRounds = N / nthr;
         int kTail = -1;
         if (active) {
-            const int j = (threadIdx.x >> 5) * (int)Gact + (int)blockIdx.x;
+            const int j = (threadIdx.x >> 5) * (int)Gact + (int)bx;
             const int kt = fullRounds * nthr + j * 32 + (threadIdx.x & 31);
             if (kt < N) kTail = kt;
         }
@@ -1271,7 +1284,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         // hand the replicated state to the second launch (every CTA holds the same bits: rank 0 writes); a CTA must not exit while a
         // peer may still read its shared memory
         __syncthreads();
-        if (blockIdx.x == 0) {
+        if (bx == 0) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(&S);
             uint32_t* dst = reinterpret_cast<uint32_t*>(J.st);
             for (int k = threadIdx.x; k < (int)(sizeof(TrackState) / 4); k += PT_THREADS) dst[k] = src[k];
@@ -1280,7 +1293,7 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
         return;
     }
     // ---------------- result (RGBDOdometry.cpp:478-497) ----------------
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (bx == 0 && threadIdx.x == 0) {
         float dx = st->tcurr[0] - st->tprev[0], dy = st->tcurr[1] - st->tprev[1], dz = st->tcurr[2] - st->tprev[2];
         if (tp.rgb && sqrtf((dx * dx + dy * dy) + dz * dz) > 0.3f) {          // :478-482
             for (int k = 0; k < 9; ++k) { st->Rcurr[k] = st->Rprev[k]; st->trR[k] = (k % 4 == 0) ? 1.f : 0.f; }
@@ -1327,8 +1340,9 @@ static int trackBlocks(int N, int numSMs)
 }
 
 int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
-                    bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s, bool anyValidBits)
+                    bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s, unsigned lightMask)
 {
+    const bool anyValidBits = lightMask != 0;          // bit j: job j is an object model with a validity bitmask (nearly all of its pixels are rejected early)
     // per-device launch limits (several contexts on different GPUs may live in one process): occupancy and the opt-in
     // dynamic shared memory attribute are properties of (function, device)
     static int coResidentDev[64]; static size_t dynMaxDev[64], dynMaxClDev[64]; static bool devInit[64]; static int clusterOkDev[64];
@@ -1381,12 +1395,36 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     if (G * nJobs > coResident) G = coResident / nJobs;
     if (G > TRACK_MAX_BLOCKS / 2) G = TRACK_MAX_BLOCKS / 2;
     if (G < 1) throw CudaError{"too many tracked models for one cooperative launch"};
+    // Per-model shares of the persistent grid.  A full-frame model (the background) pays the whole pixel phase for every live pixel; an
+    // object model rejects nearly every pixel on its bitmask and is bound by the reduction / solve chain instead: with equal shares the
+    // background of the 8-object scene walked 37 pixels per thread while the objects' CTAs idled at their barriers.  Light models get a
+    // small fixed share, the heavy ones split the rest.  (Sums are fp64 of exact products: the result does not depend on the shares.)
+    static int sharesOn = -1;       // MFB200_TRACK_SHARES=0: equal shares (A/B)
+    if (sharesOn < 0) { const char* e = getenv("MFB200_TRACK_SHARES"); sharesOn = e ? (e[0] != '0') : 1; }
+    int Gof[TRACK_MAX_JOBS];
+    int nLight = 0;
+    for (int j = 0; j < nJobs; ++j) nLight += (lightMask >> j) & 1u;
+    const int nHeavy = nJobs - nLight, totalCTAs = std::min(numSMs, coResident);
+    int Gheavy = G, Glight = G;
+    if (sharesOn && nLight > 0 && nHeavy > 0) {
+        // a heavy model gets `ratio` times the CTAs of a light one: the measured cost of a bitmask-rejected pixel is about a third of a
+        // live one (8 objects: 251 frames/s with equal shares, 270 with 84 / 8 x 8; 3 objects: 474 equal, 450 with 100 / 3 x 16)
+        static int ratio = -1;      // MFB200_TRACK_HEAVY_RATIO (A/B)
+        if (ratio < 0) { const char* e = getenv("MFB200_TRACK_HEAVY_RATIO"); ratio = e ? std::max(1, atoi(e)) : 3; }
+        Glight = std::max(4, totalCTAs / (nLight + ratio * nHeavy));
+        Gheavy = (totalCTAs - nLight * Glight) / nHeavy;
+        if (Gheavy < Glight) { Gheavy = G; Glight = G; }
+        if (Gheavy > TRACK_MAX_BLOCKS / 2) Gheavy = TRACK_MAX_BLOCKS / 2;
+    }
+    tp.nJobs = nJobs; tp.jobStart[0] = 0;
+    for (int j = 0; j < nJobs; ++j) { Gof[j] = ((lightMask >> j) & 1u) ? Glight : Gheavy; tp.jobStart[j + 1] = (unsigned short)(tp.jobStart[j] + Gof[j]); }
+    const int gridCTAs = tp.jobStart[nJobs];
     int launches = 0;
     const TrackJob* jp = d_jobs;
     // ---- SO(3) pre-alignment + level 2 on one thread-block cluster per model (hardware barrier + distributed shared memory) ----
     bool clustered = false;
     if (clusterOkDev[dev] && (tp.so3 || tp.iterations[2] > 0)) {
-        TrackParams t1 = tp; t1.phase = 1;
+        TrackParams t1 = tp; t1.phase = 1; t1.nJobs = 0;
         const int N2 = (W >> 2) * (H >> 2);
         for (int C = 16; C >= 8 && !clustered; C >>= 1) {
             const int roundsC = (N2 + C * PT_THREADS - 1) / (C * PT_THREADS);
@@ -1415,7 +1453,8 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     }
     tp.phase = clustered ? 2 : 0;
     // photometric correspondences stay in shared memory when the per-CTA pixel share fits (8 B per pixel slot)
-    const int rounds0 = (W * H + G * PT_THREADS - 1) / (G * PT_THREADS);
+    // sized for the models with the largest share (the heavy ones); a CTA whose share needs more slots uses its model's global scratch stripe
+    const int rounds0 = (W * H + Gheavy * PT_THREADS - 1) / (Gheavy * PT_THREADS);
     size_t dyn = (size_t)rounds0 * PT_THREADS * sizeof(int2);
     if (tp.rgb && dyn <= dynMaxDev[dev]) tp.corrSlots = rounds0 * PT_THREADS; else { tp.corrSlots = 0; dyn = 0; }
     dyn = (dyn + 15) & ~(size_t)15;
@@ -1427,7 +1466,7 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     cudaCheck(cudaMemsetAsync(bars, 0, TRACK_MAX_JOBS * 32 * sizeof(unsigned), s), "barrier reset");
     prof_mark(s, "k_track_persistent");
     void* args[] = {(void*)&jp, (void*)&tp};
-    cudaCheck(cudaLaunchCooperativeKernel(llOn ? (const void*)k_track_persistent : (const void*)k_track_persistent_bar, dim3(G, nJobs), dim3(PT_THREADS), args, dyn, s), "cooperative launch (tracking)");
+    cudaCheck(cudaLaunchCooperativeKernel(llOn ? (const void*)k_track_persistent : (const void*)k_track_persistent_bar, dim3(gridCTAs), dim3(PT_THREADS), args, dyn, s), "cooperative launch (tracking)");
     return launches + 1;
 }
 

@@ -219,6 +219,52 @@ def test_sequence_ate_rgbd_so3():
     assert counts[0] == counts[1] and final["surfels_equal"] and final["pose_equal"], (counts, final)
 
 
+def test_bench_state_matches_oracle():
+    """The benchmarked state: capacity 2176^2, the background store pre-populated to ~4.6 M surfels exactly as bench.py does,
+    GUI defaults (ICP+RGB w=20, SO3), free running.  After three frames: pose logs, surfel stores (bit patterns), the index map of the last
+    predictIndices (the one that rides inside Model::clean) and the splat prediction equal the oracle's."""
+    import ctypes as C
+    import maskfusion_b200 as mfb
+    from maskfusion_b200.synth import SynthScene, dense_room_surfels
+    cap, prepop = 2176 * 2176, 4_300_000
+    sc = SynthScene(W, H, n_objects=0, seed=0)
+    orc = ol.OraclePipeline(ol.default_config(W, H, capacityGlobal=cap))
+    mf = mfb.MaskFusion(mfb.default_config(W, H, capacityGlobal=cap))
+    rgb, depth, *_ = sc.render(0)
+    orc.process_frame(rgb, depth, 0)
+    mf.processFrame(rgb, depth, 0)
+    gm = mf.getBackgroundModel()
+    cur = gm.downloadMap()
+    assert np.array_equal(cur.view(np.uint32), orc.surfels(0).view(np.uint32))
+    room = dense_room_surfels(sc, prepop, time=1, conf=20.0)
+    Tinv = np.linalg.inv(sc.camera_pose(0))
+    room[:, 0:3] = (room[:, 0:3].astype(np.float64) @ Tinv[:3, :3].T + Tinv[:3, 3]).astype(np.float32)
+    room[:, 8:11] = (room[:, 8:11].astype(np.float64) @ Tinv[:3, :3].T).astype(np.float32)
+    allv = np.ascontiguousarray(np.concatenate([cur, room], 0))
+    gm.uploadMap(allv)
+    m = orc.L.orc_mf_model(orc.h, 0)
+    C.memmove(m.contents.surf[m.contents.target], allv.ctypes.data, allv.nbytes)
+    m.contents.count = allv.shape[0]
+    for t in range(1, 4):
+        rgb, depth, *_ = sc.render(t)
+        orc.process_frame(rgb, depth, t * 33333)
+        mf.processFrame(rgb, depth, t * 33333)
+    mf.sync()
+    lo = np.array([orc.model(0).log[i] for i in range(orc.model(0).nlog * 8)]).reshape(-1, 8)
+    lc = gm.poseLog()
+    assert np.array_equal(lo, lc), f"pose logs differ: max {np.abs(lo - lc).max():.3e}"
+    assert orc.count(0) == gm.lastCount() and orc.count(0) > 4_400_000, (orc.count(0), gm.lastCount())
+    so, sm = orc.surfels(0), gm.downloadMap()
+    assert np.array_equal(so.view(np.uint32), sm.view(np.uint32)), int((so.view(np.uint32) != sm.view(np.uint32)).any(axis=1).sum())
+    idx_c, vc_c, ct_c, nr_c = gm.indexMap()
+    assert np.array_equal(idx_c, orc.tex(0, "idx")), int((idx_c != orc.tex(0, "idx")).sum())
+    assert np.array_equal(vc_c.view(np.uint32), orc.tex(0, "vertConf").view(np.uint32))
+    im, pv, pn, tt = gm.prediction()
+    assert np.array_equal(pv.view(np.uint32), orc.tex(0, "splatVertex").view(np.uint32))
+    assert np.array_equal(im, orc.tex(0, "splatImage")) and np.array_equal(tt, orc.tex(0, "splatTime"))
+    mf.close()
+
+
 def test_icp_step_matches_oracle():
     """icpStep (reduce.cu:446-525) at a fixed pose: 29 sums within 1e-4 relative of the double-precision oracle"""
     import ctypes as C
