@@ -374,7 +374,7 @@ MF_D bool cleanFinish(float4& vp, float4& vc, float x, float y, float lpz, int c
 // only REGISTERED in a device-wide candidate list; pass 1b works that list densely.
 // (An in-kernel window ran with 9/32 lanes active; a block-compacted variant was still latency bound at 2 blocks/SM.)
 #define CAND_BUF 2048
-__global__ void __launch_bounds__(256) k_clean_p1(float4* __restrict__ pos, float4* __restrict__ col, const uint32_t* __restrict__ countPtr,
+__global__ void __launch_bounds__(256, 8) k_clean_p1(float4* __restrict__ pos, float4* __restrict__ col, const uint32_t* __restrict__ countPtr,
                                                   const uint8_t* __restrict__ aflag, float4* __restrict__ m0, float4* __restrict__ m1, int Ppix,
                                                   CleanParams P, const DevPose* __restrict__ dpose, const float* __restrict__ depthFilt, const uint8_t* __restrict__ mask,
                                                   uint8_t* __restrict__ keep, uint32_t* __restrict__ cand, uint32_t* __restrict__ candCount,
@@ -718,7 +718,10 @@ MF_D void splatRange(const SplatVS& v, int W, int H, int& x0, int& x1, int& y0, 
 #ifndef SPLAT_BS
 #define SPLAT_BS 128               // surfels (= threads) per block round: smaller rounds interleave the load phase of one block with the raster phase of another
 #endif
-__global__ void __launch_bounds__(SPLAT_BS) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
+#ifndef SPLAT_MIN_BLOCKS
+#define SPLAT_MIN_BLOCKS 1             // A/B: -DSPLAT_MIN_BLOCKS=10 caps the registers at 51 for 10 blocks per SM
+#endif
+__global__ void __launch_bounds__(SPLAT_BS, SPLAT_MIN_BLOCKS) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
                                                        const uint32_t* __restrict__ countPtr, const DevPose* __restrict__ dpose, Cam cam, int W, int H,
                                                        float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
                                                        uint32_t drawBase, const float4* __restrict__ rayTab, unsigned long long* __restrict__ key)

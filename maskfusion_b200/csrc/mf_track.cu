@@ -1407,10 +1407,10 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     const int nHeavy = nJobs - nLight, totalCTAs = std::min(numSMs, coResident);
     int Gheavy = G, Glight = G;
     if (sharesOn && nLight > 0 && nHeavy > 0) {
-        // a heavy model gets `ratio` times the CTAs of a light one: the measured cost of a bitmask-rejected pixel is about a third of a
-        // live one (8 objects: 251 frames/s with equal shares, 270 with 84 / 8 x 8; 3 objects: 474 equal, 450 with 100 / 3 x 16)
+        // a heavy model gets `ratio` times the CTAs of a light one (measured, frames/s of the 8-object / 3-object scenes: equal shares
+        // 251 / 474; ratio 2: 307 / 576; ratio 3: 297 / 557; ratio 5: 297 / 516; a first 84 / 8 x 8 split: 270, 100 / 3 x 16: 450)
         static int ratio = -1;      // MFB200_TRACK_HEAVY_RATIO (A/B)
-        if (ratio < 0) { const char* e = getenv("MFB200_TRACK_HEAVY_RATIO"); ratio = e ? std::max(1, atoi(e)) : 3; }
+        if (ratio < 0) { const char* e = getenv("MFB200_TRACK_HEAVY_RATIO"); ratio = e ? std::max(1, atoi(e)) : 2; }
         Glight = std::max(4, totalCTAs / (nLight + ratio * nHeavy));
         Gheavy = (totalCTAs - nLight * Glight) / nHeavy;
         if (Gheavy < Glight) { Gheavy = G; Glight = G; }

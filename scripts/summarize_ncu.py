@@ -19,6 +19,24 @@ for f in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
     if len(rows) < 3:
         continue
     hdr, units = rows[0], rows[1]
+    if f.startswith("prof_multi"):
+        # one capture of several kernels (ncu -k regex:"a|b|c"): one summary file per kernel, the same format as the single-kernel captures
+        seen = set()
+        for vals in rows[2:]:
+            name = vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+            base = name.split("(")[0].split("<")[0].split("::")[-1]
+            if base in seen:
+                continue
+            seen.add(base)
+            with open(os.path.join(out_dir, f"{tag}_prof_{base}.txt"), "w") as o:
+                o.write(f"# ncu --set full --clock-control none, {f} (multi-kernel capture of one frame of bench.py); one launch per row block\n")
+                o.write(f"kernel: {name[:160]}\n")
+                for w in WANT:
+                    if w in hdr:
+                        i = hdr.index(w)
+                        o.write(f"  {w} = {vals[i]} {units[i]}\n")
+        print("wrote", f, sorted(seen))
+        continue
     with open(os.path.join(out_dir, f"{tag}_{f.replace('.ncu-rep', '')}.txt"), "w") as o:
         o.write(f"# ncu --set full --clock-control none, {f}; one launch per row block\n")
         for vals in rows[2:]:
