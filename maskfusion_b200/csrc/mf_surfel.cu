@@ -719,8 +719,8 @@ MF_D void splatRange(const SplatVS& v, int W, int H, int& x0, int& x1, int& y0, 
 #define SPLAT_BS 128               // surfels (= threads) per block round: smaller rounds interleave the load phase of one block with the raster phase of another
 #endif
 #ifndef SPLAT_MIN_BLOCKS
-#define SPLAT_MIN_BLOCKS 1             // A/B: -DSPLAT_MIN_BLOCKS=10 caps the registers at 51 for 10 blocks per SM
-#endif
+#define SPLAT_MIN_BLOCKS 16            // 32 registers (88 B of spills), 2048 threads per SM.  Measured (k_splat_project, us): 64 registers /
+#endif                                 // 8 blocks 224; 48 / 10: 224; 40 / 12: 205; 32 / 16: 185 -- the rasteriser hides its key / ray loads with warps, not registers
 __global__ void __launch_bounds__(SPLAT_BS, SPLAT_MIN_BLOCKS) k_splat_project(const float4* __restrict__ pos, const float4* __restrict__ col, const float4* __restrict__ nrm,
                                                        const uint32_t* __restrict__ countPtr, const DevPose* __restrict__ dpose, Cam cam, int W, int H,
                                                        float maxDepth, float confThreshold, float ftime, float fmaxTime, float ftimeDelta,
