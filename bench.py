@@ -417,7 +417,7 @@ def run_ours(args, rank, world):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "configs[1]: -static single model, 640x480 synthetic .klg replay, ICP+RGB+SO3 tracking + surfel fuse, 1 B200",
                    "surfels_live": int(st["S_live"]), "surfel_capacity": CAPACITY, "tracking": "GUI defaults icpWeight=20 so3=1 pyramid=1",
-                   "l2": "surfel store 2x227 MB + per-frame maps exceed the 126 MB L2 between steps (no explicit flush)",
+                   "l2": "surfel store (227 MB: three float4 planes x 4.73 M capacity, one copy) + per-frame maps exceed the 126 MB L2 between steps (no explicit flush)",
                    "parallelism": "single", "numerics": "fp32 per element; Gauss-Newton sums in fp64 of exact products, rounded to the reference's float record"},
         "timed_region": {"passes_ms": [round(m, 3) for m in st["ms_passes"]], "value_from": "median of three device-resident passes",
                          "min_ms_per_step": round(st["ms_passes"][0] / K, 4), "max_ms_per_step": round(st["ms_passes"][-1] / K, 4)},

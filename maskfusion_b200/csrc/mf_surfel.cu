@@ -599,13 +599,15 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_clean_compact(float4* __restrict
     const uint32_t nblk = (total + SCAN_BLOCK - 1) / SCAN_BLOCK;
     const uint32_t first = *firstMoved;
     __shared__ uint32_t wsum[SCAN_BLOCK / 32];
-    __shared__ uint32_t sBlk;
+    __shared__ uint32_t sBlk[2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (;;) {
-        if (threadIdx.x == 0) sBlk = first + atomicAdd(ticket, 1u);
-        __syncthreads();
-        const uint32_t blk = sBlk;
+    // tickets are drawn one iteration ahead: the atomic's round trip hides behind the current sub-block's loads
+    if (threadIdx.x == 0) sBlk[0] = first + atomicAdd(ticket, 1u);
+    __syncthreads();
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t blk = sBlk[it & 1];
         if (blk >= nblk) break;                                      // block uniform
+        if (threadIdx.x == 0) sBlk[(it + 1) & 1] = first + atomicAdd(ticket, 1u);
         const uint32_t e = blk * SCAN_BLOCK + threadIdx.x;
         const bool k = e < total && keep[e];
         const unsigned bal = __ballot_sync(0xffffffffu, k);
@@ -623,8 +625,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_clean_compact(float4* __restrict
             if (isOld) { a = __ldcg(pos + e); b = __ldcg(col + e); c = __ldcg(nrm + e); }      // coherent loads: the planes are written by this very kernel
             else { const uint32_t p = e - count; a = m0[p]; b = m1[p]; c = m2[p]; }
         }
-        __threadfence();                                             // this thread's loads are performed before the flag below can be observed
-        __syncthreads();
+        // The barrier below CONSUMES the loaded words (a predicate no compiler can fold): no thread passes it before every load of the block
+        // has returned its value, i.e. has been performed -- a later store to those addresses by another block cannot change what was read.
+        // (A __threadfence per thread did the same job at several hundred cycles per iteration.)
+        const unsigned probe = __float_as_uint(a.x) & __float_as_uint(b.y) & __float_as_uint(c.z);
+        __syncthreads_or(probe == 0x7fedcba9u);
         if (threadIdx.x == 0) {
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(loaded + blk), "r"(epoch) : "memory");
             if (nb) {
@@ -636,7 +641,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_clean_compact(float4* __restrict
                 }
             }
         }
-        __syncthreads();
+        __syncthreads();                                             // also: the next ticket (sBlk) is visible, wsum may be rewritten
         if (move) { stStream(pos + dst, a); stStream(col + dst, b); stStream(nrm + dst, c); }
     }
 }
