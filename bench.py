@@ -248,7 +248,8 @@ def roofline_of(stages, S_live, K, Wm, ms_prof):
     kern = {k: v for k, v in stages.items() if k.startswith("k_")}
     # the tracking schedule of a frame is one logical kernel in two launches (cluster kernel: SO3 + level 2, persistent kernel: levels 1-0);
     # its algorithmic bytes (1265 B per pixel over the whole schedule) are divided by the time of both
-    if "k_track_cluster" in kern and "k_track_persistent" in kern:
+    two_launches = "k_track_cluster" in kern and "k_track_persistent" in kern          # MFB200_TRACK_CLUSTER=1 (default: one launch)
+    if two_launches:
         a, b = kern.pop("k_track_cluster"), kern.pop("k_track_persistent")
         kern["k_track_persistent"] = (b[0], a[1] + b[1])
     total_ms = sum(v[1] for v in stages.values())
@@ -265,7 +266,7 @@ def roofline_of(stages, S_live, K, Wm, ms_prof):
         if b and n:
             g = (b / 1e9) / (ms / n / 1e3)
             per_kernel[k] = {"launches_per_step": round(n / (K + Wm), 2), "avg_ms": round(ms / n, 5), "GBps": round(g, 1), "frac": round(g / peak, 4)}
-    return {"kernel": dom if dom != "k_track_persistent" else "k_track_cluster + k_track_persistent (one tracking schedule, two launches)", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": peak_src,
+    return {"kernel": dom if not (two_launches and dom == "k_track_persistent") else "k_track_cluster + k_track_persistent (one tracking schedule, two launches)", "bound": "hbm", "achieved": round(achieved, 1) if achieved else None, "peak": peak, "peak_source": peak_src,
             "unit": "GB/s", "frac": round(achieved / peak, 4) if achieved else None, "traffic": traffic,
             "traffic_source": traffic_src, "avg_launch_ms": round(avg_ms, 5), "algorithmic_bytes_per_launch": ab,
             "note": "the tracking kernels walk 29 dependent Gauss-Newton reductions over maps that stay in L2 (DRAM traffic << algorithmic bytes): "

@@ -141,7 +141,10 @@ Model::Model(MaskFusion* o, unsigned char id_, float conf, bool enableFillIn, in
     keep.alloc((size_t)capacity + P);
     size_t nblk = ((size_t)capacity + P + 511) / 512 + 1;
     blockSums.alloc(nblk); blockSums2.alloc(nblk);
-    if (o->cleanInPlace) { cleanTicket.alloc(2); cleanTicket.zero(s); cleanLoaded.alloc(nblk); cleanLoaded.zero(s); }
+    if (o->cleanInPlace) {
+        cleanTicket.alloc(4); cleanTicket.zero(s); cleanLoaded.alloc(nblk); cleanLoaded.zero(s);
+        cudaCheck(cudaMallocHost((void**)&hCleanStat, 2 * sizeof(uint32_t)), "cudaMallocHost"); hCleanStat[0] = hCleanStat[1] = 0;
+    }
     cand.alloc((size_t)capacity + P); candCount.alloc(1); candCount.zero(s);
     for (int l = 0; l < 3; ++l) {
         size_t Pl = (size_t)(W >> l) * (H >> l);
@@ -167,6 +170,7 @@ Model::~Model()
 {
     if (hCount) cudaFreeHost(hCount);
     if (hTrackOut) cudaFreeHost(hTrackOut);
+    if (hCleanStat) cudaFreeHost(hCleanStat);
 }
 
 unsigned Model::lastCount()
@@ -271,7 +275,18 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
     MaskFusion* o = owner;
     float4* m[3] = {meas[0].p, meas[1].p, meas[2].p};
     const bool inPlace = o->cleanInPlace;
-    int other = inPlace ? target : 1 - target, otherCount = 1 - countSel;
+    // In-place compaction moves only the surfels behind the first removal: 22 us instead of the copy's 68 when removals sit in the young tail
+    // of the store (the steady state), but its ticketed hand-over needs ~140 us when most of a 4.5 M store moves (a removal near the front:
+    // e.g. the first frames after a map upload).  Both produce the same store, so the choice is free: a large store uses the copy into
+    // a second plane set (allocated on first need) for the frame that FOLLOWS one in which more than 40 % of it moved -- the statistic
+    // comes back with an asynchronous 8-byte copy and is read without waiting (a stale value only delays the switch).
+    bool pingPong = false;
+    if (inPlace && capacity >= (1u << 20) && hCleanStat && hCleanStat[1] > 0) {
+        const uint32_t first = hCleanStat[0], nb = hCleanStat[1];
+        pingPong = first < nb && (uint64_t)(nb - first) * 10 > (uint64_t)nb * 4;
+    }
+    if (pingPong && !pos[1 - target].p) { pos[1 - target].alloc(capacity); col[1 - target].alloc(capacity); nrm[1 - target].alloc(capacity); }
+    int other = (inPlace && !pingPong) ? target : 1 - target, otherCount = 1 - countSel;
     // the pending index projection rides in pass 1 when it uses this call's time gate (always, in the frame schedule)
     const bool fused = idxDeferred && idxTime == time && idxDelta == timeDelta && (size_t)capacity + (size_t)o->P < 0x80000000ull;   // bit 31 of a candidate entry is a flag
     if (!fused) flushIndex();
@@ -282,10 +297,12 @@ void Model::clean(int time, int timeDelta, float /*depthCutoff*/)
     const bool packedOK = fused || (cleanTexTime == time && cleanTexConf == confidenceThreshold);
     CleanWindowImages win{packedOK ? cleanTex.p : nullptr, vertConf.p, colorTime.p, idx.p};
     if (++cleanEpoch == 0) ++cleanEpoch;                              // 0 = "never published"
-    CleanInPlace ip{cleanTicket.p, cleanLoaded.p, cleanTicket.p + 1, cleanEpoch};
+    CleanInPlace ip{cleanTicket.p, cleanLoaded.p, cleanTicket.p + 1, cleanEpoch, pingPong};
     launch_clean(planes(target), planes(other), dCount(), count.p + otherCount, capacity, aflag, m, dpose, o->cam, o->W, o->H,
                  time, timeDelta, confidenceThreshold, o->cfg.outlierCoeff, id, win, o->depthFilt, o->mask, keep, blockSums,
                  cand, candCount, o->stream, fused ? &f : nullptr, inPlace ? &ip : nullptr);
+    if (inPlace && capacity >= (1u << 20))
+        cudaCheck(cudaMemcpyAsync(hCleanStat, cleanTicket.p + 1, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, o->stream), "clean statistic D2H");
     target = other; countSel = otherCount;
     o->launches += fused ? 6 : 5;
 }

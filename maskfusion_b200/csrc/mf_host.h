@@ -109,6 +109,7 @@ public:
     // association
     DevBuf<uint8_t> aflag; DevBuf<uint32_t> abest; DevBuf<float4> meas[3]; DevBuf<uint32_t> slot;
     DevBuf<uint8_t> keep; DevBuf<uint32_t> blockSums, blockSums2, cand, candCount;
+    uint32_t* hCleanStat = nullptr;          // pinned: {first moved sub-block, sub-blocks} of the previous clean (adaptive in-place / copy choice)
     DevBuf<uint32_t> cleanTicket, cleanLoaded; uint32_t cleanEpoch = 0;     // in-place compaction of Model::clean: [0] ticket, [1] first moved sub-block; published epochs
     // tracking
     DevBuf<float4> vmapG[3], nmapG[3], cloud[3];

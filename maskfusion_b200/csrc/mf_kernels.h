@@ -178,7 +178,7 @@ struct CleanWindowImages { const float4* packed; const float4* vertConf; const f
 struct IndexFused { uint64_t* key; uint32_t* idx; float4* vertConf; float4* colorTime; float4* normRad; float4* cleanTex; float maxDepth; };
 // in-place ordered compaction of Model::clean (k_clean_compact): ticket (reset by the sums pass), one published-epoch word per 512-entry
 // sub-block, the first sub-block that holds a removal (written by the scan), the epoch of this call (never 0, changes with every call)
-struct CleanInPlace { uint32_t* ticket; uint32_t* loaded; uint32_t* firstMoved; uint32_t epoch; };
+struct CleanInPlace { uint32_t* ticket; uint32_t* loaded; uint32_t* firstMoved; uint32_t epoch; bool pingPong; };   // firstMoved[0..1]: first moved sub-block, number of sub-blocks; pingPong: copy into `dst` instead (same result)
 void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32_t* count, uint32_t* newCount, uint32_t capacity,
                   const uint8_t* aflag, float4* const* meas, const DevPose* dpose, Cam cam, int W, int H, int time, int timeDelta, float confThreshold,
                   float outlierCoeff, uint8_t maskID, const CleanWindowImages& win,

@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* __restrict__
     __syncthreads();
     uint32_t offs = wtot[warp] + incl - run;
     for (uint32_t i = b0; i < b1; ++i) { const uint32_t v = blockSums[i]; blockSums[i] = offs; offs += v; }
-    if (threadIdx.x == 0 && firstMoved) *firstMoved = sFirst;
+    if (threadIdx.x == 0 && firstMoved) { firstMoved[0] = sFirst; firstMoved[1] = nblk; }      // [1]: read back by the host for its in-place / ping-pong choice
 }
 
 // pass 3: ordered scatter of the survivors (old surfels in buffer order, then new vertices
@@ -1084,7 +1084,7 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
     else k_clean_p2<false><<<persistentBlocks(8), 256, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], P, tinv, texels, depthFilt, mask, keep, cand, candCount);
     prof_mark(s, "k_keep_block_sums"); k_keep_block_sums<<<persistentBlocks(8), 256, 0, s>>>(keep, count, Ppix, blockSums, candCount, inplace ? inplace->ticket : nullptr);
     prof_mark(s, "k_scan_block_sums"); k_scan_block_sums<<<1, 1024, 0, s>>>(blockSums, count, Ppix, capacity, newCount, inplace ? inplace->firstMoved : nullptr);
-    if (inplace) {
+    if (inplace && !inplace->pingPong) {
         prof_mark(s, "k_clean_compact"); k_clean_compact<<<blocks, SCAN_BLOCK, 0, s>>>(src.pos, src.col, src.nrm, count, meas[0], meas[1], meas[2], Ppix, keep, blockSums, capacity,
                                                       inplace->ticket, inplace->loaded, inplace->firstMoved, inplace->epoch);
     } else {

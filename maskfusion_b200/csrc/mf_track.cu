@@ -1084,17 +1084,16 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
             if (tp.rgb) { p.valid = rgbValid[k]; p.d1 = nextDepth[k]; p.ni = nextImage[k]; }
             if (tp.icp) { p.vc = vmapC[k]; p.nc = nmapC[k]; }
         };
-        // Source pixels whose model-side depth is exactly 0 (everything outside an object model's silhouette: 95 % of the image) all warp to
-        // ONE target pixel, the projection of K t alone: d1 * (...) is +-0, so u0 = rn(kt0 / kt2), v0 = rn(kt1 / kt2) whatever (x, y).  Whether
-        // that pixel can give a correspondence is decided once per iteration (zeroCull, below); when it cannot -- always, in practice -- those
-        // pixels skip the two IEEE divisions and the two gathers of the photometric projection.  Exact: same correspondences, same counts.
-        bool zeroCull = false;
+        // (Tried: source pixels whose model-side depth is exactly 0 -- 95 % of an object model's image -- all warp to ONE target pixel, so
+        // whether they can correspond is decidable once per iteration and they could skip the photometric projection.  Exact, but the two
+        // dependent loads of that decision sat on the critical path of every iteration: tracker 390 -> 402 us on the single-model replay,
+        // 8 / 3 objects 308 / 580 -> 304 / 567 frames/s.  Removed.)
         // addresses of both gathers under the current estimate
         auto stage1 = [&](PixA& p, int k, const float3 tprev) {
             p.rOK = false; p.iOK = false; p.jr = 0; p.ji = 0; p.u0 = 0; p.v0 = 0; p.td1 = 0.f;
             p.vg = make_float3(0, 0, 0); p.vcp = p.vg;
             const int y = p.y, x = p.x;
-            if (tp.rgb && p.valid && !isnan(p.d1) && !(zeroCull && p.d1 == 0.f)) {
+            if (tp.rgb && p.valid && !isnan(p.d1)) {
                 const float* K = st->krk; const float* kt = st->kt;
                 const float d1 = p.d1;
                 p.td1 = d1 * ((K[6] * x + K[7] * y) + K[8]) + kt[2];
@@ -1133,20 +1132,6 @@ MF_D void trackBody(const TrackJob* __restrict__ jobs, const TrackParams& tp)
             int cnt = 0, sig = 0;
             if (active) {
                 const float3 tprev = make_float3(st->tprev[0], st->tprev[1], st->tprev[2]);
-                if (tp.rgb) {
-                    const float* kt = st->kt;
-                    const float td0 = 0.f + kt[2];
-                    const float fu = (0.f + kt[0]) / td0, fv = (0.f + kt[1]) / td0;
-                    const int u0 = (fu != fu || fabsf(fu) > 1e9f) ? -1 : __float2int_rn(fu);
-                    const int v0 = (fv != fv || fabsf(fv) > 1e9f) ? -1 : __float2int_rn(fv);
-                    bool can = false;
-                    if (u0 >= 0 && v0 >= 0 && u0 < W && v0 < H) {
-                        const float d0 = lastDepth[v0 * W + u0]; const int li = lastImage[v0 * W + u0];
-                        // |td1 - d0| is evaluated with td1 = +-0 + kt2: the magnitude does not depend on the sign of the zero
-                        can = d0 > 0 && fabsf(td0 - d0) <= tp.maxDepthDelta && li != 0;
-                    }
-                    zeroCull = !can;
-                }
                 // arithmetic of one pixel (same order of accumulation as a one-pixel-at-a-time loop: a before b, rounds ascending)
                 auto stage3 = [&](const PixA& p, int k, int slot) {
                     if (tp.rgb) {
