@@ -161,6 +161,10 @@ int mf_shard_project(mf_context* ctx);                                        /*
 void* mf_shard_projection_keys(mf_context* ctx);                              /* device pointer, width*height uint64 (depth bits << 32 | model index << 26 | surfel) */
 int mf_shard_frame_end(mf_context* ctx, float weight_multiplier);
 int mf_model_owner(mf_context* ctx, int i);                                   /* rank holding model i's surfels */
+/* CTAs of the persistent tracking launch per tracked model (host only): bit j of light_mask marks an object model (validity bitmask, nearly all
+ * pixels culled), the others are full-frame models and get `ratio` times the share.  Model::performTracking of a batch of models (Model.cpp:427-447)
+ * is ONE launch here; this is how its grid is dealt.  n_jobs <= 32. */
+int mf_track_shares(int n_jobs, unsigned light_mask, int total_ctas, int ratio, int* shares);
 int mf_shard_pick_owner(const int64_t* loads, int world);                     /* placement rule for a new model: least owned capacity, ties -> highest rank (host only) */
 
 /* in-stream CUDA-event stage timer (replaces the reference's TICK/TOCK Stopwatch, Core/Utils/Stopwatch.h:46-54) */

@@ -442,6 +442,12 @@ extern "C" int mf_shard_project(mf_context* ctx) { MF_TRY MF_NEED(ctx) ctx->mf->
 extern "C" void* mf_shard_projection_keys(mf_context* ctx) { if (!ctx || !ctx->mf) return nullptr; return ctx->mf->projKeys.p; }
 extern "C" int mf_shard_frame_end(mf_context* ctx, float weight_multiplier) { MF_TRY MF_NEED(ctx) ctx->mf->frameEnd(weight_multiplier); return 0; MF_CATCH(-1) }
 extern "C" int mf_model_owner(mf_context* ctx, int i) { MF_NEED(ctx) MF_MODEL(ctx, i) return m->ownerRank; }
+extern "C" int mf_track_shares(int n_jobs, unsigned light_mask, int total_ctas, int ratio, int* shares)
+{
+    if (!shares || n_jobs < 1 || n_jobs > TRACK_MAX_JOBS || total_ctas < n_jobs) return -1;
+    track_shares(n_jobs, light_mask, total_ctas, ratio, shares);
+    return 0;
+}
 extern "C" int mf_shard_pick_owner(const int64_t* loads, int world) { if (!loads || world < 1 || world > 64) return -1; return MaskFusion::pickOwner(loads, world); }
 
 extern "C" int mf_model_class_id(mf_context* ctx, int i) { MF_NEED(ctx) MF_MODEL(ctx, i) return m->classID; }

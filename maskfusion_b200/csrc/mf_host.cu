@@ -312,7 +312,7 @@ void Model::combinedPredict(float depthCutoff, int time, int maxTime, int timeDe
     MaskFusion* o = owner;
     launch_combined_predict(current(), dCount(), dpose, o->cam, o->W, o->H, depthCutoff, confidenceThreshold, time, maxTime,
                             timeDelta, o->rayTab, key, splatImage, splatVertex, splatNormal, splatTime, fillIn ? 1 : 0, o->depthFilt, o->rgb, 0,
-                            o->cfg.frameToFrameRGB ? 1 : 0, fillImage, fillVertex, fillNormal, fillIn ? nonBlack.p : nullptr, o->stream);
+                            o->cfg.frameToFrameRGB ? 1 : 0, fillImage, fillVertex, fillNormal, fillIn ? nonBlack.p : nullptr, o->stream, capacity);
     o->launches += 2;
 }
 
@@ -593,7 +593,7 @@ void MaskFusion::projectLocal()
         Model* m = models[i].get();
         if (!m->owned) continue;
         launch_splat_project_only(m->current(), m->dCount(), m->dpose, cam, W, H, cfg.depthCutoff, 12.0f /* :61 */, tick, tick,
-                                  cfg.timeDelta, (uint32_t)i << 26, rayTab, projKeys, stream);
+                                  cfg.timeDelta, (uint32_t)i << 26, rayTab, projKeys, stream, m->capacity);
         launches += 1;
     }
 }

@@ -187,7 +187,7 @@ void launch_clean(const SurfelPlanes& src, const SurfelPlanes& dst, const uint32
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth,
                              float confThreshold, int time, int maxTime, int timeDelta, const float4* rayTab, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
-                             uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s);
+                             uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s, uint32_t capacity = 0);
 void launch_ray_table(Cam cam, int W, int H, float4* tab, cudaStream_t s);      // pixel-centre viewing rays (combo_splat.frag:39-45), once per context
 void launch_init_model(const uchar4* rgb, const float* depthRaw, const float* depthFilt, Cam cam, int W, int H, int time, float maxDepth,
                        uint8_t* fr, uint8_t* ff, uint32_t* sumR, uint32_t* sumF, uint32_t capacity, const SurfelPlanes& sp, uint32_t* count,
@@ -196,6 +196,7 @@ void launch_planes_to_aos(const SurfelPlanes& sp, uint32_t n, float4* out, cudaS
 void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, cudaStream_t s);
 
 // ---- mf_track.cu ----
+void track_shares(int nJobs, unsigned lightMask, int totalCTAs, int ratio, int* G);   // CTAs per model of the persistent tracking grid
 int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
                     bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s, unsigned lightMask = false);
 int debug_track_timing(long long* out, int cap);
@@ -230,5 +231,5 @@ void launch_seg_final(const uint8_t* seg, const int* lab, const int* mapToMask, 
 void launch_apply_ignore(const uint8_t* mask, const uint8_t* isPerson, const FrameHdr* hdr, int P, uint8_t* ignore, uint8_t* edges, cudaStream_t s);
 void launch_proj_resolve(uint64_t* key, int P, const uint8_t* indexToId, uint8_t* out, cudaStream_t s);
 void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* dpose, Cam cam, int W, int H, float maxDepth, float confThreshold,
-                               int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s);
+                               int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s, uint32_t capacity = 0);
 }  // namespace mfb

@@ -790,7 +790,9 @@ __global__ void __launch_bounds__(SPLAT_BS, SPLAT_MIN_BLOCKS) k_splat_project(co
         }
         if (threadIdx.x == 0) offs[nent] = total;
         __syncthreads();
-        for (int u = threadIdx.x; u < total; u += blockDim.x) {
+        // gridDim.y > 1 (small stores): the blocks of a column redo the (cheap) vertex stage of the same 128 surfels and share their units --
+        // an object model has ~50 blocks' worth of surfels, and the units of a few large sprites kept one SM busy for 40 us while 100 idled
+        for (int u = threadIdx.x + blockIdx.y * blockDim.x; u < total; u += blockDim.x * gridDim.y) {
             int lo = 0, hi = nent - 1;                       // last entry with offs[e] <= u
             while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (offs[mid] <= u) lo = mid; else hi = mid - 1; }
             const Entry e = ent[lo];
@@ -1099,12 +1101,21 @@ void launch_ray_table(Cam cam, int W, int H, float4* tab, cudaStream_t s)
     k_ray_table<<<g, b, 0, s>>>(cam, W, H, tab);
 }
 
+// grid of the splat rasteriser: a persistent grid for large stores; for a small store (an object model: a few thousand surfels) one column
+// of blocks per 128 surfels of CAPACITY is cheap to over-provision, and 8 blocks share the units of each column (gridDim.y)
+static dim3 splatGrid(uint32_t capacity)
+{
+    const int persistent = persistentBlocks(8 * 256 / SPLAT_BS);
+    if (capacity == 0 || capacity >= (1u << 20)) return dim3(persistent);
+    const int cols = (int)std::min<uint32_t>((capacity + SPLAT_BS - 1) / SPLAT_BS, (uint32_t)persistent);
+    return dim3(cols, 8);
+}
 void launch_combined_predict(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth,
                              float confThreshold, int time, int maxTime, int timeDelta, const float4* rayTab, uint64_t* key, uchar4* image, float4* vertexConf,
                              float4* normalRad, uint16_t* timeTex, int doFill, const float* depthFilt, const uchar4* rgb, int ptVN, int ptImg,
-                             uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s)
+                             uchar4* fillImage, float4* fillVertex, float4* fillNormal, uint32_t* nonBlackSamples, cudaStream_t s, uint32_t capacity)
 {
-    prof_mark(s, "k_splat_project"); k_splat_project<<<persistentBlocks(8 * 256 / SPLAT_BS), SPLAT_BS, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
+    prof_mark(s, "k_splat_project"); k_splat_project<<<splatGrid(capacity), SPLAT_BS, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
                                                         (float)maxTime, (float)timeDelta, 0u, rayTab, (unsigned long long*)key);
     if (nonBlackSamples) cudaMemsetAsync(nonBlackSamples, 0, sizeof(uint32_t), s);
     dim3 b(32, 8), g((W + 31) / 32, (H + 7) / 8);
@@ -1133,10 +1144,10 @@ void launch_aos_to_planes(const float4* in, uint32_t n, const SurfelPlanes& sp, 
 namespace mfb {
 // splat projection into a caller-owned key image (GlobalProjection: all models share one key image)
 void launch_splat_project_only(const SurfelPlanes& sp, const uint32_t* count, const DevPose* tinv, Cam cam, int W, int H, float maxDepth, float confThreshold,
-                               int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s)
+                               int time, int maxTime, int timeDelta, uint32_t drawBase, const float4* rayTab, uint64_t* key, cudaStream_t s, uint32_t capacity)
 {
     prof_mark(s, "k_splat_project_ids");
-    k_splat_project<<<persistentBlocks(8 * 256 / SPLAT_BS), SPLAT_BS, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
+    k_splat_project<<<splatGrid(capacity), SPLAT_BS, 0, s>>>(sp.pos, sp.col, sp.nrm, count, tinv, cam, W, H, maxDepth, confThreshold, (float)time,
                                                         (float)maxTime, (float)timeDelta, drawBase, rayTab, (unsigned long long*)key);
 }
 }  // namespace mfb

@@ -1343,6 +1343,28 @@ static int trackBlocks(int N, int numSMs)
     return need < cap ? need : cap;
 }
 
+// CTAs of the persistent tracking grid per model (host logic, exported as mf_track_shares for the CPU tests).  A light model (bit set in
+// lightMask: an object model with a validity bitmask) gets one share, a heavy one (full-frame maps) `ratio` shares; measured, frames/s of the
+// 8-object / 3-object scenes: equal shares 251 / 474; ratio 2: 307 / 576; ratio 3: 297 / 557; ratio 5: 297 / 516.  Without both kinds in the
+// batch, or when the grid is too small for 4 CTAs per light model, the shares are equal.
+void track_shares(int nJobs, unsigned lightMask, int totalCTAs, int ratio, int* G)
+{
+    if (nJobs < 1) return;
+    int Geq = totalCTAs / nJobs;
+    if (Geq > TRACK_MAX_BLOCKS / 2) Geq = TRACK_MAX_BLOCKS / 2;
+    int nLight = 0;
+    for (int j = 0; j < nJobs; ++j) nLight += (lightMask >> j) & 1u;
+    const int nHeavy = nJobs - nLight;
+    int Gheavy = Geq, Glight = Geq;
+    if (nLight > 0 && nHeavy > 0) {
+        Glight = std::max(4, totalCTAs / (nLight + std::max(1, ratio) * nHeavy));
+        Gheavy = (totalCTAs - nLight * Glight) / nHeavy;
+        if (Gheavy < Glight) { Gheavy = Geq; Glight = Geq; }
+        if (Gheavy > TRACK_MAX_BLOCKS / 2) Gheavy = TRACK_MAX_BLOCKS / 2;
+    }
+    for (int j = 0; j < nJobs; ++j) G[j] = ((lightMask >> j) & 1u) ? Glight : Gheavy;
+}
+
 int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgbOnly, float icpWeight,
                     bool pyramid, bool fastOdom, bool so3, int numSMs, unsigned* bars, cudaStream_t s, unsigned lightMask)
 {
@@ -1406,22 +1428,13 @@ int launch_tracking(TrackJob* d_jobs, int nJobs, int W, int H, Cam cam, bool rgb
     static int sharesOn = -1;       // MFB200_TRACK_SHARES=0: equal shares (A/B)
     if (sharesOn < 0) { const char* e = getenv("MFB200_TRACK_SHARES"); sharesOn = e ? (e[0] != '0') : 1; }
     int Gof[TRACK_MAX_JOBS];
-    int nLight = 0;
-    for (int j = 0; j < nJobs; ++j) nLight += (lightMask >> j) & 1u;
-    const int nHeavy = nJobs - nLight, totalCTAs = std::min(numSMs, coResident);
-    int Gheavy = G, Glight = G;
-    if (sharesOn && nLight > 0 && nHeavy > 0) {
-        // a heavy model gets `ratio` times the CTAs of a light one (measured, frames/s of the 8-object / 3-object scenes: equal shares
-        // 251 / 474; ratio 2: 307 / 576; ratio 3: 297 / 557; ratio 5: 297 / 516; a first 84 / 8 x 8 split: 270, 100 / 3 x 16: 450)
-        static int ratio = -1;      // MFB200_TRACK_HEAVY_RATIO (A/B)
-        if (ratio < 0) { const char* e = getenv("MFB200_TRACK_HEAVY_RATIO"); ratio = e ? std::max(1, atoi(e)) : 2; }
-        Glight = std::max(4, totalCTAs / (nLight + ratio * nHeavy));
-        Gheavy = (totalCTAs - nLight * Glight) / nHeavy;
-        if (Gheavy < Glight) { Gheavy = G; Glight = G; }
-        if (Gheavy > TRACK_MAX_BLOCKS / 2) Gheavy = TRACK_MAX_BLOCKS / 2;
-    }
+    static int ratio = -1;          // MFB200_TRACK_HEAVY_RATIO (A/B)
+    if (ratio < 0) { const char* e = getenv("MFB200_TRACK_HEAVY_RATIO"); ratio = e ? std::max(1, atoi(e)) : 2; }
+    track_shares(nJobs, sharesOn ? lightMask : 0u, std::min(numSMs, coResident), ratio, Gof);
+    int Gheavy = 0;                  // the largest share (sizes the shared-memory correspondences)
+    for (int j = 0; j < nJobs; ++j) Gheavy = std::max(Gheavy, Gof[j]);
     tp.nJobs = nJobs; tp.jobStart[0] = 0;
-    for (int j = 0; j < nJobs; ++j) { Gof[j] = ((lightMask >> j) & 1u) ? Glight : Gheavy; tp.jobStart[j + 1] = (unsigned short)(tp.jobStart[j] + Gof[j]); }
+    for (int j = 0; j < nJobs; ++j) tp.jobStart[j + 1] = (unsigned short)(tp.jobStart[j] + Gof[j]);
     const int gridCTAs = tp.jobStart[nJobs];
     int launches = 0;
     const TrackJob* jp = d_jobs;

@@ -480,3 +480,31 @@ def test_warp_ldlt_scheme_is_bit_identical_to_the_sequential_routine(oracle):
             xo = np.zeros(n)
             L.orc_ldlt_solve(A.ctypes.data, b.ctypes.data, n, xo.ctypes.data)
             assert np.array_equal(xo.view(np.uint64), warp(A, b).view(np.uint64)), trial
+
+
+def test_track_shares_host_logic():
+    """grid shares of the persistent tracking launch (mf_track_shares): every CTA is dealt at most once, light models >= 4 CTAs, a heavy
+    model gets ~ratio times a light one, equal shares without both kinds in the batch"""
+    import ctypes as C
+    import maskfusion_b200 as mfb
+    L = mfb.load_library()
+    L.mf_track_shares.argtypes = [C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_int)]
+
+    def shares(n, mask, total=148, ratio=2):
+        out = (C.c_int * 32)()
+        assert L.mf_track_shares(n, mask, total, ratio, out) == 0
+        return list(out[:n])
+    assert shares(1, 0) == [148]
+    assert shares(3, 0) == [49, 49, 49] and shares(3, 0b111) == [49, 49, 49]           # one kind only: equal
+    s9 = shares(9, 0b111111110)                                                     # background + 8 objects
+    assert s9[0] == 148 - 8 * s9[1] and all(x == s9[1] for x in s9[1:]) and s9[1] == 148 // 10 and sum(s9) <= 148
+    s4 = shares(4, 0b1110)
+    assert s4 == [148 - 3 * 29, 29, 29, 29]
+    s17 = shares(17, 0x1fffe)                                                       # configs[4]: 16 objects + background
+    assert min(s17) >= 4 and sum(s17) <= 148 and s17[0] > s17[1]
+    for n in range(1, 33):
+        for mask in (0, 1, (1 << n) - 2, 0x55555555 & ((1 << n) - 1)):
+            for total in (132, 148, 160):
+                s = shares(n, mask, total)
+                assert min(s) >= 1 and sum(s) <= total, (n, mask, total, s)
+    assert L.mf_track_shares(0, 0, 148, 2, (C.c_int * 32)()) != 0 and L.mf_track_shares(33, 0, 148, 2, (C.c_int * 32)()) != 0
