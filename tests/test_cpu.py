@@ -508,3 +508,67 @@ def test_track_shares_host_logic():
                 s = shares(n, mask, total)
                 assert min(s) >= 1 and sum(s) <= total, (n, mask, total, s)
     assert L.mf_track_shares(0, 0, 148, 2, (C.c_int * 32)()) != 0 and L.mf_track_shares(33, 0, 148, 2, (C.c_int * 32)()) != 0
+
+
+def test_inplace_compaction_scheme_model():
+    """Model of k_clean_compact's hand-over under random schedules: sub-blocks of B entries are taken in ticket order by a few
+    resident workers; a sub-block loads its survivors, publishes `loaded`, and may store once the lower sub-blocks whose SOURCE range its
+    destination range overlaps have published.  Checked: no store ever lands on a source entry that has not been loaded yet, nobody waits on
+    a higher ticket (no deadlock), and the array ends as the ordered compaction."""
+    rng = np.random.default_rng(3)
+    B = 8
+    for trial in range(300):
+        n = int(rng.integers(1, 200))
+        keep = rng.random(n) < rng.choice([0.02, 0.5, 0.9, 0.99, 1.0])
+        if trial % 7 == 0:
+            keep[: int(rng.integers(0, n + 1))] = True                     # removals only in the tail (the steady state)
+        data = np.arange(n) + 1000
+        store = data.copy()
+        nblk = (n + B - 1) // B
+        sums = np.array([keep[b * B:(b + 1) * B].sum() for b in range(nblk)])
+        offs = np.concatenate([[0], np.cumsum(sums)[:-1]])
+        full = np.array([min(B, n - b * B) for b in range(nblk)])
+        first = next((b for b in range(nblk) if sums[b] != B), nblk)        # k_scan_block_sums: first sub-block with a removal (or a partial one)
+        assert all(sums[b] == full[b] == B for b in range(first))           # everything before it stays in place
+        loaded_src = np.zeros(n, bool)                                      # source entries whose value sits in some worker's registers
+        loaded_src[: first * B] = True                                      # never touched: nobody writes there (checked below)
+        published = np.zeros(nblk, bool)
+        regs = {}
+        next_ticket, workers, done = first, [None] * int(rng.integers(1, 5)), 0
+        guard = 0
+        while done < nblk - first:
+            guard += 1
+            assert guard < 100000, "schedule does not terminate"
+            w = int(rng.integers(0, len(workers)))
+            st = workers[w]
+            if st is None:
+                if next_ticket < nblk:
+                    workers[w] = ["load", next_ticket]; next_ticket += 1
+                continue
+            phase, b = st
+            lo, hi = b * B, min((b + 1) * B, n)
+            if phase == "load":
+                idx = [e for e in range(lo, hi) if keep[e]]
+                regs[b] = [(e, store[e]) for e in idx]
+                for e in idx:
+                    assert store[e] == data[e], "a survivor was overwritten before its sub-block loaded it"
+                loaded_src[lo:hi] = True
+                published[b] = True
+                st[0] = "store"
+            else:
+                if sums[b]:
+                    s0, s1 = offs[b] // B, (offs[b] + sums[b] - 1) // B
+                    deps = [s for s in range(s0, s1 + 1) if s < b]
+                    assert all(s >= first for s in deps)
+                    if not all(published[s] for s in deps):
+                        assert all(s < b for s in deps)                      # waits only point to lower tickets
+                        continue
+                for k, (e, v) in enumerate(regs.pop(b)):
+                    d = offs[b] + k
+                    assert d <= e
+                    if d != e:
+                        assert loaded_src[d], "store onto a source entry that has not been loaded"
+                        store[d] = v
+                workers[w] = None; done += 1
+        m = int(keep.sum())
+        assert np.array_equal(store[:m], data[keep]), (trial, n)
