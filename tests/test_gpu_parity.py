@@ -52,7 +52,7 @@ def make_pair(**kw):
     return SynthScene(W, H, n_objects=0, seed=0), OracleStages(ocfg), mfb.MaskFusion(ccfg)
 
 
-def run_stagewise(name, nframes, **kw):
+def run_stagewise(name, nframes, clean_conf=None, **kw):
     sc, orc, mf = make_pair(**kw)
     rep = Report(name)
     gm = mf.getBackgroundModel()
@@ -129,6 +129,10 @@ def run_stagewise(name, nframes, **kw):
                 rep.exact(f"[{t}] fused surfels", sm, so)
             orc.predict_indices(); gm.predictIndices(tick)
             rep.exact(f"[{t}] index map ids (2)", gm.indexMap()[0], orc.p.tex(0, "idx"))
+            if clean_conf is not None:
+                # Model::clean called with another confidence threshold than the index map was resolved with: the packed window texels
+                # (whose sign bits carry `conf > threshold`) are not valid for this call, the window reads the index-map images instead
+                orc.mptr(0).contents.confThreshold = clean_conf; gm.setConfidenceThreshold(clean_conf)
             orc.clean(); gm.clean(tick)
             so, sm = orc.p.surfels(0), gm.downloadMap()
             rep.check(f"[{t}] clean count", so.shape[0] == sm.shape[0], f"{so.shape[0]} vs {sm.shape[0]}")
@@ -157,6 +161,12 @@ def run_stagewise(name, nframes, **kw):
 def test_stagewise_icp_only():
     """-static, ICP-only tracking (icpWeight=100 => rgb=false, RGBDOdometry.cpp:236-237), no SO3"""
     run_stagewise("stagewise_icp", 6, icpWeight=100.0, so3=0)
+
+
+def test_stagewise_clean_with_other_threshold():
+    """the fallback of the clean window (three index-map images instead of the packed 16-byte texels): confidence threshold changed between
+    Model::predictIndices and Model::clean"""
+    run_stagewise("stagewise_clean_conf", 4, clean_conf=3.0, icpWeight=100.0, so3=0)
 
 
 def test_stagewise_rgbd():
