@@ -221,6 +221,16 @@ int mf_export_poses(mf_context* ctx, const char* export_dir);
  * binary little endian, x y z | r g b | -nx -ny -nz | radius.  surfels = n x 12 floats as mf_download_surfels returns them. */
 int mf_write_ply(const char* path, const float* surfels, int n, float conf_threshold);
 
+/* PreSegmentation::performSegmentation (Core/Segmentation/PreSegmentation.cpp:28-90, the "precomputed masks" performer; host code in the
+ * reference too): mask values -> model ids through the persistent table `mapping` (256 bytes, zero-initialised by the caller before the first
+ * frame; the reference's function-static vector), the first unseen value in raster order becomes next_model_id when allow_new.  Outputs: the full
+ * segmentation (W*H), has_new_label, and per model in list order (the new one last) superPixelCount, depthMean, depthStd (mean absolute deviation),
+ * the inputs of Model::setMaxDepth (MaskFusion.cpp:291,337-341).  model_ids: ids of the live models, background first.  Returns the number of
+ * entries written.  Not wired into the device-driven schedule (its statistics are sequential float sums in raster order). */
+int mf_pre_segmentation(const uint8_t* mask, const float* depth, int W, int H, const uint8_t* model_ids, int n_models, int next_model_id,
+                        int allow_new, uint8_t* mapping, uint8_t* full_segmentation, int* has_new_label, uint32_t* super_pixel_count,
+                        float* depth_mean, float* depth_std);
+
 /* Mask R-CNN post-processing (Core/Segmentation/MaskRCNN/helpers.py:70-98 generate_id_image): detections (masks HxWxN u8, N fastest;
  * scores; class ids; rois N x 4) -> id image HxW (ids 1..n in export order, later detections overwrite earlier ones), exported class ids
  * and rois.  class_filter / special_assignments may be NULL with count 0.  Returns the number of exported detections. */

@@ -50,7 +50,7 @@ EXPORTS = [
     "mf_download_prediction", "mf_download_fill_in", "mf_download_association", "mf_download_track_stats",
     "mf_download_edge_map", "mf_morph_close", "mf_debug_track_timing", "mf_attach_backbone", "mf_backbone_stream", "mf_icp_step", "mf_debug_set_poses", "mf_set_profiling", "mf_get_stage_times", "mf_set_frame_classes", "mf_download_segmentation", "mf_model_class_id", "mf_klg_open", "mf_klg_num_frames", "mf_klg_has_more", "mf_klg_get_next",
     "mf_klg_close", "mf_klg_write", "mf_dir_open", "mf_dir_num_frames", "mf_dir_has_more", "mf_dir_has_masks", "mf_dir_set_max_masks", "mf_dir_size",
-    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_decode_exr_depth", "mf_export_poses", "mf_generate_id_image", "mf_write_ply", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
+    "mf_dir_get_next", "mf_dir_close", "mf_decode_jpeg", "mf_decode_exr_depth", "mf_export_poses", "mf_generate_id_image", "mf_pre_segmentation", "mf_write_ply", "mf_cnn_last_error", "mf_gemm_bf16", "mf_conv3x3_bf16", "mf_backbone_create", "mf_backbone_destroy", "mf_backbone_num_layers",
     "mf_backbone_layer", "mf_backbone_get_weights", "mf_backbone_mold", "mf_backbone_input_buffer", "mf_backbone_forward", "mf_backbone_output",
     "mf_backbone_flops", "mf_backbone_num_gemms", "mf_backbone_download",
     "mf_shard_configure", "mf_shard_unique_id", "mf_shard_comm_init", "mf_shard_process_frame", "mf_shard_stats", "mf_shard_frame_begin", "mf_shard_get_poses", "mf_shard_set_poses", "mf_shard_project",
@@ -483,6 +483,25 @@ def generate_id_image(result: dict, min_score: float, class_filter=(), special_a
     if n < 0:
         raise MFError(L.mf_last_error().decode())
     return img, ec[:n].tolist(), er[:n].tolist()
+
+
+def pre_segmentation(mask: np.ndarray, depth: np.ndarray, model_ids, next_model_id: int, allow_new: bool, mapping: np.ndarray):
+    """PreSegmentation::performSegmentation (PreSegmentation.cpp:28-90).  mapping: uint8[256], updated in place (state across frames).
+    -> (fullSegmentation HxW u8, hasNewLabel, superPixelCount, depthMean, depthStd) with one entry per model (+1 with a new label)"""
+    L = load_library()
+    m = np.ascontiguousarray(mask, np.uint8); d = np.ascontiguousarray(depth, np.float32)
+    H, W = m.shape
+    ids = np.ascontiguousarray(model_ids, np.uint8)
+    assert mapping.dtype == np.uint8 and mapping.size == 256 and mapping.flags["C_CONTIGUOUS"]
+    seg = np.zeros((H, W), np.uint8); has_new = C.c_int(0)
+    spc = np.zeros(len(ids) + 1, np.uint32); mean = np.zeros(len(ids) + 1, np.float32); std = np.zeros(len(ids) + 1, np.float32)
+    L.mf_pre_segmentation.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.mf_pre_segmentation(_p(m), _p(d), W, H, _p(ids), len(ids), int(next_model_id), int(bool(allow_new)), _p(mapping), _p(seg), C.byref(has_new),
+                              _p(spc), _p(mean), _p(std))
+    if n < 0:
+        raise MFError(L.mf_last_error().decode())
+    return seg, bool(has_new.value), spc[:n].copy(), mean[:n].copy(), std[:n].copy()
 
 
 def decode_exr_depth(buf: bytes) -> np.ndarray:

@@ -18,6 +18,7 @@
 #include <sys/stat.h>
 #include <zlib.h>
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -488,6 +489,51 @@ extern "C" int mf_dir_get_next(mf_dir* r, uint8_t* rgb, float* depth, uint8_t* m
 // Detections are written in order: a later detection overwrites an earlier one where they overlap; ids are 1..n in export order
 // unless `special_assignments` maps the class (a list indexed BY CLASS ID, used when the class id occurs IN the list, helpers.py:91-92).
 // Returns the number of exported detections, < 0 on error.  Pinned against the reference's own Python function (tests/test_cpu_loader.py).
+// PreSegmentation::performSegmentation (Core/Segmentation/PreSegmentation.cpp:28-90): the "-segMethod precomputed" performer -- host code in the
+// reference as well.  The input mask's values are mapped to model ids through a table that persists over the frames (`mapping`, the function's
+// static vector in the reference): a value seen before keeps its model; the FIRST unseen value met in raster order takes `next_model_id` when
+// new models are allowed (and every later pixel of that value follows it); other unseen values stay background for this frame.  Per model (in
+// list order, the new one last): superPixelCount = pixels / 256 (integer; the new model: at least 1), then the mean depth and the mean absolute
+// deviation of the depth over the pixels assigned to it, accumulated in float in raster order exactly as the reference does (these feed
+// Model::setMaxDepth, MaskFusion.cpp:291,337-341).  Returns the number of model entries written (n_models, + 1 with a new label), < 0 on error.
+extern "C" int mf_pre_segmentation(const uint8_t* mask, const float* depth, int W, int H, const uint8_t* model_ids, int n_models, int next_model_id,
+                                   int allow_new, uint8_t* mapping, uint8_t* full_segmentation, int* has_new_label, uint32_t* super_pixel_count,
+                                   float* depth_mean, float* depth_std)
+{
+    if (!mask || !depth || !model_ids || !mapping || !full_segmentation || !super_pixel_count || !depth_mean || !depth_std || W <= 0 || H <= 0 ||
+        n_models < 1 || n_models > 255 || next_model_id < 0 || next_model_id > 255) { mf_set_error("mf_pre_segmentation: bad arguments"); return -1; }
+    try {
+        const size_t P = (size_t)W * H;
+        unsigned char modelIdToIndex[256];
+        memset(modelIdToIndex, 0, sizeof modelIdToIndex);                 // (uninitialised in the reference; ids outside the list never occur in its output)
+        for (int i = 0; i < n_models; ++i) modelIdToIndex[model_ids[i]] = (unsigned char)i;
+        modelIdToIndex[next_model_id] = (unsigned char)n_models;
+        std::vector<unsigned> outIds(256, 0);
+        bool hasNew = false;
+        for (size_t i = 0; i < P; ++i) {
+            const unsigned char vIn = mask[i];
+            unsigned char vOut = 0;
+            if (vIn) {
+                if (mapping[vIn] != 0) { vOut = mapping[vIn]; outIds[vOut]++; }
+                else if (allow_new && !hasNew) { vOut = (unsigned char)next_model_id; mapping[vIn] = vOut; hasNew = true; outIds[vOut]++; }
+            } else outIds[0]++;
+            full_segmentation[i] = vOut;
+        }
+        const int n = n_models + (hasNew ? 1 : 0);
+        for (int i = 0; i < n_models; ++i) super_pixel_count[i] = outIds[model_ids[i]] / (16 * 16);
+        if (hasNew) { const float c = (float)(outIds[next_model_id] / (16 * 16)); super_pixel_count[n_models] = (unsigned)(c > 1.0f ? c : 1.0f); }
+        std::vector<unsigned> cnts(n, 0);
+        for (int i = 0; i < n; ++i) { depth_mean[i] = 0.f; depth_std[i] = 0.f; }
+        for (size_t i = 0; i < P; ++i) { const size_t k = modelIdToIndex[full_segmentation[i]]; if ((int)k < n) { depth_mean[k] += depth[i]; cnts[k]++; } }
+        for (int i = 0; i < n; ++i) depth_mean[i] /= cnts[i] ? cnts[i] : 1;
+        for (size_t i = 0; i < P; ++i) { const size_t k = modelIdToIndex[full_segmentation[i]]; if ((int)k < n) depth_std[k] += std::abs(depth_mean[k] - depth[i]); }
+        for (int i = 0; i < n; ++i) depth_std[i] /= cnts[i] ? cnts[i] : 1;
+        if (has_new_label) *has_new_label = hasNew ? 1 : 0;
+        return n;
+    } catch (const std::exception& e) { mf_set_error(std::string("mf_pre_segmentation: ") + e.what()); return -2; }
+    catch (...) { mf_set_error("mf_pre_segmentation: unknown error"); return -2; }
+}
+
 extern "C" int mf_generate_id_image(const uint8_t* masks, int H, int W, int N, const float* scores, const int32_t* class_ids, const int32_t* rois,
                                     double min_score, const int32_t* class_filter, int n_filter, const int32_t* special_assignments, int n_special,
                                     uint8_t* id_image, int32_t* exported_class_ids, int32_t* exported_rois)

@@ -428,3 +428,68 @@ def test_exr_depth_decoder_matches_opencv_golden(tmp_path):
     fr = rd.getNext()
     assert np.array_equal(np.asarray(fr[1]).view(np.uint32), ref.view(np.uint32))
     rd.close()
+
+
+def _preseg_python(mask, depth, model_ids, next_id, allow_new, mapping):
+    """literal restatement of PreSegmentation::performSegmentation (Core/Segmentation/PreSegmentation.cpp:28-90) with float32 running sums"""
+    H, W = mask.shape
+    m, d = mask.reshape(-1), depth.reshape(-1).astype(np.float32)
+    seg = np.zeros(H * W, np.uint8)
+    idx = {int(v): i for i, v in enumerate(model_ids)}
+    idx[int(next_id)] = len(model_ids)
+    out_ids = [0] * 256
+    has_new = False
+    for i in range(H * W):
+        v = int(m[i])
+        if v:
+            if mapping[v] != 0:
+                seg[i] = mapping[v]; out_ids[seg[i]] += 1
+            elif allow_new and not has_new:
+                seg[i] = next_id; mapping[v] = next_id; has_new = True; out_ids[next_id] += 1
+        else:
+            out_ids[0] += 1
+    n = len(model_ids) + (1 if has_new else 0)
+    spc = [out_ids[int(v)] // 256 for v in model_ids]
+    if has_new:
+        spc.append(int(max(np.float32(out_ids[next_id] // 256), np.float32(1.0))))
+    mean = [np.float32(0)] * n; std = [np.float32(0)] * n; cnt = [0] * n
+    for i in range(H * W):
+        k = idx.get(int(seg[i]), 0)
+        if k < n:
+            mean[k] = np.float32(mean[k] + d[i]); cnt[k] += 1
+    mean = [np.float32(mean[k] / np.float32(cnt[k] if cnt[k] else 1)) for k in range(n)]
+    for i in range(H * W):
+        k = idx.get(int(seg[i]), 0)
+        if k < n:
+            std[k] = np.float32(std[k] + np.float32(abs(np.float32(mean[k] - d[i]))))
+    std = [np.float32(std[k] / np.float32(cnt[k] if cnt[k] else 1)) for k in range(n)]
+    return seg.reshape(H, W), has_new, np.array(spc, np.uint32), np.array(mean, np.float32), np.array(std, np.float32)
+
+
+def test_pre_segmentation_matches_restatement():
+    """mf_pre_segmentation (the reference's precomputed-masks performer, host code) against a literal Python restatement over a short replay: the
+    persistent mapping table, one new label per frame in raster order, superpixel counts, float32 running depth statistics -- bit for bit"""
+    from maskfusion_b200.api import pre_segmentation
+    rng = np.random.default_rng(9)
+    H, W = 48, 64
+    map_c = np.zeros(256, np.uint8); map_p = np.zeros(256, np.uint8)
+    model_ids = [0]
+    next_id = 1
+    labels = [17, 40, 3, 200]
+    for t in range(7):
+        mask = np.zeros((H, W), np.uint8)
+        for j, lab in enumerate(labels[: 1 + t // 2 + 1]):
+            y0, x0 = 4 + 9 * j + t, 6 + 13 * j
+            mask[y0:y0 + 12, x0:x0 + 14] = lab
+        depth = (1.0 + rng.random((H, W)) * 2).astype(np.float32)
+        depth[rng.random((H, W)) < 0.05] = 0.0
+        allow = t != 3                                        # one frame in which new models are not allowed
+        seg_c, new_c, spc_c, mean_c, std_c = pre_segmentation(mask, depth, model_ids, next_id, allow, map_c)
+        seg_p, new_p, spc_p, mean_p, std_p = _preseg_python(mask, depth, model_ids, next_id, allow, map_p)
+        assert np.array_equal(seg_c, seg_p) and new_c == new_p, t
+        assert np.array_equal(map_c, map_p)
+        assert np.array_equal(spc_c, spc_p), (t, spc_c, spc_p)
+        assert np.array_equal(mean_c.view(np.uint32), mean_p.view(np.uint32)) and np.array_equal(std_c.view(np.uint32), std_p.view(np.uint32)), t
+        if new_c:
+            model_ids.append(next_id); next_id += 1
+    assert len(model_ids) >= 4 and map_c[17] == 1 and map_c[40] == 2
