@@ -414,6 +414,20 @@ def test_exr_depth_decoder_matches_opencv_golden(tmp_path):
     for bad in (b"", b"abcd" * 8, g["exr0"].tobytes()[:60], g["exr3"].tobytes()[:-9]):
         with pytest.raises(MFError):
             decode_exr_depth(bad)
+    # corrupted streams either decode to something or are refused with a message -- never a crash (the entry point is behind the C ABI)
+    rng = np.random.default_rng(0)
+    for k in range(0, n, 3):
+        b = bytearray(g[f"exr{k}"].tobytes())
+        for _ in range(25):
+            c = bytearray(b)
+            for _ in range(int(rng.integers(1, 6))):
+                c[int(rng.integers(0, len(c)))] = int(rng.integers(0, 256))
+            if rng.random() < 0.2:
+                c = c[: int(rng.integers(1, len(c)))]
+            try:
+                decode_exr_depth(bytes(c))
+            except MFError:
+                pass
     # a two-frame image directory with EXR depth
     ref = g["exr0_depth"]
     H, W = ref.shape
