@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Per-source-line totals of one ncu capture (needs -lineinfo and --import-source on):
-usage: python scripts/ncu_source_lines.py gpurun_out/prof_X.ncu-rep [top_n]"""
+usage: python scripts/ncu_source_lines.py gpurun_out/prof_X.ncu-rep [top_n] [kernel regex (multi-kernel captures)]"""
 import csv, io, subprocess, sys
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kern = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"] + kern, capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 cur, hdr, lines = None, None, []
 for r in rows:
